@@ -1,0 +1,95 @@
+"""ctypes binding of libheatnet_b200.so (the C ABI declared in include/heatnet_b200.h).
+
+There is no CPU fallback: importing this module without the built library, or calling into it without an
+sm_100 device, raises.  Build with `python -c "import __graft_entry__ as g; g.build()"` (nvcc, sm_100a).
+"""
+import ctypes as C
+import os
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_DIR, "libheatnet_b200.so")
+
+HN_F32, HN_BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+
+
+class HnTensor(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("dtype", C.c_int32), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("c", C.c_int32), ("ld", C.c_int32)]
+
+
+class HnEpilogue(C.Structure):
+    _fields_ = [("scale", C.c_void_p), ("shift", C.c_void_p), ("residual", C.c_void_p), ("residual_ld", C.c_int32),
+                ("act", C.c_int32), ("slope", C.c_float), ("slope_ptr", C.c_void_p), ("out_nchw", C.c_int32),
+                ("stat_sum", C.c_void_p), ("stat_sqsum", C.c_void_p), ("per_image", C.c_int32)]
+
+
+class HnConv(C.Structure):
+    _fields_ = [("cout", C.c_int32), ("r", C.c_int32), ("s", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+                ("dil", C.c_int32)]
+
+
+# name -> (restype, argtypes); every symbol declared in include/heatnet_b200.h
+_P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+_T, _E, _CV = C.POINTER(HnTensor), C.POINTER(HnEpilogue), C.POINTER(HnConv)
+SIGNATURES = {
+    "hn_last_error": (C.c_char_p, []),
+    "hn_version": (C.c_int, []),
+    "hn_device_check": (C.c_int, []),
+    "hn_nchw_to_nhwc": (C.c_int, [_P, _T, _P]),
+    "hn_nhwc_to_nchw": (C.c_int, [_T, _P, _P]),
+    "hn_pack_weight": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "hn_bn_fold": (C.c_int, [_P, _P, _P, _P, _P, _F, _P, _P, _I32, _P]),
+    "hn_conv_cout_pad": (_I32, [_I32, _I32]),
+    "hn_conv_kpad": (_I32, [_I32, _I32, _I32]),
+    "hn_conv2d_workspace_bytes": (_I64, [_T, _CV]),
+    "hn_conv2d_fwd": (C.c_int, [_T, _P, _CV, _E, _T, _P, _I64, _P]),
+    "hn_maxpool3x3s2_fwd": (C.c_int, [_T, _T, _P]),
+    "hn_pyramid_pool_workspace_bytes": (_I64, [_T, C.POINTER(_I32), _I32]),
+    "hn_pyramid_pool_fwd": (C.c_int, [_T, C.POINTER(_I32), _I32, _P, _P, _I64, _P]),
+    "hn_bilinear_fwd": (C.c_int, [_T, _T, _P]),
+    "hn_affine_act": (C.c_int, [_T, _E, _T, _P]),
+    "hn_channel_stats": (C.c_int, [_T, _P, _P, _P]),
+    "hn_bn_finalize": (C.c_int, [_P, _P, _I64, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _I32, _P]),
+    "hn_confusion": (C.c_int, [_P, _P, _I64, _I64, _P, _I32, _P, _P, _P]),
+    "hn_argmax_labels": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library and bind every declared symbol.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build the sm_100a CUDA library first "
+                "(python -c 'import __graft_entry__ as g; g.build()').  heatnet_pub_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)        # AttributeError if the .so lacks a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int):
+    """Translate a nonzero C return code into RuntimeError(hn_last_error())."""
+    if rc < 0:
+        raise RuntimeError("libheatnet_b200: " + load().hn_last_error().decode())
+    return rc
+
+
+_device_ok = False
+
+
+def require_device():
+    """The kernels are sm_100a-only; fail loudly anywhere else."""
+    global _device_ok
+    if not _device_ok:
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("heatnet_pub_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        check(load().hn_device_check())
+        _device_ok = True

@@ -1,0 +1,628 @@
+// HBM-bound kernels of the HeatNet hot path on NHWC views: layout conversion, weight packing, BN fold /
+// statistics / apply, max-pool, pyramid adaptive average pool, bilinear resize.  Every kernel moves
+// 8 channels (16 B of BF16 / 32 B of FP32) per thread so that a warp touches contiguous 512 B / 1 KB
+// segments; grids are sized in whole waves of the SM count with grid-stride loops.
+#include "hn_common.cuh"
+
+namespace hn {
+
+static inline int wave_grid(int64_t work_items, int threads, int waves_per_sm = 8)
+{
+    int64_t want = cdiv(work_items, threads);
+    int64_t cap = (int64_t)num_sms() * waves_per_sm;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion
+// ------------------------------------------------------------------------------------------------
+// small-C path (network inputs: C = 3 / 1 / 4): one thread per pixel
+template <typename T>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_smallc(const float *__restrict__ src, T *__restrict__ dst, int64_t npix_per_img,
+                                                           int64_t n_img, int C, int ld)
+{
+    const int64_t total = npix_per_img * n_img;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n = i / npix_per_img, p = i - n * npix_per_img;
+        const float *s = src + n * C * npix_per_img + p;
+        T *d = dst + i * ld;
+        for (int c = 0; c < C; ++c) d[c] = from_f32<T>(__ldg(s + (int64_t)c * npix_per_img));
+    }
+}
+
+// general path: 32x32 tile transpose through shared memory.  grid = (pixel tiles, channel tiles, N)
+template <typename T, bool kToNHWC>
+__global__ void __launch_bounds__(256) transpose_tiles(const void *__restrict__ src_, void *__restrict__ dst_, int64_t HW, int C,
+                                                       int ld)
+{
+    __shared__ float tile[32][33];
+    const int64_t p0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int64_t n = blockIdx.z;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    if (kToNHWC) {
+        const float *src = (const float *)src_ + n * C * HW;
+        T *dst = (T *)dst_ + n * HW * ld;
+        for (int j = ty; j < 32; j += 8)
+            if (c0 + j < C && p0 + tx < HW) tile[j][tx] = src[(int64_t)(c0 + j) * HW + p0 + tx];
+        __syncthreads();
+        for (int j = ty; j < 32; j += 8)
+            if (p0 + j < HW && c0 + tx < C) dst[(p0 + j) * ld + c0 + tx] = from_f32<T>(tile[tx][j]);
+    } else {
+        const T *src = (const T *)src_ + n * HW * ld;
+        float *dst = (float *)dst_ + n * C * HW;
+        for (int j = ty; j < 32; j += 8)
+            if (p0 + j < HW && c0 + tx < C) tile[j][tx] = to_f32<T>(src[(p0 + j) * ld + c0 + tx]);
+        __syncthreads();
+        for (int j = ty; j < 32; j += 8)
+            if (c0 + j < C && p0 + tx < HW) dst[(int64_t)(c0 + j) * HW + p0 + tx] = tile[tx][j];
+    }
+}
+
+// OIHW FP32 -> [cout_pad][kpad], k = (r*S+s)*Cin + c
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float *__restrict__ w, T *__restrict__ dst, int cout, int cin, int R,
+                                                          int S, int cout_pad, int kpad)
+{
+    const int64_t total = (int64_t)cout_pad * kpad;
+    const int K = R * S * cin;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int o = (int)(i / kpad), k = (int)(i - (int64_t)o * kpad);
+        float v = 0.f;
+        if (o < cout && k < K) {
+            int tap = k / cin, c = k - tap * cin;
+            int r = tap / S, s = tap - r * S;
+            v = __ldg(w + (((int64_t)o * cin + c) * R + r) * S + s);
+        }
+        dst[i] = from_f32<T>(v);
+    }
+}
+
+__global__ void bn_fold_kernel(const float *gamma, const float *beta, const float *mean, const float *var, const float *bias,
+                               float eps, float *scale, float *shift, int C)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float b = bias ? bias[c] : 0.f;
+    if (gamma) {
+        float sc = gamma[c] / sqrtf(var[c] + eps);   // matches ATen: weight * rsqrt(var+eps) within 1 ulp
+        scale[c] = sc;
+        shift[c] = beta[c] + (b - mean[c]) * sc;
+    } else {
+        scale[c] = 1.f;
+        shift[c] = b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm2d train-mode statistics / finalize, and the fused apply pass
+// ------------------------------------------------------------------------------------------------
+// blockDim = (CVB, PL): CVB 8-channel vectors x PL pixel lanes.  grid = (pixel chunks, cvec blocks)
+template <typename T>
+__global__ void channel_stats_kernel(const T *__restrict__ x, int64_t npix, int C, int ld, int64_t pix_per_cta, double *sum,
+                                     double *sqsum)
+{
+    extern __shared__ float red[];  // [2][PL][CVB*8]
+    const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+    const int ncv = C / 8;
+    const int PL = blockDim.y, CVB = blockDim.x;
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+    const int64_t p_begin = (int64_t)blockIdx.x * pix_per_cta;
+    const int64_t p_end = min(p_begin + pix_per_cta, npix);
+    if (cv < ncv) {
+        for (int64_t p = p_begin + threadIdx.y; p < p_end; p += PL) {
+            float v[8];
+            Vec8<T>::load(x + p * ld + cv * 8, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                s[i] += v[i];
+                q[i] = fmaf(v[i], v[i], q[i]);
+            }
+        }
+    }
+    float *rs = red, *rq = red + PL * CVB * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        rs[(threadIdx.y * CVB + threadIdx.x) * 8 + i] = s[i];
+        rq[(threadIdx.y * CVB + threadIdx.x) * 8 + i] = q[i];
+    }
+    __syncthreads();
+    // threads of pixel-lane 0..: each (threadIdx.x, i) column reduced by one thread
+    const int tid = threadIdx.y * CVB + threadIdx.x;
+    for (int col = tid; col < CVB * 8; col += CVB * PL) {
+        double a = 0.0, b = 0.0;
+        for (int l = 0; l < PL; ++l) {
+            a += (double)rs[l * CVB * 8 + col];
+            b += (double)rq[l * CVB * 8 + col];
+        }
+        int ch = blockIdx.y * CVB * 8 + col;
+        if (ch < C) {
+            atomicAdd(sum + ch, a);
+            atomicAdd(sqsum + ch, b);
+        }
+    }
+}
+
+__global__ void bn_finalize_kernel(const double *sum, const double *sqsum, double count, const float *gamma, const float *beta,
+                                   float eps, float momentum, float *running_mean, float *running_var, float *scale, float *shift,
+                                   float *save_mean, float *save_invstd, int C)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double mean = sum[c] / count;
+    double var = sqsum[c] / count - mean * mean;
+    if (var < 0) var = 0;
+    double invstd = 1.0 / sqrt(var + (double)eps);
+    float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    scale[c] = (float)(g * invstd);
+    shift[c] = (float)(b - mean * g * invstd);
+    if (save_mean) save_mean[c] = (float)mean;
+    if (save_invstd) save_invstd[c] = (float)invstd;
+    if (running_mean) {
+        double unbiased = count > 1 ? var * count / (count - 1.0) : var;
+        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) affine_act_kernel(const T *__restrict__ x, int ldx, const float *__restrict__ scale,
+                                                         const float *__restrict__ shift, const T *__restrict__ res, int ldr, int act,
+                                                         float slope, const float *slope_ptr, T *__restrict__ y, int ldy, int64_t npix,
+                                                         int C, int64_t pix_per_image)
+{
+    const int ncv = C / 8;
+    const int64_t total = npix * ncv;
+    if (slope_ptr) slope = __ldg(slope_ptr);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t p = i / ncv;
+        int c = (int)(i - p * ncv) * 8;
+        float v[8];
+        Vec8<T>::load(x + p * ldx + c, v);
+        if (scale) {
+            // pix_per_image > 0: per-(image, channel) parameters (Dropout2d masks)
+            const int64_t poff = pix_per_image > 0 ? (p / pix_per_image) * C : 0;
+            float sc[8], sh[8];
+            Vec8<float>::load(scale + poff + c, sc);
+            if (shift) {
+                Vec8<float>::load(shift + poff + c, sh);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] *= sc[j];
+            }
+        }
+        if (res) {
+            float r[8];
+            Vec8<T>::load(res + p * ldr + c, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += r[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], act, slope);
+        Vec8<T>::store(y + p * ldy + c, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// nn.MaxPool2d(3, 2, 1) (pads with -inf)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_kernel(const T *__restrict__ x, int ldx, T *__restrict__ y, int ldy, int N, int H, int W,
+                                                      int Ho, int Wo, int C)
+{
+    const int ncv = C / 8;
+    const int64_t total = (int64_t)N * Ho * Wo * ncv;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % ncv) * 8;
+        int64_t p = i / ncv;
+        int wo = (int)(p % Wo);
+        int ho = (int)((p / Wo) % Ho);
+        int n = (int)(p / ((int64_t)Wo * Ho));
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            int hi = 2 * ho - 1 + r;
+            if (hi < 0 || hi >= H) continue;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                int wi = 2 * wo - 1 + s;
+                if (wi < 0 || wi >= W) continue;
+                float v[8];
+                Vec8<T>::load(x + (((int64_t)n * H + hi) * W + wi) * ldx + c, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+            }
+        }
+        Vec8<T>::store(y + p * ldy + c, m);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pyramid adaptive average pool: all sizes in one pass over x.
+// stage 1: CTA = (n, input row); thread = one 8-channel vector; accumulates the row into every column bin
+//          of every size (registers), writes row partials [N][H][ncols][C] FP32.
+// stage 2: thread = (n, bin, 8-channel vector): adds the rows of the bin, divides by the bin area.
+// Deterministic (no atomics).  Bin i of size s covers [floor(i*H/s), ceil((i+1)*H/s)).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxPoolCols = 12;  // sum of sizes, (1,2,3,6) -> 12
+struct PoolSizes {
+    int n, s[4];
+    int ncols, w0[kMaxPoolCols], w1[kMaxPoolCols];  // column-bin bounds of every size, concatenated
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) pyramid_rows_kernel(const T *__restrict__ x, int ldx, int H, int W, int C,
+                                                           const __grid_constant__ PoolSizes ps, float *__restrict__ rowpart)
+{
+    const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+    if (cv * 8 >= C) return;
+    const int64_t nh = blockIdx.x;  // n*H + h
+    const int ncols = ps.ncols;
+    float acc[kMaxPoolCols][8];
+#pragma unroll
+    for (int b = 0; b < kMaxPoolCols; ++b)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[b][j] = 0.f;
+    const T *row = x + nh * W * ldx + cv * 8;
+    for (int w = 0; w < W; ++w) {
+        float v[8];
+        Vec8<T>::load(row + (int64_t)w * ldx, v);
+#pragma unroll
+        for (int b = 0; b < kMaxPoolCols; ++b) {
+            if (b < ncols && w >= ps.w0[b] && w < ps.w1[b]) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[b][j] += v[j];
+            }
+        }
+    }
+    float *out = rowpart + nh * ncols * C + cv * 8;
+#pragma unroll
+    for (int b = 0; b < kMaxPoolCols; ++b)
+        if (b < ncols) Vec8<float>::store(out + (int64_t)b * C, acc[b]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pyramid_bins_kernel(const float *__restrict__ rowpart, int N, int H, int W, int C, PoolSizes ps,
+                                                           T *__restrict__ out)
+{
+    int nbins = 0, ncols = 0;
+    for (int a = 0; a < ps.n; ++a) {
+        nbins += ps.s[a] * ps.s[a];
+        ncols += ps.s[a];
+    }
+    const int ncv = C / 8;
+    const int64_t total = (int64_t)N * nbins * ncv;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % ncv) * 8;
+        int bin = (int)((i / ncv) % nbins);
+        int n = (int)(i / ((int64_t)ncv * nbins));
+        int a = 0, base = 0, colbase = 0;
+        while (bin - base >= ps.s[a] * ps.s[a]) {
+            base += ps.s[a] * ps.s[a];
+            colbase += ps.s[a];
+            ++a;
+        }
+        int s = ps.s[a], bi = (bin - base) / s, bj = (bin - base) % s;
+        int h0 = (bi * H) / s, h1 = ((bi + 1) * H + s - 1) / s;
+        int w0 = (bj * W) / s, w1 = ((bj + 1) * W + s - 1) / s;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int h = h0; h < h1; ++h) {
+            float v[8];
+            Vec8<float>::load(rowpart + (((int64_t)n * H + h) * ncols + colbase + bj) * C + c, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += v[j];
+        }
+        float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] *= inv;
+        // per-size dense NHWC blocks: size a occupies [N][s*s][C] starting at pixel row N*base
+        Vec8<T>::store(out + ((int64_t)base * N + (int64_t)n * s * s + (bin - base)) * C + c, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bilinear resize, align_corners = False (ATen upsample_bilinear2d index rule, computed in FP32)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, int &i0, int &i1, float &l1)
+{
+    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    i0 = (int)src;
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = src - (float)i0;
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) bilinear_vec_kernel(const TI *__restrict__ x, int ldx, TO *__restrict__ y, int ldy, int N, int H,
+                                                           int W, int Ho, int Wo, int C, float sh, float sw)
+{
+    const int ncv = C / 8;
+    const int64_t total = (int64_t)N * Ho * Wo * ncv;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % ncv) * 8;
+        int64_t p = i / ncv;
+        int wo = (int)(p % Wo);
+        int ho = (int)((p / Wo) % Ho);
+        int n = (int)(p / ((int64_t)Wo * Ho));
+        int y0, y1, x0, x1;
+        float ly, lx;
+        bilinear_src(ho, sh, H, y0, y1, ly);
+        bilinear_src(wo, sw, W, x0, x1, lx);
+        const TI *b = x + (int64_t)n * H * W * ldx + c;
+        float a00[8], a01[8], a10[8], a11[8], o[8];
+        Vec8<TI>::load(b + ((int64_t)y0 * W + x0) * ldx, a00);
+        Vec8<TI>::load(b + ((int64_t)y0 * W + x1) * ldx, a01);
+        Vec8<TI>::load(b + ((int64_t)y1 * W + x0) * ldx, a10);
+        Vec8<TI>::load(b + ((int64_t)y1 * W + x1) * ldx, a11);
+        const float hy = 1.f - ly, hx = 1.f - lx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = hy * (hx * a00[j] + lx * a01[j]) + ly * (hx * a10[j] + lx * a11[j]);
+        Vec8<TO>::store(y + p * ldy + c, o);
+    }
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) bilinear_scalar_kernel(const TI *__restrict__ x, int ldx, TO *__restrict__ y, int ldy, int N,
+                                                              int H, int W, int Ho, int Wo, int C, float sh, float sw)
+{
+    const int64_t total = (int64_t)N * Ho * Wo * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        int64_t p = i / C;
+        int wo = (int)(p % Wo);
+        int ho = (int)((p / Wo) % Ho);
+        int n = (int)(p / ((int64_t)Wo * Ho));
+        int y0, y1, x0, x1;
+        float ly, lx;
+        bilinear_src(ho, sh, H, y0, y1, ly);
+        bilinear_src(wo, sw, W, x0, x1, lx);
+        const TI *b = x + (int64_t)n * H * W * ldx + c;
+        float a00 = to_f32<TI>(b[((int64_t)y0 * W + x0) * ldx]), a01 = to_f32<TI>(b[((int64_t)y0 * W + x1) * ldx]);
+        float a10 = to_f32<TI>(b[((int64_t)y1 * W + x0) * ldx]), a11 = to_f32<TI>(b[((int64_t)y1 * W + x1) * ldx]);
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        y[p * ldy + c] = from_f32<TO>(hy * (hx * a00 + lx * a01) + ly * (hx * a10 + lx * a11));
+    }
+}
+
+template <typename TI, typename TO>
+static int launch_bilinear(const hn_tensor *x, const hn_tensor *y, cudaStream_t st)
+{
+    const float sh = (float)x->h / (float)y->h, sw = (float)x->w / (float)y->w;
+    if (vec8_ok(x) && vec8_ok(y)) {
+        int64_t total = (int64_t)y->n * y->h * y->w * (y->c / 8);
+        bilinear_vec_kernel<TI, TO><<<wave_grid(total, 256), 256, 0, st>>>((const TI *)x->ptr, x->ld, (TO *)y->ptr, y->ld, x->n, x->h,
+                                                                         x->w, y->h, y->w, x->c, sh, sw);
+    } else {
+        int64_t total = (int64_t)y->n * y->h * y->w * y->c;
+        bilinear_scalar_kernel<TI, TO><<<wave_grid(total, 256), 256, 0, st>>>((const TI *)x->ptr, x->ld, (TO *)y->ptr, y->ld, x->n,
+                                                                            x->h, x->w, y->h, y->w, x->c, sh, sw);
+    }
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+}  // namespace hn
+
+using namespace hn;
+
+extern "C" int hn_nchw_to_nhwc(const float *src, const hn_tensor *dst, void *stream)
+{
+    HN_CHECK_ARG(src && dst && dst->ptr, "hn_nchw_to_nhwc: null pointer");
+    HN_CHECK_ARG(dst->ld >= dst->c && dst->c > 0, "hn_nchw_to_nhwc: bad channel stride");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t HW = (int64_t)dst->h * dst->w;
+    if (HW * dst->n == 0) return HN_OK;
+    if (dst->c <= 8) {
+        int grid = wave_grid(HW * dst->n, 256);
+        if (dst->dtype == HN_BF16)
+            nchw_to_nhwc_smallc<__nv_bfloat16><<<grid, 256, 0, st>>>(src, (__nv_bfloat16 *)dst->ptr, HW, dst->n, dst->c, dst->ld);
+        else
+            nchw_to_nhwc_smallc<float><<<grid, 256, 0, st>>>(src, (float *)dst->ptr, HW, dst->n, dst->c, dst->ld);
+    } else {
+        dim3 grid((unsigned)cdiv(HW, 32), (unsigned)cdiv(dst->c, 32), (unsigned)dst->n);
+        if (dst->dtype == HN_BF16)
+            transpose_tiles<__nv_bfloat16, true><<<grid, 256, 0, st>>>(src, dst->ptr, HW, dst->c, dst->ld);
+        else
+            transpose_tiles<float, true><<<grid, 256, 0, st>>>(src, dst->ptr, HW, dst->c, dst->ld);
+    }
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_nhwc_to_nchw(const hn_tensor *src, float *dst, void *stream)
+{
+    HN_CHECK_ARG(src && src->ptr && dst, "hn_nhwc_to_nchw: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t HW = (int64_t)src->h * src->w;
+    if (HW * src->n == 0) return HN_OK;
+    dim3 grid((unsigned)cdiv(HW, 32), (unsigned)cdiv(src->c, 32), (unsigned)src->n);
+    if (src->dtype == HN_BF16)
+        transpose_tiles<__nv_bfloat16, false><<<grid, 256, 0, st>>>(src->ptr, dst, HW, src->c, src->ld);
+    else
+        transpose_tiles<float, false><<<grid, 256, 0, st>>>(src->ptr, dst, HW, src->c, src->ld);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_pack_weight(const float *w_oihw, void *dst, int32_t dtype, int32_t cout, int32_t cin, int32_t r, int32_t s,
+                              int32_t cout_pad, int32_t kpad, void *stream)
+{
+    HN_CHECK_ARG(w_oihw && dst, "hn_pack_weight: null pointer");
+    HN_CHECK_ARG(cout_pad >= cout && kpad >= r * s * cin, "hn_pack_weight: padded sizes too small");
+    int64_t total = (int64_t)cout_pad * kpad;
+    int grid = wave_grid(total, 256);
+    if (dtype == HN_BF16)
+        pack_weight_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, (__nv_bfloat16 *)dst, cout, cin, r, s, cout_pad, kpad);
+    else
+        pack_weight_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, (float *)dst, cout, cin, r, s, cout_pad, kpad);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_bn_fold(const float *gamma, const float *beta, const float *mean, const float *var, const float *bias, float eps,
+                          float *scale, float *shift, int32_t c, void *stream)
+{
+    HN_CHECK_ARG(scale && shift && c > 0, "hn_bn_fold: bad arguments");
+    HN_CHECK_ARG(!gamma || (beta && mean && var), "hn_bn_fold: gamma given without beta/mean/var");
+    bn_fold_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, mean, var, bias, eps, scale, shift, c);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_channel_stats(const hn_tensor *x, double *sum, double *sqsum, void *stream)
+{
+    HN_CHECK_ARG(x && x->ptr && sum && sqsum, "hn_channel_stats: null pointer");
+    HN_CHECK_ARG(vec8_ok(x), "hn_channel_stats: view must be 8-channel aligned (C=%d ld=%d)", x->c, x->ld);
+    cudaStream_t st = (cudaStream_t)stream;
+    HN_CUDA(cudaMemsetAsync(sum, 0, sizeof(double) * x->c, st));
+    HN_CUDA(cudaMemsetAsync(sqsum, 0, sizeof(double) * x->c, st));
+    const int64_t npix = (int64_t)x->n * x->h * x->w;
+    if (npix == 0) return HN_OK;
+    const int ncv = x->c / 8;
+    const int CVB = ncv < 32 ? ncv : 32;
+    const int PL = 256 / CVB;
+    const int cvblocks = (int)cdiv(ncv, CVB);
+    // ~4 waves of CTAs, at least PL*8 pixels each
+    int64_t chunks = cdiv((int64_t)num_sms() * 4, cvblocks);
+    int64_t pix_per_cta = cdiv(npix, chunks);
+    if (pix_per_cta < (int64_t)PL * 8) pix_per_cta = (int64_t)PL * 8;
+    chunks = cdiv(npix, pix_per_cta);
+    dim3 grid((unsigned)chunks, (unsigned)cvblocks), block(CVB, PL);
+    size_t smem = (size_t)2 * PL * CVB * 8 * sizeof(float);
+    if (x->dtype == HN_BF16)
+        channel_stats_kernel<__nv_bfloat16><<<grid, block, smem, st>>>((const __nv_bfloat16 *)x->ptr, npix, x->c, x->ld, pix_per_cta, sum, sqsum);
+    else
+        channel_stats_kernel<float><<<grid, block, smem, st>>>((const float *)x->ptr, npix, x->c, x->ld, pix_per_cta, sum, sqsum);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_bn_finalize(const double *sum, const double *sqsum, int64_t count, const float *gamma, const float *beta, float eps,
+                              float momentum, float *running_mean, float *running_var, float *scale, float *shift, float *save_mean,
+                              float *save_invstd, int32_t c, void *stream)
+{
+    HN_CHECK_ARG(sum && sqsum && scale && shift && c > 0 && count > 0, "hn_bn_finalize: bad arguments");
+    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sqsum, (double)count, gamma, beta, eps, momentum,
+                                                                         running_mean, running_var, scale, shift, save_mean,
+                                                                         save_invstd, c);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_affine_act(const hn_tensor *x, const hn_epilogue *ep, const hn_tensor *y, void *stream)
+{
+    HN_CHECK_ARG(x && y && ep && x->ptr && y->ptr, "hn_affine_act: null pointer");
+    HN_CHECK_ARG(x->dtype == y->dtype, "hn_affine_act: dtype mismatch");
+    HN_CHECK_ARG(x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c, "hn_affine_act: shape mismatch");
+    HN_CHECK_ARG(vec8_ok(x) && vec8_ok(y), "hn_affine_act: views must be 8-channel aligned");
+    HN_CHECK_ARG(ep->scale != nullptr || ep->shift == nullptr, "hn_affine_act: shift given without scale");
+    const int64_t npix = (int64_t)x->n * x->h * x->w;
+    const int64_t ppi = ep->per_image ? (int64_t)x->h * x->w : 0;
+    if (npix == 0) return HN_OK;
+    int grid = wave_grid(npix * (x->c / 8), 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x->dtype == HN_BF16)
+        affine_act_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x->ptr, x->ld, ep->scale, ep->shift,
+                                                             (const __nv_bfloat16 *)ep->residual, ep->residual_ld, ep->act, ep->slope,
+                                                             ep->slope_ptr, (__nv_bfloat16 *)y->ptr, y->ld, npix, x->c, ppi);
+    else
+        affine_act_kernel<float><<<grid, 256, 0, st>>>((const float *)x->ptr, x->ld, ep->scale, ep->shift, (const float *)ep->residual,
+                                                     ep->residual_ld, ep->act, ep->slope, ep->slope_ptr, (float *)y->ptr, y->ld, npix,
+                                                     x->c, ppi);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_maxpool3x3s2_fwd(const hn_tensor *x, const hn_tensor *y, void *stream)
+{
+    HN_CHECK_ARG(x && y && x->ptr && y->ptr, "hn_maxpool3x3s2_fwd: null pointer");
+    HN_CHECK_ARG(x->dtype == y->dtype && x->c == y->c && x->n == y->n, "hn_maxpool3x3s2_fwd: dtype/shape mismatch");
+    HN_CHECK_ARG(y->h == (x->h - 1) / 2 + 1 && y->w == (x->w - 1) / 2 + 1, "hn_maxpool3x3s2_fwd: output must be %dx%d",
+                 (x->h - 1) / 2 + 1, (x->w - 1) / 2 + 1);
+    HN_CHECK_ARG(vec8_ok(x) && vec8_ok(y), "hn_maxpool3x3s2_fwd: views must be 8-channel aligned");
+    int64_t total = (int64_t)y->n * y->h * y->w * (y->c / 8);
+    if (total == 0) return HN_OK;
+    int grid = wave_grid(total, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x->dtype == HN_BF16)
+        maxpool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x->ptr, x->ld, (__nv_bfloat16 *)y->ptr, y->ld, x->n, x->h,
+                                                          x->w, y->h, y->w, x->c);
+    else
+        maxpool_kernel<float><<<grid, 256, 0, st>>>((const float *)x->ptr, x->ld, (float *)y->ptr, y->ld, x->n, x->h, x->w, y->h, y->w, x->c);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int64_t hn_pyramid_pool_workspace_bytes(const hn_tensor *x, const int32_t *sizes, int32_t nsizes)
+{
+    int ncols = 0;
+    for (int i = 0; i < nsizes; ++i) ncols += sizes[i];
+    return (int64_t)x->n * x->h * ncols * x->c * (int64_t)sizeof(float);
+}
+
+extern "C" int hn_pyramid_pool_fwd(const hn_tensor *x, const int32_t *sizes, int32_t nsizes, void *out, void *workspace,
+                                      int64_t workspace_bytes, void *stream)
+{
+    HN_CHECK_ARG(x && x->ptr && sizes && out && workspace, "hn_pyramid_pool_fwd: null pointer");
+    HN_CHECK_ARG(nsizes >= 1 && nsizes <= 4, "hn_pyramid_pool_fwd: 1..4 pyramid sizes supported");
+    HN_CHECK_ARG(vec8_ok(x), "hn_pyramid_pool_fwd: view must be 8-channel aligned");
+    PoolSizes ps{};
+    ps.n = nsizes;
+    int ncols = 0;
+    for (int i = 0; i < nsizes; ++i) {
+        HN_CHECK_ARG(sizes[i] >= 1, "hn_pyramid_pool_fwd: bad size");
+        ps.s[i] = sizes[i];
+        ncols += sizes[i];
+    }
+    HN_CHECK_ARG(ncols <= kMaxPoolCols, "hn_pyramid_pool_fwd: sum of sizes %d > %d", ncols, kMaxPoolCols);
+    ps.ncols = 0;
+    for (int i = 0; i < nsizes; ++i)
+        for (int j = 0; j < sizes[i]; ++j) {
+            ps.w0[ps.ncols] = (j * x->w) / sizes[i];
+            ps.w1[ps.ncols] = ((j + 1) * x->w + sizes[i] - 1) / sizes[i];
+            ++ps.ncols;
+        }
+    if (workspace_bytes < hn_pyramid_pool_workspace_bytes(x, sizes, nsizes)) {
+        set_error("hn_pyramid_pool_fwd: workspace too small");
+        return HN_ERR_WORKSPACE;
+    }
+    if ((int64_t)x->n * x->h * x->w == 0) return HN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ncv = x->c / 8;
+    const int threads = ncv < 256 ? ((ncv + 31) / 32) * 32 : 256;
+    dim3 grid1((unsigned)(x->n * x->h), (unsigned)cdiv(ncv, threads));
+    int nbins = 0;
+    for (int i = 0; i < nsizes; ++i) nbins += sizes[i] * sizes[i];
+    int grid2 = wave_grid((int64_t)x->n * nbins * ncv, 256);
+    if (x->dtype == HN_BF16) {
+        pyramid_rows_kernel<__nv_bfloat16><<<grid1, threads, 0, st>>>((const __nv_bfloat16 *)x->ptr, x->ld, x->h, x->w, x->c, ps, (float *)workspace);
+        pyramid_bins_kernel<__nv_bfloat16><<<grid2, 256, 0, st>>>((const float *)workspace, x->n, x->h, x->w, x->c, ps, (__nv_bfloat16 *)out);
+    } else {
+        pyramid_rows_kernel<float><<<grid1, threads, 0, st>>>((const float *)x->ptr, x->ld, x->h, x->w, x->c, ps, (float *)workspace);
+        pyramid_bins_kernel<float><<<grid2, 256, 0, st>>>((const float *)workspace, x->n, x->h, x->w, x->c, ps, (float *)out);
+    }
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_bilinear_fwd(const hn_tensor *x, const hn_tensor *y, void *stream)
+{
+    HN_CHECK_ARG(x && y && x->ptr && y->ptr, "hn_bilinear_fwd: null pointer");
+    HN_CHECK_ARG(x->n == y->n && x->c == y->c, "hn_bilinear_fwd: batch/channel mismatch");
+    HN_CHECK_ARG(x->h > 0 && x->w > 0, "hn_bilinear_fwd: empty input");
+    if ((int64_t)y->n * y->h * y->w == 0) return HN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x->dtype == HN_BF16 && y->dtype == HN_BF16) return launch_bilinear<__nv_bfloat16, __nv_bfloat16>(x, y, st);
+    if (x->dtype == HN_F32 && y->dtype == HN_F32) return launch_bilinear<float, float>(x, y, st);
+    if (x->dtype == HN_BF16 && y->dtype == HN_F32) return launch_bilinear<__nv_bfloat16, float>(x, y, st);
+    return launch_bilinear<float, __nv_bfloat16>(x, y, st);
+}

@@ -1,0 +1,593 @@
+// BF16 implicit-GEMM convolution on the 5th-generation tensor cores (sm_100a):
+//   D[pixels, Cout] = im2col(X)[pixels, R*S*Cin] * W[Cout, R*S*Cin]^T,   FP32 accumulators in TMEM.
+//
+// * Operands are staged by TMA into 128B-swizzled, K-major shared-memory tiles; one elected thread issues
+//   tcgen05.mma (cta_group::1, M=128, N=BLOCK_N, K=16 per instruction, 4 per 64-channel k-block).
+// * The im2col matrix is never materialised for stride-1 convolutions: an M tile is a TH x TW patch of output
+//   pixels of one image (TH*TW = 128) and the A tile of filter tap (r,s) is the same patch of the NHWC input
+//   shifted by (r*dil - pad, s*dil - pad), fetched as one 4-D TMA box {64 ch, TW, TH, 1}.  Out-of-bounds
+//   coordinates (zero padding, ragged right/bottom tiles) are zero-filled by the TMA unit.  1x1 convolutions
+//   use the same path with the pixel axis flattened (TH=1, TW=128).
+// * Strided / small-Cin convolutions (7x7 s2 stems, 3x3 s2, 1x1 s2, the critics' 4x4 s2) first run a
+//   bandwidth-bound im2col gather into a workspace and then the flattened path with K = kpad.
+// * Warp-specialised persistent kernel: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+//   warps 4-7 = epilogue (tcgen05.ld -> scale/shift/residual/activation -> global).  Two TMEM accumulator
+//   buffers let the epilogue of tile i overlap the main loop of tile i+1.
+#include <cuda.h>
+
+#include "hn_common.cuh"
+
+namespace hn {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 BF16 = 128 B = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (BF16 inputs, FP32 accumulate)
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive FP32 columns: thread t of the warp receives lane (taddr.lane + t)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (sm_100 "version 1"):
+//   start address >> 4 | LBO (unused for swizzled K-major; 1) | SBO = 8 rows * 128 B = 1024 B | layout SWIZZLE_128B (2)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor: D=F32, A=B=BF16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+struct TcParams {
+    // tiling of the output pixel space
+    int tiles_w, tiles_h, n_img;   // M tiles = n_img * tiles_h * tiles_w
+    int TH, TW;                    // TH*TW = 128
+    int Ho, Wo;                    // output spatial size (flat mode: Ho = 1, Wo = total pixels)
+    int n_tiles;                   // Cout tiles
+    int R, S, pad, dil;
+    int cblocks;                   // Cin / 64 (flat-from-workspace: kpad / 64 with R=S=1)
+    int Cout;
+    // epilogue
+    void *y;
+    int ldy, y_f32;
+    const float *scale, *shift;
+    const void *res;
+    int ldr;
+    int act;
+    float slope;
+    const float *slope_ptr;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcParams p)
+{
+    constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+    constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;   // columns per accumulator buffer
+    constexpr int TMEM_COLS = 2 * ACC_COLS;                   // power of two >= 32
+    constexpr uint32_t IDESC = make_idesc_bf16(BLOCK_M, BLOCK_N);
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *full_bar = bars, *empty_bar = bars + STAGES, *tfull_bar = bars + 2 * STAGES, *tempty_bar = bars + 2 * STAGES + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m_tiles = p.n_img * p.tiles_h * p.tiles_w;
+    const int num_tiles = num_m_tiles * p.n_tiles;
+    const int num_kb = p.R * p.S * p.cblocks;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(smem_u32(full_bar + i), 1);
+            mbar_init(smem_u32(empty_bar + i), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(tfull_bar + i), 1);
+            mbar_init(smem_u32(tempty_bar + i), 4);   // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
+                const int w_base = tw * p.TW - p.pad, h_base = th * p.TH - p.pad;
+                int kb = 0;
+                for (int r = 0; r < p.R; ++r)
+                    for (int s = 0; s < p.S; ++s)
+                        for (int cb = 0; cb < p.cblocks; ++cb, ++kb) {
+                            mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+                            const uint32_t fb = smem_u32(full_bar + stage);
+                            mbar_expect_tx(fb, STAGE_BYTES);
+                            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                            tma_load_4d(sa, &tmap_a, fb, cb * BLOCK_K, w_base + s * p.dil, h_base + r * p.dil, img);
+                            tma_load_2d(sa + A_STAGE_BYTES, &tmap_b, fb, kb * BLOCK_K, nt * BLOCK_N);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(smem_u32(full_bar + stage), phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint64_t adesc = make_kmajor_sw128_desc(sa);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(sa + A_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // advance 16 BF16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
+                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+                    }
+                    umma_commit(smem_u32(empty_bar + stage));   // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(smem_u32(tfull_bar + acc));          // accumulator ready for the epilogue
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===================== epilogue =====================
+        const int q = warp - EPI_WARP0;          // == warp % 4: the TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;           // accumulator row = pixel within the tile
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        float slope = p.slope;
+        if (p.slope_ptr) slope = __ldg(p.slope_ptr);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
+            const int ho = th * p.TH + row / p.TW, wo = tw * p.TW + row % p.TW;
+            const bool valid = ho < p.Ho && wo < p.Wo;
+            const int64_t pix = ((int64_t)img * p.Ho + ho) * p.Wo + wo;
+            mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
+            constexpr int CHUNK = BLOCK_N < 32 ? 16 : 32;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += CHUNK) {
+                uint32_t raw[CHUNK];
+                if constexpr (CHUNK == 32) tmem_ld_32x32(taddr + c0, raw);
+                else tmem_ld_32x16(taddr + c0, raw);
+                tmem_ld_wait();
+                const int cbase = nt * BLOCK_N + c0;
+                if (valid && cbase < p.Cout) {
+                    float v[CHUNK];
+#pragma unroll
+                    for (int j = 0; j < CHUNK; ++j) v[j] = __uint_as_float(raw[j]);
+                    const bool full = cbase + CHUNK <= p.Cout;
+                    if (p.scale) {
+                        if (full) {   // warp-uniform 16-byte broadcast loads
+#pragma unroll
+                            for (int j = 0; j < CHUNK; j += 4) {
+                                const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + cbase + j));
+                                const float4 sh = __ldg(reinterpret_cast<const float4 *>(p.shift + cbase + j));
+                                v[j] = fmaf(v[j], sc.x, sh.x);
+                                v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
+                                v[j + 2] = fmaf(v[j + 2], sc.z, sh.z);
+                                v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CHUNK; ++j)
+                                if (cbase + j < p.Cout) v[j] = fmaf(v[j], __ldg(p.scale + cbase + j), __ldg(p.shift + cbase + j));
+                        }
+                    }
+                    if (p.res) {
+                        const __nv_bfloat16 *rp = (const __nv_bfloat16 *)p.res + pix * p.ldr + cbase;
+                        if (full && (p.ldr & 7) == 0) {
+#pragma unroll
+                            for (int j = 0; j < CHUNK; j += 8) {
+                                float r8[8];
+                                Vec8<__nv_bfloat16>::load(rp + j, r8);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[j + i] += r8[i];
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CHUNK; ++j)
+                                if (cbase + j < p.Cout) v[j] += __bfloat162float(rp[j]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < CHUNK; ++j) v[j] = apply_act(v[j], p.act, slope);
+                    if (p.y_f32) {
+                        float *yp = (float *)p.y + pix * p.ldy + cbase;
+                        if (full && (p.ldy & 3) == 0) {
+#pragma unroll
+                            for (int j = 0; j < CHUNK; j += 4) *reinterpret_cast<float4 *>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CHUNK; ++j)
+                                if (cbase + j < p.Cout) yp[j] = v[j];
+                        }
+                    } else {
+                        __nv_bfloat16 *yp = (__nv_bfloat16 *)p.y + pix * p.ldy + cbase;
+                        if (full && (p.ldy & 7) == 0) {
+#pragma unroll
+                            for (int j = 0; j < CHUNK; j += 8) {
+                                float o8[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) o8[i] = v[j + i];
+                                Vec8<__nv_bfloat16>::store(yp + j, o8);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CHUNK; ++j)
+                                if (cbase + j < p.Cout) yp[j] = __float2bfloat16_rn(v[j]);
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ im2col gather
+// A[m][k], k = (r*S+s)*Cin + c, zero for padding and for k >= R*S*Cin.  Thread = (pixel, 8 consecutive k).
+__global__ void __launch_bounds__(256) im2col_bf16_kernel(const __nv_bfloat16 *__restrict__ x, int ldx, int N, int H, int W, int C,
+                                                          int Ho, int Wo, int R, int S, int stride, int pad, int dil, int kpad,
+                                                          __nv_bfloat16 *__restrict__ a)
+{
+    const int k8n = kpad / 8;
+    const int64_t total = (int64_t)N * Ho * Wo * k8n;
+    const int K = R * S * C;
+    const bool vec = (C % 8 == 0) && (ldx % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k0 = (int)(i % k8n) * 8;
+        const int64_t m = i / k8n;
+        const int wo = (int)(m % Wo);
+        const int ho = (int)((m / Wo) % Ho);
+        const int n = (int)(m / ((int64_t)Wo * Ho));
+        uint4 out = make_uint4(0, 0, 0, 0);
+        if (vec) {
+            if (k0 < K) {
+                int tap = k0 / C, c = k0 - tap * C;
+                int r = tap / S, s = tap - r * S;
+                int hi = ho * stride - pad + r * dil, wi = wo * stride - pad + s * dil;
+                if (hi >= 0 && hi < H && wi >= 0 && wi < W)
+                    out = *reinterpret_cast<const uint4 *>(x + (((int64_t)n * H + hi) * W + wi) * ldx + c);
+            }
+        } else {
+            __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(&out);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int k = k0 + j;
+                if (k < K) {
+                    int tap = k / C, c = k - tap * C;
+                    int r = tap / S, s = tap - r * S;
+                    int hi = ho * stride - pad + r * dil, wi = wo * stride - pad + s * dil;
+                    if (hi >= 0 && hi < H && wi >= 0 && wi < W) o[j] = x[(((int64_t)n * H + hi) * W + wi) * ldx + c];
+                }
+            }
+        }
+        *reinterpret_cast<uint4 *>(a + m * kpad + k0) = out;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// BF16 tensor map over up to 4 dims (innermost first), 128B swizzle, zero OOB fill
+static int make_tmap(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box)
+{
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return HN_ERR_CUDA;
+    }
+    cuuint64_t gd[4];
+    cuuint64_t gs[3];
+    cuuint32_t bx[4], es[4];
+    for (int i = 0; i < rank; ++i) {
+        gd[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        if (i > 0) gs[i - 1] = strides_bytes[i];
+    }
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u]", (int)r, rank,
+                  (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+                  (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+        return HN_ERR_CUDA;
+    }
+    return HN_OK;
+}
+
+static bool implicit_ok(const hn_tensor *x, const hn_conv *cv)
+{
+    return cv->stride == 1 && x->c % 64 == 0 && x->ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x->ptr) & 15) == 0;
+}
+
+int64_t conv2d_tc_workspace(const hn_tensor *x, const hn_conv *cv)
+{
+    if (implicit_ok(x, cv)) return 0;
+    const int Ho = (x->h + 2 * cv->pad - cv->dil * (cv->r - 1) - 1) / cv->stride + 1;
+    const int Wo = (x->w + 2 * cv->pad - cv->dil * (cv->s - 1) - 1) / cv->stride + 1;
+    return (int64_t)x->n * Ho * Wo * hn_conv_kpad(x->c, cv->r, cv->s) * 2;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, int num_tiles, cudaStream_t st)
+{
+    constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * BLOCK_K * 2) + (2 * STAGES + 4) * 8 + 16 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        HN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    conv_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, st>>>(ta, tb, p);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn_epilogue *ep, const hn_tensor *y, void *ws,
+                  int64_t ws_bytes, cudaStream_t st)
+{
+    const int Ho = y->h, Wo = y->w;
+    const int64_t M = (int64_t)x->n * Ho * Wo;
+    if (M == 0) return HN_OK;
+    const int kpad = hn_conv_kpad(x->c, cv->r, cv->s);
+    const int cout_pad = hn_conv_cout_pad(cv->cout, HN_BF16);
+    HN_CHECK_ARG((reinterpret_cast<uintptr_t>(w) & 15) == 0, "conv_tc: packed weights must be 16-byte aligned");
+
+    TcParams p{};
+    CUtensorMap ta, tb;
+    const bool implicit = implicit_ok(x, cv);
+    const bool flat = !implicit || (cv->r == 1 && cv->s == 1 && cv->pad == 0);
+    if (flat) {
+        // A is a dense-or-strided [M][K] matrix: the NHWC view itself (1x1 s1) or the im2col workspace
+        const void *abase = x->ptr;
+        uint64_t lda = (uint64_t)x->ld;
+        int cblocks = x->c / 64;
+        if (!implicit) {
+            const int64_t need = conv2d_tc_workspace(x, cv);
+            if (!ws || ws_bytes < need) {
+                set_error("conv_tc: workspace of %lld bytes required, %lld given", (long long)need, (long long)ws_bytes);
+                return HN_ERR_WORKSPACE;
+            }
+            HN_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 127) == 0, "conv_tc: workspace must be 128-byte aligned");
+            const int64_t total = M * (kpad / 8);
+            int64_t want = cdiv(total, 256);
+            int grid = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
+            im2col_bf16_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x->ptr, x->ld, x->n, x->h, x->w, x->c, Ho, Wo, cv->r, cv->s,
+                                                    cv->stride, cv->pad, cv->dil, kpad, (__nv_bfloat16 *)ws);
+            HN_LAUNCH_CHECK();
+            abase = ws;
+            lda = (uint64_t)kpad;
+            cblocks = kpad / 64;
+        }
+        uint64_t dims[4] = {(uint64_t)cblocks * 64, (uint64_t)M, 1, 1};
+        uint64_t strides[4] = {2, lda * 2, lda * 2, lda * 2};   // dims 2,3 have extent 1
+        uint32_t box[4] = {64, 128, 1, 1};
+        int rc = make_tmap(&ta, abase, 4, dims, strides, box);
+        if (rc) return rc;
+        p.tiles_w = (int)cdiv(M, 128); p.tiles_h = 1; p.n_img = 1;
+        p.TH = 1; p.TW = 128; p.Ho = 1; p.Wo = (int)M;
+        HN_CHECK_ARG(M < (int64_t)1 << 31, "conv_tc: too many pixels");
+        p.R = 1; p.S = 1; p.pad = 0; p.dil = 1; p.cblocks = cblocks;
+    } else {
+        // spatial tile menu: minimise padded area, prefer squarer tiles (halo reuse in L2)
+        const int menu[5][2] = {{8, 16}, {4, 32}, {16, 8}, {2, 64}, {1, 128}};
+        int best = 0;
+        int64_t best_area = -1;
+        for (int i = 0; i < 5; ++i) {
+            int64_t area = cdiv(Ho, menu[i][0]) * menu[i][0] * cdiv(Wo, menu[i][1]) * menu[i][1];
+            if (best_area < 0 || area < best_area) { best_area = area; best = i; }
+        }
+        p.TH = menu[best][0]; p.TW = menu[best][1];
+        uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
+        uint64_t strides[4] = {2, (uint64_t)x->ld * 2, (uint64_t)x->ld * 2 * x->w, (uint64_t)x->ld * 2 * x->w * x->h};
+        uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+        int rc = make_tmap(&ta, x->ptr, 4, dims, strides, box);
+        if (rc) return rc;
+        p.tiles_w = (int)cdiv(Wo, p.TW); p.tiles_h = (int)cdiv(Ho, p.TH); p.n_img = x->n;
+        p.Ho = Ho; p.Wo = Wo;
+        p.R = cv->r; p.S = cv->s; p.pad = cv->pad; p.dil = cv->dil; p.cblocks = x->c / 64;
+    }
+    const int num_m_tiles = p.n_img * p.tiles_h * p.tiles_w;
+    // Cout tile: the widest of 256/128/64 that divides cout_pad and still leaves >= 2 tiles per SM
+    int bn;
+    if (cout_pad < 64) bn = cout_pad;   // 16 or 32
+    else {
+        bn = 64;
+        for (int cand : {256, 128}) {
+            if (cout_pad % cand == 0 && (int64_t)num_m_tiles * (cout_pad / cand) >= 2 * (int64_t)num_sms()) { bn = cand; break; }
+        }
+    }
+    p.n_tiles = cout_pad / bn;
+    p.Cout = cv->cout;
+    {
+        uint64_t dims[2] = {(uint64_t)kpad, (uint64_t)cout_pad};
+        uint64_t strides[2] = {2, (uint64_t)kpad * 2};
+        uint32_t box[2] = {64, (uint32_t)bn};
+        int rc = make_tmap(&tb, w, 2, dims, strides, box);
+        if (rc) return rc;
+    }
+    p.y = y->ptr; p.ldy = y->ld; p.y_f32 = (y->dtype == HN_F32);
+    p.scale = ep->scale; p.shift = ep->shift; p.res = ep->residual; p.ldr = ep->residual_ld;
+    p.act = ep->act; p.slope = ep->slope; p.slope_ptr = ep->slope_ptr;
+    const int num_tiles = num_m_tiles * p.n_tiles;
+    switch (bn) {
+        case 256: return launch_tc<256, 4>(ta, tb, p, num_tiles, st);
+        case 128: return launch_tc<128, 6>(ta, tb, p, num_tiles, st);
+        case 64: return launch_tc<64, 8>(ta, tb, p, num_tiles, st);
+        case 32: return launch_tc<32, 8>(ta, tb, p, num_tiles, st);
+        case 16: return launch_tc<16, 8>(ta, tb, p, num_tiles, st);
+    }
+    set_error("conv_tc: unsupported Cout tile %d", bn);
+    return HN_ERR_ARG;
+}
+
+}  // namespace hn

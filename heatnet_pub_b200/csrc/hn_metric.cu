@@ -1,0 +1,195 @@
+// iou_eval confusion matrix on the device (replaces the D2H + np.bincount of scripts/iou_eval.py:53-88
+// and the `max(1)` of :154-157).  HBM-bound integer work: 16 B/pixel on the label path, (4K+8) B/pixel on
+// the scores path.
+//
+// Counting scheme: no atomics in the hot loop.  Every warp owns a table  word[ceil(K*K/2)][32 lanes]  in
+// shared memory; lane L only ever touches column L (bank L), so the read-modify-write is conflict-free and
+// race-free.  One 32-bit word packs the 16-bit counters of bins 2j and 2j+1; a warp flushes its table to the
+// global int64 matrix (warp-shuffle reduction + one atomicAdd per bin) before any counter can overflow.
+#include "hn_common.cuh"
+
+namespace hn {
+
+constexpr int kMaxIterBeforeFlush = 16000;  // x2 pixels per lane per iteration x2 unroll < 65535
+
+__device__ __forceinline__ void count_pixel(uint32_t *table, int lane, long long p, long long t, int K, int &flags)
+{
+    bool pbad = (p < 0) | (p >= K);
+    bool tbad = (t < 0) | (t >= K);
+    if (pbad | tbad) {
+        flags |= (pbad ? 1 : 0) | (tbad ? 2 : 0);
+        return;
+    }
+    int bin = (int)t * K + (int)p;
+    uint32_t *w = table + (bin >> 1) * 32 + lane;
+    *w += (bin & 1) ? 0x10000u : 1u;
+}
+
+__device__ __forceinline__ void flush_table(uint32_t *table, int lane, int nwords, int nbins,
+                                            unsigned long long *conf)
+{
+    __syncwarp();
+    for (int j = 0; j < nwords; ++j) {
+        uint32_t v = table[j * 32 + lane];
+        table[j * 32 + lane] = 0;
+        uint32_t lo = v & 0xFFFFu, hi = v >> 16;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo += __shfl_xor_sync(0xffffffffu, lo, o);
+            hi += __shfl_xor_sync(0xffffffffu, hi, o);
+        }
+        if (lane == 0) {
+            if (lo) atomicAdd(conf + 2 * j, (unsigned long long)lo);
+            if (hi && 2 * j + 1 < nbins) atomicAdd(conf + 2 * j + 1, (unsigned long long)hi);
+        }
+    }
+    __syncwarp();
+}
+
+// label path: pred and target are int64 [n]
+__global__ void __launch_bounds__(256) confusion_labels_kernel(const long long *__restrict__ pred,
+                                                               const long long *__restrict__ target, long long n, int K,
+                                                               unsigned long long *conf, int *flags_out)
+{
+    extern __shared__ uint32_t smem[];
+    const int nbins = K * K, nwords = (nbins + 1) / 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *table = smem + warp * nwords * 32;
+    for (int j = 0; j < nwords; ++j) table[j * 32 + lane] = 0;
+    __syncwarp();
+
+    int flags = 0, iters = 0;
+    const long long nvec = n >> 1;  // pairs of pixels (16-byte loads)
+    const longlong2 *p2 = reinterpret_cast<const longlong2 *>(pred);
+    const longlong2 *t2 = reinterpret_cast<const longlong2 *>(target);
+    const long long gthreads = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // 2x unrolled: 4 independent 16-byte loads in flight per lane
+    for (; i + gthreads < nvec; i += 2 * gthreads) {
+        longlong2 pa = __ldg(p2 + i), ta = __ldg(t2 + i);
+        longlong2 pb = __ldg(p2 + i + gthreads), tb = __ldg(t2 + i + gthreads);
+        count_pixel(table, lane, pa.x, ta.x, K, flags);
+        count_pixel(table, lane, pa.y, ta.y, K, flags);
+        count_pixel(table, lane, pb.x, tb.x, K, flags);
+        count_pixel(table, lane, pb.y, tb.y, K, flags);
+        if (++iters == kMaxIterBeforeFlush) {
+            flush_table(table, lane, nwords, nbins, conf);
+            iters = 0;
+        }
+    }
+    for (; i < nvec; i += gthreads) {
+        longlong2 pa = __ldg(p2 + i), ta = __ldg(t2 + i);
+        count_pixel(table, lane, pa.x, ta.x, K, flags);
+        count_pixel(table, lane, pa.y, ta.y, K, flags);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) count_pixel(table, lane, pred[n - 1], target[n - 1], K, flags);
+    flush_table(table, lane, nwords, nbins, conf);
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if (lane == 0 && flags) atomicOr(flags_out, flags);
+}
+
+// scores path: NCHW FP32 [N][K][hw]; first-max argmax over K fused (torch max(1) tie rule)
+__global__ void __launch_bounds__(256) confusion_scores_kernel(const float *__restrict__ scores,
+                                                               const long long *__restrict__ target, long long n_images,
+                                                               long long hw, int K, unsigned long long *conf,
+                                                               int *flags_out)
+{
+    extern __shared__ uint32_t smem[];
+    const int nbins = K * K, nwords = (nbins + 1) / 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *table = smem + warp * nwords * 32;
+    for (int j = 0; j < nwords; ++j) table[j * 32 + lane] = 0;
+    __syncwarp();
+    int flags = 0, iters = 0;
+    const long long total = n_images * hw;
+    const long long gthreads = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gthreads) {
+        long long img = i / hw, px = i - img * hw;
+        const float *s = scores + img * K * hw + px;
+        float best = __ldg(s);
+        int arg = 0;
+        for (int k = 1; k < K; ++k) {
+            float v = __ldg(s + (long long)k * hw);
+            if (v > best) { best = v; arg = k; }
+        }
+        count_pixel(table, lane, arg, __ldg(target + i), K, flags);
+        if (++iters == 4 * kMaxIterBeforeFlush) {
+            flush_table(table, lane, nwords, nbins, conf);
+            iters = 0;
+        }
+    }
+    flush_table(table, lane, nwords, nbins, conf);
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if (lane == 0 && flags) atomicOr(flags_out, flags);
+}
+
+__global__ void __launch_bounds__(256) argmax_labels_kernel(const float *__restrict__ scores, long long n_images,
+                                                            long long hw, int K, uint8_t *out_u8, long long *out_i64)
+{
+    const long long total = n_images * hw;
+    const long long gthreads = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gthreads) {
+        long long img = i / hw, px = i - img * hw;
+        const float *s = scores + img * K * hw + px;
+        float best = __ldg(s);
+        int arg = 0;
+        for (int k = 1; k < K; ++k) {
+            float v = __ldg(s + (long long)k * hw);
+            if (v > best) { best = v; arg = k; }
+        }
+        if (out_u8) out_u8[i] = (uint8_t)arg;
+        if (out_i64) out_i64[i] = arg;
+    }
+}
+
+}  // namespace hn
+
+extern "C" int hn_confusion(const int64_t *pred_labels, const float *scores, int64_t n_images, int64_t hw,
+                            const int64_t *target, int32_t k, int64_t *conf, int32_t *flags, void *stream)
+{
+    using namespace hn;
+    HN_CHECK_ARG((pred_labels != nullptr) != (scores != nullptr), "hn_confusion: give exactly one of pred_labels / scores");
+    HN_CHECK_ARG(target && conf && flags, "hn_confusion: null pointer");
+    HN_CHECK_ARG(k >= 1 && k <= 32, "hn_confusion: K=%d outside [1,32]", k);
+    HN_CHECK_ARG(n_images >= 0 && hw >= 0, "hn_confusion: negative size");
+    const int64_t n = n_images * hw;
+    if (n == 0) return HN_OK;
+    const int nwords = (k * k + 1) / 2;
+    const int warps = 8;
+    const size_t smem = (size_t)warps * nwords * 32 * sizeof(uint32_t);
+    cudaStream_t st = (cudaStream_t)stream;
+    // one resident wave: grid = SMs x CTAs/SM that fit in shared memory
+    int per_sm = (int)((200 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    int64_t want = cdiv(scores ? n : cdiv(n, 2), 256);
+    int grid = (int)((want < (int64_t)num_sms() * per_sm) ? want : (int64_t)num_sms() * per_sm);
+    if (pred_labels) {
+        HN_CHECK_ARG((reinterpret_cast<uintptr_t>(pred_labels) | reinterpret_cast<uintptr_t>(target)) % 16 == 0,
+                     "hn_confusion: label pointers must be 16-byte aligned");
+        HN_CUDA(cudaFuncSetAttribute(confusion_labels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        confusion_labels_kernel<<<grid, 256, smem, st>>>((const long long *)pred_labels, (const long long *)target, n, k,
+                                                         (unsigned long long *)conf, flags);
+    } else {
+        HN_CUDA(cudaFuncSetAttribute(confusion_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        confusion_scores_kernel<<<grid, 256, smem, st>>>(scores, (const long long *)target, n_images, hw, k,
+                                                         (unsigned long long *)conf, flags);
+    }
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_argmax_labels(const float *scores, int64_t n_images, int64_t hw, int32_t k, uint8_t *out_u8,
+                                int64_t *out_i64, void *stream)
+{
+    using namespace hn;
+    HN_CHECK_ARG(scores && (out_u8 || out_i64), "hn_argmax_labels: null pointer");
+    HN_CHECK_ARG(k >= 1 && k <= 255, "hn_argmax_labels: K=%d", k);
+    const int64_t n = n_images * hw;
+    if (n == 0) return HN_OK;
+    int64_t want = cdiv(n, 256);
+    int grid = (int)((want < (int64_t)num_sms() * 8) ? want : (int64_t)num_sms() * 8);
+    argmax_labels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(scores, n_images, hw, k, out_u8, (long long *)out_i64);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}

@@ -1,0 +1,370 @@
+"""Host-side op layer over the C ABI: NHWC activation views, parameter caches and one Python function per
+kernel family.  torch is used for device memory (caching allocator), the current stream and parameter
+storage only; every FLOP on the path runs in libheatnet_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, HN_BF16, HN_F32, HnConv, HnEpilogue, HnTensor
+
+BN_EPS_DEFAULT = 1e-5
+_TORCH_DTYPE = {HN_F32: torch.float32, HN_BF16: torch.bfloat16}
+_HN_DTYPE = {torch.float32: HN_F32, torch.bfloat16: HN_BF16}
+
+DEFAULT_PRECISION = os.environ.get("HEATNET_B200_PRECISION", "bf16")
+
+# number of libheatnet_b200 kernels enqueued by this process (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def precision_dtype(precision: str) -> torch.dtype:
+    if precision == "bf16":
+        return torch.bfloat16
+    if precision == "fp32":
+        return torch.float32
+    raise ValueError("precision must be 'bf16' or 'fp32'")
+
+
+def refuse_autograd(module, *inputs):
+    """The forward-only entry points build no autograd graph: refuse loudly instead of dropping gradients."""
+    if not torch.is_grad_enabled():
+        return
+    if any(p.requires_grad for p in module.parameters()) or any(torch.is_tensor(t) and t.requires_grad for t in inputs):
+        raise NotImplementedError(
+            "heatnet_pub_b200: backward kernels are not wired into this entry point yet -- call under "
+            "torch.no_grad() (inference / validation), or freeze the parameters")
+
+
+class Act:
+    """NHWC activation view: `buf` is a dense [N, H, W, LD] tensor, the view covers channels
+    [coff, coff + c).  Channel slices of one buffer are how torch.cat(dim=1) becomes zero-copy."""
+    __slots__ = ("buf", "c", "coff")
+
+    def __init__(self, buf: torch.Tensor, c: Optional[int] = None, coff: int = 0):
+        assert buf.dim() == 4 and buf.is_contiguous() and buf.is_cuda
+        self.buf, self.coff = buf, coff
+        self.c = buf.shape[3] - coff if c is None else c
+
+    n = property(lambda s: s.buf.shape[0])
+    h = property(lambda s: s.buf.shape[1])
+    w = property(lambda s: s.buf.shape[2])
+    ld = property(lambda s: s.buf.shape[3])
+    dtype = property(lambda s: s.buf.dtype)
+
+    def ptr(self) -> int:
+        return self.buf.data_ptr() + self.coff * self.buf.element_size()
+
+    def hn(self) -> HnTensor:
+        return HnTensor(self.ptr(), _HN_DTYPE[self.buf.dtype], self.n, self.h, self.w, self.c, self.ld)
+
+    def slice(self, coff: int, c: int) -> "Act":
+        assert coff + c <= self.c
+        return Act(self.buf, c, self.coff + coff)
+
+    def nchw(self) -> torch.Tensor:
+        """Zero-copy NCHW-shaped (channels-last strided) torch view, the layout returned to callers."""
+        return self.buf[..., self.coff:self.coff + self.c].permute(0, 3, 1, 2)
+
+
+def new_act(n, h, w, c, dtype, device, ld=None) -> Act:
+    return Act(torch.empty((n, h, w, ld or c), dtype=dtype, device=device), c)
+
+
+def act_from_view(t: torch.Tensor) -> Optional[Act]:
+    """Recover the NHWC Act behind a tensor produced by Act.nchw() (no copy), else None."""
+    if t.dim() != 4 or not t.is_cuda or t.dtype not in _HN_DTYPE:
+        return None
+    n, c, h, w = t.shape
+    sn, sc, sh, sw = t.stride()
+    if sc != 1 or sw < c or sh != w * sw or sn != h * w * sw:
+        return None
+    base = t._base if t._base is not None else None
+    if base is None or base.dim() != 4 or not base.is_contiguous() or base.shape[:3] != (n, h, w) or base.shape[3] != sw:
+        return None
+    coff = (t.data_ptr() - base.data_ptr()) // t.element_size()
+    if coff < 0 or coff + c > sw:
+        return None
+    return Act(base, c, coff)
+
+
+# -------------------------------------------------------------------------------------------------- workspace
+_workspace = {}
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only scratch buffer per device; safe because every kernel is stream-ordered on one stream."""
+    key = torch.device(device).index
+    ws = _workspace.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = None
+        _workspace[key] = None
+        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspace[key] = ws
+    return ws
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+# -------------------------------------------------------------------------------------------------- layout
+def from_nchw(t: torch.Tensor, dtype: torch.dtype, out: Optional[Act] = None) -> Act:
+    """User NCHW tensor -> NHWC Act of the compute dtype (zero-copy when it already is one of our views and
+    no destination slice is given)."""
+    _lib.require_device()
+    if out is None:
+        a = act_from_view(t)
+        if a is not None and a.dtype == dtype:
+            return a
+    src = t.detach()
+    if src.dtype != torch.float32 or not src.is_contiguous():
+        src = src.float().contiguous()
+    n, c, h, w = src.shape
+    if out is None:
+        out = new_act(n, h, w, c, dtype, src.device)
+    assert (out.n, out.h, out.w, out.c) == (n, h, w, c) and out.dtype == dtype
+    _lib.check(_lib.load().hn_nchw_to_nhwc(src.data_ptr(), C.byref(out.hn()), _stream()))
+    _count()
+    return out
+
+
+def fuse_inputs(modal_1: torch.Tensor, modal_2: Optional[torch.Tensor], dtype: torch.dtype) -> Act:
+    """Early fusion: torch.cat([modal_1, modal_2], 1) (cm/models/extractors.py:173) done by converting both
+    NCHW inputs straight into channel slices of one NHWC buffer."""
+    if modal_2 is None:
+        return from_nchw(modal_1, dtype)
+    n, c1, h, w = modal_1.shape
+    c2 = modal_2.shape[1]
+    cat = new_act(n, h, w, c1 + c2, dtype, modal_1.device)
+    from_nchw(modal_1, dtype, cat.slice(0, c1))
+    from_nchw(modal_2, dtype, cat.slice(c1, c2))
+    return cat
+
+
+def to_nchw_f32(a: Act) -> torch.Tensor:
+    out = torch.empty((a.n, a.c, a.h, a.w), dtype=torch.float32, device=a.buf.device)
+    _lib.check(_lib.load().hn_nhwc_to_nchw(C.byref(a.hn()), out.data_ptr(), _stream()))
+    _count()
+    return out
+
+
+# -------------------------------------------------------------------------------------------------- parameter caches
+def _versions(*tensors):
+    return tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors)
+
+
+def packed_weight(conv: torch.nn.Conv2d, dtype: torch.dtype) -> torch.Tensor:
+    """K-major pack [cout_pad][kpad] of the OIHW FP32 master weight, cached until the parameter changes."""
+    lib = _lib.load()
+    cache = conv.__dict__.setdefault("_hn_wcache", {})
+    key = (dtype, conv.weight.device)
+    ver = _versions(conv.weight)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    w = conv.weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    cout, cin, r, s = w.shape
+    hdt = _HN_DTYPE[dtype]
+    cout_pad, kpad = lib.hn_conv_cout_pad(cout, hdt), lib.hn_conv_kpad(cin, r, s)
+    dst = torch.empty((cout_pad, kpad), dtype=dtype, device=w.device)
+    _lib.check(lib.hn_pack_weight(w.data_ptr(), dst.data_ptr(), hdt, cout, cin, r, s, cout_pad, kpad, _stream()))
+    _count()
+    cache[key] = (ver, dst)
+    return dst
+
+
+def folded_affine(conv: torch.nn.Conv2d, bn: Optional[torch.nn.BatchNorm2d]):
+    """(scale, shift) FP32 vectors for the conv epilogue: BatchNorm2d(eval) and the conv bias folded;
+    (None, None) when the conv has neither."""
+    bias = conv.bias
+    if bn is None and bias is None:
+        return None, None
+    cache = conv.__dict__.setdefault("_hn_acache", {})
+    if bn is not None:
+        ver = _versions(bn.weight, bn.bias, bn.running_mean, bn.running_var, bias)
+    else:
+        ver = _versions(bias)
+    hit = cache.get("fold")
+    if hit is not None and hit[0] == ver:
+        return hit[1], hit[2]
+    cch = conv.out_channels
+    dev = conv.weight.device
+    scale = torch.empty(cch, dtype=torch.float32, device=dev)
+    shift = torch.empty(cch, dtype=torch.float32, device=dev)
+    p = lambda t: t.detach().data_ptr() if t is not None else None
+    if bn is not None:
+        rc = _lib.load().hn_bn_fold(p(bn.weight), p(bn.bias), p(bn.running_mean), p(bn.running_var), p(bias),
+                                    float(bn.eps), scale.data_ptr(), shift.data_ptr(), cch, _stream())
+    else:
+        rc = _lib.load().hn_bn_fold(None, None, None, None, p(bias), BN_EPS_DEFAULT, scale.data_ptr(), shift.data_ptr(),
+                                    cch, _stream())
+    _lib.check(rc)
+    _count()
+    cache["fold"] = (ver, scale, shift)
+    return scale, shift
+
+
+# -------------------------------------------------------------------------------------------------- ops
+def conv_out_hw(h, w, conv: torch.nn.Conv2d):
+    k, s, p, d = conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0]
+    return (h + 2 * p - d * (k - 1) - 1) // s + 1, (w + 2 * p - d * (k - 1) - 1) // s + 1
+
+
+def _epilogue(scale, shift, residual: Optional[Act], act, slope, slope_ptr) -> HnEpilogue:
+    ep = HnEpilogue()
+    ep.scale = scale.data_ptr() if scale is not None else None
+    ep.shift = shift.data_ptr() if shift is not None else None
+    if residual is not None:
+        ep.residual, ep.residual_ld = residual.ptr(), residual.ld
+    ep.act, ep.slope = act, float(slope)
+    ep.slope_ptr = slope_ptr.detach().data_ptr() if slope_ptr is not None else None
+    return ep
+
+
+def conv2d(x: Act, conv: torch.nn.Conv2d, scale=None, shift=None, residual: Optional[Act] = None, act=ACT_NONE,
+           slope=0.0, slope_ptr=None, out: Optional[Act] = None, out_dtype=None) -> Act:
+    """y = act(conv(x) * scale + shift + residual) in one launch (plus an im2col gather for strided /
+    small-Cin shapes on the BF16 path)."""
+    lib = _lib.load()
+    assert conv.groups == 1 and conv.kernel_size[0] == conv.kernel_size[1] and conv.stride[0] == conv.stride[1]
+    assert conv.padding[0] == conv.padding[1] and conv.dilation[0] == conv.dilation[1]
+    if x.c != conv.in_channels:
+        raise RuntimeError(f"expected input with {conv.in_channels} channels, got {x.c}")
+    ho, wo = conv_out_hw(x.h, x.w, conv)
+    if ho < 1 or wo < 1:
+        raise RuntimeError(f"Calculated padded input size per channel: ({x.h + 2 * conv.padding[0]} x "
+                           f"{x.w + 2 * conv.padding[0]}). Kernel size: {tuple(conv.kernel_size)}. "
+                           "Kernel size can't be greater than actual input size")
+    if out is None:
+        out = new_act(x.n, ho, wo, conv.out_channels, out_dtype or x.dtype, x.buf.device)
+    assert (out.n, out.h, out.w, out.c) == (x.n, ho, wo, conv.out_channels)
+    if residual is not None:
+        assert residual.dtype == out.dtype and (residual.n, residual.h, residual.w, residual.c) == (out.n, out.h, out.w, out.c)
+    wp = packed_weight(conv, x.dtype)
+    cv = HnConv(conv.out_channels, conv.kernel_size[0], conv.kernel_size[1], conv.stride[0], conv.padding[0],
+                conv.dilation[0])
+    xh, yh = x.hn(), out.hn()
+    ws_bytes = lib.hn_conv2d_workspace_bytes(C.byref(xh), C.byref(cv))
+    ws_ptr = None
+    if ws_bytes:
+        ws_ptr = workspace(ws_bytes, x.buf.device).data_ptr()
+        _count()
+    ep = _epilogue(scale, shift, residual, act, slope, slope_ptr)
+    _lib.check(lib.hn_conv2d_fwd(C.byref(xh), wp.data_ptr(), C.byref(cv), C.byref(ep), C.byref(yh), ws_ptr, ws_bytes,
+                                 _stream()))
+    _count()
+    return out
+
+
+def affine_act(x: Act, scale, shift, residual: Optional[Act], act, slope=0.0, slope_ptr=None, out: Optional[Act] = None) -> Act:
+    out = out or x
+    ep = _epilogue(scale, shift, residual, act, slope, slope_ptr)
+    _lib.check(_lib.load().hn_affine_act(C.byref(x.hn()), C.byref(ep), C.byref(out.hn()), _stream()))
+    _count()
+    return out
+
+
+def batchnorm_train_affine(x: Act, bn: torch.nn.BatchNorm2d):
+    """Batch statistics of x (FP64 accumulation) -> (scale, shift) for the apply pass; updates the module's
+    running statistics exactly like nn.BatchNorm2d in train mode (momentum, unbiased variance,
+    num_batches_tracked)."""
+    lib = _lib.load()
+    dev = x.buf.device
+    sums = torch.empty((2, x.c), dtype=torch.float64, device=dev)
+    _lib.check(lib.hn_channel_stats(C.byref(x.hn()), sums[0].data_ptr(), sums[1].data_ptr(), _stream()))
+    _count(3)
+    out = torch.empty((4, x.c), dtype=torch.float32, device=dev)     # scale, shift, save_mean, save_invstd
+    track = bn.track_running_stats and bn.running_mean is not None
+    momentum = 0.0
+    if track:
+        bn.num_batches_tracked.add_(1)
+        momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked.item())
+    p = lambda t: t.detach().data_ptr() if t is not None else None
+    _lib.check(lib.hn_bn_finalize(sums[0].data_ptr(), sums[1].data_ptr(), x.n * x.h * x.w, p(bn.weight), p(bn.bias),
+                                  float(bn.eps), float(momentum), p(bn.running_mean) if track else None,
+                                  p(bn.running_var) if track else None, out[0].data_ptr(), out[1].data_ptr(),
+                                  out[2].data_ptr(), out[3].data_ptr(), x.c, _stream()))
+    _count()
+    if track:   # in-place kernel writes bypass torch's version counter; bump it so folded caches refresh
+        bn.running_mean.add_(0)
+        bn.running_var.add_(0)
+    return out[0], out[1], out[2], out[3]
+
+
+def conv_bn_act(x: Act, conv, bn, act=ACT_NONE, slope=0.0, slope_ptr=None, residual: Optional[Act] = None,
+                out: Optional[Act] = None, bn_training: Optional[bool] = None) -> Act:
+    """conv -> BatchNorm2d -> (+residual) -> activation.
+    eval BN: folded into the conv epilogue (1 launch).  train BN: conv (+bias) -> batch statistics -> one fused
+    normalise + residual + activation pass in place."""
+    if bn_training is None:      # like nn.BatchNorm2d: batch statistics iff the BN module itself is in train mode
+        bn_training = bn is not None and (bn.training or bn.running_mean is None)
+    if bn is None or not bn_training:
+        scale, shift = folded_affine(conv, bn)
+        return conv2d(x, conv, scale, shift, residual, act, slope, slope_ptr, out)
+    scale, shift = folded_affine(conv, None)                      # conv bias only
+    y = conv2d(x, conv, scale, shift, None, ACT_NONE, out=out)
+    bscale, bshift, _, _ = batchnorm_train_affine(y, bn)
+    return affine_act(y, bscale, bshift, residual, act, slope, slope_ptr)
+
+
+def maxpool3x3s2(x: Act, out: Optional[Act] = None) -> Act:
+    ho, wo = (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1
+    out = out or new_act(x.n, ho, wo, x.c, x.dtype, x.buf.device)
+    _lib.check(_lib.load().hn_maxpool3x3s2_fwd(C.byref(x.hn()), C.byref(out.hn()), _stream()))
+    _count()
+    return out
+
+
+def pyramid_pool(x: Act, sizes: Sequence[int]):
+    """All adaptive average pools of the PSP module in one pass -> list of dense Acts [N, s, s, C]."""
+    lib = _lib.load()
+    arr = (C.c_int32 * len(sizes))(*sizes)
+    nb = sum(s * s for s in sizes)
+    out = torch.empty((x.n * nb * x.c,), dtype=x.dtype, device=x.buf.device)
+    xh = x.hn()
+    ws_bytes = lib.hn_pyramid_pool_workspace_bytes(C.byref(xh), arr, len(sizes))
+    ws = workspace(ws_bytes, x.buf.device)
+    _lib.check(lib.hn_pyramid_pool_fwd(C.byref(xh), arr, len(sizes), out.data_ptr(), ws.data_ptr(), ws_bytes, _stream()))
+    _count(2)
+    acts, off = [], 0
+    for s in sizes:
+        cnt = x.n * s * s * x.c
+        acts.append(Act(out[off:off + cnt].view(x.n, s, s, x.c)))
+        off += cnt
+    return acts
+
+
+def bilinear(x: Act, h: int, w: int, out: Optional[Act] = None, out_dtype=None) -> Act:
+    out = out or new_act(x.n, h, w, x.c, out_dtype or x.dtype, x.buf.device)
+    assert (out.n, out.h, out.w, out.c) == (x.n, h, w, x.c)
+    _lib.check(_lib.load().hn_bilinear_fwd(C.byref(x.hn()), C.byref(out.hn()), _stream()))
+    _count()
+    return out
+
+
+def dropout2d(x: Act, p: float, mask: Optional[torch.Tensor] = None) -> Act:
+    """nn.Dropout2d in train mode: whole channels of each image zeroed with probability p, survivors scaled by
+    1/(1-p).  `mask` (N, C) of {0,1} keep flags may be injected for parity runs; otherwise it is drawn from
+    torch's CUDA generator (the reference's exact RNG stream cannot be reproduced by any other kernel)."""
+    if mask is None:
+        mask = torch.rand((x.n, x.c), device=x.buf.device) >= p
+    scale = (mask.to(device=x.buf.device, dtype=torch.float32) * (1.0 / (1.0 - p))).contiguous()
+    ep = _epilogue(scale, None, None, ACT_NONE, 0.0, None)
+    ep.per_image = 1
+    out = new_act(x.n, x.h, x.w, x.c, x.dtype, x.buf.device)
+    _lib.check(_lib.load().hn_affine_act(C.byref(x.hn()), C.byref(ep), C.byref(out.hn()), _stream()))
+    _count()
+    return out

@@ -1,0 +1,158 @@
+"""PSPNet pyramid-pooling head and PSPUpsample decoder on the B200 kernel library.
+
+Host-side mirror of the reference's `models/pspnet.py` (top level, RGB, `forward(x) -> logits`) and
+`models/confusion_maximization/models/pspnet.py` (HeatNet, `forward(modal_1, modal_2) ->
+(logits, [logits, x5, x4, x3, x2, x1], None)`): same class names, constructor arguments, attribute
+names and state_dict.  Reference: cm/models/pspnet.py:8-76, models/pspnet.py:8-75.
+"""
+import torch
+from torch import nn
+
+from . import engine as E
+from . import extractors
+from .engine import ACT_LEAKY, ACT_NONE, ACT_RELU, Act
+from .extractors import _KernelModule
+
+
+class PSPModule(_KernelModule):
+    """cm/models/pspnet.py:8-25.  One pass over the features produces all pyramid bins; each prior is
+    upsampled straight into its channel slice of the (features*(len(sizes)+1))-channel buffer the encoder's
+    last block also wrote into, so the 10240-channel torch.cat never happens; bias + ReLU sit in the
+    bottleneck GEMM's epilogue."""
+
+    def __init__(self, features, out_features=1024, sizes=(1, 2, 3, 6)):
+        super().__init__()
+        self.stages = []
+        self.stages = nn.ModuleList([self._make_stage(features, size) for size in sizes])
+        self.bottleneck = nn.Conv2d(features * (len(sizes) + 1), out_features, kernel_size=1)
+        self.relu = nn.ReLU()
+
+    def _make_stage(self, features, size):
+        prior = nn.AdaptiveAvgPool2d(output_size=(size, size))
+        conv = nn.Conv2d(features, features, kernel_size=1, bias=False)
+        return nn.Sequential(prior, conv)
+
+    def sizes(self):
+        out = []
+        for st in self.stages:
+            s = st[0].output_size
+            s = s if isinstance(s, int) else s[0]
+            out.append(int(s))
+        return out
+
+    def alloc_cat(self, n, h, w, dtype, device) -> Act:
+        return E.new_act(n, h, w, self.bottleneck.in_channels, dtype, device)
+
+    def feats_slice(self, cat: Act) -> Act:
+        f = self.stages[0][1].in_channels
+        return cat.slice(len(self.stages) * f, f)
+
+    def _run_cat(self, cat: Act) -> Act:
+        """`cat` already holds the features in its last channel slice."""
+        feats = self.feats_slice(cat)
+        f = feats.c
+        pooled = E.pyramid_pool(feats, self.sizes())
+        for i, st in enumerate(self.stages):
+            prior = E.conv2d(pooled[i], st[1])
+            E.bilinear(prior, cat.h, cat.w, out=cat.slice(i * f, f))
+        scale, shift = E.folded_affine(self.bottleneck, None)
+        return E.conv2d(cat, self.bottleneck, scale, shift, act=ACT_RELU)
+
+    def _run(self, feats: Act) -> Act:
+        cat = self.alloc_cat(feats.n, feats.h, feats.w, feats.dtype, feats.buf.device)
+        dst = self.feats_slice(cat)
+        dst.buf[..., dst.coff:dst.coff + dst.c].copy_(feats.nchw().permute(0, 2, 3, 1))   # stand-alone use only
+        return self._run_cat(cat)
+
+
+class PSPUpsample(_KernelModule):
+    """cm/models/pspnet.py:28-40: bilinear 2x -> 3x3 conv (+bias) -> BN -> PReLU."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.conv = nn.Sequential(
+            nn.Conv2d(in_channels, out_channels, 3, padding=1),
+            nn.BatchNorm2d(out_channels),
+            nn.PReLU()
+        )
+
+    def _run(self, x: Act) -> Act:
+        p = E.bilinear(x, 2 * x.h, 2 * x.w)
+        return E.conv_bn_act(p, self.conv[0], self.conv[1], ACT_LEAKY, slope_ptr=self.conv[2].weight)
+
+
+class PSPNet(_KernelModule):
+    """HeatNet PSPNet, cm/models/pspnet.py:43-76."""
+
+    def __init__(self, n_classes=13, sizes=(1, 2, 3, 6), psp_size=2048, deep_features_size=1024, backend='resnet34',
+                 pretrained=True, late_fusion=False, in_channels=3):
+        super().__init__()
+        self.feats = getattr(extractors, backend)(pretrained, late_fusion=late_fusion, in_channels=in_channels)
+        self.psp = PSPModule(psp_size, 1024, sizes)
+        self.drop_1 = nn.Dropout2d(p=0.3)
+
+        self.up_1 = PSPUpsample(1024, 256)
+        self.up_2 = PSPUpsample(256, 64)
+        self.up_3 = PSPUpsample(64, 64)
+
+        self.drop_2 = nn.Dropout2d(p=0.15)
+        self.final = nn.Sequential(
+            nn.Conv2d(64, n_classes, kernel_size=1)
+        )
+
+    def set_precision(self, precision: str):
+        """'bf16' (tcgen05 tensor-core convolutions) or 'fp32' (CUDA-core parity path, 1e-4 vs the reference)."""
+        E.precision_dtype(precision)
+        for m in self.modules():
+            if isinstance(m, _KernelModule):
+                m.precision = precision
+        return self
+
+    def _dropout(self, p: Act, drop: nn.Dropout2d) -> Act:
+        if not (drop.training and drop.p > 0.0):
+            return p
+        masks = getattr(self, "_injected_dropout_masks", None)
+        return E.dropout2d(p, drop.p, masks.pop(0) if masks else None)
+
+    def _run_full(self, m1: Act, m2: Act = None):
+        h8, w8 = self._h8w8(m1.h, m1.w)
+        cat = self.psp.alloc_cat(m1.n, h8, w8, m1.dtype, m1.buf.device)
+        f = self.feats._run_taps(m1, m2, x5_out=self.psp.feats_slice(cat))
+        p = self.psp._run_cat(cat)
+        p = self._dropout(p, self.drop_1)
+        p = self.up_1._run(p)
+        p = self._dropout(p, self.drop_2)
+        p = self.up_2._run(p)
+        p = self._dropout(p, self.drop_2)
+        p = self.up_3._run(p)
+        p = self._dropout(p, self.drop_2)
+        fin = self.final[0]
+        scale, shift = E.folded_affine(fin, None)
+        # logits are produced in FP32 on both paths (NHWC, channel stride padded to a multiple of 8)
+        logits = E.new_act(p.n, p.h, p.w, fin.out_channels, torch.float32, p.buf.device, ld=(fin.out_channels + 7) // 8 * 8)
+        E.conv2d(p, fin, scale, shift, out=logits)
+        return logits, f
+
+    def _h8w8(self, h, w):
+        h2, w2 = E.conv_out_hw(h, w, self.feats.conv1)
+        h4, w4 = (h2 - 1) // 2 + 1, (w2 - 1) // 2 + 1
+        st = self.feats.layer2[0].stride
+        return (h4 - 1) // st + 1, (w4 - 1) // st + 1
+
+    def forward(self, modal_1, modal_2=None):
+        E.refuse_autograd(self, modal_1, modal_2)
+        m1, m2 = self.feats._inputs(modal_1, modal_2)
+        logits, f = self._run_full(m1, m2)
+        out = E.to_nchw_f32(logits)                       # the reference's NCHW FP32 logits
+        return out, [out, f[0].nchw(), f[1].nchw(), f[2].nchw(), f[3].nchw(), f[4].nchw()], None
+
+
+class PSPNetRGB(PSPNet):
+    """Top-level models/pspnet.py:43-75 signature: `PSPNet(n_classes=18, ..., pretrained=True)`, `forward(x) -> logits`."""
+
+    def __init__(self, n_classes=18, sizes=(1, 2, 3, 6), psp_size=2048, deep_features_size=1024, backend='resnet34',
+                 pretrained=True):
+        super().__init__(n_classes, sizes, psp_size, deep_features_size, backend, pretrained, late_fusion=False, in_channels=3)
+
+    def forward(self, x):
+        return super().forward(x)[0]

@@ -1,0 +1,136 @@
+/* heatnet_b200.h -- C ABI of libheatnet_b200.so: the B200 (sm_100a) kernels behind HeatNet's
+ * dense-segmentation hot path.
+ *
+ * The reference (jzuern/heatnet-pub) has no FFI: every op below is a PyTorch library call made from
+ * Python modules.  Each entry point names the reference call site(s) it replaces (paths relative to the
+ * reference root; "cm/" = models/confusion_maximization/).  The Python host in heatnet_pub_b200/ binds
+ * these with ctypes; no torch types cross this boundary.
+ *
+ * Conventions
+ *  - every function returns 0 on success and a negative code on failure; hn_last_error() returns a
+ *    thread-local message for the last failure on the calling thread.
+ *  - all device pointers are borrowed for the duration of the call; the library allocates no device
+ *    memory.  Kernels are enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises.
+ *  - activations are NHWC ("pixel-major") views: element (n,h,w,c) lives at
+ *        ptr + (((n*H + h)*W + w) * ld + c) * sizeof(dtype)
+ *    where `ld` >= C is the channel count of the underlying buffer, so a view can be a channel slice of
+ *    a wider buffer (this is how torch.cat(dim=1) in cm/models/extractors.py:192-196 and
+ *    cm/models/pspnet.py:24 becomes zero-copy).
+ */
+#ifndef HEATNET_B200_H
+#define HEATNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { HN_F32 = 0, HN_BF16 = 1 };
+enum { HN_ACT_NONE = 0, HN_ACT_RELU = 1, HN_ACT_LEAKY = 2 /* y = x>=0 ? x : slope*x (LeakyReLU, PReLU) */ };
+enum {
+    HN_OK = 0,
+    HN_ERR_ARG = -1,      /* invalid argument / unsupported shape */
+    HN_ERR_CUDA = -2,     /* CUDA runtime or driver error */
+    HN_ERR_WORKSPACE = -3 /* workspace too small */
+};
+
+typedef struct hn_tensor {
+    void *ptr;     /* device pointer to element (0,0,0,0) of the view */
+    int32_t dtype; /* HN_F32 or HN_BF16 */
+    int32_t n, h, w, c;
+    int32_t ld;    /* channel stride of the underlying NHWC buffer (>= c) */
+} hn_tensor;
+
+/* Fused conv epilogue: y = act(acc * scale[k] + shift[k] + residual).  Replaces the separate
+ * BatchNorm2d(eval) / bias / `out += residual` / ReLU / PReLU / LeakyReLU launches of
+ * cm/models/extractors.py:85-101, cm/models/pspnet.py:25,32-34, cm/discriminator_model.py:51-59. */
+typedef struct hn_epilogue {
+    const float *scale;     /* [Cout] or NULL (1) */
+    const float *shift;     /* [Cout] or NULL (0) */
+    const void *residual;   /* NHWC view with the output's dtype/shape, or NULL */
+    int32_t residual_ld;
+    int32_t act;            /* HN_ACT_* */
+    float slope;            /* used when slope_ptr == NULL */
+    const float *slope_ptr; /* device scalar (PReLU weight), optional */
+    int32_t out_nchw;       /* 1: y is written as NCHW FP32 (the reference's logits layout) */
+    float *stat_sum;        /* optional [Cout] FP32: += sum over pixels of the PRE-activation value ... */
+    float *stat_sqsum;      /* ... and of its square (BatchNorm2d batch statistics in train mode) */
+    int32_t per_image;      /* hn_affine_act only: scale (and shift, if given) are [N][C] -- Dropout2d channel masks */
+} hn_epilogue;
+
+typedef struct hn_conv {
+    int32_t cout, r, s, stride, pad, dil;
+} hn_conv;
+
+const char *hn_last_error(void);
+int hn_version(void);
+/* SM count / cc of the current device; fails (HN_ERR_CUDA) without a usable sm_100 device. */
+int hn_device_check(void);
+
+/* ---- layout + parameter preparation (no reference counterpart: the reference keeps NCHW/OIHW) ---- */
+/* NCHW FP32 (user tensors) -> NHWC view. */
+int hn_nchw_to_nhwc(const float *src, const hn_tensor *dst, void *stream);
+/* NHWC view -> dense NCHW FP32. */
+int hn_nhwc_to_nchw(const hn_tensor *src, float *dst, void *stream);
+/* OIHW FP32 conv weight -> K-major pack [cout_pad][kpad], k = (r*S + s)*Cin + c, zero padded.
+ * dtype HN_BF16 (tensor-core path) or HN_F32 (FP32 parity path). */
+int hn_pack_weight(const float *w_oihw, void *dst, int32_t dtype, int32_t cout, int32_t cin, int32_t r, int32_t s,
+                   int32_t cout_pad, int32_t kpad, void *stream);
+/* BatchNorm2d(eval) + conv bias folded to per-channel scale/shift:
+ * scale = gamma/sqrt(var+eps), shift = beta + (bias - mean)*scale.  gamma==NULL => plain bias. */
+int hn_bn_fold(const float *gamma, const float *beta, const float *mean, const float *var, const float *bias,
+               float eps, float *scale, float *shift, int32_t c, void *stream);
+
+/* ---- convolution (replaces nn.Conv2d forward: cm/models/extractors.py:71-76,111-123,
+ *      cm/models/pspnet.py:13,18,32,57, cm/discriminator_model.py:40-44) ---- */
+/* rows of the packed weight matrix: FP32 pack -> multiple of 64; BF16 pack -> 16/32/64 or a multiple of 64 */
+int32_t hn_conv_cout_pad(int32_t cout, int32_t dtype);
+int32_t hn_conv_kpad(int32_t cin, int32_t r, int32_t s);
+/* bytes of scratch hn_conv2d_fwd needs for this problem (0 for the implicit-GEMM cases) */
+int64_t hn_conv2d_workspace_bytes(const hn_tensor *x, const hn_conv *cv);
+/* BF16 x / BF16 packed weights -> tcgen05 implicit GEMM (FP32 accumulate in TMEM);
+ * FP32 x / FP32 packed weights -> FP32 CUDA-core implicit GEMM (the 1e-4 parity path). */
+int hn_conv2d_fwd(const hn_tensor *x, const void *w_packed, const hn_conv *cv, const hn_epilogue *ep,
+                  const hn_tensor *y, void *workspace, int64_t workspace_bytes, void *stream);
+
+/* ---- bandwidth-bound ops ---- */
+/* nn.MaxPool2d(3,2,1): cm/models/extractors.py:128 */
+int hn_maxpool3x3s2_fwd(const hn_tensor *x, const hn_tensor *y, void *stream);
+/* the four nn.AdaptiveAvgPool2d(s), s in sizes[0..nsizes), in one pass over x (cm/models/pspnet.py:17).
+ * out (x's dtype): one dense NHWC block [N][s][s][C] per size, concatenated in the order of `sizes`,
+ * i.e. size a starts at element N * C * sum_{b<a} s_b^2.  workspace: FP32 row partials. */
+int64_t hn_pyramid_pool_workspace_bytes(const hn_tensor *x, const int32_t *sizes, int32_t nsizes);
+int hn_pyramid_pool_fwd(const hn_tensor *x, const int32_t *sizes, int32_t nsizes, void *out, void *workspace,
+                        int64_t workspace_bytes, void *stream);
+/* F.upsample(mode='bilinear') == interpolate(align_corners=False): cm/models/pspnet.py:23,39,
+ * cm/discriminator_model.py:47.  x and y may differ in dtype. */
+int hn_bilinear_fwd(const hn_tensor *x, const hn_tensor *y, void *stream);
+/* per-channel affine + residual + activation over an NHWC view (BatchNorm2d apply in train mode; with
+ * per_image=1 and shift=NULL the nn.Dropout2d channel mask of cm/models/pspnet.py:64-73):
+ * y = act(x*scale[c] + shift[c] + residual) */
+int hn_affine_act(const hn_tensor *x, const hn_epilogue *ep, const hn_tensor *y, void *stream);
+/* per-channel sum / sum of squares over all pixels (BatchNorm2d batch statistics), FP64 accumulators */
+int hn_channel_stats(const hn_tensor *x, double *sum, double *sqsum, void *stream);
+/* train-mode BatchNorm2d finalize (cm/models/extractors.py:72-77): from FP64 sums over `count` pixels
+ * computes scale/shift for the apply pass and updates running_mean/var (momentum, unbiased var). */
+int hn_bn_finalize(const double *sum, const double *sqsum, int64_t count, const float *gamma, const float *beta,
+                   float eps, float momentum, float *running_mean, float *running_var, float *scale, float *shift,
+                   float *save_mean, float *save_invstd, int32_t c, void *stream);
+
+/* ---- metric: scripts/iou_eval.py:53-88,154-159 (max(1) + np.bincount(pred + K*target) on the host) ---- */
+/* pred_labels: int64 [n_pixels] class ids, or NULL when `scores` (NCHW FP32 [N][K][HW]) is given, in which
+ * case the first-max argmax over K is fused.  conf: device int64 [K*K], row = target, col = predicted,
+ * ACCUMULATED into.  flags: device int32 [1], bit0 set if any pred outside [0,K), bit1 if any target is
+ * (the reference's range asserts, iou_eval.py:58-79); out-of-range pixels are not counted. */
+int hn_confusion(const int64_t *pred_labels, const float *scores, int64_t n_images, int64_t hw,
+                 const int64_t *target, int32_t k, int64_t *conf, int32_t *flags, void *stream);
+/* argmax over classes of NCHW FP32 scores -> uint8 / int64 label map (validation_bdd_mf.py:331) */
+int hn_argmax_labels(const float *scores, int64_t n_images, int64_t hw, int32_t k, uint8_t *out_u8,
+                     int64_t *out_i64, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEATNET_B200_H */

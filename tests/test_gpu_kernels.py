@@ -1,0 +1,342 @@
+"""Per-kernel parity on a B200: every C-ABI entry point against the oracle (plain-C / torch-functional CPU
+restatements) on seeded inputs.  Integer work is bit-exact; FP32 kernels within 1e-4 relative (the north
+star's FP32 bound, written next to each check); BF16 tensor-core convs within 2e-2 of the FP32 oracle and
+within 1e-3 of an FP32 evaluation on the same BF16-rounded operands."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def E():
+    from heatnet_pub_b200 import engine
+    from heatnet_pub_b200 import _lib
+    _lib.require_device()
+    return engine
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def to_act(E, t, dtype):
+    return E.from_nchw(t.cuda(), dtype)
+
+
+def back(act):
+    return act.nchw().float().cpu()
+
+
+# ------------------------------------------------------------------------------------------------ layout
+@pytest.mark.parametrize("shape", [(2, 3, 17, 23), (1, 1, 8, 8), (2, 13, 9, 31), (1, 64, 5, 7), (2, 100, 33, 4)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_layout_roundtrip(E, shape, dtype):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(shape, generator=g)
+    a = to_act(E, x, dtype)
+    want = x.to(dtype).float()
+    assert torch.equal(back(a), want)
+    assert torch.equal(E.to_nchw_f32(a).cpu(), want)
+
+
+# ------------------------------------------------------------------------------------------------ convolution
+CONV_CASES = [
+    # cin, cout, k, stride, pad, dil, h, w, bias        (layer classes of SURVEY.md appendix A)
+    (64, 64, 1, 1, 0, 1, 20, 24, False),      # layer1 conv1
+    (64, 256, 1, 1, 0, 1, 20, 24, False),     # layer1 conv3
+    (128, 128, 3, 1, 1, 1, 10, 12, False),    # 3x3 d1
+    (256, 256, 3, 1, 2, 2, 10, 13, False),    # layer3 3x3 d2 (ragged width)
+    (512, 512, 3, 1, 4, 4, 11, 12, False),    # layer4 3x3 d4 (ragged height)
+    (128, 128, 3, 2, 1, 1, 21, 24, False),    # layer2.0 conv2 stride 2, odd height
+    (256, 512, 1, 2, 0, 1, 21, 24, False),    # layer2.0 downsample stride 2
+    (3, 64, 7, 2, 3, 1, 33, 40, False),       # RGB stem
+    (1, 64, 7, 2, 3, 1, 33, 40, False),       # IR stem
+    (4, 64, 7, 2, 3, 1, 32, 40, False),       # early-fusion stem
+    (2048, 1024, 1, 1, 0, 1, 6, 9, True),     # deep 1x1 with bias (PSP bottleneck class)
+    (1024, 256, 3, 1, 1, 1, 12, 16, True),    # up_1 conv
+    (64, 13, 1, 1, 0, 1, 16, 24, True),       # final
+    (13, 64, 4, 2, 1, 1, 32, 48, True),       # critic conv1 on logits
+    (128, 64, 4, 2, 1, 1, 16, 24, True),      # critic conv1 on x1
+    (512, 1, 4, 2, 1, 1, 4, 6, True),         # critic classifier
+]
+
+
+def _conv_case(case, seed=0):
+    cin, cout, k, stride, pad, dil, h, w, bias = case
+    g = torch.Generator().manual_seed(seed)
+    conv = nn.Conv2d(cin, cout, k, stride, pad, dil, bias=bias)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * (2.0 / (k * k * cin)) ** 0.5)
+        if bias:
+            conv.bias.copy_(torch.randn(cout, generator=g) * 0.1)
+    x = torch.randn(2, cin, h, w, generator=g)
+    return conv, x
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fp32_matches_oracle(E, case):
+    conv, x = _conv_case(case)
+    ref = F.conv2d(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation)     # oracle primitive (CPU FP32)
+    convg = conv.cuda()
+    scale, shift = E.folded_affine(convg, None)
+    y = E.conv2d(to_act(E, x, torch.float32), convg, scale, shift)
+    assert rel(back(y), ref) < FP32_TOL
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_bf16_tensor_core_matches_oracle(E, case):
+    conv, x = _conv_case(case)
+    ref = F.conv2d(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation)
+    # same operands rounded to BF16, evaluated in FP32 on the CPU: isolates kernel bugs from rounding
+    ref_r = F.conv2d(x.bfloat16().float(), conv.weight.detach().bfloat16().float(), conv.bias, conv.stride, conv.padding,
+                     conv.dilation)
+    convg = conv.cuda()
+    scale, shift = E.folded_affine(convg, None)
+    y32 = E.conv2d(to_act(E, x, torch.bfloat16), convg, scale, shift, out_dtype=torch.float32)
+    assert rel(back(y32), ref_r) < 1e-3
+    y16 = E.conv2d(to_act(E, x, torch.bfloat16), convg, scale, shift)
+    assert y16.dtype == torch.bfloat16
+    assert rel(back(y16), ref) < BF16_TOL
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+def test_conv_fused_epilogue_bn_residual_relu(E, dtype, tol):
+    """conv -> BN(eval) -> += residual -> ReLU in one launch == cm/models/extractors.py:96-101."""
+    g = torch.Generator().manual_seed(1)
+    conv = nn.Conv2d(128, 512, 1, bias=False)
+    bn = nn.BatchNorm2d(512)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * 0.1)
+        bn.weight.copy_(torch.rand(512, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(512, generator=g) * 0.1)
+        bn.running_mean.copy_(torch.randn(512, generator=g) * 0.1)
+        bn.running_var.copy_(torch.rand(512, generator=g) + 0.5)
+    bn.eval()
+    x = torch.randn(2, 128, 9, 14, generator=g)
+    res = torch.randn(2, 512, 9, 14, generator=g)
+    with torch.no_grad():
+        ref = F.relu(bn(conv(x)) + res)
+    convg, bng = conv.cuda(), bn.cuda()
+    y = E.conv_bn_act(to_act(E, x, dtype), convg, bng, E.ACT_RELU, residual=to_act(E, res, dtype))
+    assert rel(back(y), ref) < tol
+    # PReLU slope read from device memory
+    prelu = nn.PReLU().cuda()
+    with torch.no_grad():
+        prelu.weight.fill_(0.3)
+        ref2 = F.prelu(bn(conv(x)), torch.tensor([0.3]))
+    y2 = E.conv_bn_act(to_act(E, x, dtype), convg, bng, E.ACT_LEAKY, slope_ptr=prelu.weight)
+    assert rel(back(y2), ref2) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+def test_conv_into_channel_slice_is_the_concat(E, dtype, tol):
+    """Two producers writing channel halves of one buffer == torch.cat(dim=1) (cm/models/extractors.py:192)."""
+    g = torch.Generator().manual_seed(2)
+    c1, c2 = nn.Conv2d(64, 128, 1, bias=False), nn.Conv2d(64, 128, 3, padding=1, bias=False)
+    xa, xb = torch.randn(1, 64, 10, 12, generator=g), torch.randn(1, 64, 10, 12, generator=g)
+    with torch.no_grad():
+        ref = torch.cat([c1(xa), c2(xb)], 1)
+    cat = E.new_act(1, 10, 12, 256, dtype, "cuda")
+    E.conv2d(to_act(E, xa, dtype), c1.cuda(), out=cat.slice(0, 128))
+    E.conv2d(to_act(E, xb, dtype), c2.cuda(), out=cat.slice(128, 128))
+    assert rel(back(cat), ref) < tol
+    # and a conv reading a channel slice
+    c3 = nn.Conv2d(128, 64, 1, bias=False)
+    with torch.no_grad():
+        ref3 = c3(ref[:, 128:])
+    y3 = E.conv2d(cat.slice(128, 128), c3.cuda())
+    assert rel(back(y3), ref3) < (tol if dtype == torch.float32 else 3e-2)
+
+
+def test_conv_kernel_larger_than_input_raises(E):
+    conv = nn.Conv2d(64, 64, 4, 2, 1).cuda()
+    with pytest.raises(RuntimeError, match="Kernel size can't be greater than actual input size"):
+        E.conv2d(E.new_act(1, 1, 1, 64, torch.bfloat16, "cuda"), conv)
+
+
+def test_weight_cache_follows_parameter_updates(E):
+    conv = nn.Conv2d(64, 64, 1, bias=False).cuda()
+    x = torch.randn(1, 64, 8, 8)
+    y0 = back(E.conv2d(to_act(E, x, torch.float32), conv))
+    with torch.no_grad():
+        conv.weight.mul_(2.0)          # in-place update bumps the version counter -> re-pack
+    y1 = back(E.conv2d(to_act(E, x, torch.float32), conv))
+    assert rel(y1, 2 * y0) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ bandwidth kernels
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("hw", [(17, 24), (16, 16), (7, 9)])
+def test_maxpool(E, dtype, hw):
+    x = torch.randn(2, 64, *hw, generator=torch.Generator().manual_seed(3))
+    ref = F.max_pool2d(x.to(dtype).float(), 3, 2, 1)
+    assert torch.equal(back(E.maxpool3x3s2(to_act(E, x, dtype))), ref)      # max is exact in any dtype
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("hw", [(8, 12), (40, 80), (11, 30), (5, 7)])
+def test_pyramid_pool(E, dtype, tol, hw):
+    x = torch.randn(2, 128, *hw, generator=torch.Generator().manual_seed(4))
+    outs = E.pyramid_pool(to_act(E, x, dtype), (1, 2, 3, 6))
+    for s, o in zip((1, 2, 3, 6), outs):
+        ref = F.adaptive_avg_pool2d(x.to(dtype).float(), s)                  # overlapping bins when hw % s != 0
+        assert (o.n, o.h, o.w, o.c) == (2, s, s, 128)
+        assert rel(back(o), ref) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("sizes", [((6, 6), (40, 80)), ((1, 1), (8, 12)), ((8, 12), (16, 24)), ((41, 60), (82, 120)), ((3, 3), (11, 30))])
+def test_bilinear(E, dtype, tol, sizes):
+    (h, w), (ho, wo) = sizes
+    x = torch.randn(2, 64, h, w, generator=torch.Generator().manual_seed(5))
+    ref = F.interpolate(x.to(dtype).float(), size=(ho, wo), mode="bilinear", align_corners=False)
+    assert rel(back(E.bilinear(to_act(E, x, dtype), ho, wo)), ref) < tol
+
+
+def test_bilinear_x32_single_channel_fp32(E):
+    """nn.Upsample(scale_factor=32, mode='bilinear') on the critics' 1-channel map (cm/discriminator_model.py:47)."""
+    x = torch.randn(2, 1, 2, 3, generator=torch.Generator().manual_seed(6))
+    ref = nn.Upsample(scale_factor=32, mode='bilinear')(x)
+    y = E.bilinear(to_act(E, x, torch.float32), 64, 96)
+    assert rel(back(y), ref) < 1e-5
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+def test_batchnorm_train_mode(E, dtype, tol):
+    """conv -> BN(train) -> ReLU: batch statistics, running-stat update (momentum .1, unbiased var),
+    num_batches_tracked -- appendix B.3."""
+    g = torch.Generator().manual_seed(7)
+    conv = nn.Conv2d(64, 128, 3, padding=1, bias=True)
+    bn = nn.BatchNorm2d(128)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(128, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(128, generator=g) * 0.1)
+    x = torch.randn(3, 64, 10, 14, generator=g) + 0.5
+    import copy
+    convg, bng = copy.deepcopy(conv).cuda(), copy.deepcopy(bn).cuda()
+    bn.train()
+    with torch.no_grad():
+        ref = F.relu(bn(conv(x)))
+    bng.train()
+    y = E.conv_bn_act(to_act(E, x, dtype), convg, bng, E.ACT_RELU)
+    assert rel(back(y), ref) < tol
+    st = 1e-5 if dtype == torch.float32 else 1e-2
+    assert rel(bng.running_mean.cpu(), bn.running_mean) < st
+    assert rel(bng.running_var.cpu(), bn.running_var) < st
+    assert int(bng.num_batches_tracked) == 1
+    # eval right after must pick the updated running statistics up (cache invalidation)
+    bn.eval(); bng.eval()
+    with torch.no_grad():
+        ref_e = F.relu(bn(conv(x)))
+    y_e = E.conv_bn_act(to_act(E, x, dtype), convg, bng, E.ACT_RELU)
+    assert rel(back(y_e), ref_e) < tol
+
+
+# ------------------------------------------------------------------------------------------------ confusion matrix
+def test_confusion_bit_exact_labels_and_scores(golden_dir):
+    import os
+    from heatnet_pub_b200 import iou_eval
+    from oracle.iou_oracle import IoUOracle
+    g = np.load(os.path.join(golden_dir, "iou_golden.npz"))
+    m = iou_eval.IoU(14, False, [12, 13])
+    m.add(torch.from_numpy(g["pred"][:3]).cuda(), torch.from_numpy(g["tgt"][:3]).cuda())
+    assert np.array_equal(m.conf_metric.conf, g["conf_after_add1"]) and m.conf_metric.conf.dtype == np.int32
+    iou, miou = m.value()
+    assert np.array_equal(iou, g["iou1"], equal_nan=True) and miou == g["miou1"]
+    assert np.array_equal(m.conf_metric.conf, g["conf_after_value1"])
+    m.add(torch.from_numpy(g["pred"][3:]), torch.from_numpy(g["tgt"][3:]))          # CPU tensors take the same kernel
+    assert np.array_equal(m.conf_metric.conf, g["conf_after_add2"])
+    iou, miou = m.value()
+    assert np.array_equal(iou, g["iou2"], equal_nan=True) and miou == g["miou2"]
+    m2 = iou_eval.IoU(14, False, None)
+    m2.add(torch.from_numpy(g["scores"]).cuda(), torch.from_numpy(g["tgt_s"]).cuda())   # fused argmax, ties -> first
+    assert np.array_equal(m2.conf_metric.conf, g["conf_scores"])
+    iou, miou = m2.value()
+    assert np.array_equal(iou, g["iou3"], equal_nan=True) and miou == g["miou3"]
+    m3 = iou_eval.IoU(14, True, 13)
+    m3.add(torch.from_numpy(g["pred"]).cuda(), torch.from_numpy(g["tgt"]).cuda())
+    assert np.array_equal(m3.conf_metric.value(), g["conf_normalized"])
+    from heatnet_pub_b200 import utils
+    got = utils.calculate_ious(torch.from_numpy(g["pred"]).cuda(), torch.from_numpy(g["tgt"]).cuda(), 13)
+    assert np.array_equal(got, g["calc_ious"], equal_nan=True)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 255, 4097, 320 * 640 * 3 + 1])
+def test_confusion_ragged_sizes_vs_oracle(n):
+    from heatnet_pub_b200 import iou_eval
+    from oracle import c_oracle
+    rng = np.random.RandomState(n)
+    pred, tgt = rng.randint(0, 14, n).astype(np.int64), rng.randint(0, 14, n).astype(np.int64)
+    cm = iou_eval.ConfusionMatrix(14)
+    cm.add(torch.from_numpy(pred).cuda(), torch.from_numpy(tgt).cuda())
+    want = c_oracle.confusion(pred, tgt, 14) if n else np.zeros((14, 14), np.int32)
+    assert np.array_equal(cm.conf, want)
+
+
+def test_confusion_skewed_labels_and_large_k():
+    """Real label maps are dominated by a few classes: every lane of a warp hits the same bin."""
+    from heatnet_pub_b200 import iou_eval
+    from oracle import c_oracle
+    n = 1 << 22
+    pred, tgt = np.full(n, 3, np.int64), np.full(n, 3, np.int64)
+    pred[::1000] = 7
+    cm = iou_eval.ConfusionMatrix(14)
+    cm.add(torch.from_numpy(pred).cuda(), torch.from_numpy(tgt).cuda())
+    assert np.array_equal(cm.conf, c_oracle.confusion(pred, tgt, 14))
+    rng = np.random.RandomState(1)
+    pred, tgt = rng.randint(0, 32, 100000).astype(np.int64), rng.randint(0, 32, 100000).astype(np.int64)
+    cm = iou_eval.ConfusionMatrix(32)
+    cm.add(torch.from_numpy(pred).cuda(), torch.from_numpy(tgt).cuda())
+    assert np.array_equal(cm.conf, c_oracle.confusion(pred, tgt, 32))
+
+
+def test_confusion_range_asserts_like_reference():
+    from heatnet_pub_b200 import iou_eval
+    cm = iou_eval.ConfusionMatrix(14)
+    ok = torch.zeros(10, dtype=torch.int64).cuda()
+    bad = ok.clone(); bad[3] = 14
+    with pytest.raises(AssertionError, match="predicted values are not between 0 and k-1"):
+        cm.add(bad, ok)
+    neg = ok.clone(); neg[5] = -1
+    with pytest.raises(AssertionError, match="target values are not between 0 and k-1"):
+        cm.add(ok, neg)
+    with pytest.raises(AssertionError, match="number of targets and predicted outputs do not match"):
+        cm.add(ok, ok[:5])
+    m = iou_eval.IoU(14)
+    with pytest.raises(AssertionError, match="predictions must be of dimension"):
+        m.add(torch.zeros(2, 3).cuda(), torch.zeros(2, 3).cuda())
+
+
+def test_confusion_checksum_at_full_size():
+    """Config 5 property at the reference's map size: the matrix sums to the pixel count, row sums are the
+    target histogram and column sums the prediction histogram (10 x 500 maps of 320x640 would take the CPU
+    oracle minutes; 40 maps are checked bit-exactly, the rest through the checksums)."""
+    from heatnet_pub_b200 import iou_eval
+    from oracle import c_oracle
+    g = torch.Generator(device="cuda").manual_seed(1203412412)
+    cm = iou_eval.ConfusionMatrix(14)
+    tot_t, tot_p = torch.zeros(14, dtype=torch.int64), torch.zeros(14, dtype=torch.int64)
+    n_maps = 0
+    for chunk in range(4):
+        pred = torch.randint(0, 14, (100, 320, 640), generator=g, device="cuda")
+        tgt = torch.randint(0, 14, (100, 320, 640), generator=g, device="cuda")
+        cm.add(pred.view(-1), tgt.view(-1))
+        tot_t += torch.bincount(tgt.view(-1), minlength=14).cpu()
+        tot_p += torch.bincount(pred.view(-1), minlength=14).cpu()
+        n_maps += 100
+        if chunk == 0:
+            want = c_oracle.confusion(pred[:40].cpu().numpy(), tgt[:40].cpu().numpy(), 14)
+            cm40 = iou_eval.ConfusionMatrix(14)
+            cm40.add(pred[:40].reshape(-1), tgt[:40].reshape(-1))
+            assert np.array_equal(cm40.conf, want)
+    conf = cm.conf.astype(np.int64)
+    assert conf.sum() == n_maps * 320 * 640
+    assert np.array_equal(conf.sum(1), tot_t.numpy()) and np.array_equal(conf.sum(0), tot_p.numpy())

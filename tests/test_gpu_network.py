@@ -1,0 +1,183 @@
+"""Whole-network parity on a B200: the RGB+thermal PSPNet-ResNet50, early-fusion and RGB variants and the
+domain critics against (a) the golden vectors the REFERENCE produced (tests/golden/*.npz) and (b) the CPU
+oracle on the same seeded inputs and weights.
+
+Tolerances (north star): logits within 1e-4 relative in FP32, within 2e-2 relative in BF16 -- relative to
+max|ref| of the tensor.  Argmax agreement is reported next to the oracle's own BF16-vs-FP32 noise floor,
+because with random weights many pixels have near-tied top-2 logits."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import heatnet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL = 2e-2
+
+
+def rel(a, b):
+    a = torch.as_tensor(np.asarray(a)).double()
+    b = torch.as_tensor(np.asarray(b)).double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def _late_net(seed=0):
+    from heatnet_pub_b200 import pspnet
+    net = pspnet.PSPNet(sizes=(1, 2, 3, 6), psp_size=2048, deep_features_size=1024, backend='resnet50', in_channels=4,
+                        pretrained=False, late_fusion=True)
+    net.load_state_dict(O.recipe_fill(O.pspnet_state_dict(True, 4), seed=seed))
+    return net.cuda()
+
+
+@pytest.fixture(scope="module")
+def late_golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "pspnet_late_golden.npz"))
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_late_fusion_train_then_eval_matches_reference_golden(late_golden, precision, tol):
+    """Same sequence as the fixture generator: one train-mode forward (batch-stat BN, dropout off) on B=2, then
+    an eval forward on B=1 that uses the running statistics the first call updated."""
+    g = late_golden
+    net = _late_net().set_precision(precision)
+    net.drop_1.p = 0.0
+    net.drop_2.p = 0.0
+    rgb, ir = torch.from_numpy(g["rgb"]).cuda(), torch.from_numpy(g["ir"]).cuda()
+    net.train()
+    with torch.no_grad():
+        logits, taps, none = net(rgb, ir)
+    assert none is None and len(taps) == 6 and taps[0] is logits
+    assert logits.shape == (2, 13, 64, 96) and logits.dtype == torch.float32 and logits.is_contiguous()
+    assert rel(logits.cpu(), g["logits_train"]) < tol
+    for i in range(1, 6):
+        assert rel(taps[i][:, ::8].float().cpu(), g[f"tap{i}_train_sub"]) < tol
+    sd = net.state_dict()
+    bn_tol = 1e-4 if precision == "fp32" else 2e-2
+    for k in g.files:
+        if k.startswith("bn_after_train/"):
+            name = k.split("/", 1)[1]
+            if name.endswith("num_batches_tracked"):
+                assert int(sd[name]) == int(g[k])
+            else:
+                assert rel(sd[name].cpu(), g[k]) < bn_tol, name
+    net.eval()
+    with torch.no_grad():
+        logits_e, taps_e, _ = net(rgb[:1], ir[:1])
+    assert rel(logits_e.cpu(), g["logits_eval"]) < tol
+    for i in range(1, 6):
+        assert rel(taps_e[i][:, ::8].float().cpu(), g[f"tap{i}_eval_sub"]) < tol
+    agree = (logits_e.cpu().argmax(1).numpy() == g["logits_eval"].argmax(1)).mean()
+    print(f"[{precision}] eval argmax agreement vs reference golden: {agree:.5f}")
+    if precision == "fp32":
+        assert agree >= 0.999
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_early_fusion_and_rgb_signature(golden_dir, precision, tol):
+    from heatnet_pub_b200 import pspnet
+    g = np.load(os.path.join(golden_dir, "pspnet_early_golden.npz"))
+    net = pspnet.PSPNet(backend='resnet50', in_channels=4, pretrained=False, late_fusion=False)
+    net.load_state_dict(O.recipe_fill(O.pspnet_state_dict(False, 4), seed=1))
+    net = net.cuda().eval().set_precision(precision)
+    rgb, ir = O.synthetic_inputs(2, 64, 96)
+    with torch.no_grad():
+        logits, taps, _ = net(rgb[:1].cuda(), ir[:1].cuda())
+    assert rel(logits.cpu(), g["logits_eval"]) < tol
+    assert [t.shape[1] for t in taps] == [13, 2048, 1024, 512, 256, 64]
+    # top-level models/pspnet.py signature: forward(x) -> logits only, 18 classes
+    rgbnet = pspnet.PSPNetRGB(backend='resnet50', pretrained=False)
+    sd = O.recipe_fill(O.pspnet_state_dict(False, 3, n_classes=18), seed=5)
+    rgbnet.load_state_dict(sd)
+    rgbnet = rgbnet.cuda().eval().set_precision(precision)
+    with torch.no_grad():
+        out = rgbnet(rgb.cuda())
+        ref, _, _ = O.pspnet_forward(sd, rgb, None, late_fusion=False, training=False)
+    assert torch.is_tensor(out) and out.shape == (2, 18, 64, 96)
+    assert rel(out.cpu(), ref) < tol
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_critic_matches_reference_golden(golden_dir, precision, tol):
+    from heatnet_pub_b200 import discriminator_model
+    g = np.load(os.path.join(golden_dir, "critic_golden.npz"))
+    crit = discriminator_model.FCDiscriminator(13)
+    crit.load_state_dict(O.recipe_fill(O.critic_state_dict(13), seed=2))
+    crit = crit.cuda()
+    crit.precision = precision
+    with torch.no_grad():
+        y = crit(torch.from_numpy(g["x"]).cuda())
+    assert y.shape == (2, 1, 64, 96) and y.dtype == torch.float32
+    assert rel(y.cpu(), g["y"]) < tol
+    with pytest.raises(RuntimeError, match="Kernel size can't be greater than actual input size"):
+        with torch.no_grad():
+            crit(torch.zeros(1, 13, 16, 16).cuda())       # reference: same failure in conv4 / classifier
+
+
+def test_config1_shape_bf16_vs_oracle_with_noise_floor():
+    """BASELINE config 1 shape (B=1, 3+1 ch, 320x640) in BF16 against the CPU FP32 oracle; the oracle's own
+    BF16-autocast result on the CPU is the noise floor for argmax agreement."""
+    sd = O.recipe_fill(O.pspnet_state_dict(True, 4), seed=0)
+    rgb, ir = O.synthetic_inputs(1, 320, 640)
+    with torch.no_grad():
+        ref, ref_taps, _ = O.pspnet_forward(sd, rgb, ir, late_fusion=True, training=False)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            ref_bf16, _, _ = O.pspnet_forward(sd, rgb, ir, late_fusion=True, training=False)
+    net = _late_net().eval()
+    with torch.no_grad():
+        logits, taps, _ = net(rgb.cuda(), ir.cuda())
+    assert logits.shape == (1, 13, 320, 640)
+    err = rel(logits.cpu(), ref)
+    agree = (logits.cpu().argmax(1) == ref.argmax(1)).float().mean().item()
+    floor_err = rel(ref_bf16.float(), ref)
+    floor_agree = (ref_bf16.float().argmax(1) == ref.argmax(1)).float().mean().item()
+    print(f"bf16 320x640: rel err {err:.3e} (torch CPU bf16 autocast: {floor_err:.3e}); "
+          f"argmax agreement {agree:.5f} (torch CPU bf16 autocast: {floor_agree:.5f})")
+    assert err < BF16_TOL
+    assert agree >= floor_agree - 0.005
+    for i, t in enumerate(taps[1:], 1):
+        assert rel(t.float().cpu(), ref_taps[i]) < BF16_TOL
+    net.set_precision("fp32")
+    with torch.no_grad():
+        logits32, _, _ = net(rgb.cuda(), ir.cuda())
+    assert rel(logits32.cpu(), ref) < FP32_TOL
+    assert (logits32.cpu().argmax(1) == ref.argmax(1)).float().mean().item() >= 0.999
+
+
+def test_full_frame_properties_650x1920():
+    """BASELINE config 2 geometry: 650x1920 frames -> 656x1920 logits (ceil at every stride-2, x8); results
+    do not depend on the batch an image sits in (bit-exact), and match the oracle run on the GPU by torch in
+    FP32 (TF32 off) within the BF16 bound."""
+    net = _late_net().eval()
+    rgb, ir = O.synthetic_inputs(2, 650, 1920)
+    rgb, ir = rgb.cuda(), ir.cuda()
+    with torch.no_grad():
+        logits, taps, _ = net(rgb, ir)
+        logits1, taps1, _ = net(rgb[1:], ir[1:])
+    assert logits.shape == (2, 13, 656, 1920)
+    assert [tuple(t.shape[1:]) for t in taps[1:]] == [(2048, 82, 240), (1024, 82, 240), (1024, 82, 240), (512, 163, 480), (128, 163, 480)]
+    assert torch.equal(logits[1:], logits1)
+    assert torch.equal(taps[1][1:], taps1[1])
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sd = {k: v.cuda() for k, v in O.recipe_fill(O.pspnet_state_dict(True, 4), seed=0).items()}
+    with torch.no_grad():
+        ref, _, _ = O.pspnet_forward(sd, rgb[:1], ir[:1], late_fusion=True, training=False)
+    err = rel(logits[:1].cpu(), ref.cpu())
+    agree = (logits[:1].argmax(1) == ref.argmax(1)).float().mean().item()
+    print(f"bf16 650x1920: rel err vs FP32 oracle (torch CUDA, TF32 off) {err:.3e}, argmax agreement {agree:.5f}")
+    assert err < BF16_TOL
+
+
+def test_grad_mode_is_refused_until_backward_exists():
+    """A training call must either build a graph or fail loudly -- never silently drop gradients."""
+    net = _late_net().train()
+    rgb, ir = O.synthetic_inputs(1, 64, 96)
+    try:
+        out, _, _ = net(rgb.cuda(), ir.cuda())
+    except NotImplementedError:
+        return
+    assert out.requires_grad, "forward under grad mode returned a tensor without a graph"

@@ -1,0 +1,152 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares, the Python host
+mirrors the reference's module API / state_dict layout, and the product path refuses to run without a GPU
+(no CPU fallback).  No kernel is launched here."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import heatnet_oracle as O
+from oracle.iou_oracle import IoUOracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    import __graft_entry__ as g
+    g.build()
+
+
+def test_library_exports_every_declared_symbol():
+    from heatnet_pub_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "heatnet_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(hn_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/heatnet_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes signatures out of sync with the header"
+    assert lib.hn_version() >= 100
+    assert lib.hn_conv_kpad(3, 7, 7) == 192 and lib.hn_conv_kpad(2048, 1, 1) == 2048
+    assert lib.hn_conv_cout_pad(13, _lib.HN_BF16) == 16 and lib.hn_conv_cout_pad(13, _lib.HN_F32) == 64
+    assert lib.hn_conv_cout_pad(2048, _lib.HN_BF16) == 2048
+
+
+def test_struct_layout_matches_header(tmp_path):
+    """ctypes mirrors of the C structs: sizes and field offsets compared with what gcc computes from the header."""
+    import ctypes as C
+    import subprocess
+    from heatnet_pub_b200 import _lib
+    structs = {"hn_tensor": _lib.HnTensor, "hn_epilogue": _lib.HnEpilogue, "hn_conv": _lib.HnConv}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "heatnet_b200.h"', 'int main(void){']
+    for cname, st in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in st._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines.append('return 0;}')
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    want = dict(l.split() for l in subprocess.check_output([str(exe)]).decode().splitlines())
+    for cname, st in structs.items():
+        assert C.sizeof(st) == int(want[cname]), cname
+        for fname, _ in st._fields_:
+            assert getattr(st, fname).offset == int(want[f"{cname}.{fname}"]), f"{cname}.{fname}"
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="needs a box without a GPU")
+def test_no_cpu_fallback():
+    from heatnet_pub_b200 import pspnet
+    net = pspnet.PSPNet(backend='resnet50', pretrained=False, late_fusion=True, in_channels=4).eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        with torch.no_grad():
+            net(torch.zeros(1, 3, 32, 32), torch.zeros(1, 1, 32, 32))
+    from heatnet_pub_b200 import iou_eval
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        iou_eval.IoU(14).add(torch.zeros(1, 4, 4, dtype=torch.int64), torch.zeros(1, 4, 4, dtype=torch.int64))
+
+
+def test_product_path_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "heatnet_pub_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("no CPU fallback", ""), f"{fn} mentions the oracle"
+
+
+def test_state_dict_layout_matches_reference(golden_dir):
+    from heatnet_pub_b200 import pspnet
+    g = np.load(os.path.join(golden_dir, "pspnet_late_golden.npz"))
+    net = pspnet.PSPNet(sizes=(1, 2, 3, 6), psp_size=2048, deep_features_size=1024, backend='resnet50', in_channels=4,
+                        pretrained=False, late_fusion=True)
+    sd = net.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g["state_dict_keys"]]
+    assert [str(tuple(v.shape)) for v in sd.values()] == [str(s) for s in g["state_dict_shapes"]]
+    assert len(sd) == 488
+    ge = np.load(os.path.join(golden_dir, "pspnet_early_golden.npz"))
+    net_e = pspnet.PSPNet(backend='resnet50', in_channels=4, pretrained=False, late_fusion=False)
+    assert list(net_e.state_dict().keys()) == [str(k) for k in ge["state_dict_keys"]]
+    # top-level models/pspnet.py signature: n_classes=18, identical keys to the early-fusion 3-channel net
+    net_rgb = pspnet.PSPNetRGB(backend='resnet50', pretrained=False)
+    assert net_rgb.final[0].out_channels == 18 and len(net_rgb.state_dict()) == 350
+    # attributes the reference exposes
+    for attr in ("feats", "psp", "drop_1", "up_1", "up_2", "up_3", "drop_2", "final"):
+        assert hasattr(net, attr)
+    assert isinstance(net.psp.stages[0][0], nn.AdaptiveAvgPool2d) and isinstance(net.up_1.conv[2], nn.PReLU)
+    assert net.drop_1.p == 0.3 and net.drop_2.p == 0.15
+    # load_state_dict of a reference-shaped state dict works both ways
+    net.load_state_dict(O.recipe_fill(O.pspnet_state_dict(True, 4), seed=0))
+
+
+def test_build_network_both_signatures(monkeypatch):
+    from heatnet_pub_b200 import build_net, pspnet
+    monkeypatch.setattr(nn.Module, "cuda", lambda self, *a, **k: self)     # the reference calls .cuda() unconditionally
+    net = build_net.build_network(None, 'resnet50', in_channels=4, late_fusion=True)
+    assert isinstance(net, pspnet.PSPNet) and net.feats.late_fusion and len(net.state_dict()) == 488
+    assert set(build_net.models) == {'squeezenet', 'densenet', 'resnet18', 'resnet34', 'resnet50', 'resnet101', 'resnet152'}
+    with pytest.raises(KeyError):
+        build_net.build_network(None, 'vgg')
+
+
+def test_conf_segnet_mirror(monkeypatch, capsys):
+    from heatnet_pub_b200 import conf_segnet, discriminator_model
+    monkeypatch.setattr(nn.Module, "cuda", lambda self, *a, **k: self)
+    m = conf_segnet.conv_segnet(pretrained=False, disc_arch='cyclegan', num_critics=6, no_conf=False, modalities='ir_rgb',
+                                arch='pspnet', late_fusion=True)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(O.conf_segnet_state_dict(True, 6).keys()) and len(sd) == 548
+    assert [c.conv1.in_channels for c in m.critics] == [13, 2048, 1024, 1024, 512, 128]
+    assert all(isinstance(c, discriminator_model.FCDiscriminator) for c in m.critics)
+    assert m.phase == "train_seg"
+    m.setPhase("train_critic")
+    assert not any(p.requires_grad for p in m.trgb_segnet.parameters()) and all(p.requires_grad for p in m.critics.parameters())
+    m.setPhase("train_seg")
+    assert all(p.requires_grad for p in m.trgb_segnet.parameters()) and not any(p.requires_grad for p in m.critics.parameters())
+    # weights_init_normal reached the BN layers: gamma ~ N(1, 0.02), beta = 0
+    bn = m.trgb_segnet.feats.bn1
+    assert abs(bn.weight.mean().item() - 1) < 0.02 and bn.bias.abs().max().item() == 0
+    with pytest.raises(NotImplementedError):
+        conf_segnet.conv_segnet(pretrained=False, disc_arch='cyclegan', arch='custom')
+
+
+def test_iou_value_host_logic_matches_oracle():
+    """IoU.value() (ignore-index zeroing in place, NaN classes, nanmean) is host arithmetic on the K x K matrix."""
+    from heatnet_pub_b200 import iou_eval
+    rng = np.random.RandomState(0)
+    conf = rng.randint(0, 1000, (14, 14)).astype(np.int32)
+    conf[5, :] = 0
+    conf[:, 5] = 0
+    m, mo = iou_eval.IoU(14, False, [12, 13]), IoUOracle(14, False, [12, 13])
+    m.conf_metric.conf[:] = conf
+    mo.conf_metric.conf[:] = conf
+    (iou, miou), (iou_o, miou_o) = m.value(), mo.value()
+    assert np.array_equal(iou, iou_o, equal_nan=True) and miou == miou_o and np.isnan(iou[5])
+    assert np.array_equal(m.conf_metric.conf, mo.conf_metric.conf) and m.conf_metric.conf[12].sum() == 0
+    with pytest.raises(ValueError):
+        iou_eval.IoU(14, False, 1.5)
