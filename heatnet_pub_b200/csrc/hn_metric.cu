@@ -155,24 +155,27 @@ extern "C" int hn_confusion(const int64_t *pred_labels, const float *scores, int
     const int64_t n = n_images * hw;
     if (n == 0) return HN_OK;
     const int nwords = (k * k + 1) / 2;
-    const int warps = 8;
+    // one private table per warp: as many warps (<= 8) as fit in ~200 KB of shared memory
+    int warps = (int)((200 * 1024) / ((size_t)nwords * 32 * sizeof(uint32_t)));
+    warps = warps < 1 ? 1 : (warps > 8 ? 8 : warps);
+    const int threads = warps * 32;
     const size_t smem = (size_t)warps * nwords * 32 * sizeof(uint32_t);
     cudaStream_t st = (cudaStream_t)stream;
     // one resident wave: grid = SMs x CTAs/SM that fit in shared memory
     int per_sm = (int)((200 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;
-    int64_t want = cdiv(scores ? n : cdiv(n, 2), 256);
+    int64_t want = cdiv(scores ? n : cdiv(n, 2), threads);
     int grid = (int)((want < (int64_t)num_sms() * per_sm) ? want : (int64_t)num_sms() * per_sm);
     if (pred_labels) {
         HN_CHECK_ARG((reinterpret_cast<uintptr_t>(pred_labels) | reinterpret_cast<uintptr_t>(target)) % 16 == 0,
                      "hn_confusion: label pointers must be 16-byte aligned");
         HN_CUDA(cudaFuncSetAttribute(confusion_labels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        confusion_labels_kernel<<<grid, 256, smem, st>>>((const long long *)pred_labels, (const long long *)target, n, k,
+        confusion_labels_kernel<<<grid, threads, smem, st>>>((const long long *)pred_labels, (const long long *)target, n, k,
                                                          (unsigned long long *)conf, flags);
     } else {
         HN_CUDA(cudaFuncSetAttribute(confusion_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        confusion_scores_kernel<<<grid, 256, smem, st>>>(scores, (const long long *)target, n_images, hw, k,
+        confusion_scores_kernel<<<grid, threads, smem, st>>>(scores, (const long long *)target, n_images, hw, k,
                                                          (unsigned long long *)conf, flags);
     }
     HN_LAUNCH_CHECK();

@@ -124,7 +124,8 @@ def test_conv_fused_epilogue_bn_residual_relu(E, dtype, tol):
     res = torch.randn(2, 512, 9, 14, generator=g)
     with torch.no_grad():
         ref = F.relu(bn(conv(x)) + res)
-    convg, bng = conv.cuda(), bn.cuda()
+    import copy
+    convg, bng = copy.deepcopy(conv).cuda(), copy.deepcopy(bn).cuda()
     y = E.conv_bn_act(to_act(E, x, dtype), convg, bng, E.ACT_RELU, residual=to_act(E, res, dtype))
     assert rel(back(y), ref) < tol
     # PReLU slope read from device memory
