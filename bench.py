@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""HeatNet hot-path benchmark (driver contract: one JSON line on stdout from rank 0).
+
+Metric (BASELINE.json): RGB+thermal segmentation images/sec.  A "step" is one forward of the two-stream
+PSPNet-ResNet50 over one synthetic batch; at N=1 the workload is BASELINE.json configs[1]: BF16, batch 16,
+650x1920 frames (logits 16x13x656x1920).  N>1: the path shards over images -- every rank runs the same
+batch size on its own GPU, no data-path collective ("scaling": "weak").
+
+  value     images/s with inputs resident in HBM, CUDA-event timed, max over ranks.
+  e2e       same metric through the public module API from PINNED HOST buffers: H2D of the RGB+IR frames,
+            forward, class argmax on the device, D2H of the uint8 label maps -- all inside the timed region.
+  roofline  the tensor-core convolution kernel (conv_tc_kernel): algorithmic conv FLOPs per step (2*MAC of
+            every nn.Conv2d the reference executes) / device time summed over the
+            step's conv launches (CUDA events on the launching stream, separate instrumented pass).
+  cpu_baseline  the oracle (torch CPU FP32 restatement of the reference = the reference's own arithmetic)
+            timed on the box's host cores on a bounded sample of the same workload.
+
+`--impl reference` times that CPU path as the reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rgb_thermal_seg_images_per_sec"
+UNIT = "images/s"
+SEED = 1203412412           # the reference's own seed, scripts/main.py:126
+
+
+def conv_flops_per_image(net, h, w, late=True):
+    """2*MAC of every convolution of the forward at input h x w, from the module tree (matches SURVEY appendix A:
+    325.84 GFLOP at 320x640, 2001.24 GFLOP at 650x1920 for late fusion)."""
+    import torch.nn as nn
+
+    def out(n, k, s, p, d):
+        return (n + 2 * p - d * (k - 1) - 1) // s + 1
+
+    total = 0
+
+    def conv(m, hh, ww):
+        nonlocal total
+        k, s, p, d = m.kernel_size[0], m.stride[0], m.padding[0], m.dilation[0]
+        ho, wo = out(hh, k, s, p, d), out(ww, k, s, p, d)
+        total += 2 * ho * wo * m.out_channels * m.in_channels * k * k
+        return ho, wo
+
+    f = net.feats
+    streams = [(f.conv1, f.layer1, f.layer2)]
+    if f.late_fusion:
+        streams.append((f.conv1_2, f.layer1_2, f.layer2_2))
+    for c1, l1, l2 in streams:
+        hh, ww = conv(c1, h, w)
+        hh, ww = out(hh, 3, 2, 1, 1), out(ww, 3, 2, 1, 1)
+        for layer in (l1, l2):
+            for blk in layer:
+                conv(blk.conv1, hh, ww)
+                h2, w2 = conv(blk.conv2, hh, ww)
+                conv(blk.conv3, h2, w2)
+                if blk.downsample is not None:
+                    conv(blk.downsample[0], hh, ww)
+                hh, ww = h2, w2
+    for layer in (f.layer3, f.layer4):
+        for blk in layer:
+            conv(blk.conv1, hh, ww)
+            conv(blk.conv2, hh, ww)
+            conv(blk.conv3, hh, ww)
+            if blk.downsample is not None:
+                conv(blk.downsample[0], hh, ww)
+    for st in net.psp.stages:
+        s = st[0].output_size
+        s = s if isinstance(s, int) else s[0]
+        conv(st[1], s, s)
+    conv(net.psp.bottleneck, hh, ww)
+    for up in (net.up_1, net.up_2, net.up_3):
+        hh, ww = 2 * hh, 2 * ww
+        conv(up.conv[0], hh, ww)
+    conv(net.final[0], hh, ww)
+    return total
+
+
+def he_init_(net, seed=0):
+    """Random-init weights of the named architecture (no checkpoints offline): fan-in He init for convs, BN
+    gamma ~ U(.8,1.2) (x0.5 on block-closing bn3), running stats near (0,1) -- keeps eval-mode activations O(1)."""
+    import torch
+    import torch.nn as nn
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, m in net.named_modules():
+            if isinstance(m, nn.Conv2d):
+                fan_in = m.in_channels * m.kernel_size[0] * m.kernel_size[1]
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * (2.0 / fan_in) ** 0.5)
+                if m.bias is not None:
+                    m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.05)
+            elif isinstance(m, nn.BatchNorm2d):
+                gain = 0.5 if name.endswith("bn3") else 1.0
+                m.weight.copy_((torch.rand(m.weight.shape, generator=g) * 0.4 + 0.8) * gain)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.05)
+                m.running_mean.copy_(torch.randn(m.bias.shape, generator=g) * 0.05)
+                m.running_var.copy_(torch.rand(m.bias.shape, generator=g) * 0.8 + 0.6)
+    return net
+
+
+def synthetic_batch(batch, h, w, seed=SEED):
+    """RGB / IR in U(-1,1), the value range the reference's loaders produce (thermal_loader.py:649-659)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    rgb = torch.rand(batch, 3, h, w, generator=g) * 2 - 1
+    ir = torch.rand(batch, 1, h, w, generator=g) * 2 - 1
+    return rgb, ir
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, reasons, smax, pw = [], set(), None, []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax = float(parts[2]); pw.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        os.unlink(self.f.name)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm), power_w_max=max(pw))
+        return out
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------- CPU arms
+def cpu_forward_images_per_sec(h, w, images, threads=None):
+    """The oracle (= the reference's own torch CPU FP32 arithmetic) on `images` frames of h x w, one at a time."""
+    import torch
+    from oracle import heatnet_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    sd = O.recipe_fill(O.pspnet_state_dict(True, 4), seed=0)
+    rgb, ir = O.synthetic_inputs(1, h, w)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        for _ in range(images):
+            O.pspnet_forward(sd, rgb, ir, late_fusion=True, training=False)
+        dt = time.perf_counter() - t0
+    return images / dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (oracle port; /root/reference is Python that
+    cannot travel to the GPU box and has no compilable sources) on the host cores, one frame per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import heatnet_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    h, w = args.height, args.width
+    sd = O.recipe_fill(O.pspnet_state_dict(True, 4), seed=0)
+    rgb, ir = O.synthetic_inputs(1, h, w)
+    steps, warmup = args.steps, args.warmup
+    budget_s = 240.0
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        O.pspnet_forward(sd, rgb, ir, late_fusion=True, training=False)
+        first = time.perf_counter() - t0
+        done_w = 1
+        while done_w < warmup and (done_w + 1) * first < 0.3 * budget_s:
+            O.pspnet_forward(sd, rgb, ir, late_fusion=True, training=False)
+            done_w += 1
+        k = max(1, min(steps, int((budget_s - done_w * first) / max(first, 1e-3))))
+        t0 = time.perf_counter()
+        for _ in range(k):
+            O.pspnet_forward(sd, rgb, ir, late_fusion=True, training=False)
+        dt = time.perf_counter() - t0
+    v = k / dt
+    sample = f"{k} timed steps of 1 frame {h}x{w} each (FP32, torch CPU, {done_w} warm-up); steps capped to fit ~4 min"
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": k, "warmup": done_w,
+            "ms_per_step": 1000.0 * dt / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"PSPNet-ResNet50 RGB+thermal late-fusion forward, {h}x{w}, 1 frame per step on CPU"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--height", type=int, default=650)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layer-table", default=None, help="write the per-conv-launch timing table (JSON) here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__ as ge
+    if rank == 0 and not os.path.exists(ge.LIB):
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from heatnet_pub_b200 import _lib, engine as E, pspnet
+
+    B, H, W = args.batch, args.height, args.width
+    net = pspnet.PSPNet(sizes=(1, 2, 3, 6), psp_size=2048, deep_features_size=1024, backend='resnet50', in_channels=4,
+                        pretrained=False, late_fusion=True)
+    he_init_(net)
+    net = net.to(dev).eval().set_precision(args.precision)
+    rgb_h, ir_h = synthetic_batch(B, H, W, seed=SEED + rank)
+    rgb_h, ir_h = rgb_h.pin_memory(), ir_h.pin_memory()
+    rgb, ir = rgb_h.to(dev), ir_h.to(dev)
+    flops_img = conv_flops_per_image(net, H, W)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        with torch.no_grad():
+            logits, taps, _ = net(rgb, ir)
+        return logits
+
+    for _ in range(args.warmup):
+        out = step()
+    del out
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = E.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = E.launch_count - l0
+    clocks = sampler.stop() if sampler else None
+    Hout, Wout = out.shape[2], out.shape[3]
+    del out
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = t.item()
+    value = world * B * args.steps / (ms_max / 1000.0)
+
+    # ---- e2e: pinned host frames -> H2D -> forward -> device argmax -> D2H uint8 label maps
+    lib = _lib.load()
+    labels_d = torch.empty((B, Hout, Wout), dtype=torch.uint8, device=dev)
+    labels_h = torch.empty((B, Hout, Wout), dtype=torch.uint8).pin_memory()
+    rgb_d, ir_d = torch.empty_like(rgb), torch.empty_like(ir)
+
+    def e2e_step():
+        rgb_d.copy_(rgb_h, non_blocking=True)
+        ir_d.copy_(ir_h, non_blocking=True)
+        with torch.no_grad():
+            logits, _, _ = net(rgb_d, ir_d)
+        _lib.check(lib.hn_argmax_labels(logits.data_ptr(), B, Hout * Wout, logits.shape[1], labels_d.data_ptr(), None,
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        labels_h.copy_(labels_d, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (t.item() / 1000.0)
+    h2d = rgb_h.numel() * 4 + ir_h.numel() * 4
+    d2h = labels_h.numel()
+
+    # ---- roofline of the dominant kernel: events around every conv launch, separate instrumented pass
+    roofline = None
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        E.conv_timer = []
+        n_prof = min(args.steps, 3)
+        for _ in range(n_prof):
+            step()
+        torch.cuda.synchronize()
+        recs = E.conv_timer
+        E.conv_timer = None
+        conv_ms = sum(a.elapsed_time(b) for (_, a, b) in recs) / n_prof
+        n_conv = len(recs) // n_prof
+        total_flops = flops_img * B
+        achieved = total_flops / (conv_ms / 1000.0) / 1e12
+        peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])       # kernel timed inside a long step
+        roofline = {"kernel": "conv_tc_kernel (tcgen05 implicit GEMM; %d launches/step incl. im2col gathers)" % n_conv,
+                    "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "frac_of_burst_peak": achieved / peaks["bf16_tflops"], "peak_source": peak_src + " (sustained cuBLAS bf16)",
+                    "traffic": None, "conv_ms_per_step": conv_ms, "step_ms": ms_max / args.steps,
+                    "conv_share_of_step": conv_ms / (ms_max / args.steps), "algorithmic_gflop_per_image": flops_img / 1e9}
+        if args.layer_table:
+            per = {}
+            for (desc, a, b) in recs:
+                per.setdefault(desc, []).append(a.elapsed_time(b))
+            rows = [{"layer": k, "launches_per_step": len(v) // n_prof, "ms_per_step": sum(v) / n_prof} for k, v in per.items()]
+            json.dump(rows, open(args.layer_table, "w"), indent=1)
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            v, cores = cpu_forward_images_per_sec(H, W, images=2, threads=os.cpu_count())
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"2 frames of {H}x{W} through oracle.pspnet_forward (torch CPU FP32, the reference's arithmetic), one frame per call"}
+        except Exception as e:                                   # the baseline is reported, never required
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": f"PSPNet-ResNet50 RGB+thermal late-fusion forward (eval), batch {B} per GPU, {H}x{W} frames -> "
+                                       f"{Hout}x{Wout} logits, random-init weights",
+                           "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"image-sharded x{world}, no collective",
+                           "l2": "inputs and activations (GBs per step) far exceed the 126 MB L2; no explicit flush"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "what": "pinned host FP32 frames -> H2D -> PSPNet forward -> device argmax -> D2H uint8 label maps"},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -167,8 +167,8 @@ __global__ void bn_finalize_kernel(const double *sum, const double *sqsum, doubl
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) affine_act_kernel(const T *__restrict__ x, int ldx, const float *__restrict__ scale,
+template <typename TI, typename T>
+__global__ void __launch_bounds__(256) affine_act_kernel(const TI *__restrict__ x, int ldx, const float *__restrict__ scale,
                                                          const float *__restrict__ shift, const T *__restrict__ res, int ldr, int act,
                                                          float slope, const float *slope_ptr, T *__restrict__ y, int ldy, int64_t npix,
                                                          int C, int64_t pix_per_image)
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const T *__restrict__ x
         int64_t p = i / ncv;
         int c = (int)(i - p * ncv) * 8;
         float v[8];
-        Vec8<T>::load(x + p * ldx + c, v);
+        Vec8<TI>::load(x + p * ldx + c, v);
         if (scale) {
             // pix_per_image > 0: per-(image, channel) parameters (Dropout2d masks)
             const int64_t poff = pix_per_image > 0 ? (p / pix_per_image) * C : 0;
@@ -521,7 +521,8 @@ extern "C" int hn_bn_finalize(const double *sum, const double *sqsum, int64_t co
 extern "C" int hn_affine_act(const hn_tensor *x, const hn_epilogue *ep, const hn_tensor *y, void *stream)
 {
     HN_CHECK_ARG(x && y && ep && x->ptr && y->ptr, "hn_affine_act: null pointer");
-    HN_CHECK_ARG(x->dtype == y->dtype, "hn_affine_act: dtype mismatch");
+    HN_CHECK_ARG(x->dtype == y->dtype || (x->dtype == HN_F32 && y->dtype == HN_BF16),
+                 "hn_affine_act: x/y dtypes must match, or FP32 -> BF16");
     HN_CHECK_ARG(x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c, "hn_affine_act: shape mismatch");
     HN_CHECK_ARG(vec8_ok(x) && vec8_ok(y), "hn_affine_act: views must be 8-channel aligned");
     HN_CHECK_ARG(ep->scale != nullptr || ep->shift == nullptr, "hn_affine_act: shift given without scale");
@@ -530,14 +531,19 @@ extern "C" int hn_affine_act(const hn_tensor *x, const hn_epilogue *ep, const hn
     if (npix == 0) return HN_OK;
     int grid = wave_grid(npix * (x->c / 8), 256);
     cudaStream_t st = (cudaStream_t)stream;
-    if (x->dtype == HN_BF16)
-        affine_act_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x->ptr, x->ld, ep->scale, ep->shift,
-                                                             (const __nv_bfloat16 *)ep->residual, ep->residual_ld, ep->act, ep->slope,
-                                                             ep->slope_ptr, (__nv_bfloat16 *)y->ptr, y->ld, npix, x->c, ppi);
+    using bf16 = __nv_bfloat16;
+    if (y->dtype == HN_BF16 && x->dtype == HN_BF16)
+        affine_act_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16 *)x->ptr, x->ld, ep->scale, ep->shift, (const bf16 *)ep->residual,
+                                                          ep->residual_ld, ep->act, ep->slope, ep->slope_ptr, (bf16 *)y->ptr, y->ld, npix,
+                                                          x->c, ppi);
+    else if (y->dtype == HN_BF16)   // FP32 pre-normalisation values -> BF16 activations (train-mode BatchNorm2d)
+        affine_act_kernel<float, bf16><<<grid, 256, 0, st>>>((const float *)x->ptr, x->ld, ep->scale, ep->shift, (const bf16 *)ep->residual,
+                                                           ep->residual_ld, ep->act, ep->slope, ep->slope_ptr, (bf16 *)y->ptr, y->ld, npix,
+                                                           x->c, ppi);
     else
-        affine_act_kernel<float><<<grid, 256, 0, st>>>((const float *)x->ptr, x->ld, ep->scale, ep->shift, (const float *)ep->residual,
-                                                     ep->residual_ld, ep->act, ep->slope, ep->slope_ptr, (float *)y->ptr, y->ld, npix,
-                                                     x->c, ppi);
+        affine_act_kernel<float, float><<<grid, 256, 0, st>>>((const float *)x->ptr, x->ld, ep->scale, ep->shift, (const float *)ep->residual,
+                                                            ep->residual_ld, ep->act, ep->slope, ep->slope_ptr, (float *)y->ptr, y->ld, npix,
+                                                            x->c, ppi);
     HN_LAUNCH_CHECK();
     return HN_OK;
 }

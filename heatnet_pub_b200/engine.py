@@ -18,9 +18,12 @@ _TORCH_DTYPE = {HN_F32: torch.float32, HN_BF16: torch.bfloat16}
 _HN_DTYPE = {torch.float32: HN_F32, torch.bfloat16: HN_BF16}
 
 DEFAULT_PRECISION = os.environ.get("HEATNET_B200_PRECISION", "bf16")
+BN_TRAIN_RAW_FP32 = os.environ.get("HEATNET_B200_BN_RAW_FP32", "1") != "0"
 
 # number of libheatnet_b200 kernels enqueued by this process (bench.py reports it as gpu_launches)
 launch_count = 0
+# bench.py sets this to a list to collect (description, start_event, end_event) around every conv launch
+conv_timer = None
 
 
 def _stream():
@@ -263,8 +266,15 @@ def conv2d(x: Act, conv: torch.nn.Conv2d, scale=None, shift=None, residual: Opti
         ws_ptr = workspace(ws_bytes, x.buf.device).data_ptr()
         _count()
     ep = _epilogue(scale, shift, residual, act, slope, slope_ptr)
+    timing = conv_timer is not None
+    if timing:
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev_a.record()
     _lib.check(lib.hn_conv2d_fwd(C.byref(xh), wp.data_ptr(), C.byref(cv), C.byref(ep), C.byref(yh), ws_ptr, ws_bytes,
                                  _stream()))
+    if timing:
+        ev_b.record()
+        conv_timer.append((f"{x.c}->{conv.out_channels} k{cv.r} s{cv.stride} d{cv.dil} @{x.h}x{x.w}", ev_a, ev_b))
     _count()
     return out
 
@@ -315,9 +325,14 @@ def conv_bn_act(x: Act, conv, bn, act=ACT_NONE, slope=0.0, slope_ptr=None, resid
         scale, shift = folded_affine(conv, bn)
         return conv2d(x, conv, scale, shift, residual, act, slope, slope_ptr, out)
     scale, shift = folded_affine(conv, None)                      # conv bias only
-    y = conv2d(x, conv, scale, shift, None, ACT_NONE, out=out)
-    bscale, bshift, _, _ = batchnorm_train_affine(y, bn)
-    return affine_act(y, bscale, bshift, residual, act, slope, slope_ptr)
+    # The pre-normalisation tensor stays FP32: (x - mean) * invstd amplifies BF16 rounding of x by |mean|/std,
+    # which is large for channels with little spatial variation.  Statistics and the normalise pass read the
+    # FP32 values; only the normalised activation is rounded to the compute dtype.
+    raw = conv2d(x, conv, scale, shift, None, ACT_NONE, out_dtype=torch.float32 if BN_TRAIN_RAW_FP32 else None)
+    bscale, bshift, _, _ = batchnorm_train_affine(raw, bn)
+    if out is None:
+        out = raw if raw.dtype == x.dtype else new_act(raw.n, raw.h, raw.w, raw.c, x.dtype, x.buf.device)
+    return affine_act(raw, bscale, bshift, residual, act, slope, slope_ptr, out=out)
 
 
 def maxpool3x3s2(x: Act, out: Optional[Act] = None) -> Act:
