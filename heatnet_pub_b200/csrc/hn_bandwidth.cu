@@ -6,6 +6,15 @@
 
 namespace hn {
 
+// (rows, chunks-per-row) grid for the row-decomposed kernels: rows in grid.x (up to 2^31-1), at most 4 items per thread
+static inline dim3 row_grid(int64_t rows, int64_t items_per_row, int threads = 256)
+{
+    int64_t chunks = cdiv(items_per_row, (int64_t)threads * 4);
+    if (chunks < 1) chunks = 1;
+    if (chunks > 65535) chunks = 65535;
+    return dim3((unsigned)rows, (unsigned)chunks);
+}
+
 static inline int wave_grid(int64_t work_items, int threads, int waves_per_sm = 8)
 {
     int64_t want = cdiv(work_items, threads);
@@ -27,6 +36,36 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_smallc(const float *__restri
         const float *s = src + n * C * npix_per_img + p;
         T *d = dst + i * ld;
         for (int c = 0; c < C; ++c) d[c] = from_f32<T>(__ldg(s + (int64_t)c * npix_per_img));
+    }
+}
+
+// small-C NHWC -> NCHW (the logits: C = 13 in a 16-wide buffer): one thread per pixel reads its channel vector
+// (contiguous), writes C coalesced planes
+template <typename T>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_smallc(const T *__restrict__ src, float *__restrict__ dst, int64_t npix_per_img,
+                                                           int64_t n_img, int C, int ld)
+{
+    const int64_t total = npix_per_img * n_img;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n = i / npix_per_img, p = i - n * npix_per_img;
+        const T *s = src + i * ld;
+        float v[16];
+        if (sizeof(T) == 4 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+            for (int c = 0; c < 16; c += 4)
+                if (c < C) {
+                    float4 q = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(s) + c);
+                    v[c] = q.x; v[c + 1] = q.y; v[c + 2] = q.z; v[c + 3] = q.w;
+                }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+                if (c < C) v[c] = to_f32<T>(s[c]);
+        }
+        float *d = dst + n * C * npix_per_img + p;
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+            if (c < C) d[(int64_t)c * npix_per_img] = v[c];
     }
 }
 
@@ -174,11 +213,16 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const TI *__restrict__ 
                                                          int C, int64_t pix_per_image)
 {
     const int ncv = C / 8;
-    const int64_t total = npix * ncv;
     if (slope_ptr) slope = __ldg(slope_ptr);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t p = i / ncv;
-        int c = (int)(i - p * ncv) * 8;
+    // a CTA walks blocks of kPixPerBlock pixels; inside a block the (pixel, 8-channel vector) split is 32-bit math
+    constexpr int kPixPerBlock = 64;
+    const int64_t nblocks = (npix + kPixPerBlock - 1) / kPixPerBlock;
+    for (int64_t pb = blockIdx.x; pb < nblocks; pb += gridDim.x)
+    for (int i = threadIdx.x; i < kPixPerBlock * ncv; i += blockDim.x) {
+        const int pl = i / ncv;
+        const int64_t p = pb * kPixPerBlock + pl;
+        if (p >= npix) break;
+        const int c = (i - pl * ncv) * 8;
         float v[8];
         Vec8<TI>::load(x + p * ldx + c, v);
         if (scale) {
@@ -210,18 +254,19 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const TI *__restrict__ 
 // ------------------------------------------------------------------------------------------------
 // nn.MaxPool2d(3, 2, 1) (pads with -inf)
 // ------------------------------------------------------------------------------------------------
+// grid.x = output rows (n*Ho + ho), grid.y = chunks of the row's Wo * C/8 work items: no 64-bit div/mod per element
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool_kernel(const T *__restrict__ x, int ldx, T *__restrict__ y, int ldy, int N, int H, int W,
                                                       int Ho, int Wo, int C)
 {
     const int ncv = C / 8;
-    const int64_t total = (int64_t)N * Ho * Wo * ncv;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int c = (int)(i % ncv) * 8;
-        int64_t p = i / ncv;
-        int wo = (int)(p % Wo);
-        int ho = (int)((p / Wo) % Ho);
-        int n = (int)(p / ((int64_t)Wo * Ho));
+    const int row = blockIdx.x;
+    const int n = row / Ho, ho = row - n * Ho;
+    const int items = Wo * ncv;
+    const T *xin = x + (int64_t)n * H * W * ldx;
+    T *yrow = y + (int64_t)row * Wo * ldy;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < items; i += gridDim.y * blockDim.x) {
+        const int wo = i / ncv, c = (i - wo * ncv) * 8;
         float m[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
@@ -234,12 +279,12 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const T *__restrict__ x, i
                 int wi = 2 * wo - 1 + s;
                 if (wi < 0 || wi >= W) continue;
                 float v[8];
-                Vec8<T>::load(x + (((int64_t)n * H + hi) * W + wi) * ldx + c, v);
+                Vec8<T>::load(xin + ((int64_t)hi * W + wi) * ldx + c, v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
             }
         }
-        Vec8<T>::store(y + p * ldy + c, m);
+        Vec8<T>::store(yrow + (int64_t)wo * ldy + c, m);
     }
 }
 
@@ -341,32 +386,36 @@ __device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, 
     l1 = src - (float)i0;
 }
 
+// grid.x = output rows (n*Ho + ho), grid.y = chunks of the row's Wo * C/8 work items
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) bilinear_vec_kernel(const TI *__restrict__ x, int ldx, TO *__restrict__ y, int ldy, int N, int H,
                                                            int W, int Ho, int Wo, int C, float sh, float sw)
 {
     const int ncv = C / 8;
-    const int64_t total = (int64_t)N * Ho * Wo * ncv;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int c = (int)(i % ncv) * 8;
-        int64_t p = i / ncv;
-        int wo = (int)(p % Wo);
-        int ho = (int)((p / Wo) % Ho);
-        int n = (int)(p / ((int64_t)Wo * Ho));
-        int y0, y1, x0, x1;
-        float ly, lx;
-        bilinear_src(ho, sh, H, y0, y1, ly);
+    const int row = blockIdx.x;
+    const int n = row / Ho, ho = row - n * Ho;
+    int y0, y1;
+    float ly;
+    bilinear_src(ho, sh, H, y0, y1, ly);
+    const float hy = 1.f - ly;
+    const TI *r0 = x + ((int64_t)n * H + y0) * W * ldx;
+    const TI *r1 = x + ((int64_t)n * H + y1) * W * ldx;
+    TO *yrow = y + (int64_t)row * Wo * ldy;
+    const int items = Wo * ncv;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < items; i += gridDim.y * blockDim.x) {
+        const int wo = i / ncv, c = (i - wo * ncv) * 8;
+        int x0, x1;
+        float lx;
         bilinear_src(wo, sw, W, x0, x1, lx);
-        const TI *b = x + (int64_t)n * H * W * ldx + c;
         float a00[8], a01[8], a10[8], a11[8], o[8];
-        Vec8<TI>::load(b + ((int64_t)y0 * W + x0) * ldx, a00);
-        Vec8<TI>::load(b + ((int64_t)y0 * W + x1) * ldx, a01);
-        Vec8<TI>::load(b + ((int64_t)y1 * W + x0) * ldx, a10);
-        Vec8<TI>::load(b + ((int64_t)y1 * W + x1) * ldx, a11);
-        const float hy = 1.f - ly, hx = 1.f - lx;
+        Vec8<TI>::load(r0 + (int64_t)x0 * ldx + c, a00);
+        Vec8<TI>::load(r0 + (int64_t)x1 * ldx + c, a01);
+        Vec8<TI>::load(r1 + (int64_t)x0 * ldx + c, a10);
+        Vec8<TI>::load(r1 + (int64_t)x1 * ldx + c, a11);
+        const float hx = 1.f - lx;
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = hy * (hx * a00[j] + lx * a01[j]) + ly * (hx * a10[j] + lx * a11[j]);
-        Vec8<TO>::store(y + p * ldy + c, o);
+        Vec8<TO>::store(yrow + (int64_t)wo * ldy + c, o);
     }
 }
 
@@ -398,8 +447,7 @@ static int launch_bilinear(const hn_tensor *x, const hn_tensor *y, cudaStream_t 
 {
     const float sh = (float)x->h / (float)y->h, sw = (float)x->w / (float)y->w;
     if (vec8_ok(x) && vec8_ok(y)) {
-        int64_t total = (int64_t)y->n * y->h * y->w * (y->c / 8);
-        bilinear_vec_kernel<TI, TO><<<wave_grid(total, 256), 256, 0, st>>>((const TI *)x->ptr, x->ld, (TO *)y->ptr, y->ld, x->n, x->h,
+        bilinear_vec_kernel<TI, TO><<<row_grid((int64_t)y->n * y->h, (int64_t)y->w * (y->c / 8)), 256, 0, st>>>((const TI *)x->ptr, x->ld, (TO *)y->ptr, y->ld, x->n, x->h,
                                                                          x->w, y->h, y->w, x->c, sh, sw);
     } else {
         int64_t total = (int64_t)y->n * y->h * y->w * y->c;
@@ -444,6 +492,15 @@ extern "C" int hn_nhwc_to_nchw(const hn_tensor *src, float *dst, void *stream)
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t HW = (int64_t)src->h * src->w;
     if (HW * src->n == 0) return HN_OK;
+    if (src->c <= 16 && src->ld >= ((src->c + 3) / 4) * 4) {      // the float4 path may read up to 3 pad channels
+        int grid = wave_grid(HW * src->n, 256);
+        if (src->dtype == HN_BF16)
+            nhwc_to_nchw_smallc<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)src->ptr, dst, HW, src->n, src->c, src->ld);
+        else
+            nhwc_to_nchw_smallc<float><<<grid, 256, 0, st>>>((const float *)src->ptr, dst, HW, src->n, src->c, src->ld);
+        HN_LAUNCH_CHECK();
+        return HN_OK;
+    }
     dim3 grid((unsigned)cdiv(HW, 32), (unsigned)cdiv(src->c, 32), (unsigned)src->n);
     if (src->dtype == HN_BF16)
         transpose_tiles<__nv_bfloat16, false><<<grid, 256, 0, st>>>(src->ptr, dst, HW, src->c, src->ld);
@@ -529,7 +586,7 @@ extern "C" int hn_affine_act(const hn_tensor *x, const hn_epilogue *ep, const hn
     const int64_t npix = (int64_t)x->n * x->h * x->w;
     const int64_t ppi = ep->per_image ? (int64_t)x->h * x->w : 0;
     if (npix == 0) return HN_OK;
-    int grid = wave_grid(npix * (x->c / 8), 256);
+    int grid = wave_grid(cdiv(npix, 64) * 256, 256, 16);
     cudaStream_t st = (cudaStream_t)stream;
     using bf16 = __nv_bfloat16;
     if (y->dtype == HN_BF16 && x->dtype == HN_BF16)
@@ -557,7 +614,7 @@ extern "C" int hn_maxpool3x3s2_fwd(const hn_tensor *x, const hn_tensor *y, void 
     HN_CHECK_ARG(vec8_ok(x) && vec8_ok(y), "hn_maxpool3x3s2_fwd: views must be 8-channel aligned");
     int64_t total = (int64_t)y->n * y->h * y->w * (y->c / 8);
     if (total == 0) return HN_OK;
-    int grid = wave_grid(total, 256);
+    dim3 grid = row_grid((int64_t)y->n * y->h, (int64_t)y->w * (y->c / 8));
     cudaStream_t st = (cudaStream_t)stream;
     if (x->dtype == HN_BF16)
         maxpool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x->ptr, x->ld, (__nv_bfloat16 *)y->ptr, y->ld, x->n, x->h,

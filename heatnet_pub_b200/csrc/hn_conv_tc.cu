@@ -11,7 +11,8 @@
 // * Strided / small-Cin convolutions (7x7 s2 stems, 3x3 s2, 1x1 s2, the critics' 4x4 s2) first run a
 //   bandwidth-bound im2col gather into a workspace and then the flattened path with K = kpad.
 // * Warp-specialised persistent kernel: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-//   warps 4-7 = epilogue (tcgen05.ld -> scale/shift/residual/activation -> global).  Two TMEM accumulator
+//   warps 4-11 = epilogue (tcgen05.ld -> scale/shift/residual/activation -> global; the residual is
+//   prefetched into registers while the warp waits for the accumulator).  Two TMEM accumulator
 //   buffers let the epilogue of tile i overlap the main loop of tile i+1.
 #include <cuda.h>
 
@@ -23,7 +24,7 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 BF16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;   // 4 control warps + 8 epilogue warps
 constexpr int EPI_WARP0 = 4;
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -201,7 +202,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(tfull_bar + i), 1);
-            mbar_init(smem_u32(tempty_bar + i), 4);   // one arrive per epilogue warp
+            mbar_init(smem_u32(tempty_bar + i), BLOCK_N >= 64 ? 8 : 4);   // one arrive per working epilogue warp
         }
         fence_barrier_init();
     }
@@ -269,102 +270,127 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue =====================
-        const int q = warp - EPI_WARP0;          // == warp % 4: the TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;           // accumulator row = pixel within the tile
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        float slope = p.slope;
-        if (p.slope_ptr) slope = __ldg(p.slope_ptr);
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
-            const int ho = th * p.TH + row / p.TW, wo = tw * p.TW + row % p.TW;
-            const bool valid = ho < p.Ho && wo < p.Wo;
-            const int64_t pix = ((int64_t)img * p.Ho + ho) * p.Wo + wo;
-            mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
-            tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
-            constexpr int CHUNK = BLOCK_N < 32 ? 16 : 32;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += CHUNK) {
-                uint32_t raw[CHUNK];
-                if constexpr (CHUNK == 32) tmem_ld_32x32(taddr + c0, raw);
-                else tmem_ld_32x16(taddr + c0, raw);
-                tmem_ld_wait();
-                const int cbase = nt * BLOCK_N + c0;
-                if (valid && cbase < p.Cout) {
-                    float v[CHUNK];
+        // 8 warps: warp w may only touch TMEM lanes [32*(w%4), +32); warps 4-7 take the low half of the tile's
+        // columns, warps 8-11 the high half (narrow tiles: only the first group works).
+        constexpr int GROUPS = BLOCK_N >= 64 ? 2 : 1;
+        constexpr int COLS = BLOCK_N / GROUPS;                 // columns per warp
+        constexpr int CHUNK = COLS < 32 ? COLS : 32;           // columns per tcgen05.ld
+        constexpr int NCHUNK = COLS / CHUNK;
+        const int ew = warp - EPI_WARP0;
+        const int q = ew & 3, grp = ew >> 2;
+        if (grp < GROUPS) {
+            const int row = q * 32 + lane;                     // accumulator row = pixel within the tile
+            const int col0 = grp * COLS;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            float slope = p.slope;
+            if (p.slope_ptr) slope = __ldg(p.slope_ptr);
+            const bool res_vec = p.res != nullptr && (p.ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
+                const int ho = th * p.TH + row / p.TW, wo = tw * p.TW + row % p.TW;
+                const bool valid = ho < p.Ho && wo < p.Wo;
+                const int64_t pix = ((int64_t)img * p.Ho + ho) * p.Wo + wo;
+                const int ctile = nt * BLOCK_N + col0;         // first output channel of this warp's columns
+                const __nv_bfloat16 *rrow = (const __nv_bfloat16 *)p.res + pix * p.ldr + ctile;
+                // residual prefetch, double-buffered in registers: the loads for chunk 0 are in flight while the
+                // warp waits for the accumulator, the loads for chunk i+1 while chunk i is processed
+                uint4 rbuf[2][CHUNK / 8 > 0 ? CHUNK / 8 : 1];
+                auto prefetch_res = [&](int ci, uint4 (&dst)[CHUNK / 8 > 0 ? CHUNK / 8 : 1]) {
+                    if (res_vec && valid && ctile + (ci + 1) * CHUNK <= p.Cout) {
 #pragma unroll
-                    for (int j = 0; j < CHUNK; ++j) v[j] = __uint_as_float(raw[j]);
-                    const bool full = cbase + CHUNK <= p.Cout;
-                    if (p.scale) {
-                        if (full) {   // warp-uniform 16-byte broadcast loads
-#pragma unroll
-                            for (int j = 0; j < CHUNK; j += 4) {
-                                const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + cbase + j));
-                                const float4 sh = __ldg(reinterpret_cast<const float4 *>(p.shift + cbase + j));
-                                v[j] = fmaf(v[j], sc.x, sh.x);
-                                v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
-                                v[j + 2] = fmaf(v[j + 2], sc.z, sh.z);
-                                v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < CHUNK; ++j)
-                                if (cbase + j < p.Cout) v[j] = fmaf(v[j], __ldg(p.scale + cbase + j), __ldg(p.shift + cbase + j));
-                        }
+                        for (int j = 0; j < CHUNK / 8; ++j) dst[j] = __ldg(reinterpret_cast<const uint4 *>(rrow + ci * CHUNK) + j);
                     }
-                    if (p.res) {
-                        const __nv_bfloat16 *rp = (const __nv_bfloat16 *)p.res + pix * p.ldr + cbase;
-                        if (full && (p.ldr & 7) == 0) {
+                };
+                prefetch_res(0, rbuf[0]);
+                mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
+                tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + col0;
 #pragma unroll
-                            for (int j = 0; j < CHUNK; j += 8) {
-                                float r8[8];
-                                Vec8<__nv_bfloat16>::load(rp + j, r8);
+                for (int ci = 0; ci < NCHUNK; ++ci) {
+                    uint32_t raw[CHUNK];
+                    if constexpr (CHUNK == 32) tmem_ld_32x32(taddr + ci * CHUNK, raw);
+                    else if constexpr (CHUNK == 16) tmem_ld_32x16(taddr + ci * CHUNK, raw);
+                    if (ci + 1 < NCHUNK) prefetch_res(ci + 1, rbuf[(ci + 1) & 1]);
+                    tmem_ld_wait();
+                    const int cbase = ctile + ci * CHUNK;
+                    if (valid && cbase < p.Cout) {
+                        float v[CHUNK];
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) v[j + i] += r8[i];
+                        for (int j = 0; j < CHUNK; ++j) v[j] = __uint_as_float(raw[j]);
+                        const bool full = cbase + CHUNK <= p.Cout;
+                        if (p.scale) {
+                            if (full) {   // warp-uniform 16-byte broadcast loads
+#pragma unroll
+                                for (int j = 0; j < CHUNK; j += 4) {
+                                    const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + cbase + j));
+                                    const float4 sh = __ldg(reinterpret_cast<const float4 *>(p.shift + cbase + j));
+                                    v[j] = fmaf(v[j], sc.x, sh.x);
+                                    v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
+                                    v[j + 2] = fmaf(v[j + 2], sc.z, sh.z);
+                                    v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < CHUNK; ++j)
+                                    if (cbase + j < p.Cout) v[j] = fmaf(v[j], __ldg(p.scale + cbase + j), __ldg(p.shift + cbase + j));
+                            }
+                        }
+                        if (p.res) {
+                            if (res_vec && full) {
+#pragma unroll
+                                for (int j = 0; j < CHUNK / 8; ++j) {
+                                    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&rbuf[ci & 1][j]);
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        const float2 f = __bfloat1622float2(h[i]);
+                                        v[8 * j + 2 * i] += f.x;
+                                        v[8 * j + 2 * i + 1] += f.y;
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < CHUNK; ++j)
+                                    if (cbase + j < p.Cout) v[j] += __bfloat162float(rrow[ci * CHUNK + j]);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < CHUNK; ++j) v[j] = apply_act(v[j], p.act, slope);
+                        if (p.y_f32) {
+                            float *yp = (float *)p.y + pix * p.ldy + cbase;
+                            if (full && (p.ldy & 3) == 0) {
+#pragma unroll
+                                for (int j = 0; j < CHUNK; j += 4) *reinterpret_cast<float4 *>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < CHUNK; ++j)
+                                    if (cbase + j < p.Cout) yp[j] = v[j];
                             }
                         } else {
+                            __nv_bfloat16 *yp = (__nv_bfloat16 *)p.y + pix * p.ldy + cbase;
+                            if (full && (p.ldy & 7) == 0) {
 #pragma unroll
-                            for (int j = 0; j < CHUNK; ++j)
-                                if (cbase + j < p.Cout) v[j] += __bfloat162float(rp[j]);
-                        }
-                    }
+                                for (int j = 0; j < CHUNK; j += 8) {
+                                    float o8[8];
 #pragma unroll
-                    for (int j = 0; j < CHUNK; ++j) v[j] = apply_act(v[j], p.act, slope);
-                    if (p.y_f32) {
-                        float *yp = (float *)p.y + pix * p.ldy + cbase;
-                        if (full && (p.ldy & 3) == 0) {
+                                    for (int i = 0; i < 8; ++i) o8[i] = v[j + i];
+                                    Vec8<__nv_bfloat16>::store(yp + j, o8);
+                                }
+                            } else {
 #pragma unroll
-                            for (int j = 0; j < CHUNK; j += 4) *reinterpret_cast<float4 *>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < CHUNK; ++j)
-                                if (cbase + j < p.Cout) yp[j] = v[j];
-                        }
-                    } else {
-                        __nv_bfloat16 *yp = (__nv_bfloat16 *)p.y + pix * p.ldy + cbase;
-                        if (full && (p.ldy & 7) == 0) {
-#pragma unroll
-                            for (int j = 0; j < CHUNK; j += 8) {
-                                float o8[8];
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) o8[i] = v[j + i];
-                                Vec8<__nv_bfloat16>::store(yp + j, o8);
+                                for (int j = 0; j < CHUNK; ++j)
+                                    if (cbase + j < p.Cout) yp[j] = __float2bfloat16_rn(v[j]);
                             }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < CHUNK; ++j)
-                                if (cbase + j < p.Cout) yp[j] = __float2bfloat16_rn(v[j]);
                         }
                     }
                 }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
             }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
         }
     }
 
@@ -377,21 +403,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------ im2col gather
-// A[m][k], k = (r*S+s)*Cin + c, zero for padding and for k >= R*S*Cin.  Thread = (pixel, 8 consecutive k).
+// A[m][k], k = (r*S+s)*Cin + c, zero for padding and for k >= R*S*Cin.
+// grid.x = output rows (n*Ho + ho), grid.y = chunks of the row's Wo * kpad/8 work items; thread = 8 consecutive k.
 __global__ void __launch_bounds__(256) im2col_bf16_kernel(const __nv_bfloat16 *__restrict__ x, int ldx, int N, int H, int W, int C,
                                                           int Ho, int Wo, int R, int S, int stride, int pad, int dil, int kpad,
                                                           __nv_bfloat16 *__restrict__ a)
 {
     const int k8n = kpad / 8;
-    const int64_t total = (int64_t)N * Ho * Wo * k8n;
     const int K = R * S * C;
     const bool vec = (C % 8 == 0) && (ldx % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int k0 = (int)(i % k8n) * 8;
-        const int64_t m = i / k8n;
-        const int wo = (int)(m % Wo);
-        const int ho = (int)((m / Wo) % Ho);
-        const int n = (int)(m / ((int64_t)Wo * Ho));
+    const int row = blockIdx.x;
+    const int n = row / Ho, ho = row - n * Ho;
+    const __nv_bfloat16 *xin = x + (int64_t)n * H * W * ldx;
+    __nv_bfloat16 *arow = a + (int64_t)row * Wo * kpad;
+    const int items = Wo * k8n;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < items; i += gridDim.y * blockDim.x) {
+        const int wo = i / k8n;
+        const int k0 = (i - wo * k8n) * 8;
         uint4 out = make_uint4(0, 0, 0, 0);
         if (vec) {
             if (k0 < K) {
@@ -399,22 +427,25 @@ __global__ void __launch_bounds__(256) im2col_bf16_kernel(const __nv_bfloat16 *_
                 int r = tap / S, s = tap - r * S;
                 int hi = ho * stride - pad + r * dil, wi = wo * stride - pad + s * dil;
                 if (hi >= 0 && hi < H && wi >= 0 && wi < W)
-                    out = *reinterpret_cast<const uint4 *>(x + (((int64_t)n * H + hi) * W + wi) * ldx + c);
+                    out = *reinterpret_cast<const uint4 *>(xin + ((int64_t)hi * W + wi) * ldx + c);
             }
         } else {
             __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(&out);
+            int tap = k0 / C, c = k0 - tap * C;
+            int r = tap / S, s = tap - r * S;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                int k = k0 + j;
-                if (k < K) {
-                    int tap = k / C, c = k - tap * C;
-                    int r = tap / S, s = tap - r * S;
+                if (k0 + j < K) {
                     int hi = ho * stride - pad + r * dil, wi = wo * stride - pad + s * dil;
-                    if (hi >= 0 && hi < H && wi >= 0 && wi < W) o[j] = x[(((int64_t)n * H + hi) * W + wi) * ldx + c];
+                    if (hi >= 0 && hi < H && wi >= 0 && wi < W) o[j] = xin[((int64_t)hi * W + wi) * ldx + c];
+                }
+                if (++c == C) {      // next filter tap
+                    c = 0;
+                    if (++s == S) { s = 0; ++r; }
                 }
             }
         }
-        *reinterpret_cast<uint4 *>(a + m * kpad + k0) = out;
+        *reinterpret_cast<uint4 *>(arow + (int64_t)wo * kpad + k0) = out;
     }
 }
 
@@ -518,9 +549,8 @@ int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn
                 return HN_ERR_WORKSPACE;
             }
             HN_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 127) == 0, "conv_tc: workspace must be 128-byte aligned");
-            const int64_t total = M * (kpad / 8);
-            int64_t want = cdiv(total, 256);
-            int grid = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
+            int64_t chunks = cdiv((int64_t)Wo * (kpad / 8), 1024);
+            dim3 grid((unsigned)(x->n * Ho), (unsigned)(chunks < 1 ? 1 : (chunks > 65535 ? 65535 : chunks)));
             im2col_bf16_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x->ptr, x->ld, x->n, x->h, x->w, x->c, Ho, Wo, cv->r, cv->s,
                                                     cv->stride, cv->pad, cv->dil, kpad, (__nv_bfloat16 *)ws);
             HN_LAUNCH_CHECK();
