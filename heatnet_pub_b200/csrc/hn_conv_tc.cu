@@ -15,6 +15,7 @@
 //   prefetched into registers while the warp waits for the accumulator).  Two TMEM accumulator
 //   buffers let the epilogue of tile i overlap the main loop of tile i+1.
 #include <cuda.h>
+#include <string.h>
 
 #include "hn_common.cuh"
 
@@ -74,6 +75,29 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map
         "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// shared -> global tensor store (bulk async-group completion); out-of-range box elements are clipped
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+                 "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -168,11 +192,18 @@ struct TcParams {
     int act;
     float slope;
     const float *slope_ptr;
+    // TMA epilogue: output (and residual) go through a swizzled shared-memory staging tile per epilogue warp
+    int tma_out, tma_res;
+    int ebw;                       // staging box = {128 B of channels, ebw pixels, 32/ebw rows, 1}: ebw = min(TW, 32)
 };
+
+constexpr int EPI_STAGE_BYTES = 32 * 128;   // 32 pixels x 128 B per epilogue warp
+constexpr int NUM_EPI_WARPS = 8;
 
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcParams p)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_r, const TcParams p)
 {
     constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -182,9 +213,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint8_t *epi_stage = smem + STAGES * STAGE_BYTES;                       // NUM_EPI_WARPS x 4 KB, 1024-aligned
+    uint64_t *bars = reinterpret_cast<uint64_t *>(epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES);
     uint64_t *full_bar = bars, *empty_bar = bars + STAGES, *tfull_bar = bars + 2 * STAGES, *tempty_bar = bars + 2 * STAGES + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+    uint64_t *res_bar = bars + 2 * STAGES + 4;                              // one per epilogue warp
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4 + NUM_EPI_WARPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_m_tiles = p.n_img * p.tiles_h * p.tiles_w;
@@ -194,6 +227,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
         prefetch_tmap(&tmap_b);
+        if (p.tma_out) prefetch_tmap(&tmap_y);
+        if (p.tma_res) prefetch_tmap(&tmap_r);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -202,8 +237,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(tfull_bar + i), 1);
-            mbar_init(smem_u32(tempty_bar + i), BLOCK_N >= 64 ? 8 : 4);   // one arrive per working epilogue warp
+            mbar_init(smem_u32(tempty_bar + i), BLOCK_N >= 128 ? 8 : 4);   // one arrive per working epilogue warp
         }
+        for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(smem_u32(res_bar + i), 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -270,17 +306,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue =====================
-        // 8 warps: warp w may only touch TMEM lanes [32*(w%4), +32); warps 4-7 take the low half of the tile's
-        // columns, warps 8-11 the high half (narrow tiles: only the first group works).
-        constexpr int GROUPS = BLOCK_N >= 64 ? 2 : 1;
+        // Warp w may only touch TMEM lanes [32*(w%4), +32): one accumulator row (= output pixel) per thread.
+        // Wide tiles (>= 128 columns) are split between two groups of 4 warps.  Per 128-byte chunk of a row's
+        // channels the warp: (optionally) TMA-loads the residual chunk into its private staging tile, tcgen05.ld's
+        // the accumulator, applies scale/shift/residual/activation, writes the row back into the (128B-swizzled,
+        // bank-conflict-free) staging tile and one lane TMA-stores the 32-pixel x 128-byte box.  Global traffic is
+        // therefore full-line bulk transfers; the LSU only sees shared memory.  Views that TMA cannot address
+        // (channel stride or base not 16-byte aligned) take the direct per-thread path.
+        constexpr int GROUPS = BLOCK_N >= 128 ? 2 : 1;
         constexpr int COLS = BLOCK_N / GROUPS;                 // columns per warp
-        constexpr int CHUNK = COLS < 32 ? COLS : 32;           // columns per tcgen05.ld
-        constexpr int NCHUNK = COLS / CHUNK;
+        constexpr int SUB = COLS < 32 ? COLS : 32;             // columns per tcgen05.ld
         const int ew = warp - EPI_WARP0;
         const int q = ew & 3, grp = ew >> 2;
         if (grp < GROUPS) {
             const int row = q * 32 + lane;                     // accumulator row = pixel within the tile
             const int col0 = grp * COLS;
+            const int esz = p.y_f32 ? 4 : 2;
+            const int tch = 128 / esz;                         // columns per staging chunk (128 B per pixel)
+            const uint32_t stage = smem_u32(epi_stage + ew * EPI_STAGE_BYTES);
+            const uint32_t srow = stage + lane * 128;          // this thread's pixel row in the staging tile
+            const uint32_t rbar = smem_u32(res_bar + ew);
+            uint32_t rphase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             float slope = p.slope;
@@ -293,37 +339,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const bool valid = ho < p.Ho && wo < p.Wo;
                 const int64_t pix = ((int64_t)img * p.Ho + ho) * p.Wo + wo;
                 const int ctile = nt * BLOCK_N + col0;         // first output channel of this warp's columns
+                // coordinates of this warp's 32-pixel box (first pixel = row q*32 of the tile)
+                const int bx = tw * p.TW + (q * 32) % p.TW, by = th * p.TH + (q * 32) / p.TW;
                 const __nv_bfloat16 *rrow = (const __nv_bfloat16 *)p.res + pix * p.ldr + ctile;
-                // residual prefetch, double-buffered in registers: the loads for chunk 0 are in flight while the
-                // warp waits for the accumulator, the loads for chunk i+1 while chunk i is processed
-                uint4 rbuf[2][CHUNK / 8 > 0 ? CHUNK / 8 : 1];
-                auto prefetch_res = [&](int ci, uint4 (&dst)[CHUNK / 8 > 0 ? CHUNK / 8 : 1]) {
-                    if (res_vec && valid && ctile + (ci + 1) * CHUNK <= p.Cout) {
-#pragma unroll
-                        for (int j = 0; j < CHUNK / 8; ++j) dst[j] = __ldg(reinterpret_cast<const uint4 *>(rrow + ci * CHUNK) + j);
+                bool waited = false;
+                for (int ck = 0; ck < COLS; ck += tch) {
+                    const bool chunk_on = ctile + ck < p.Cout;          // warp-uniform
+                    if (p.tma_out && lane == 0) {
+                        bulk_wait_read0();                               // previous store has drained the staging tile
+                        if (p.tma_res && chunk_on) {
+                            mbar_expect_tx(rbar, EPI_STAGE_BYTES);
+                            tma_load_4d(stage, &tmap_r, rbar, ctile + ck, bx, by, img);
+                        }
                     }
-                };
-                prefetch_res(0, rbuf[0]);
-                mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
-                tcgen05_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + col0;
+                    if (p.tma_out) __syncwarp();
+                    if (!waited) {
+                        mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
+                        tcgen05_fence_after();
+                        waited = true;
+                    }
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + col0 + ck;
+                    if (p.tma_res && chunk_on) {
+                        mbar_wait(rbar, rphase);
+                        rphase ^= 1;
+                    }
+                    const int nsub = (tch < COLS - ck ? tch : COLS - ck) / SUB;
+                    for (int si = 0; si < nsub; ++si) {
+                        uint32_t raw[SUB];
+                        if constexpr (SUB == 32) tmem_ld_32x32(taddr + si * SUB, raw);
+                        else if constexpr (SUB == 16) tmem_ld_32x16(taddr + si * SUB, raw);
+                        tmem_ld_wait();
+                        const int cbase = ctile + ck + si * SUB;
+                        if (!chunk_on) continue;
+                        float v[SUB];
 #pragma unroll
-                for (int ci = 0; ci < NCHUNK; ++ci) {
-                    uint32_t raw[CHUNK];
-                    if constexpr (CHUNK == 32) tmem_ld_32x32(taddr + ci * CHUNK, raw);
-                    else if constexpr (CHUNK == 16) tmem_ld_32x16(taddr + ci * CHUNK, raw);
-                    if (ci + 1 < NCHUNK) prefetch_res(ci + 1, rbuf[(ci + 1) & 1]);
-                    tmem_ld_wait();
-                    const int cbase = ctile + ci * CHUNK;
-                    if (valid && cbase < p.Cout) {
-                        float v[CHUNK];
-#pragma unroll
-                        for (int j = 0; j < CHUNK; ++j) v[j] = __uint_as_float(raw[j]);
-                        const bool full = cbase + CHUNK <= p.Cout;
+                        for (int j = 0; j < SUB; ++j) v[j] = __uint_as_float(raw[j]);
+                        const bool full = cbase + SUB <= p.Cout;
                         if (p.scale) {
                             if (full) {   // warp-uniform 16-byte broadcast loads
 #pragma unroll
-                                for (int j = 0; j < CHUNK; j += 4) {
+                                for (int j = 0; j < SUB; j += 4) {
                                     const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + cbase + j));
                                     const float4 sh = __ldg(reinterpret_cast<const float4 *>(p.shift + cbase + j));
                                     v[j] = fmaf(v[j], sc.x, sh.x);
@@ -333,15 +388,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                 }
                             } else {
 #pragma unroll
-                                for (int j = 0; j < CHUNK; ++j)
+                                for (int j = 0; j < SUB; ++j)
                                     if (cbase + j < p.Cout) v[j] = fmaf(v[j], __ldg(p.scale + cbase + j), __ldg(p.shift + cbase + j));
                             }
                         }
                         if (p.res) {
-                            if (res_vec && full) {
+                            if (p.tma_res) {          // residual chunk sits in the staging tile (BF16, swizzled)
 #pragma unroll
-                                for (int j = 0; j < CHUNK / 8; ++j) {
-                                    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&rbuf[ci & 1][j]);
+                                for (int j = 0; j < SUB / 8; ++j) {
+                                    const uint4 rv = lds128(srow + ((((si * SUB) >> 3) + j) ^ (lane & 7)) * 16);
+                                    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&rv);
 #pragma unroll
                                     for (int i = 0; i < 4; ++i) {
                                         const float2 f = __bfloat1622float2(h[i]);
@@ -349,39 +405,77 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                         v[8 * j + 2 * i + 1] += f.y;
                                     }
                                 }
-                            } else {
+                            } else if (valid) {
+                                if (res_vec && full) {
 #pragma unroll
-                                for (int j = 0; j < CHUNK; ++j)
-                                    if (cbase + j < p.Cout) v[j] += __bfloat162float(rrow[ci * CHUNK + j]);
+                                    for (int j = 0; j < SUB / 8; ++j) {
+                                        float r8[8];
+                                        Vec8<__nv_bfloat16>::load(rrow + ck + si * SUB + 8 * j, r8);
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) v[8 * j + i] += r8[i];
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < SUB; ++j)
+                                        if (cbase + j < p.Cout) v[j] += __bfloat162float(rrow[ck + si * SUB + j]);
+                                }
                             }
                         }
 #pragma unroll
-                        for (int j = 0; j < CHUNK; ++j) v[j] = apply_act(v[j], p.act, slope);
-                        if (p.y_f32) {
-                            float *yp = (float *)p.y + pix * p.ldy + cbase;
-                            if (full && (p.ldy & 3) == 0) {
+                        for (int j = 0; j < SUB; ++j) v[j] = apply_act(v[j], p.act, slope);
+                        if (p.tma_out) {
+                            if (p.y_f32) {
 #pragma unroll
-                                for (int j = 0; j < CHUNK; j += 4) *reinterpret_cast<float4 *>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < CHUNK; ++j)
-                                    if (cbase + j < p.Cout) yp[j] = v[j];
-                            }
-                        } else {
-                            __nv_bfloat16 *yp = (__nv_bfloat16 *)p.y + pix * p.ldy + cbase;
-                            if (full && (p.ldy & 7) == 0) {
-#pragma unroll
-                                for (int j = 0; j < CHUNK; j += 8) {
-                                    float o8[8];
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) o8[i] = v[j + i];
-                                    Vec8<__nv_bfloat16>::store(yp + j, o8);
+                                for (int j = 0; j < SUB / 4; ++j) {
+                                    uint4 o = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                                                         __float_as_uint(v[4 * j + 3]));
+                                    sts128(srow + ((((si * SUB) >> 2) + j) ^ (lane & 7)) * 16, o);
                                 }
                             } else {
 #pragma unroll
-                                for (int j = 0; j < CHUNK; ++j)
-                                    if (cbase + j < p.Cout) yp[j] = __float2bfloat16_rn(v[j]);
+                                for (int j = 0; j < SUB / 8; ++j) {
+                                    uint4 o;
+                                    __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+                                    sts128(srow + ((((si * SUB) >> 3) + j) ^ (lane & 7)) * 16, o);
+                                }
                             }
+                        } else if (valid) {
+                            if (p.y_f32) {
+                                float *yp = (float *)p.y + pix * p.ldy + cbase;
+                                if (full && (p.ldy & 3) == 0) {
+#pragma unroll
+                                    for (int j = 0; j < SUB; j += 4) *reinterpret_cast<float4 *>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < SUB; ++j)
+                                        if (cbase + j < p.Cout) yp[j] = v[j];
+                                }
+                            } else {
+                                __nv_bfloat16 *yp = (__nv_bfloat16 *)p.y + pix * p.ldy + cbase;
+                                if (full && (p.ldy & 7) == 0) {
+#pragma unroll
+                                    for (int j = 0; j < SUB; j += 8) {
+                                        float o8[8];
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) o8[i] = v[j + i];
+                                        Vec8<__nv_bfloat16>::store(yp + j, o8);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < SUB; ++j)
+                                        if (cbase + j < p.Cout) yp[j] = __float2bfloat16_rn(v[j]);
+                                }
+                            }
+                        }
+                    }
+                    if (p.tma_out) {
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0 && chunk_on) {
+                            tma_store_4d(&tmap_y, stage, ctile + ck, bx, by, img);
+                            bulk_commit();
                         }
                     }
                 }
@@ -391,6 +485,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
+            if (p.tma_out && lane == 0) bulk_wait_read0();    // staging tile must outlive the last bulk store
         }
     }
 
@@ -467,7 +562,8 @@ static PFN_encodeTiled get_encode()
 }
 
 // BF16 tensor map over up to 4 dims (innermost first), 128B swizzle, zero OOB fill
-static int make_tmap(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box)
+static int make_tmap(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box,
+                     CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) {
@@ -483,7 +579,7 @@ static int make_tmap(CUtensorMap *m, const void *base, int rank, const uint64_t 
         es[i] = 1;
         if (i > 0) gs[i - 1] = strides_bytes[i];
     }
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, es,
+    CUresult r = enc(m, dtype, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -509,16 +605,19 @@ int64_t conv2d_tc_workspace(const hn_tensor *x, const hn_conv *cv)
 }
 
 template <int BN, int STAGES>
-static int launch_tc(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, int num_tiles, cudaStream_t st)
+static int launch_tc(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &ty, const CUtensorMap &tr, const TcParams &p,
+                     int num_tiles, cudaStream_t st)
 {
-    constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * BLOCK_K * 2) + (2 * STAGES + 4) * 8 + 16 + 1024;
+    constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * BLOCK_K * 2) + NUM_EPI_WARPS * EPI_STAGE_BYTES +
+                            (2 * STAGES + 4 + NUM_EPI_WARPS) * 8 + 16 + 1024;
+    static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
     static bool configured = false;
     if (!configured) {
         HN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    conv_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, st>>>(ta, tb, p);
+    conv_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, st>>>(ta, tb, ty, tr, p);
     HN_LAUNCH_CHECK();
     return HN_OK;
 }
@@ -609,12 +708,35 @@ int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn
     p.scale = ep->scale; p.shift = ep->shift; p.res = ep->residual; p.ldr = ep->residual_ld;
     p.act = ep->act; p.slope = ep->slope; p.slope_ptr = ep->slope_ptr;
     const int num_tiles = num_m_tiles * p.n_tiles;
+    // epilogue tensor maps: the output view (and the residual view) as {C, W, H, N} with a {128 B, ebw, 32/ebw, 1} box
+    CUtensorMap ty, tr;
+    memset(&ty, 0, sizeof(ty));
+    memset(&tr, 0, sizeof(tr));
+    p.ebw = p.TW < 32 ? p.TW : 32;
+    {
+        const uint64_t esz = p.y_f32 ? 4 : 2;
+        const bool ok = (reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0 && ((uint64_t)y->ld * esz) % 16 == 0;
+        if (ok) {
+            uint64_t dims[4] = {(uint64_t)cv->cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.n_img};
+            uint64_t strides[4] = {esz, (uint64_t)y->ld * esz, (uint64_t)y->ld * esz * p.Wo, (uint64_t)y->ld * esz * p.Wo * p.Ho};
+            uint32_t box[4] = {(uint32_t)(128 / esz), (uint32_t)p.ebw, (uint32_t)(32 / p.ebw), 1};
+            int rc = make_tmap(&ty, y->ptr, 4, dims, strides, box, p.y_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+            if (rc) return rc;
+            p.tma_out = 1;
+            if (ep->residual && !p.y_f32 && (reinterpret_cast<uintptr_t>(ep->residual) & 15) == 0 && ((uint64_t)ep->residual_ld * 2) % 16 == 0) {
+                uint64_t rs[4] = {2, (uint64_t)ep->residual_ld * 2, (uint64_t)ep->residual_ld * 2 * p.Wo, (uint64_t)ep->residual_ld * 2 * p.Wo * p.Ho};
+                rc = make_tmap(&tr, ep->residual, 4, dims, rs, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+                if (rc) return rc;
+                p.tma_res = 1;
+            }
+        }
+    }
     switch (bn) {
-        case 256: return launch_tc<256, 4>(ta, tb, p, num_tiles, st);
-        case 128: return launch_tc<128, 6>(ta, tb, p, num_tiles, st);
-        case 64: return launch_tc<64, 8>(ta, tb, p, num_tiles, st);
-        case 32: return launch_tc<32, 8>(ta, tb, p, num_tiles, st);
-        case 16: return launch_tc<16, 8>(ta, tb, p, num_tiles, st);
+        case 256: return launch_tc<256, 4>(ta, tb, ty, tr, p, num_tiles, st);
+        case 128: return launch_tc<128, 6>(ta, tb, ty, tr, p, num_tiles, st);
+        case 64: return launch_tc<64, 7>(ta, tb, ty, tr, p, num_tiles, st);
+        case 32: return launch_tc<32, 8>(ta, tb, ty, tr, p, num_tiles, st);
+        case 16: return launch_tc<16, 8>(ta, tb, ty, tr, p, num_tiles, st);
     }
     set_error("conv_tc: unsupported Cout tile %d", bn);
     return HN_ERR_ARG;
