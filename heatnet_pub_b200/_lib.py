@@ -51,6 +51,19 @@ SIGNATURES = {
     "hn_affine_act": (C.c_int, [_T, _E, _T, _P]),
     "hn_channel_stats": (C.c_int, [_T, _P, _P, _P]),
     "hn_bn_finalize": (C.c_int, [_P, _P, _I64, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _I32, _P]),
+    "hn_act_bwd": (C.c_int, [_T, _T, _I32, _F, _T, _P]),
+    "hn_bn_bwd": (C.c_int, [_T, _T, _T, _P, _P, _P, _I32, _F, _P, _P, _T, _T, _I32, _I32, _P]),
+    "hn_accumulate": (C.c_int, [_T, _T, _I32, _P]),
+    "hn_maxpool3x3s2_fwd_idx": (C.c_int, [_T, _T, _P, _P]),
+    "hn_maxpool3x3s2_bwd": (C.c_int, [_T, _P, _T, _I32, _P]),
+    "hn_bilinear_bwd": (C.c_int, [_T, _T, _I32, _P]),
+    "hn_pyramid_pool_bwd": (C.c_int, [_P, C.POINTER(_I32), _I32, _T, _I32, _P]),
+    "hn_dilate": (C.c_int, [_T, _I32, _T, _P]),
+    "hn_pack_weight_dgrad": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "hn_conv2d_wgrad_workspace_bytes": (_I64, [_T, _CV]),
+    "hn_conv2d_wgrad": (C.c_int, [_T, _T, _CV, _P, _I32, _P, _I64, _P]),
+    "hn_unpack_wgrad": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "hn_vec_to_grad": (C.c_int, [_P, _P, _I32, _I32, _P]),
     "hn_confusion": (C.c_int, [_P, _P, _I64, _I64, _P, _I32, _P, _P, _P]),
     "hn_argmax_labels": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _P]),
 }

@@ -1,0 +1,716 @@
+// Bandwidth-bound backward kernels on NHWC views: activation / BatchNorm2d(train) backward, max-pool backward
+// (saved window indices), bilinear and pyramid-pool adjoints (gather form: deterministic, no atomics),
+// zero-insertion for strided-conv dgrad, gradient unpack/accumulate into the OIHW FP32 masters.
+// Same conventions as hn_bandwidth.cu: 8 channels per thread, row-decomposed grids, no 64-bit div/mod per element.
+#include "hn_common.cuh"
+
+namespace hn {
+
+static inline dim3 row_grid_b(int64_t rows, int64_t items_per_row, int threads = 256)
+{
+    int64_t chunks = cdiv(items_per_row, (int64_t)threads * 4);
+    if (chunks < 1) chunks = 1;
+    if (chunks > 65535) chunks = 65535;
+    return dim3((unsigned)rows, (unsigned)chunks);
+}
+static inline int wave_grid_b(int64_t work_items, int threads, int waves_per_sm = 8)
+{
+    int64_t want = cdiv(work_items, threads);
+    int64_t cap = (int64_t)num_sms() * waves_per_sm;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+__device__ __forceinline__ float act_grad(float out, int act, float slope)
+{
+    // derivative of y = act(z) expressed through the saved OUTPUT (sign(out) == sign(z) for slope > 0)
+    if (act == HN_ACT_RELU) return out > 0.f ? 1.f : 0.f;
+    if (act == HN_ACT_LEAKY) return out >= 0.f ? 1.f : slope;
+    return 1.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dz = dout * act'(out)   (conv + bias + activation layers: PSP bottleneck, critics)
+// ------------------------------------------------------------------------------------------------
+template <typename TG, typename TO>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const TG *__restrict__ dout, int ldg, const TO *__restrict__ out, int ldo, int act,
+                                                      float slope, TG *__restrict__ dz, int ldz, int64_t npix, int C)
+{
+    const int ncv = C / 8;
+    constexpr int kPixPerBlock = 64;
+    const int64_t nblocks = (npix + kPixPerBlock - 1) / kPixPerBlock;
+    for (int64_t pb = blockIdx.x; pb < nblocks; pb += gridDim.x)
+        for (int i = threadIdx.x; i < kPixPerBlock * ncv; i += blockDim.x) {
+            const int pl = i / ncv;
+            const int64_t p = pb * kPixPerBlock + pl;
+            if (p >= npix) break;
+            const int c = (i - pl * ncv) * 8;
+            float g[8], o[8];
+            Vec8<TG>::load(dout + p * ldg + c, g);
+            Vec8<TO>::load(out + p * ldo + c, o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] *= act_grad(o[j], act, slope);
+            Vec8<TG>::store(dz + p * ldz + c, g);
+        }
+}
+
+// scalar variant for C % 8 != 0 (the critics' 1-channel classifier map)
+template <typename TG, typename TO>
+__global__ void __launch_bounds__(256) act_bwd_scalar_kernel(const TG *__restrict__ dout, int ldg, const TO *__restrict__ out, int ldo,
+                                                             int act, float slope, TG *__restrict__ dz, int ldz, int64_t npix, int C)
+{
+    const int64_t total = npix * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t p = i / C;
+        int c = (int)(i - p * C);
+        float g = to_f32<TG>(dout[p * ldg + c]) * act_grad(to_f32<TO>(out[p * ldo + c]), act, slope);
+        dz[p * ldz + c] = from_f32<TG>(g);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm2d (train) backward.  z = raw*scale + shift (+ res), out = act(z).
+//   reduce: s1[c] = sum dz, s2[c] = sum dz * xhat,  dz = dout*act'(out), xhat = (raw - mean)*invstd; for PReLU also
+//           sp = sum over z<0 of dout * z (gradient of the shared slope)
+//   apply : draw = gamma*invstd*(dz - s1/m - xhat*s2/m)   and   dres (+)= dz
+// blockDim = (CVB, PL) as in channel_stats_kernel.
+// ------------------------------------------------------------------------------------------------
+template <typename TG, typename TO>
+__global__ void bn_bwd_reduce_kernel(const TG *__restrict__ dout, int ldg, const TO *__restrict__ out, int ldo, const float *__restrict__ raw,
+                                     int ldr, const float *__restrict__ mean, const float *__restrict__ invstd, int act, float slope,
+                                     const float *slope_ptr, int64_t npix, int C, int64_t pix_per_cta, double *s1, double *s2,
+                                     double *sprelu)
+{
+    extern __shared__ float red[];  // [2][PL][CVB*8]
+    const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+    const int ncv = C / 8;
+    const int PL = blockDim.y, CVB = blockDim.x;
+    if (slope_ptr) slope = __ldg(slope_ptr);
+    float a[8], b[8], mu[8], is[8], sp = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = b[i] = 0.f;
+    const int64_t p_begin = (int64_t)blockIdx.x * pix_per_cta;
+    const int64_t p_end = min(p_begin + pix_per_cta, npix);
+    if (cv < ncv) {
+        Vec8<float>::load(mean + cv * 8, mu);
+        Vec8<float>::load(invstd + cv * 8, is);
+        for (int64_t p = p_begin + threadIdx.y; p < p_end; p += PL) {
+            float g[8], o[8], r[8];
+            Vec8<TG>::load(dout + p * ldg + cv * 8, g);
+            Vec8<TO>::load(out + p * ldo + cv * 8, o);
+            Vec8<float>::load(raw + p * ldr + cv * 8, r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (sprelu && o[i] < 0.f) sp += g[i] * (o[i] / slope);      // z = out / slope on the negative side
+                const float dz = g[i] * act_grad(o[i], act, slope);
+                a[i] += dz;
+                b[i] = fmaf(dz, (r[i] - mu[i]) * is[i], b[i]);
+            }
+        }
+    }
+    float *ra = red, *rb = red + PL * CVB * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        ra[(threadIdx.y * CVB + threadIdx.x) * 8 + i] = a[i];
+        rb[(threadIdx.y * CVB + threadIdx.x) * 8 + i] = b[i];
+    }
+    __syncthreads();
+    const int tid = threadIdx.y * CVB + threadIdx.x;
+    for (int col = tid; col < CVB * 8; col += CVB * PL) {
+        double x = 0.0, y = 0.0;
+        for (int l = 0; l < PL; ++l) {
+            x += (double)ra[l * CVB * 8 + col];
+            y += (double)rb[l * CVB * 8 + col];
+        }
+        int ch = blockIdx.y * CVB * 8 + col;
+        if (ch < C) {
+            atomicAdd(s1 + ch, x);
+            atomicAdd(s2 + ch, y);
+        }
+    }
+    if (sprelu) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sp += __shfl_xor_sync(0xffffffffu, sp, o);
+        if (((threadIdx.y * CVB + threadIdx.x) & 31) == 0 && sp != 0.f) atomicAdd(sprelu, (double)sp);
+    }
+}
+
+template <typename TG, typename TO>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TG *__restrict__ dout, int ldg, const TO *__restrict__ out, int ldo,
+                                                           const float *__restrict__ raw, int ldr, const float *__restrict__ mean,
+                                                           const float *__restrict__ invstd, const float *__restrict__ gamma,
+                                                           const double *__restrict__ s1, const double *__restrict__ s2, double inv_count,
+                                                           int act, float slope, const float *slope_ptr, TG *__restrict__ draw, int ldd,
+                                                           TG *__restrict__ dres, int ldres, int dres_accumulate, int64_t npix, int C)
+{
+    const int ncv = C / 8;
+    if (slope_ptr) slope = __ldg(slope_ptr);
+    constexpr int kPixPerBlock = 64;
+    const int64_t nblocks = (npix + kPixPerBlock - 1) / kPixPerBlock;
+    for (int64_t pb = blockIdx.x; pb < nblocks; pb += gridDim.x)
+        for (int i = threadIdx.x; i < kPixPerBlock * ncv; i += blockDim.x) {
+            const int pl = i / ncv;
+            const int64_t p = pb * kPixPerBlock + pl;
+            if (p >= npix) break;
+            const int c = (i - pl * ncv) * 8;
+            float g[8], o[8], r[8], mu[8], is[8], ga[8];
+            Vec8<TG>::load(dout + p * ldg + c, g);
+            Vec8<TO>::load(out + p * ldo + c, o);
+            Vec8<float>::load(raw + p * ldr + c, r);
+            Vec8<float>::load(mean + c, mu);
+            Vec8<float>::load(invstd + c, is);
+            if (gamma) Vec8<float>::load(gamma + c, ga);
+            float dx[8], dz[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                dz[j] = g[j] * act_grad(o[j], act, slope);
+                const float xhat = (r[j] - mu[j]) * is[j];
+                const float m1 = (float)(s1[c + j] * inv_count), m2 = (float)(s2[c + j] * inv_count);
+                dx[j] = (gamma ? ga[j] : 1.f) * is[j] * (dz[j] - m1 - xhat * m2);
+            }
+            Vec8<TG>::store(draw + p * ldd + c, dx);
+            if (dres) {
+                if (dres_accumulate) {
+                    float e[8];
+                    Vec8<TG>::load(dres + p * ldres + c, e);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dz[j] += e[j];
+                }
+                Vec8<TG>::store(dres + p * ldres + c, dz);
+            }
+        }
+}
+
+// y (+)= x   (gradient accumulation between NHWC views; x may be FP32 or the view's dtype)
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(256) accumulate_kernel(const TX *__restrict__ x, int ldx, TY *__restrict__ y, int ldy, int accumulate,
+                                                         int64_t npix, int C)
+{
+    const int ncv = C / 8;
+    constexpr int kPixPerBlock = 64;
+    const int64_t nblocks = (npix + kPixPerBlock - 1) / kPixPerBlock;
+    for (int64_t pb = blockIdx.x; pb < nblocks; pb += gridDim.x)
+        for (int i = threadIdx.x; i < kPixPerBlock * ncv; i += blockDim.x) {
+            const int pl = i / ncv;
+            const int64_t p = pb * kPixPerBlock + pl;
+            if (p >= npix) break;
+            const int c = (i - pl * ncv) * 8;
+            float a[8];
+            Vec8<TX>::load(x + p * ldx + c, a);
+            if (accumulate) {
+                float b[8];
+                Vec8<TY>::load(y + p * ldy + c, b);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] += b[j];
+            }
+            Vec8<TY>::store(y + p * ldy + c, a);
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// max-pool 3x3 s2 p1: forward that also records the winning tap (0..8, first max in window order like ATen),
+// and the backward gather: every input pixel looks at the <= 4 windows that contain it.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_idx_kernel(const T *__restrict__ x, int ldx, T *__restrict__ y, int ldy, uint8_t *__restrict__ idx,
+                                                          int N, int H, int W, int Ho, int Wo, int C)
+{
+    const int ncv = C / 8;
+    const int row = blockIdx.x;
+    const int n = row / Ho, ho = row - n * Ho;
+    const int items = Wo * ncv;
+    const T *xin = x + (int64_t)n * H * W * ldx;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < items; i += gridDim.y * blockDim.x) {
+        const int wo = i / ncv, c = (i - wo * ncv) * 8;
+        float m[8];
+        uint8_t w8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { m[j] = -INFINITY; w8[j] = 0; }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            int hi = 2 * ho - 1 + r;
+            if (hi < 0 || hi >= H) continue;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                int wi = 2 * wo - 1 + s;
+                if (wi < 0 || wi >= W) continue;
+                float v[8];
+                Vec8<T>::load(xin + ((int64_t)hi * W + wi) * ldx + c, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (v[j] > m[j]) { m[j] = v[j]; w8[j] = (uint8_t)(r * 3 + s); }   // strictly greater: first max wins (ATen)
+            }
+        }
+        const int64_t po = (int64_t)row * Wo + wo;
+        Vec8<T>::store(y + po * ldy + c, m);
+        uint2 packed;
+        uint8_t *pb = reinterpret_cast<uint8_t *>(&packed);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pb[j] = w8[j];
+        *reinterpret_cast<uint2 *>(idx + po * C + c) = packed;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T *__restrict__ dy, int ldy, const uint8_t *__restrict__ idx, T *__restrict__ dx,
+                                                          int ldx, int accumulate, int N, int H, int W, int Ho, int Wo, int C)
+{
+    const int ncv = C / 8;
+    const int row = blockIdx.x;                    // n*H + hi
+    const int n = row / H, hi = row - n * H;
+    const int items = W * ncv;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < items; i += gridDim.y * blockDim.x) {
+        const int wi = i / ncv, c = (i - wi * ncv) * 8;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        // windows ho with 2*ho-1 <= hi <= 2*ho+1
+        for (int ho = hi / 2; ho <= (hi + 1) / 2; ++ho) {
+            if (ho >= Ho) continue;
+            const int r = hi - (2 * ho - 1);
+            for (int wo = wi / 2; wo <= (wi + 1) / 2; ++wo) {
+                if (wo >= Wo) continue;
+                const int s = wi - (2 * wo - 1);
+                const int64_t po = ((int64_t)n * Ho + ho) * Wo + wo;
+                const uint2 packed = *reinterpret_cast<const uint2 *>(idx + po * C + c);
+                const uint8_t *pb = reinterpret_cast<const uint8_t *>(&packed);
+                float g[8];
+                Vec8<T>::load(dy + po * ldy + c, g);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (pb[j] == r * 3 + s) acc[j] += g[j];
+            }
+        }
+        T *d = dx + ((int64_t)row * W + wi) * ldx + c;
+        if (accumulate) {
+            float e[8];
+            Vec8<T>::load(d, e);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += e[j];
+        }
+        Vec8<T>::store(d, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bilinear adjoint (gather): dx[n, yi, xi, c] = sum over outputs (yo, xo) whose source taps include (yi, xi)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bilinear_src_b(int dst, float scale, int in_size, int &i0, int &i1, float &l1)
+{
+    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    i0 = (int)src;
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = src - (float)i0;
+}
+// candidate output range [lo, hi] that can touch input index i (conservative; exact membership is re-checked)
+__device__ __forceinline__ void out_range(int i, float scale, int out_size, int &lo, int &hi)
+{
+    float a = ((float)i - 1.0f + 0.5f) / scale - 0.5f;
+    float b = ((float)i + 1.0f + 0.5f) / scale - 0.5f;
+    lo = (int)floorf(a) - 1;
+    hi = (int)ceilf(b) + 1;
+    if (lo < 0) lo = 0;
+    if (hi > out_size - 1) hi = out_size - 1;
+}
+
+template <typename TG, typename TX, bool kVec>
+__global__ void __launch_bounds__(256) bilinear_bwd_kernel(const TG *__restrict__ dy, int ldy, TX *__restrict__ dx, int ldx, int accumulate,
+                                                           int N, int H, int W, int Ho, int Wo, int C, float sh, float sw)
+{
+    constexpr int V = kVec ? 8 : 1;
+    const int ncv = C / V;
+    const int row = blockIdx.x;               // n*H + yi
+    const int n = row / H, yi = row - n * H;
+    int ylo, yhi;
+    out_range(yi, sh, Ho, ylo, yhi);
+    const int items = W * ncv;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < items; i += gridDim.y * blockDim.x) {
+        const int xi = i / ncv, c = (i - xi * ncv) * V;
+        int xlo, xhi;
+        out_range(xi, sw, Wo, xlo, xhi);
+        float acc[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = 0.f;
+        for (int yo = ylo; yo <= yhi; ++yo) {
+            int y0, y1;
+            float ly;
+            bilinear_src_b(yo, sh, H, y0, y1, ly);
+            const float wy = (y0 == yi ? 1.f - ly : 0.f) + (y1 == yi ? ly : 0.f);
+            if (wy == 0.f) continue;
+            const TG *grow = dy + ((int64_t)n * Ho + yo) * Wo * ldy + c;
+            for (int xo = xlo; xo <= xhi; ++xo) {
+                int x0, x1;
+                float lx;
+                bilinear_src_b(xo, sw, W, x0, x1, lx);
+                const float wx = (x0 == xi ? 1.f - lx : 0.f) + (x1 == xi ? lx : 0.f);
+                if (wx == 0.f) continue;
+                const float wgt = wy * wx;
+                if constexpr (kVec) {
+                    float g[8];
+                    Vec8<TG>::load(grow + (int64_t)xo * ldy, g);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, g[j], acc[j]);
+                } else {
+                    acc[0] = fmaf(wgt, to_f32<TG>(grow[(int64_t)xo * ldy]), acc[0]);
+                }
+            }
+        }
+        TX *d = dx + ((int64_t)row * W + xi) * ldx + c;
+        if constexpr (kVec) {
+            if (accumulate) {
+                float e[8];
+                Vec8<TX>::load(d, e);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += e[j];
+            }
+            Vec8<TX>::store(d, acc);
+        } else {
+            float v = acc[0] + (accumulate ? to_f32<TX>(d[0]) : 0.f);
+            d[0] = from_f32<TX>(v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pyramid pool adjoint: dx[n,h,w,c] (+)= sum over sizes s and bins (i,j) containing (h,w) of dbin / area
+// dpool: the forward's per-size dense blocks [N][s][s][C]
+// ------------------------------------------------------------------------------------------------
+struct PoolSizesB {
+    int n, s[4];
+};
+template <typename T>
+__global__ void __launch_bounds__(256) pyramid_bwd_kernel(const T *__restrict__ dpool, T *__restrict__ dx, int ldx, int accumulate, int N, int H,
+                                                          int W, int C, PoolSizesB ps)
+{
+    const int ncv = C / 8;
+    const int row = blockIdx.x;       // n*H + h
+    const int n = row / H, h = row - n * H;
+    const int items = W * ncv;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < items; i += gridDim.y * blockDim.x) {
+        const int w = i / ncv, c = (i - w * ncv) * 8;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        int64_t base = 0;
+        for (int a = 0; a < ps.n; ++a) {
+            const int s = ps.s[a];
+            // bins bi with floor(bi*H/s) <= h < ceil((bi+1)*H/s): at most two, around h*s/H
+            int b0 = (h * s) / H;
+            for (int bi = max(b0 - 1, 0); bi <= min(b0 + 1, s - 1); ++bi) {
+                const int h0 = (bi * H) / s, h1 = ((bi + 1) * H + s - 1) / s;
+                if (h < h0 || h >= h1) continue;
+                int c0 = (w * s) / W;
+                for (int bj = max(c0 - 1, 0); bj <= min(c0 + 1, s - 1); ++bj) {
+                    const int w0 = (bj * W) / s, w1 = ((bj + 1) * W + s - 1) / s;
+                    if (w < w0 || w >= w1) continue;
+                    float g[8];
+                    Vec8<T>::load(dpool + (base * N + ((int64_t)n * s + bi) * s + bj) * C + c, g);
+                    const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(g[j], inv, acc[j]);
+                }
+            }
+            base += (int64_t)s * s;
+        }
+        T *d = dx + ((int64_t)row * W + w) * ldx + c;
+        if (accumulate) {
+            float e[8];
+            Vec8<T>::load(d, e);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += e[j];
+        }
+        Vec8<T>::store(d, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// zero insertion: up[n, h*stride, w*stride, c] = x[n,h,w,c], zeros elsewhere (strided-conv dgrad as a stride-1 conv)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) dilate_scalar_kernel(const T *__restrict__ x, int ldx, T *__restrict__ up, int ldu, int N, int H, int W,
+                                                            int Hu, int Wu, int C, int stride)
+{
+    const int64_t total = (int64_t)N * Hu * Wu * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        int64_t p = i / C;
+        int wu = (int)(p % Wu), hu = (int)((p / Wu) % Hu), n = (int)(p / ((int64_t)Wu * Hu));
+        T v = from_f32<T>(0.f);
+        if (hu % stride == 0 && wu % stride == 0 && hu / stride < H && wu / stride < W)
+            v = x[(((int64_t)n * H + hu / stride) * W + wu / stride) * ldx + c];
+        up[p * ldu + c] = v;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dilate_kernel(const T *__restrict__ x, int ldx, T *__restrict__ up, int ldu, int N, int H, int W, int Hu,
+                                                     int Wu, int C, int stride)
+{
+    const int ncv = C / 8;
+    const int row = blockIdx.x;   // n*Hu + hu
+    const int n = row / Hu, hu = row - n * Hu;
+    const bool rowlive = (hu % stride) == 0 && hu / stride < H;
+    const int items = Wu * ncv;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < items; i += gridDim.y * blockDim.x) {
+        const int wu = i / ncv, c = (i - wu * ncv) * 8;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        if (rowlive && (wu % stride) == 0 && wu / stride < W)
+            Vec8<T>::load(x + (((int64_t)n * H + hu / stride) * W + wu / stride) * ldx + c, v);
+        Vec8<T>::store(up + ((int64_t)row * Wu + wu) * ldu + c, v);
+    }
+}
+
+// packed FP32 weight gradient [cout_pad][kpad] (k = (r*S+s)*Cin + c) -> OIHW FP32, optionally accumulating
+__global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float *__restrict__ packed, float *__restrict__ grad, int cout, int cin, int R,
+                                                           int S, int kpad, int accumulate)
+{
+    const int64_t total = (int64_t)cout * cin * R * S;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int s = (int)(i % S);
+        int r = (int)((i / S) % R);
+        int c = (int)((i / ((int64_t)S * R)) % cin);
+        int o = (int)(i / ((int64_t)S * R * cin));
+        float v = packed[(int64_t)o * kpad + (r * S + s) * cin + c];
+        grad[i] = accumulate ? grad[i] + v : v;
+    }
+}
+
+// dgrad weight pack: OIHW FP32 -> [cin_pad][kpad'] with k' = ((R-1-r)*S + (S-1-s))*Cout + o  (flipped taps, in/out swapped)
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weight_dgrad_kernel(const float *__restrict__ w, T *__restrict__ dst, int cout, int cin, int R, int S,
+                                                                int cin_pad, int kpad)
+{
+    const int64_t total = (int64_t)cin_pad * kpad;
+    const int K = R * S * cout;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int ci = (int)(i / kpad), k = (int)(i - (int64_t)ci * kpad);
+        float v = 0.f;
+        if (ci < cin && k < K) {
+            int tap = k / cout, o = k - tap * cout;
+            int rf = tap / S, sf = tap - rf * S;
+            int r = R - 1 - rf, s = S - 1 - sf;
+            v = __ldg(w + (((int64_t)o * cin + ci) * R + r) * S + s);
+        }
+        dst[i] = from_f32<T>(v);
+    }
+}
+
+// f64 -> f32 vector add into a parameter gradient: grad (+)= alpha * src
+__global__ void vec_f64_to_grad_kernel(const double *__restrict__ src, float *__restrict__ grad, int n, int accumulate)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) grad[i] = (accumulate ? grad[i] : 0.f) + (float)src[i];
+}
+
+}  // namespace hn
+
+using namespace hn;
+using bf16 = __nv_bfloat16;
+
+static bool same_shape(const hn_tensor *a, const hn_tensor *b) { return a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c; }
+
+extern "C" int hn_act_bwd(const hn_tensor *dout, const hn_tensor *out, int32_t act, float slope, const hn_tensor *dz, void *stream)
+{
+    HN_CHECK_ARG(dout && out && dz && dout->ptr && out->ptr && dz->ptr, "hn_act_bwd: null pointer");
+    HN_CHECK_ARG(same_shape(dout, out) && same_shape(dout, dz) && dout->dtype == dz->dtype, "hn_act_bwd: shape/dtype mismatch");
+    const int64_t npix = (int64_t)dout->n * dout->h * dout->w;
+    if (npix == 0) return HN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = vec8_ok(dout) && vec8_ok(out) && vec8_ok(dz);
+#define HN_ACT_BWD(TG, TO)                                                                                                               \
+    do {                                                                                                                                 \
+        if (vec)                                                                                                                         \
+            act_bwd_kernel<TG, TO><<<wave_grid_b(cdiv(npix, 64) * 256, 256, 16), 256, 0, st>>>((const TG *)dout->ptr, dout->ld, (const TO *)out->ptr, out->ld, act, slope, (TG *)dz->ptr, dz->ld, npix, dout->c); \
+        else                                                                                                                             \
+            act_bwd_scalar_kernel<TG, TO><<<wave_grid_b(npix * dout->c, 256), 256, 0, st>>>((const TG *)dout->ptr, dout->ld, (const TO *)out->ptr, out->ld, act, slope, (TG *)dz->ptr, dz->ld, npix, dout->c); \
+    } while (0)
+    if (dout->dtype == HN_BF16 && out->dtype == HN_BF16) HN_ACT_BWD(bf16, bf16);
+    else if (dout->dtype == HN_F32 && out->dtype == HN_F32) HN_ACT_BWD(float, float);
+    else if (dout->dtype == HN_BF16 && out->dtype == HN_F32) HN_ACT_BWD(bf16, float);
+    else HN_ACT_BWD(float, bf16);
+#undef HN_ACT_BWD
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_bn_bwd(const hn_tensor *dout, const hn_tensor *out, const hn_tensor *raw, const float *mean, const float *invstd,
+                         const float *gamma, int32_t act, float slope, const float *slope_ptr, double *sums /* [2*C + 1] scratch+result */,
+                         const hn_tensor *draw, const hn_tensor *dres, int32_t dres_accumulate, int32_t want_prelu_grad, void *stream)
+{
+    HN_CHECK_ARG(dout && out && raw && mean && invstd && sums && draw, "hn_bn_bwd: null pointer");
+    HN_CHECK_ARG(same_shape(dout, out) && same_shape(dout, raw) && same_shape(dout, draw), "hn_bn_bwd: shape mismatch");
+    HN_CHECK_ARG(raw->dtype == HN_F32, "hn_bn_bwd: the pre-normalisation tensor is FP32");
+    HN_CHECK_ARG(dout->dtype == draw->dtype && (!dres || dres->dtype == dout->dtype), "hn_bn_bwd: gradient dtypes must match");
+    HN_CHECK_ARG(vec8_ok(dout) && vec8_ok(out) && vec8_ok(raw) && vec8_ok(draw) && (!dres || vec8_ok(dres)), "hn_bn_bwd: views must be 8-channel aligned");
+    const int C = dout->c;
+    const int64_t npix = (int64_t)dout->n * dout->h * dout->w;
+    cudaStream_t st = (cudaStream_t)stream;
+    HN_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C + 1), st));
+    if (npix == 0) return HN_OK;
+    const int ncv = C / 8;
+    const int CVB = ncv < 32 ? ncv : 32;
+    const int PL = 256 / CVB;
+    const int cvblocks = (int)cdiv(ncv, CVB);
+    int64_t chunks = cdiv((int64_t)num_sms() * 4, cvblocks);
+    int64_t pix_per_cta = cdiv(npix, chunks);
+    if (pix_per_cta < (int64_t)PL * 8) pix_per_cta = (int64_t)PL * 8;
+    chunks = cdiv(npix, pix_per_cta);
+    dim3 grid((unsigned)chunks, (unsigned)cvblocks), block(CVB, PL);
+    size_t smem = (size_t)2 * PL * CVB * 8 * sizeof(float);
+    double *s1 = sums, *s2 = sums + C, *sp = want_prelu_grad ? sums + 2 * C : nullptr;
+    int grid2 = wave_grid_b(cdiv(npix, 64) * 256, 256, 16);
+    const double inv_count = 1.0 / (double)npix;
+#define HN_BN_BWD(TG, TO)                                                                                                                 \
+    do {                                                                                                                                  \
+        bn_bwd_reduce_kernel<TG, TO><<<grid, block, smem, st>>>((const TG *)dout->ptr, dout->ld, (const TO *)out->ptr, out->ld, (const float *)raw->ptr, raw->ld, mean, invstd, act, slope, slope_ptr, npix, C, pix_per_cta, s1, s2, sp); \
+        bn_bwd_apply_kernel<TG, TO><<<grid2, 256, 0, st>>>((const TG *)dout->ptr, dout->ld, (const TO *)out->ptr, out->ld, (const float *)raw->ptr, raw->ld, mean, invstd, gamma, s1, s2, inv_count, act, slope, slope_ptr, (TG *)draw->ptr, draw->ld, dres ? (TG *)dres->ptr : nullptr, dres ? dres->ld : 0, dres_accumulate, npix, C); \
+    } while (0)
+    if (dout->dtype == HN_BF16 && out->dtype == HN_BF16) HN_BN_BWD(bf16, bf16);
+    else if (dout->dtype == HN_F32 && out->dtype == HN_F32) HN_BN_BWD(float, float);
+    else {
+        set_error("hn_bn_bwd: unsupported dtype combination");
+        return HN_ERR_ARG;
+    }
+#undef HN_BN_BWD
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_accumulate(const hn_tensor *x, const hn_tensor *y, int32_t accumulate, void *stream)
+{
+    HN_CHECK_ARG(x && y && x->ptr && y->ptr && same_shape(x, y), "hn_accumulate: bad arguments");
+    HN_CHECK_ARG(vec8_ok(x) && vec8_ok(y), "hn_accumulate: views must be 8-channel aligned");
+    const int64_t npix = (int64_t)x->n * x->h * x->w;
+    if (npix == 0) return HN_OK;
+    int grid = wave_grid_b(cdiv(npix, 64) * 256, 256, 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x->dtype == HN_BF16 && y->dtype == HN_BF16) accumulate_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16 *)x->ptr, x->ld, (bf16 *)y->ptr, y->ld, accumulate, npix, x->c);
+    else if (x->dtype == HN_F32 && y->dtype == HN_F32) accumulate_kernel<float, float><<<grid, 256, 0, st>>>((const float *)x->ptr, x->ld, (float *)y->ptr, y->ld, accumulate, npix, x->c);
+    else if (x->dtype == HN_F32 && y->dtype == HN_BF16) accumulate_kernel<float, bf16><<<grid, 256, 0, st>>>((const float *)x->ptr, x->ld, (bf16 *)y->ptr, y->ld, accumulate, npix, x->c);
+    else accumulate_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16 *)x->ptr, x->ld, (float *)y->ptr, y->ld, accumulate, npix, x->c);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_maxpool3x3s2_fwd_idx(const hn_tensor *x, const hn_tensor *y, uint8_t *idx, void *stream)
+{
+    HN_CHECK_ARG(x && y && idx && x->ptr && y->ptr, "hn_maxpool3x3s2_fwd_idx: null pointer");
+    HN_CHECK_ARG(x->dtype == y->dtype && x->c == y->c && x->n == y->n, "hn_maxpool3x3s2_fwd_idx: dtype/shape mismatch");
+    HN_CHECK_ARG(y->h == (x->h - 1) / 2 + 1 && y->w == (x->w - 1) / 2 + 1, "hn_maxpool3x3s2_fwd_idx: bad output size");
+    HN_CHECK_ARG(vec8_ok(x) && vec8_ok(y), "hn_maxpool3x3s2_fwd_idx: views must be 8-channel aligned");
+    if ((int64_t)y->n * y->h * y->w == 0) return HN_OK;
+    dim3 grid = row_grid_b((int64_t)y->n * y->h, (int64_t)y->w * (y->c / 8));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x->dtype == HN_BF16) maxpool_idx_kernel<bf16><<<grid, 256, 0, st>>>((const bf16 *)x->ptr, x->ld, (bf16 *)y->ptr, y->ld, idx, x->n, x->h, x->w, y->h, y->w, x->c);
+    else maxpool_idx_kernel<float><<<grid, 256, 0, st>>>((const float *)x->ptr, x->ld, (float *)y->ptr, y->ld, idx, x->n, x->h, x->w, y->h, y->w, x->c);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_maxpool3x3s2_bwd(const hn_tensor *dy, const uint8_t *idx, const hn_tensor *dx, int32_t accumulate, void *stream)
+{
+    HN_CHECK_ARG(dy && dx && idx && dy->ptr && dx->ptr, "hn_maxpool3x3s2_bwd: null pointer");
+    HN_CHECK_ARG(dy->dtype == dx->dtype && dy->c == dx->c && dy->n == dx->n, "hn_maxpool3x3s2_bwd: dtype/shape mismatch");
+    HN_CHECK_ARG(dy->h == (dx->h - 1) / 2 + 1 && dy->w == (dx->w - 1) / 2 + 1, "hn_maxpool3x3s2_bwd: bad sizes");
+    HN_CHECK_ARG(vec8_ok(dy) && vec8_ok(dx), "hn_maxpool3x3s2_bwd: views must be 8-channel aligned");
+    if ((int64_t)dx->n * dx->h * dx->w == 0) return HN_OK;
+    dim3 grid = row_grid_b((int64_t)dx->n * dx->h, (int64_t)dx->w * (dx->c / 8));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dy->dtype == HN_BF16) maxpool_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16 *)dy->ptr, dy->ld, idx, (bf16 *)dx->ptr, dx->ld, accumulate, dx->n, dx->h, dx->w, dy->h, dy->w, dx->c);
+    else maxpool_bwd_kernel<float><<<grid, 256, 0, st>>>((const float *)dy->ptr, dy->ld, idx, (float *)dx->ptr, dx->ld, accumulate, dx->n, dx->h, dx->w, dy->h, dy->w, dx->c);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_bilinear_bwd(const hn_tensor *dy, const hn_tensor *dx, int32_t accumulate, void *stream)
+{
+    HN_CHECK_ARG(dy && dx && dy->ptr && dx->ptr, "hn_bilinear_bwd: null pointer");
+    HN_CHECK_ARG(dy->n == dx->n && dy->c == dx->c && dx->h > 0 && dx->w > 0, "hn_bilinear_bwd: shape mismatch");
+    if ((int64_t)dx->n * dx->h * dx->w == 0) return HN_OK;
+    const float sh = (float)dx->h / (float)dy->h, sw = (float)dx->w / (float)dy->w;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = vec8_ok(dy) && vec8_ok(dx);
+    dim3 grid = row_grid_b((int64_t)dx->n * dx->h, (int64_t)dx->w * (vec ? dx->c / 8 : dx->c));
+#define HN_BIL_BWD(TG, TX)                                                                                                            \
+    do {                                                                                                                              \
+        if (vec) bilinear_bwd_kernel<TG, TX, true><<<grid, 256, 0, st>>>((const TG *)dy->ptr, dy->ld, (TX *)dx->ptr, dx->ld, accumulate, dx->n, dx->h, dx->w, dy->h, dy->w, dx->c, sh, sw); \
+        else bilinear_bwd_kernel<TG, TX, false><<<grid, 256, 0, st>>>((const TG *)dy->ptr, dy->ld, (TX *)dx->ptr, dx->ld, accumulate, dx->n, dx->h, dx->w, dy->h, dy->w, dx->c, sh, sw); \
+    } while (0)
+    if (dy->dtype == HN_BF16 && dx->dtype == HN_BF16) HN_BIL_BWD(bf16, bf16);
+    else if (dy->dtype == HN_F32 && dx->dtype == HN_F32) HN_BIL_BWD(float, float);
+    else if (dy->dtype == HN_F32 && dx->dtype == HN_BF16) HN_BIL_BWD(float, bf16);
+    else HN_BIL_BWD(bf16, float);
+#undef HN_BIL_BWD
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_pyramid_pool_bwd(const void *dpool, const int32_t *sizes, int32_t nsizes, const hn_tensor *dx, int32_t accumulate, void *stream)
+{
+    HN_CHECK_ARG(dpool && sizes && dx && dx->ptr, "hn_pyramid_pool_bwd: null pointer");
+    HN_CHECK_ARG(nsizes >= 1 && nsizes <= 4 && vec8_ok(dx), "hn_pyramid_pool_bwd: bad arguments");
+    if ((int64_t)dx->n * dx->h * dx->w == 0) return HN_OK;
+    PoolSizesB ps{};
+    ps.n = nsizes;
+    for (int i = 0; i < nsizes; ++i) ps.s[i] = sizes[i];
+    dim3 grid = row_grid_b((int64_t)dx->n * dx->h, (int64_t)dx->w * (dx->c / 8));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dx->dtype == HN_BF16) pyramid_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16 *)dpool, (bf16 *)dx->ptr, dx->ld, accumulate, dx->n, dx->h, dx->w, dx->c, ps);
+    else pyramid_bwd_kernel<float><<<grid, 256, 0, st>>>((const float *)dpool, (float *)dx->ptr, dx->ld, accumulate, dx->n, dx->h, dx->w, dx->c, ps);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_dilate(const hn_tensor *x, int32_t stride, const hn_tensor *up, void *stream)
+{
+    HN_CHECK_ARG(x && up && x->ptr && up->ptr && stride >= 1, "hn_dilate: bad arguments");
+    HN_CHECK_ARG(x->dtype == up->dtype && x->n == up->n && x->c == up->c, "hn_dilate: dtype/shape mismatch");
+    HN_CHECK_ARG(up->h >= (x->h - 1) * stride + 1 && up->w >= (x->w - 1) * stride + 1, "hn_dilate: output too small");
+    if ((int64_t)up->n * up->h * up->w == 0) return HN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!(vec8_ok(x) && vec8_ok(up))) {
+        int g = wave_grid_b((int64_t)up->n * up->h * up->w * up->c, 256);
+        if (x->dtype == HN_BF16) dilate_scalar_kernel<bf16><<<g, 256, 0, st>>>((const bf16 *)x->ptr, x->ld, (bf16 *)up->ptr, up->ld, x->n, x->h, x->w, up->h, up->w, x->c, stride);
+        else dilate_scalar_kernel<float><<<g, 256, 0, st>>>((const float *)x->ptr, x->ld, (float *)up->ptr, up->ld, x->n, x->h, x->w, up->h, up->w, x->c, stride);
+        HN_LAUNCH_CHECK();
+        return HN_OK;
+    }
+    dim3 grid = row_grid_b((int64_t)up->n * up->h, (int64_t)up->w * (up->c / 8));
+    if (x->dtype == HN_BF16) dilate_kernel<bf16><<<grid, 256, 0, st>>>((const bf16 *)x->ptr, x->ld, (bf16 *)up->ptr, up->ld, x->n, x->h, x->w, up->h, up->w, x->c, stride);
+    else dilate_kernel<float><<<grid, 256, 0, st>>>((const float *)x->ptr, x->ld, (float *)up->ptr, up->ld, x->n, x->h, x->w, up->h, up->w, x->c, stride);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_unpack_wgrad(const float *packed, float *grad_oihw, int32_t cout, int32_t cin, int32_t r, int32_t s, int32_t kpad,
+                               int32_t accumulate, void *stream)
+{
+    HN_CHECK_ARG(packed && grad_oihw && kpad >= cin * r * s, "hn_unpack_wgrad: bad arguments");
+    int64_t total = (int64_t)cout * cin * r * s;
+    unpack_wgrad_kernel<<<wave_grid_b(total, 256), 256, 0, (cudaStream_t)stream>>>(packed, grad_oihw, cout, cin, r, s, kpad, accumulate);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_pack_weight_dgrad(const float *w_oihw, void *dst, int32_t dtype, int32_t cout, int32_t cin, int32_t r, int32_t s,
+                                    int32_t cin_pad, int32_t kpad, void *stream)
+{
+    HN_CHECK_ARG(w_oihw && dst && cin_pad >= cin && kpad >= r * s * cout, "hn_pack_weight_dgrad: bad arguments");
+    int64_t total = (int64_t)cin_pad * kpad;
+    int grid = wave_grid_b(total, 256);
+    if (dtype == HN_BF16) pack_weight_dgrad_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, (bf16 *)dst, cout, cin, r, s, cin_pad, kpad);
+    else pack_weight_dgrad_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, (float *)dst, cout, cin, r, s, cin_pad, kpad);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_vec_to_grad(const double *src, float *grad, int32_t n, int32_t accumulate, void *stream)
+{
+    HN_CHECK_ARG(src && grad && n > 0, "hn_vec_to_grad: bad arguments");
+    vec_f64_to_grad_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(src, grad, n, accumulate);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}

@@ -1,0 +1,408 @@
+// Convolution weight gradient:  dW[co][(r*S+s)*Cin + ci] = sum over output pixels of dY[pix][co] * X[pix shifted by tap][ci].
+//
+// BF16 path (tcgen05): a GEMM whose reduction axis is the PIXEL axis.  Both operands are NHWC, i.e. their GEMM
+// M / N index (channels) is the contiguous one, so the shared-memory tiles are MN-major: a TMA box
+// {64 channels, TW, TH, 1} of a TH x TW = 64-pixel patch lands as [64 pixel rows][128 B], which is exactly the
+// 128B-swizzled MN-major UMMA layout with K = pixel rows.  For filter tap (r,s) the X patch is the dY patch
+// shifted by (r*dil - pad, s*dil - pad); TMA zero-fills padding and ragged edges for both operands.
+// Work item = (128-wide Cout tile, <=256-wide Cin tile, tap, pixel split); FP32 accumulators in TMEM; the
+// epilogue adds the partial tile into the packed FP32 gradient [Cout_pad][Kpad] with red.global.add.f32
+// (split-K over pixels keeps all 148 SMs busy even for layers with few channel tiles).
+// Strided / small-Cin convolutions run the same kernel in flat mode on the im2col workspace (K columns = taps*Cin).
+//
+// FP32 path: CUDA-core implicit GEMM with the same decomposition (parity mode).
+#include <string.h>
+
+#include "hn_common.cuh"
+#include "hn_tc_ptx.cuh"
+
+namespace hn {
+
+constexpr int WG_THREADS = 256;     // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
+constexpr int WG_KPIX = 64;         // pixels per k-block
+constexpr int WG_BLOCK_BYTES = WG_KPIX * 128;   // one [64 px][64 ch] block = 8 KB
+constexpr int WG_M = 128;
+
+struct WgParams {
+    int tiles_w, tiles_h, n_img;    // pixel patches: n_img * tiles_h * tiles_w k-blocks in total
+    int TH, TW;                     // TH*TW = 64
+    int taps, S, pad, dil;          // taps = R*S (1 in flat mode)
+    int m_tiles, n_tiles;           // Cout / 128 tiles, Ncols / BN tiles
+    int splits;                     // pixel splits per (m, n, tap)
+    int Cout, ncols;                // valid rows / valid columns per tap (Cin, or Kpad in flat mode)
+    int kpad;                       // row stride of the packed gradient
+    float *dw;                      // [Cout_pad][kpad] FP32, accumulated into
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x, const WgParams p)
+{
+    constexpr int A_BYTES = 2 * WG_BLOCK_BYTES;              // 128 couts = 2 blocks
+    constexpr int B_BYTES = (BN / 64) * WG_BLOCK_BYTES;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t IDESC = make_idesc_bf16_mn(WG_M, BN);
+    constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *full_bar = bars, *empty_bar = bars + STAGES, *tfull_bar = bars + 2 * STAGES, *tempty_bar = bars + 2 * STAGES + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = p.n_img * p.tiles_h * p.tiles_w;
+    const int num_items = p.m_tiles * p.n_tiles * p.taps * p.splits;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_dy);
+        prefetch_tmap(&tmap_x);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(smem_u32(full_bar + i), 1);
+            mbar_init(smem_u32(empty_bar + i), 1);
+        }
+        mbar_init(smem_u32(tfull_bar), 1);
+        mbar_init(smem_u32(tempty_bar), 4);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // work item -> (split, tap, nt, mt), split fastest so concurrently running CTAs stream disjoint pixel ranges
+    auto decode = [&](int item, int &mt, int &nt, int &tap, int &kb0, int &kb1) {
+        const int sp = item % p.splits;
+        int rest = item / p.splits;
+        tap = rest % p.taps; rest /= p.taps;
+        nt = rest % p.n_tiles;
+        mt = rest / p.n_tiles;
+        const int per = (num_kb + p.splits - 1) / p.splits;
+        kb0 = sp * per;
+        kb1 = kb0 + per < num_kb ? kb0 + per : num_kb;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                int mt, nt, tap, kb0, kb1;
+                decode(item, mt, nt, tap, kb0, kb1);
+                const int r = tap / p.S, s = tap - r * p.S;
+                const int dx = s * p.dil - p.pad, dyy = r * p.dil - p.pad;
+                const int xcol0 = (p.taps > 1 ? 0 : 0) + nt * BN;      // column offset inside the tap (Cin offset / flat K offset)
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    const int tw = kb % p.tiles_w, th = (kb / p.tiles_w) % p.tiles_h, img = kb / (p.tiles_w * p.tiles_h);
+                    mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+                    const uint32_t fb = smem_u32(full_bar + stage);
+                    mbar_expect_tx(fb, STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+#pragma unroll
+                    for (int b = 0; b < 2; ++b)
+                        tma_load_4d(sa + b * WG_BLOCK_BYTES, &tmap_dy, fb, mt * WG_M + b * 64, tw * p.TW, th * p.TH, img);
+#pragma unroll
+                    for (int b = 0; b < BN / 64; ++b)
+                        tma_load_4d(sa + A_BYTES + b * WG_BLOCK_BYTES, &tmap_x, fb, xcol0 + b * 64, tw * p.TW + dx, th * p.TH + dyy, img);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                int mt, nt, tap, kb0, kb1;
+                decode(item, mt, nt, tap, kb0, kb1);
+                mbar_wait(smem_u32(tempty_bar), acc_phase ^ 1);
+                tcgen05_fence_after();
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(smem_u32(full_bar + stage), phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint64_t adesc = make_mnmajor_sw128_desc(sa, WG_BLOCK_BYTES);
+                    const uint64_t bdesc = make_mnmajor_sw128_desc(sa + A_BYTES, WG_BLOCK_BYTES);
+#pragma unroll
+                    for (int k = 0; k < WG_KPIX / 16; ++k) {
+                        // 16 pixel rows = 2048 B further along K: +128 in the (addr >> 4) field
+                        umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(smem_u32(empty_bar + stage));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(smem_u32(tfull_bar));
+                acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp - 4;
+        const int row = q * 32 + lane;
+        uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            int mt, nt, tap, kb0, kb1;
+            decode(item, mt, nt, tap, kb0, kb1);
+            const int co = mt * WG_M + row;
+            mbar_wait(smem_u32(tfull_bar), acc_phase);
+            tcgen05_fence_after();
+            acc_phase ^= 1;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+            float *drow = p.dw + (int64_t)co * p.kpad + (int64_t)tap * p.ncols + nt * BN;
+            constexpr int CH = BN < 32 ? BN : 32;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += CH) {
+                uint32_t raw[CH];
+                if constexpr (CH == 32) tmem_ld_32x32(taddr + c0, raw);
+                else tmem_ld_32x16(taddr + c0, raw);
+                tmem_ld_wait();
+                if (co < p.Cout && kb1 > kb0) {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j)
+                        if (nt * BN + c0 + j < p.ncols) atomicAdd(drow + c0 + j, __uint_as_float(raw[j]));
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(tempty_bar));
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int BN, int STAGES>
+static int launch_wgrad(const CUtensorMap &tdy, const CUtensorMap &tx, const WgParams &p, cudaStream_t st)
+{
+    constexpr size_t smem = (size_t)STAGES * (2 + BN / 64) * WG_BLOCK_BYTES + (2 * STAGES + 2) * 8 + 16 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        HN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int items = p.m_tiles * p.n_tiles * p.taps * p.splits;
+    int grid = items < num_sms() ? items : num_sms();
+    wgrad_tc_kernel<BN, STAGES><<<grid, WG_THREADS, smem, st>>>(tdy, tx, p);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+// im2col gather shared with the forward engine (hn_conv_tc.cu)
+int im2col_bf16(const hn_tensor *x, const hn_conv *cv, int Ho, int Wo, int kpad, void *ws, cudaStream_t st);
+
+int conv2d_wgrad_tc(const hn_tensor *x, const hn_tensor *dy, const hn_conv *cv, float *dw_packed, void *ws, int64_t ws_bytes,
+                    cudaStream_t st)
+{
+    const int kpad = hn_conv_kpad(x->c, cv->r, cv->s);
+    const int64_t M = (int64_t)dy->n * dy->h * dy->w;
+    if (M == 0) return HN_OK;
+    HN_CHECK_ARG((reinterpret_cast<uintptr_t>(dy->ptr) & 15) == 0 && dy->ld % 8 == 0, "conv_wgrad: dY view must be 16-byte aligned");
+    const bool implicit = cv->stride == 1 && x->c % 64 == 0 && x->ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x->ptr) & 15) == 0;
+    WgParams p{};
+    CUtensorMap tdy, tx;
+    p.Cout = cv->cout;
+    p.kpad = kpad;
+    p.dw = dw_packed;
+    p.m_tiles = (int)cdiv(cv->cout, WG_M);
+    int ncols;
+    if (implicit) {
+        const int menu[4][2] = {{8, 8}, {4, 16}, {2, 32}, {1, 64}};
+        int best = 0;
+        int64_t best_area = -1;
+        for (int i = 0; i < 4; ++i) {
+            int64_t area = cdiv(dy->h, menu[i][0]) * menu[i][0] * cdiv(dy->w, menu[i][1]) * menu[i][1];
+            if (best_area < 0 || area < best_area) { best_area = area; best = i; }
+        }
+        p.TH = menu[best][0]; p.TW = menu[best][1];
+        p.tiles_h = (int)cdiv(dy->h, p.TH); p.tiles_w = (int)cdiv(dy->w, p.TW); p.n_img = dy->n;
+        p.taps = cv->r * cv->s; p.S = cv->s; p.pad = cv->pad; p.dil = cv->dil;
+        ncols = x->c;
+        uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+        uint64_t dd[4] = {(uint64_t)dy->c, (uint64_t)dy->w, (uint64_t)dy->h, (uint64_t)dy->n};
+        uint64_t ds[4] = {2, (uint64_t)dy->ld * 2, (uint64_t)dy->ld * 2 * dy->w, (uint64_t)dy->ld * 2 * dy->w * dy->h};
+        int rc = make_tmap(&tdy, dy->ptr, 4, dd, ds, box);
+        if (rc) return rc;
+        uint64_t xd[4] = {(uint64_t)x->c, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
+        uint64_t xs[4] = {2, (uint64_t)x->ld * 2, (uint64_t)x->ld * 2 * x->w, (uint64_t)x->ld * 2 * x->w * x->h};
+        rc = make_tmap(&tx, x->ptr, 4, xd, xs, box);
+        if (rc) return rc;
+    } else {
+        const int64_t need = M * kpad * 2;
+        if (!ws || ws_bytes < need) {
+            set_error("conv_wgrad: workspace of %lld bytes required, %lld given", (long long)need, (long long)ws_bytes);
+            return HN_ERR_WORKSPACE;
+        }
+        int rc = im2col_bf16(x, cv, dy->h, dy->w, kpad, ws, st);
+        if (rc) return rc;
+        HN_CHECK_ARG(M < ((int64_t)1 << 31), "conv_wgrad: too many pixels");
+        p.TH = 1; p.TW = 64;
+        p.tiles_h = 1; p.tiles_w = (int)cdiv(M, 64); p.n_img = 1;
+        p.taps = 1; p.S = 1; p.pad = 0; p.dil = 1;
+        ncols = kpad;
+        uint32_t box[4] = {64, 64, 1, 1};
+        uint64_t dd[4] = {(uint64_t)dy->c, (uint64_t)M, 1, 1};
+        uint64_t ds[4] = {2, (uint64_t)dy->ld * 2, (uint64_t)dy->ld * 2, (uint64_t)dy->ld * 2};
+        rc = make_tmap(&tdy, dy->ptr, 4, dd, ds, box);
+        if (rc) return rc;
+        uint64_t xd[4] = {(uint64_t)kpad, (uint64_t)M, 1, 1};
+        uint64_t xs[4] = {2, (uint64_t)kpad * 2, (uint64_t)kpad * 2, (uint64_t)kpad * 2};
+        rc = make_tmap(&tx, ws, 4, xd, xs, box);
+        if (rc) return rc;
+    }
+    p.ncols = ncols;
+    const int bn = ncols % 256 == 0 ? 256 : (ncols % 128 == 0 ? 128 : 64);
+    p.n_tiles = (int)cdiv(ncols, bn);
+    const int num_kb = p.n_img * p.tiles_h * p.tiles_w;
+    const int base_items = p.m_tiles * p.n_tiles * p.taps;
+    int splits = (int)cdiv(2 * (int64_t)num_sms(), base_items);
+    if (splits > num_kb) splits = num_kb;
+    if (splits < 1) splits = 1;
+    // make every split non-empty
+    const int per = (int)cdiv(num_kb, splits);
+    splits = (int)cdiv(num_kb, per);
+    p.splits = splits;
+    switch (bn) {
+        case 256: return launch_wgrad<256, 4>(tdy, tx, p, st);
+        case 128: return launch_wgrad<128, 6>(tdy, tx, p, st);
+        default: return launch_wgrad<64, 8>(tdy, tx, p, st);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ FP32 CUDA-core wgrad
+constexpr int WF_BM = 64, WF_BN = 64, WF_BK = 16;   // cout tile, k-column tile, pixels per step
+
+__global__ void __launch_bounds__(256) wgrad_f32_kernel(const float *__restrict__ x, int ldx, const float *__restrict__ dy, int ldy, int N,
+                                                        int H, int W, int C, int Ho, int Wo, int Cout, int R, int S, int stride, int pad,
+                                                        int dil, int kpad, int64_t pix_per_split, float *__restrict__ dw)
+{
+    __shared__ float As[WF_BK][WF_BM + 4];   // dY[pix][co]
+    __shared__ float Bs[WF_BK][WF_BN + 4];   // im2col(X)[pix][k]
+    const int tid = threadIdx.x;
+    const int co0 = blockIdx.x * WF_BM, k0 = blockIdx.y * WF_BN;
+    const int K = R * S * C;
+    const int64_t M = (int64_t)N * Ho * Wo;
+    const int64_t p0 = (int64_t)blockIdx.z * pix_per_split;
+    const int64_t p1 = p0 + pix_per_split < M ? p0 + pix_per_split : M;
+    // loader: pixel lp = tid / 16 (0..15), 4 consecutive columns lc = (tid % 16) * 4
+    const int lp = tid >> 4, lc = (tid & 15) * 4;
+    // the 4 k-columns this thread gathers are fixed for the whole kernel: decode taps once
+    int kr[4], ks[4], kc[4];
+    bool kv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int k = k0 + lc + j;
+        kv[j] = k < K;
+        int tap = kv[j] ? k / C : 0;
+        kc[j] = kv[j] ? k - tap * C : 0;
+        kr[j] = tap / S;
+        ks[j] = tap - kr[j] * S;
+    }
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int64_t pb = p0; pb < p1; pb += WF_BK) {
+        const int64_t pix = pb + lp;
+        float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (pix < p1) {
+            const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((int64_t)Wo * Ho));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (co0 + lc + j < Cout) av[j] = dy[pix * ldy + co0 + lc + j];
+                if (kv[j]) {
+                    int hi = ho * stride - pad + kr[j] * dil, wi = wo * stride - pad + ks[j] * dil;
+                    if (hi >= 0 && hi < H && wi >= 0 && wi < W) bv[j] = x[(((int64_t)n * H + hi) * W + wi) * ldx + kc[j]];
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            As[lp][lc + j] = av[j];
+            Bs[lp][lc + j] = bv[j];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < WF_BK; ++kk) {
+            float4 a = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
+            float4 b = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+            const float aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int co = co0 + ty * 4 + i;
+        if (co >= Cout) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int k = k0 + tx * 4 + j;
+            if (k < K) atomicAdd(dw + (int64_t)co * kpad + k, acc[i][j]);
+        }
+    }
+}
+
+int conv2d_wgrad_f32(const hn_tensor *x, const hn_tensor *dy, const hn_conv *cv, float *dw_packed, cudaStream_t st)
+{
+    const int kpad = hn_conv_kpad(x->c, cv->r, cv->s);
+    const int K = cv->r * cv->s * x->c;
+    const int64_t M = (int64_t)dy->n * dy->h * dy->w;
+    if (M == 0) return HN_OK;
+    const int gx = (int)cdiv(cv->cout, WF_BM), gy = (int)cdiv(K, WF_BN);
+    int64_t splits = cdiv(4 * (int64_t)num_sms(), (int64_t)gx * gy);
+    int64_t pps = cdiv(M, splits);
+    pps = cdiv(pps, WF_BK) * WF_BK;
+    if (pps < 256) pps = 256;
+    splits = cdiv(M, pps);
+    if (splits > 65535) { pps = cdiv(cdiv(M, 65535), WF_BK) * WF_BK; splits = cdiv(M, pps); }
+    dim3 grid(gx, gy, (unsigned)splits);
+    wgrad_f32_kernel<<<grid, 256, 0, st>>>((const float *)x->ptr, x->ld, (const float *)dy->ptr, dy->ld, x->n, x->h, x->w, x->c, dy->h, dy->w,
+                                          cv->cout, cv->r, cv->s, cv->stride, cv->pad, cv->dil, kpad, pps, dw_packed);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+}  // namespace hn
+
+using namespace hn;
+
+static int conv_out_dim_w(int in, int k, int stride, int pad, int dil) { return (in + 2 * pad - dil * (k - 1) - 1) / stride + 1; }
+
+extern "C" int64_t hn_conv2d_wgrad_workspace_bytes(const hn_tensor *x, const hn_conv *cv)
+{
+    if (!x || !cv || x->dtype != HN_BF16) return 0;
+    const bool implicit = cv->stride == 1 && x->c % 64 == 0 && x->ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x->ptr) & 15) == 0;
+    if (implicit) return 0;
+    const int Ho = conv_out_dim_w(x->h, cv->r, cv->stride, cv->pad, cv->dil), Wo = conv_out_dim_w(x->w, cv->s, cv->stride, cv->pad, cv->dil);
+    return (int64_t)x->n * Ho * Wo * hn_conv_kpad(x->c, cv->r, cv->s) * 2;
+}
+
+extern "C" int hn_conv2d_wgrad(const hn_tensor *x, const hn_tensor *dy, const hn_conv *cv, float *dw_packed, int32_t zero_init,
+                               void *workspace, int64_t workspace_bytes, void *stream)
+{
+    HN_CHECK_ARG(x && dy && cv && dw_packed && x->ptr && dy->ptr, "hn_conv2d_wgrad: null pointer");
+    HN_CHECK_ARG(x->dtype == dy->dtype, "hn_conv2d_wgrad: x and dY must share a dtype");
+    const int Ho = conv_out_dim_w(x->h, cv->r, cv->stride, cv->pad, cv->dil), Wo = conv_out_dim_w(x->w, cv->s, cv->stride, cv->pad, cv->dil);
+    HN_CHECK_ARG(dy->n == x->n && dy->h == Ho && dy->w == Wo && dy->c == cv->cout, "hn_conv2d_wgrad: dY must be N=%d %dx%d C=%d", x->n, Ho, Wo,
+                 cv->cout);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int kpad = hn_conv_kpad(x->c, cv->r, cv->s);
+    const int cout_pad = hn_conv_cout_pad(cv->cout, x->dtype);
+    if (zero_init) HN_CUDA(cudaMemsetAsync(dw_packed, 0, sizeof(float) * (size_t)cout_pad * kpad, st));
+    if (x->dtype == HN_F32) return conv2d_wgrad_f32(x, dy, cv, dw_packed, st);
+    return conv2d_wgrad_tc(x, dy, cv, dw_packed, workspace, workspace_bytes, st);
+}

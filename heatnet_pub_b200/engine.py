@@ -237,28 +237,22 @@ def _epilogue(scale, shift, residual: Optional[Act], act, slope, slope_ptr) -> H
     return ep
 
 
-def conv2d(x: Act, conv: torch.nn.Conv2d, scale=None, shift=None, residual: Optional[Act] = None, act=ACT_NONE,
-           slope=0.0, slope_ptr=None, out: Optional[Act] = None, out_dtype=None) -> Act:
-    """y = act(conv(x) * scale + shift + residual) in one launch (plus an im2col gather for strided /
-    small-Cin shapes on the BF16 path)."""
+def conv2d_raw(x: Act, wp: torch.Tensor, cout: int, k: int, stride: int, pad: int, dil: int, scale=None, shift=None,
+               residual: Optional[Act] = None, act=ACT_NONE, slope=0.0, slope_ptr=None, out: Optional[Act] = None,
+               out_dtype=None, out_hw=None) -> Act:
+    """One convolution launch on a packed weight matrix (see hn_conv2d_fwd)."""
     lib = _lib.load()
-    assert conv.groups == 1 and conv.kernel_size[0] == conv.kernel_size[1] and conv.stride[0] == conv.stride[1]
-    assert conv.padding[0] == conv.padding[1] and conv.dilation[0] == conv.dilation[1]
-    if x.c != conv.in_channels:
-        raise RuntimeError(f"expected input with {conv.in_channels} channels, got {x.c}")
-    ho, wo = conv_out_hw(x.h, x.w, conv)
+    ho = (x.h + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    wo = (x.w + 2 * pad - dil * (k - 1) - 1) // stride + 1
     if ho < 1 or wo < 1:
-        raise RuntimeError(f"Calculated padded input size per channel: ({x.h + 2 * conv.padding[0]} x "
-                           f"{x.w + 2 * conv.padding[0]}). Kernel size: {tuple(conv.kernel_size)}. "
-                           "Kernel size can't be greater than actual input size")
+        raise RuntimeError(f"Calculated padded input size per channel: ({x.h + 2 * pad} x {x.w + 2 * pad}). "
+                           f"Kernel size: ({k}, {k}). Kernel size can't be greater than actual input size")
     if out is None:
-        out = new_act(x.n, ho, wo, conv.out_channels, out_dtype or x.dtype, x.buf.device)
-    assert (out.n, out.h, out.w, out.c) == (x.n, ho, wo, conv.out_channels)
+        out = new_act(x.n, ho, wo, cout, out_dtype or x.dtype, x.buf.device)
+    assert (out.n, out.h, out.w, out.c) == (x.n, ho, wo, cout), ((out.n, out.h, out.w, out.c), (x.n, ho, wo, cout))
     if residual is not None:
         assert residual.dtype == out.dtype and (residual.n, residual.h, residual.w, residual.c) == (out.n, out.h, out.w, out.c)
-    wp = packed_weight(conv, x.dtype)
-    cv = HnConv(conv.out_channels, conv.kernel_size[0], conv.kernel_size[1], conv.stride[0], conv.padding[0],
-                conv.dilation[0])
+    cv = HnConv(cout, k, k, stride, pad, dil)
     xh, yh = x.hn(), out.hn()
     ws_bytes = lib.hn_conv2d_workspace_bytes(C.byref(xh), C.byref(cv))
     ws_ptr = None
@@ -274,9 +268,21 @@ def conv2d(x: Act, conv: torch.nn.Conv2d, scale=None, shift=None, residual: Opti
                                  _stream()))
     if timing:
         ev_b.record()
-        conv_timer.append((f"{x.c}->{conv.out_channels} k{cv.r} s{cv.stride} d{cv.dil} @{x.h}x{x.w}", ev_a, ev_b))
+        conv_timer.append((f"{x.c}->{cout} k{k} s{stride} d{dil} @{x.h}x{x.w}", ev_a, ev_b))
     _count()
     return out
+
+
+def conv2d(x: Act, conv: torch.nn.Conv2d, scale=None, shift=None, residual: Optional[Act] = None, act=ACT_NONE,
+           slope=0.0, slope_ptr=None, out: Optional[Act] = None, out_dtype=None) -> Act:
+    """y = act(conv(x) * scale + shift + residual) in one launch (plus an im2col gather for strided /
+    small-Cin shapes on the BF16 path)."""
+    assert conv.groups == 1 and conv.kernel_size[0] == conv.kernel_size[1] and conv.stride[0] == conv.stride[1]
+    assert conv.padding[0] == conv.padding[1] and conv.dilation[0] == conv.dilation[1]
+    if x.c != conv.in_channels:
+        raise RuntimeError(f"expected input with {conv.in_channels} channels, got {x.c}")
+    return conv2d_raw(x, packed_weight(conv, x.dtype), conv.out_channels, conv.kernel_size[0], conv.stride[0], conv.padding[0],
+                      conv.dilation[0], scale, shift, residual, act, slope, slope_ptr, out, out_dtype)
 
 
 def affine_act(x: Act, scale, shift, residual: Optional[Act], act, slope=0.0, slope_ptr=None, out: Optional[Act] = None) -> Act:
@@ -383,3 +389,133 @@ def dropout2d(x: Act, p: float, mask: Optional[torch.Tensor] = None) -> Act:
     _lib.check(_lib.load().hn_affine_act(C.byref(x.hn()), C.byref(ep), C.byref(out.hn()), _stream()))
     _count()
     return out
+
+
+# -------------------------------------------------------------------------------------------------- backward ops
+def packed_weight_dgrad(conv: torch.nn.Conv2d, dtype: torch.dtype) -> torch.Tensor:
+    """Pack for dgrad-as-forward-conv: [cin_pad][kpad'], k' = ((R-1-r)*S + (S-1-s))*Cout + o (flipped taps, in/out
+    channels swapped), cached like the forward pack."""
+    lib = _lib.load()
+    cache = conv.__dict__.setdefault("_hn_wcache", {})
+    key = ("dgrad", dtype, conv.weight.device)
+    ver = _versions(conv.weight)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    w = conv.weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    cout, cin, r, s = w.shape
+    hdt = _HN_DTYPE[dtype]
+    cin_pad, kpad = lib.hn_conv_cout_pad(cin, hdt), lib.hn_conv_kpad(cout, r, s)
+    dst = torch.empty((cin_pad, kpad), dtype=dtype, device=w.device)
+    _lib.check(lib.hn_pack_weight_dgrad(w.data_ptr(), dst.data_ptr(), hdt, cout, cin, r, s, cin_pad, kpad, _stream()))
+    _count()
+    cache[key] = (ver, dst)
+    return dst
+
+
+def conv2d_dgrad(dy: Act, conv: torch.nn.Conv2d, in_h: int, in_w: int, out: Optional[Act] = None,
+                 accumulate: bool = False) -> Act:
+    """dX of a convolution = stride-1 convolution of dY (zero-inserted when the forward stride is > 1) with the
+    flipped, channel-transposed filter; `accumulate` adds into `out` through the epilogue's residual input."""
+    k, st, pad, dil = conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0]
+    padp = dil * (k - 1) - pad
+    assert padp >= 0, "dgrad needs pad <= dil*(k-1)"
+    g = dy
+    # the (zero-inserted) gradient map must be exactly this large for a stride-1 conv with pad' to return in_h x in_w
+    hu, wu = in_h - dil * (k - 1) + 2 * pad, in_w - dil * (k - 1) + 2 * pad
+    if st > 1 or (hu, wu) != (dy.h, dy.w):
+        up = new_act(dy.n, hu, wu, dy.c, dy.dtype, dy.buf.device, ld=(dy.c + 7) // 8 * 8)
+        _lib.check(_lib.load().hn_dilate(C.byref(dy.hn()), st, C.byref(up.hn()), _stream()))
+        _count()
+        g = up
+    wp = packed_weight_dgrad(conv, dy.dtype)
+    res = out if accumulate else None
+    return conv2d_raw(g, wp, conv.in_channels, k, 1, padp, dil, residual=res, out=out)
+
+
+def conv2d_wgrad(x: Act, dy: Act, conv: torch.nn.Conv2d) -> torch.Tensor:
+    """-> OIHW FP32 weight gradient (new tensor)."""
+    lib = _lib.load()
+    hdt = _HN_DTYPE[x.dtype]
+    cout, cin, k = conv.out_channels, conv.in_channels, conv.kernel_size[0]
+    cout_pad, kpad = lib.hn_conv_cout_pad(cout, hdt), lib.hn_conv_kpad(cin, k, k)
+    packed = torch.empty((cout_pad, kpad), dtype=torch.float32, device=x.buf.device)
+    cv = HnConv(cout, k, k, conv.stride[0], conv.padding[0], conv.dilation[0])
+    xh, dh = x.hn(), dy.hn()
+    ws_bytes = lib.hn_conv2d_wgrad_workspace_bytes(C.byref(xh), C.byref(cv))
+    ws_ptr = workspace(ws_bytes, x.buf.device).data_ptr() if ws_bytes else None
+    _lib.check(lib.hn_conv2d_wgrad(C.byref(xh), C.byref(dh), C.byref(cv), packed.data_ptr(), 1, ws_ptr, ws_bytes, _stream()))
+    _count(2 + (1 if ws_bytes else 0))
+    grad = torch.empty((cout, cin, k, k), dtype=torch.float32, device=x.buf.device)
+    _lib.check(lib.hn_unpack_wgrad(packed.data_ptr(), grad.data_ptr(), cout, cin, k, k, kpad, 0, _stream()))
+    _count()
+    return grad
+
+
+def act_bwd(dout: Act, out: Act, act, slope=0.0) -> Act:
+    dz = new_act(dout.n, dout.h, dout.w, dout.c, dout.dtype, dout.buf.device, ld=dout.ld if dout.c % 8 else None)
+    _lib.check(_lib.load().hn_act_bwd(C.byref(dout.hn()), C.byref(out.hn()), act, float(slope), C.byref(dz.hn()), _stream()))
+    _count()
+    return dz
+
+
+def channel_sums(x: Act) -> torch.Tensor:
+    """FP64 [2, C]: per-channel sum and sum of squares over all pixels."""
+    sums = torch.empty((2, x.c), dtype=torch.float64, device=x.buf.device)
+    _lib.check(_lib.load().hn_channel_stats(C.byref(x.hn()), sums[0].data_ptr(), sums[1].data_ptr(), _stream()))
+    _count(3)
+    return sums
+
+
+def vec_to_grad(src_f64: torch.Tensor, n: int) -> torch.Tensor:
+    g = torch.empty((n,), dtype=torch.float32, device=src_f64.device)
+    _lib.check(_lib.load().hn_vec_to_grad(src_f64.data_ptr(), g.data_ptr(), n, 0, _stream()))
+    _count()
+    return g
+
+
+def bn_bwd(dout: Act, out: Act, raw: Act, mean, invstd, gamma, act, slope=0.0, slope_ptr=None, dres: Optional[Act] = None,
+           dres_accumulate=False, want_prelu_grad=False):
+    """-> (draw Act, sums FP64 [2C+1]): sums[:C] = dbeta, sums[C:2C] = dgamma, sums[2C] = dslope."""
+    cch = dout.c
+    sums = torch.empty((2 * cch + 1,), dtype=torch.float64, device=dout.buf.device)
+    draw = new_act(dout.n, dout.h, dout.w, cch, dout.dtype, dout.buf.device)
+    p = lambda t: t.detach().data_ptr() if t is not None else None
+    _lib.check(_lib.load().hn_bn_bwd(C.byref(dout.hn()), C.byref(out.hn()), C.byref(raw.hn()), p(mean), p(invstd), p(gamma), act,
+                                    float(slope), p(slope_ptr), sums.data_ptr(), C.byref(draw.hn()),
+                                    C.byref(dres.hn()) if dres is not None else None, int(dres_accumulate),
+                                    int(want_prelu_grad), _stream()))
+    _count(3)
+    return draw, sums
+
+
+def accumulate(x: Act, y: Act, add: bool):
+    _lib.check(_lib.load().hn_accumulate(C.byref(x.hn()), C.byref(y.hn()), int(add), _stream()))
+    _count()
+
+
+def maxpool3x3s2_idx(x: Act, out: Optional[Act] = None):
+    ho, wo = (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1
+    out = out or new_act(x.n, ho, wo, x.c, x.dtype, x.buf.device)
+    idx = torch.empty((x.n, ho, wo, x.c), dtype=torch.uint8, device=x.buf.device)
+    _lib.check(_lib.load().hn_maxpool3x3s2_fwd_idx(C.byref(x.hn()), C.byref(out.hn()), idx.data_ptr(), _stream()))
+    _count()
+    return out, idx
+
+
+def maxpool3x3s2_bwd(dy: Act, idx: torch.Tensor, dx: Act, add: bool):
+    _lib.check(_lib.load().hn_maxpool3x3s2_bwd(C.byref(dy.hn()), idx.data_ptr(), C.byref(dx.hn()), int(add), _stream()))
+    _count()
+
+
+def bilinear_bwd(dy: Act, dx: Act, add: bool):
+    _lib.check(_lib.load().hn_bilinear_bwd(C.byref(dy.hn()), C.byref(dx.hn()), int(add), _stream()))
+    _count()
+
+
+def pyramid_pool_bwd(dpool: torch.Tensor, sizes: Sequence[int], dx: Act, add: bool):
+    arr = (C.c_int32 * len(sizes))(*sizes)
+    _lib.check(_lib.load().hn_pyramid_pool_bwd(dpool.data_ptr(), arr, len(sizes), C.byref(dx.hn()), int(add), _stream()))
+    _count()

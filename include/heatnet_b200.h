@@ -119,6 +119,37 @@ int hn_bn_finalize(const double *sum, const double *sqsum, int64_t count, const 
                    float eps, float momentum, float *running_mean, float *running_var, float *scale, float *shift,
                    float *save_mean, float *save_invstd, int32_t c, void *stream);
 
+/* ---- backward (autograd of the ops above; the reference gets these from torch.autograd / cuDNN) ---- */
+/* dz = dout * act'(out), the derivative taken through the saved output (conv + bias + activation layers) */
+int hn_act_bwd(const hn_tensor *dout, const hn_tensor *out, int32_t act, float slope, const hn_tensor *dz, void *stream);
+/* BatchNorm2d (train) backward fused with the activation / residual split:
+ *   dz = dout*act'(out);  sums[0..C) = sum dz (= dbeta), sums[C..2C) = sum dz*xhat (= dgamma), sums[2C] = dPReLU slope
+ *   draw = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat));  dres (+)= dz.   raw: FP32 pre-normalisation tensor. */
+int hn_bn_bwd(const hn_tensor *dout, const hn_tensor *out, const hn_tensor *raw, const float *mean, const float *invstd,
+              const float *gamma, int32_t act, float slope, const float *slope_ptr, double *sums, const hn_tensor *draw,
+              const hn_tensor *dres, int32_t dres_accumulate, int32_t want_prelu_grad, void *stream);
+/* y = x (accumulate == 0) or y += x; dtypes may differ */
+int hn_accumulate(const hn_tensor *x, const hn_tensor *y, int32_t accumulate, void *stream);
+/* MaxPool2d(3,2,1) forward that also records the winning tap (uint8 [N][Ho][Wo][C]) and its backward */
+int hn_maxpool3x3s2_fwd_idx(const hn_tensor *x, const hn_tensor *y, uint8_t *idx, void *stream);
+int hn_maxpool3x3s2_bwd(const hn_tensor *dy, const uint8_t *idx, const hn_tensor *dx, int32_t accumulate, void *stream);
+/* adjoints of hn_bilinear_fwd / hn_pyramid_pool_fwd (gather form, deterministic) */
+int hn_bilinear_bwd(const hn_tensor *dy, const hn_tensor *dx, int32_t accumulate, void *stream);
+int hn_pyramid_pool_bwd(const void *dpool, const int32_t *sizes, int32_t nsizes, const hn_tensor *dx, int32_t accumulate, void *stream);
+/* conv dgrad = hn_conv2d_fwd of the (zero-inserted, for stride > 1) output gradient with the flipped/transposed pack */
+int hn_dilate(const hn_tensor *x, int32_t stride, const hn_tensor *up, void *stream);
+int hn_pack_weight_dgrad(const float *w_oihw, void *dst, int32_t dtype, int32_t cout, int32_t cin, int32_t r, int32_t s,
+                         int32_t cin_pad, int32_t kpad, void *stream);
+/* conv wgrad into the packed FP32 layout [cout_pad][kpad] (BF16: tcgen05 with MN-major operands, split over pixels;
+ * FP32: CUDA cores), then packed -> OIHW parameter gradient */
+int64_t hn_conv2d_wgrad_workspace_bytes(const hn_tensor *x, const hn_conv *cv);
+int hn_conv2d_wgrad(const hn_tensor *x, const hn_tensor *dy, const hn_conv *cv, float *dw_packed, int32_t zero_init, void *workspace,
+                    int64_t workspace_bytes, void *stream);
+int hn_unpack_wgrad(const float *packed, float *grad_oihw, int32_t cout, int32_t cin, int32_t r, int32_t s, int32_t kpad,
+                    int32_t accumulate, void *stream);
+/* FP64 per-channel sums -> FP32 parameter gradient (bias / gamma / beta / PReLU slope) */
+int hn_vec_to_grad(const double *src, float *grad, int32_t n, int32_t accumulate, void *stream);
+
 /* ---- metric: scripts/iou_eval.py:53-88,154-159 (max(1) + np.bincount(pred + K*target) on the host) ---- */
 /* pred_labels: int64 [n_pixels] class ids, or NULL when `scores` (NCHW FP32 [N][K][HW]) is given, in which
  * case the first-max argmax over K is fused.  conf: device int64 [K*K], row = target, col = predicted,
