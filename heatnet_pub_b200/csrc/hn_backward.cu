@@ -206,6 +206,20 @@ __global__ void __launch_bounds__(256) accumulate_kernel(const TX *__restrict__ 
         }
 }
 
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(256) accumulate_scalar_kernel(const TX *__restrict__ x, int ldx, TY *__restrict__ y, int ldy, int accumulate,
+                                                                int64_t npix, int C)
+{
+    const int64_t total = npix * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t p = i / C;
+        int c = (int)(i - p * C);
+        float v = to_f32<TX>(x[p * ldx + c]);
+        if (accumulate) v += to_f32<TY>(y[p * ldy + c]);
+        y[p * ldy + c] = from_f32<TY>(v);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // max-pool 3x3 s2 p1: forward that also records the winning tap (0..8, first max in window order like ATen),
 // and the backward gather: every input pixel looks at the <= 4 windows that contain it.
@@ -582,15 +596,21 @@ extern "C" int hn_bn_bwd(const hn_tensor *dout, const hn_tensor *out, const hn_t
 extern "C" int hn_accumulate(const hn_tensor *x, const hn_tensor *y, int32_t accumulate, void *stream)
 {
     HN_CHECK_ARG(x && y && x->ptr && y->ptr && same_shape(x, y), "hn_accumulate: bad arguments");
-    HN_CHECK_ARG(vec8_ok(x) && vec8_ok(y), "hn_accumulate: views must be 8-channel aligned");
     const int64_t npix = (int64_t)x->n * x->h * x->w;
     if (npix == 0) return HN_OK;
-    int grid = wave_grid_b(cdiv(npix, 64) * 256, 256, 16);
     cudaStream_t st = (cudaStream_t)stream;
-    if (x->dtype == HN_BF16 && y->dtype == HN_BF16) accumulate_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16 *)x->ptr, x->ld, (bf16 *)y->ptr, y->ld, accumulate, npix, x->c);
-    else if (x->dtype == HN_F32 && y->dtype == HN_F32) accumulate_kernel<float, float><<<grid, 256, 0, st>>>((const float *)x->ptr, x->ld, (float *)y->ptr, y->ld, accumulate, npix, x->c);
-    else if (x->dtype == HN_F32 && y->dtype == HN_BF16) accumulate_kernel<float, bf16><<<grid, 256, 0, st>>>((const float *)x->ptr, x->ld, (bf16 *)y->ptr, y->ld, accumulate, npix, x->c);
-    else accumulate_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16 *)x->ptr, x->ld, (float *)y->ptr, y->ld, accumulate, npix, x->c);
+    const bool vec = vec8_ok(x) && vec8_ok(y);
+    int grid = vec ? wave_grid_b(cdiv(npix, 64) * 256, 256, 16) : wave_grid_b(npix * x->c, 256);
+#define HN_ACC(TX, TY)                                                                                                       \
+    do {                                                                                                                     \
+        if (vec) accumulate_kernel<TX, TY><<<grid, 256, 0, st>>>((const TX *)x->ptr, x->ld, (TY *)y->ptr, y->ld, accumulate, npix, x->c); \
+        else accumulate_scalar_kernel<TX, TY><<<grid, 256, 0, st>>>((const TX *)x->ptr, x->ld, (TY *)y->ptr, y->ld, accumulate, npix, x->c); \
+    } while (0)
+    if (x->dtype == HN_BF16 && y->dtype == HN_BF16) HN_ACC(bf16, bf16);
+    else if (x->dtype == HN_F32 && y->dtype == HN_F32) HN_ACC(float, float);
+    else if (x->dtype == HN_F32 && y->dtype == HN_BF16) HN_ACC(float, bf16);
+    else HN_ACC(bf16, float);
+#undef HN_ACC
     HN_LAUNCH_CHECK();
     return HN_OK;
 }

@@ -184,6 +184,35 @@ __global__ void channel_stats_kernel(const T *__restrict__ x, int64_t npix, int 
     }
 }
 
+// narrow / unaligned views (C = 13 logits, C = 1 critic maps): grid = (pixel chunks, C), block-wide reduction per channel
+template <typename T>
+__global__ void __launch_bounds__(256) channel_stats_scalar_kernel(const T *__restrict__ x, int64_t npix, int ld, int64_t pix_per_cta,
+                                                                   double *sum, double *sqsum)
+{
+    __shared__ double sa[8], sb[8];
+    const int c = blockIdx.y;
+    const int64_t p0 = (int64_t)blockIdx.x * pix_per_cta;
+    const int64_t p1 = min(p0 + pix_per_cta, npix);
+    double a = 0.0, b = 0.0;
+    for (int64_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+        float v = to_f32<T>(x[p * ld + c]);
+        a += v;
+        b += (double)v * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = a; sb[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) { a += sa[i]; b += sb[i]; }
+        atomicAdd(sum + c, a);
+        atomicAdd(sqsum + c, b);
+    }
+}
+
 __global__ void bn_finalize_kernel(const double *sum, const double *sqsum, double count, const float *gamma, const float *beta,
                                    float eps, float momentum, float *running_mean, float *running_var, float *scale, float *shift,
                                    float *save_mean, float *save_invstd, int C)
@@ -538,12 +567,22 @@ extern "C" int hn_bn_fold(const float *gamma, const float *beta, const float *me
 extern "C" int hn_channel_stats(const hn_tensor *x, double *sum, double *sqsum, void *stream)
 {
     HN_CHECK_ARG(x && x->ptr && sum && sqsum, "hn_channel_stats: null pointer");
-    HN_CHECK_ARG(vec8_ok(x), "hn_channel_stats: view must be 8-channel aligned (C=%d ld=%d)", x->c, x->ld);
     cudaStream_t st = (cudaStream_t)stream;
     HN_CUDA(cudaMemsetAsync(sum, 0, sizeof(double) * x->c, st));
     HN_CUDA(cudaMemsetAsync(sqsum, 0, sizeof(double) * x->c, st));
     const int64_t npix = (int64_t)x->n * x->h * x->w;
     if (npix == 0) return HN_OK;
+    if (!vec8_ok(x)) {
+        int64_t nch = cdiv((int64_t)num_sms() * 4, x->c);
+        int64_t ppc = cdiv(npix, nch);
+        if (ppc < 2048) ppc = 2048;
+        nch = cdiv(npix, ppc);
+        dim3 g((unsigned)nch, (unsigned)x->c);
+        if (x->dtype == HN_BF16) channel_stats_scalar_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16 *)x->ptr, npix, x->ld, ppc, sum, sqsum);
+        else channel_stats_scalar_kernel<float><<<g, 256, 0, st>>>((const float *)x->ptr, npix, x->ld, ppc, sum, sqsum);
+        HN_LAUNCH_CHECK();
+        return HN_OK;
+    }
     const int ncv = x->c / 8;
     const int CVB = ncv < 32 ? ncv : 32;
     const int PL = 256 / CVB;

@@ -7,6 +7,7 @@ Bias and LeakyReLU run in the conv epilogues; the critic map is returned as FP32
 import torch
 import torch.nn as nn
 
+from . import autograd
 from . import engine as E
 from .engine import ACT_LEAKY, ACT_NONE, Act
 from .extractors import _KernelModule
@@ -29,14 +30,25 @@ class FCDiscriminator(_KernelModule):
     def _run(self, x: Act) -> Act:
         slope = self.leaky_relu.negative_slope
         for conv in (self.conv1, self.conv2, self.conv3, self.conv4):
-            scale, shift = E.folded_affine(conv, None)
-            x = E.conv2d(x, conv, scale, shift, act=ACT_LEAKY, slope=slope)
-        scale, shift = E.folded_affine(self.classifier, None)
-        x = E.conv2d(x, self.classifier, scale, shift, out_dtype=torch.float32)
+            x = E.conv_bn_act(x, conv, None, ACT_LEAKY, slope)
+        ho, wo = E.conv_out_hw(x.h, x.w, self.classifier)
+        if ho < 1 or wo < 1:
+            raise RuntimeError(f"Calculated padded input size per channel: ({x.h + 2} x {x.w + 2}). Kernel size: (4, 4). "
+                               "Kernel size can't be greater than actual input size")
+        score = E.new_act(x.n, ho, wo, 1, torch.float32, x.buf.device, ld=4)      # FP32 critic map
+        E.conv_bn_act(x, self.classifier, None, out=score)
         f = int(self.up_sample.scale_factor)
-        return E.bilinear(x, f * x.h, f * x.w)
+        return E.bilinear(score, f * score.h, f * score.w)
 
     def forward(self, x):
-        E.refuse_autograd(self, x)
+        if autograd.needs_autograd(self, x):
+            return autograd.apply(self._autograd_runner, [x], self)[0]
         y = self._run(E.from_nchw(x, self._dtype()))
         return y.nchw()            # C == 1: NHWC and NCHW coincide, dense FP32 (N,1,H,W)
+
+    def _autograd_runner(self, tape, inputs):
+        xin = E.from_nchw(inputs[0], self._dtype())
+        if inputs[0].requires_grad:
+            tape.require(xin)
+        y = self._run(xin)
+        return [xin], [y], [y.nchw()]

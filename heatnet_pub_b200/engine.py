@@ -100,6 +100,111 @@ def act_from_view(t: torch.Tensor) -> Optional[Act]:
     return Act(base, c, coff)
 
 
+# -------------------------------------------------------------------------------------------------- autograd tape
+class Grads:
+    """Gradient storage of one backward pass: one NHWC gradient buffer per activation buffer (same shape, compute
+    dtype), with the channel ranges that already hold contributions.  Channel-slice views of one buffer (the
+    zero-copy concats) therefore accumulate into slices of one gradient buffer."""
+
+    def __init__(self):
+        self.bufs = {}          # activation buf data_ptr -> [grad tensor, [(c0, c1), ...]]
+        self.params = {}        # nn.Parameter -> gradient tensor
+
+    def _entry(self, act: "Act", dtype=None):
+        key = act.buf.data_ptr()
+        e = self.bufs.get(key)
+        if e is None:
+            e = [torch.empty(act.buf.shape, dtype=dtype or act.buf.dtype, device=act.buf.device), []]
+            self.bufs[key] = e
+        return e
+
+    @staticmethod
+    def _covered(ranges, c0, c1):
+        return any(a <= c0 and c1 <= b for a, b in ranges)
+
+    @staticmethod
+    def _touches(ranges, c0, c1):
+        return any(a < c1 and c0 < b for a, b in ranges)
+
+    def target(self, act: "Act", dtype=None):
+        """-> (gradient view for act's channel range, already_initialised).  Call mark() after writing."""
+        e = self._entry(act, dtype)
+        c0, c1 = act.coff, act.coff + act.c
+        if self._covered(e[1], c0, c1):
+            inited = True
+        elif not self._touches(e[1], c0, c1):
+            inited = False
+        else:                                   # partial overlap: zero the rest, then accumulate
+            self._zero_uncovered(e, c0, c1)
+            inited = True
+        return Act(e[0], act.c, act.coff), inited
+
+    def _zero_uncovered(self, e, c0, c1):
+        c = c0
+        for a, b in sorted(e[1]):
+            if b <= c or a >= c1:
+                continue
+            if a > c:
+                e[0][..., c:a].zero_()
+            c = max(c, b)
+        if c < c1:
+            e[0][..., c:c1].zero_()
+        e[1].append((c0, c1))
+
+    def mark(self, act: "Act"):
+        e = self._entry(act)
+        c0, c1 = act.coff, act.coff + act.c
+        if not self._covered(e[1], c0, c1):
+            e[1].append((c0, c1))
+
+    def get(self, act: "Act") -> Optional["Act"]:
+        """Gradient of act, or None when nothing flowed into it."""
+        e = self.bufs.get(act.buf.data_ptr())
+        if e is None:
+            return None
+        c0, c1 = act.coff, act.coff + act.c
+        if not self._touches(e[1], c0, c1):
+            return None
+        if not self._covered(e[1], c0, c1):
+            self._zero_uncovered(e, c0, c1)
+        return Act(e[0], act.c, act.coff)
+
+    def add_param(self, param, grad):
+        if param in self.params:
+            self.params[param] = self.params[param] + grad
+        else:
+            self.params[param] = grad
+
+
+class Tape:
+    """Backward closures recorded by the ops below during a training-mode forward, replayed in reverse."""
+
+    def __init__(self, input_needs_grad=False):
+        self.ops = []
+        self.live = set()        # data_ptrs of activation buffers whose gradient is needed
+
+    def needs(self, act: Optional["Act"]) -> bool:
+        return act is not None and act.buf.data_ptr() in self.live
+
+    def require(self, act: "Act"):
+        self.live.add(act.buf.data_ptr())
+
+    def record(self, fn):
+        self.ops.append(fn)
+
+    def backward(self, grads: Grads):
+        for fn in reversed(self.ops):
+            fn(grads)
+        self.ops = []
+
+
+current_tape: Optional[Tape] = None
+
+
+def _wants(p) -> bool:
+    return p is not None and p.requires_grad
+
+
 # -------------------------------------------------------------------------------------------------- workspace
 _workspace = {}
 
@@ -320,28 +425,120 @@ def batchnorm_train_affine(x: Act, bn: torch.nn.BatchNorm2d):
     return out[0], out[1], out[2], out[3]
 
 
+def _conv_param_backward(grads: Grads, tape: Tape, x: Act, conv, dz: Act):
+    """Shared tail of every conv backward: weight / bias gradients and the input gradient."""
+    if dz.dtype != x.dtype:                       # e.g. FP32 critic map gradient -> BF16 operands
+        cast = new_act(dz.n, dz.h, dz.w, dz.c, x.dtype, dz.buf.device, ld=(dz.c + 7) // 8 * 8)
+        accumulate(dz, cast, False)
+        dz = cast
+    if _wants(conv.weight):
+        grads.add_param(conv.weight, conv2d_wgrad(x, dz, conv))
+    if _wants(conv.bias):
+        grads.add_param(conv.bias, vec_to_grad(channel_sums(dz)[0], conv.out_channels))
+    if tape.needs(x):
+        gx, inited = grads.target(x)
+        conv2d_dgrad(dz, conv, x.h, x.w, out=gx, accumulate=inited)
+        grads.mark(x)
+
+
 def conv_bn_act(x: Act, conv, bn, act=ACT_NONE, slope=0.0, slope_ptr=None, residual: Optional[Act] = None,
                 out: Optional[Act] = None, bn_training: Optional[bool] = None) -> Act:
     """conv -> BatchNorm2d -> (+residual) -> activation.
     eval BN: folded into the conv epilogue (1 launch).  train BN: conv (+bias) -> batch statistics -> one fused
-    normalise + residual + activation pass in place."""
+    normalise + residual + activation pass.  With a tape active the backward closure is recorded."""
+    tape = current_tape
     if bn_training is None:      # like nn.BatchNorm2d: batch statistics iff the BN module itself is in train mode
         bn_training = bn is not None and (bn.training or bn.running_mean is None)
     if bn is None or not bn_training:
         scale, shift = folded_affine(conv, bn)
-        return conv2d(x, conv, scale, shift, residual, act, slope, slope_ptr, out)
+        y = conv2d(x, conv, scale, shift, residual, act, slope, slope_ptr, out)
+        if tape is not None:
+            _record_conv_affine(tape, x, conv, bn, scale, y, residual, act, slope, slope_ptr)
+        return y
     scale, shift = folded_affine(conv, None)                      # conv bias only
     # The pre-normalisation tensor stays FP32: (x - mean) * invstd amplifies BF16 rounding of x by |mean|/std,
     # which is large for channels with little spatial variation.  Statistics and the normalise pass read the
     # FP32 values; only the normalised activation is rounded to the compute dtype.
-    raw = conv2d(x, conv, scale, shift, None, ACT_NONE, out_dtype=torch.float32 if BN_TRAIN_RAW_FP32 else None)
-    bscale, bshift, _, _ = batchnorm_train_affine(raw, bn)
+    raw_fp32 = BN_TRAIN_RAW_FP32 or tape is not None
+    raw = conv2d(x, conv, scale, shift, None, ACT_NONE, out_dtype=torch.float32 if raw_fp32 else None)
+    bscale, bshift, mean, invstd = batchnorm_train_affine(raw, bn)
     if out is None:
-        out = raw if raw.dtype == x.dtype else new_act(raw.n, raw.h, raw.w, raw.c, x.dtype, x.buf.device)
-    return affine_act(raw, bscale, bshift, residual, act, slope, slope_ptr, out=out)
+        in_place = raw.dtype == x.dtype and tape is None
+        out = raw if in_place else new_act(raw.n, raw.h, raw.w, raw.c, x.dtype, x.buf.device)
+    y = affine_act(raw, bscale, bshift, residual, act, slope, slope_ptr, out=out)
+    if tape is not None:
+        live = tape.needs(x) or tape.needs(residual) or any(_wants(p) for p in (conv.weight, conv.bias, bn.weight, bn.bias, slope_ptr))
+        if live:
+            tape.require(y)
+
+            def backward(grads: Grads):
+                dout = grads.get(y)
+                if dout is None:
+                    return
+                dres, dres_acc = None, False
+                if tape.needs(residual):
+                    dres, dres_acc = grads.target(residual)
+                prelu = _wants(slope_ptr)
+                draw, sums = bn_bwd(dout, y, raw, mean, invstd, bn.weight, act, slope, slope_ptr, dres, dres_acc, prelu)
+                if dres is not None:
+                    grads.mark(residual)
+                cch = y.c
+                if _wants(bn.bias):
+                    grads.add_param(bn.bias, vec_to_grad(sums, cch))
+                if _wants(bn.weight):
+                    grads.add_param(bn.weight, vec_to_grad(sums[cch:], cch))
+                if prelu:
+                    grads.add_param(slope_ptr, vec_to_grad(sums[2 * cch:], 1))
+                _conv_param_backward(grads, tape, x, conv, draw)
+
+            tape.record(backward)
+    return y
+
+
+def _record_conv_affine(tape: Tape, x: Act, conv, bn, scale, y: Act, residual, act, slope, slope_ptr):
+    """Backward of y = act(conv(x)*scale + shift + residual) with constant scale (conv bias / eval-mode BN)."""
+    if bn is not None and (_wants(bn.weight) or _wants(bn.bias)):
+        raise NotImplementedError("gradients of BatchNorm2d affine parameters need the BN module in train mode")
+    live = tape.needs(x) or tape.needs(residual) or any(_wants(p) for p in (conv.weight, conv.bias, slope_ptr))
+    if not live:
+        return
+    if _wants(slope_ptr):
+        raise NotImplementedError("PReLU slope gradient is only implemented behind a train-mode BatchNorm2d")
+    tape.require(y)
+
+    def backward(grads: Grads):
+        dout = grads.get(y)
+        if dout is None:
+            return
+        sl = float(slope_ptr.detach().item()) if slope_ptr is not None else slope
+        dz = act_bwd(dout, y, act, sl) if act != ACT_NONE else dout
+        if tape.needs(residual):
+            gr, inited = grads.target(residual)
+            accumulate(dz, gr, inited)
+            grads.mark(residual)
+        if bn is not None:            # eval-mode BN: constant per-channel scale in front of the conv output
+            dz = affine_act(dz, scale, None, None, ACT_NONE, out=new_act(dz.n, dz.h, dz.w, dz.c, dz.dtype, dz.buf.device))
+        _conv_param_backward(grads, tape, x, conv, dz)
+
+    tape.record(backward)
 
 
 def maxpool3x3s2(x: Act, out: Optional[Act] = None) -> Act:
+    tape = current_tape
+    if tape is not None and tape.needs(x):
+        y, idx = maxpool3x3s2_idx(x, out)
+        tape.require(y)
+
+        def backward(grads: Grads):
+            dy = grads.get(y)
+            if dy is None:
+                return
+            gx, inited = grads.target(x)
+            maxpool3x3s2_bwd(dy, idx, gx, inited)
+            grads.mark(x)
+
+        tape.record(backward)
+        return y
     ho, wo = (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1
     out = out or new_act(x.n, ho, wo, x.c, x.dtype, x.buf.device)
     _lib.check(_lib.load().hn_maxpool3x3s2_fwd(C.byref(x.hn()), C.byref(out.hn()), _stream()))
@@ -365,6 +562,27 @@ def pyramid_pool(x: Act, sizes: Sequence[int]):
         cnt = x.n * s * s * x.c
         acts.append(Act(out[off:off + cnt].view(x.n, s, s, x.c)))
         off += cnt
+    tape = current_tape
+    if tape is not None and tape.needs(x):
+        for a in acts:
+            tape.require(a)
+
+        def backward(grads: Grads):
+            gs = [grads.get(a) for a in acts]
+            if all(g is None for g in gs):
+                return
+            dpool = torch.zeros_like(out)        # the per-size blocks, in the forward's layout
+            o = 0
+            for a, g in zip(acts, gs):
+                cnt = a.buf.numel()
+                if g is not None:
+                    accumulate(g, Act(dpool[o:o + cnt].view(a.buf.shape)), False)
+                o += cnt
+            gx, inited = grads.target(x)
+            pyramid_pool_bwd(dpool, list(sizes), gx, inited)
+            grads.mark(x)
+
+        tape.record(backward)
     return acts
 
 
@@ -373,6 +591,20 @@ def bilinear(x: Act, h: int, w: int, out: Optional[Act] = None, out_dtype=None) 
     assert (out.n, out.h, out.w, out.c) == (x.n, h, w, x.c)
     _lib.check(_lib.load().hn_bilinear_fwd(C.byref(x.hn()), C.byref(out.hn()), _stream()))
     _count()
+    tape = current_tape
+    if tape is not None and tape.needs(x):
+        y = out
+        tape.require(y)
+
+        def backward(grads: Grads):
+            dy = grads.get(y)
+            if dy is None:
+                return
+            gx, inited = grads.target(x)
+            bilinear_bwd(dy, gx, inited)
+            grads.mark(x)
+
+        tape.record(backward)
     return out
 
 
@@ -388,6 +620,28 @@ def dropout2d(x: Act, p: float, mask: Optional[torch.Tensor] = None) -> Act:
     out = new_act(x.n, x.h, x.w, x.c, x.dtype, x.buf.device)
     _lib.check(_lib.load().hn_affine_act(C.byref(x.hn()), C.byref(ep), C.byref(out.hn()), _stream()))
     _count()
+    tape = current_tape
+    if tape is not None and tape.needs(x):
+        y = out
+        tape.require(y)
+
+        def backward(grads: Grads):
+            dy = grads.get(y)
+            if dy is None:
+                return
+            gx, inited = grads.target(x)
+            if inited:
+                tmp = new_act(x.n, x.h, x.w, x.c, dy.dtype, x.buf.device)
+                _lib.check(_lib.load().hn_affine_act(C.byref(dy.hn()), C.byref(ep), C.byref(tmp.hn()), _stream()))
+                accumulate(tmp, gx, True)
+                _count()
+            else:
+                _lib.check(_lib.load().hn_affine_act(C.byref(dy.hn()), C.byref(ep), C.byref(gx.hn()), _stream()))
+                _count()
+            grads.mark(x)
+            _keep = scale          # the mask vector must outlive the closure's ep pointer
+
+        tape.record(backward)
     return out
 
 

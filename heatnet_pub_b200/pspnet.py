@@ -8,6 +8,7 @@ names and state_dict.  Reference: cm/models/pspnet.py:8-76, models/pspnet.py:8-7
 import torch
 from torch import nn
 
+from . import autograd
 from . import engine as E
 from . import extractors
 from .engine import ACT_LEAKY, ACT_NONE, ACT_RELU, Act
@@ -53,10 +54,9 @@ class PSPModule(_KernelModule):
         f = feats.c
         pooled = E.pyramid_pool(feats, self.sizes())
         for i, st in enumerate(self.stages):
-            prior = E.conv2d(pooled[i], st[1])
+            prior = E.conv_bn_act(pooled[i], st[1], None)
             E.bilinear(prior, cat.h, cat.w, out=cat.slice(i * f, f))
-        scale, shift = E.folded_affine(self.bottleneck, None)
-        return E.conv2d(cat, self.bottleneck, scale, shift, act=ACT_RELU)
+        return E.conv_bn_act(cat, self.bottleneck, None, ACT_RELU)
 
     def _run(self, feats: Act) -> Act:
         cat = self.alloc_cat(feats.n, feats.h, feats.w, feats.dtype, feats.buf.device)
@@ -127,10 +127,9 @@ class PSPNet(_KernelModule):
         p = self.up_3._run(p)
         p = self._dropout(p, self.drop_2)
         fin = self.final[0]
-        scale, shift = E.folded_affine(fin, None)
         # logits are produced in FP32 on both paths (NHWC, channel stride padded to a multiple of 8)
         logits = E.new_act(p.n, p.h, p.w, fin.out_channels, torch.float32, p.buf.device, ld=(fin.out_channels + 7) // 8 * 8)
-        E.conv2d(p, fin, scale, shift, out=logits)
+        E.conv_bn_act(p, fin, None, out=logits)
         return logits, f
 
     def _h8w8(self, h, w):
@@ -140,11 +139,30 @@ class PSPNet(_KernelModule):
         return (h4 - 1) // st + 1, (w4 - 1) // st + 1
 
     def forward(self, modal_1, modal_2=None):
-        E.refuse_autograd(self, modal_1, modal_2)
+        if autograd.needs_autograd(self, modal_1, modal_2):
+            outs = autograd.apply(self._autograd_runner, [modal_1, modal_2], self)
+            return outs[0], list(outs), None
         m1, m2 = self.feats._inputs(modal_1, modal_2)
         logits, f = self._run_full(m1, m2)
         out = E.to_nchw_f32(logits)                       # the reference's NCHW FP32 logits
         return out, [out, f[0].nchw(), f[1].nchw(), f[2].nchw(), f[3].nchw(), f[4].nchw()], None
+
+    def _autograd_runner(self, tape, inputs):
+        """Forward under a tape: -> (input acts, output acts, output tensors) for autograd._NetFunction."""
+        modal_1, modal_2 = inputs
+        m1, m2 = self.feats._inputs(modal_1, modal_2)
+        if modal_1.requires_grad:
+            tape.require(m1)
+        if m2 is not None and modal_2.requires_grad:
+            tape.require(m2)
+        logits, f = self._run_full(m1, m2)
+        out = E.to_nchw_f32(logits)
+        if self.feats.late_fusion or modal_2 is None:
+            in_acts = [m1, m2]
+        else:                                                   # early fusion: the two inputs are channel slices of m1
+            c1 = modal_1.shape[1]
+            in_acts = [m1.slice(0, c1), m1.slice(c1, m1.c - c1)]
+        return in_acts, [logits] + list(f), [out] + [t.nchw() for t in f]
 
 
 class PSPNetRGB(PSPNet):
