@@ -30,20 +30,43 @@ def _oracle_grads(sd, loss_fn):
     return loss.item(), {k: sd[k].grad for k in keys if sd[k].grad is not None}
 
 
-@pytest.mark.parametrize("precision,gtol", [("fp32", 2e-3), ("bf16", None)])
-def test_pspnet_backward_matches_oracle_autograd(precision, gtol):
+def rel_l2(a, b):
+    a = torch.as_tensor(np.asarray(a)).double()
+    b = torch.as_tensor(np.asarray(b)).double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_pspnet_backward_matches_oracle_autograd(precision):
     """Late-fusion PSPNet, train-mode BN, dropout off, loss = CE(logits) + mean-square of every tap: every
-    parameter gradient against torch.autograd of the oracle."""
+    parameter gradient against torch.autograd of the oracle evaluated in FP64.
+
+    Gradients through 79 batch-statistic BN layers on a small map are ill-conditioned: the oracle's own FP32
+    gradients differ from its FP64 ones by up to 1e-1 on individual tensors (measured: feats.conv1.weight 6.6e-3,
+    feats.layer3.3.conv1.weight 1.1e-1), and three conv biases that sit in front of a BN have an exactly-zero true
+    gradient.  Each tensor is therefore bounded by the oracle's own FP32 (resp. BF16-autocast) deviation from FP64,
+    with errors measured against max(|ref|, 1e-4 * largest gradient entry of the whole net)."""
     from heatnet_pub_b200 import pspnet
     sd = O.recipe_fill(O.pspnet_state_dict(True, 4), seed=0)
     rgb, ir = O.synthetic_inputs(2, 64, 96)
     label = torch.randint(0, 13, (2, 64, 96), generator=torch.Generator().manual_seed(5))
 
     def loss_of(logits, taps):
-        return F.cross_entropy(logits, label.to(logits.device)) + sum((t.float() ** 2).mean() for t in taps[1:])
+        return F.cross_entropy(logits.float(), label.to(logits.device)) + sum((t.float() ** 2).mean() for t in taps[1:])
 
-    ref_loss, ref_g = _oracle_grads({k: v.clone() for k, v in sd.items()},
-                                    lambda s: loss_of(*O.pspnet_forward(s, rgb, ir, late_fusion=True, training=True, dropout=False)[:2]))
+    def oracle(dtype, autocast=False):
+        s = {k: (v.clone().to(dtype) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+        with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast):
+            return _oracle_grads(s, lambda q: loss_of(*O.pspnet_forward(q, rgb.to(dtype), ir.to(dtype), late_fusion=True, training=True,
+                                                                        dropout=False)[:2]))
+
+    ref_loss, ref_g = oracle(torch.float64)
+    _, floor_g = oracle(torch.float32, autocast=(precision == "bf16"))
+    gmax = max(g.abs().max().item() for g in ref_g.values())
+
+    def err(a, b):
+        return ((a.double() - b.double()).abs().max() / max(b.abs().max().item(), 1e-4 * gmax)).item()
+
     net = pspnet.PSPNet(sizes=(1, 2, 3, 6), psp_size=2048, deep_features_size=1024, backend='resnet50', in_channels=4,
                         pretrained=False, late_fusion=True)
     net.load_state_dict(sd)
@@ -57,25 +80,21 @@ def test_pspnet_backward_matches_oracle_autograd(precision, gtol):
     assert set(k for k, g in got.items() if g is not None) == set(ref_g)
     if precision == "fp32":
         assert abs(loss.item() - ref_loss) < 1e-4 * abs(ref_loss)
-    worst = 0.0
+    worst, worst_floor, bad = 0.0, 0.0, []
     for k, g in ref_g.items():
-        e = rel(got[k].cpu(), g)
-        worst = max(worst, e)
-        if gtol is not None:
-            assert e < gtol, (k, e)
-    print(f"[{precision}] loss {loss.item():.6f} (oracle {ref_loss:.6f}); worst per-tensor gradient rel err {worst:.3e}")
-    if gtol is None:
-        # BF16 + batch-stat BN: bounded by the oracle's own BF16-autocast gradient noise
-        sd2 = {k: v.clone() for k, v in sd.items()}
-        with torch.autocast("cpu", dtype=torch.bfloat16):
-            _, bf_g = _oracle_grads(sd2, lambda s: loss_of(*O.pspnet_forward(s, rgb, ir, late_fusion=True, training=True, dropout=False)[:2]))
-        floor = max(rel(bf_g[k].float(), g) for k, g in ref_g.items())
-        print(f"[bf16] oracle BF16-autocast worst gradient rel err {floor:.3e}")
-        assert worst < max(1.5 * floor, 0.1)
+        e, f = err(got[k].cpu(), g), err(floor_g[k].float(), g)
+        worst, worst_floor = max(worst, e), max(worst_floor, f)
+        if e > max(3.0 * f, 2e-3 if precision == "fp32" else 5e-2):
+            bad.append((k, e, f))
+    print(f"[{precision}] loss {loss.item():.6f} (FP64 oracle {ref_loss:.6f}); worst gradient err {worst:.3e}; "
+          f"oracle {'BF16-autocast' if precision == 'bf16' else 'FP32'} worst {worst_floor:.3e}")
+    assert not bad, bad[:5]
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 5e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 3e-2)])
 def test_critic_backward(precision, tol):
+    """FCDiscriminator forward + backward (MSE vs 1): FP32 max-abs relative 1e-3; BF16 relative L2 3e-2 per tensor."""
+    metric = rel if precision == "fp32" else rel_l2
     from heatnet_pub_b200 import discriminator_model
     sd = O.recipe_fill(O.critic_state_dict(64), seed=2)
     x = torch.randn(2, 64, 64, 96, generator=torch.Generator().manual_seed(1))
@@ -93,8 +112,8 @@ def test_critic_backward(precision, tol):
     F.mse_loss(y, torch.ones_like(y)).backward()
     assert rel(y.detach().cpu(), yr.detach()) < (1e-4 if precision == "fp32" else 2e-2)
     for k, p in crit.named_parameters():
-        assert rel(p.grad.cpu(), ref_sd[k].grad) < tol, k
-    assert rel(xg.grad.cpu(), xr.grad) < tol
+        assert metric(p.grad.cpu(), ref_sd[k].grad) < tol, k
+    assert metric(xg.grad.cpu(), xr.grad) < tol
     # frozen critic (train_seg phase): no parameter gradients, input gradient still flows
     for p in crit.parameters():
         p.requires_grad = False
@@ -102,7 +121,7 @@ def test_critic_backward(precision, tol):
     xg2 = x.cuda().requires_grad_(True)
     F.mse_loss(crit(xg2), torch.ones_like(y)).backward()
     assert all(p.grad is None for p in crit.parameters())
-    assert rel(xg2.grad.cpu(), xr.grad) < tol
+    assert metric(xg2.grad.cpu(), xr.grad) < tol
 
 
 @pytest.mark.timeout(900)
@@ -147,4 +166,6 @@ def test_conf_segnet_step_matches_reference_golden_fp32(golden_dir):
         gn = np.array([dict(m.named_parameters())[k].grad.double().norm().item() for k in names])
         err = np.abs(gn - g[phase + "/grad_norm"]) / np.maximum(g[phase + "/grad_norm"], 1e-12)
         print(f"{phase}: {len(names)} gradient tensors, worst grad-norm rel err {err.max():.3e}")
-        np.testing.assert_allclose(gn, g[phase + "/grad_norm"], rtol=3e-3, atol=1e-7)
+        # conv biases in front of a BN have an exactly-zero true gradient (both sides hold rounding noise there):
+        # absolute slack of 1e-5 of the largest gradient norm
+        np.testing.assert_allclose(gn, g[phase + "/grad_norm"], rtol=3e-3, atol=1e-5 * g[phase + "/grad_norm"].max())
