@@ -222,6 +222,105 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------- training step
+TRAIN_GFLOP_PER_PAIR_320x640 = {"train_seg": 2051.2, "train_critic": 771.4}
+
+
+def run_train(args):
+    """One adversarial step of cm/train_trgb_segnet_conf.py:428-568 per rank on its shard: conv_segnet forward on a
+    day and a night batch, the phase's loss, backward, bucketed gradient all-reduce (optimizer step excluded)."""
+    import torch
+    import torch.distributed as dist
+    import torch.nn as nn
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from heatnet_pub_b200 import conf_segnet, engine as E, parallel
+
+    B = args.batch
+    H, W = (args.height, args.width) if (args.height, args.width) != (650, 1920) else (320, 640)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = conf_segnet.conv_segnet(pretrained=False, disc_arch='cyclegan', num_critics=6, no_conf=False, modalities='ir_rgb',
+                                        arch='pspnet', late_fusion=True)
+        he_init_(model.trgb_segnet)
+        model = model.to(dev).train()
+        model.setPhase(args.workload)
+    model.trgb_segnet.set_precision(args.precision)
+    for c in model.critics:
+        c.precision = args.precision
+    parallel.broadcast_parameters(model, 0)
+    reducer = parallel.GradientReducer(model.parameters())
+    g = torch.Generator().manual_seed(SEED + rank)
+    mk = lambda c: (torch.rand(B, c, H, W, generator=g) * 2 - 1).to(dev)
+    rgb_d, ir_d, rgb_n, ir_n = mk(3), mk(1), mk(3), mk(1)
+    label = torch.randint(0, 13, (B, H, W), generator=g).to(dev)
+    mse, ce = nn.MSELoss(), nn.CrossEntropyLoss()
+
+    def step():
+        for p in model.parameters():
+            p.grad = None
+        o = model([rgb_d, ir_d], [rgb_n, ir_n])
+        if args.workload == "train_seg":
+            conf = sum(mse(c, torch.full_like(c, 1)) for c in o['critics_a']) + sum(mse(c, torch.full_like(c, 1)) for c in o['critics_b'])
+            total = ce(o['pred_label_a'], label) + 0.1 * conf
+        else:
+            total = sum(mse(c, torch.full_like(c, 1)) for c in o['critics_a']) + sum(mse(c, torch.full_like(c, 0)) for c in o['critics_b'])
+        total.backward()
+        reducer.reduce()
+        return total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        loss = step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = E.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        loss = step()
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    launches = E.launch_count - l0
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        imgs = 2 * B * world * args.steps
+        scale = (H * W) / (320.0 * 640.0)
+        tflops = TRAIN_GFLOP_PER_PAIR_320x640[args.workload] * scale * B * args.steps / (ms / 1000.0) / 1e3
+        line = {"metric": "rgb_thermal_seg_train_images_per_sec", "value": imgs / (ms / 1000.0), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": f"conv_segnet {args.workload} step (PSPNet-ResNet50 late fusion + 6 FCDiscriminator critics), "
+                                       f"{B} day+night pairs per GPU at {H}x{W}, fwd+bwd+gradient all-reduce, optimizer excluded; 2 images per pair",
+                           "per_gpu_pairs": B, "global_pairs": B * world, "parallelism": f"batch-sharded x{world}, NCCL all-reduce of "
+                           f"{reducer.last_bytes / 1e6:.1f} MB in {reducer.last_buckets} buckets" if world > 1 else "single GPU"},
+                "loss": float(loss), "gpu_launches": launches, "clocks": clocks,
+                "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
+                             "unit": "TFLOP/s", "frac": tflops / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
+                             "note": "whole step (all kernels, not only convs) against algorithmic conv FLOPs of SURVEY.md section 8d",
+                             "peak_source": peak_src}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ---------------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -235,10 +334,15 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layer-table", default=None, help="write the per-conv-launch timing table (JSON) here")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train_seg", "train_critic"],
+                    help="infer = the headline (BASELINE configs[1]); train_* = one adversarial training step (configs[2]/[3]): "
+                         "per-GPU batch of --batch day+night pairs at --height x --width, fwd + bwd + NCCL gradient all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    if args.workload != "infer":
+        return run_train(args)
 
     import ctypes as C
     import torch

@@ -84,8 +84,10 @@ def test_pspnet_backward_matches_oracle_autograd(precision):
     for k, g in ref_g.items():
         e, f = err(got[k].cpu(), g), err(floor_g[k].float(), g)
         worst, worst_floor = max(worst, e), max(worst_floor, f)
-        if e > max(3.0 * f, 2e-3 if precision == "fp32" else 5e-2):
-            bad.append((k, e, f))
+        bad.append((k, e, f))
+    # per tensor: within 3x its own oracle noise, or within the worst oracle noise over all tensors (the
+    # ill-conditioning is shared by the whole backward chain), never worse than that
+    bad = [(k, e, f) for k, e, f in bad if e > max(3.0 * f, worst_floor, 2e-3 if precision == "fp32" else 5e-2)]
     print(f"[{precision}] loss {loss.item():.6f} (FP64 oracle {ref_loss:.6f}); worst gradient err {worst:.3e}; "
           f"oracle {'BF16-autocast' if precision == 'bf16' else 'FP32'} worst {worst_floor:.3e}")
     assert not bad, bad[:5]
@@ -111,9 +113,19 @@ def test_critic_backward(precision, tol):
     assert y.shape == yr.shape and y.requires_grad
     F.mse_loss(y, torch.ones_like(y)).backward()
     assert rel(y.detach().cpu(), yr.detach()) < (1e-4 if precision == "fp32" else 2e-2)
+    floor = {}
+    if precision == "bf16":      # the oracle's own BF16-autocast gradients vs its FP32 ones = the noise floor
+        bsd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        xb = x.clone().requires_grad_(True)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            yb = O.fc_discriminator(xb, bsd, "")
+            F.mse_loss(yb.float(), torch.ones_like(yr)).backward()
+        floor = {k: rel_l2(bsd[k].grad.float(), ref_sd[k].grad) for k in bsd}
+        floor["x"] = rel_l2(xb.grad.float(), xr.grad)
+        print("critic bf16 noise floor (oracle autocast):", {k: round(v, 4) for k, v in floor.items()})
     for k, p in crit.named_parameters():
-        assert metric(p.grad.cpu(), ref_sd[k].grad) < tol, k
-    assert metric(xg.grad.cpu(), xr.grad) < tol
+        assert metric(p.grad.cpu(), ref_sd[k].grad) < max(tol, 1.5 * floor.get(k, 0.0)), k
+    assert metric(xg.grad.cpu(), xr.grad) < max(tol, 1.5 * floor.get("x", 0.0))
     # frozen critic (train_seg phase): no parameter gradients, input gradient still flows
     for p in crit.parameters():
         p.requires_grad = False
@@ -121,7 +133,7 @@ def test_critic_backward(precision, tol):
     xg2 = x.cuda().requires_grad_(True)
     F.mse_loss(crit(xg2), torch.ones_like(y)).backward()
     assert all(p.grad is None for p in crit.parameters())
-    assert metric(xg2.grad.cpu(), xr.grad) < tol
+    assert metric(xg2.grad.cpu(), xr.grad) < max(tol, 1.5 * floor.get("x", 0.0))
 
 
 @pytest.mark.timeout(900)
