@@ -2,6 +2,8 @@
 // statistics / apply, max-pool, pyramid adaptive average pool, bilinear resize.  Every kernel moves
 // 8 channels (16 B of BF16 / 32 B of FP32) per thread so that a warp touches contiguous 512 B / 1 KB
 // segments; grids are sized in whole waves of the SM count with grid-stride loops.
+#include <type_traits>
+
 #include "hn_common.cuh"
 
 namespace hn {
@@ -448,6 +450,97 @@ __global__ void __launch_bounds__(256) bilinear_vec_kernel(const TI *__restrict_
     }
 }
 
+// exact 2x upsample (the three PSPUpsample stages): one thread produces the 2x2 output block of one input pixel from its
+// 3x3 neighbourhood (9 loads for 4 outputs instead of 16) with the same FP32 expression as the generic kernel, so
+// the results are bit-identical to it.  grid.x = input rows (n*H + y), grid.y = chunks of the row's W * C/8 items.
+template <typename T>
+__global__ void __launch_bounds__(256) bilinear_up2_kernel(const T *__restrict__ x, int ldx, T *__restrict__ y, int ldy, int N, int H, int W,
+                                                           int C)
+{
+    const int ncv = C / 8;
+    const int row = blockIdx.x;
+    const int n = row / H, yi = row - n * H;
+    const int ym = yi > 0 ? yi - 1 : 0, yp = yi < H - 1 ? yi + 1 : H - 1;
+    const T *rm = x + ((int64_t)n * H + ym) * W * ldx;
+    const T *r0 = x + ((int64_t)n * H + yi) * W * ldx;
+    const T *rp = x + ((int64_t)n * H + yp) * W * ldx;
+    const int Wo = 2 * W;
+    T *o0 = y + ((int64_t)n * 2 * H + 2 * yi) * Wo * ldy;
+    T *o1 = o0 + (int64_t)Wo * ldy;
+    // output row 2y   : src = y - 0.25 -> rows (y-1, y), ly = 0.75 (clamped to row 0: ly = 0)
+    // output row 2y+1 : src = y + 0.25 -> rows (y, y+1), ly = 0.25
+    const float ly0 = yi > 0 ? 0.75f : 0.f, ly1 = 0.25f;
+    const int items = W * ncv;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < items; i += gridDim.y * blockDim.x) {
+        const int xi = i / ncv, c = (i - xi * ncv) * 8;
+        const int xm = xi > 0 ? xi - 1 : 0, xp = xi < W - 1 ? xi + 1 : W - 1;
+        const float lx0 = xi > 0 ? 0.75f : 0.f, lx1 = 0.25f;
+        float a[3][3][8];
+        Vec8<T>::load(rm + (int64_t)xm * ldx + c, a[0][0]); Vec8<T>::load(rm + (int64_t)xi * ldx + c, a[0][1]); Vec8<T>::load(rm + (int64_t)xp * ldx + c, a[0][2]);
+        Vec8<T>::load(r0 + (int64_t)xm * ldx + c, a[1][0]); Vec8<T>::load(r0 + (int64_t)xi * ldx + c, a[1][1]); Vec8<T>::load(r0 + (int64_t)xp * ldx + c, a[1][2]);
+        Vec8<T>::load(rp + (int64_t)xm * ldx + c, a[2][0]); Vec8<T>::load(rp + (int64_t)xi * ldx + c, a[2][1]); Vec8<T>::load(rp + (int64_t)xp * ldx + c, a[2][2]);
+        float o[8];
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            // generic kernel: y0 = floor(src), y1 = y0 + 1 (clamped); for dy = 0 and yi == 0 both are row 0
+            const int ra = dy == 0 ? (yi > 0 ? 0 : 1) : 1, rb = dy == 0 ? 1 : 2;
+            const float ly = dy == 0 ? ly0 : ly1, hy = 1.f - ly;
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const int ca = dx == 0 ? (xi > 0 ? 0 : 1) : 1, cb = dx == 0 ? 1 : 2;
+                const float lx = dx == 0 ? lx0 : lx1, hx = 1.f - lx;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    o[j] = hy * (hx * a[ra][ca][j] + lx * a[ra][cb][j]) + ly * (hx * a[rb][ca][j] + lx * a[rb][cb][j]);
+                Vec8<T>::store((dy == 0 ? o0 : o1) + (int64_t)(2 * xi + dx) * ldy + c, o);
+            }
+        }
+    }
+}
+
+// y = sum_i upsample(x_i): up to 4 low-resolution sources accumulated in FP32 and written once (the PSP priors after
+// the bottleneck projection).  Same index rule as bilinear_vec_kernel.
+struct BilinearSrcs {
+    const void *ptr[4];
+    int h[4], w[4], ld[4];
+    int n;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) bilinear_sum_kernel(const __grid_constant__ BilinearSrcs src, T *__restrict__ y, int ldy, int N, int Ho,
+                                                           int Wo, int C)
+{
+    const int ncv = C / 8;
+    const int row = blockIdx.x;
+    const int n = row / Ho, ho = row - n * Ho;
+    T *yrow = y + (int64_t)row * Wo * ldy;
+    const int items = Wo * ncv;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < items; i += gridDim.y * blockDim.x) {
+        const int wo = i / ncv, c = (i - wo * ncv) * 8;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            if (s >= src.n) break;
+            const int H = src.h[s], W = src.w[s], ld = src.ld[s];
+            int y0, y1, x0, x1;
+            float ly, lx;
+            bilinear_src(ho, (float)H / (float)Ho, H, y0, y1, ly);
+            bilinear_src(wo, (float)W / (float)Wo, W, x0, x1, lx);
+            const T *b = (const T *)src.ptr[s] + (int64_t)n * H * W * ld + c;
+            float a00[8], a01[8], a10[8], a11[8];
+            Vec8<T>::load(b + ((int64_t)y0 * W + x0) * ld, a00);
+            Vec8<T>::load(b + ((int64_t)y0 * W + x1) * ld, a01);
+            Vec8<T>::load(b + ((int64_t)y1 * W + x0) * ld, a10);
+            Vec8<T>::load(b + ((int64_t)y1 * W + x1) * ld, a11);
+            const float hy = 1.f - ly, hx = 1.f - lx;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += hy * (hx * a00[j] + lx * a01[j]) + ly * (hx * a10[j] + lx * a11[j]);
+        }
+        Vec8<T>::store(yrow + (int64_t)wo * ldy + c, acc);
+    }
+}
+
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) bilinear_scalar_kernel(const TI *__restrict__ x, int ldx, TO *__restrict__ y, int ldy, int N,
                                                               int H, int W, int Ho, int Wo, int C, float sh, float sw)
@@ -475,6 +568,14 @@ template <typename TI, typename TO>
 static int launch_bilinear(const hn_tensor *x, const hn_tensor *y, cudaStream_t st)
 {
     const float sh = (float)x->h / (float)y->h, sw = (float)x->w / (float)y->w;
+    if constexpr (std::is_same<TI, TO>::value) {
+        if (vec8_ok(x) && vec8_ok(y) && y->h == 2 * x->h && y->w == 2 * x->w) {
+            bilinear_up2_kernel<TI><<<row_grid((int64_t)x->n * x->h, (int64_t)x->w * (x->c / 8)), 256, 0, st>>>(
+                (const TI *)x->ptr, x->ld, (TO *)y->ptr, y->ld, x->n, x->h, x->w, x->c);
+            HN_LAUNCH_CHECK();
+            return HN_OK;
+        }
+    }
     if (vec8_ok(x) && vec8_ok(y)) {
         bilinear_vec_kernel<TI, TO><<<row_grid((int64_t)y->n * y->h, (int64_t)y->w * (y->c / 8)), 256, 0, st>>>((const TI *)x->ptr, x->ld, (TO *)y->ptr, y->ld, x->n, x->h,
                                                                          x->w, y->h, y->w, x->c, sh, sw);
@@ -727,4 +828,24 @@ extern "C" int hn_bilinear_fwd(const hn_tensor *x, const hn_tensor *y, void *str
     if (x->dtype == HN_F32 && y->dtype == HN_F32) return launch_bilinear<float, float>(x, y, st);
     if (x->dtype == HN_BF16 && y->dtype == HN_F32) return launch_bilinear<__nv_bfloat16, float>(x, y, st);
     return launch_bilinear<float, __nv_bfloat16>(x, y, st);
+}
+
+extern "C" int hn_bilinear_sum_fwd(const hn_tensor *xs, int32_t nsrc, const hn_tensor *y, void *stream)
+{
+    HN_CHECK_ARG(xs && y && y->ptr && nsrc >= 1 && nsrc <= 4, "hn_bilinear_sum_fwd: 1..4 sources");
+    HN_CHECK_ARG(vec8_ok(y), "hn_bilinear_sum_fwd: output view must be 8-channel aligned");
+    BilinearSrcs src{};
+    src.n = nsrc;
+    for (int i = 0; i < nsrc; ++i) {
+        HN_CHECK_ARG(xs[i].ptr && xs[i].dtype == y->dtype && xs[i].n == y->n && xs[i].c == y->c && vec8_ok(&xs[i]) && xs[i].h > 0 && xs[i].w > 0,
+                     "hn_bilinear_sum_fwd: source %d does not match the output", i);
+        src.ptr[i] = xs[i].ptr; src.h[i] = xs[i].h; src.w[i] = xs[i].w; src.ld[i] = xs[i].ld;
+    }
+    if ((int64_t)y->n * y->h * y->w == 0) return HN_OK;
+    dim3 grid = row_grid((int64_t)y->n * y->h, (int64_t)y->w * (y->c / 8));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (y->dtype == HN_BF16) bilinear_sum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, (__nv_bfloat16 *)y->ptr, y->ld, y->n, y->h, y->w, y->c);
+    else bilinear_sum_kernel<float><<<grid, 256, 0, st>>>(src, (float *)y->ptr, y->ld, y->n, y->h, y->w, y->c);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
 }

@@ -294,6 +294,26 @@ def packed_weight(conv: torch.nn.Conv2d, dtype: torch.dtype) -> torch.Tensor:
     return dst
 
 
+def packed_weight_slice(conv: torch.nn.Conv2d, c0: int, c1: int, dtype: torch.dtype) -> torch.Tensor:
+    """Pack of the input-channel slice [c0, c1) of a conv weight (the per-prior blocks of the PSP bottleneck)."""
+    lib = _lib.load()
+    cache = conv.__dict__.setdefault("_hn_wcache", {})
+    key = ("slice", c0, c1, dtype, conv.weight.device)
+    ver = _versions(conv.weight)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    w = conv.weight.detach()[:, c0:c1].float().contiguous()
+    cout, cin, r, s = w.shape
+    hdt = _HN_DTYPE[dtype]
+    cout_pad, kpad = lib.hn_conv_cout_pad(cout, hdt), lib.hn_conv_kpad(cin, r, s)
+    dst = torch.empty((cout_pad, kpad), dtype=dtype, device=w.device)
+    _lib.check(lib.hn_pack_weight(w.data_ptr(), dst.data_ptr(), hdt, cout, cin, r, s, cout_pad, kpad, _stream()))
+    _count()
+    cache[key] = (ver, dst)
+    return dst
+
+
 def folded_affine(conv: torch.nn.Conv2d, bn: Optional[torch.nn.BatchNorm2d]):
     """(scale, shift) FP32 vectors for the conv epilogue: BatchNorm2d(eval) and the conv bias folded;
     (None, None) when the conv has neither."""
@@ -773,3 +793,13 @@ def pyramid_pool_bwd(dpool: torch.Tensor, sizes: Sequence[int], dx: Act, add: bo
     arr = (C.c_int32 * len(sizes))(*sizes)
     _lib.check(_lib.load().hn_pyramid_pool_bwd(dpool.data_ptr(), arr, len(sizes), C.byref(dx.hn()), int(add), _stream()))
     _count()
+
+
+def bilinear_sum(xs: Sequence[Act], h: int, w: int) -> Act:
+    """sum_i upsample(xs[i]) -> [N, h, w, C] in one pass (FP32 accumulation, one write)."""
+    x0 = xs[0]
+    out = new_act(x0.n, h, w, x0.c, x0.dtype, x0.buf.device)
+    arr = (HnTensor * len(xs))(*[x.hn() for x in xs])
+    _lib.check(_lib.load().hn_bilinear_sum_fwd(arr, len(xs), C.byref(out.hn()), _stream()))
+    _count()
+    return out

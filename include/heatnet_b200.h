@@ -107,6 +107,9 @@ int hn_pyramid_pool_fwd(const hn_tensor *x, const int32_t *sizes, int32_t nsizes
 /* F.upsample(mode='bilinear') == interpolate(align_corners=False): cm/models/pspnet.py:23,39,
  * cm/discriminator_model.py:47.  x and y may differ in dtype. */
 int hn_bilinear_fwd(const hn_tensor *x, const hn_tensor *y, void *stream);
+/* y = sum_i upsample(xs[i]) for up to 4 low-resolution sources, FP32 accumulation, one write: the PSP priors after the
+ * bottleneck projection (a 1x1 conv commutes with bilinear upsampling -- cm/models/pspnet.py:23-25 restructured) */
+int hn_bilinear_sum_fwd(const hn_tensor *xs, int32_t nsrc, const hn_tensor *y, void *stream);
 /* per-channel affine + residual + activation over an NHWC view (BatchNorm2d apply in train mode; with
  * per_image=1 and shift=NULL the nn.Dropout2d channel mask of cm/models/pspnet.py:64-73):
  * y = act(x*scale[c] + shift[c] + residual) */
