@@ -110,5 +110,8 @@ int conv2d_fwd_f32(const hn_tensor *x, const void *w, const hn_conv *cv, const h
 int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn_epilogue *ep, const hn_tensor *y,
                   void *ws, int64_t ws_bytes, cudaStream_t st);
 int64_t conv2d_tc_workspace(const hn_tensor *x, const hn_conv *cv);
+bool conv_halo_ok(const hn_tensor *x, const hn_conv *cv, const hn_tensor *y, bool upsample);
+int conv2d_fwd_halo(const hn_tensor *x, const void *w, const hn_conv *cv, const hn_epilogue *ep, const hn_tensor *y, bool upsample,
+                    cudaStream_t st);
 
 }  // namespace hn

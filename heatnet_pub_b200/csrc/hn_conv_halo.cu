@@ -1,0 +1,393 @@
+// 3x3 stride-1 convolution from ONE shared-memory halo patch per k-block, optionally fused with the 2x bilinear
+// upsample that precedes it in PSPUpsample (cm/models/pspnet.py:37-40).
+//
+// The generic implicit-GEMM kernel (hn_conv_tc.cu) fetches the A tile of every filter tap separately: 9 TMA boxes per
+// 64-channel k-block, 9x the L2->SM traffic of the input patch.  For layers with few output channels (Cout = 64: 64 MACs
+// per fetched element) that traffic, not the tensor pipe, is the bound.  Here an M tile is a 16x8 patch of output
+// pixels and ONE (16+2d)x(8+2d)-pixel halo patch of the input is staged per k-block; the A operand of tap (r,s) is the
+// sub-window that starts (r*d) patch rows and (s*d) pixels into it.  That works because the 128B swizzle of both TMA and
+// tcgen05 is a pure function of the shared-memory ADDRESS bits (chunk ^= (addr >> 7) & 7): a K-major SWIZZLE_128B
+// descriptor may start at any 128-byte row of the patch, and its stride-byte-offset (distance between 8-row groups =
+// one 8-pixel tile row) is simply the patch row pitch (8+2d)*128 B.  (Verified on B200 by scripts/probe_umma_offset.cu.)
+// Weights stream through their own ring, one [BLOCK_N][64] tile per (k-block, tap); when the whole filter fits in the
+// ring (Cin = 64, Cout = 64: 72 KB) it is loaded once per CTA and stays resident across all tiles.
+//
+// UPSAMPLE variant: the halo patch is not fetched but COMPUTED by producer warps from the low-resolution input with the
+// exact ATen bilinear rule (align_corners = False, FP32 weights), written with the same address-based swizzle.  The 2x
+// upsampled activation (the three largest tensors of the network) never exists in HBM.
+#include <stdlib.h>
+#include <string.h>
+
+#include "hn_common.cuh"
+#include "hn_tc_epilogue.cuh"
+#include "hn_tc_ptx.cuh"
+
+namespace hn {
+
+constexpr int HALO_THREADS = 384;
+constexpr int HALO_TH = 16, HALO_TW = 8;
+constexpr int HALO_NA = 2;        // A patch slots
+constexpr int HALO_NB_MAX = 12;   // B ring stages (upper bound)
+
+struct HaloParams {
+    TcParams t;
+    int PW, PH;              // patch extent in pixels
+    int a_slot_bytes;        // patch bytes rounded up to 1024
+    int nb;                  // B ring depth
+    int b_resident;          // ring holds every (k-block, tap) tile: load once per CTA
+    // upsample variant: low-resolution input [N][Hl][Wl][C]
+    const __nv_bfloat16 *xlow;
+    int ldx, Hl, Wl;
+};
+
+__device__ __forceinline__ void bilinear_src_h(int dst, int in_size, int &i0, int &i1, float &l1)
+{
+    float src = 0.5f * ((float)dst + 0.5f) - 0.5f;     // scale = in/out = 0.5 exactly
+    if (src < 0.f) src = 0.f;
+    i0 = (int)src;
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = src - (float)i0;
+}
+
+template <int BLOCK_N, bool UPSAMPLE>
+__global__ void __launch_bounds__(HALO_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_r, const HaloParams hp)
+{
+    constexpr int B_STAGE_BYTES = BLOCK_N * 128;
+    constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    constexpr int TMEM_COLS = 2 * ACC_COLS;
+    constexpr uint32_t IDESC = make_idesc_bf16(128, BLOCK_N);
+    // A-producer warps of the UPSAMPLE variant: warps 2,3 always; warps 8-11 too when the epilogue only needs 4 warps
+    constexpr int NPROD = BLOCK_N <= 64 ? 6 : 2;
+    const TcParams &p = hp.t;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *a_ring = smem;
+    uint8_t *b_ring = a_ring + HALO_NA * hp.a_slot_bytes;
+    uint8_t *epi_stage = b_ring + hp.nb * B_STAGE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES);
+    uint64_t *a_full = bars, *a_empty = bars + HALO_NA, *b_full = bars + 2 * HALO_NA, *b_empty = b_full + HALO_NB_MAX;
+    uint64_t *tfull_bar = b_empty + HALO_NB_MAX, *tempty_bar = tfull_bar + 2, *res_bar = tempty_bar + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_bar + NUM_EPI_WARPS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m_tiles = p.n_img * p.tiles_h * p.tiles_w;
+    const int num_tiles = num_m_tiles * p.n_tiles;
+    const int num_kb = p.cblocks;
+    const int d = p.dil;
+
+    if (warp == 0 && lane == 0) {
+        if (!UPSAMPLE) prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_b);
+        if (p.tma_out) prefetch_tmap(&tmap_y);
+        if (p.tma_res) prefetch_tmap(&tmap_r);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < HALO_NA; ++i) {
+            mbar_init(smem_u32(a_full + i), UPSAMPLE ? NPROD : 1);
+            mbar_init(smem_u32(a_empty + i), 1);
+        }
+        for (int i = 0; i < HALO_NB_MAX; ++i) {
+            mbar_init(smem_u32(b_full + i), 1);
+            mbar_init(smem_u32(b_empty + i), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(tfull_bar + i), 1);
+            mbar_init(smem_u32(tempty_bar + i), BLOCK_N >= 128 ? 8 : 4);
+        }
+        for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(smem_u32(res_bar + i), 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const bool is_prod = UPSAMPLE && (warp == 2 || warp == 3 || (NPROD == 6 && warp >= 8));
+    const bool is_epi = warp >= EPI_WARP0 && !(UPSAMPLE && NPROD == 6 && warp >= 8);
+
+    if (warp == 0) {
+        // ===================== TMA producer: weight tiles (and the halo patches when they are fetched) =====================
+        if (lane == 0) {
+            int aslot = 0, bst = 0;
+            uint32_t aphase = 0, bphase = 0;
+            bool first = true;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    if (!UPSAMPLE) {
+                        mbar_wait(smem_u32(a_empty + aslot), aphase ^ 1);
+                        const uint32_t fb = smem_u32(a_full + aslot);
+                        mbar_expect_tx(fb, hp.PW * hp.PH * 128);
+                        tma_load_4d(smem_u32(a_ring + aslot * hp.a_slot_bytes), &tmap_a, fb, kb * 64, tw * HALO_TW - d, th * HALO_TH - d, img);
+                        if (++aslot == HALO_NA) { aslot = 0; aphase ^= 1; }
+                    }
+                    if (hp.b_resident && !first) continue;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (!hp.b_resident) mbar_wait(smem_u32(b_empty + bst), bphase ^ 1);
+                        const uint32_t fb = smem_u32(b_full + bst);
+                        mbar_expect_tx(fb, B_STAGE_BYTES);
+                        tma_load_2d(smem_u32(b_ring + bst * B_STAGE_BYTES), &tmap_b, fb, (tap * num_kb + kb) * 64, nt * BLOCK_N);
+                        if (++bst == hp.nb) { bst = 0; bphase ^= 1; }
+                    }
+                }
+                first = false;
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int aslot = 0, bst = 0, acc = 0;
+            uint32_t aphase = 0, bphase = 0, acc_phase = 0;
+            bool first = true;
+            const uint32_t sbo = (uint32_t)(hp.PW * 128) >> 4;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+                if (hp.b_resident) bst = 0;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(smem_u32(a_full + aslot), aphase);
+                    tcgen05_fence_after();
+                    const uint32_t a_base = smem_u32(a_ring + aslot * hp.a_slot_bytes);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int r = tap / 3, s = tap - r * 3;
+                        if (!hp.b_resident || first) {
+                            mbar_wait(smem_u32(b_full + bst), bphase);
+                            tcgen05_fence_after();
+                        }
+                        // sub-window of the patch: starts (r*d) patch rows and (s*d) pixels in; 8-row groups are one patch row apart
+                        const uint32_t a_addr = a_base + (uint32_t)((r * d) * hp.PW + s * d) * 128;
+                        uint64_t adesc = 0;
+                        adesc |= (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+                        adesc |= (uint64_t)1 << 16;
+                        adesc |= (uint64_t)(sbo & 0x3FFF) << 32;
+                        adesc |= (uint64_t)1 << 46;
+                        adesc |= (uint64_t)2 << 61;
+                        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(b_ring + bst * B_STAGE_BYTES));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | tap | k) != 0);
+                        if (!hp.b_resident) umma_commit(smem_u32(b_empty + bst));
+                        if (++bst == hp.nb) { bst = 0; bphase ^= 1; }
+                    }
+                    umma_commit(smem_u32(a_empty + aslot));
+                    if (++aslot == HALO_NA) { aslot = 0; aphase ^= 1; }
+                }
+                umma_commit(smem_u32(tfull_bar + acc));
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+                first = false;
+            }
+        }
+    } else if (is_prod) {
+        // ===================== halo patch producers (UPSAMPLE): bilinear 2x of the low-res input on the fly =====================
+        const int pi = warp == 2 ? 0 : (warp == 3 ? 1 : warp - 8 + 2);
+        int aslot = 0;
+        uint32_t aphase = 0;
+        const int Hu = 2 * hp.Hl, Wu = 2 * hp.Wl;
+        const int ntask = hp.PH * hp.PW * 8;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int mt = tile / p.n_tiles;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
+            const int uy0 = th * HALO_TH - 1, ux0 = tw * HALO_TW - 1;
+            const __nv_bfloat16 *ximg = hp.xlow + (int64_t)img * hp.Hl * hp.Wl * hp.ldx;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(smem_u32(a_empty + aslot), aphase ^ 1);
+                const uint32_t a_base = smem_u32(a_ring + aslot * hp.a_slot_bytes);
+                for (int t = pi * 32 + lane; t < ntask; t += NPROD * 32) {
+                    const int pp = t >> 3, j = t & 7;
+                    const int py = pp / hp.PW, px = pp - py * hp.PW;
+                    const int uy = uy0 + py, ux = ux0 + px;
+                    uint4 outv = make_uint4(0, 0, 0, 0);
+                    if (uy >= 0 && uy < Hu && ux >= 0 && ux < Wu) {
+                        int y0, y1, x0, x1;
+                        float ly, lx;
+                        bilinear_src_h(uy, hp.Hl, y0, y1, ly);
+                        bilinear_src_h(ux, hp.Wl, x0, x1, lx);
+                        const __nv_bfloat16 *b = ximg + kb * 64 + j * 8;
+                        float a00[8], a01[8], a10[8], a11[8], o[8];
+                        Vec8<__nv_bfloat16>::load(b + ((int64_t)y0 * hp.Wl + x0) * hp.ldx, a00);
+                        Vec8<__nv_bfloat16>::load(b + ((int64_t)y0 * hp.Wl + x1) * hp.ldx, a01);
+                        Vec8<__nv_bfloat16>::load(b + ((int64_t)y1 * hp.Wl + x0) * hp.ldx, a10);
+                        Vec8<__nv_bfloat16>::load(b + ((int64_t)y1 * hp.Wl + x1) * hp.ldx, a11);
+                        const float hy = 1.f - ly, hx = 1.f - lx;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) o[q] = hy * (hx * a00[q] + lx * a01[q]) + ly * (hx * a10[q] + lx * a11[q]);
+                        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&outv);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(o[2 * q], o[2 * q + 1]);
+                    }
+                    const uint32_t rowaddr = a_base + pp * 128;
+                    sts128(rowaddr + ((j ^ ((rowaddr >> 7) & 7)) << 4), outv);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(a_full + aslot));
+                if (++aslot == HALO_NA) { aslot = 0; aphase ^= 1; }
+            }
+        }
+    } else if (is_epi) {
+        conv_epilogue<BLOCK_N>(p, &tmap_y, &tmap_r, tmem_base, tfull_bar, tempty_bar, res_bar, epi_stage, num_tiles, warp, lane);
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int BN, bool UP>
+static int launch_halo(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &ty, const CUtensorMap &tr, const HaloParams &hp,
+                       size_t smem, int num_tiles, cudaStream_t st)
+{
+    static size_t configured = 0;
+    if (configured < smem) {
+        HN_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        configured = 227 * 1024;
+    }
+    int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    conv_halo_kernel<BN, UP><<<grid, HALO_THREADS, smem, st>>>(ta, tb, ty, tr, hp);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+// Is the halo kernel applicable / profitable for this 3x3 convolution of x (or of the 2x upsample of x)?
+bool conv_halo_ok(const hn_tensor *x, const hn_conv *cv, const hn_tensor *y, bool upsample)
+{
+    static const bool disabled = getenv("HN_NO_HALO") != nullptr;
+    if (disabled && !upsample) return false;
+    if (x->dtype != HN_BF16 || cv->r != 3 || cv->s != 3 || cv->stride != 1 || cv->pad != cv->dil) return false;
+    if (cv->dil != 1 && (upsample || cv->dil != 2)) return false;
+    if (x->c % 64 != 0 || x->ld % 8 != 0 || (reinterpret_cast<uintptr_t>(x->ptr) & 15) != 0) return false;
+    if (hn_conv_cout_pad(cv->cout, HN_BF16) < 64) return false;
+    if (upsample) return true;
+    // ragged-tile waste of the fixed 16x8 tile against the best tile of the generic kernel's menu
+    const int64_t halo_area = cdiv(y->h, HALO_TH) * HALO_TH * cdiv(y->w, HALO_TW) * HALO_TW;
+    const int menu[5][2] = {{8, 16}, {4, 32}, {16, 8}, {2, 64}, {1, 128}};
+    int64_t best = -1;
+    for (int i = 0; i < 5; ++i) {
+        int64_t a = cdiv(y->h, menu[i][0]) * menu[i][0] * cdiv(y->w, menu[i][1]) * menu[i][1];
+        if (best < 0 || a < best) best = a;
+    }
+    if (halo_area * 100 > best * 104) return false;                 // > 4 % more padded work than the generic kernel
+    // the gain is the 9x smaller A traffic: decisive for narrow outputs, irrelevant for wide compute-bound layers
+    return hn_conv_cout_pad(cv->cout, HN_BF16) <= 128;
+}
+
+int conv2d_fwd_halo(const hn_tensor *x, const void *w, const hn_conv *cv, const hn_epilogue *ep, const hn_tensor *y, bool upsample,
+                    cudaStream_t st)
+{
+    const int Ho = y->h, Wo = y->w;
+    if ((int64_t)x->n * Ho * Wo == 0) return HN_OK;
+    const int d = cv->dil;
+    const int kpad = hn_conv_kpad(x->c, 3, 3);
+    const int cout_pad = hn_conv_cout_pad(cv->cout, HN_BF16);
+    HaloParams hp{};
+    TcParams &p = hp.t;
+    hp.PW = HALO_TW + 2 * d;
+    hp.PH = HALO_TH + 2 * d;
+    hp.a_slot_bytes = (int)(cdiv((int64_t)hp.PW * hp.PH * 128, 1024) * 1024);
+    p.TH = HALO_TH; p.TW = HALO_TW;
+    p.tiles_h = (int)cdiv(Ho, HALO_TH); p.tiles_w = (int)cdiv(Wo, HALO_TW); p.n_img = x->n;
+    p.Ho = Ho; p.Wo = Wo;
+    p.R = 3; p.S = 3; p.pad = cv->pad; p.dil = d; p.cblocks = x->c / 64;
+    p.Cout = cv->cout;
+    const int num_m_tiles = p.n_img * p.tiles_h * p.tiles_w;
+    int bn = 64;
+    for (int cand : {256, 128})
+        if (cout_pad % cand == 0 && (int64_t)num_m_tiles * (cout_pad / cand) >= 2 * (int64_t)num_sms()) { bn = cand; break; }
+    p.n_tiles = cout_pad / bn;
+    // shared-memory plan: A slots + B ring + epilogue staging + barriers
+    const int64_t fixed = (int64_t)HALO_NA * hp.a_slot_bytes + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/;
+    int nb = (int)((227 * 1024 - fixed) / (bn * 128));
+    if (nb > HALO_NB_MAX) nb = HALO_NB_MAX;
+    HN_CHECK_ARG(nb >= 2, "conv_halo: shared memory too small for this shape");
+    hp.nb = nb;
+    hp.b_resident = (p.cblocks * 9 <= nb && p.n_tiles == 1) ? 1 : 0;   // one Cout tile: the same weights for every tile
+    if (hp.b_resident) hp.nb = p.cblocks * 9;
+    const size_t smem = (size_t)HALO_NA * hp.a_slot_bytes + (size_t)hp.nb * bn * 128 + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 + 1024;
+
+    CUtensorMap ta, tb, ty, tr;
+    memset(&ta, 0, sizeof(ta));
+    memset(&ty, 0, sizeof(ty));
+    memset(&tr, 0, sizeof(tr));
+    if (upsample) {
+        hp.xlow = (const __nv_bfloat16 *)x->ptr;
+        hp.ldx = x->ld; hp.Hl = x->h; hp.Wl = x->w;
+    } else {
+        uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
+        uint64_t strides[4] = {2, (uint64_t)x->ld * 2, (uint64_t)x->ld * 2 * x->w, (uint64_t)x->ld * 2 * x->w * x->h};
+        uint32_t box[4] = {64, (uint32_t)hp.PW, (uint32_t)hp.PH, 1};
+        int rc = make_tmap(&ta, x->ptr, 4, dims, strides, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)kpad, (uint64_t)cout_pad};
+        uint64_t strides[2] = {2, (uint64_t)kpad * 2};
+        uint32_t box[2] = {64, (uint32_t)bn};
+        int rc = make_tmap(&tb, w, 2, dims, strides, box);
+        if (rc) return rc;
+    }
+    p.y = y->ptr; p.ldy = y->ld; p.y_f32 = (y->dtype == HN_F32);
+    p.scale = ep->scale; p.shift = ep->shift; p.res = ep->residual; p.ldr = ep->residual_ld;
+    p.act = ep->act; p.slope = ep->slope; p.slope_ptr = ep->slope_ptr;
+    p.ebw = HALO_TW;
+    {
+        const uint64_t esz = p.y_f32 ? 4 : 2;
+        const bool ok = (reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0 && ((uint64_t)y->ld * esz) % 16 == 0;
+        if (ok) {
+            uint64_t dims[4] = {(uint64_t)cv->cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)p.n_img};
+            uint64_t strides[4] = {esz, (uint64_t)y->ld * esz, (uint64_t)y->ld * esz * Wo, (uint64_t)y->ld * esz * Wo * Ho};
+            uint32_t box[4] = {(uint32_t)(128 / esz), (uint32_t)p.ebw, (uint32_t)(32 / p.ebw), 1};
+            int rc = make_tmap(&ty, y->ptr, 4, dims, strides, box, p.y_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+            if (rc) return rc;
+            p.tma_out = 1;
+            if (ep->residual && !p.y_f32 && (reinterpret_cast<uintptr_t>(ep->residual) & 15) == 0 && ((uint64_t)ep->residual_ld * 2) % 16 == 0) {
+                uint64_t rs[4] = {2, (uint64_t)ep->residual_ld * 2, (uint64_t)ep->residual_ld * 2 * Wo, (uint64_t)ep->residual_ld * 2 * Wo * Ho};
+                rc = make_tmap(&tr, ep->residual, 4, dims, rs, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+                if (rc) return rc;
+                p.tma_res = 1;
+            }
+        }
+    }
+    const int num_tiles = num_m_tiles * p.n_tiles;
+    if (upsample) {
+        switch (bn) {
+            case 256: return launch_halo<256, true>(ta, tb, ty, tr, hp, smem, num_tiles, st);
+            case 128: return launch_halo<128, true>(ta, tb, ty, tr, hp, smem, num_tiles, st);
+            default: return launch_halo<64, true>(ta, tb, ty, tr, hp, smem, num_tiles, st);
+        }
+    }
+    switch (bn) {
+        case 256: return launch_halo<256, false>(ta, tb, ty, tr, hp, smem, num_tiles, st);
+        case 128: return launch_halo<128, false>(ta, tb, ty, tr, hp, smem, num_tiles, st);
+        default: return launch_halo<64, false>(ta, tb, ty, tr, hp, smem, num_tiles, st);
+    }
+}
+
+}  // namespace hn
+
+using namespace hn;
+
+// PSPUpsample fused: y = epilogue(conv3x3_pad1(bilinear_2x(x)))  (cm/models/pspnet.py:37-40 without the upsampled tensor)
+extern "C" int hn_upconv3x3_fwd(const hn_tensor *x, const void *w_packed, const hn_conv *cv, const hn_epilogue *ep, const hn_tensor *y,
+                                void *stream)
+{
+    HN_CHECK_ARG(x && w_packed && cv && ep && y && x->ptr && y->ptr, "hn_upconv3x3_fwd: null pointer");
+    HN_CHECK_ARG(y->n == x->n && y->h == 2 * x->h && y->w == 2 * x->w && y->c == cv->cout, "hn_upconv3x3_fwd: output must be N=%d %dx%d C=%d",
+                 x->n, 2 * x->h, 2 * x->w, cv->cout);
+    HN_CHECK_ARG((ep->scale != nullptr) == (ep->shift != nullptr), "hn_upconv3x3_fwd: scale and shift go together");
+    HN_CHECK_ARG(conv_halo_ok(x, cv, y, true), "hn_upconv3x3_fwd: needs BF16 NHWC input with Cin %% 64 == 0, a 3x3 stride-1 pad-1 filter and Cout >= 33");
+    HN_CHECK_ARG(!ep->out_nchw && !ep->stat_sum && !ep->stat_sqsum, "hn_upconv3x3_fwd: out_nchw / fused statistics are not implemented");
+    return conv2d_fwd_halo(x, w_packed, cv, ep, y, true, (cudaStream_t)stream);
+}

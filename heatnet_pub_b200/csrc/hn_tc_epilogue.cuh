@@ -1,0 +1,231 @@
+// Shared epilogue of the tcgen05 convolution kernels (hn_conv_tc.cu, hn_conv_halo.cu).
+#pragma once
+#include "hn_common.cuh"
+#include "hn_tc_ptx.cuh"
+
+namespace hn {
+
+constexpr int EPI_WARP0 = 4;
+
+struct TcParams {
+    // tiling of the output pixel space
+    int tiles_w, tiles_h, n_img;   // M tiles = n_img * tiles_h * tiles_w
+    int TH, TW;                    // TH*TW = 128
+    int Ho, Wo;                    // output spatial size (flat mode: Ho = 1, Wo = total pixels)
+    int n_tiles;                   // Cout tiles
+    int R, S, pad, dil;
+    int cblocks;                   // Cin / 64 (flat-from-workspace: kpad / 64 with R=S=1)
+    int Cout;
+    // epilogue
+    void *y;
+    int ldy, y_f32;
+    const float *scale, *shift;
+    const void *res;
+    int ldr;
+    int act;
+    float slope;
+    const float *slope_ptr;
+    // TMA epilogue: output (and residual) go through a swizzled shared-memory staging tile per epilogue warp
+    int tma_out, tma_res;
+    int ebw;                       // staging box = {128 B of channels, ebw pixels, 32/ebw rows, 1}: ebw = min(TW, 32)
+};
+
+constexpr int EPI_STAGE_BYTES = 32 * 128;   // 32 pixels x 128 B per epilogue warp
+constexpr int NUM_EPI_WARPS = 8;
+
+
+// Runs on warps EPI_WARP0 .. EPI_WARP0+7 of a CTA.  `tiles`: this CTA walks tile = blockIdx.x, += gridDim.x, ... < num_tiles;
+// ACC_COLS: TMEM columns per accumulator buffer (two buffers).
+template <int BLOCK_N>
+__device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorMap *tmap_y_p, const CUtensorMap *tmap_r_p, uint32_t tmem_base,
+                                              uint64_t *tfull_bar, uint64_t *tempty_bar, uint64_t *res_bar, uint8_t *epi_stage,
+                                              int num_tiles, int warp, int lane)
+{
+    constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    const CUtensorMap &tmap_y = *tmap_y_p;
+    const CUtensorMap &tmap_r = *tmap_r_p;
+        // ===================== epilogue =====================
+        // Warp w may only touch TMEM lanes [32*(w%4), +32): one accumulator row (= output pixel) per thread.
+        // Wide tiles (>= 128 columns) are split between two groups of 4 warps.  Per 128-byte chunk of a row's
+        // channels the warp: (optionally) TMA-loads the residual chunk into its private staging tile, tcgen05.ld's
+        // the accumulator, applies scale/shift/residual/activation, writes the row back into the (128B-swizzled,
+        // bank-conflict-free) staging tile and one lane TMA-stores the 32-pixel x 128-byte box.  Global traffic is
+        // therefore full-line bulk transfers; the LSU only sees shared memory.  Views that TMA cannot address
+        // (channel stride or base not 16-byte aligned) take the direct per-thread path.
+        constexpr int GROUPS = BLOCK_N >= 128 ? 2 : 1;
+        constexpr int COLS = BLOCK_N / GROUPS;                 // columns per warp
+        constexpr int SUB = COLS < 32 ? COLS : 32;             // columns per tcgen05.ld
+        const int ew = warp - EPI_WARP0;
+        const int q = ew & 3, grp = ew >> 2;
+        if (grp < GROUPS) {
+            const int row = q * 32 + lane;                     // accumulator row = pixel within the tile
+            const int col0 = grp * COLS;
+            const int esz = p.y_f32 ? 4 : 2;
+            const int tch = 128 / esz;                         // columns per staging chunk (128 B per pixel)
+            const uint32_t stage = smem_u32(epi_stage + ew * EPI_STAGE_BYTES);
+            const uint32_t srow = stage + lane * 128;          // this thread's pixel row in the staging tile
+            const uint32_t rbar = smem_u32(res_bar + ew);
+            uint32_t rphase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            float slope = p.slope;
+            if (p.slope_ptr) slope = __ldg(p.slope_ptr);
+            const bool res_vec = p.res != nullptr && (p.ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
+                const int ho = th * p.TH + row / p.TW, wo = tw * p.TW + row % p.TW;
+                const bool valid = ho < p.Ho && wo < p.Wo;
+                const int64_t pix = ((int64_t)img * p.Ho + ho) * p.Wo + wo;
+                const int ctile = nt * BLOCK_N + col0;         // first output channel of this warp's columns
+                // coordinates of this warp's 32-pixel box (first pixel = row q*32 of the tile)
+                const int bx = tw * p.TW + (q * 32) % p.TW, by = th * p.TH + (q * 32) / p.TW;
+                const __nv_bfloat16 *rrow = (const __nv_bfloat16 *)p.res + pix * p.ldr + ctile;
+                bool waited = false;
+                for (int ck = 0; ck < COLS; ck += tch) {
+                    const bool chunk_on = ctile + ck < p.Cout;          // warp-uniform
+                    if (p.tma_out && lane == 0) {
+                        bulk_wait_read0();                               // previous store has drained the staging tile
+                        if (p.tma_res && chunk_on) {
+                            mbar_expect_tx(rbar, EPI_STAGE_BYTES);
+                            tma_load_4d(stage, &tmap_r, rbar, ctile + ck, bx, by, img);
+                        }
+                    }
+                    if (p.tma_out) __syncwarp();
+                    if (!waited) {
+                        mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
+                        tcgen05_fence_after();
+                        waited = true;
+                    }
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + col0 + ck;
+                    if (p.tma_res && chunk_on) {
+                        mbar_wait(rbar, rphase);
+                        rphase ^= 1;
+                    }
+                    const int nsub = (tch < COLS - ck ? tch : COLS - ck) / SUB;
+                    for (int si = 0; si < nsub; ++si) {
+                        uint32_t raw[SUB];
+                        if constexpr (SUB == 32) tmem_ld_32x32(taddr + si * SUB, raw);
+                        else if constexpr (SUB == 16) tmem_ld_32x16(taddr + si * SUB, raw);
+                        tmem_ld_wait();
+                        const int cbase = ctile + ck + si * SUB;
+                        if (!chunk_on) continue;
+                        float v[SUB];
+#pragma unroll
+                        for (int j = 0; j < SUB; ++j) v[j] = __uint_as_float(raw[j]);
+                        const bool full = cbase + SUB <= p.Cout;
+                        if (p.scale) {
+                            if (full) {   // warp-uniform 16-byte broadcast loads
+#pragma unroll
+                                for (int j = 0; j < SUB; j += 4) {
+                                    const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + cbase + j));
+                                    const float4 sh = __ldg(reinterpret_cast<const float4 *>(p.shift + cbase + j));
+                                    v[j] = fmaf(v[j], sc.x, sh.x);
+                                    v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
+                                    v[j + 2] = fmaf(v[j + 2], sc.z, sh.z);
+                                    v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < SUB; ++j)
+                                    if (cbase + j < p.Cout) v[j] = fmaf(v[j], __ldg(p.scale + cbase + j), __ldg(p.shift + cbase + j));
+                            }
+                        }
+                        if (p.res) {
+                            if (p.tma_res) {          // residual chunk sits in the staging tile (BF16, swizzled)
+#pragma unroll
+                                for (int j = 0; j < SUB / 8; ++j) {
+                                    const uint4 rv = lds128(srow + ((((si * SUB) >> 3) + j) ^ (lane & 7)) * 16);
+                                    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&rv);
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        const float2 f = __bfloat1622float2(h[i]);
+                                        v[8 * j + 2 * i] += f.x;
+                                        v[8 * j + 2 * i + 1] += f.y;
+                                    }
+                                }
+                            } else if (valid) {
+                                if (res_vec && full) {
+#pragma unroll
+                                    for (int j = 0; j < SUB / 8; ++j) {
+                                        float r8[8];
+                                        Vec8<__nv_bfloat16>::load(rrow + ck + si * SUB + 8 * j, r8);
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) v[8 * j + i] += r8[i];
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < SUB; ++j)
+                                        if (cbase + j < p.Cout) v[j] += __bfloat162float(rrow[ck + si * SUB + j]);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < SUB; ++j) v[j] = apply_act(v[j], p.act, slope);
+                        if (p.tma_out) {
+                            if (p.y_f32) {
+#pragma unroll
+                                for (int j = 0; j < SUB / 4; ++j) {
+                                    uint4 o = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                                                         __float_as_uint(v[4 * j + 3]));
+                                    sts128(srow + ((((si * SUB) >> 2) + j) ^ (lane & 7)) * 16, o);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < SUB / 8; ++j) {
+                                    uint4 o;
+                                    __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+                                    sts128(srow + ((((si * SUB) >> 3) + j) ^ (lane & 7)) * 16, o);
+                                }
+                            }
+                        } else if (valid) {
+                            if (p.y_f32) {
+                                float *yp = (float *)p.y + pix * p.ldy + cbase;
+                                if (full && (p.ldy & 3) == 0) {
+#pragma unroll
+                                    for (int j = 0; j < SUB; j += 4) *reinterpret_cast<float4 *>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < SUB; ++j)
+                                        if (cbase + j < p.Cout) yp[j] = v[j];
+                                }
+                            } else {
+                                __nv_bfloat16 *yp = (__nv_bfloat16 *)p.y + pix * p.ldy + cbase;
+                                if (full && (p.ldy & 7) == 0) {
+#pragma unroll
+                                    for (int j = 0; j < SUB; j += 8) {
+                                        float o8[8];
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) o8[i] = v[j + i];
+                                        Vec8<__nv_bfloat16>::store(yp + j, o8);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < SUB; ++j)
+                                        if (cbase + j < p.Cout) yp[j] = __float2bfloat16_rn(v[j]);
+                                }
+                            }
+                        }
+                    }
+                    if (p.tma_out) {
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0 && chunk_on) {
+                            tma_store_4d(&tmap_y, stage, ctile + ck, bx, by, img);
+                            bulk_commit();
+                        }
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+            if (p.tma_out && lane == 0) bulk_wait_read0();    // staging tile must outlive the last bulk store
+        }
+}
+
+}  // namespace hn

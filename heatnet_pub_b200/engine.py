@@ -24,6 +24,26 @@ BN_TRAIN_RAW_FP32 = os.environ.get("HEATNET_B200_BN_RAW_FP32", "1") != "0"
 launch_count = 0
 # bench.py sets this to a list to collect (description, start_event, end_event) around every conv launch
 conv_timer = None
+# ... and this one around every other op (bilinear, pools, layout conversion)
+op_timer = None
+
+
+class _timed:
+    """`with _timed("bilinear"):` records CUDA events around the enclosed launches when op_timer is a list."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if op_timer is not None:
+            self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if op_timer is not None:
+            self.b.record()
+            op_timer.append((self.name, self.a, self.b))
+        return False
 
 
 def _stream():
@@ -242,7 +262,8 @@ def from_nchw(t: torch.Tensor, dtype: torch.dtype, out: Optional[Act] = None) ->
     if out is None:
         out = new_act(n, h, w, c, dtype, src.device)
     assert (out.n, out.h, out.w, out.c) == (n, h, w, c) and out.dtype == dtype
-    _lib.check(_lib.load().hn_nchw_to_nhwc(src.data_ptr(), C.byref(out.hn()), _stream()))
+    with _timed("nchw_to_nhwc"):
+        _lib.check(_lib.load().hn_nchw_to_nhwc(src.data_ptr(), C.byref(out.hn()), _stream()))
     _count()
     return out
 
@@ -262,7 +283,8 @@ def fuse_inputs(modal_1: torch.Tensor, modal_2: Optional[torch.Tensor], dtype: t
 
 def to_nchw_f32(a: Act) -> torch.Tensor:
     out = torch.empty((a.n, a.c, a.h, a.w), dtype=torch.float32, device=a.buf.device)
-    _lib.check(_lib.load().hn_nhwc_to_nchw(C.byref(a.hn()), out.data_ptr(), _stream()))
+    with _timed("nhwc_to_nchw"):
+        _lib.check(_lib.load().hn_nhwc_to_nchw(C.byref(a.hn()), out.data_ptr(), _stream()))
     _count()
     return out
 
@@ -561,7 +583,8 @@ def maxpool3x3s2(x: Act, out: Optional[Act] = None) -> Act:
         return y
     ho, wo = (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1
     out = out or new_act(x.n, ho, wo, x.c, x.dtype, x.buf.device)
-    _lib.check(_lib.load().hn_maxpool3x3s2_fwd(C.byref(x.hn()), C.byref(out.hn()), _stream()))
+    with _timed("maxpool"):
+        _lib.check(_lib.load().hn_maxpool3x3s2_fwd(C.byref(x.hn()), C.byref(out.hn()), _stream()))
     _count()
     return out
 
@@ -575,7 +598,8 @@ def pyramid_pool(x: Act, sizes: Sequence[int]):
     xh = x.hn()
     ws_bytes = lib.hn_pyramid_pool_workspace_bytes(C.byref(xh), arr, len(sizes))
     ws = workspace(ws_bytes, x.buf.device)
-    _lib.check(lib.hn_pyramid_pool_fwd(C.byref(xh), arr, len(sizes), out.data_ptr(), ws.data_ptr(), ws_bytes, _stream()))
+    with _timed("pyramid_pool"):
+        _lib.check(lib.hn_pyramid_pool_fwd(C.byref(xh), arr, len(sizes), out.data_ptr(), ws.data_ptr(), ws_bytes, _stream()))
     _count(2)
     acts, off = [], 0
     for s in sizes:
@@ -609,7 +633,8 @@ def pyramid_pool(x: Act, sizes: Sequence[int]):
 def bilinear(x: Act, h: int, w: int, out: Optional[Act] = None, out_dtype=None) -> Act:
     out = out or new_act(x.n, h, w, x.c, out_dtype or x.dtype, x.buf.device)
     assert (out.n, out.h, out.w, out.c) == (x.n, h, w, x.c)
-    _lib.check(_lib.load().hn_bilinear_fwd(C.byref(x.hn()), C.byref(out.hn()), _stream()))
+    with _timed("bilinear"):
+        _lib.check(_lib.load().hn_bilinear_fwd(C.byref(x.hn()), C.byref(out.hn()), _stream()))
     _count()
     tape = current_tape
     if tape is not None and tape.needs(x):
@@ -800,6 +825,32 @@ def bilinear_sum(xs: Sequence[Act], h: int, w: int) -> Act:
     x0 = xs[0]
     out = new_act(x0.n, h, w, x0.c, x0.dtype, x0.buf.device)
     arr = (HnTensor * len(xs))(*[x.hn() for x in xs])
-    _lib.check(_lib.load().hn_bilinear_sum_fwd(arr, len(xs), C.byref(out.hn()), _stream()))
+    with _timed("bilinear_sum"):
+        _lib.check(_lib.load().hn_bilinear_sum_fwd(arr, len(xs), C.byref(out.hn()), _stream()))
     _count()
     return out
+
+
+def upconv3x3(x: Act, conv: torch.nn.Conv2d, scale=None, shift=None, act=ACT_NONE, slope=0.0, slope_ptr=None, out_dtype=None) -> Act:
+    """act(conv3x3(bilinear_2x(x)) * scale + shift) in ONE kernel: the upsampled tensor is never written to HBM."""
+    lib = _lib.load()
+    assert conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1) and conv.dilation == (1, 1)
+    out = new_act(x.n, 2 * x.h, 2 * x.w, conv.out_channels, out_dtype or x.dtype, x.buf.device)
+    wp = packed_weight(conv, x.dtype)
+    cv = HnConv(conv.out_channels, 3, 3, 1, 1, 1)
+    ep = _epilogue(scale, shift, None, act, slope, slope_ptr)
+    timing = conv_timer is not None
+    if timing:
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev_a.record()
+    _lib.check(lib.hn_upconv3x3_fwd(C.byref(x.hn()), wp.data_ptr(), C.byref(cv), C.byref(ep), C.byref(out.hn()), _stream()))
+    if timing:
+        ev_b.record()
+        conv_timer.append((f"{x.c}->{conv.out_channels} k3 s1 d1 @{2 * x.h}x{2 * x.w}", ev_a, ev_b))
+    _count()
+    return out
+
+
+def upconv3x3_ok(x: Act, conv: torch.nn.Conv2d) -> bool:
+    return (x.dtype == torch.bfloat16 and x.c % 64 == 0 and x.ld % 8 == 0 and conv.out_channels >= 33
+            and os.environ.get("HN_NO_UPCONV") is None)

@@ -100,8 +100,20 @@ class PSPUpsample(_KernelModule):
         )
 
     def _run(self, x: Act) -> Act:
+        conv, bn, prelu = self.conv[0], self.conv[1], self.conv[2]
+        bn_train = bn.training or bn.running_mean is None
+        if E.current_tape is None and E.upconv3x3_ok(x, conv):
+            # inference / validation: upsample fused into the conv's operand producer (no 2x tensor in HBM)
+            if not bn_train:
+                scale, shift = E.folded_affine(conv, bn)
+                return E.upconv3x3(x, conv, scale, shift, ACT_LEAKY, slope_ptr=prelu.weight)
+            scale, shift = E.folded_affine(conv, None)
+            raw = E.upconv3x3(x, conv, scale, shift, out_dtype=torch.float32)
+            bscale, bshift, _, _ = E.batchnorm_train_affine(raw, bn)
+            return E.affine_act(raw, bscale, bshift, None, ACT_LEAKY, slope_ptr=prelu.weight,
+                                out=E.new_act(raw.n, raw.h, raw.w, raw.c, x.dtype, x.buf.device))
         p = E.bilinear(x, 2 * x.h, 2 * x.w)
-        return E.conv_bn_act(p, self.conv[0], self.conv[1], ACT_LEAKY, slope_ptr=self.conv[2].weight)
+        return E.conv_bn_act(p, conv, bn, ACT_LEAKY, slope_ptr=prelu.weight)
 
 
 class PSPNet(_KernelModule):

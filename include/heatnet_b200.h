@@ -95,6 +95,12 @@ int64_t hn_conv2d_workspace_bytes(const hn_tensor *x, const hn_conv *cv);
 int hn_conv2d_fwd(const hn_tensor *x, const void *w_packed, const hn_conv *cv, const hn_epilogue *ep,
                   const hn_tensor *y, void *workspace, int64_t workspace_bytes, void *stream);
 
+/* PSPUpsample without the upsampled tensor (cm/models/pspnet.py:37-40): y = epilogue(conv3x3_pad1(bilinear_2x(x))).
+ * The 2x-upsampled halo patch of every tile is computed in shared memory by producer warps (exact ATen bilinear rule)
+ * and consumed by tcgen05 straight from there.  BF16, Cin % 64 == 0, w_packed = hn_pack_weight of the 3x3 filter. */
+int hn_upconv3x3_fwd(const hn_tensor *x, const void *w_packed, const hn_conv *cv, const hn_epilogue *ep, const hn_tensor *y,
+                     void *stream);
+
 /* ---- bandwidth-bound ops ---- */
 /* nn.MaxPool2d(3,2,1): cm/models/extractors.py:128 */
 int hn_maxpool3x3s2_fwd(const hn_tensor *x, const hn_tensor *y, void *stream);

@@ -107,6 +107,64 @@ def test_conv_bf16_tensor_core_matches_oracle(E, case):
     assert rel(back(y16), ref) < BF16_TOL
 
 
+HALO_CASES = [
+    # cin, cout, dil, h, w      3x3 stride-1 layers with narrow outputs: one halo patch per k-block (hn_conv_halo.cu)
+    (64, 64, 1, 33, 40),       # ragged both ways, weights resident in shared memory
+    (64, 64, 1, 16, 8),        # exactly one tile
+    (256, 64, 1, 20, 24),      # 4 k-blocks, streamed weights
+    (128, 128, 1, 18, 30),     # two Cout tiles possible
+    (64, 64, 2, 21, 17),       # dilation 2
+    (192, 64, 1, 7, 5),        # smaller than a tile
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv3x3_halo_patch_path(E, case):
+    cin, cout, dil, h, w = case
+    g = torch.Generator().manual_seed(11)
+    conv = nn.Conv2d(cin, cout, 3, 1, dil, dil, bias=True)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * (2.0 / (9 * cin)) ** 0.5)
+        conv.bias.copy_(torch.randn(cout, generator=g) * 0.1)
+    x = torch.randn(3, cin, h, w, generator=g)
+    res = torch.randn(3, cout, h, w, generator=g)
+    ref_r = F.relu(F.conv2d(x.bfloat16().float(), conv.weight.detach().bfloat16().float(), conv.bias, 1, dil, dil) + res.bfloat16().float())
+    import copy
+    convg = copy.deepcopy(conv).cuda()
+    scale, shift = E.folded_affine(convg, None)
+    y32 = E.conv2d(to_act(E, x, torch.bfloat16), convg, scale, shift, act=E.ACT_RELU, out_dtype=torch.float32)
+    ref_nores = F.relu(F.conv2d(x.bfloat16().float(), conv.weight.detach().bfloat16().float(), conv.bias, 1, dil, dil))
+    assert rel(back(y32), ref_nores) < 1e-3
+    y16 = E.conv2d(to_act(E, x, torch.bfloat16), convg, scale, shift, residual=to_act(E, res, torch.bfloat16), act=E.ACT_RELU)
+    assert rel(back(y16), ref_r) < 1e-2
+
+
+@pytest.mark.parametrize("case", [(64, 64, 9, 11), (64, 64, 16, 8), (256, 64, 10, 12), (1024, 256, 6, 9), (128, 64, 1, 1)])
+def test_upsample2x_conv3x3_fused(E, case):
+    """PSPUpsample's bilinear 2x + 3x3 conv in one kernel (the upsampled tensor only ever exists as shared-memory halo
+    patches) == F.interpolate(align_corners=False) -> conv2d on the same BF16-rounded intermediate."""
+    cin, cout, h, w = case
+    g = torch.Generator().manual_seed(12)
+    conv = nn.Conv2d(cin, cout, 3, 1, 1, bias=True)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * (2.0 / (9 * cin)) ** 0.5)
+        conv.bias.copy_(torch.randn(cout, generator=g) * 0.1)
+    x = torch.randn(2, cin, h, w, generator=g)
+    up = F.interpolate(x.bfloat16().float(), size=(2 * h, 2 * w), mode="bilinear", align_corners=False).bfloat16().float()
+    ref = F.leaky_relu(F.conv2d(up, conv.weight.detach().bfloat16().float(), conv.bias, 1, 1), 0.25)
+    import copy
+    convg = copy.deepcopy(conv).cuda()
+    scale, shift = E.folded_affine(convg, None)
+    xa = to_act(E, x, torch.bfloat16)
+    assert E.upconv3x3_ok(xa, convg)
+    y = E.upconv3x3(xa, convg, scale, shift, E.ACT_LEAKY, slope=0.25, out_dtype=torch.float32)
+    assert (y.n, y.h, y.w, y.c) == (2, 2 * h, 2 * w, cout)
+    assert rel(back(y), ref) < 1e-3
+    # and identical (up to FP32 summation order) to the unfused path
+    y2 = E.conv2d(E.bilinear(xa, 2 * h, 2 * w), convg, scale, shift, act=E.ACT_LEAKY, slope=0.25, out_dtype=torch.float32)
+    assert rel(back(y), back(y2)) < 1e-5
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
 def test_conv_fused_epilogue_bn_residual_relu(E, dtype, tol):
     """conv -> BN(eval) -> += residual -> ReLU in one launch == cm/models/extractors.py:96-101."""
