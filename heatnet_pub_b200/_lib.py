@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_DIR, "libheatnet_b200.so")
+LIB_PATH = os.environ.get("HEATNET_B200_LIB", os.path.join(_DIR, "libheatnet_b200.so"))
 
 HN_F32, HN_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
@@ -36,9 +36,11 @@ SIGNATURES = {
     "hn_last_error": (C.c_char_p, []),
     "hn_version": (C.c_int, []),
     "hn_device_check": (C.c_int, []),
+    "hn_prof_read": (C.c_int, [_P, C.c_int]),
     "hn_nchw_to_nhwc": (C.c_int, [_P, _T, _P]),
     "hn_nhwc_to_nchw": (C.c_int, [_T, _P, _P]),
     "hn_pack_weight": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "hn_pack_weight_scaled": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "hn_bn_fold": (C.c_int, [_P, _P, _P, _P, _P, _F, _P, _P, _I32, _P]),
     "hn_conv_cout_pad": (_I32, [_I32, _I32]),
     "hn_conv_kpad": (_I32, [_I32, _I32, _I32]),

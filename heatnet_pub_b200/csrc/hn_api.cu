@@ -62,7 +62,7 @@ extern "C" int hn_conv2d_fwd(const hn_tensor *x, const void *w_packed, const hn_
     HN_CHECK_ARG(Ho >= 1 && Wo >= 1, "hn_conv2d_fwd: kernel size can't be greater than actual input size (%dx%d, k=%d)", x->h, x->w, cv->r);
     HN_CHECK_ARG(y->n == x->n && y->h == Ho && y->w == Wo && y->c == cv->cout, "hn_conv2d_fwd: output view must be N=%d %dx%d C=%d", x->n,
                  Ho, Wo, cv->cout);
-    HN_CHECK_ARG((ep->scale != nullptr) == (ep->shift != nullptr), "hn_conv2d_fwd: scale and shift go together");
+    // y = act(acc * scale + shift + residual): either vector may be absent (scale: 1, shift: 0)
     HN_CHECK_ARG(!ep->out_nchw && !ep->stat_sum && !ep->stat_sqsum, "hn_conv2d_fwd: out_nchw / fused statistics are not implemented yet");
     cudaStream_t st = (cudaStream_t)stream;
     if (x->dtype == HN_F32) {
@@ -70,4 +70,26 @@ extern "C" int hn_conv2d_fwd(const hn_tensor *x, const void *w_packed, const hn_
         return conv2d_fwd_f32(x, w_packed, cv, ep, y, st);
     }
     return conv2d_fwd_tc(x, w_packed, cv, ep, y, workspace, workspace_bytes, st);
+}
+
+// ---- role-level cycle accounting (only meaningful in the -DHN_PROFILE_ROLES build; zeros otherwise)
+namespace hn {
+#ifdef HN_PROFILE_ROLES
+__device__ unsigned long long g_role_cycles[16];
+#endif
+}
+extern "C" int hn_prof_read(unsigned long long *out16, int reset)
+{
+#ifdef HN_PROFILE_ROLES
+    HN_CUDA(cudaMemcpyFromSymbol(out16, hn::g_role_cycles, sizeof(unsigned long long) * 16));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        HN_CUDA(cudaMemcpyToSymbol(hn::g_role_cycles, z, sizeof(z)));
+    }
+    return 1;
+#else
+    for (int i = 0; i < 16; ++i) out16[i] = 0;
+    (void)reset;
+    return 0;
+#endif
 }

@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(256) transpose_tiles(const void *__restrict__ 
 
 // OIHW FP32 -> [cout_pad][kpad], k = (r*S+s)*Cin + c
 template <typename T>
-__global__ void __launch_bounds__(256) pack_weight_kernel(const float *__restrict__ w, T *__restrict__ dst, int cout, int cin, int R,
-                                                          int S, int cout_pad, int kpad)
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float *__restrict__ w, const float *__restrict__ row_scale,
+                                                          T *__restrict__ dst, int cout, int cin, int R, int S, int cout_pad, int kpad)
 {
     const int64_t total = (int64_t)cout_pad * kpad;
     const int K = R * S * cin;
@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float *__restric
             int tap = k / cin, c = k - tap * cin;
             int r = tap / S, s = tap - r * S;
             v = __ldg(w + (((int64_t)o * cin + c) * R + r) * S + s);
+            if (row_scale) v *= __ldg(row_scale + o);      // BatchNorm2d(eval) scale folded into the filter
         }
         dst[i] = from_f32<T>(v);
     }
@@ -640,17 +641,25 @@ extern "C" int hn_nhwc_to_nchw(const hn_tensor *src, float *dst, void *stream)
     return HN_OK;
 }
 
+extern "C" int hn_pack_weight_scaled(const float *w_oihw, const float *row_scale, void *dst, int32_t dtype, int32_t cout, int32_t cin,
+                                     int32_t r, int32_t s, int32_t cout_pad, int32_t kpad, void *stream);
 extern "C" int hn_pack_weight(const float *w_oihw, void *dst, int32_t dtype, int32_t cout, int32_t cin, int32_t r, int32_t s,
                               int32_t cout_pad, int32_t kpad, void *stream)
+{
+    return hn_pack_weight_scaled(w_oihw, nullptr, dst, dtype, cout, cin, r, s, cout_pad, kpad, stream);
+}
+
+extern "C" int hn_pack_weight_scaled(const float *w_oihw, const float *row_scale, void *dst, int32_t dtype, int32_t cout, int32_t cin,
+                                     int32_t r, int32_t s, int32_t cout_pad, int32_t kpad, void *stream)
 {
     HN_CHECK_ARG(w_oihw && dst, "hn_pack_weight: null pointer");
     HN_CHECK_ARG(cout_pad >= cout && kpad >= r * s * cin, "hn_pack_weight: padded sizes too small");
     int64_t total = (int64_t)cout_pad * kpad;
     int grid = wave_grid(total, 256);
     if (dtype == HN_BF16)
-        pack_weight_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, (__nv_bfloat16 *)dst, cout, cin, r, s, cout_pad, kpad);
+        pack_weight_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, row_scale, (__nv_bfloat16 *)dst, cout, cin, r, s, cout_pad, kpad);
     else
-        pack_weight_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, (float *)dst, cout, cin, r, s, cout_pad, kpad);
+        pack_weight_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, row_scale, (float *)dst, cout, cin, r, s, cout_pad, kpad);
     HN_LAUNCH_CHECK();
     return HN_OK;
 }

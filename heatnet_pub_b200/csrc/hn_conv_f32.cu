@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const float *__restrict__
             int co = n0 + tx * 4 + j;
             if (co >= g.Cout) continue;
             float v = acc[i][j];
-            if (scale) v = fmaf(v, __ldg(scale + co), __ldg(shift + co));
+            if (scale) v *= __ldg(scale + co);
+            if (shift) v += __ldg(shift + co);
             if (res) v += res[m * ldr + co];
             y[m * g.ldy + co] = apply_act(v, act, slope);
         }

@@ -60,7 +60,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     constexpr int TMEM_COLS = 2 * ACC_COLS;
     constexpr uint32_t IDESC = make_idesc_bf16(128, BLOCK_N);
     // A-producer warps of the UPSAMPLE variant: warps 2,3 always; warps 8-11 too when the epilogue only needs 4 warps
-    constexpr int NPROD = BLOCK_N <= 64 ? 6 : 2;
+    constexpr int NPROD = 6;   // warps 2, 3, 8-11 (the UPSAMPLE variant's epilogue runs on warps 4-7 only)
     const TcParams &p = hp.t;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -72,6 +72,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t *a_full = bars, *a_empty = bars + HALO_NA, *b_full = bars + 2 * HALO_NA, *b_empty = b_full + HALO_NB_MAX;
     uint64_t *tfull_bar = b_empty + HALO_NB_MAX, *tempty_bar = tfull_bar + 2, *res_bar = tempty_bar + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_bar + NUM_EPI_WARPS);
+    float *s_shift = reinterpret_cast<float *>(tmem_slot + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_m_tiles = p.n_img * p.tiles_h * p.tiles_w;
@@ -96,7 +97,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(tfull_bar + i), 1);
-            mbar_init(smem_u32(tempty_bar + i), BLOCK_N >= 128 ? 8 : 4);
+            mbar_init(smem_u32(tempty_bar + i), (BLOCK_N >= 128 && !UPSAMPLE) ? 8 : 4);
         }
         for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(smem_u32(res_bar + i), 1);
         fence_barrier_init();
@@ -110,8 +111,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const bool is_prod = UPSAMPLE && (warp == 2 || warp == 3 || (NPROD == 6 && warp >= 8));
-    const bool is_epi = warp >= EPI_WARP0 && !(UPSAMPLE && NPROD == 6 && warp >= 8);
+    const bool is_prod = UPSAMPLE && (warp == 2 || warp == 3 || warp >= 8);
+    const bool is_epi = warp >= EPI_WARP0 && !(UPSAMPLE && warp >= 8);
 
     if (warp == 0) {
         // ===================== TMA producer: weight tiles (and the halo patches when they are fetched) =====================
@@ -202,31 +203,59 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(smem_u32(a_empty + aslot), aphase ^ 1);
                 const uint32_t a_base = smem_u32(a_ring + aslot * hp.a_slot_bytes);
-                for (int t = pi * 32 + lane; t < ntask; t += NPROD * 32) {
-                    const int pp = t >> 3, j = t & 7;
-                    const int py = pp / hp.PW, px = pp - py * hp.PW;
-                    const int uy = uy0 + py, ux = ux0 + px;
-                    uint4 outv = make_uint4(0, 0, 0, 0);
-                    if (uy >= 0 && uy < Hu && ux >= 0 && ux < Wu) {
-                        int y0, y1, x0, x1;
-                        float ly, lx;
-                        bilinear_src_h(uy, hp.Hl, y0, y1, ly);
-                        bilinear_src_h(ux, hp.Wl, x0, x1, lx);
-                        const __nv_bfloat16 *b = ximg + kb * 64 + j * 8;
-                        float a00[8], a01[8], a10[8], a11[8], o[8];
-                        Vec8<__nv_bfloat16>::load(b + ((int64_t)y0 * hp.Wl + x0) * hp.ldx, a00);
-                        Vec8<__nv_bfloat16>::load(b + ((int64_t)y0 * hp.Wl + x1) * hp.ldx, a01);
-                        Vec8<__nv_bfloat16>::load(b + ((int64_t)y1 * hp.Wl + x0) * hp.ldx, a10);
-                        Vec8<__nv_bfloat16>::load(b + ((int64_t)y1 * hp.Wl + x1) * hp.ldx, a11);
-                        const float hy = 1.f - ly, hx = 1.f - lx;
+                // 4 tasks (one 16-byte channel chunk of one patch pixel each) per iteration: all 16 loads are issued before
+                // the first is consumed, so the L1/L2 latency of the gathers overlaps
+                constexpr int UNR = 4, STRIDE = NPROD * 32;
+                for (int t0 = pi * 32 + lane; t0 < ntask; t0 += UNR * STRIDE) {
+                    uint4 v[UNR][4];
+                    float ly[UNR], lx[UNR];
+                    uint32_t dst[UNR];
+                    bool live[UNR], inb[UNR];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) o[q] = hy * (hx * a00[q] + lx * a01[q]) + ly * (hx * a10[q] + lx * a11[q]);
-                        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&outv);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(o[2 * q], o[2 * q + 1]);
+                    for (int u = 0; u < UNR; ++u) {
+                        const int t = t0 + u * STRIDE;
+                        live[u] = t < ntask;
+                        inb[u] = false;
+                        if (!live[u]) continue;
+                        const int pp = t >> 3, j = t & 7;
+                        const int py = pp / hp.PW, px = pp - py * hp.PW;
+                        const int uy = uy0 + py, ux = ux0 + px;
+                        const uint32_t rowaddr = a_base + pp * 128;
+                        dst[u] = rowaddr + ((j ^ ((rowaddr >> 7) & 7)) << 4);
+                        if (uy >= 0 && uy < Hu && ux >= 0 && ux < Wu) {
+                            inb[u] = true;
+                            int y0, y1, x0, x1;
+                            bilinear_src_h(uy, hp.Hl, y0, y1, ly[u]);
+                            bilinear_src_h(ux, hp.Wl, x0, x1, lx[u]);
+                            const __nv_bfloat16 *b = ximg + kb * 64 + j * 8;
+                            v[u][0] = __ldg(reinterpret_cast<const uint4 *>(b + ((int64_t)y0 * hp.Wl + x0) * hp.ldx));
+                            v[u][1] = __ldg(reinterpret_cast<const uint4 *>(b + ((int64_t)y0 * hp.Wl + x1) * hp.ldx));
+                            v[u][2] = __ldg(reinterpret_cast<const uint4 *>(b + ((int64_t)y1 * hp.Wl + x0) * hp.ldx));
+                            v[u][3] = __ldg(reinterpret_cast<const uint4 *>(b + ((int64_t)y1 * hp.Wl + x1) * hp.ldx));
+                        }
                     }
-                    const uint32_t rowaddr = a_base + pp * 128;
-                    sts128(rowaddr + ((j ^ ((rowaddr >> 7) & 7)) << 4), outv);
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
+                        if (!live[u]) continue;
+                        uint4 outv = make_uint4(0, 0, 0, 0);
+                        if (inb[u]) {
+                            const float hy = 1.f - ly[u], hx = 1.f - lx[u];
+                            const __nv_bfloat162 *h00 = reinterpret_cast<const __nv_bfloat162 *>(&v[u][0]);
+                            const __nv_bfloat162 *h01 = reinterpret_cast<const __nv_bfloat162 *>(&v[u][1]);
+                            const __nv_bfloat162 *h10 = reinterpret_cast<const __nv_bfloat162 *>(&v[u][2]);
+                            const __nv_bfloat162 *h11 = reinterpret_cast<const __nv_bfloat162 *>(&v[u][3]);
+                            __nv_bfloat162 *ho = reinterpret_cast<__nv_bfloat162 *>(&outv);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 a00 = __bfloat1622float2(h00[q]), a01 = __bfloat1622float2(h01[q]);
+                                const float2 a10 = __bfloat1622float2(h10[q]), a11 = __bfloat1622float2(h11[q]);
+                                const float ox = hy * (hx * a00.x + lx[u] * a01.x) + ly[u] * (hx * a10.x + lx[u] * a11.x);
+                                const float oy = hy * (hx * a00.y + lx[u] * a01.y) + ly[u] * (hx * a10.y + lx[u] * a11.y);
+                                ho[q] = __floats2bfloat162_rn(ox, oy);
+                            }
+                        }
+                        sts128(dst[u], outv);
+                    }
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -235,7 +264,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
         }
     } else if (is_epi) {
-        conv_epilogue<BLOCK_N>(p, &tmap_y, &tmap_r, tmem_base, tfull_bar, tempty_bar, res_bar, epi_stage, num_tiles, warp, lane);
+        conv_epilogue<BLOCK_N, UPSAMPLE>(p, &tmap_y, &tmap_r, tmem_base, tfull_bar, tempty_bar, res_bar, epi_stage, s_shift, num_tiles, warp, lane);
     }
 
     tcgen05_fence_before();
@@ -308,14 +337,14 @@ int conv2d_fwd_halo(const hn_tensor *x, const void *w, const hn_conv *cv, const 
         if (cout_pad % cand == 0 && (int64_t)num_m_tiles * (cout_pad / cand) >= 2 * (int64_t)num_sms()) { bn = cand; break; }
     p.n_tiles = cout_pad / bn;
     // shared-memory plan: A slots + B ring + epilogue staging + barriers
-    const int64_t fixed = (int64_t)HALO_NA * hp.a_slot_bytes + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/;
+    const int64_t fixed = (int64_t)HALO_NA * hp.a_slot_bytes + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + 2048 /*barriers + shift table*/;
     int nb = (int)((227 * 1024 - fixed) / (bn * 128));
     if (nb > HALO_NB_MAX) nb = HALO_NB_MAX;
     HN_CHECK_ARG(nb >= 2, "conv_halo: shared memory too small for this shape");
     hp.nb = nb;
     hp.b_resident = (p.cblocks * 9 <= nb && p.n_tiles == 1) ? 1 : 0;   // one Cout tile: the same weights for every tile
     if (hp.b_resident) hp.nb = p.cblocks * 9;
-    const size_t smem = (size_t)HALO_NA * hp.a_slot_bytes + (size_t)hp.nb * bn * 128 + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 + 1024;
+    const size_t smem = (size_t)HALO_NA * hp.a_slot_bytes + (size_t)hp.nb * bn * 128 + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 + 2048;
 
     CUtensorMap ta, tb, ty, tr;
     memset(&ta, 0, sizeof(ta));
@@ -386,7 +415,6 @@ extern "C" int hn_upconv3x3_fwd(const hn_tensor *x, const void *w_packed, const 
     HN_CHECK_ARG(x && w_packed && cv && ep && y && x->ptr && y->ptr, "hn_upconv3x3_fwd: null pointer");
     HN_CHECK_ARG(y->n == x->n && y->h == 2 * x->h && y->w == 2 * x->w && y->c == cv->cout, "hn_upconv3x3_fwd: output must be N=%d %dx%d C=%d",
                  x->n, 2 * x->h, 2 * x->w, cv->cout);
-    HN_CHECK_ARG((ep->scale != nullptr) == (ep->shift != nullptr), "hn_upconv3x3_fwd: scale and shift go together");
     HN_CHECK_ARG(conv_halo_ok(x, cv, y, true), "hn_upconv3x3_fwd: needs BF16 NHWC input with Cin %% 64 == 0, a 3x3 stride-1 pad-1 filter and Cout >= 33");
     HN_CHECK_ARG(!ep->out_nchw && !ep->stat_sum && !ep->stat_sqsum, "hn_upconv3x3_fwd: out_nchw / fused statistics are not implemented");
     return conv2d_fwd_halo(x, w_packed, cv, ep, y, true, (cudaStream_t)stream);

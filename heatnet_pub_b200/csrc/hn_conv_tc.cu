@@ -49,6 +49,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t *full_bar = bars, *empty_bar = bars + STAGES, *tfull_bar = bars + 2 * STAGES, *tempty_bar = bars + 2 * STAGES + 2;
     uint64_t *res_bar = bars + 2 * STAGES + 4;                              // one per epilogue warp
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4 + NUM_EPI_WARPS);
+    float *s_shift = reinterpret_cast<float *>(tmem_slot + 4);                // BLOCK_N floats (epilogue shift table)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_m_tiles = p.n_img * p.tiles_h * p.tiles_w;
@@ -87,7 +88,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            long long pw_empty = 0, pw_total = 0, ntl = 0;
+            (void)pw_empty; (void)pw_total; (void)ntl;
+#ifdef HN_PROFILE_ROLES
+            const long long prod_t0 = clock64();
+#endif
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                ++ntl;
                 const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
                 const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
                 const int w_base = tw * p.TW - p.pad, h_base = th * p.TH - p.pad;
@@ -95,7 +102,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 for (int r = 0; r < p.R; ++r)
                     for (int s = 0; s < p.S; ++s)
                         for (int cb = 0; cb < p.cblocks; ++cb, ++kb) {
-                            mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+                            { HN_PROF_T0(); mbar_wait(smem_u32(empty_bar + stage), phase ^ 1); HN_PROF_ADD(pw_empty); }
                             const uint32_t fb = smem_u32(full_bar + stage);
                             mbar_expect_tx(fb, STAGE_BYTES);
                             const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
@@ -104,6 +111,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
             }
+#ifdef HN_PROFILE_ROLES
+            pw_total = clock64() - prod_t0;
+            HN_PROF_FLUSH(0, pw_empty); HN_PROF_FLUSH(1, pw_total); HN_PROF_FLUSH(9, ntl); HN_PROF_FLUSH(10, 1);
+#endif
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -112,12 +123,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            long long mw_full = 0, mw_tempty = 0;
+            (void)mw_full; (void)mw_tempty;
+#ifdef HN_PROFILE_ROLES
+            const long long mma_t0 = clock64();
+#endif
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
+                { HN_PROF_T0(); mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1); HN_PROF_ADD(mw_tempty); }
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(smem_u32(full_bar + stage), phase);
+                    { HN_PROF_T0(); mbar_wait(smem_u32(full_bar + stage), phase); HN_PROF_ADD(mw_full); }
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                     const uint64_t adesc = make_kmajor_sw128_desc(sa);
@@ -134,9 +150,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
+#ifdef HN_PROFILE_ROLES
+            HN_PROF_FLUSH(2, mw_full); HN_PROF_FLUSH(3, mw_tempty); HN_PROF_FLUSH(4, clock64() - mma_t0);
+#endif
         }
     } else if (warp >= EPI_WARP0) {
-        conv_epilogue<BLOCK_N>(p, &tmap_y, &tmap_r, tmem_base, tfull_bar, tempty_bar, res_bar, epi_stage, num_tiles, warp, lane);
+        conv_epilogue<BLOCK_N>(p, &tmap_y, &tmap_r, tmem_base, tfull_bar, tempty_bar, res_bar, epi_stage, s_shift, num_tiles, warp, lane);
     }
 
     tcgen05_fence_before();
@@ -270,7 +289,7 @@ static int launch_tc(const CUtensorMap &ta, const CUtensorMap &tb, const CUtenso
                      int num_tiles, cudaStream_t st)
 {
     constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * BLOCK_K * 2) + NUM_EPI_WARPS * EPI_STAGE_BYTES +
-                            (2 * STAGES + 4 + NUM_EPI_WARPS) * 8 + 16 + 1024;
+                            (2 * STAGES + 4 + NUM_EPI_WARPS) * 8 + 16 + BN * 4 + 1024;
     static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
     static bool configured = false;
     if (!configured) {

@@ -34,108 +34,167 @@ constexpr int EPI_STAGE_BYTES = 32 * 128;   // 32 pixels x 128 B per epilogue wa
 constexpr int NUM_EPI_WARPS = 8;
 
 
-// Runs on warps EPI_WARP0 .. EPI_WARP0+7 of a CTA.  `tiles`: this CTA walks tile = blockIdx.x, += gridDim.x, ... < num_tiles;
-// ACC_COLS: TMEM columns per accumulator buffer (two buffers).
-template <int BLOCK_N>
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// Runs on warps EPI_WARP0 .. EPI_WARP0+7 of a CTA.  This CTA walks tile = blockIdx.x, += gridDim.x, ... < num_tiles.
+//
+// Warp w may only touch TMEM lanes [32*(w%4), +32): one accumulator row (= output pixel) per thread.  Wide tiles
+// (>= 128 columns) are split between two groups of 4 warps.  Per 128-byte chunk of a pixel's channels the warp
+// (optionally) TMA-loads the residual chunk into its private staging tile, tcgen05.ld's the accumulator, adds the
+// per-channel shift, packs to BF16, adds the residual and applies ReLU on packed BF16x2 (the same two roundings a BF16
+// torch pipeline performs), writes the row back into the (128B-swizzled, bank-conflict-free) staging tile and one lane
+// TMA-stores the 32-pixel x 128-byte box.  Global traffic is full-line bulk transfers; the LSU only sees shared memory.
+//
+// The epilogue is INSTRUCTION-ISSUE bound on the output-heavy layers (ncu: ~340 SASS instructions per 32 columns in the
+// first version, 60 % of all instructions of the kernel), so the hot path is kept minimal: the BN scale is folded into
+// the weights on the host (p.scale == NULL), the shift comes from a shared-memory table via 128-bit broadcast loads (with
+// ~224 KB of the SM carved out as shared memory there is next to no L1: per-element __ldg costs an L2 round trip),
+// residual add / ReLU run on packed pairs, swizzled staging offsets are precomputed.  Anything else (FP32 outputs,
+// unaligned views, explicit scale, LeakyReLU + residual) takes the general path below.
+template <int BLOCK_N, bool ONE_GROUP = false>
 __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorMap *tmap_y_p, const CUtensorMap *tmap_r_p, uint32_t tmem_base,
                                               uint64_t *tfull_bar, uint64_t *tempty_bar, uint64_t *res_bar, uint8_t *epi_stage,
-                                              int num_tiles, int warp, int lane)
+                                              float *s_shift, int num_tiles, int warp, int lane)
 {
     constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
     const CUtensorMap &tmap_y = *tmap_y_p;
     const CUtensorMap &tmap_r = *tmap_r_p;
-        // ===================== epilogue =====================
-        // Warp w may only touch TMEM lanes [32*(w%4), +32): one accumulator row (= output pixel) per thread.
-        // Wide tiles (>= 128 columns) are split between two groups of 4 warps.  Per 128-byte chunk of a row's
-        // channels the warp: (optionally) TMA-loads the residual chunk into its private staging tile, tcgen05.ld's
-        // the accumulator, applies scale/shift/residual/activation, writes the row back into the (128B-swizzled,
-        // bank-conflict-free) staging tile and one lane TMA-stores the 32-pixel x 128-byte box.  Global traffic is
-        // therefore full-line bulk transfers; the LSU only sees shared memory.  Views that TMA cannot address
-        // (channel stride or base not 16-byte aligned) take the direct per-thread path.
-        constexpr int GROUPS = BLOCK_N >= 128 ? 2 : 1;
-        constexpr int COLS = BLOCK_N / GROUPS;                 // columns per warp
-        constexpr int SUB = COLS < 32 ? COLS : 32;             // columns per tcgen05.ld
-        const int ew = warp - EPI_WARP0;
-        const int q = ew & 3, grp = ew >> 2;
-        if (grp < GROUPS) {
-            const int row = q * 32 + lane;                     // accumulator row = pixel within the tile
-            const int col0 = grp * COLS;
-            const int esz = p.y_f32 ? 4 : 2;
-            const int tch = 128 / esz;                         // columns per staging chunk (128 B per pixel)
-            const uint32_t stage = smem_u32(epi_stage + ew * EPI_STAGE_BYTES);
-            const uint32_t srow = stage + lane * 128;          // this thread's pixel row in the staging tile
-            const uint32_t rbar = smem_u32(res_bar + ew);
-            uint32_t rphase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            float slope = p.slope;
-            if (p.slope_ptr) slope = __ldg(p.slope_ptr);
-            const bool res_vec = p.res != nullptr && (p.ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
-                const int ho = th * p.TH + row / p.TW, wo = tw * p.TW + row % p.TW;
-                const bool valid = ho < p.Ho && wo < p.Wo;
-                const int64_t pix = ((int64_t)img * p.Ho + ho) * p.Wo + wo;
-                const int ctile = nt * BLOCK_N + col0;         // first output channel of this warp's columns
-                // coordinates of this warp's 32-pixel box (first pixel = row q*32 of the tile)
-                const int bx = tw * p.TW + (q * 32) % p.TW, by = th * p.TH + (q * 32) / p.TW;
-                const __nv_bfloat16 *rrow = (const __nv_bfloat16 *)p.res + pix * p.ldr + ctile;
-                bool waited = false;
-                for (int ck = 0; ck < COLS; ck += tch) {
-                    const bool chunk_on = ctile + ck < p.Cout;          // warp-uniform
-                    if (p.tma_out && lane == 0) {
-                        bulk_wait_read0();                               // previous store has drained the staging tile
-                        if (p.tma_res && chunk_on) {
-                            mbar_expect_tx(rbar, EPI_STAGE_BYTES);
-                            tma_load_4d(stage, &tmap_r, rbar, ctile + ck, bx, by, img);
-                        }
-                    }
-                    if (p.tma_out) __syncwarp();
-                    if (!waited) {
-                        mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
-                        tcgen05_fence_after();
-                        waited = true;
-                    }
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + col0 + ck;
-                    if (p.tma_res && chunk_on) {
-                        mbar_wait(rbar, rphase);
-                        rphase ^= 1;
-                    }
-                    const int nsub = (tch < COLS - ck ? tch : COLS - ck) / SUB;
-                    for (int si = 0; si < nsub; ++si) {
-                        uint32_t raw[SUB];
-                        if constexpr (SUB == 32) tmem_ld_32x32(taddr + si * SUB, raw);
-                        else if constexpr (SUB == 16) tmem_ld_32x16(taddr + si * SUB, raw);
-                        tmem_ld_wait();
-                        const int cbase = ctile + ck + si * SUB;
-                        if (!chunk_on) continue;
-                        float v[SUB];
+    constexpr int GROUPS = (BLOCK_N >= 128 && !ONE_GROUP) ? 2 : 1;   // ONE_GROUP: warps 8-11 have another job
+    constexpr int COLS = BLOCK_N / GROUPS;                 // columns per warp
+    constexpr int SUB = COLS < 32 ? COLS : 32;             // columns per tcgen05.ld
+    const int ew = warp - EPI_WARP0;
+    const int q = ew & 3, grp = ew >> 2;
+    if (grp >= GROUPS) return;
+    const int row = q * 32 + lane;                     // accumulator row = pixel within the tile
+    const int col0 = grp * COLS;
+    const int esz = p.y_f32 ? 4 : 2;
+    const int tch = 128 / esz;                         // columns per staging chunk (128 B per pixel)
+    const uint32_t stage = smem_u32(epi_stage + ew * EPI_STAGE_BYTES);
+    const uint32_t srow = stage + lane * 128;          // this thread's pixel row in the staging tile
+    uint32_t off[8];                                   // swizzled address of each 16-byte chunk of that row
 #pragma unroll
-                        for (int j = 0; j < SUB; ++j) v[j] = __uint_as_float(raw[j]);
+    for (int c = 0; c < 8; ++c) off[c] = srow + ((c ^ (lane & 7)) << 4);
+    const uint32_t rbar = smem_u32(res_bar + ew);
+    uint32_t rphase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    float slope = p.slope;
+    if (p.slope_ptr) slope = __ldg(p.slope_ptr);
+    const int act = p.act;
+    const bool res_vec = p.res != nullptr && (p.ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0;
+    // packed-BF16 fast path: TMA staging, BF16 output, no explicit scale, residual (if any) staged by TMA
+    const bool fast = SUB == 32 && p.tma_out && !p.y_f32 && p.scale == nullptr && (p.res == nullptr || p.tma_res) &&
+                      !(act == HN_ACT_LEAKY && p.res != nullptr);
+    float *tab = s_shift + col0;                       // this group's per-channel shift table
+    const uint32_t tab_addr = smem_u32(tab);
+    int loaded_ctile = -1;
+    long long ew_tfull = 0, ew_bulk = 0, ew_res = 0;
+    (void)ew_tfull; (void)ew_bulk; (void)ew_res;
+#ifdef HN_PROFILE_ROLES
+    const long long epi_t0 = clock64();
+#endif
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
+        const int ho = th * p.TH + row / p.TW, wo = tw * p.TW + row % p.TW;
+        const bool valid = ho < p.Ho && wo < p.Wo;
+        const int64_t pix = ((int64_t)img * p.Ho + ho) * p.Wo + wo;
+        const int ctile = nt * BLOCK_N + col0;         // first output channel of this warp's columns
+        // coordinates of this warp's 32-pixel box (first pixel = row q*32 of the tile)
+        const int bx = tw * p.TW + (q * 32) % p.TW, by = th * p.TH + (q * 32) / p.TW;
+        const __nv_bfloat16 *rrow = (const __nv_bfloat16 *)p.res + pix * p.ldr + ctile;
+        if (p.shift && ctile != loaded_ctile) {        // same decision in all 4 warps of the group
+            if (loaded_ctile >= 0) named_bar_sync(1 + grp, 128);          // everybody is done with the old table
+            if (q == 0)
+                for (int e = lane; e < COLS; e += 32) tab[e] = ctile + e < p.Cout ? __ldg(p.shift + ctile + e) : 0.f;
+            named_bar_sync(1 + grp, 128);
+            loaded_ctile = ctile;
+        }
+        bool waited = false;
+        for (int ck = 0; ck < COLS; ck += tch) {
+            const bool chunk_on = ctile + ck < p.Cout;          // warp-uniform
+            if (p.tma_out && lane == 0) {
+                { HN_PROF_T0(); bulk_wait_read0(); HN_PROF_ADD(ew_bulk); }   // previous store has drained the staging tile
+                if (p.tma_res && chunk_on) {
+                    mbar_expect_tx(rbar, EPI_STAGE_BYTES);
+                    tma_load_4d(stage, &tmap_r, rbar, ctile + ck, bx, by, img);
+                }
+            }
+            if (p.tma_out) __syncwarp();
+            if (!waited) {
+                { HN_PROF_T0(); mbar_wait(smem_u32(tfull_bar + acc), acc_phase); HN_PROF_ADD(ew_tfull); }
+                tcgen05_fence_after();
+                waited = true;
+            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + col0 + ck;
+            if (p.tma_res && chunk_on) {
+                { HN_PROF_T0(); mbar_wait(rbar, rphase); HN_PROF_ADD(ew_res); }
+                rphase ^= 1;
+            }
+            const int nsub = (tch < COLS - ck ? tch : COLS - ck) / SUB;
+            for (int si = 0; si < nsub; ++si) {
+                uint32_t raw[SUB];
+                if constexpr (SUB == 32) tmem_ld_32x32(taddr + si * SUB, raw);
+                else if constexpr (SUB == 16) tmem_ld_32x16(taddr + si * SUB, raw);
+                tmem_ld_wait();
+                const int cbase = ctile + ck + si * SUB;
+                if (chunk_on) {
+                    float v[SUB];
+#pragma unroll
+                    for (int j = 0; j < SUB; ++j) v[j] = __uint_as_float(raw[j]);
+                    if (fast) {
+                        if constexpr (SUB == 32) {
+                            if (p.shift) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const uint4 t4 = lds128(tab_addr + (ck + si * SUB + 4 * j) * 4);
+                                    v[4 * j] += __uint_as_float(t4.x);
+                                    v[4 * j + 1] += __uint_as_float(t4.y);
+                                    v[4 * j + 2] += __uint_as_float(t4.z);
+                                    v[4 * j + 3] += __uint_as_float(t4.w);
+                                }
+                            }
+                            if (act == HN_ACT_LEAKY) {
+#pragma unroll
+                                for (int j = 0; j < SUB; ++j) v[j] = fmaxf(v[j], 0.f) + slope * fminf(v[j], 0.f);
+                            }
+                            __nv_bfloat162 h[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                            if (p.res) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const uint4 rv = lds128(off[si * 4 + j]);
+                                    const __nv_bfloat162 *r2 = reinterpret_cast<const __nv_bfloat162 *>(&rv);
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) h[4 * j + i] = __hadd2(h[4 * j + i], r2[i]);
+                                }
+                            }
+                            if (act == HN_ACT_RELU) {
+                                const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) h[j] = __hmax2(h[j], z);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) sts128(off[si * 4 + j], *reinterpret_cast<const uint4 *>(&h[4 * j]));
+                        }
+                    } else {
+                        // ---------------- general path ----------------
                         const bool full = cbase + SUB <= p.Cout;
                         if (p.scale) {
-                            if (full) {   // warp-uniform 16-byte broadcast loads
 #pragma unroll
-                                for (int j = 0; j < SUB; j += 4) {
-                                    const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + cbase + j));
-                                    const float4 sh = __ldg(reinterpret_cast<const float4 *>(p.shift + cbase + j));
-                                    v[j] = fmaf(v[j], sc.x, sh.x);
-                                    v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
-                                    v[j + 2] = fmaf(v[j + 2], sc.z, sh.z);
-                                    v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
-                                }
-                            } else {
+                            for (int j = 0; j < SUB; ++j)
+                                if (cbase + j < p.Cout) v[j] *= __ldg(p.scale + cbase + j);
+                        }
+                        if (p.shift) {
 #pragma unroll
-                                for (int j = 0; j < SUB; ++j)
-                                    if (cbase + j < p.Cout) v[j] = fmaf(v[j], __ldg(p.scale + cbase + j), __ldg(p.shift + cbase + j));
-                            }
+                            for (int j = 0; j < SUB; ++j) v[j] += tab[ck + si * SUB + j];
                         }
                         if (p.res) {
                             if (p.tma_res) {          // residual chunk sits in the staging tile (BF16, swizzled)
 #pragma unroll
                                 for (int j = 0; j < SUB / 8; ++j) {
-                                    const uint4 rv = lds128(srow + ((((si * SUB) >> 3) + j) ^ (lane & 7)) * 16);
+                                    const uint4 rv = lds128(off[((si * SUB) >> 3) + j]);
                                     const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&rv);
 #pragma unroll
                                     for (int i = 0; i < 4; ++i) {
@@ -161,14 +220,14 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
                             }
                         }
 #pragma unroll
-                        for (int j = 0; j < SUB; ++j) v[j] = apply_act(v[j], p.act, slope);
+                        for (int j = 0; j < SUB; ++j) v[j] = apply_act(v[j], act, slope);
                         if (p.tma_out) {
                             if (p.y_f32) {
 #pragma unroll
                                 for (int j = 0; j < SUB / 4; ++j) {
                                     uint4 o = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
                                                          __float_as_uint(v[4 * j + 3]));
-                                    sts128(srow + ((((si * SUB) >> 2) + j) ^ (lane & 7)) * 16, o);
+                                    sts128(off[((si * SUB) >> 2) + j], o);
                                 }
                             } else {
 #pragma unroll
@@ -177,7 +236,7 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
                                     __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&o);
 #pragma unroll
                                     for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
-                                    sts128(srow + ((((si * SUB) >> 3) + j) ^ (lane & 7)) * 16, o);
+                                    sts128(off[((si * SUB) >> 3) + j], o);
                                 }
                             }
                         } else if (valid) {
@@ -209,23 +268,29 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
                             }
                         }
                     }
-                    if (p.tma_out) {
-                        fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0 && chunk_on) {
-                            tma_store_4d(&tmap_y, stage, ctile + ck, bx, by, img);
-                            bulk_commit();
-                        }
-                    }
                 }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
             }
-            if (p.tma_out && lane == 0) bulk_wait_read0();    // staging tile must outlive the last bulk store
+            if (p.tma_out) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0 && chunk_on) {
+                    tma_store_4d(&tmap_y, stage, ctile + ck, bx, by, img);
+                    bulk_commit();
+                }
+            }
         }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+    }
+    if (p.tma_out && lane == 0) bulk_wait_read0();    // staging tile must outlive the last bulk store
+#ifdef HN_PROFILE_ROLES
+    if (ew == 0 && lane == 0) {
+        HN_PROF_FLUSH(5, ew_tfull); HN_PROF_FLUSH(6, ew_bulk); HN_PROF_FLUSH(7, ew_res); HN_PROF_FLUSH(8, clock64() - epi_t0);
+    }
+#endif
 }
 
 }  // namespace hn

@@ -6,6 +6,18 @@
 
 namespace hn {
 
+// Role-level cycle accounting for tuning (compiled in only with -DHN_PROFILE_ROLES; see scripts/profile_roles.py)
+#ifdef HN_PROFILE_ROLES
+extern __device__ unsigned long long g_role_cycles[16];
+#define HN_PROF_T0() long long _pt0 = clock64()
+#define HN_PROF_ADD(acc) (acc) += clock64() - _pt0
+#define HN_PROF_FLUSH(slot, v) atomicAdd(&g_role_cycles[slot], (unsigned long long)(v))
+#else
+#define HN_PROF_T0()
+#define HN_PROF_ADD(acc)
+#define HN_PROF_FLUSH(slot, v)
+#endif
+
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -19,6 +19,7 @@ _HN_DTYPE = {torch.float32: HN_F32, torch.bfloat16: HN_BF16}
 
 DEFAULT_PRECISION = os.environ.get("HEATNET_B200_PRECISION", "bf16")
 BN_TRAIN_RAW_FP32 = os.environ.get("HEATNET_B200_BN_RAW_FP32", "1") != "0"
+UPCONV_MIN_CIN = int(os.environ.get("HN_UPCONV_MIN_CIN", "512"))
 
 # number of libheatnet_b200 kernels enqueued by this process (bench.py reports it as gpu_launches)
 launch_count = 0
@@ -316,6 +317,33 @@ def packed_weight(conv: torch.nn.Conv2d, dtype: torch.dtype) -> torch.Tensor:
     return dst
 
 
+def packed_weight_folded(conv: torch.nn.Conv2d, bn: Optional[torch.nn.BatchNorm2d], dtype: torch.dtype):
+    """(pack, shift) for y = conv(x) folded with BatchNorm2d(eval) and the conv bias: the BN scale is multiplied into
+    the filter rows before rounding to the compute dtype (what inference engines do), so the conv epilogue only adds a
+    per-channel shift.  Cached on the versions of every tensor involved."""
+    lib = _lib.load()
+    scale, shift = folded_affine(conv, bn)
+    if bn is None:
+        return packed_weight(conv, dtype), shift
+    cache = conv.__dict__.setdefault("_hn_wcache", {})
+    key = ("folded", dtype, conv.weight.device)
+    ver = _versions(conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1], shift
+    w = conv.weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    cout, cin, r, s = w.shape
+    hdt = _HN_DTYPE[dtype]
+    cout_pad, kpad = lib.hn_conv_cout_pad(cout, hdt), lib.hn_conv_kpad(cin, r, s)
+    dst = torch.empty((cout_pad, kpad), dtype=dtype, device=w.device)
+    _lib.check(lib.hn_pack_weight_scaled(w.data_ptr(), scale.data_ptr(), dst.data_ptr(), hdt, cout, cin, r, s, cout_pad, kpad, _stream()))
+    _count()
+    cache[key] = (ver, dst)
+    return dst, shift
+
+
 def packed_weight_slice(conv: torch.nn.Conv2d, c0: int, c1: int, dtype: torch.dtype) -> torch.Tensor:
     """Pack of the input-channel slice [c0, c1) of a conv weight (the per-prior blocks of the PSP bottleneck)."""
     lib = _lib.load()
@@ -361,6 +389,7 @@ def folded_affine(conv: torch.nn.Conv2d, bn: Optional[torch.nn.BatchNorm2d]):
     else:
         rc = _lib.load().hn_bn_fold(None, None, None, None, p(bias), BN_EPS_DEFAULT, scale.data_ptr(), shift.data_ptr(),
                                     cch, _stream())
+        scale = None                       # bias only: no scale vector for the epilogue
     _lib.check(rc)
     _count()
     cache["fold"] = (ver, scale, shift)
@@ -493,7 +522,13 @@ def conv_bn_act(x: Act, conv, bn, act=ACT_NONE, slope=0.0, slope_ptr=None, resid
         bn_training = bn is not None and (bn.training or bn.running_mean is None)
     if bn is None or not bn_training:
         scale, shift = folded_affine(conv, bn)
-        y = conv2d(x, conv, scale, shift, residual, act, slope, slope_ptr, out)
+        if bn is not None and x.dtype == torch.bfloat16:
+            # BF16 engine: BN scale folded into the packed filter, the epilogue only adds the shift
+            wp, shift = packed_weight_folded(conv, bn, x.dtype)
+            y = conv2d_raw(x, wp, conv.out_channels, conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0], None, shift,
+                           residual, act, slope, slope_ptr, out)
+        else:
+            y = conv2d(x, conv, scale, shift, residual, act, slope, slope_ptr, out)
         if tape is not None:
             _record_conv_affine(tape, x, conv, bn, scale, y, residual, act, slope, slope_ptr)
         return y
@@ -831,12 +866,13 @@ def bilinear_sum(xs: Sequence[Act], h: int, w: int) -> Act:
     return out
 
 
-def upconv3x3(x: Act, conv: torch.nn.Conv2d, scale=None, shift=None, act=ACT_NONE, slope=0.0, slope_ptr=None, out_dtype=None) -> Act:
+def upconv3x3(x: Act, conv: torch.nn.Conv2d, scale=None, shift=None, act=ACT_NONE, slope=0.0, slope_ptr=None, out_dtype=None,
+              wp=None) -> Act:
     """act(conv3x3(bilinear_2x(x)) * scale + shift) in ONE kernel: the upsampled tensor is never written to HBM."""
     lib = _lib.load()
     assert conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1) and conv.dilation == (1, 1)
     out = new_act(x.n, 2 * x.h, 2 * x.w, conv.out_channels, out_dtype or x.dtype, x.buf.device)
-    wp = packed_weight(conv, x.dtype)
+    wp = wp if wp is not None else packed_weight(conv, x.dtype)
     cv = HnConv(conv.out_channels, 3, 3, 1, 1, 1)
     ep = _epilogue(scale, shift, None, act, slope, slope_ptr)
     timing = conv_timer is not None
@@ -852,5 +888,6 @@ def upconv3x3(x: Act, conv: torch.nn.Conv2d, scale=None, shift=None, act=ACT_NON
 
 
 def upconv3x3_ok(x: Act, conv: torch.nn.Conv2d) -> bool:
+    # the halo-patch producers are CUDA-core work: hidden behind the tensor pipe only when a tile has many k-blocks
     return (x.dtype == torch.bfloat16 and x.c % 64 == 0 and x.ld % 8 == 0 and conv.out_channels >= 33
-            and os.environ.get("HN_NO_UPCONV") is None)
+            and x.c >= UPCONV_MIN_CIN)

@@ -105,8 +105,8 @@ class PSPUpsample(_KernelModule):
         if E.current_tape is None and E.upconv3x3_ok(x, conv):
             # inference / validation: upsample fused into the conv's operand producer (no 2x tensor in HBM)
             if not bn_train:
-                scale, shift = E.folded_affine(conv, bn)
-                return E.upconv3x3(x, conv, scale, shift, ACT_LEAKY, slope_ptr=prelu.weight)
+                wp, shift = E.packed_weight_folded(conv, bn, x.dtype)
+                return E.upconv3x3(x, conv, None, shift, ACT_LEAKY, slope_ptr=prelu.weight, wp=wp)
             scale, shift = E.folded_affine(conv, None)
             raw = E.upconv3x3(x, conv, scale, shift, out_dtype=torch.float32)
             bscale, bshift, _, _ = E.batchnorm_train_affine(raw, bn)

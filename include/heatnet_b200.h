@@ -47,7 +47,7 @@ typedef struct hn_tensor {
  * BatchNorm2d(eval) / bias / `out += residual` / ReLU / PReLU / LeakyReLU launches of
  * cm/models/extractors.py:85-101, cm/models/pspnet.py:25,32-34, cm/discriminator_model.py:51-59. */
 typedef struct hn_epilogue {
-    const float *scale;     /* [Cout] or NULL (1) */
+    const float *scale;     /* [Cout] or NULL (1); the BF16 engine is fastest with scale == NULL (fold it: hn_pack_weight_scaled) */
     const float *shift;     /* [Cout] or NULL (0) */
     const void *residual;   /* NHWC view with the output's dtype/shape, or NULL */
     int32_t residual_ld;
@@ -68,6 +68,9 @@ const char *hn_last_error(void);
 int hn_version(void);
 /* SM count / cc of the current device; fails (HN_ERR_CUDA) without a usable sm_100 device. */
 int hn_device_check(void);
+/* tuning aid: per-role wait-cycle counters of the tcgen05 conv kernel; returns 0 (all zeros) unless the library was built
+ * with -DHN_PROFILE_ROLES (scripts/profile_roles.py builds such a copy) */
+int hn_prof_read(unsigned long long *out16, int reset);
 
 /* ---- layout + parameter preparation (no reference counterpart: the reference keeps NCHW/OIHW) ---- */
 /* NCHW FP32 (user tensors) -> NHWC view. */
@@ -78,6 +81,10 @@ int hn_nhwc_to_nchw(const hn_tensor *src, float *dst, void *stream);
  * dtype HN_BF16 (tensor-core path) or HN_F32 (FP32 parity path). */
 int hn_pack_weight(const float *w_oihw, void *dst, int32_t dtype, int32_t cout, int32_t cin, int32_t r, int32_t s,
                    int32_t cout_pad, int32_t kpad, void *stream);
+/* same, with every output-channel row multiplied by row_scale[o] first: BatchNorm2d(eval) folded into the filter, which
+ * leaves only the per-channel shift for the conv epilogue (row_scale == NULL: plain pack) */
+int hn_pack_weight_scaled(const float *w_oihw, const float *row_scale, void *dst, int32_t dtype, int32_t cout, int32_t cin,
+                          int32_t r, int32_t s, int32_t cout_pad, int32_t kpad, void *stream);
 /* BatchNorm2d(eval) + conv bias folded to per-channel scale/shift:
  * scale = gamma/sqrt(var+eps), shift = beta + (bias - mean)*scale.  gamma==NULL => plain bias. */
 int hn_bn_fold(const float *gamma, const float *beta, const float *mean, const float *var, const float *bias,
