@@ -470,29 +470,28 @@ __global__ void __launch_bounds__(256) bilinear_up2_kernel(const T *__restrict__
     T *o1 = o0 + (int64_t)Wo * ldy;
     // output row 2y   : src = y - 0.25 -> rows (y-1, y), ly = 0.75 (clamped to row 0: ly = 0)
     // output row 2y+1 : src = y + 0.25 -> rows (y, y+1), ly = 0.25
-    const float ly0 = yi > 0 ? 0.75f : 0.f, ly1 = 0.25f;
+    const float ly0 = yi > 0 ? 0.75f : 1.f, ly1 = 0.25f;   // yi == 0: all weight on tap 1 (= row 0 itself; tap 0 is the same clamped row)
     const int items = W * ncv;
     for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < items; i += gridDim.y * blockDim.x) {
         const int xi = i / ncv, c = (i - xi * ncv) * 8;
         const int xm = xi > 0 ? xi - 1 : 0, xp = xi < W - 1 ? xi + 1 : W - 1;
-        const float lx0 = xi > 0 ? 0.75f : 0.f, lx1 = 0.25f;
+        const float lx0 = xi > 0 ? 0.75f : 1.f, lx1 = 0.25f;
         float a[3][3][8];
         Vec8<T>::load(rm + (int64_t)xm * ldx + c, a[0][0]); Vec8<T>::load(rm + (int64_t)xi * ldx + c, a[0][1]); Vec8<T>::load(rm + (int64_t)xp * ldx + c, a[0][2]);
         Vec8<T>::load(r0 + (int64_t)xm * ldx + c, a[1][0]); Vec8<T>::load(r0 + (int64_t)xi * ldx + c, a[1][1]); Vec8<T>::load(r0 + (int64_t)xp * ldx + c, a[1][2]);
         Vec8<T>::load(rp + (int64_t)xm * ldx + c, a[2][0]); Vec8<T>::load(rp + (int64_t)xi * ldx + c, a[2][1]); Vec8<T>::load(rp + (int64_t)xp * ldx + c, a[2][2]);
         float o[8];
+        // rows/cols are already clamped (ym/yp, xm/xp), so the tap pairs are static: (0,1) for the even output and (1,2) for
+        // the odd one; at the low border the weight of the second tap is 0 and both taps are the same pixel
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy) {
-            // generic kernel: y0 = floor(src), y1 = y0 + 1 (clamped); for dy = 0 and yi == 0 both are row 0
-            const int ra = dy == 0 ? (yi > 0 ? 0 : 1) : 1, rb = dy == 0 ? 1 : 2;
             const float ly = dy == 0 ? ly0 : ly1, hy = 1.f - ly;
 #pragma unroll
             for (int dx = 0; dx < 2; ++dx) {
-                const int ca = dx == 0 ? (xi > 0 ? 0 : 1) : 1, cb = dx == 0 ? 1 : 2;
                 const float lx = dx == 0 ? lx0 : lx1, hx = 1.f - lx;
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    o[j] = hy * (hx * a[ra][ca][j] + lx * a[ra][cb][j]) + ly * (hx * a[rb][ca][j] + lx * a[rb][cb][j]);
+                    o[j] = hy * (hx * a[dy][dx][j] + lx * a[dy][dx + 1][j]) + ly * (hx * a[dy + 1][dx][j] + lx * a[dy + 1][dx + 1][j]);
                 Vec8<T>::store((dy == 0 ? o0 : o1) + (int64_t)(2 * xi + dx) * ldy + c, o);
             }
         }

@@ -213,9 +213,67 @@ __global__ void __launch_bounds__(256) im2col_bf16_kernel(const __nv_bfloat16 *_
     }
 }
 
+// Small-Cin gather (the 7x7 stride-2 stems, Cin = 3 / 1 / 4; the critic on 13-channel logits): a CTA stages the R input rows
+// that 64 consecutive output pixels of one output row need in shared memory (coalesced, zero padded), then assembles the
+// K-major rows from shared memory and writes them as 16-byte chunks.  grid = (ceil(Wo/64), N*Ho).
+constexpr int IM2COL_TW = 64;
+__global__ void __launch_bounds__(256) im2col_smallc_kernel(const __nv_bfloat16 *__restrict__ x, int ldx, int N, int H, int W, int C, int Ho,
+                                                            int Wo, int R, int S, int stride, int pad, int dil, int kpad,
+                                                            __nv_bfloat16 *__restrict__ a)
+{
+    extern __shared__ __nv_bfloat16 patch[];   // [R][ncols][C]
+    const int row = blockIdx.y;
+    const int n = row / Ho, ho = row - n * Ho;
+    const int wo0 = blockIdx.x * IM2COL_TW;
+    const int ncols = (IM2COL_TW - 1) * stride + (S - 1) * dil + 1;
+    const int wi0 = wo0 * stride - pad;
+    const __nv_bfloat16 *xin = x + (int64_t)n * H * W * ldx;
+    const int per_row = ncols * C;
+    for (int i = threadIdx.x; i < R * per_row; i += blockDim.x) {
+        const int r = i / per_row, rem = i - r * per_row;
+        const int col = rem / C, c = rem - col * C;
+        const int hi = ho * stride - pad + r * dil, wi = wi0 + col;
+        __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = xin[((int64_t)hi * W + wi) * ldx + c];
+        patch[i] = v;
+    }
+    __syncthreads();
+    const int k8n = kpad / 8;
+    const int K = R * S * C;
+    const int npx = min(IM2COL_TW, Wo - wo0);
+    __nv_bfloat16 *arow = a + ((int64_t)row * Wo + wo0) * kpad;
+    for (int i = threadIdx.x; i < npx * k8n; i += blockDim.x) {
+        const int pl = i / k8n, k0 = (i - pl * k8n) * 8;
+        uint4 out = make_uint4(0, 0, 0, 0);
+        __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(&out);
+        int tap = k0 / C, c = k0 - tap * C;
+        int r = tap / S, s = tap - r * S;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (k0 + j < K) o[j] = patch[(r * ncols + pl * stride + s * dil) * C + c];
+            if (++c == C) {
+                c = 0;
+                if (++s == S) { s = 0; ++r; }
+            }
+        }
+        *reinterpret_cast<uint4 *>(arow + (int64_t)pl * kpad + k0) = out;
+    }
+}
+
 int im2col_bf16(const hn_tensor *x, const hn_conv *cv, int Ho, int Wo, int kpad, void *ws, cudaStream_t st)
 {
     HN_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 127) == 0, "im2col: workspace must be 128-byte aligned");
+    if (x->c < 8 || x->c % 8 != 0) {
+        const int ncols = (IM2COL_TW - 1) * cv->stride + (cv->s - 1) * cv->dil + 1;
+        const size_t smem = (size_t)cv->r * ncols * x->c * 2;
+        if (smem <= 48 * 1024 && (int64_t)x->n * Ho <= 65535) {
+            dim3 grid((unsigned)cdiv(Wo, IM2COL_TW), (unsigned)(x->n * Ho));
+            im2col_smallc_kernel<<<grid, 256, smem, st>>>((const __nv_bfloat16 *)x->ptr, x->ld, x->n, x->h, x->w, x->c, Ho, Wo, cv->r, cv->s,
+                                                       cv->stride, cv->pad, cv->dil, kpad, (__nv_bfloat16 *)ws);
+            HN_LAUNCH_CHECK();
+            return HN_OK;
+        }
+    }
     int64_t chunks = cdiv((int64_t)Wo * (kpad / 8), 1024);
     dim3 grid((unsigned)(x->n * Ho), (unsigned)(chunks < 1 ? 1 : (chunks > 65535 ? 65535 : chunks)));
     im2col_bf16_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x->ptr, x->ld, x->n, x->h, x->w, x->c, Ho, Wo, cv->r, cv->s, cv->stride,
