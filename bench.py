@@ -455,10 +455,18 @@ def main():
         total_flops = flops_img * B
         achieved = total_flops / (conv_ms / 1000.0) / 1e12
         peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])       # kernel timed inside a long step
-        roofline = {"kernel": "conv_tc_kernel (tcgen05 implicit GEMM; %d launches/step incl. im2col gathers)" % n_conv,
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            wl = tj.get("workload", {})
+            if (wl.get("batch"), wl.get("height"), wl.get("width"), wl.get("precision")) == (B, H, W, args.precision):
+                traffic = tj["conv_dram_bytes_per_step"]        # ncu dram__bytes_read+write summed over one step's conv launches
+        roofline = {"kernel": "conv_tc_kernel / conv_halo_kernel (tcgen05 implicit GEMM; %d launches/step incl. im2col gathers)" % n_conv,
                     "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "frac_of_burst_peak": achieved / peaks["bf16_tflops"], "peak_source": peak_src + " (sustained cuBLAS bf16)",
-                    "traffic": None, "conv_ms_per_step": conv_ms, "step_ms": ms_max / args.steps,
+                    "traffic": traffic, "traffic_unit": "bytes of DRAM traffic per step, all conv launches (ncu, profiles/r1_conv_step_metrics.csv)",
+                    "conv_ms_per_step": conv_ms, "step_ms": ms_max / args.steps,
                     "conv_share_of_step": conv_ms / (ms_max / args.steps), "algorithmic_gflop_per_image": flops_img / 1e9,
                     "other_ops_ms_per_step": {k: round(v, 3) for k, v in sorted(other.items(), key=lambda kv: -kv[1])},
                     "note": "achieved = the reference's algorithmic conv FLOPs / conv kernel time; on this inference path the PSP head "
