@@ -47,6 +47,9 @@ SIGNATURES = {
     "hn_conv2d_workspace_bytes": (_I64, [_T, _CV]),
     "hn_conv2d_fwd": (C.c_int, [_T, _P, _CV, _E, _T, _P, _I64, _P]),
     "hn_upconv3x3_fwd": (C.c_int, [_T, _P, _CV, _E, _T, _P]),
+    "hn_stem_pad": (C.c_int, [_T, _T, _P]),
+    "hn_pack_stem_weight": (C.c_int, [_P, _P, _P, _I32, _I32, _P]),
+    "hn_stem7x7s2_fwd": (C.c_int, [_T, _P, _I32, _E, _T, _P]),
     "hn_maxpool3x3s2_fwd": (C.c_int, [_T, _T, _P]),
     "hn_pyramid_pool_workspace_bytes": (_I64, [_T, C.POINTER(_I32), _I32]),
     "hn_pyramid_pool_fwd": (C.c_int, [_T, C.POINTER(_I32), _I32, _P, _P, _I64, _P]),

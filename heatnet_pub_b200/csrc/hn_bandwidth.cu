@@ -857,3 +857,75 @@ extern "C" int hn_bilinear_sum_fwd(const hn_tensor *xs, int32_t nsrc, const hn_t
     HN_LAUNCH_CHECK();
     return HN_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ stem preparation
+namespace hn {
+// NHWC (C <= 4, any channel stride) -> zero-bordered 4-channel image [N][Hp][Wp][4] BF16 (border 3 = conv padding)
+template <typename T>
+__global__ void __launch_bounds__(256) stem_pad_kernel(const T *__restrict__ x, int ldx, int N, int H, int W, int C, __nv_bfloat16 *__restrict__ dst,
+                                                       int Hp, int Wp)
+{
+    const int row = blockIdx.x;          // n*Hp + hp
+    const int n = row / Hp, hp = row - n * Hp;
+    const int hi = hp - 3;
+    for (int wp = blockIdx.y * blockDim.x + threadIdx.x; wp < Wp; wp += gridDim.y * blockDim.x) {
+        const int wi = wp - 3;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
+            const T *s = x + (((int64_t)n * H + hi) * W + wi) * ldx;
+            for (int c = 0; c < C; ++c) v[c] = to_f32<T>(s[c]);
+        }
+        uint2 o;
+        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&o);
+        h[0] = __floats2bfloat162_rn(v[0], v[1]);
+        h[1] = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2 *>(dst + ((int64_t)row * Wp + wp) * 4) = o;
+    }
+}
+// OIHW FP32 [cout][cin<=4][7][7] -> [cout_pad=64][7][8][4] BF16 (zero for s = 7 and c >= cin), optional per-row scale
+__global__ void pack_stem_weight_kernel(const float *__restrict__ w, const float *__restrict__ row_scale, __nv_bfloat16 *__restrict__ dst, int cout,
+                                        int cin)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 64 * 224) return;
+    const int o = i / 224, k = i - o * 224;
+    const int r = k / 32, s = (k % 32) / 4, c = k % 4;
+    float v = 0.f;
+    if (o < cout && s < 7 && c < cin) {
+        v = w[(((int64_t)o * cin + c) * 7 + r) * 7 + s];
+        if (row_scale) v *= row_scale[o];
+    }
+    dst[i] = __float2bfloat16_rn(v);
+}
+int conv_stem_tc(const hn_tensor *xpad, const void *w, int cout, const hn_epilogue *ep, const hn_tensor *y, cudaStream_t st);
+}  // namespace hn
+
+extern "C" int hn_stem_pad(const hn_tensor *x, const hn_tensor *xpad, void *stream)
+{
+    HN_CHECK_ARG(x && xpad && x->ptr && xpad->ptr, "hn_stem_pad: null pointer");
+    HN_CHECK_ARG(x->c >= 1 && x->c <= 4 && xpad->c == 4 && xpad->ld == 4 && xpad->dtype == HN_BF16 && xpad->n == x->n, "hn_stem_pad: bad views");
+    HN_CHECK_ARG(xpad->h >= x->h + 6 && xpad->w >= x->w + 6, "hn_stem_pad: padded image must be at least (H+6)x(W+6)");
+    dim3 grid((unsigned)(xpad->n * xpad->h), (unsigned)hn::cdiv(xpad->w, 1024));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x->dtype == HN_BF16)
+        hn::stem_pad_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x->ptr, x->ld, x->n, x->h, x->w, x->c, (__nv_bfloat16 *)xpad->ptr, xpad->h, xpad->w);
+    else
+        hn::stem_pad_kernel<float><<<grid, 256, 0, st>>>((const float *)x->ptr, x->ld, x->n, x->h, x->w, x->c, (__nv_bfloat16 *)xpad->ptr, xpad->h, xpad->w);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_pack_stem_weight(const float *w_oihw, const float *row_scale, void *dst, int32_t cout, int32_t cin, void *stream)
+{
+    HN_CHECK_ARG(w_oihw && dst && cout >= 1 && cout <= 64 && cin >= 1 && cin <= 4, "hn_pack_stem_weight: 7x7 filter with Cout <= 64, Cin <= 4");
+    hn::pack_stem_weight_kernel<<<(64 * 224 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_oihw, row_scale, (__nv_bfloat16 *)dst, cout, cin);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_stem7x7s2_fwd(const hn_tensor *xpad, const void *w_packed, int32_t cout, const hn_epilogue *ep, const hn_tensor *y, void *stream)
+{
+    HN_CHECK_ARG(xpad && w_packed && ep && y && xpad->ptr && y->ptr, "hn_stem7x7s2_fwd: null pointer");
+    HN_CHECK_ARG(y->n == xpad->n && y->c == cout, "hn_stem7x7s2_fwd: output view mismatch");
+    return hn::conv_stem_tc(xpad, w_packed, cout, ep, y, (cudaStream_t)stream);
+}

@@ -25,19 +25,20 @@
 namespace hn {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;   // 64 BF16 = 128 B = one swizzle-128B row
+constexpr int BLOCK_K = 64;   // 64 BF16 = 128 B = one swizzle-128B row (the stem variant uses 32 = one swizzle-64B row)
 constexpr int UMMA_K = 16;
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int NUM_THREADS = 384;   // 4 control warps + 8 epilogue warps
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int BK = BLOCK_K>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_r, const TcParams p)
 {
-    constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+    constexpr int A_STAGE_BYTES = BLOCK_M * BK * 2;
+    constexpr int B_STAGE_BYTES = BLOCK_N * BK * 2;
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static_assert(A_STAGE_BYTES % 1024 == 0 && B_STAGE_BYTES % 1024 == 0, "stage tiles must keep 1024-byte alignment");
     constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;   // columns per accumulator buffer
     constexpr int TMEM_COLS = 2 * ACC_COLS;                   // power of two >= 32
     constexpr uint32_t IDESC = make_idesc_bf16(BLOCK_M, BLOCK_N);
@@ -97,7 +98,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 ++ntl;
                 const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
                 const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
-                const int w_base = tw * p.TW - p.pad, h_base = th * p.TH - p.pad;
+                const int w_base = tw * p.TW - p.pad, h_base = th * p.TH * p.hmul - p.pad;
                 int kb = 0;
                 for (int r = 0; r < p.R; ++r)
                     for (int s = 0; s < p.S; ++s)
@@ -106,8 +107,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             const uint32_t fb = smem_u32(full_bar + stage);
                             mbar_expect_tx(fb, STAGE_BYTES);
                             const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                            tma_load_4d(sa, &tmap_a, fb, cb * BLOCK_K, w_base + s * p.dil, h_base + r * p.dil, img);
-                            tma_load_2d(sa + A_STAGE_BYTES, &tmap_b, fb, kb * BLOCK_K, nt * BLOCK_N);
+                            tma_load_4d(sa, &tmap_a, fb, cb * BK, w_base + s * p.dil, h_base + r * p.dil, img);
+                            tma_load_2d(sa + A_STAGE_BYTES, &tmap_b, fb, kb * BK, nt * BLOCK_N);
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
             }
@@ -136,10 +137,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     { HN_PROF_T0(); mbar_wait(smem_u32(full_bar + stage), phase); HN_PROF_ADD(mw_full); }
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint64_t adesc = make_kmajor_sw128_desc(sa);
-                    const uint64_t bdesc = make_kmajor_sw128_desc(sa + A_STAGE_BYTES);
+                    const uint64_t adesc = make_kmajor_desc(sa, BK * 2);
+                    const uint64_t bdesc = make_kmajor_desc(sa + A_STAGE_BYTES, BK * 2);
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance 16 BF16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
                         umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
                     }
@@ -301,7 +302,7 @@ static PFN_encodeTiled get_encode()
 
 // BF16 tensor map over up to 4 dims (innermost first), 128B swizzle, zero OOB fill
 int make_tmap(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box,
-              CUtensorMapDataType dtype)
+              CUtensorMapDataType dtype, CUtensorMapSwizzle swizzle)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) {
@@ -318,7 +319,7 @@ int make_tmap(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, 
         if (i > 0) gs[i - 1] = strides_bytes[i];
     }
     CUresult r = enc(m, dtype, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u]", (int)r, rank,
@@ -342,20 +343,20 @@ int64_t conv2d_tc_workspace(const hn_tensor *x, const hn_conv *cv)
     return (int64_t)x->n * Ho * Wo * hn_conv_kpad(x->c, cv->r, cv->s) * 2;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int BK = BLOCK_K>
 static int launch_tc(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &ty, const CUtensorMap &tr, const TcParams &p,
                      int num_tiles, cudaStream_t st)
 {
-    constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * BLOCK_K * 2) + NUM_EPI_WARPS * EPI_STAGE_BYTES +
+    constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BK * 2 + BN * BK * 2) + NUM_EPI_WARPS * EPI_STAGE_BYTES +
                             (2 * STAGES + 4 + NUM_EPI_WARPS) * 8 + 16 + BN * 4 + 1024;
     static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
     static bool configured = false;
     if (!configured) {
-        HN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    conv_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, st>>>(ta, tb, ty, tr, p);
+    conv_tc_kernel<BN, STAGES, BK><<<grid, NUM_THREADS, smem, st>>>(ta, tb, ty, tr, p);
     HN_LAUNCH_CHECK();
     return HN_OK;
 }
@@ -372,6 +373,7 @@ int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn
     HN_CHECK_ARG((reinterpret_cast<uintptr_t>(w) & 15) == 0, "conv_tc: packed weights must be 16-byte aligned");
 
     TcParams p{};
+    p.hmul = 1;
     CUtensorMap ta, tb;
     const bool implicit = implicit_ok(x, cv);
     const bool flat = !implicit || (cv->r == 1 && cv->s == 1 && cv->pad == 0);
@@ -481,6 +483,70 @@ int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn
     }
     set_error("conv_tc: unsupported Cout tile %d", bn);
     return HN_ERR_ARG;
+}
+
+
+// ------------------------------------------------------------------------------------------------ 7x7 stride-2 stems
+// The stems (Cin = 3 / 1 / 4) without an im2col pass: the input is kept as a zero-bordered, 4-channel NHWC image
+// xpad[N][Hp][Wp][4] (border 3 = the conv padding).  The 8 pixels x 4 channels = 32 BF16 that one filter row touches for
+// output pixel wo are CONTIGUOUS in it (they start at padded pixel 2*wo), and the windows of consecutive output pixels
+// overlap by 6 pixels -- which a tiled tensor map expresses directly: dims {32, Wo, Hp, N} with a 16-byte stride between
+// windows.  One TMA box {32, 128, 1, 1} is the A tile of filter row r for 128 output pixels (64-byte rows, SWIZZLE_64B);
+// K = 7 rows x 32 (28 real taps + 4 zero) per output.  The weights are packed [Cout][7][8][4] to match.
+int conv_stem_tc(const hn_tensor *xpad, const void *w, int cout, const hn_epilogue *ep, const hn_tensor *y, cudaStream_t st)
+{
+    const int Ho = y->h, Wo = y->w;
+    if ((int64_t)y->n * Ho * Wo == 0) return HN_OK;
+    HN_CHECK_ARG(xpad->c == 4 && xpad->ld == 4 && xpad->dtype == HN_BF16, "conv_stem: input must be the padded 4-channel BF16 image");
+    HN_CHECK_ARG(xpad->w >= 2 * Wo + 6 && xpad->h >= 2 * Ho + 5, "conv_stem: padded image too small (%dx%d for output %dx%d)", xpad->h, xpad->w, Ho, Wo);
+    HN_CHECK_ARG((reinterpret_cast<uintptr_t>(xpad->ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0, "conv_stem: 16-byte alignment");
+    const int cout_pad = hn_conv_cout_pad(cout, HN_BF16);
+    HN_CHECK_ARG(cout_pad == 64, "conv_stem: Cout must be 64 (got %d)", cout);
+    constexpr int BK = 32, KTOT = 7 * BK;
+    TcParams p{};
+    p.hmul = 2;
+    p.TH = 1; p.TW = 128;
+    p.tiles_w = (int)cdiv(Wo, 128); p.tiles_h = Ho; p.n_img = y->n;
+    p.Ho = Ho; p.Wo = Wo;
+    p.R = 7; p.S = 1; p.pad = 0; p.dil = 1; p.cblocks = 1;
+    p.n_tiles = 1; p.Cout = cout;
+    CUtensorMap ta, tb, ty, tr;
+    memset(&ty, 0, sizeof(ty));
+    memset(&tr, 0, sizeof(tr));
+    {
+        const uint64_t rowb = (uint64_t)xpad->w * 8;
+        uint64_t dims[4] = {32, (uint64_t)Wo, (uint64_t)xpad->h, (uint64_t)xpad->n};
+        uint64_t strides[4] = {2, 16, rowb, rowb * xpad->h};
+        uint32_t box[4] = {32, 128, 1, 1};
+        int rc = make_tmap(&ta, xpad->ptr, 4, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)KTOT, (uint64_t)cout_pad};
+        uint64_t strides[2] = {2, (uint64_t)KTOT * 2};
+        uint32_t box[2] = {32, 64};
+        int rc = make_tmap(&tb, w, 2, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+    }
+    p.y = y->ptr; p.ldy = y->ld; p.y_f32 = (y->dtype == HN_F32);
+    p.scale = ep->scale; p.shift = ep->shift; p.res = ep->residual; p.ldr = ep->residual_ld;
+    p.act = ep->act; p.slope = ep->slope; p.slope_ptr = ep->slope_ptr;
+    p.ebw = 32;
+    {
+        const uint64_t esz = p.y_f32 ? 4 : 2;
+        const bool ok = (reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0 && ((uint64_t)y->ld * esz) % 16 == 0;
+        if (ok) {
+            uint64_t dims[4] = {(uint64_t)cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)p.n_img};
+            uint64_t strides[4] = {esz, (uint64_t)y->ld * esz, (uint64_t)y->ld * esz * Wo, (uint64_t)y->ld * esz * Wo * Ho};
+            uint32_t box[4] = {(uint32_t)(128 / esz), 32, 1, 1};
+            int rc = make_tmap(&ty, y->ptr, 4, dims, strides, box, p.y_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+            if (rc) return rc;
+            p.tma_out = 1;
+        }
+    }
+    HN_CHECK_ARG(!ep->residual, "conv_stem: no residual input");
+    const int num_tiles = p.n_img * p.tiles_h * p.tiles_w;
+    return launch_tc<64, 12, BK>(ta, tb, ty, tr, p, num_tiles, st);
 }
 
 }  // namespace hn

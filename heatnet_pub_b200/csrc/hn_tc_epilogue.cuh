@@ -14,6 +14,7 @@ struct TcParams {
     int Ho, Wo;                    // output spatial size (flat mode: Ho = 1, Wo = total pixels)
     int n_tiles;                   // Cout tiles
     int R, S, pad, dil;
+    int hmul;                      // input row of tap r = (output row) * hmul - pad + r * dil (2 for the stem's window map, else 1)
     int cblocks;                   // Cin / 64 (flat-from-workspace: kpad / 64 with R=S=1)
     int Cout;
     // epilogue

@@ -157,6 +157,17 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr)
     d |= (uint64_t)2 << 61;
     return d;
 }
+// K-major swizzled descriptor for 128-byte (SWIZZLE_128B, 64 BF16 per row) or 64-byte (SWIZZLE_64B, 32 BF16) rows
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, int row_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8 * row_bytes) >> 4) << 32;          // SBO: 8 rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;      // SWIZZLE_128B = 2, SWIZZLE_64B = 4
+    return d;
+}
 // instruction descriptor: D=F32, A=B=BF16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n)
 {
@@ -182,6 +193,6 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int m, int n) { return
 
 // host: driver entry point for tensor-map encoding, BF16/FP32 maps of rank <= 4 with 128B swizzle and zero OOB fill
 int make_tmap(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box,
-              CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+              CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B);
 
 }  // namespace hn

@@ -20,6 +20,7 @@ _HN_DTYPE = {torch.float32: HN_F32, torch.bfloat16: HN_BF16}
 DEFAULT_PRECISION = os.environ.get("HEATNET_B200_PRECISION", "bf16")
 BN_TRAIN_RAW_FP32 = os.environ.get("HEATNET_B200_BN_RAW_FP32", "1") != "0"
 UPCONV_MIN_CIN = int(os.environ.get("HN_UPCONV_MIN_CIN", "512"))
+STEM_FAST = os.environ.get("HN_NO_STEM_FAST") is None
 
 # number of libheatnet_b200 kernels enqueued by this process (bench.py reports it as gpu_launches)
 launch_count = 0
@@ -344,6 +345,54 @@ def packed_weight_folded(conv: torch.nn.Conv2d, bn: Optional[torch.nn.BatchNorm2
     return dst, shift
 
 
+def stem_ok(x: "Act", conv: torch.nn.Conv2d) -> bool:
+    """7x7 stride-2 pad-3 stem on <= 4 input channels: runs without an im2col pass (hn_stem7x7s2_fwd)."""
+    return (x.dtype == torch.bfloat16 and conv.kernel_size == (7, 7) and conv.stride == (2, 2) and conv.padding == (3, 3)
+            and conv.dilation == (1, 1) and conv.in_channels <= 4 and conv.out_channels == 64 and STEM_FAST)
+
+
+def packed_stem_weight(conv: torch.nn.Conv2d, bn: Optional[torch.nn.BatchNorm2d]):
+    """[64][7][8][4] BF16 pack of a stem filter (BN(eval) scale folded in when `bn` is given) -> (pack, shift)."""
+    lib = _lib.load()
+    scale, shift = folded_affine(conv, bn) if (bn is not None or conv.bias is not None) else (None, None)
+    cache = conv.__dict__.setdefault("_hn_wcache", {})
+    key = ("stem", bn is not None, conv.weight.device)
+    ver = _versions(conv.weight, conv.bias, *((bn.weight, bn.bias, bn.running_mean, bn.running_var) if bn is not None else ()))
+    hit = cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1], shift
+    w = conv.weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    dst = torch.empty((64, 224), dtype=torch.bfloat16, device=w.device)
+    _lib.check(lib.hn_pack_stem_weight(w.data_ptr(), scale.data_ptr() if (bn is not None and scale is not None) else None, dst.data_ptr(),
+                                       conv.out_channels, conv.in_channels, _stream()))
+    _count()
+    cache[key] = (ver, dst)
+    return dst, shift
+
+
+def stem_conv(x: "Act", conv: torch.nn.Conv2d, wp: torch.Tensor, shift, act=ACT_NONE, slope=0.0, slope_ptr=None,
+              out: Optional["Act"] = None, out_dtype=None) -> "Act":
+    lib = _lib.load()
+    ho, wo = conv_out_hw(x.h, x.w, conv)
+    xpad = new_act(x.n, 2 * ho + 6, 2 * wo + 6, 4, torch.bfloat16, x.buf.device)
+    if out is None:
+        out = new_act(x.n, ho, wo, conv.out_channels, out_dtype or x.dtype, x.buf.device)
+    ep = _epilogue(None, shift, None, act, slope, slope_ptr)
+    timing = conv_timer is not None
+    if timing:
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev_a.record()
+    _lib.check(lib.hn_stem_pad(C.byref(x.hn()), C.byref(xpad.hn()), _stream()))
+    _lib.check(lib.hn_stem7x7s2_fwd(C.byref(xpad.hn()), wp.data_ptr(), conv.out_channels, C.byref(ep), C.byref(out.hn()), _stream()))
+    if timing:
+        ev_b.record()
+        conv_timer.append((f"{x.c}->{conv.out_channels} k7 s2 d1 @{x.h}x{x.w}", ev_a, ev_b))
+    _count(2)
+    return out
+
+
 def packed_weight_slice(conv: torch.nn.Conv2d, c0: int, c1: int, dtype: torch.dtype) -> torch.Tensor:
     """Pack of the input-channel slice [c0, c1) of a conv weight (the per-prior blocks of the PSP bottleneck)."""
     lib = _lib.load()
@@ -522,7 +571,10 @@ def conv_bn_act(x: Act, conv, bn, act=ACT_NONE, slope=0.0, slope_ptr=None, resid
         bn_training = bn is not None and (bn.training or bn.running_mean is None)
     if bn is None or not bn_training:
         scale, shift = folded_affine(conv, bn)
-        if bn is not None and x.dtype == torch.bfloat16:
+        if residual is None and stem_ok(x, conv):
+            wp, shift = packed_stem_weight(conv, bn)
+            y = stem_conv(x, conv, wp, shift, act, slope, slope_ptr, out)
+        elif bn is not None and x.dtype == torch.bfloat16:
             # BF16 engine: BN scale folded into the packed filter, the epilogue only adds the shift
             wp, shift = packed_weight_folded(conv, bn, x.dtype)
             y = conv2d_raw(x, wp, conv.out_channels, conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0], None, shift,
@@ -537,7 +589,11 @@ def conv_bn_act(x: Act, conv, bn, act=ACT_NONE, slope=0.0, slope_ptr=None, resid
     # which is large for channels with little spatial variation.  Statistics and the normalise pass read the
     # FP32 values; only the normalised activation is rounded to the compute dtype.
     raw_fp32 = BN_TRAIN_RAW_FP32 or tape is not None
-    raw = conv2d(x, conv, scale, shift, None, ACT_NONE, out_dtype=torch.float32 if raw_fp32 else None)
+    if stem_ok(x, conv):
+        wp, shift = packed_stem_weight(conv, None)
+        raw = stem_conv(x, conv, wp, shift, out_dtype=torch.float32 if raw_fp32 else None)
+    else:
+        raw = conv2d(x, conv, scale, shift, None, ACT_NONE, out_dtype=torch.float32 if raw_fp32 else None)
     bscale, bshift, mean, invstd = batchnorm_train_affine(raw, bn)
     if out is None:
         in_place = raw.dtype == x.dtype and tape is None

@@ -108,6 +108,14 @@ int hn_conv2d_fwd(const hn_tensor *x, const void *w_packed, const hn_conv *cv, c
 int hn_upconv3x3_fwd(const hn_tensor *x, const void *w_packed, const hn_conv *cv, const hn_epilogue *ep, const hn_tensor *y,
                      void *stream);
 
+/* The 7x7 stride-2 pad-3 stems (Cin <= 4; cm/models/extractors.py:111-123) without an im2col pass: hn_stem_pad writes the
+ * input as a zero-bordered 4-channel BF16 image [N][>=2*Ho+6][>=2*Wo+6][4]; in it the 8x4 values a filter row needs for one
+ * output pixel are contiguous and consecutive windows overlap, which a strided tensor map hands to TMA directly.
+ * hn_pack_stem_weight: OIHW -> [64][7][8][4] (optionally scaled per output channel). */
+int hn_stem_pad(const hn_tensor *x, const hn_tensor *xpad, void *stream);
+int hn_pack_stem_weight(const float *w_oihw, const float *row_scale, void *dst, int32_t cout, int32_t cin, void *stream);
+int hn_stem7x7s2_fwd(const hn_tensor *xpad, const void *w_packed, int32_t cout, const hn_epilogue *ep, const hn_tensor *y, void *stream);
+
 /* ---- bandwidth-bound ops ---- */
 /* nn.MaxPool2d(3,2,1): cm/models/extractors.py:128 */
 int hn_maxpool3x3s2_fwd(const hn_tensor *x, const hn_tensor *y, void *stream);

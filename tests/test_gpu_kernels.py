@@ -165,6 +165,34 @@ def test_upsample2x_conv3x3_fused(E, case):
     assert rel(back(y), back(y2)) < 1e-5
 
 
+@pytest.mark.parametrize("cin,h,w", [(3, 33, 40), (1, 33, 40), (4, 32, 40), (3, 65, 257), (1, 7, 9)])
+def test_stem7x7_overlapping_window_path(E, cin, h, w):
+    """7x7 s2 p3 stem -> BN(eval) -> ReLU without im2col (padded 4-channel image + strided tensor map) vs the oracle
+    primitive on BF16-rounded operands; also the FP32-output variant the train-mode BN path uses."""
+    g = torch.Generator().manual_seed(21)
+    conv = nn.Conv2d(cin, 64, 7, 2, 3, bias=False)
+    bn = nn.BatchNorm2d(64)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * (2.0 / (49 * cin)) ** 0.5)
+        bn.weight.copy_(torch.rand(64, generator=g) + 0.5); bn.bias.copy_(torch.randn(64, generator=g) * 0.1)
+        bn.running_mean.copy_(torch.randn(64, generator=g) * 0.1); bn.running_var.copy_(torch.rand(64, generator=g) + 0.5)
+    bn.eval()
+    x = torch.rand(2, cin, h, w, generator=g) * 2 - 1
+    with torch.no_grad():
+        ref = F.relu(bn(conv(x)))
+        ref_raw = F.conv2d(x.bfloat16().float(), conv.weight.bfloat16().float(), None, 2, 3)
+    import copy
+    convg, bng = copy.deepcopy(conv).cuda(), copy.deepcopy(bn).cuda().eval()
+    xa = to_act(E, x, torch.bfloat16)
+    assert E.stem_ok(xa, convg)
+    y = E.conv_bn_act(xa, convg, bng, E.ACT_RELU)
+    assert (y.h, y.w) == (ref.shape[2], ref.shape[3])
+    assert rel(back(y), ref) < BF16_TOL
+    wp, shift = E.packed_stem_weight(convg, None)
+    raw = E.stem_conv(xa, convg, wp, shift, out_dtype=torch.float32)
+    assert rel(back(raw), ref_raw) < 1e-3
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
 def test_conv_fused_epilogue_bn_residual_relu(E, dtype, tol):
     """conv -> BN(eval) -> += residual -> ReLU in one launch == cm/models/extractors.py:96-101."""
