@@ -73,6 +73,14 @@ SIGNATURES = {
     "hn_vec_to_grad": (C.c_int, [_P, _P, _I32, _I32, _P]),
     "hn_confusion": (C.c_int, [_P, _P, _I64, _I64, _P, _I32, _P, _P, _P]),
     "hn_argmax_labels": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _P]),
+    "hn_loss_scratch_bytes": (_I64, []),
+    "hn_ce_loss_fwd_bwd": (C.c_int, [_P, _P, _I64, _I32, _I64, _I64, _F, _P, _P, _P, _P, _I64, _P]),
+    "hn_critic_loss_fwd_bwd": (C.c_int, [_P, _P, _F, _I64, _I32, _F, _P, _P, _P, _I64, _P]),
+    "hn_scale_by_scalar": (C.c_int, [_P, _I64, _P, _P]),
+    "hn_optim_chunk": (_I32, []),
+    "hn_grad_sqnorm": (C.c_int, [_P, _P, _I32, _P, _P, _P]),
+    "hn_rmsprop_step": (C.c_int, [_P, _P, _I32, _F, _F, _F, _F, _F, _F, _F, _P, _P]),
+    "hn_adam_step": (C.c_int, [_P, _P, _I32, _F, _F, _F, _F, _F, _I64, _F, _F, _P, _P]),
 }
 
 _lib = None

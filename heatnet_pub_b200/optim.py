@@ -1,0 +1,163 @@
+"""Fused multi-tensor optimisers for the trainers on this path.
+
+`RMSprop` replaces `torch.optim.RMSprop(conf_segnet_model.parameters(), lr=opt.lr)`
+(`models/confusion_maximization/train_trgb_segnet_conf.py:270`) and `Adam` replaces
+`Adam(model.parameters(), lr=...)` (`scripts/main.py:159`).  Both subclass `torch.optim.Optimizer` with torch's
+hyper-parameter names and per-parameter state keys (`step`, `square_avg`, `momentum_buffer`, `exp_avg`,
+`exp_avg_sq`), so `lr_scheduler.StepLR`, `poly_lr_scheduler` (which writes `param_groups[i]['lr']`) and optimizer
+checkpoints (`state_dict()` / `load_state_dict()`, `train_trgb_segnet_conf.py:281,652`) interoperate.
+
+One kernel launch updates every parameter of a group (hn_rmsprop_step / hn_adam_step), with two things folded in:
+the gradient average of the data-parallel all-reduce (`grad_scale`) and `clip_grad_norm` (`scripts/main.py:256-257`,
+`max_norm=`; the clip coefficient comes from one extra read of the gradients, hn_grad_sqnorm, and is applied inside
+the update instead of rewriting the gradients).  Parameters whose `.grad` is None are skipped, as torch does
+(`conv_segnet.setPhase` leaves the frozen half of the model without gradients).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import engine as E
+
+
+class _FusedOptimizer(torch.optim.Optimizer):
+    _state_names = ()
+
+    def __init__(self, params, defaults, max_norm=None, grad_scale=1.0):
+        super().__init__(params, defaults)
+        self.max_norm = max_norm
+        self.grad_scale = float(grad_scale)
+        self._tables = {}
+        self.last_sqnorm = None
+
+    # ---- device tables: slots (param, grad, state1, state2, numel) and the block -> (slot, chunk) map
+    def _table(self, gi, live, states):
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), *(s.data_ptr() if s is not None else 0 for s in st)) for p, st in zip(live, states))
+        hit = self._tables.get(gi)
+        if hit is not None and hit[0] == key:
+            return hit[1:]
+        chunk = _lib.load().hn_optim_chunk()
+        slots = np.zeros((len(live), 5), dtype=np.int64)
+        blocks = []
+        for i, (p, st) in enumerate(zip(live, states)):
+            slots[i] = (p.data_ptr(), p.grad.data_ptr(), st[0].data_ptr(), st[1].data_ptr() if st[1] is not None else 0, p.numel())
+            nchunk = (p.numel() + chunk - 1) // chunk
+            blocks.append(np.stack([np.full(nchunk, i, dtype=np.int32), np.arange(nchunk, dtype=np.int32)], axis=1))
+        bmap = np.concatenate(blocks, axis=0) if blocks else np.zeros((0, 2), dtype=np.int32)
+        dev = live[0].device
+        slots_d = torch.from_numpy(slots).to(dev)
+        bmap_d = torch.from_numpy(np.ascontiguousarray(bmap)).to(dev)
+        partial = torch.empty(bmap.shape[0] + 1, dtype=torch.float64, device=dev)
+        self._tables[gi] = (key, slots_d, bmap_d, partial, bmap.shape[0])
+        return slots_d, bmap_d, partial, bmap.shape[0]
+
+    def _live(self, group):
+        live = []
+        for p in group['params']:
+            if p.grad is None:
+                continue
+            if p.grad.is_sparse:
+                raise RuntimeError(f"{type(self).__name__} does not support sparse gradients")
+            if p.dtype != torch.float32 or not p.is_contiguous() or not p.is_cuda:
+                raise RuntimeError("heatnet_pub_b200.optim: parameters must be dense FP32 CUDA tensors (the FP32 masters)")
+            if p.grad.dtype != torch.float32 or not p.grad.is_contiguous():
+                p.grad = p.grad.float().contiguous()
+            live.append(p)
+        return live
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        _lib.require_device()
+        lib = _lib.load()
+        for gi, group in enumerate(self.param_groups):
+            live = self._live(group)
+            if not live:
+                continue
+            states = [self._init_state(p, group) for p in live]
+            slots_d, bmap_d, partial, nblocks = self._table(gi, live, states)
+            sq_ptr = None
+            max_norm = float(self.max_norm) if self.max_norm else 0.0
+            if max_norm > 0.0:
+                sq = partial[nblocks:]
+                _lib.check(lib.hn_grad_sqnorm(slots_d.data_ptr(), bmap_d.data_ptr(), nblocks, partial.data_ptr(), sq.data_ptr(), E._stream()))
+                E._count(2)
+                sq_ptr, self.last_sqnorm = sq.data_ptr(), sq
+            self._launch(lib, group, live, slots_d, bmap_d, nblocks, max_norm, sq_ptr)
+            E._count()
+            torch.autograd.graph.increment_version(live)      # the kernel writes behind torch's back: refresh packed-weight caches
+        return loss
+
+    def total_grad_norm(self):
+        """sqrt of the last clip pass's squared norm, times |grad_scale| (what clip_grad_norm returns); one D2H read."""
+        return None if self.last_sqnorm is None else float(self.last_sqnorm.item()) ** 0.5 * abs(self.grad_scale)
+
+
+class RMSprop(_FusedOptimizer):
+    def __init__(self, params, lr=1e-2, alpha=0.99, eps=1e-8, weight_decay=0, momentum=0, centered=False, max_norm=None, grad_scale=1.0):
+        if centered:
+            raise NotImplementedError("centered RMSprop is not on the hot path")
+        if lr < 0.0 or eps < 0.0 or momentum < 0.0 or weight_decay < 0.0 or alpha < 0.0:
+            raise ValueError("Invalid hyper-parameter (negative lr / eps / momentum / weight_decay / alpha)")
+        super().__init__(params, dict(lr=lr, alpha=alpha, eps=eps, weight_decay=weight_decay, momentum=momentum, centered=False),
+                         max_norm, grad_scale)
+
+    def _init_state(self, p, group):
+        st = self.state[p]
+        if len(st) == 0:
+            st['step'] = torch.tensor(0.0)
+            st['square_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            if group['momentum'] > 0:
+                st['momentum_buffer'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        st['step'] += 1
+        return st['square_avg'], st.get('momentum_buffer')
+
+    def _launch(self, lib, group, live, slots_d, bmap_d, nblocks, max_norm, sq_ptr):
+        _lib.check(lib.hn_rmsprop_step(slots_d.data_ptr(), bmap_d.data_ptr(), nblocks, group['lr'], group['alpha'], group['eps'],
+                                       group['weight_decay'], group['momentum'], self.grad_scale, max_norm, sq_ptr, E._stream()))
+
+
+class Adam(_FusedOptimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, max_norm=None, grad_scale=1.0):
+        if amsgrad:
+            raise NotImplementedError("amsgrad is not on the hot path")
+        if lr < 0.0 or eps < 0.0 or not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0 or weight_decay < 0.0:
+            raise ValueError("Invalid hyper-parameter")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False), max_norm, grad_scale)
+
+    def _init_state(self, p, group):
+        st = self.state[p]
+        if len(st) == 0:
+            st['step'] = torch.tensor(0.0)
+            st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        st['step'] += 1
+        return st['exp_avg'], st['exp_avg_sq']
+
+    def _launch(self, lib, group, live, slots_d, bmap_d, nblocks, max_norm, sq_ptr):
+        steps = {int(self.state[p]['step'].item()) for p in live}
+        # one launch per distinct step count (parameters that joined later, e.g. after a phase switch, have their own)
+        if len(steps) == 1:
+            _lib.check(lib.hn_adam_step(slots_d.data_ptr(), bmap_d.data_ptr(), nblocks, group['lr'], group['betas'][0], group['betas'][1],
+                                        group['eps'], group['weight_decay'], steps.pop(), self.grad_scale, max_norm, sq_ptr, E._stream()))
+            return
+        bmap = bmap_d.cpu().numpy()
+        for s in sorted(steps):
+            idx = [i for i, p in enumerate(live) if int(self.state[p]['step'].item()) == s]
+            sel = np.ascontiguousarray(bmap[np.isin(bmap[:, 0], idx)])
+            sub = torch.from_numpy(sel).to(bmap_d.device)
+            _lib.check(lib.hn_adam_step(slots_d.data_ptr(), sub.data_ptr(), sel.shape[0], group['lr'], group['betas'][0], group['betas'][1],
+                                        group['eps'], group['weight_decay'], s, self.grad_scale, max_norm, sq_ptr, E._stream()))
+
+
+def poly_lr_scheduler(optimizer, init_lr, iter, max_iter=100, power=0.9):
+    """helper/utils.py:71-84 (called at scripts/main.py:232): same signature, same arithmetic, returns the new lr."""
+    lr = init_lr * (1 - iter / max_iter) ** power
+    for param_group in optimizer.param_groups:
+        param_group['lr'] = lr
+    return lr

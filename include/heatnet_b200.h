@@ -185,6 +185,49 @@ int hn_confusion(const int64_t *pred_labels, const float *scores, int64_t n_imag
 int hn_argmax_labels(const float *scores, int64_t n_images, int64_t hw, int32_t k, uint8_t *out_u8,
                      int64_t *out_i64, void *stream);
 
+/* ---- losses of the training step, forward + backward in one pass ----
+ * cm/train_trgb_segnet_conf.py:244 `criterion_semseg = CrossEntropyLoss()` applied at :452; scripts/main.py:223
+ * `CrossEntropyLoss(ignore_index=13)`; cm/train_trgb_segnet_conf.py:238-240 `BCEWithLogitsLoss()` / `MSELoss()` of a critic
+ * map against `torch.full_like(c, 1 or 0)` at :437-446,529-546.  All reductions are 'mean'.
+ * scratch: device memory of at least hn_loss_scratch_bytes() (FP64 per-block partials; deterministic fold). */
+int64_t hn_loss_scratch_bytes(void);
+/* logits NCHW FP32 [N][K][HW], labels int64 [N][HW].  loss_out: device float.  dlogits (optional, same layout) receives
+ * grad_scale * d loss / d logits.  Labels equal to ignore_index are skipped (pass a value outside [0,K) for "none");
+ * other labels outside [0,K) set bit 0 of *flags (torch raises a device assert there) and are skipped. */
+int hn_ce_loss_fwd_bwd(const float *logits_nchw, const int64_t *labels, int64_t n_images, int32_t k, int64_t hw, int64_t ignore_index,
+                       float grad_scale, float *loss_out, float *dlogits_nchw, int32_t *flags, void *scratch, int64_t scratch_bytes,
+                       void *stream);
+/* kind 0: mean((x - t)^2); kind 1: mean(BCE-with-logits(x, t)); t = target[i] or, when target == NULL, target_const (the
+ * reference fills its target with a constant: torch.full_like(c, 1 / 0)).  dx (optional) = grad_scale * d loss / dx */
+int hn_critic_loss_fwd_bwd(const float *x, const float *target, float target_const, int64_t n, int32_t kind, float grad_scale,
+                           float *loss_out, float *dx, void *scratch, int64_t scratch_bytes, void *stream);
+/* y *= *scalar_dev (chain rule with the upstream gradient of a loss term, kept on the device) */
+int hn_scale_by_scalar(float *y, int64_t n, const float *scalar_dev, void *stream);
+
+/* ---- optimiser step: cm/train_trgb_segnet_conf.py:270 `torch.optim.RMSprop(params, lr)`,
+ * scripts/main.py:159 `Adam(params, lr)`, scripts/main.py:256-257 `clip_grad_norm(params, clip)` ----
+ * One launch updates every tensor.  slots_dev: device array, one entry per parameter tensor (FP32, dense).
+ * block_map_dev: device int32 pairs (slot index, chunk index); chunk c of a slot covers elements
+ * [c*hn_optim_chunk(), (c+1)*hn_optim_chunk()).  The caller builds both tables (they change only when a tensor moves). */
+typedef struct hn_param_slot {
+    float *param;
+    const float *grad;
+    float *state1; /* RMSprop: square_avg.            Adam: exp_avg    */
+    float *state2; /* RMSprop: momentum_buffer / NULL. Adam: exp_avg_sq */
+    int64_t numel;
+} hn_param_slot;
+int32_t hn_optim_chunk(void);
+/* sqnorm_dev[0] = sum over all slots of sum(grad^2) (FP64; deterministic: per-block partials in partial_dev[n_blocks]) */
+int hn_grad_sqnorm(const hn_param_slot *slots_dev, const int32_t *block_map_dev, int32_t n_blocks, double *partial_dev,
+                   double *sqnorm_dev, void *stream);
+/* Every gradient is first multiplied by grad_scale (1/world after an all-reduce SUM) and, when max_norm > 0, by
+ * min(1, max_norm / (|grad_scale| * sqrt(*sqnorm_dev) + 1e-6)) -- torch.nn.utils.clip_grad_norm_ without the extra pass. */
+int hn_rmsprop_step(const hn_param_slot *slots_dev, const int32_t *block_map_dev, int32_t n_blocks, float lr, float alpha, float eps,
+                    float weight_decay, float momentum, float grad_scale, float max_norm, const double *sqnorm_dev, void *stream);
+/* step: 1-based step count (bias corrections 1 - beta^step) */
+int hn_adam_step(const hn_param_slot *slots_dev, const int32_t *block_map_dev, int32_t n_blocks, float lr, float beta1, float beta2,
+                 float eps, float weight_decay, int64_t step, float grad_scale, float max_norm, const double *sqnorm_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

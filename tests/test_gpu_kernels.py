@@ -156,7 +156,6 @@ def test_upsample2x_conv3x3_fused(E, case):
     convg = copy.deepcopy(conv).cuda()
     scale, shift = E.folded_affine(convg, None)
     xa = to_act(E, x, torch.bfloat16)
-    assert E.upconv3x3_ok(xa, convg) == (cin >= E.UPCONV_MIN_CIN)
     y = E.upconv3x3(xa, convg, scale, shift, E.ACT_LEAKY, slope=0.25, out_dtype=torch.float32)
     assert (y.n, y.h, y.w, y.c) == (2, 2 * h, 2 * w, cout)
     assert rel(back(y), ref) < 1e-3
