@@ -261,19 +261,29 @@ def run_train(args):
     mk = lambda c: (torch.rand(B, c, H, W, generator=g) * 2 - 1).to(dev)
     rgb_d, ir_d, rgb_n, ir_n = mk(3), mk(1), mk(3), mk(1)
     label = torch.randint(0, 13, (B, H, W), generator=g).to(dev)
-    mse, ce = nn.MSELoss(), nn.CrossEntropyLoss()
+    from heatnet_pub_b200 import losses, optim
+    if args.torch_losses:
+        mse, ce = nn.MSELoss(), nn.CrossEntropyLoss()
+        tgt = lambda c, v: torch.full_like(c, v)
+    else:       # fused forward+backward criteria (hn_ce_loss_fwd_bwd / hn_critic_loss_fwd_bwd); constant targets as floats
+        mse, ce = losses.MSELoss(), losses.CrossEntropyLoss()
+        tgt = lambda c, v: float(v)
+    # cm/train_trgb_segnet_conf.py:270: ONE RMSprop over all parameters; the frozen half has no .grad and is skipped
+    optimizer = None if args.no_optimizer else optim.RMSprop(model.parameters(), lr=1e-5)
 
     def step():
         for p in model.parameters():
             p.grad = None
         o = model([rgb_d, ir_d], [rgb_n, ir_n])
         if args.workload == "train_seg":
-            conf = sum(mse(c, torch.full_like(c, 1)) for c in o['critics_a']) + sum(mse(c, torch.full_like(c, 1)) for c in o['critics_b'])
+            conf = sum(mse(c, tgt(c, 1)) for c in o['critics_a']) + sum(mse(c, tgt(c, 1)) for c in o['critics_b'])
             total = ce(o['pred_label_a'], label) + 0.1 * conf
         else:
-            total = sum(mse(c, torch.full_like(c, 1)) for c in o['critics_a']) + sum(mse(c, torch.full_like(c, 0)) for c in o['critics_b'])
+            total = sum(mse(c, tgt(c, 1)) for c in o['critics_a']) + sum(mse(c, tgt(c, 0)) for c in o['critics_b'])
         total.backward()
         reducer.reduce()
+        if optimizer is not None:
+            optimizer.step()
         return total
 
     def barrier():
@@ -308,7 +318,8 @@ def run_train(args):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": f"conv_segnet {args.workload} step (PSPNet-ResNet50 late fusion + 6 FCDiscriminator critics), "
-                                       f"{B} day+night pairs per GPU at {H}x{W}, fwd+bwd+gradient all-reduce, optimizer excluded; 2 images per pair",
+                                       f"{B} day+night pairs per GPU at {H}x{W}, fwd + {'torch' if args.torch_losses else 'fused'} losses + bwd + gradient all-reduce"
+                                       f"{' (optimizer excluded)' if args.no_optimizer else ' + fused RMSprop step'}; 2 images per pair",
                            "per_gpu_pairs": B, "global_pairs": B * world, "parallelism": f"batch-sharded x{world}, NCCL all-reduce of "
                            f"{reducer.last_bytes / 1e6:.1f} MB in {reducer.last_buckets} buckets" if world > 1 else "single GPU"},
                 "loss": float(loss), "gpu_launches": launches, "clocks": clocks,
@@ -333,6 +344,8 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-optimizer", action="store_true", help="training workloads: leave the optimizer step out of the timed step")
+    ap.add_argument("--torch-losses", action="store_true", help="training workloads: torch criteria instead of the fused loss kernels")
     ap.add_argument("--layer-table", default=None, help="write the per-conv-launch timing table (JSON) here")
     ap.add_argument("--workload", default="infer", choices=["infer", "train_seg", "train_critic"],
                     help="infer = the headline (BASELINE configs[1]); train_* = one adversarial training step (configs[2]/[3]): "

@@ -63,7 +63,8 @@ SIGNATURES = {
     "hn_accumulate": (C.c_int, [_T, _T, _I32, _P]),
     "hn_maxpool3x3s2_fwd_idx": (C.c_int, [_T, _T, _P, _P]),
     "hn_maxpool3x3s2_bwd": (C.c_int, [_T, _P, _T, _I32, _P]),
-    "hn_bilinear_bwd": (C.c_int, [_T, _T, _I32, _P]),
+    "hn_bilinear_bwd_workspace_bytes": (_I64, [_T, _T]),
+    "hn_bilinear_bwd": (C.c_int, [_T, _T, _I32, _P, _I64, _P]),
     "hn_pyramid_pool_bwd": (C.c_int, [_P, C.POINTER(_I32), _I32, _T, _I32, _P]),
     "hn_dilate": (C.c_int, [_T, _I32, _T, _P]),
     "hn_pack_weight_dgrad": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),

@@ -134,50 +134,76 @@ __global__ void bn_bwd_reduce_kernel(const TG *__restrict__ dout, int ldg, const
     }
 }
 
+// blockDim = (CVB, PL) like the reduce pass: a thread keeps ONE 8-channel group for all its pixels, so the per-channel
+// coefficients (FP64 sums -> three FP32 vectors) are formed once per thread and the pixel loop only moves data:
+//   draw = ka*dz + kb*(raw - mean) + kc,   ka = gamma*invstd, kb = -ka*invstd*s2/m, kc = -ka*s1/m
 template <typename TG, typename TO>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TG *__restrict__ dout, int ldg, const TO *__restrict__ out, int ldo,
                                                            const float *__restrict__ raw, int ldr, const float *__restrict__ mean,
                                                            const float *__restrict__ invstd, const float *__restrict__ gamma,
                                                            const double *__restrict__ s1, const double *__restrict__ s2, double inv_count,
                                                            int act, float slope, const float *slope_ptr, TG *__restrict__ draw, int ldd,
-                                                           TG *__restrict__ dres, int ldres, int dres_accumulate, int64_t npix, int C)
+                                                           TG *__restrict__ dres, int ldres, int dres_accumulate, int64_t npix, int C,
+                                                           int64_t pix_per_cta)
 {
-    const int ncv = C / 8;
+    const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+    if (cv >= C / 8) return;
+    const int PL = blockDim.y;
+    const int c = cv * 8;
     if (slope_ptr) slope = __ldg(slope_ptr);
-    constexpr int kPixPerBlock = 64;
-    const int64_t nblocks = (npix + kPixPerBlock - 1) / kPixPerBlock;
-    for (int64_t pb = blockIdx.x; pb < nblocks; pb += gridDim.x)
-        for (int i = threadIdx.x; i < kPixPerBlock * ncv; i += blockDim.x) {
-            const int pl = i / ncv;
-            const int64_t p = pb * kPixPerBlock + pl;
-            if (p >= npix) break;
-            const int c = (i - pl * ncv) * 8;
-            float g[8], o[8], r[8], mu[8], is[8], ga[8];
-            Vec8<TG>::load(dout + p * ldg + c, g);
-            Vec8<TO>::load(out + p * ldo + c, o);
-            Vec8<float>::load(raw + p * ldr + c, r);
-            Vec8<float>::load(mean + c, mu);
-            Vec8<float>::load(invstd + c, is);
-            if (gamma) Vec8<float>::load(gamma + c, ga);
-            float dx[8], dz[8];
+    float mu[8], ka[8], kb[8], kc[8];
+    {
+        float is[8], ga[8];
+        Vec8<float>::load(mean + c, mu);
+        Vec8<float>::load(invstd + c, is);
+        if (gamma) Vec8<float>::load(gamma + c, ga);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                dz[j] = g[j] * act_grad(o[j], act, slope);
-                const float xhat = (r[j] - mu[j]) * is[j];
-                const float m1 = (float)(s1[c + j] * inv_count), m2 = (float)(s2[c + j] * inv_count);
-                dx[j] = (gamma ? ga[j] : 1.f) * is[j] * (dz[j] - m1 - xhat * m2);
-            }
-            Vec8<TG>::store(draw + p * ldd + c, dx);
-            if (dres) {
-                if (dres_accumulate) {
-                    float e[8];
-                    Vec8<TG>::load(dres + p * ldres + c, e);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) dz[j] += e[j];
-                }
-                Vec8<TG>::store(dres + p * ldres + c, dz);
-            }
+        for (int j = 0; j < 8; ++j) {
+            const float m1 = (float)(s1[c + j] * inv_count), m2 = (float)(s2[c + j] * inv_count);
+            ka[j] = (gamma ? ga[j] : 1.f) * is[j];
+            kb[j] = -ka[j] * is[j] * m2;
+            kc[j] = -ka[j] * m1;
         }
+    }
+    const int64_t p_begin = (int64_t)blockIdx.x * pix_per_cta;
+    const int64_t p_end = min(p_begin + pix_per_cta, npix);
+    auto one = [&](int64_t p, const float (&g)[8], const float (&o)[8], const float (&r)[8]) {
+        float dx[8], dz[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            dz[j] = g[j] * act_grad(o[j], act, slope);
+            dx[j] = fmaf(ka[j], dz[j], fmaf(kb[j], r[j] - mu[j], kc[j]));
+        }
+        Vec8<TG>::store(draw + p * ldd + c, dx);
+        if (dres) {
+            if (dres_accumulate) {
+                float e[8];
+                Vec8<TG>::load(dres + p * ldres + c, e);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dz[j] += e[j];
+            }
+            Vec8<TG>::store(dres + p * ldres + c, dz);
+        }
+    };
+    int64_t p = p_begin + threadIdx.y;
+    for (; p + PL < p_end; p += 2 * PL) {       // two pixels in flight per thread
+        float g0[8], o0[8], r0[8], g1[8], o1[8], r1[8];
+        Vec8<TG>::load(dout + p * ldg + c, g0);
+        Vec8<TG>::load(dout + (p + PL) * ldg + c, g1);
+        Vec8<TO>::load(out + p * ldo + c, o0);
+        Vec8<TO>::load(out + (p + PL) * ldo + c, o1);
+        Vec8<float>::load(raw + p * ldr + c, r0);
+        Vec8<float>::load(raw + (p + PL) * ldr + c, r1);
+        one(p, g0, o0, r0);
+        one(p + PL, g1, o1, r1);
+    }
+    if (p < p_end) {
+        float g0[8], o0[8], r0[8];
+        Vec8<TG>::load(dout + p * ldg + c, g0);
+        Vec8<TO>::load(out + p * ldo + c, o0);
+        Vec8<float>::load(raw + p * ldr + c, r0);
+        one(p, g0, o0, r0);
+    }
 }
 
 // y (+)= x   (gradient accumulation between NHWC views; x may be FP32 or the view's dtype)
@@ -387,6 +413,220 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const TG *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// exact 2x adjoint (PSPUpsample): input index i receives  .25*dy[2i-1] + .75*dy[2i] + .75*dy[2i+1] + .25*dy[2i+2]  along each
+// axis; at the borders the clamped taps fold in (weight 1 for dy[0] -> 0 and dy[2H-1] -> H-1).  A thread produces a 2x2 block
+// of dx for 8 channels from the 6x6 block of dy around it: 9 loads per output instead of 16.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void up2_adjoint_weights(int i, int size, float (&w)[4])
+{
+    // weights of dy[2i-1], dy[2i], dy[2i+1], dy[2i+2] for input index i (0 when the output index does not exist / does not tap i)
+    w[0] = i >= 1 ? 0.25f : 0.f;
+    w[1] = i >= 1 ? 0.75f : 1.f;
+    w[2] = i + 1 <= size - 1 ? 0.75f : 1.f;
+    w[3] = i + 1 <= size - 1 ? 0.25f : 0.f;
+}
+
+template <typename TG, typename TX>
+__global__ void __launch_bounds__(256) bilinear_up2_bwd_kernel(const TG *__restrict__ dy, int ldy, TX *__restrict__ dx, int ldx, int accumulate,
+                                                               int N, int H, int W, int C)
+{
+    const int ncv = C / 8;
+    const int Ho = 2 * H, Wo = 2 * W;
+    const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+    const int row = blockIdx.x;                 // n*H2 + tile row
+    const int n = row / H2, yi = (row - n * H2) * 2;
+    float wyA[4], wyB[4];
+    up2_adjoint_weights(yi, H, wyA);
+    up2_adjoint_weights(yi + 1, H, wyB);
+    const bool rowB = yi + 1 < H;
+    const int items = W2 * ncv;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < items; i += gridDim.y * blockDim.x) {
+        const int xt = i / ncv, c = (i - xt * ncv) * 8;
+        const int xi = xt * 2;
+        const bool colB = xi + 1 < W;
+        float wxA[4], wxB[4];
+        up2_adjoint_weights(xi, W, wxA);
+        up2_adjoint_weights(xi + 1, W, wxB);
+        float a00[8], a01[8], a10[8], a11[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a00[j] = a01[j] = a10[j] = a11[j] = 0.f;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const int yo = 2 * yi - 1 + r;
+            if (yo < 0 || yo >= Ho) continue;
+            const TG *grow = dy + (((int64_t)n * Ho + yo) * Wo) * ldy + c;
+            float ra[8], rb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ra[j] = rb[j] = 0.f;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const int xo = 2 * xi - 1 + q;
+                if (xo < 0 || xo >= Wo) continue;
+                float g[8];
+                Vec8<TG>::load(grow + (int64_t)xo * ldy, g);
+                if (q < 4) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) ra[j] = fmaf(wxA[q], g[j], ra[j]);
+                }
+                if (q >= 2) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rb[j] = fmaf(wxB[q - 2], g[j], rb[j]);
+                }
+            }
+            if (r < 4) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    a00[j] = fmaf(wyA[r], ra[j], a00[j]);
+                    a01[j] = fmaf(wyA[r], rb[j], a01[j]);
+                }
+            }
+            if (r >= 2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    a10[j] = fmaf(wyB[r - 2], ra[j], a10[j]);
+                    a11[j] = fmaf(wyB[r - 2], rb[j], a11[j]);
+                }
+            }
+        }
+        auto put = [&](int y, int x, float (&v)[8]) {
+            TX *d = dx + (((int64_t)n * H + y) * W + x) * ldx + c;
+            if (accumulate) {
+                float e[8];
+                Vec8<TX>::load(d, e);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += e[j];
+            }
+            Vec8<TX>::store(d, v);
+        };
+        put(yi, xi, a00);
+        if (colB) put(yi, xi + 1, a01);
+        if (rowB) put(yi + 1, xi, a10);
+        if (rowB && colB) put(yi + 1, xi + 1, a11);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// large magnification (PSP priors s x s -> h x w, critic maps x32): the gather form leaves only N*H*W*C/8 threads with a long
+// serial loop each.  Separable two-pass adjoint instead, every element of dy read once by a fully parallel pass:
+//   pass A  tmp[n, yo, xi, c] = sum_xo wx(xo, xi) dy[n, yo, xo, c]      (FP32 workspace, N*Ho*W*C)
+//   pass B  dx[n, yi, xi, c] (+)= sum_yo wy(yo, yi) tmp[n, yo, xi, c]
+// ------------------------------------------------------------------------------------------------
+constexpr int kSepMaxW = 8;
+template <typename TG>
+__global__ void __launch_bounds__(256) bilinear_bwd_rows_vec_kernel(const TG *__restrict__ dy, int ldy, float *__restrict__ tmp, int64_t nrows,
+                                                                    int W, int Wo, int C, float sw)
+{
+    // one thread: one (n, yo) row x one 8-channel group, all W <= kSepMaxW input columns in registers
+    const int ncv = C / 8;
+    const int64_t total = nrows * ncv;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = t / ncv;
+        const int c = (int)(t - row * ncv) * 8;
+        float acc[kSepMaxW][8];
+#pragma unroll
+        for (int x = 0; x < kSepMaxW; ++x)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[x][j] = 0.f;
+        const TG *g0 = dy + row * Wo * ldy + c;
+        for (int xo = 0; xo < Wo; ++xo) {
+            int x0, x1;
+            float lx;
+            bilinear_src_b(xo, sw, W, x0, x1, lx);
+            float g[8];
+            Vec8<TG>::load(g0 + (int64_t)xo * ldy, g);
+#pragma unroll
+            for (int x = 0; x < kSepMaxW; ++x) {
+                const float w = (x == x0 ? 1.f - lx : 0.f) + (x == x1 ? lx : 0.f);
+                if (x < W) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[x][j] = fmaf(w, g[j], acc[x][j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < kSepMaxW; ++x)
+            if (x < W) Vec8<float>::store(tmp + (row * W + x) * C + c, acc[x]);
+    }
+}
+
+// scalar-channel variant (critic maps, C == 1 typically): one thread per (row, xi, c), gathers its output columns
+template <typename TG>
+__global__ void __launch_bounds__(256) bilinear_bwd_rows_scalar_kernel(const TG *__restrict__ dy, int ldy, float *__restrict__ tmp, int64_t nrows,
+                                                                       int W, int Wo, int C, float sw)
+{
+    const int64_t total = nrows * W * C;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(t % C);
+        const int64_t rx = t / C;
+        const int xi = (int)(rx % W);
+        const int64_t row = rx / W;
+        int xlo, xhi;
+        out_range(xi, sw, Wo, xlo, xhi);
+        float acc = 0.f;
+        const TG *g0 = dy + row * Wo * ldy + c;
+        for (int xo = xlo; xo <= xhi; ++xo) {
+            int x0, x1;
+            float lx;
+            bilinear_src_b(xo, sw, W, x0, x1, lx);
+            const float w = (x0 == xi ? 1.f - lx : 0.f) + (x1 == xi ? lx : 0.f);
+            if (w != 0.f) acc = fmaf(w, to_f32<TG>(g0[(int64_t)xo * ldy]), acc);
+        }
+        tmp[t] = acc;
+    }
+}
+
+// pass B: one thread per element of dx (V channels), sums its output rows from tmp
+template <typename TX, bool kVec>
+__global__ void __launch_bounds__(256) bilinear_bwd_cols_kernel(const float *__restrict__ tmp, TX *__restrict__ dx, int ldx, int accumulate, int N,
+                                                                int H, int W, int Ho, int C, float sh)
+{
+    constexpr int V = kVec ? 8 : 1;
+    const int ncv = C / V;
+    const int64_t total = (int64_t)N * H * W * ncv;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(t % ncv) * V;
+        int64_t r = t / ncv;
+        const int xi = (int)(r % W);
+        r /= W;
+        const int yi = (int)(r % H);
+        const int n = (int)(r / H);
+        int ylo, yhi;
+        out_range(yi, sh, Ho, ylo, yhi);
+        float acc[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = 0.f;
+        for (int yo = ylo; yo <= yhi; ++yo) {
+            int y0, y1;
+            float ly;
+            bilinear_src_b(yo, sh, H, y0, y1, ly);
+            const float w = (y0 == yi ? 1.f - ly : 0.f) + (y1 == yi ? ly : 0.f);
+            if (w == 0.f) continue;
+            const float *src = tmp + (((int64_t)n * Ho + yo) * W + xi) * C + c;
+            if constexpr (kVec) {
+                float g[8];
+                Vec8<float>::load(src, g);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, g[j], acc[j]);
+            } else {
+                acc[0] = fmaf(w, src[0], acc[0]);
+            }
+        }
+        TX *d = dx + (((int64_t)n * H + yi) * W + xi) * ldx + c;
+        if constexpr (kVec) {
+            if (accumulate) {
+                float e[8];
+                Vec8<TX>::load(d, e);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += e[j];
+            }
+            Vec8<TX>::store(d, acc);
+        } else {
+            d[0] = from_f32<TX>(acc[0] + (accumulate ? to_f32<TX>(d[0]) : 0.f));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // pyramid pool adjoint: dx[n,h,w,c] (+)= sum over sizes s and bins (i,j) containing (h,w) of dbin / area
 // dpool: the forward's per-size dense blocks [N][s][s][C]
 // ------------------------------------------------------------------------------------------------
@@ -575,12 +815,17 @@ extern "C" int hn_bn_bwd(const hn_tensor *dout, const hn_tensor *out, const hn_t
     dim3 grid((unsigned)chunks, (unsigned)cvblocks), block(CVB, PL);
     size_t smem = (size_t)2 * PL * CVB * 8 * sizeof(float);
     double *s1 = sums, *s2 = sums + C, *sp = want_prelu_grad ? sums + 2 * C : nullptr;
-    int grid2 = wave_grid_b(cdiv(npix, 64) * 256, 256, 16);
+    // apply pass: no reduction, so finer pixel chunks (about 8 CTAs per SM)
+    int64_t chunks2 = cdiv((int64_t)num_sms() * 8, cvblocks);
+    int64_t pix_per_cta2 = cdiv(npix, chunks2);
+    if (pix_per_cta2 < (int64_t)PL * 4) pix_per_cta2 = (int64_t)PL * 4;
+    chunks2 = cdiv(npix, pix_per_cta2);
+    dim3 grid2((unsigned)chunks2, (unsigned)cvblocks);
     const double inv_count = 1.0 / (double)npix;
 #define HN_BN_BWD(TG, TO)                                                                                                                 \
     do {                                                                                                                                  \
         bn_bwd_reduce_kernel<TG, TO><<<grid, block, smem, st>>>((const TG *)dout->ptr, dout->ld, (const TO *)out->ptr, out->ld, (const float *)raw->ptr, raw->ld, mean, invstd, act, slope, slope_ptr, npix, C, pix_per_cta, s1, s2, sp); \
-        bn_bwd_apply_kernel<TG, TO><<<grid2, 256, 0, st>>>((const TG *)dout->ptr, dout->ld, (const TO *)out->ptr, out->ld, (const float *)raw->ptr, raw->ld, mean, invstd, gamma, s1, s2, inv_count, act, slope, slope_ptr, (TG *)draw->ptr, draw->ld, dres ? (TG *)dres->ptr : nullptr, dres ? dres->ld : 0, dres_accumulate, npix, C); \
+        bn_bwd_apply_kernel<TG, TO><<<grid2, block, 0, st>>>((const TG *)dout->ptr, dout->ld, (const TO *)out->ptr, out->ld, (const float *)raw->ptr, raw->ld, mean, invstd, gamma, s1, s2, inv_count, act, slope, slope_ptr, (TG *)draw->ptr, draw->ld, dres ? (TG *)dres->ptr : nullptr, dres ? dres->ld : 0, dres_accumulate, npix, C, pix_per_cta2); \
     } while (0)
     if (dout->dtype == HN_BF16 && out->dtype == HN_BF16) HN_BN_BWD(bf16, bf16);
     else if (dout->dtype == HN_F32 && out->dtype == HN_F32) HN_BN_BWD(float, float);
@@ -645,7 +890,25 @@ extern "C" int hn_maxpool3x3s2_bwd(const hn_tensor *dy, const uint8_t *idx, cons
     return HN_OK;
 }
 
-extern "C" int hn_bilinear_bwd(const hn_tensor *dy, const hn_tensor *dx, int32_t accumulate, void *stream)
+// which algorithm the adjoint uses: 0 = generic gather, 1 = exact 2x micro-tiles, 2 = separable two-pass (needs workspace)
+static int bilinear_bwd_mode(const hn_tensor *dy, const hn_tensor *dx)
+{
+    const bool vec = vec8_ok(dy) && vec8_ok(dx);
+    if (vec && dy->h == 2 * dx->h && dy->w == 2 * dx->w) return 1;
+    const int64_t mag = ((int64_t)dy->h * dy->w) / ((int64_t)dx->h * dx->w > 0 ? (int64_t)dx->h * dx->w : 1);
+    if (mag >= 16 && (vec ? dx->w <= kSepMaxW : true)) return 2;
+    return 0;
+}
+
+extern "C" int64_t hn_bilinear_bwd_workspace_bytes(const hn_tensor *dy, const hn_tensor *dx)
+{
+    if (!dy || !dx || dx->h <= 0 || dx->w <= 0) return 0;
+    if (bilinear_bwd_mode(dy, dx) != 2) return 0;
+    return (int64_t)sizeof(float) * dy->n * dy->h * dx->w * dx->c;
+}
+
+extern "C" int hn_bilinear_bwd(const hn_tensor *dy, const hn_tensor *dx, int32_t accumulate, void *workspace, int64_t workspace_bytes,
+                               void *stream)
 {
     HN_CHECK_ARG(dy && dx && dy->ptr && dx->ptr, "hn_bilinear_bwd: null pointer");
     HN_CHECK_ARG(dy->n == dx->n && dy->c == dx->c && dx->h > 0 && dx->w > 0, "hn_bilinear_bwd: shape mismatch");
@@ -653,6 +916,43 @@ extern "C" int hn_bilinear_bwd(const hn_tensor *dy, const hn_tensor *dx, int32_t
     const float sh = (float)dx->h / (float)dy->h, sw = (float)dx->w / (float)dy->w;
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = vec8_ok(dy) && vec8_ok(dx);
+    int mode = bilinear_bwd_mode(dy, dx);
+    if (mode == 2 && (!workspace || workspace_bytes < hn_bilinear_bwd_workspace_bytes(dy, dx))) mode = 0;   // no scratch: gather form
+    if (mode == 1) {
+        dim3 grid = row_grid_b((int64_t)dx->n * ((dx->h + 1) / 2), (int64_t)((dx->w + 1) / 2) * (dx->c / 8));
+#define HN_UP2_BWD(TG, TX) bilinear_up2_bwd_kernel<TG, TX><<<grid, 256, 0, st>>>((const TG *)dy->ptr, dy->ld, (TX *)dx->ptr, dx->ld, accumulate, dx->n, dx->h, dx->w, dx->c)
+        if (dy->dtype == HN_BF16 && dx->dtype == HN_BF16) HN_UP2_BWD(bf16, bf16);
+        else if (dy->dtype == HN_F32 && dx->dtype == HN_F32) HN_UP2_BWD(float, float);
+        else if (dy->dtype == HN_F32 && dx->dtype == HN_BF16) HN_UP2_BWD(float, bf16);
+        else HN_UP2_BWD(bf16, float);
+#undef HN_UP2_BWD
+        HN_LAUNCH_CHECK();
+        return HN_OK;
+    }
+    if (mode == 2) {
+        float *tmp = reinterpret_cast<float *>(workspace);
+        const int64_t nrows = (int64_t)dy->n * dy->h;
+        if (vec) {
+            const int g1 = wave_grid_b(nrows * (dx->c / 8), 256, 8);
+            if (dy->dtype == HN_BF16) bilinear_bwd_rows_vec_kernel<bf16><<<g1, 256, 0, st>>>((const bf16 *)dy->ptr, dy->ld, tmp, nrows, dx->w, dy->w, dx->c, sw);
+            else bilinear_bwd_rows_vec_kernel<float><<<g1, 256, 0, st>>>((const float *)dy->ptr, dy->ld, tmp, nrows, dx->w, dy->w, dx->c, sw);
+        } else {
+            const int g1 = wave_grid_b(nrows * dx->w * dx->c, 256, 8);
+            if (dy->dtype == HN_BF16) bilinear_bwd_rows_scalar_kernel<bf16><<<g1, 256, 0, st>>>((const bf16 *)dy->ptr, dy->ld, tmp, nrows, dx->w, dy->w, dx->c, sw);
+            else bilinear_bwd_rows_scalar_kernel<float><<<g1, 256, 0, st>>>((const float *)dy->ptr, dy->ld, tmp, nrows, dx->w, dy->w, dx->c, sw);
+        }
+        HN_LAUNCH_CHECK();
+        const int g2 = wave_grid_b((int64_t)dx->n * dx->h * dx->w * (vec ? dx->c / 8 : dx->c), 256, 8);
+        if (vec) {
+            if (dx->dtype == HN_BF16) bilinear_bwd_cols_kernel<bf16, true><<<g2, 256, 0, st>>>(tmp, (bf16 *)dx->ptr, dx->ld, accumulate, dx->n, dx->h, dx->w, dy->h, dx->c, sh);
+            else bilinear_bwd_cols_kernel<float, true><<<g2, 256, 0, st>>>(tmp, (float *)dx->ptr, dx->ld, accumulate, dx->n, dx->h, dx->w, dy->h, dx->c, sh);
+        } else {
+            if (dx->dtype == HN_BF16) bilinear_bwd_cols_kernel<bf16, false><<<g2, 256, 0, st>>>(tmp, (bf16 *)dx->ptr, dx->ld, accumulate, dx->n, dx->h, dx->w, dy->h, dx->c, sh);
+            else bilinear_bwd_cols_kernel<float, false><<<g2, 256, 0, st>>>(tmp, (float *)dx->ptr, dx->ld, accumulate, dx->n, dx->h, dx->w, dy->h, dx->c, sh);
+        }
+        HN_LAUNCH_CHECK();
+        return HN_OK;
+    }
     dim3 grid = row_grid_b((int64_t)dx->n * dx->h, (int64_t)dx->w * (vec ? dx->c / 8 : dx->c));
 #define HN_BIL_BWD(TG, TX)                                                                                                            \
     do {                                                                                                                              \

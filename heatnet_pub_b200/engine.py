@@ -906,8 +906,12 @@ def maxpool3x3s2_bwd(dy: Act, idx: torch.Tensor, dx: Act, add: bool):
 
 
 def bilinear_bwd(dy: Act, dx: Act, add: bool):
-    _lib.check(_lib.load().hn_bilinear_bwd(C.byref(dy.hn()), C.byref(dx.hn()), int(add), _stream()))
-    _count()
+    lib = _lib.load()
+    dyh, dxh = dy.hn(), dx.hn()
+    ws_bytes = lib.hn_bilinear_bwd_workspace_bytes(C.byref(dyh), C.byref(dxh))
+    ws_ptr = workspace(ws_bytes, dy.buf.device).data_ptr() if ws_bytes else None
+    _lib.check(lib.hn_bilinear_bwd(C.byref(dyh), C.byref(dxh), int(add), ws_ptr, ws_bytes, _stream()))
+    _count(2 if ws_bytes else 1)
 
 
 def pyramid_pool_bwd(dpool: torch.Tensor, sizes: Sequence[int], dx: Act, add: bool):

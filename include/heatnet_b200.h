@@ -158,7 +158,11 @@ int hn_accumulate(const hn_tensor *x, const hn_tensor *y, int32_t accumulate, vo
 int hn_maxpool3x3s2_fwd_idx(const hn_tensor *x, const hn_tensor *y, uint8_t *idx, void *stream);
 int hn_maxpool3x3s2_bwd(const hn_tensor *dy, const uint8_t *idx, const hn_tensor *dx, int32_t accumulate, void *stream);
 /* adjoints of hn_bilinear_fwd / hn_pyramid_pool_fwd (gather form, deterministic) */
-int hn_bilinear_bwd(const hn_tensor *dy, const hn_tensor *dx, int32_t accumulate, void *stream);
+/* adjoint of hn_bilinear_fwd: exact 2x (PSPUpsample) in 2x2 micro-tiles; large magnifications (PSP priors, the critics' x32
+ * maps) by a separable two-pass reduction through an FP32 workspace of hn_bilinear_bwd_workspace_bytes() (0 = not needed;
+ * without it the generic gather form runs); deterministic, no atomics */
+int64_t hn_bilinear_bwd_workspace_bytes(const hn_tensor *dy, const hn_tensor *dx);
+int hn_bilinear_bwd(const hn_tensor *dy, const hn_tensor *dx, int32_t accumulate, void *workspace, int64_t workspace_bytes, void *stream);
 int hn_pyramid_pool_bwd(const void *dpool, const int32_t *sizes, int32_t nsizes, const hn_tensor *dx, int32_t accumulate, void *stream);
 /* conv dgrad = hn_conv2d_fwd of the (zero-inserted, for stride > 1) output gradient with the flipped/transposed pack */
 int hn_dilate(const hn_tensor *x, int32_t stride, const hn_tensor *up, void *stream);

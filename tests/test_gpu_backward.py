@@ -186,8 +186,12 @@ def test_maxpool_backward(E, dtype, hw):
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
-@pytest.mark.parametrize("sizes", [((6, 6), (40, 80)), ((1, 1), (8, 12)), ((8, 12), (16, 24)), ((41, 60), (82, 120)), ((3, 3), (11, 30)), ((2, 3), (64, 96))])
+@pytest.mark.parametrize("sizes", [((6, 6), (40, 80)), ((1, 1), (8, 12)), ((8, 12), (16, 24)), ((41, 60), (82, 120)), ((3, 3), (11, 30)), ((2, 3), (64, 96)),
+                                   ((1, 1), (2, 2)), ((5, 7), (10, 14)), ((1, 9), (2, 18)), ((7, 1), (14, 2)),      # exact 2x, odd sizes (2x2 micro-tiles)
+                                   ((2, 2), (40, 80)), ((6, 8), (41, 83)), ((3, 12), (30, 120))])                    # separable two-pass / gather fallback (W > 8)
 def test_bilinear_backward(E, dtype, tol, sizes):
+    """All three adjoint algorithms (exact-2x micro-tiles, separable two-pass, generic gather) against autograd of
+    F.interpolate (= the reference's F.upsample / nn.Upsample), plus the accumulate flag."""
     (h, w), (ho, wo) = sizes
     g = torch.Generator().manual_seed(6)
     x = torch.randn(2, 64, h, w, generator=g, requires_grad=True)
@@ -197,15 +201,32 @@ def test_bilinear_backward(E, dtype, tol, sizes):
     dx = E.new_act(2, h, w, 64, dtype, "cuda")
     E.bilinear_bwd(to_act(E, dy, dtype), dx, False)
     assert rel(back(dx), x.grad) < tol
+    E.bilinear_bwd(to_act(E, dy, dtype), dx, True)
+    assert rel(back(dx), 2 * x.grad) < 2 * tol
 
 
-def test_bilinear_backward_single_channel_x32(E):
+def test_bilinear_backward_into_channel_slice(E):
+    """dx is a channel slice of a wider buffer (zero-copy concat): neighbours must stay untouched."""
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 64, 6, 8, generator=g, requires_grad=True)
+    y = F.interpolate(x, size=(12, 16), mode="bilinear", align_corners=False)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    wide = E.Act(torch.full((2, 6, 8, 192), 7.0, device="cuda"))
+    E.bilinear_bwd(to_act(E, dy, torch.float32), wide.slice(64, 64), False)
+    assert rel(back(wide.slice(64, 64)), x.grad) < 1e-5
+    assert torch.all(wide.buf[..., :64] == 7.0) and torch.all(wide.buf[..., 128:] == 7.0)
+
+
+@pytest.mark.parametrize("hw", [(2, 3), (10, 20), (1, 1), (5, 9)])
+def test_bilinear_backward_single_channel_x32(E, hw):
+    """The critics' nn.Upsample(scale_factor=32) adjoint on single-channel FP32 maps (cm/discriminator_model.py:46,61)."""
     g = torch.Generator().manual_seed(7)
-    x = torch.randn(2, 1, 2, 3, generator=g, requires_grad=True)
+    x = torch.randn(2, 1, *hw, generator=g, requires_grad=True)
     y = nn.Upsample(scale_factor=32, mode='bilinear')(x)
     dy = torch.randn(y.shape, generator=g)
     y.backward(dy)
-    dx = E.new_act(2, 2, 3, 1, torch.float32, "cuda")
+    dx = E.new_act(2, hw[0], hw[1], 1, torch.float32, "cuda")
     E.bilinear_bwd(to_act(E, dy, torch.float32), dx, False)
     assert rel(back(dx), x.grad) < 1e-5
 
