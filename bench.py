@@ -309,6 +309,25 @@ def run_train(args):
     ms = t.item()
     launches = E.launch_count - l0
     clocks = sampler.stop() if sampler else None
+    if rank == 0 and args.layer_table:
+        # per C-ABI-call device timeline of ONE step (needs HN_TIMELINE=1 at start-up), aggregated by call + geometry
+        from heatnet_pub_b200 import _lib as L
+        if not os.environ.get("HN_TIMELINE"):
+            raise SystemExit("--layer-table on a training workload needs HN_TIMELINE=1 in the environment")
+        L.timeline = []
+        step()
+        torch.cuda.synchronize()
+        recs, L.timeline = L.timeline, None
+        agg = {}
+        for name, desc, a, b in recs:
+            e = agg.setdefault((name, desc), [0, 0.0])
+            e[0] += 1
+            e[1] += a.elapsed_time(b)
+        rows = [{"call": k[0], "what": k[1], "launches_per_step": v[0], "ms_per_step": v[1]} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])]
+        by_call = {}
+        for r in rows:
+            by_call[r["call"]] = by_call.get(r["call"], 0.0) + r["ms_per_step"]
+        json.dump({"by_call_ms": dict(sorted(by_call.items(), key=lambda kv: -kv[1])), "rows": rows}, open(args.layer_table, "w"), indent=1)
     if rank == 0:
         peaks, peak_src = load_peaks()
         imgs = 2 * B * world * args.steps
@@ -332,6 +351,110 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------- iou_eval (config 5)
+def run_iou_eval(args):
+    """BASELINE.json configs[4]: iou_eval.IoU(14, ignore [12,13]) over synthetic 320x640 int64 label maps in chunks of
+    `--batch` maps (default 500; 20 steps = 10 000 maps = 2.048e9 pixels).  A step = IoU.add(pred, target) on one chunk.
+    value: label maps/s with the chunk resident in HBM (includes the K*K D2H + host int32 accumulate every step);
+    e2e: the same call on pinned HOST int64 tensors (H2D of 16 B/pixel inside the timed region);
+    roofline: hn_confusion alone, 16 algorithmic bytes per pixel, against the measured HBM copy bandwidth."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from heatnet_pub_b200 import _lib, iou_eval, engine as E
+    K, H, W = 14, 320, 640
+    maps = args.batch if args.batch != 16 else 500
+    g = torch.Generator(device=dev).manual_seed(SEED + rank)
+    pred = torch.randint(0, K, (maps, H, W), generator=g, device=dev)
+    target = torch.randint(0, K, (maps, H, W), generator=g, device=dev)
+    npix = maps * H * W
+    metric = iou_eval.IoU(K, False, [12, 13])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    for _ in range(args.warmup):
+        metric.add(pred, target)
+    metric.reset()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms = timed(lambda: metric.add(pred, target), args.steps)
+    clocks = sampler.stop() if sampler else None
+    # size-independent property: every pixel counted exactly once per step (modulo 2^32: the reference's accumulator is int32)
+    assert int(metric.conf_metric.conf.astype(np.uint32).sum(dtype=np.uint64)) % (1 << 32) == (npix * args.steps) % (1 << 32)
+    iou, miou = metric.value()
+
+    # kernel alone (no D2H): CUDA events on the launching stream
+    lib = _lib.load()
+    out = torch.zeros(K * K + 1, dtype=torch.int64, device=dev)
+    flags = out[K * K:].view(torch.int32)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    kern = lambda: _lib.check(lib.hn_confusion(pred.data_ptr(), None, 1, npix, target.data_ptr(), K, out.data_ptr(), flags.data_ptr(), st))
+    for _ in range(3):
+        kern()
+    kms = timed(kern, args.steps) / args.steps
+    assert int(out[:K * K].sum().item()) == npix * (args.steps + 3)
+
+    # e2e from pinned host memory
+    pred_h, target_h = pred.cpu().pin_memory(), target.cpu().pin_memory()
+    metric.reset()
+    metric.add(pred_h, target_h)
+    e2e_ms = timed(lambda: metric.add(pred_h, target_h), args.steps)
+
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        achieved = 16.0 * npix / (kms / 1e3) / 1e9
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle.iou_oracle import IoUOracle
+            o = IoUOracle(K, False, [12, 13])
+            n_cpu = min(maps, 200)
+            ph, th = pred_h[:n_cpu].numpy(), target_h[:n_cpu].numpy()
+            t0 = time.perf_counter()
+            o.add(ph, th)
+            dt = time.perf_counter() - t0
+            cpu = {"value": n_cpu / dt, "unit": "label maps/s", "cores": 1, "kind": "port",
+                   "sample": f"{n_cpu} maps of {H}x{W} through oracle.iou_oracle.IoUOracle.add (numpy bincount, the reference's arithmetic)"}
+        line = {"metric": "iou_eval_label_maps_per_sec", "value": maps * world * args.steps / (ms / 1e3), "unit": "label maps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+                "config": {"workload": f"iou_eval.IoU(14, ignore [12,13]).add over {maps} pred/target int64 label maps of {H}x{W} per step per GPU "
+                                       f"({args.steps} steps = {maps * args.steps} maps per GPU)", "maps_per_step": maps, "parallelism": f"map-sharded x{world}, no collective",
+                           "l2": "each step streams 1.6 GB of labels (>> 126 MB L2); no explicit flush"},
+                "e2e": {"value": maps * world * args.steps / (e2e_ms / 1e3), "unit": "label maps/s", "h2d_bytes_per_step": 16 * npix,
+                        "d2h_bytes_per_step": 8 * (K * K + 1), "what": "IoU.add on pinned host int64 tensors: H2D + histogram + K*K D2H per step"},
+                "gpu_launches": args.steps, "clocks": clocks, "miou": float(miou),
+                "roofline": {"kernel": "confusion_labels_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                             "traffic": None, "kernel_ms": kms, "algorithmic_bytes_per_pixel": 16, "peak_source": peak_src},
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ---------------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -347,13 +470,15 @@ def main():
     ap.add_argument("--no-optimizer", action="store_true", help="training workloads: leave the optimizer step out of the timed step")
     ap.add_argument("--torch-losses", action="store_true", help="training workloads: torch criteria instead of the fused loss kernels")
     ap.add_argument("--layer-table", default=None, help="write the per-conv-launch timing table (JSON) here")
-    ap.add_argument("--workload", default="infer", choices=["infer", "train_seg", "train_critic"],
+    ap.add_argument("--workload", default="infer", choices=["infer", "train_seg", "train_critic", "iou_eval"],
                     help="infer = the headline (BASELINE configs[1]); train_* = one adversarial training step (configs[2]/[3]): "
                          "per-GPU batch of --batch day+night pairs at --height x --width, fwd + bwd + NCCL gradient all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    if args.workload == "iou_eval":
+        return run_iou_eval(args)
     if args.workload != "infer":
         return run_train(args)
 

@@ -59,7 +59,9 @@ SIGNATURES = {
     "hn_channel_stats": (C.c_int, [_T, _P, _P, _P]),
     "hn_bn_finalize": (C.c_int, [_P, _P, _I64, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _I32, _P]),
     "hn_act_bwd": (C.c_int, [_T, _T, _I32, _F, _T, _P]),
-    "hn_bn_bwd": (C.c_int, [_T, _T, _T, _P, _P, _P, _I32, _F, _P, _P, _T, _T, _I32, _I32, _P]),
+    "hn_bn_bwd": (C.c_int, [_T, _T, _T, _P, _P, _P, _I32, _F, _P, _P, _T, _T, _I32, _I32, _P, _P, _P, _I32, _P]),
+    "hn_bn_batch_stats_scratch_bytes": (_I64, [_I32]),
+    "hn_bn_batch_stats": (C.c_int, [_T, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
     "hn_accumulate": (C.c_int, [_T, _T, _I32, _P]),
     "hn_maxpool3x3s2_fwd_idx": (C.c_int, [_T, _T, _P, _P]),
     "hn_maxpool3x3s2_bwd": (C.c_int, [_T, _P, _T, _I32, _P]),
@@ -99,8 +101,58 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)        # AttributeError if the .so lacks a declared symbol
             fn.restype, fn.argtypes = res, args
+        if os.environ.get("HN_TIMELINE"):
+            lib = _Timed(lib)
         _lib = lib
     return _lib
+
+
+# ---- optional per-call device timeline (HN_TIMELINE=1): CUDA events around every enqueueing C-ABI call, used by
+# bench.py --layer-table on the training workloads.  `timeline` is a list while recording, else None.
+timeline = None
+_NO_TIMING = {"hn_last_error", "hn_version", "hn_device_check", "hn_prof_read", "hn_conv_cout_pad", "hn_conv_kpad", "hn_optim_chunk",
+              "hn_conv2d_workspace_bytes", "hn_conv2d_wgrad_workspace_bytes", "hn_pyramid_pool_workspace_bytes",
+              "hn_bilinear_bwd_workspace_bytes", "hn_loss_scratch_bytes", "hn_bn_batch_stats_scratch_bytes"}
+
+
+def _describe(name, args):
+    try:
+        if name in ("hn_conv2d_fwd", "hn_conv2d_wgrad", "hn_upconv3x3_fwd"):
+            x, cv = args[0]._obj, args[2]._obj
+            return f"{x.c}->{cv.cout} k{cv.r} s{cv.stride} d{cv.dil} @{x.h}x{x.w} n{x.n}"
+        if name in ("hn_bilinear_bwd", "hn_bilinear_fwd"):
+            a, b = args[0]._obj, args[1]._obj
+            return f"{a.h}x{a.w}->{b.h}x{b.w} c{a.c}"
+        if hasattr(args[0], "_obj") and isinstance(args[0]._obj, HnTensor):
+            x = args[0]._obj
+            return f"c{x.c} @{x.h}x{x.w} n{x.n} dt{x.dtype}"
+    except Exception:
+        pass
+    return ""
+
+
+class _Timed:
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if name in _NO_TIMING:
+            return fn
+
+        def call(*args):
+            if timeline is None:
+                return fn(*args)
+            import torch
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rc = fn(*args)
+            b.record()
+            timeline.append((name, _describe(name, args), a, b))
+            return rc
+
+        setattr(self, name, call)
+        return call
 
 
 def check(rc: int):

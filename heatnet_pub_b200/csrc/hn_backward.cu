@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(256) act_bwd_scalar_kernel(const TG *__restric
 //   apply : draw = gamma*invstd*(dz - s1/m - xhat*s2/m)   and   dres (+)= dz
 // blockDim = (CVB, PL) as in channel_stats_kernel.
 // ------------------------------------------------------------------------------------------------
-template <typename TG, typename TO>
-__global__ void bn_bwd_reduce_kernel(const TG *__restrict__ dout, int ldg, const TO *__restrict__ out, int ldo, const float *__restrict__ raw,
+template <typename TG, typename TO, typename TR>
+__global__ void bn_bwd_reduce_kernel(const TG *__restrict__ dout, int ldg, const TO *__restrict__ out, int ldo, const TR *__restrict__ raw,
                                      int ldr, const float *__restrict__ mean, const float *__restrict__ invstd, int act, float slope,
                                      const float *slope_ptr, int64_t npix, int C, int64_t pix_per_cta, double *s1, double *s2,
                                      double *sprelu)
@@ -97,7 +97,7 @@ __global__ void bn_bwd_reduce_kernel(const TG *__restrict__ dout, int ldg, const
             float g[8], o[8], r[8];
             Vec8<TG>::load(dout + p * ldg + cv * 8, g);
             Vec8<TO>::load(out + p * ldo + cv * 8, o);
-            Vec8<float>::load(raw + p * ldr + cv * 8, r);
+            Vec8<TR>::load(raw + p * ldr + cv * 8, r);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if (sprelu && o[i] < 0.f) sp += g[i] * (o[i] / slope);      // z = out / slope on the negative side
@@ -137,20 +137,29 @@ __global__ void bn_bwd_reduce_kernel(const TG *__restrict__ dout, int ldg, const
 // blockDim = (CVB, PL) like the reduce pass: a thread keeps ONE 8-channel group for all its pixels, so the per-channel
 // coefficients (FP64 sums -> three FP32 vectors) are formed once per thread and the pixel loop only moves data:
 //   draw = ka*dz + kb*(raw - mean) + kc,   ka = gamma*invstd, kb = -ka*invstd*s2/m, kc = -ka*s1/m
-template <typename TG, typename TO>
+template <typename TG, typename TO, typename TR>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TG *__restrict__ dout, int ldg, const TO *__restrict__ out, int ldo,
-                                                           const float *__restrict__ raw, int ldr, const float *__restrict__ mean,
+                                                           const TR *__restrict__ raw, int ldr, const float *__restrict__ mean,
                                                            const float *__restrict__ invstd, const float *__restrict__ gamma,
                                                            const double *__restrict__ s1, const double *__restrict__ s2, double inv_count,
                                                            int act, float slope, const float *slope_ptr, TG *__restrict__ draw, int ldd,
                                                            TG *__restrict__ dres, int ldres, int dres_accumulate, int64_t npix, int C,
-                                                           int64_t pix_per_cta)
+                                                           int64_t pix_per_cta, float *__restrict__ dbeta, float *__restrict__ dgamma,
+                                                           float *__restrict__ dslope, const double *__restrict__ sprelu, int param_accumulate)
 {
     const int cv = blockIdx.y * blockDim.x + threadIdx.x;
     if (cv >= C / 8) return;
     const int PL = blockDim.y;
     const int c = cv * 8;
     if (slope_ptr) slope = __ldg(slope_ptr);
+    if (blockIdx.x == 0 && threadIdx.y == 0) {      // parameter gradients straight from the FP64 sums (no extra launches)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (dbeta) dbeta[c + j] = (param_accumulate ? dbeta[c + j] : 0.f) + (float)s1[c + j];
+            if (dgamma) dgamma[c + j] = (param_accumulate ? dgamma[c + j] : 0.f) + (float)s2[c + j];
+        }
+        if (dslope && sprelu && cv == 0) dslope[0] = (param_accumulate ? dslope[0] : 0.f) + (float)sprelu[0];
+    }
     float mu[8], ka[8], kb[8], kc[8];
     {
         float is[8], ga[8];
@@ -192,8 +201,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TG *__restrict_
         Vec8<TG>::load(dout + (p + PL) * ldg + c, g1);
         Vec8<TO>::load(out + p * ldo + c, o0);
         Vec8<TO>::load(out + (p + PL) * ldo + c, o1);
-        Vec8<float>::load(raw + p * ldr + c, r0);
-        Vec8<float>::load(raw + (p + PL) * ldr + c, r1);
+        Vec8<TR>::load(raw + p * ldr + c, r0);
+        Vec8<TR>::load(raw + (p + PL) * ldr + c, r1);
         one(p, g0, o0, r0);
         one(p + PL, g1, o1, r1);
     }
@@ -201,7 +210,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TG *__restrict_
         float g0[8], o0[8], r0[8];
         Vec8<TG>::load(dout + p * ldg + c, g0);
         Vec8<TO>::load(out + p * ldo + c, o0);
-        Vec8<float>::load(raw + p * ldr + c, r0);
+        Vec8<TR>::load(raw + p * ldr + c, r0);
         one(p, g0, o0, r0);
     }
 }
@@ -792,11 +801,12 @@ extern "C" int hn_act_bwd(const hn_tensor *dout, const hn_tensor *out, int32_t a
 
 extern "C" int hn_bn_bwd(const hn_tensor *dout, const hn_tensor *out, const hn_tensor *raw, const float *mean, const float *invstd,
                          const float *gamma, int32_t act, float slope, const float *slope_ptr, double *sums /* [2*C + 1] scratch+result */,
-                         const hn_tensor *draw, const hn_tensor *dres, int32_t dres_accumulate, int32_t want_prelu_grad, void *stream)
+                         const hn_tensor *draw, const hn_tensor *dres, int32_t dres_accumulate, int32_t want_prelu_grad, float *dbeta, float *dgamma,
+                         float *dslope, int32_t param_accumulate, void *stream)
 {
     HN_CHECK_ARG(dout && out && raw && mean && invstd && sums && draw, "hn_bn_bwd: null pointer");
     HN_CHECK_ARG(same_shape(dout, out) && same_shape(dout, raw) && same_shape(dout, draw), "hn_bn_bwd: shape mismatch");
-    HN_CHECK_ARG(raw->dtype == HN_F32, "hn_bn_bwd: the pre-normalisation tensor is FP32");
+    HN_CHECK_ARG(raw->dtype == HN_F32 || (raw->dtype == HN_BF16 && dout->dtype == HN_BF16), "hn_bn_bwd: the pre-normalisation tensor is FP32 (or BF16 on the BF16 path)");
     HN_CHECK_ARG(dout->dtype == draw->dtype && (!dres || dres->dtype == dout->dtype), "hn_bn_bwd: gradient dtypes must match");
     HN_CHECK_ARG(vec8_ok(dout) && vec8_ok(out) && vec8_ok(raw) && vec8_ok(draw) && (!dres || vec8_ok(dres)), "hn_bn_bwd: views must be 8-channel aligned");
     const int C = dout->c;
@@ -822,13 +832,14 @@ extern "C" int hn_bn_bwd(const hn_tensor *dout, const hn_tensor *out, const hn_t
     chunks2 = cdiv(npix, pix_per_cta2);
     dim3 grid2((unsigned)chunks2, (unsigned)cvblocks);
     const double inv_count = 1.0 / (double)npix;
-#define HN_BN_BWD(TG, TO)                                                                                                                 \
+#define HN_BN_BWD(TG, TO, TR)                                                                                                             \
     do {                                                                                                                                  \
-        bn_bwd_reduce_kernel<TG, TO><<<grid, block, smem, st>>>((const TG *)dout->ptr, dout->ld, (const TO *)out->ptr, out->ld, (const float *)raw->ptr, raw->ld, mean, invstd, act, slope, slope_ptr, npix, C, pix_per_cta, s1, s2, sp); \
-        bn_bwd_apply_kernel<TG, TO><<<grid2, block, 0, st>>>((const TG *)dout->ptr, dout->ld, (const TO *)out->ptr, out->ld, (const float *)raw->ptr, raw->ld, mean, invstd, gamma, s1, s2, inv_count, act, slope, slope_ptr, (TG *)draw->ptr, draw->ld, dres ? (TG *)dres->ptr : nullptr, dres ? dres->ld : 0, dres_accumulate, npix, C, pix_per_cta2); \
+        bn_bwd_reduce_kernel<TG, TO, TR><<<grid, block, smem, st>>>((const TG *)dout->ptr, dout->ld, (const TO *)out->ptr, out->ld, (const TR *)raw->ptr, raw->ld, mean, invstd, act, slope, slope_ptr, npix, C, pix_per_cta, s1, s2, sp); \
+        bn_bwd_apply_kernel<TG, TO, TR><<<grid2, block, 0, st>>>((const TG *)dout->ptr, dout->ld, (const TO *)out->ptr, out->ld, (const TR *)raw->ptr, raw->ld, mean, invstd, gamma, s1, s2, inv_count, act, slope, slope_ptr, (TG *)draw->ptr, draw->ld, dres ? (TG *)dres->ptr : nullptr, dres ? dres->ld : 0, dres_accumulate, npix, C, pix_per_cta2, dbeta, dgamma, want_prelu_grad ? dslope : nullptr, sp, param_accumulate); \
     } while (0)
-    if (dout->dtype == HN_BF16 && out->dtype == HN_BF16) HN_BN_BWD(bf16, bf16);
-    else if (dout->dtype == HN_F32 && out->dtype == HN_F32) HN_BN_BWD(float, float);
+    if (dout->dtype == HN_BF16 && out->dtype == HN_BF16 && raw->dtype == HN_BF16) HN_BN_BWD(bf16, bf16, bf16);
+    else if (dout->dtype == HN_BF16 && out->dtype == HN_BF16) HN_BN_BWD(bf16, bf16, float);
+    else if (dout->dtype == HN_F32 && out->dtype == HN_F32) HN_BN_BWD(float, float, float);
     else {
         set_error("hn_bn_bwd: unsupported dtype combination");
         return HN_ERR_ARG;

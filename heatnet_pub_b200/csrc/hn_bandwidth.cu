@@ -140,9 +140,39 @@ __global__ void bn_fold_kernel(const float *gamma, const float *beta, const floa
 // BatchNorm2d train-mode statistics / finalize, and the fused apply pass
 // ------------------------------------------------------------------------------------------------
 // blockDim = (CVB, PL): CVB 8-channel vectors x PL pixel lanes.  grid = (pixel chunks, cvec blocks)
+// Optional fused finalize (hn_bn_batch_stats): the LAST CTA to finish (ticket counter) turns the sums into the BatchNorm2d
+// scale/shift, the saved mean/invstd and the running-statistic update, so a train-mode BN forward is memset + ONE kernel.
+struct BnFinalize {
+    unsigned int *ticket;      // nullptr: plain statistics
+    double count;
+    const float *gamma, *beta;
+    float eps, momentum;
+    float *running_mean, *running_var;
+    long long *num_batches_tracked;
+    float *scale, *shift, *save_mean, *save_invstd;
+};
+
+__device__ __forceinline__ void bn_finalize_channel(int c, double s, double q, const BnFinalize &f)
+{
+    double mean = s / f.count;
+    double var = q / f.count - mean * mean;
+    if (var < 0) var = 0;
+    double invstd = 1.0 / sqrt(var + (double)f.eps);
+    float g = f.gamma ? f.gamma[c] : 1.f, b = f.beta ? f.beta[c] : 0.f;
+    f.scale[c] = (float)(g * invstd);
+    f.shift[c] = (float)(b - mean * g * invstd);
+    if (f.save_mean) f.save_mean[c] = (float)mean;
+    if (f.save_invstd) f.save_invstd[c] = (float)invstd;
+    if (f.running_mean) {
+        double unbiased = f.count > 1 ? var * f.count / (f.count - 1.0) : var;
+        f.running_mean[c] = (float)((1.0 - f.momentum) * f.running_mean[c] + f.momentum * mean);
+        f.running_var[c] = (float)((1.0 - f.momentum) * f.running_var[c] + f.momentum * unbiased);
+    }
+}
+
 template <typename T>
 __global__ void channel_stats_kernel(const T *__restrict__ x, int64_t npix, int C, int ld, int64_t pix_per_cta, double *sum,
-                                     double *sqsum)
+                                     double *sqsum, BnFinalize fin)
 {
     extern __shared__ float red[];  // [2][PL][CVB*8]
     const int cv = blockIdx.y * blockDim.x + threadIdx.x;
@@ -183,6 +213,18 @@ __global__ void channel_stats_kernel(const T *__restrict__ x, int64_t npix, int 
         if (ch < C) {
             atomicAdd(sum + ch, a);
             atomicAdd(sqsum + ch, b);
+        }
+    }
+    if (fin.ticket) {
+        __shared__ bool last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) last = atomicAdd(fin.ticket, 1u) == gridDim.x * gridDim.y - 1;
+        __syncthreads();
+        if (last) {
+            __threadfence();
+            for (int c = tid; c < C; c += CVB * PL) bn_finalize_channel(c, __ldcg(sum + c), __ldcg(sqsum + c), fin);
+            if (tid == 0 && fin.num_batches_tracked) *fin.num_batches_tracked += 1;
         }
     }
 }
@@ -237,6 +279,8 @@ __global__ void bn_finalize_kernel(const double *sum, const double *sqsum, doubl
         running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
     }
 }
+
+__global__ void bn_count_kernel(long long *num_batches_tracked) { *num_batches_tracked += 1; }
 
 template <typename TI, typename T>
 __global__ void __launch_bounds__(256) affine_act_kernel(const TI *__restrict__ x, int ldx, const float *__restrict__ scale,
@@ -704,9 +748,67 @@ extern "C" int hn_channel_stats(const hn_tensor *x, double *sum, double *sqsum, 
     dim3 grid((unsigned)chunks, (unsigned)cvblocks), block(CVB, PL);
     size_t smem = (size_t)2 * PL * CVB * 8 * sizeof(float);
     if (x->dtype == HN_BF16)
-        channel_stats_kernel<__nv_bfloat16><<<grid, block, smem, st>>>((const __nv_bfloat16 *)x->ptr, npix, x->c, x->ld, pix_per_cta, sum, sqsum);
+        channel_stats_kernel<__nv_bfloat16><<<grid, block, smem, st>>>((const __nv_bfloat16 *)x->ptr, npix, x->c, x->ld, pix_per_cta, sum, sqsum, BnFinalize{});
     else
-        channel_stats_kernel<float><<<grid, block, smem, st>>>((const float *)x->ptr, npix, x->c, x->ld, pix_per_cta, sum, sqsum);
+        channel_stats_kernel<float><<<grid, block, smem, st>>>((const float *)x->ptr, npix, x->c, x->ld, pix_per_cta, sum, sqsum, BnFinalize{});
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int64_t hn_bn_batch_stats_scratch_bytes(int32_t c) { return (int64_t)sizeof(double) * (2 * (int64_t)c + 1); }
+
+extern "C" int hn_bn_batch_stats(const hn_tensor *x, void *scratch, const float *gamma, const float *beta, float eps, float momentum,
+                                 float *running_mean, float *running_var, int64_t *num_batches_tracked, float *scale, float *shift,
+                                 float *save_mean, float *save_invstd, void *stream)
+{
+    HN_CHECK_ARG(x && x->ptr && scratch && scale && shift, "hn_bn_batch_stats: null pointer");
+    HN_CHECK_ARG(x->c >= 1 && x->ld >= x->c, "hn_bn_batch_stats: bad channel strides");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t npix = (int64_t)x->n * x->h * x->w;
+    HN_CHECK_ARG(npix > 0, "hn_bn_batch_stats: empty input");
+    double *sum = reinterpret_cast<double *>(scratch), *sqsum = sum + x->c;
+    if (!vec8_ok(x)) {      // narrow / unaligned views: the three-launch sequence
+        int rc = hn_channel_stats(x, sum, sqsum, stream);
+        if (rc) return rc;
+        rc = hn_bn_finalize(sum, sqsum, npix, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, save_mean, save_invstd, x->c,
+                            stream);
+        if (rc) return rc;
+        if (num_batches_tracked) {
+            // rare path (C not a multiple of 8): a one-thread finalize of the counter
+            bn_count_kernel<<<1, 1, 0, st>>>(reinterpret_cast<long long *>(num_batches_tracked));
+            HN_LAUNCH_CHECK();
+        }
+        return HN_OK;
+    }
+    HN_CUDA(cudaMemsetAsync(scratch, 0, (size_t)hn_bn_batch_stats_scratch_bytes(x->c), st));
+    const int ncv = x->c / 8;
+    const int CVB = ncv < 32 ? ncv : 32;
+    const int PL = 256 / CVB;
+    const int cvblocks = (int)cdiv(ncv, CVB);
+    int64_t chunks = cdiv((int64_t)num_sms() * 4, cvblocks);
+    int64_t pix_per_cta = cdiv(npix, chunks);
+    if (pix_per_cta < (int64_t)PL * 8) pix_per_cta = (int64_t)PL * 8;
+    chunks = cdiv(npix, pix_per_cta);
+    dim3 grid((unsigned)chunks, (unsigned)cvblocks), block(CVB, PL);
+    size_t smem = (size_t)2 * PL * CVB * 8 * sizeof(float);
+    BnFinalize f{};
+    f.ticket = reinterpret_cast<unsigned int *>(sum + 2 * x->c);
+    f.count = (double)npix;
+    f.gamma = gamma;
+    f.beta = beta;
+    f.eps = eps;
+    f.momentum = momentum;
+    f.running_mean = running_mean;
+    f.running_var = running_var;
+    f.num_batches_tracked = reinterpret_cast<long long *>(num_batches_tracked);
+    f.scale = scale;
+    f.shift = shift;
+    f.save_mean = save_mean;
+    f.save_invstd = save_invstd;
+    if (x->dtype == HN_BF16)
+        channel_stats_kernel<__nv_bfloat16><<<grid, block, smem, st>>>((const __nv_bfloat16 *)x->ptr, npix, x->c, x->ld, pix_per_cta, sum, sqsum, f);
+    else
+        channel_stats_kernel<float><<<grid, block, smem, st>>>((const float *)x->ptr, npix, x->c, x->ld, pix_per_cta, sum, sqsum, f);
     HN_LAUNCH_CHECK();
     return HN_OK;
 }

@@ -10,12 +10,21 @@
 
 namespace hn {
 
-constexpr int kMaxIterBeforeFlush = 16000;  // x2 pixels per lane per iteration x2 unroll < 65535
+constexpr int kLabelUnroll = 4;
+constexpr int kMaxIterBeforeFlush = 8000;  // x2 pixels per lane per load x4 unroll = 64000 < 65535 (+ the tail loop's < 8)
+
+// streaming 16-byte load: read-only path, no L1 allocation (every label is touched once)
+__device__ __forceinline__ longlong2 ld_stream(const longlong2 *p)
+{
+    longlong2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+    return v;
+}
 
 __device__ __forceinline__ void count_pixel(uint32_t *table, int lane, long long p, long long t, int K, int &flags)
 {
-    bool pbad = (p < 0) | (p >= K);
-    bool tbad = (t < 0) | (t >= K);
+    bool pbad = (unsigned long long)p >= (unsigned long long)K;
+    bool tbad = (unsigned long long)t >= (unsigned long long)K;
     if (pbad | tbad) {
         flags |= (pbad ? 1 : 0) | (tbad ? 2 : 0);
         return;
@@ -46,8 +55,10 @@ __device__ __forceinline__ void flush_table(uint32_t *table, int lane, int nword
     __syncwarp();
 }
 
-// label path: pred and target are int64 [n]
-__global__ void __launch_bounds__(256) confusion_labels_kernel(const long long *__restrict__ pred,
+// label path: pred and target are int64 [n].  Latency-bound unless enough bytes are in flight (Little: ~35 KB per SM at
+// 6.5 TB/s): each lane issues 2*U independent 16-byte loads before the first use, 16 warps per SM -> 64 KB in flight.
+template <int U>
+__global__ void __launch_bounds__(512) confusion_labels_kernel(const long long *__restrict__ pred,
                                                                const long long *__restrict__ target, long long n, int K,
                                                                unsigned long long *conf, int *flags_out)
 {
@@ -64,14 +75,18 @@ __global__ void __launch_bounds__(256) confusion_labels_kernel(const long long *
     const longlong2 *t2 = reinterpret_cast<const longlong2 *>(target);
     const long long gthreads = (long long)gridDim.x * blockDim.x;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    // 2x unrolled: 4 independent 16-byte loads in flight per lane
-    for (; i + gthreads < nvec; i += 2 * gthreads) {
-        longlong2 pa = __ldg(p2 + i), ta = __ldg(t2 + i);
-        longlong2 pb = __ldg(p2 + i + gthreads), tb = __ldg(t2 + i + gthreads);
-        count_pixel(table, lane, pa.x, ta.x, K, flags);
-        count_pixel(table, lane, pa.y, ta.y, K, flags);
-        count_pixel(table, lane, pb.x, tb.x, K, flags);
-        count_pixel(table, lane, pb.y, tb.y, K, flags);
+    for (; i + (U - 1) * gthreads < nvec; i += U * gthreads) {
+        longlong2 pv[U], tv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            pv[u] = ld_stream(p2 + i + u * gthreads);
+            tv[u] = ld_stream(t2 + i + u * gthreads);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            count_pixel(table, lane, pv[u].x, tv[u].x, K, flags);
+            count_pixel(table, lane, pv[u].y, tv[u].y, K, flags);
+        }
         if (++iters == kMaxIterBeforeFlush) {
             flush_table(table, lane, nwords, nbins, conf);
             iters = 0;
@@ -156,8 +171,9 @@ extern "C" int hn_confusion(const int64_t *pred_labels, const float *scores, int
     if (n == 0) return HN_OK;
     const int nwords = (k * k + 1) / 2;
     // one private table per warp: as many warps (<= 8) as fit in ~200 KB of shared memory
+    const int max_warps = pred_labels ? 16 : 8;
     int warps = (int)((200 * 1024) / ((size_t)nwords * 32 * sizeof(uint32_t)));
-    warps = warps < 1 ? 1 : (warps > 8 ? 8 : warps);
+    warps = warps < 1 ? 1 : (warps > max_warps ? max_warps : warps);
     const int threads = warps * 32;
     const size_t smem = (size_t)warps * nwords * 32 * sizeof(uint32_t);
     cudaStream_t st = (cudaStream_t)stream;
@@ -170,8 +186,8 @@ extern "C" int hn_confusion(const int64_t *pred_labels, const float *scores, int
     if (pred_labels) {
         HN_CHECK_ARG((reinterpret_cast<uintptr_t>(pred_labels) | reinterpret_cast<uintptr_t>(target)) % 16 == 0,
                      "hn_confusion: label pointers must be 16-byte aligned");
-        HN_CUDA(cudaFuncSetAttribute(confusion_labels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        confusion_labels_kernel<<<grid, threads, smem, st>>>((const long long *)pred_labels, (const long long *)target, n, k,
+        HN_CUDA(cudaFuncSetAttribute(confusion_labels_kernel<kLabelUnroll>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        confusion_labels_kernel<kLabelUnroll><<<grid, threads, smem, st>>>((const long long *)pred_labels, (const long long *)target, n, k,
                                                          (unsigned long long *)conf, flags);
     } else {
         HN_CUDA(cudaFuncSetAttribute(confusion_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -18,6 +18,9 @@ _TORCH_DTYPE = {HN_F32: torch.float32, HN_BF16: torch.bfloat16}
 _HN_DTYPE = {torch.float32: HN_F32, torch.bfloat16: HN_BF16}
 
 DEFAULT_PRECISION = os.environ.get("HEATNET_B200_PRECISION", "bf16")
+# Storage type of the pre-normalisation conv output in train-mode BatchNorm2d on the BF16 path.  FP32 (default) keeps
+# (x - mean) * invstd free of the BF16 rounding of x (amplified by |mean|/std); "0" stores BF16 like torch.autocast does
+# (10 bytes/element less HBM traffic over the forward + backward of every BN layer).
 BN_TRAIN_RAW_FP32 = os.environ.get("HEATNET_B200_BN_RAW_FP32", "1") != "0"
 # Fused 2x-upsample + 3x3 conv (hn_upconv3x3_fwd) is used for inputs with at least this many channels.  Measured on B200
 # (batch 16, 650x1920): with the exact-2x bilinear kernel at 3.1 TB/s the separate path wins everywhere -- up_1 (Cin 1024):
@@ -524,29 +527,31 @@ def affine_act(x: Act, scale, shift, residual: Optional[Act], act, slope=0.0, sl
 
 
 def batchnorm_train_affine(x: Act, bn: torch.nn.BatchNorm2d):
-    """Batch statistics of x (FP64 accumulation) -> (scale, shift) for the apply pass; updates the module's
+    """Batch statistics of x (FP64 accumulation) -> (scale, shift, mean, invstd) for the apply pass; updates the module's
     running statistics exactly like nn.BatchNorm2d in train mode (momentum, unbiased variance,
-    num_batches_tracked)."""
+    num_batches_tracked).  One memset + ONE kernel (hn_bn_batch_stats: the last CTA finalizes)."""
     lib = _lib.load()
     dev = x.buf.device
-    sums = torch.empty((2, x.c), dtype=torch.float64, device=dev)
-    _lib.check(lib.hn_channel_stats(C.byref(x.hn()), sums[0].data_ptr(), sums[1].data_ptr(), _stream()))
-    _count(3)
     out = torch.empty((4, x.c), dtype=torch.float32, device=dev)     # scale, shift, save_mean, save_invstd
     track = bn.track_running_stats and bn.running_mean is not None
-    momentum = 0.0
-    if track:
-        bn.num_batches_tracked.add_(1)
-        momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked.item())
     p = lambda t: t.detach().data_ptr() if t is not None else None
-    _lib.check(lib.hn_bn_finalize(sums[0].data_ptr(), sums[1].data_ptr(), x.n * x.h * x.w, p(bn.weight), p(bn.bias),
-                                  float(bn.eps), float(momentum), p(bn.running_mean) if track else None,
-                                  p(bn.running_var) if track else None, out[0].data_ptr(), out[1].data_ptr(),
-                                  out[2].data_ptr(), out[3].data_ptr(), x.c, _stream()))
-    _count()
+    momentum = 0.0
+    nbt = None
+    if track:
+        if bn.momentum is None:      # cumulative moving average: the factor depends on the counter's value
+            bn.num_batches_tracked.add_(1)
+            momentum = 1.0 / float(bn.num_batches_tracked.item())
+        else:
+            momentum = bn.momentum
+            nbt = p(bn.num_batches_tracked)
+    scratch = torch.empty((2 * x.c + 1,), dtype=torch.float64, device=dev)
+    _lib.check(lib.hn_bn_batch_stats(C.byref(x.hn()), scratch.data_ptr(), p(bn.weight), p(bn.bias), float(bn.eps), float(momentum),
+                                     p(bn.running_mean) if track else None, p(bn.running_var) if track else None, nbt,
+                                     out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), _stream()))
+    _count(2)
     if track:   # in-place kernel writes bypass torch's version counter; bump it so folded caches refresh
-        bn.running_mean.add_(0)
-        bn.running_var.add_(0)
+        bn.running_mean._bump_version() if hasattr(bn.running_mean, "_bump_version") else bn.running_mean.add_(0)
+        bn.running_var._bump_version() if hasattr(bn.running_var, "_bump_version") else bn.running_var.add_(0)
     return out[0], out[1], out[2], out[3]
 
 
@@ -593,7 +598,7 @@ def conv_bn_act(x: Act, conv, bn, act=ACT_NONE, slope=0.0, slope_ptr=None, resid
     # The pre-normalisation tensor stays FP32: (x - mean) * invstd amplifies BF16 rounding of x by |mean|/std,
     # which is large for channels with little spatial variation.  Statistics and the normalise pass read the
     # FP32 values; only the normalised activation is rounded to the compute dtype.
-    raw_fp32 = BN_TRAIN_RAW_FP32 or tape is not None
+    raw_fp32 = BN_TRAIN_RAW_FP32
     if stem_ok(x, conv):
         wp, shift = packed_stem_weight(conv, None)
         raw = stem_conv(x, conv, wp, shift, out_dtype=torch.float32 if raw_fp32 else None)
@@ -617,16 +622,16 @@ def conv_bn_act(x: Act, conv, bn, act=ACT_NONE, slope=0.0, slope_ptr=None, resid
                 if tape.needs(residual):
                     dres, dres_acc = grads.target(residual)
                 prelu = _wants(slope_ptr)
-                draw, sums = bn_bwd(dout, y, raw, mean, invstd, bn.weight, act, slope, slope_ptr, dres, dres_acc, prelu)
+                draw, pg = bn_bwd(dout, y, raw, mean, invstd, bn.weight, act, slope, slope_ptr, dres, dres_acc, prelu,
+                                  _wants(bn.bias), _wants(bn.weight))
                 if dres is not None:
                     grads.mark(residual)
-                cch = y.c
-                if _wants(bn.bias):
-                    grads.add_param(bn.bias, vec_to_grad(sums, cch))
-                if _wants(bn.weight):
-                    grads.add_param(bn.weight, vec_to_grad(sums[cch:], cch))
-                if prelu:
-                    grads.add_param(slope_ptr, vec_to_grad(sums[2 * cch:], 1))
+                if pg[0] is not None:
+                    grads.add_param(bn.bias, pg[0])
+                if pg[1] is not None:
+                    grads.add_param(bn.weight, pg[1])
+                if pg[2] is not None:
+                    grads.add_param(slope_ptr, pg[2])
                 _conv_param_backward(grads, tape, x, conv, draw)
 
             tape.record(backward)
@@ -872,18 +877,24 @@ def vec_to_grad(src_f64: torch.Tensor, n: int) -> torch.Tensor:
 
 
 def bn_bwd(dout: Act, out: Act, raw: Act, mean, invstd, gamma, act, slope=0.0, slope_ptr=None, dres: Optional[Act] = None,
-           dres_accumulate=False, want_prelu_grad=False):
-    """-> (draw Act, sums FP64 [2C+1]): sums[:C] = dbeta, sums[C:2C] = dgamma, sums[2C] = dslope."""
+           dres_accumulate=False, want_prelu_grad=False, want_dbeta=True, want_dgamma=True):
+    """-> (draw Act, (dbeta, dgamma, dslope)): FP32 parameter gradients written by the apply kernel itself (None when not
+    asked for)."""
     cch = dout.c
-    sums = torch.empty((2 * cch + 1,), dtype=torch.float64, device=dout.buf.device)
-    draw = new_act(dout.n, dout.h, dout.w, cch, dout.dtype, dout.buf.device)
+    dev = dout.buf.device
+    sums = torch.empty((2 * cch + 1,), dtype=torch.float64, device=dev)
+    draw = new_act(dout.n, dout.h, dout.w, cch, dout.dtype, dev)
+    pg = torch.empty((2 * cch + 1,), dtype=torch.float32, device=dev)
+    dbeta = pg[:cch] if want_dbeta else None
+    dgamma = pg[cch:2 * cch] if want_dgamma else None
+    dslope = pg[2 * cch:] if want_prelu_grad else None
     p = lambda t: t.detach().data_ptr() if t is not None else None
     _lib.check(_lib.load().hn_bn_bwd(C.byref(dout.hn()), C.byref(out.hn()), C.byref(raw.hn()), p(mean), p(invstd), p(gamma), act,
                                     float(slope), p(slope_ptr), sums.data_ptr(), C.byref(draw.hn()),
                                     C.byref(dres.hn()) if dres is not None else None, int(dres_accumulate),
-                                    int(want_prelu_grad), _stream()))
+                                    int(want_prelu_grad), p(dbeta), p(dgamma), p(dslope), 0, _stream()))
     _count(3)
-    return draw, sums
+    return draw, (dbeta, dgamma, dslope)
 
 
 def accumulate(x: Act, y: Act, add: bool):

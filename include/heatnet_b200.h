@@ -142,16 +142,26 @@ int hn_channel_stats(const hn_tensor *x, double *sum, double *sqsum, void *strea
 int hn_bn_finalize(const double *sum, const double *sqsum, int64_t count, const float *gamma, const float *beta,
                    float eps, float momentum, float *running_mean, float *running_var, float *scale, float *shift,
                    float *save_mean, float *save_invstd, int32_t c, void *stream);
+/* train-mode BatchNorm2d statistics in ONE kernel (+ one memset): hn_channel_stats and hn_bn_finalize fused through a
+ * last-CTA ticket, including `num_batches_tracked += 1` (cm/models/extractors.py:85-101: every nn.BatchNorm2d in train mode).
+ * scratch: device memory of hn_bn_batch_stats_scratch_bytes(C) (FP64 sums + ticket), zeroed by the call. */
+int64_t hn_bn_batch_stats_scratch_bytes(int32_t c);
+int hn_bn_batch_stats(const hn_tensor *x, void *scratch, const float *gamma, const float *beta, float eps, float momentum,
+                      float *running_mean, float *running_var, int64_t *num_batches_tracked, float *scale, float *shift,
+                      float *save_mean, float *save_invstd, void *stream);
 
 /* ---- backward (autograd of the ops above; the reference gets these from torch.autograd / cuDNN) ---- */
 /* dz = dout * act'(out), the derivative taken through the saved output (conv + bias + activation layers) */
 int hn_act_bwd(const hn_tensor *dout, const hn_tensor *out, int32_t act, float slope, const hn_tensor *dz, void *stream);
 /* BatchNorm2d (train) backward fused with the activation / residual split:
  *   dz = dout*act'(out);  sums[0..C) = sum dz (= dbeta), sums[C..2C) = sum dz*xhat (= dgamma), sums[2C] = dPReLU slope
- *   draw = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat));  dres (+)= dz.   raw: FP32 pre-normalisation tensor. */
+ *   draw = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat));  dres (+)= dz.   raw: pre-normalisation tensor (FP32, or BF16
+ *   on the BF16 path).  dbeta / dgamma [C] and dslope [1] (each optional) receive the FP32 parameter gradients directly,
+ *   added to their current contents when param_accumulate is set (a second backward pass into an existing .grad). */
 int hn_bn_bwd(const hn_tensor *dout, const hn_tensor *out, const hn_tensor *raw, const float *mean, const float *invstd,
               const float *gamma, int32_t act, float slope, const float *slope_ptr, double *sums, const hn_tensor *draw,
-              const hn_tensor *dres, int32_t dres_accumulate, int32_t want_prelu_grad, void *stream);
+              const hn_tensor *dres, int32_t dres_accumulate, int32_t want_prelu_grad, float *dbeta, float *dgamma, float *dslope,
+              int32_t param_accumulate, void *stream);
 /* y = x (accumulate == 0) or y += x; dtypes may differ */
 int hn_accumulate(const hn_tensor *x, const hn_tensor *y, int32_t accumulate, void *stream);
 /* MaxPool2d(3,2,1) forward that also records the winning tap (uint8 [N][Ho][Wo][C]) and its backward */
