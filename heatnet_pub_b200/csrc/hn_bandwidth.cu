@@ -585,6 +585,60 @@ __global__ void __launch_bounds__(256) bilinear_sum_kernel(const __grid_constant
     }
 }
 
+// Same sum, restructured for the PSP head (tiny sources, 16x..80x magnification): a thread owns one 8-channel vector and walks
+// SEG consecutive output pixels of one row.  The source taps of an output pixel change only every Wo/W_s pixels, so the
+// vertically blended tap pair of every source lives in registers and is reloaded on a change of x0 -- ~1 load per output
+// vector instead of 16; the stores of a warp cover 512 contiguous bytes.  (The blend is re-associated -- vertical first --
+// which differs from bilinear_vec_kernel by FP32 rounding only.)
+template <typename T, int SEG>
+__global__ void __launch_bounds__(128) bilinear_sum_seg_kernel(const __grid_constant__ BilinearSrcs src, T *__restrict__ y, int ldy, int N,
+                                                               int Ho, int Wo, int C)
+{
+    const int cv = blockIdx.z * blockDim.x + threadIdx.x;
+    if (cv >= C / 8) return;
+    const int c = cv * 8;
+    const int row = blockIdx.x;
+    const int n = row / Ho, ho = row - n * Ho;
+    const int w_begin = blockIdx.y * SEG, w_end = w_begin + SEG < Wo ? w_begin + SEG : Wo;
+    T *yrow = y + (int64_t)row * Wo * ldy + c;
+    float a0[4][8], a1[4][8];
+    int cur[4] = {-1, -1, -1, -1};
+    for (int wo = w_begin; wo < w_end; ++wo) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            if (s >= src.n) break;
+            const int H = src.h[s], W = src.w[s], ld = src.ld[s];
+            int x0, x1;
+            float lx;
+            bilinear_src(wo, (float)W / (float)Wo, W, x0, x1, lx);
+            if (x0 != cur[s]) {                                   // warp-uniform
+                int y0, y1;
+                float ly;
+                bilinear_src(ho, (float)H / (float)Ho, H, y0, y1, ly);
+                const float hy = 1.f - ly;
+                const T *b = (const T *)src.ptr[s] + (int64_t)n * H * W * ld + c;
+                float t0[8], t1[8];
+                Vec8<T>::load(b + ((int64_t)y0 * W + x0) * ld, t0);
+                Vec8<T>::load(b + ((int64_t)y1 * W + x0) * ld, t1);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a0[s][j] = hy * t0[j] + ly * t1[j];
+                Vec8<T>::load(b + ((int64_t)y0 * W + x1) * ld, t0);
+                Vec8<T>::load(b + ((int64_t)y1 * W + x1) * ld, t1);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a1[s][j] = hy * t0[j] + ly * t1[j];
+                cur[s] = x0;
+            }
+            const float hx = 1.f - lx;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += hx * a0[s][j] + lx * a1[s][j];
+        }
+        Vec8<T>::store(yrow + (int64_t)wo * ldy, acc);
+    }
+}
+
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) bilinear_scalar_kernel(const TI *__restrict__ x, int ldx, TO *__restrict__ y, int ldy, int N,
                                                               int H, int W, int Ho, int Wo, int C, float sh, float sw)
@@ -952,8 +1006,18 @@ extern "C" int hn_bilinear_sum_fwd(const hn_tensor *xs, int32_t nsrc, const hn_t
         src.ptr[i] = xs[i].ptr; src.h[i] = xs[i].h; src.w[i] = xs[i].w; src.ld[i] = xs[i].ld;
     }
     if ((int64_t)y->n * y->h * y->w == 0) return HN_OK;
-    dim3 grid = row_grid((int64_t)y->n * y->h, (int64_t)y->w * (y->c / 8));
     cudaStream_t st = (cudaStream_t)stream;
+    bool magnify = true;          // every source at least 4x smaller along W: the register-resident tap pairs pay off
+    for (int i = 0; i < nsrc; ++i) magnify = magnify && (4 * xs[i].w <= y->w);
+    if (magnify && (int64_t)y->n * y->h < 65535) {
+        constexpr int SEG = 16;
+        dim3 g((unsigned)(y->n * y->h), (unsigned)cdiv(y->w, SEG), (unsigned)cdiv(y->c / 8, 128));
+        if (y->dtype == HN_BF16) bilinear_sum_seg_kernel<__nv_bfloat16, SEG><<<g, 128, 0, st>>>(src, (__nv_bfloat16 *)y->ptr, y->ld, y->n, y->h, y->w, y->c);
+        else bilinear_sum_seg_kernel<float, SEG><<<g, 128, 0, st>>>(src, (float *)y->ptr, y->ld, y->n, y->h, y->w, y->c);
+        HN_LAUNCH_CHECK();
+        return HN_OK;
+    }
+    dim3 grid = row_grid((int64_t)y->n * y->h, (int64_t)y->w * (y->c / 8));
     if (y->dtype == HN_BF16) bilinear_sum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, (__nv_bfloat16 *)y->ptr, y->ld, y->n, y->h, y->w, y->c);
     else bilinear_sum_kernel<float><<<grid, 256, 0, st>>>(src, (float *)y->ptr, y->ld, y->n, y->h, y->w, y->c);
     HN_LAUNCH_CHECK();

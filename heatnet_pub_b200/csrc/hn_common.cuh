@@ -111,7 +111,12 @@ int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn
                   void *ws, int64_t ws_bytes, cudaStream_t st);
 int64_t conv2d_tc_workspace(const hn_tensor *x, const hn_conv *cv);
 bool conv_halo_ok(const hn_tensor *x, const hn_conv *cv, const hn_tensor *y, bool upsample);
+struct HeadArgs {               // fused 1x1 classifier head of the halo kernel (hn_conv3x3_head_fwd)
+    const float *w, *b;         // HOST pointers: [n][64] FP32, [n] FP32 or NULL (they become kernel parameters)
+    float *out;                 // NCHW FP32 logits
+    int n;
+};
 int conv2d_fwd_halo(const hn_tensor *x, const void *w, const hn_conv *cv, const hn_epilogue *ep, const hn_tensor *y, bool upsample,
-                    cudaStream_t st);
+                    cudaStream_t st, const HeadArgs *head = nullptr);
 
 }  // namespace hn

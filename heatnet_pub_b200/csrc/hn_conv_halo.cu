@@ -57,7 +57,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 {
     constexpr int B_STAGE_BYTES = BLOCK_N * 128;
     constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
-    constexpr int TMEM_COLS = 2 * ACC_COLS;
+    constexpr int TMEM_COLS = BLOCK_N == 64 ? 256 : 2 * ACC_COLS;    // BLOCK_N = 64: + 2 x 16 columns for the fused classifier head
     constexpr uint32_t IDESC = make_idesc_bf16(128, BLOCK_N);
     // A-producer warps of the UPSAMPLE variant: warps 2,3 always; warps 8-11 too when the epilogue only needs 4 warps
     constexpr int NPROD = 6;   // warps 2, 3, 8-11 (the UPSAMPLE variant's epilogue runs on warps 4-7 only)
@@ -68,7 +68,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t *a_ring = smem;
     uint8_t *b_ring = a_ring + HALO_NA * hp.a_slot_bytes;
     uint8_t *epi_stage = b_ring + hp.nb * B_STAGE_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES);
+    // [16][64] BF16 classifier tile (2 KB, 1024-aligned) sits right behind the staging buffers: hn_tc_epilogue.cuh relies on it
+    uint64_t *bars = reinterpret_cast<uint64_t *>(epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES + 2048);
     uint64_t *a_full = bars, *a_empty = bars + HALO_NA, *b_full = bars + 2 * HALO_NA, *b_empty = b_full + HALO_NB_MAX;
     uint64_t *tfull_bar = b_empty + HALO_NB_MAX, *tempty_bar = tfull_bar + 2, *res_bar = tempty_bar + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_bar + NUM_EPI_WARPS);
@@ -314,9 +315,10 @@ bool conv_halo_ok(const hn_tensor *x, const hn_conv *cv, const hn_tensor *y, boo
 }
 
 int conv2d_fwd_halo(const hn_tensor *x, const void *w, const hn_conv *cv, const hn_epilogue *ep, const hn_tensor *y, bool upsample,
-                    cudaStream_t st)
+                    cudaStream_t st, const HeadArgs *head)
 {
-    const int Ho = y->h, Wo = y->w;
+    // with a classifier head the activation is not stored: y may be NULL, the output extent is that of a pad = dil 3x3
+    const int Ho = y ? y->h : (upsample ? 2 * x->h : x->h), Wo = y ? y->w : (upsample ? 2 * x->w : x->w);
     if ((int64_t)x->n * Ho * Wo == 0) return HN_OK;
     const int d = cv->dil;
     const int kpad = hn_conv_kpad(x->c, 3, 3);
@@ -335,16 +337,18 @@ int conv2d_fwd_halo(const hn_tensor *x, const void *w, const hn_conv *cv, const 
     int bn = 64;
     for (int cand : {256, 128})
         if (cout_pad % cand == 0 && (int64_t)num_m_tiles * (cout_pad / cand) >= 2 * (int64_t)num_sms()) { bn = cand; break; }
+    if (head) bn = 64;
     p.n_tiles = cout_pad / bn;
+    const int tail = 2048 /*classifier tile*/ + 2048 /*barriers + shift table*/;
     // shared-memory plan: A slots + B ring + epilogue staging + barriers
-    const int64_t fixed = (int64_t)HALO_NA * hp.a_slot_bytes + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + 2048 /*barriers + shift table*/;
+    const int64_t fixed = (int64_t)HALO_NA * hp.a_slot_bytes + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + tail;
     int nb = (int)((227 * 1024 - fixed) / (bn * 128));
     if (nb > HALO_NB_MAX) nb = HALO_NB_MAX;
     HN_CHECK_ARG(nb >= 2, "conv_halo: shared memory too small for this shape");
     hp.nb = nb;
     hp.b_resident = (p.cblocks * 9 <= nb && p.n_tiles == 1) ? 1 : 0;   // one Cout tile: the same weights for every tile
     if (hp.b_resident) hp.nb = p.cblocks * 9;
-    const size_t smem = (size_t)HALO_NA * hp.a_slot_bytes + (size_t)hp.nb * bn * 128 + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 + 2048;
+    const size_t smem = (size_t)HALO_NA * hp.a_slot_bytes + (size_t)hp.nb * bn * 128 + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 + tail;
 
     CUtensorMap ta, tb, ty, tr;
     memset(&ta, 0, sizeof(ta));
@@ -367,11 +371,17 @@ int conv2d_fwd_halo(const hn_tensor *x, const void *w, const hn_conv *cv, const 
         int rc = make_tmap(&tb, w, 2, dims, strides, box);
         if (rc) return rc;
     }
-    p.y = y->ptr; p.ldy = y->ld; p.y_f32 = (y->dtype == HN_F32);
     p.scale = ep->scale; p.shift = ep->shift; p.res = ep->residual; p.ldr = ep->residual_ld;
     p.act = ep->act; p.slope = ep->slope; p.slope_ptr = ep->slope_ptr;
     p.ebw = HALO_TW;
-    {
+    if (head) {
+        HN_CHECK_ARG(cv->cout == 64 && !ep->scale && !ep->residual, "conv3x3_head: needs Cout == 64, no explicit scale, no residual");
+        HN_CHECK_ARG(head->n >= 1 && head->n <= HEAD_MAX && head->w && head->out, "conv3x3_head: 1..%d classes", HEAD_MAX);
+        p.head_out = head->out; p.head_n = head->n;
+        memcpy(p.head.w, head->w, sizeof(float) * 64 * head->n);          // hp{} zero-initialised the rest
+        if (head->b) memcpy(p.head.b, head->b, sizeof(float) * head->n);
+    } else {
+        p.y = y->ptr; p.ldy = y->ld; p.y_f32 = (y->dtype == HN_F32);
         const uint64_t esz = p.y_f32 ? 4 : 2;
         const bool ok = (reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0 && ((uint64_t)y->ld * esz) % 16 == 0;
         if (ok) {
@@ -418,4 +428,19 @@ extern "C" int hn_upconv3x3_fwd(const hn_tensor *x, const void *w_packed, const 
     HN_CHECK_ARG(conv_halo_ok(x, cv, y, true), "hn_upconv3x3_fwd: needs BF16 NHWC input with Cin %% 64 == 0, a 3x3 stride-1 pad-1 filter and Cout >= 33");
     HN_CHECK_ARG(!ep->out_nchw && !ep->stat_sum && !ep->stat_sqsum, "hn_upconv3x3_fwd: out_nchw / fused statistics are not implemented");
     return conv2d_fwd_halo(x, w_packed, cv, ep, y, true, (cudaStream_t)stream);
+}
+
+// up_3 + final of PSPNet in one kernel (cm/models/pspnet.py:72-75 in eval mode: conv3x3 -> BN -> PReLU -> Dropout2d (identity)
+// -> 1x1 classifier): the 64-channel full-resolution activation never leaves the SM; logits are written NCHW FP32.
+extern "C" int hn_conv3x3_head_fwd(const hn_tensor *x, const void *w_packed, const hn_conv *cv, const hn_epilogue *ep, const float *head_w_host,
+                                   const float *head_b_host, int32_t head_classes, float *logits_nchw, void *stream)
+{
+    HN_CHECK_ARG(x && w_packed && cv && ep && head_w_host && logits_nchw && x->ptr, "hn_conv3x3_head_fwd: null pointer");
+    HN_CHECK_ARG(x->dtype == HN_BF16 && cv->r == 3 && cv->s == 3 && cv->stride == 1 && cv->pad == 1 && cv->dil == 1 && cv->cout == 64 &&
+                     x->c % 64 == 0 && x->ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x->ptr) & 15) == 0,
+                 "hn_conv3x3_head_fwd: needs BF16 NHWC input with Cin %% 64 == 0 and a 3x3 stride-1 pad-1 filter with 64 outputs");
+    HN_CHECK_ARG(!ep->out_nchw && !ep->stat_sum && !ep->stat_sqsum && !ep->scale && !ep->residual,
+                 "hn_conv3x3_head_fwd: epilogue = shift + activation only (fold the BN scale into the filter)");
+    HeadArgs h{head_w_host, head_b_host, logits_nchw, head_classes};
+    return conv2d_fwd_halo(x, w_packed, cv, ep, nullptr, false, (cudaStream_t)stream, &h);
 }

@@ -6,7 +6,10 @@
 // shared memory; lane L only ever touches column L (bank L), so the read-modify-write is conflict-free and
 // race-free.  One 32-bit word packs the 16-bit counters of bins 2j and 2j+1; a warp flushes its table to the
 // global int64 matrix (warp-shuffle reduction + one atomicAdd per bin) before any counter can overflow.
+#include <stdlib.h>
+
 #include "hn_common.cuh"
+#include "hn_tc_ptx.cuh"
 
 namespace hn {
 
@@ -103,6 +106,94 @@ __global__ void __launch_bounds__(512) confusion_labels_kernel(const long long *
     if (lane == 0 && flags) atomicOr(flags_out, flags);
 }
 
+// label path, TMA-staged (K <= 15): a producer warp streams 1024-pixel chunks of pred and target into a 6-stage shared-memory
+// ring with cp.async.bulk (96 KB in flight per SM, independent of the consumers' register budget); 8 consumer warps count
+// from shared memory with 16-byte loads.  Same per-lane private counters and flush rule as above.
+constexpr int CL_WARPS = 8;
+constexpr int CL_CHUNK = 1024;                 // pixels per stage: 8 KB of pred + 8 KB of target
+constexpr int CL_STAGES = 6;
+constexpr int CL_STAGE_BYTES = 2 * CL_CHUNK * 8;
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__((CL_WARPS + 1) * 32, 1) confusion_labels_tma_kernel(const long long *__restrict__ pred,
+                                                                                      const long long *__restrict__ target, long long n, int K,
+                                                                                      unsigned long long *conf, int *flags_out)
+{
+    extern __shared__ __align__(128) uint8_t cl_smem[];
+    const int nbins = K * K, nwords = (nbins + 1) / 2;
+    uint8_t *ring = cl_smem;
+    uint32_t *tables = reinterpret_cast<uint32_t *>(ring + CL_STAGES * CL_STAGE_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(tables + CL_WARPS * nwords * 32), *empty = full + CL_STAGES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long n_even = n & ~1LL;
+    const long long nchunks = (n_even + CL_CHUNK - 1) / CL_CHUNK;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < CL_STAGES; ++i) {
+            mbar_init(smem_u32(full + i), 1);
+            mbar_init(smem_u32(empty + i), CL_WARPS);
+        }
+        fence_barrier_init();
+    }
+    uint32_t *table = tables + (warp < CL_WARPS ? warp : 0) * nwords * 32;
+    if (warp < CL_WARPS)
+        for (int j = 0; j < nwords; ++j) table[j * 32 + lane] = 0;
+    __syncthreads();
+
+    if (warp == CL_WARPS) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+                mbar_wait(smem_u32(empty + stage), phase ^ 1);
+                const long long left = n_even - c * CL_CHUNK;
+                const uint32_t bytes = (uint32_t)(left < CL_CHUNK ? left : CL_CHUNK) * 8u;
+                const uint32_t fb = smem_u32(full + stage);
+                mbar_expect_tx(fb, 2 * bytes);
+                const uint32_t dst = smem_u32(ring + stage * CL_STAGE_BYTES);
+                bulk_load_1d(dst, pred + c * CL_CHUNK, bytes, fb);
+                bulk_load_1d(dst + CL_CHUNK * 8, target + c * CL_CHUNK, bytes, fb);
+                if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+    int flags = 0, iters = 0, stage = 0;
+    uint32_t phase = 0;
+    for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        mbar_wait(smem_u32(full + stage), phase);
+        const long long left = n_even - c * CL_CHUNK;
+        const int pairs = (int)(left < CL_CHUNK ? left : CL_CHUNK) >> 1;
+        const longlong2 *ps = reinterpret_cast<const longlong2 *>(ring + stage * CL_STAGE_BYTES);
+        const longlong2 *ts = ps + CL_CHUNK / 2;
+#pragma unroll
+        for (int u = 0; u < CL_CHUNK / 2 / (CL_WARPS * 32); ++u) {
+            const int i = u * CL_WARPS * 32 + threadIdx.x;
+            if (i < pairs) {
+                const longlong2 pv = ps[i], tv = ts[i];
+                count_pixel(table, lane, pv.x, tv.x, K, flags);
+                count_pixel(table, lane, pv.y, tv.y, K, flags);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(empty + stage));
+        if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+        if (++iters == 2 * kMaxIterBeforeFlush) {        // <= 4 pixels per lane per chunk
+            flush_table(table, lane, nwords, nbins, conf);
+            iters = 0;
+        }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) count_pixel(table, lane, pred[n - 1], target[n - 1], K, flags);
+    flush_table(table, lane, nwords, nbins, conf);
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if (lane == 0 && flags) atomicOr(flags_out, flags);
+}
+
 // scores path: NCHW FP32 [N][K][hw]; first-max argmax over K fused (torch max(1) tie rule)
 __global__ void __launch_bounds__(256) confusion_scores_kernel(const float *__restrict__ scores,
                                                                const long long *__restrict__ target, long long n_images,
@@ -186,6 +277,17 @@ extern "C" int hn_confusion(const int64_t *pred_labels, const float *scores, int
     if (pred_labels) {
         HN_CHECK_ARG((reinterpret_cast<uintptr_t>(pred_labels) | reinterpret_cast<uintptr_t>(target)) % 16 == 0,
                      "hn_confusion: label pointers must be 16-byte aligned");
+        static const bool no_tma = getenv("HN_CONFUSION_NO_TMA") != nullptr;
+        const size_t tsmem = (size_t)CL_STAGES * CL_STAGE_BYTES + (size_t)CL_WARPS * nwords * 32 * sizeof(uint32_t) + 2 * CL_STAGES * 8;
+        if (!no_tma && tsmem <= 226 * 1024 && n >= 4 * CL_CHUNK) {
+            HN_CUDA(cudaFuncSetAttribute(confusion_labels_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+            const int64_t nch = cdiv(n & ~(int64_t)1, CL_CHUNK);
+            const int g = (int)(nch < num_sms() ? nch : num_sms());
+            confusion_labels_tma_kernel<<<g, (CL_WARPS + 1) * 32, tsmem, st>>>((const long long *)pred_labels, (const long long *)target, n, k,
+                                                                               (unsigned long long *)conf, flags);
+            HN_LAUNCH_CHECK();
+            return HN_OK;
+        }
         HN_CUDA(cudaFuncSetAttribute(confusion_labels_kernel<kLabelUnroll>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         confusion_labels_kernel<kLabelUnroll><<<grid, threads, smem, st>>>((const long long *)pred_labels, (const long long *)target, n, k,
                                                          (unsigned long long *)conf, flags);

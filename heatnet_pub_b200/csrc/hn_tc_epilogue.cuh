@@ -7,6 +7,14 @@ namespace hn {
 
 constexpr int EPI_WARP0 = 4;
 
+// Classifier weights travel as KERNEL PARAMETERS (constant bank): every FMA of the head takes its weight as a constant-bank
+// operand (LDC / uniform registers) -- no shared-memory or global loads in the 13 x 64 FMA loop of each pixel.
+constexpr int HEAD_MAX = 16;
+struct HeadConst {
+    float w[HEAD_MAX][64];
+    float b[HEAD_MAX];
+};
+
 struct TcParams {
     // tiling of the output pixel space
     int tiles_w, tiles_h, n_img;   // M tiles = n_img * tiles_h * tiles_w
@@ -29,6 +37,10 @@ struct TcParams {
     // TMA epilogue: output (and residual) go through a swizzled shared-memory staging tile per epilogue warp
     int tma_out, tma_res;
     int ebw;                       // staging box = {128 B of channels, ebw pixels, 32/ebw rows, 1}: ebw = min(TW, 32)
+    // fused 1x1 classifier head (halo kernel, BLOCK_N = 64 = Cout): logits written as NCHW FP32, the activation is not stored
+    float *head_out;               // [n_img][head_n][Ho][Wo]
+    int head_n;                    // <= HEAD_MAX; 0 = no head
+    HeadConst head;                // classifier weights (rows >= head_n are zero)
 };
 
 constexpr int EPI_STAGE_BYTES = 32 * 128;   // 32 pixels x 128 B per epilogue warp
@@ -36,6 +48,25 @@ constexpr int NUM_EPI_WARPS = 8;
 
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// phase B of the fused classifier: wait for the head MMA of a tile, read this thread's pixel (TMEM lane) back and write its
+// logits as NCHW FP32 (streaming stores: the logits are not re-read by this kernel)
+__device__ __forceinline__ void head_emit(const TcParams &p, uint32_t taddr, uint32_t bar, uint32_t phase, int img, int ho, int wo, bool valid)
+{
+    mbar_wait(bar, phase);
+    tcgen05_fence_after();
+    uint32_t raw[16];
+    tmem_ld_32x16(taddr, raw);
+    tmem_ld_wait();
+    tcgen05_fence_before();
+    if (valid) {
+        const int64_t plane = (int64_t)p.Ho * p.Wo;
+        float *o = p.head_out + (int64_t)img * p.head_n * plane + (int64_t)ho * p.Wo + wo;
+#pragma unroll
+        for (int k = 0; k < HEAD_MAX; ++k)
+            if (k < p.head_n) __stcs(o + k * plane, __uint_as_float(raw[k]) + p.head.b[k]);
+    }
+}
 
 // Runs on warps EPI_WARP0 .. EPI_WARP0+7 of a CTA.  This CTA walks tile = blockIdx.x, += gridDim.x, ... < num_tiles.
 //
@@ -84,7 +115,9 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
     const int act = p.act;
     const bool res_vec = p.res != nullptr && (p.ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0;
     // packed-BF16 fast path: TMA staging, BF16 output, no explicit scale, residual (if any) staged by TMA
-    const bool fast = SUB == 32 && p.tma_out && !p.y_f32 && p.scale == nullptr && (p.res == nullptr || p.tma_res) &&
+    const bool head = BLOCK_N == 64 && p.head_n > 0;   // host guarantees the fast-path preconditions when a head is given
+    const bool tma_out = p.tma_out && !head;
+    const bool fast = SUB == 32 && (tma_out || head) && !p.y_f32 && p.scale == nullptr && (p.res == nullptr || p.tma_res) &&
                       !(act == HN_ACT_LEAKY && p.res != nullptr);
     float *tab = s_shift + col0;                       // this group's per-channel shift table
     const uint32_t tab_addr = smem_u32(tab);
@@ -94,6 +127,21 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
 #ifdef HN_PROFILE_ROLES
     const long long epi_t0 = clock64();
 #endif
+    int hpar = 0, prev_img = 0, prev_ho = 0, prev_wo = 0;
+    bool have_prev = false, prev_valid = false;
+    uint32_t hph = 0;                                   // phase bits of the two head barriers
+    if constexpr (BLOCK_N == 64) {
+        if (head) {
+            // classifier weights -> BF16 [16 classes][64 ch] K-major SWIZZLE_128B tile behind the staging buffers (rows >= head_n: 0)
+            const int t = q * 32 + lane, k = t >> 3, cidx = t & 7;
+            __nv_bfloat162 h4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h4[e] = __floats2bfloat162_rn(p.head.w[k][cidx * 8 + 2 * e], p.head.w[k][cidx * 8 + 2 * e + 1]);
+            sts128(smem_u32(epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES) + k * 128 + ((cidx ^ (k & 7)) << 4), *reinterpret_cast<const uint4 *>(h4));
+            fence_proxy_async();
+            named_bar_sync(1 + grp, 128);
+        }
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
         const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
@@ -112,16 +160,85 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
             loaded_ctile = ctile;
         }
         bool waited = false;
+        if constexpr (BLOCK_N == 64) {
+            if (head) {
+                // ---------------- conv + activation + 1x1 classifier on the tensor core ----------------
+                // phase A(i): activation tile -> BF16 -> swizzled staging buffer (i & 1), which IS a K-major SWIZZLE_128B
+                // [128 pixels][64 ch] UMMA operand; one elected thread issues logits[128][16] = tile x head^T into spare TMEM
+                // columns.  phase B(i-1): the logits of the previous tile (its MMA had a whole tile period to retire) are read
+                // back and written NCHW FP32.  The 64-channel activation never leaves the SM.
+                { HN_PROF_T0(); mbar_wait(smem_u32(tfull_bar + acc), acc_phase); HN_PROF_ADD(ew_tfull); }
+                tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
+                const uint32_t poff = hpar * (4 * EPI_STAGE_BYTES);
+#pragma unroll
+                for (int si = 0; si < 2; ++si) {
+                    uint32_t raw[32];
+                    tmem_ld_32x32(taddr + si * 32, raw);
+                    tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+                    if (p.shift) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint4 t4 = lds128(tab_addr + (si * 32 + 4 * j) * 4);
+                            v[4 * j] += __uint_as_float(t4.x);
+                            v[4 * j + 1] += __uint_as_float(t4.y);
+                            v[4 * j + 2] += __uint_as_float(t4.z);
+                            v[4 * j + 3] += __uint_as_float(t4.w);
+                        }
+                    }
+                    if (act == HN_ACT_LEAKY) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f) + slope * fminf(v[j], 0.f);
+                    } else if (act == HN_ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
+                    __nv_bfloat162 h[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) sts128(off[si * 4 + j] + poff, *reinterpret_cast<const uint4 *>(&h[4 * j]));
+                }
+                tcgen05_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+                named_bar_sync(1 + grp, 128);           // all four staging quarters written; phase B(i-2) reads of D2[hpar] done
+                if (ew == 0 && lane == 0) {
+                    tcgen05_fence_after();
+                    const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(epi_stage) + poff);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES));
+                    const uint32_t d2 = tmem_base + 2 * ACC_COLS + hpar * HEAD_MAX;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(d2, adesc + 2 * k, bdesc + 2 * k, make_idesc_bf16(128, HEAD_MAX), k != 0);
+                    umma_commit(smem_u32(res_bar + 4 + hpar));
+                }
+                if (have_prev) {
+                    head_emit(p, tmem_base + ((uint32_t)(q * 32) << 16) + 2 * ACC_COLS + (hpar ^ 1) * HEAD_MAX,
+                              smem_u32(res_bar + 4 + (hpar ^ 1)), (hph >> (hpar ^ 1)) & 1u, prev_img, prev_ho, prev_wo, prev_valid);
+                    hph ^= 1u << (hpar ^ 1);
+                }
+                have_prev = true;
+                prev_img = img; prev_ho = ho; prev_wo = wo; prev_valid = valid;
+                hpar ^= 1;
+                continue;
+            }
+        }
         for (int ck = 0; ck < COLS; ck += tch) {
             const bool chunk_on = ctile + ck < p.Cout;          // warp-uniform
-            if (p.tma_out && lane == 0) {
+            if (tma_out && lane == 0) {
                 { HN_PROF_T0(); bulk_wait_read0(); HN_PROF_ADD(ew_bulk); }   // previous store has drained the staging tile
                 if (p.tma_res && chunk_on) {
                     mbar_expect_tx(rbar, EPI_STAGE_BYTES);
                     tma_load_4d(stage, &tmap_r, rbar, ctile + ck, bx, by, img);
                 }
             }
-            if (p.tma_out) __syncwarp();
+            if (tma_out) __syncwarp();
             if (!waited) {
                 { HN_PROF_T0(); mbar_wait(smem_u32(tfull_bar + acc), acc_phase); HN_PROF_ADD(ew_tfull); }
                 tcgen05_fence_after();
@@ -222,7 +339,7 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
                         }
 #pragma unroll
                         for (int j = 0; j < SUB; ++j) v[j] = apply_act(v[j], act, slope);
-                        if (p.tma_out) {
+                        if (tma_out) {
                             if (p.y_f32) {
 #pragma unroll
                                 for (int j = 0; j < SUB / 4; ++j) {
@@ -271,7 +388,7 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
                     }
                 }
             }
-            if (p.tma_out) {
+            if (tma_out) {
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0 && chunk_on) {
@@ -286,7 +403,12 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
     }
-    if (p.tma_out && lane == 0) bulk_wait_read0();    // staging tile must outlive the last bulk store
+    if constexpr (BLOCK_N == 64) {
+        if (head && have_prev)
+            head_emit(p, tmem_base + ((uint32_t)(q * 32) << 16) + 2 * ACC_COLS + (hpar ^ 1) * HEAD_MAX, smem_u32(res_bar + 4 + (hpar ^ 1)),
+                      (hph >> (hpar ^ 1)) & 1u, prev_img, prev_ho, prev_wo, prev_valid);
+    }
+    if (tma_out && lane == 0) bulk_wait_read0();    // staging tile must outlive the last bulk store
 #ifdef HN_PROFILE_ROLES
     if (ew == 0 && lane == 0) {
         HN_PROF_FLUSH(5, ew_tfull); HN_PROF_FLUSH(6, ew_bulk); HN_PROF_FLUSH(7, ew_res); HN_PROF_FLUSH(8, clock64() - epi_t0);

@@ -963,6 +963,51 @@ def upconv3x3(x: Act, conv: torch.nn.Conv2d, scale=None, shift=None, act=ACT_NON
     return out
 
 
+HEAD_FUSION = os.environ.get("HN_NO_HEAD_FUSION") is None
+
+
+def conv3x3_head_ok(x: Act, conv: torch.nn.Conv2d, bn, head: torch.nn.Conv2d) -> bool:
+    """conv3x3 (+ eval-mode BN) + activation + 1x1 classifier in one launch (hn_conv3x3_head_fwd)?"""
+    return (HEAD_FUSION and current_tape is None and x.dtype == torch.bfloat16 and x.c % 64 == 0 and x.ld % 8 == 0
+            and conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1) and conv.dilation == (1, 1)
+            and conv.out_channels == 64 and (bn is None or not (bn.training or bn.running_mean is None))
+            and head.kernel_size == (1, 1) and head.stride == (1, 1) and head.padding == (0, 0) and head.in_channels == 64
+            and head.out_channels <= 16)
+
+
+def conv3x3_head(x: Act, conv: torch.nn.Conv2d, bn, head: torch.nn.Conv2d, act=ACT_NONE, slope=0.0, slope_ptr=None) -> torch.Tensor:
+    """-> NCHW FP32 logits = head(act(bn(conv(x)))) without the intermediate activation in HBM (cm/models/pspnet.py:72-75, eval)."""
+    lib = _lib.load()
+    if bn is not None:
+        wp, shift = packed_weight_folded(conv, bn, x.dtype)
+    else:
+        wp, (_, shift) = packed_weight(conv, x.dtype), folded_affine(conv, None)
+    # the classifier travels as kernel parameters: host copies, refreshed when the parameters change (one D2H sync then)
+    cache = head.__dict__.setdefault("_hn_wcache", {})
+    ver = _versions(head.weight, head.bias)
+    hit = cache.get("host")
+    if hit is None or hit[0] != ver:
+        hw = head.weight.detach().float().reshape(head.out_channels, 64).cpu().contiguous()
+        hb = head.bias.detach().float().cpu().contiguous() if head.bias is not None else None
+        hit = (ver, hw, hb)
+        cache["host"] = hit
+    hw, hb = hit[1], hit[2]
+    out = torch.empty((x.n, head.out_channels, x.h, x.w), dtype=torch.float32, device=x.buf.device)
+    cv = HnConv(64, 3, 3, 1, 1, 1)
+    ep = _epilogue(None, shift, None, act, slope, slope_ptr)
+    timing = conv_timer is not None
+    if timing:
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev_a.record()
+    _lib.check(lib.hn_conv3x3_head_fwd(C.byref(x.hn()), wp.data_ptr(), C.byref(cv), C.byref(ep), hw.data_ptr(),
+                                       hb.data_ptr() if hb is not None else None, head.out_channels, out.data_ptr(), _stream()))
+    if timing:
+        ev_b.record()
+        conv_timer.append((f"{x.c}->64 k3 s1 d1 @{x.h}x{x.w} + head 64->{head.out_channels}", ev_a, ev_b))
+    _count()
+    return out
+
+
 def upconv3x3_ok(x: Act, conv: torch.nn.Conv2d) -> bool:
     # the halo-patch producers are CUDA-core work: hidden behind the tensor pipe only when a tile has many k-blocks
     return (x.dtype == torch.bfloat16 and x.c % 64 == 0 and x.ld % 8 == 0 and conv.out_channels >= 33

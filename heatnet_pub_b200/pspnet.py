@@ -163,9 +163,18 @@ class PSPNet(_KernelModule):
         p = self._dropout(p, self.drop_2)
         p = self.up_2._run(p)
         p = self._dropout(p, self.drop_2)
-        p = self.up_3._run(p)
-        p = self._dropout(p, self.drop_2)
         fin = self.final[0]
+        up3 = self.up_3.conv
+        drop_off = not (self.drop_2.training and self.drop_2.p > 0.0)
+        if drop_off and not E.upconv3x3_ok(p, up3[0]):
+            p = E.bilinear(p, 2 * p.h, 2 * p.w)
+            if E.conv3x3_head_ok(p, up3[0], up3[1], fin):
+                # inference: up_3's conv + BN + PReLU and the classifier in one kernel, logits written NCHW FP32 directly
+                return E.conv3x3_head(p, up3[0], up3[1], fin, ACT_LEAKY, slope_ptr=up3[2].weight), f
+            p = E.conv_bn_act(p, up3[0], up3[1], ACT_LEAKY, slope_ptr=up3[2].weight)
+        else:
+            p = self.up_3._run(p)
+        p = self._dropout(p, self.drop_2)
         # logits are produced in FP32 on both paths (NHWC, channel stride padded to a multiple of 8)
         logits = E.new_act(p.n, p.h, p.w, fin.out_channels, torch.float32, p.buf.device, ld=(fin.out_channels + 7) // 8 * 8)
         E.conv_bn_act(p, fin, None, out=logits)
@@ -183,7 +192,7 @@ class PSPNet(_KernelModule):
             return outs[0], list(outs), None
         m1, m2 = self.feats._inputs(modal_1, modal_2)
         logits, f = self._run_full(m1, m2)
-        out = E.to_nchw_f32(logits)                       # the reference's NCHW FP32 logits
+        out = logits if torch.is_tensor(logits) else E.to_nchw_f32(logits)      # the reference's NCHW FP32 logits
         return out, [out, f[0].nchw(), f[1].nchw(), f[2].nchw(), f[3].nchw(), f[4].nchw()], None
 
     def _autograd_runner(self, tape, inputs):

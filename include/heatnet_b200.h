@@ -108,6 +108,15 @@ int hn_conv2d_fwd(const hn_tensor *x, const void *w_packed, const hn_conv *cv, c
 int hn_upconv3x3_fwd(const hn_tensor *x, const void *w_packed, const hn_conv *cv, const hn_epilogue *ep, const hn_tensor *y,
                      void *stream);
 
+/* PSPUpsample's 3x3 conv and the PSPNet classifier in ONE kernel (cm/models/pspnet.py:72-75 in eval mode: up_3.conv ->
+ * drop_2 (identity) -> final 1x1): logits[n][k][h][w] (NCHW FP32, the reference's layout) = head_b[k] + sum_c head_w[k][c] *
+ * act(conv3x3(x)[c] + shift[c]).  The classifier runs in the epilogue on the FP32 activations; the 64-channel
+ * full-resolution tensor is never written.  BF16 x, Cin % 64 == 0, Cout == 64, head_classes <= 16.
+ * head_w_host [classes][64] / head_b_host [classes] (or NULL) are HOST pointers: the classifier travels as kernel parameters
+ * (constant bank), so its FMAs need no loads; they are read during the call and need not outlive it. */
+int hn_conv3x3_head_fwd(const hn_tensor *x, const void *w_packed, const hn_conv *cv, const hn_epilogue *ep, const float *head_w_host,
+                        const float *head_b_host, int32_t head_classes, float *logits_nchw, void *stream);
+
 /* The 7x7 stride-2 pad-3 stems (Cin <= 4; cm/models/extractors.py:111-123) without an im2col pass: hn_stem_pad writes the
  * input as a zero-bordered 4-channel BF16 image [N][>=2*Ho+6][>=2*Wo+6][4]; in it the 8x4 values a filter row needs for one
  * output pixel are contiguous and consecutive windows overlap, which a strided tensor map hands to TMA directly.

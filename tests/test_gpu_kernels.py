@@ -164,6 +164,50 @@ def test_upsample2x_conv3x3_fused(E, case):
     assert rel(back(y), back(y2)) < 1e-5
 
 
+@pytest.mark.parametrize("case", [(64, 13, 16, 8), (64, 13, 21, 30), (128, 16, 9, 11), (64, 1, 5, 3)])
+def test_conv3x3_bn_prelu_classifier_fused(E, case):
+    """up_3.conv -> BN(eval) -> PReLU -> final 1x1 (cm/models/pspnet.py:72-75) in one kernel: NCHW FP32 logits equal
+    conv -> BN -> PReLU -> 1x1 conv of the oracle on the BF16-rounded operands (the classifier is a second tcgen05 MMA on
+    the BF16 activation tile with BF16 weights, FP32 accumulation -- the numerics of the two-launch path)."""
+    cin, ncls, h, w = case
+    g = torch.Generator().manual_seed(13)
+    conv = nn.Conv2d(cin, 64, 3, 1, 1, bias=True)
+    bn = nn.BatchNorm2d(64)
+    prelu = nn.PReLU()
+    head = nn.Conv2d(64, ncls, 1)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * (2.0 / (9 * cin)) ** 0.5)
+        bn.weight.copy_(torch.rand(64, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(64, generator=g) * 0.1)
+        bn.running_mean.copy_(torch.randn(64, generator=g) * 0.1)
+        bn.running_var.copy_(torch.rand(64, generator=g) + 0.5)
+        prelu.weight.fill_(0.3)
+        head.weight.copy_(torch.randn(head.weight.shape, generator=g) * 0.125)
+        head.bias.copy_(torch.randn(ncls, generator=g) * 0.1)
+    bn.eval()
+    x = torch.randn(3, cin, h, w, generator=g)
+    with torch.no_grad():
+        scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+        wfold = (conv.weight * scale[:, None, None, None]).bfloat16().float()
+        z = F.conv2d(x.bfloat16().float(), wfold, None, 1, 1) + (bn.bias + (conv.bias - bn.running_mean) * scale)[None, :, None, None]
+        ref = F.conv2d(F.prelu(z, prelu.weight).bfloat16().float(), head.weight.bfloat16().float(), head.bias)
+        ref_exact = head(F.prelu(z, prelu.weight))
+    import copy
+    convg, bng, prelug, headg = (copy.deepcopy(m).cuda() for m in (conv, bn, prelu, head))
+    xa = to_act(E, x, torch.bfloat16)
+    assert E.conv3x3_head_ok(xa, convg, bng, headg)
+    out = E.conv3x3_head(xa, convg, bng, headg, E.ACT_LEAKY, slope_ptr=prelug.weight)
+    assert out.shape == (3, ncls, h, w) and out.dtype == torch.float32 and out.is_contiguous()
+    # 3e-3: an activation that sits on a BF16 rounding boundary may round the other way than in the CPU evaluation
+    assert rel(out.cpu(), ref) < 3e-3
+    assert rel(out.cpu(), ref_exact) < BF16_TOL
+    # and the unfused pair of launches agrees (same roundings, different summation order)
+    y = E.conv_bn_act(xa, convg, bng, E.ACT_LEAKY, slope_ptr=prelug.weight)
+    lo = E.new_act(3, h, w, ncls, torch.float32, "cuda", ld=(ncls + 7) // 8 * 8)
+    E.conv_bn_act(y, headg, None, out=lo)
+    assert rel(out.cpu(), back(lo)) < 3e-3
+
+
 @pytest.mark.parametrize("cin,h,w", [(3, 33, 40), (1, 33, 40), (4, 32, 40), (3, 65, 257), (1, 7, 9)])
 def test_stem7x7_overlapping_window_path(E, cin, h, w):
     """7x7 s2 p3 stem -> BN(eval) -> ReLU without im2col (padded 4-channel image + strided tensor map) vs the oracle
@@ -287,6 +331,18 @@ def test_bilinear(E, dtype, tol, sizes):
     assert rel(back(E.bilinear(to_act(E, x, dtype), ho, wo)), ref) < tol
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("out_hw", [(40, 80), (41, 83), (7, 9)])      # segmented (>= 4x magnification) and generic kernels
+def test_bilinear_sum_of_pyramid_priors(E, dtype, tol, out_hw):
+    """sum_s upsample(prior_s) of the PSP head (cm/models/pspnet.py:23-24 after the 1x1 projection) in one pass."""
+    g = torch.Generator().manual_seed(11)
+    ho, wo = out_hw
+    xs = [torch.randn(2, 136, s, s, generator=g) for s in (1, 2, 3, 6)]
+    ref = sum(F.interpolate(x.to(dtype).float(), size=(ho, wo), mode="bilinear", align_corners=False) for x in xs)
+    y = E.bilinear_sum([to_act(E, x, dtype) for x in xs], ho, wo)
+    assert rel(back(y), ref) < tol
+
+
 def test_bilinear_x32_single_channel_fp32(E):
     """nn.Upsample(scale_factor=32, mode='bilinear') on the critics' 1-channel map (cm/discriminator_model.py:47)."""
     x = torch.randn(2, 1, 2, 3, generator=torch.Generator().manual_seed(6))
@@ -396,6 +452,13 @@ def test_confusion_range_asserts_like_reference():
         cm.add(ok, neg)
     with pytest.raises(AssertionError, match="number of targets and predicted outputs do not match"):
         cm.add(ok, ok[:5])
+    big = torch.zeros(50001, dtype=torch.int64).cuda()          # the TMA-staged kernel (n >= 4096), odd length
+    bad = big.clone(); bad[40000] = 14
+    with pytest.raises(AssertionError, match="predicted values are not between 0 and k-1"):
+        cm.add(bad, big)
+    neg = big.clone(); neg[50000] = -(1 << 40)
+    with pytest.raises(AssertionError, match="target values are not between 0 and k-1"):
+        cm.add(big, neg)
     m = iou_eval.IoU(14)
     with pytest.raises(AssertionError, match="predictions must be of dimension"):
         m.add(torch.zeros(2, 3).cuda(), torch.zeros(2, 3).cuda())
