@@ -4,6 +4,8 @@
 // segments; grids are sized in whole waves of the SM count with grid-stride loops.
 #include <type_traits>
 
+#include <stdlib.h>
+
 #include "hn_common.cuh"
 
 namespace hn {
@@ -542,6 +544,61 @@ __global__ void __launch_bounds__(256) bilinear_up2_kernel(const T *__restrict__
     }
 }
 
+// Column-walking variant of the exact 2x upsample: a thread owns one 8-channel vector of one input COLUMN position and walks
+// RY consecutive input rows, keeping the 3x3 neighbourhood in registers as a sliding window -- 3 new loads per 4 stores instead
+// of 9 (the L1/L2 load traffic, not HBM, was the bound of the 9-load version).  Same FP32 expression per output as
+// bilinear_up2_kernel, so the results are bit-identical to it.  grid = (W*C/8 item chunks, row chunks, N).
+template <typename T, int RY>
+__global__ void __launch_bounds__(128) bilinear_up2_walk_kernel(const T *__restrict__ x, int ldx, T *__restrict__ y, int ldy, int N, int H,
+                                                                int W, int C)
+{
+    const int ncv = C / 8;
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= W * ncv) return;
+    const int xi = item / ncv, c = (item - xi * ncv) * 8;
+    const int n = blockIdx.z;
+    const int y_begin = blockIdx.y * RY, y_end = y_begin + RY < H ? y_begin + RY : H;
+    const int xm = xi > 0 ? xi - 1 : 0, xp = xi < W - 1 ? xi + 1 : W - 1;
+    const float lx0 = xi > 0 ? 0.75f : 1.f, lx1 = 0.25f;
+    const T *img = x + (int64_t)n * H * W * ldx + c;
+    const int Wo = 2 * W;
+    float a[3][3][8];
+    auto load_row = [&](int row, float (&dst)[3][8]) {
+        const T *r = img + (int64_t)row * W * ldx;
+        Vec8<T>::load(r + (int64_t)xm * ldx, dst[0]);
+        Vec8<T>::load(r + (int64_t)xi * ldx, dst[1]);
+        Vec8<T>::load(r + (int64_t)xp * ldx, dst[2]);
+    };
+    load_row(y_begin > 0 ? y_begin - 1 : 0, a[0]);
+    load_row(y_begin, a[1]);
+    for (int yi = y_begin; yi < y_end; ++yi) {
+        load_row(yi < H - 1 ? yi + 1 : H - 1, a[2]);
+        const float ly0 = yi > 0 ? 0.75f : 1.f, ly1 = 0.25f;
+        T *o0 = y + ((int64_t)n * 2 * H + 2 * yi) * Wo * ldy + c;
+        T *o1 = o0 + (int64_t)Wo * ldy;
+        float o[8];
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            const float ly = dy == 0 ? ly0 : ly1, hy = 1.f - ly;
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const float lx = dx == 0 ? lx0 : lx1, hx = 1.f - lx;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    o[j] = hy * (hx * a[dy][dx][j] + lx * a[dy][dx + 1][j]) + ly * (hx * a[dy + 1][dx][j] + lx * a[dy + 1][dx + 1][j]);
+                Vec8<T>::store((dy == 0 ? o0 : o1) + (int64_t)(2 * xi + dx) * ldy, o);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a[0][k][j] = a[1][k][j];
+                a[1][k][j] = a[2][k][j];
+            }
+    }
+}
+
 // y = sum_i upsample(x_i): up to 4 low-resolution sources accumulated in FP32 and written once (the PSP priors after
 // the bottleneck projection).  Same index rule as bilinear_vec_kernel.
 struct BilinearSrcs {
@@ -668,8 +725,15 @@ static int launch_bilinear(const hn_tensor *x, const hn_tensor *y, cudaStream_t 
     const float sh = (float)x->h / (float)y->h, sw = (float)x->w / (float)y->w;
     if constexpr (std::is_same<TI, TO>::value) {
         if (vec8_ok(x) && vec8_ok(y) && y->h == 2 * x->h && y->w == 2 * x->w) {
-            bilinear_up2_kernel<TI><<<row_grid((int64_t)x->n * x->h, (int64_t)x->w * (x->c / 8)), 256, 0, st>>>(
-                (const TI *)x->ptr, x->ld, (TO *)y->ptr, y->ld, x->n, x->h, x->w, x->c);
+            static const bool no_walk = getenv("HN_UP2_NO_WALK") != nullptr;
+            constexpr int RY = 8;
+            const int64_t items = (int64_t)x->w * (x->c / 8);
+            if (!no_walk && x->n <= 65535 && cdiv(x->h, RY) <= 65535) {
+                dim3 grid((unsigned)cdiv(items, 128), (unsigned)cdiv(x->h, RY), (unsigned)x->n);
+                bilinear_up2_walk_kernel<TI, RY><<<grid, 128, 0, st>>>((const TI *)x->ptr, x->ld, (TO *)y->ptr, y->ld, x->n, x->h, x->w, x->c);
+            } else
+                bilinear_up2_kernel<TI><<<row_grid((int64_t)x->n * x->h, (int64_t)x->w * (x->c / 8)), 256, 0, st>>>(
+                    (const TI *)x->ptr, x->ld, (TO *)y->ptr, y->ld, x->n, x->h, x->w, x->c);
             HN_LAUNCH_CHECK();
             return HN_OK;
         }

@@ -56,8 +56,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_r, const HaloParams hp)
 {
     constexpr int B_STAGE_BYTES = BLOCK_N * 128;
-    constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
-    constexpr int TMEM_COLS = BLOCK_N == 64 ? 256 : 2 * ACC_COLS;    // BLOCK_N = 64: + 2 x 16 columns for the fused classifier head
+    // BLOCK_N = 64: the 36+ MMAs of a tile alternate between TWO accumulators (independent dependency chains on the tensor
+    // pipe), summed by the epilogue; + 2 x 16 columns for the fused classifier head
+    constexpr int NACC = BLOCK_N == 64 ? 2 : 1;
+    constexpr int SUB_ACC = BLOCK_N < 32 ? 32 : BLOCK_N;
+    constexpr int ACC_COLS = NACC * SUB_ACC;
+    constexpr int TMEM_COLS = BLOCK_N == 64 ? 512 : 2 * ACC_COLS;
     constexpr uint32_t IDESC = make_idesc_bf16(128, BLOCK_N);
     // A-producer warps of the UPSAMPLE variant: warps 2,3 always; warps 8-11 too when the epilogue only needs 4 warps
     constexpr int NPROD = 6;   // warps 2, 3, 8-11 (the UPSAMPLE variant's epilogue runs on warps 4-7 only)
@@ -117,7 +121,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
     if (warp == 0) {
         // ===================== TMA producer: weight tiles (and the halo patches when they are fetched) =====================
-        if (lane == 0) {
+        // whole warp runs the loop (uniform values stay in uniform registers), the elected lane issues
+        {
             int aslot = 0, bst = 0;
             uint32_t aphase = 0, bphase = 0;
             bool first = true;
@@ -128,16 +133,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (!UPSAMPLE) {
                         mbar_wait(smem_u32(a_empty + aslot), aphase ^ 1);
                         const uint32_t fb = smem_u32(a_full + aslot);
-                        mbar_expect_tx(fb, hp.PW * hp.PH * 128);
-                        tma_load_4d(smem_u32(a_ring + aslot * hp.a_slot_bytes), &tmap_a, fb, kb * 64, tw * HALO_TW - d, th * HALO_TH - d, img);
+                        if (elect_one()) {
+                            mbar_expect_tx(fb, hp.PW * hp.PH * 128);
+                            tma_load_4d(smem_u32(a_ring + aslot * hp.a_slot_bytes), &tmap_a, fb, kb * 64, tw * HALO_TW - d, th * HALO_TH - d, img);
+                        }
+                        __syncwarp();
                         if (++aslot == HALO_NA) { aslot = 0; aphase ^= 1; }
                     }
                     if (hp.b_resident && !first) continue;
                     for (int tap = 0; tap < 9; ++tap) {
                         if (!hp.b_resident) mbar_wait(smem_u32(b_empty + bst), bphase ^ 1);
                         const uint32_t fb = smem_u32(b_full + bst);
-                        mbar_expect_tx(fb, B_STAGE_BYTES);
-                        tma_load_2d(smem_u32(b_ring + bst * B_STAGE_BYTES), &tmap_b, fb, (tap * num_kb + kb) * 64, nt * BLOCK_N);
+                        if (elect_one()) {
+                            mbar_expect_tx(fb, B_STAGE_BYTES);
+                            tma_load_2d(smem_u32(b_ring + bst * B_STAGE_BYTES), &tmap_b, fb, (tap * num_kb + kb) * 64, nt * BLOCK_N);
+                        }
+                        __syncwarp();
                         if (++bst == hp.nb) { bst = 0; bphase ^= 1; }
                     }
                 }
@@ -145,12 +156,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp, elected lane issues) =====================
+        {
             int aslot = 0, bst = 0, acc = 0;
             uint32_t aphase = 0, bphase = 0, acc_phase = 0;
             bool first = true;
             const uint32_t sbo = (uint32_t)(hp.PW * 128) >> 4;
+            // everything of the A descriptor but the start address: LBO = 1, SBO = patch row pitch, version 1, SWIZZLE_128B
+            const uint64_t adesc_hi = ((uint64_t)1 << 16) | ((uint64_t)(sbo & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
                 tcgen05_fence_after();
@@ -160,6 +173,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     mbar_wait(smem_u32(a_full + aslot), aphase);
                     tcgen05_fence_after();
                     const uint32_t a_base = smem_u32(a_ring + aslot * hp.a_slot_bytes);
+#pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const int r = tap / 3, s = tap - r * 3;
                         if (!hp.b_resident || first) {
@@ -168,22 +182,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         }
                         // sub-window of the patch: starts (r*d) patch rows and (s*d) pixels in; 8-row groups are one patch row apart
                         const uint32_t a_addr = a_base + (uint32_t)((r * d) * hp.PW + s * d) * 128;
-                        uint64_t adesc = 0;
-                        adesc |= (uint64_t)((a_addr & 0x3FFFFu) >> 4);
-                        adesc |= (uint64_t)1 << 16;
-                        adesc |= (uint64_t)(sbo & 0x3FFF) << 32;
-                        adesc |= (uint64_t)1 << 46;
-                        adesc |= (uint64_t)2 << 61;
+                        const uint64_t adesc = adesc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
                         const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(b_ring + bst * B_STAGE_BYTES));
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | tap | k) != 0);
-                        if (!hp.b_resident) umma_commit(smem_u32(b_empty + bst));
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(d_tmem + (NACC == 2 ? (tap & 1) * SUB_ACC : 0), adesc + 2 * k, bdesc + 2 * k, IDESC,
+                                          NACC == 2 ? ((kb | (tap >> 1) | k) != 0) : ((kb | tap | k) != 0));
+                            if (!hp.b_resident) umma_commit(smem_u32(b_empty + bst));
+                            if (tap == 8) {
+                                umma_commit(smem_u32(a_empty + aslot));
+                                if (kb == num_kb - 1) umma_commit(smem_u32(tfull_bar + acc));
+                            }
+                        }
+                        __syncwarp();
                         if (++bst == hp.nb) { bst = 0; bphase ^= 1; }
                     }
-                    umma_commit(smem_u32(a_empty + aslot));
                     if (++aslot == HALO_NA) { aslot = 0; aphase ^= 1; }
                 }
-                umma_commit(smem_u32(tfull_bar + acc));
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
                 first = false;
@@ -265,7 +281,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
         }
     } else if (is_epi) {
-        conv_epilogue<BLOCK_N, UPSAMPLE>(p, &tmap_y, &tmap_r, tmem_base, tfull_bar, tempty_bar, res_bar, epi_stage, s_shift, num_tiles, warp, lane);
+        conv_epilogue<BLOCK_N, UPSAMPLE, NACC>(p, &tmap_y, &tmap_r, tmem_base, tfull_bar, tempty_bar, res_bar, epi_stage, s_shift, num_tiles, warp, lane);
     }
 
     tcgen05_fence_before();

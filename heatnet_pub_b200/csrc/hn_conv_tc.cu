@@ -50,7 +50,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t *full_bar = bars, *empty_bar = bars + STAGES, *tfull_bar = bars + 2 * STAGES, *tempty_bar = bars + 2 * STAGES + 2;
     uint64_t *res_bar = bars + 2 * STAGES + 4;                              // one per epilogue warp
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4 + NUM_EPI_WARPS);
-    float *s_shift = reinterpret_cast<float *>(tmem_slot + 4);                // BLOCK_N floats (epilogue shift table)
+    float *s_shift = reinterpret_cast<float *>(tmem_slot + 4);                // epilogue shift table(s): BLOCK_N floats (x2 for BLOCK_N < 128)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_m_tiles = p.n_img * p.tiles_h * p.tiles_w;
@@ -85,8 +85,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (whole warp, elected lane issues) =====================
+        {
             int stage = 0;
             uint32_t phase = 0;
             long long pw_empty = 0, pw_total = 0, ntl = 0;
@@ -105,21 +105,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         for (int cb = 0; cb < p.cblocks; ++cb, ++kb) {
                             { HN_PROF_T0(); mbar_wait(smem_u32(empty_bar + stage), phase ^ 1); HN_PROF_ADD(pw_empty); }
                             const uint32_t fb = smem_u32(full_bar + stage);
-                            mbar_expect_tx(fb, STAGE_BYTES);
                             const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                            tma_load_4d(sa, &tmap_a, fb, cb * BK, w_base + s * p.dil, h_base + r * p.dil, img);
-                            tma_load_2d(sa + A_STAGE_BYTES, &tmap_b, fb, kb * BK, nt * BLOCK_N);
+                            if (elect_one()) {
+                                mbar_expect_tx(fb, STAGE_BYTES);
+                                tma_load_4d(sa, &tmap_a, fb, cb * BK, w_base + s * p.dil, h_base + r * p.dil, img);
+                                tma_load_2d(sa + A_STAGE_BYTES, &tmap_b, fb, kb * BK, nt * BLOCK_N);
+                            }
+                            __syncwarp();
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
             }
 #ifdef HN_PROFILE_ROLES
             pw_total = clock64() - prod_t0;
-            HN_PROF_FLUSH(0, pw_empty); HN_PROF_FLUSH(1, pw_total); HN_PROF_FLUSH(9, ntl); HN_PROF_FLUSH(10, 1);
+            if (lane == 0) { HN_PROF_FLUSH(0, pw_empty); HN_PROF_FLUSH(1, pw_total); HN_PROF_FLUSH(9, ntl); HN_PROF_FLUSH(10, 1); }
 #endif
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp, elected lane issues) =====================
+        {
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -139,20 +142,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                     const uint64_t adesc = make_kmajor_desc(sa, BK * 2);
                     const uint64_t bdesc = make_kmajor_desc(sa + A_STAGE_BYTES, BK * 2);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advance 16 BF16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
-                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            // advance 16 BF16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
+                            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+                        }
+                        umma_commit(smem_u32(empty_bar + stage));   // frees the smem slot when these MMAs retire
+                        if (kb == num_kb - 1) umma_commit(smem_u32(tfull_bar + acc));   // accumulator ready for the epilogue
                     }
-                    umma_commit(smem_u32(empty_bar + stage));   // frees the smem slot when these MMAs retire
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(smem_u32(tfull_bar + acc));          // accumulator ready for the epilogue
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
 #ifdef HN_PROFILE_ROLES
-            HN_PROF_FLUSH(2, mw_full); HN_PROF_FLUSH(3, mw_tempty); HN_PROF_FLUSH(4, clock64() - mma_t0);
+            if (lane == 0) { HN_PROF_FLUSH(2, mw_full); HN_PROF_FLUSH(3, mw_tempty); HN_PROF_FLUSH(4, clock64() - mma_t0); }
 #endif
         }
     } else if (warp >= EPI_WARP0) {
@@ -348,7 +354,7 @@ static int launch_tc(const CUtensorMap &ta, const CUtensorMap &tb, const CUtenso
                      int num_tiles, cudaStream_t st)
 {
     constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BK * 2 + BN * BK * 2) + NUM_EPI_WARPS * EPI_STAGE_BYTES +
-                            (2 * STAGES + 4 + NUM_EPI_WARPS) * 8 + 16 + BN * 4 + 1024;
+                            (2 * STAGES + 4 + NUM_EPI_WARPS) * 8 + 16 + (BN < 128 ? 2 : 1) * BN * 4 + 1024;   // narrow tiles: one shift table per epilogue group
     static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
     static bool configured = false;
     if (!configured) {

@@ -89,7 +89,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
     };
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // whole warp runs the loop, the elected lane issues (see elect_one)
             int stage = 0;
             uint32_t phase = 0;
             for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -102,20 +102,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
                     const int tw = kb % p.tiles_w, th = (kb / p.tiles_w) % p.tiles_h, img = kb / (p.tiles_w * p.tiles_h);
                     mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
                     const uint32_t fb = smem_u32(full_bar + stage);
-                    mbar_expect_tx(fb, STAGE_BYTES);
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    if (elect_one()) {
+                        mbar_expect_tx(fb, STAGE_BYTES);
 #pragma unroll
-                    for (int b = 0; b < 2; ++b)
-                        tma_load_4d(sa + b * WG_BLOCK_BYTES, &tmap_dy, fb, mt * WG_M + b * 64, tw * p.TW, th * p.TH, img);
+                        for (int b = 0; b < 2; ++b)
+                            tma_load_4d(sa + b * WG_BLOCK_BYTES, &tmap_dy, fb, mt * WG_M + b * 64, tw * p.TW, th * p.TH, img);
 #pragma unroll
-                    for (int b = 0; b < BN / 64; ++b)
-                        tma_load_4d(sa + A_BYTES + b * WG_BLOCK_BYTES, &tmap_x, fb, xcol0 + b * 64, tw * p.TW + dx, th * p.TH + dyy, img);
+                        for (int b = 0; b < BN / 64; ++b)
+                            tma_load_4d(sa + A_BYTES + b * WG_BLOCK_BYTES, &tmap_x, fb, xcol0 + b * 64, tw * p.TW + dx, th * p.TH + dyy, img);
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             int stage = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -129,15 +132,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                     const uint64_t adesc = make_mnmajor_sw128_desc(sa, WG_BLOCK_BYTES);
                     const uint64_t bdesc = make_mnmajor_sw128_desc(sa + A_BYTES, WG_BLOCK_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < WG_KPIX / 16; ++k) {
-                        // 16 pixel rows = 2048 B further along K: +128 in the (addr >> 4) field
-                        umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < WG_KPIX / 16; ++k) {
+                            // 16 pixel rows = 2048 B further along K: +128 in the (addr >> 4) field
+                            umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit(smem_u32(empty_bar + stage));
+                        if (kb == kb1 - 1) umma_commit(smem_u32(tfull_bar));
                     }
-                    umma_commit(smem_u32(empty_bar + stage));
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(smem_u32(tfull_bar));
+                if (kb1 <= kb0 && elect_one()) umma_commit(smem_u32(tfull_bar));     // empty split: nothing was issued
+                __syncwarp();
                 acc_phase ^= 1;
             }
         }

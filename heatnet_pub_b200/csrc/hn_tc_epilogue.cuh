@@ -83,12 +83,16 @@ __device__ __forceinline__ void head_emit(const TcParams &p, uint32_t taddr, uin
 // ~224 KB of the SM carved out as shared memory there is next to no L1: per-element __ldg costs an L2 round trip),
 // residual add / ReLU run on packed pairs, swizzled staging offsets are precomputed.  Anything else (FP32 outputs,
 // unaligned views, explicit scale, LeakyReLU + residual) takes the general path below.
-template <int BLOCK_N, bool ONE_GROUP = false>
+template <int BLOCK_N, bool ONE_GROUP = false, int NACC = 1>
 __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorMap *tmap_y_p, const CUtensorMap *tmap_r_p, uint32_t tmem_base,
                                               uint64_t *tfull_bar, uint64_t *tempty_bar, uint64_t *res_bar, uint8_t *epi_stage,
                                               float *s_shift, int num_tiles, int warp, int lane)
 {
-    constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    // NACC = 2: the MMA warp spreads a tile's MMAs over two accumulators (independent accumulation chains: back-to-back MMAs
+    // into ONE accumulator serialise on the tensor pipe's latency, ~100 cycles each, which bounds narrow N = 64 tiles); the
+    // epilogue adds the two halves.  ACC_COLS = TMEM columns per tile buffer.
+    constexpr int SUB_ACC = BLOCK_N < 32 ? 32 : BLOCK_N;
+    constexpr int ACC_COLS = NACC * SUB_ACC;
     const CUtensorMap &tmap_y = *tmap_y_p;
     const CUtensorMap &tmap_r = *tmap_r_p;
     constexpr int GROUPS = (BLOCK_N >= 128 && !ONE_GROUP) ? 2 : 1;   // ONE_GROUP: warps 8-11 have another job
@@ -96,9 +100,12 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
     constexpr int SUB = COLS < 32 ? COLS : 32;             // columns per tcgen05.ld
     const int ew = warp - EPI_WARP0;
     const int q = ew & 3, grp = ew >> 2;
-    if (grp >= GROUPS) return;
+    // narrow tiles (one column group): the two groups of 4 warps ALTERNATE tiles -- group g owns accumulator buffer g, i.e.
+    // every other tile of this CTA -- so two tiles are in the epilogue at once (measured: the N = 64 layers were epilogue-bound)
+    constexpr bool ALT = GROUPS == 1 && !ONE_GROUP;
+    if (!ALT && grp >= GROUPS) return;
     const int row = q * 32 + lane;                     // accumulator row = pixel within the tile
-    const int col0 = grp * COLS;
+    const int col0 = ALT ? 0 : grp * COLS;
     const int esz = p.y_f32 ? 4 : 2;
     const int tch = 128 / esz;                         // columns per staging chunk (128 B per pixel)
     const uint32_t stage = smem_u32(epi_stage + ew * EPI_STAGE_BYTES);
@@ -108,7 +115,7 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
     for (int c = 0; c < 8; ++c) off[c] = srow + ((c ^ (lane & 7)) << 4);
     const uint32_t rbar = smem_u32(res_bar + ew);
     uint32_t rphase = 0;
-    int acc = 0;
+    int acc = ALT ? grp : 0;
     uint32_t acc_phase = 0;
     float slope = p.slope;
     if (p.slope_ptr) slope = __ldg(p.slope_ptr);
@@ -119,7 +126,7 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
     const bool tma_out = p.tma_out && !head;
     const bool fast = SUB == 32 && (tma_out || head) && !p.y_f32 && p.scale == nullptr && (p.res == nullptr || p.tma_res) &&
                       !(act == HN_ACT_LEAKY && p.res != nullptr);
-    float *tab = s_shift + col0;                       // this group's per-channel shift table
+    float *tab = s_shift + (ALT ? grp * BLOCK_N : col0);   // this group's per-channel shift table (ALT: one full table per group)
     const uint32_t tab_addr = smem_u32(tab);
     int loaded_ctile = -1;
     long long ew_tfull = 0, ew_bulk = 0, ew_res = 0;
@@ -127,9 +134,11 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
 #ifdef HN_PROFILE_ROLES
     const long long epi_t0 = clock64();
 #endif
-    int hpar = 0, prev_img = 0, prev_ho = 0, prev_wo = 0;
+    int prev_img = 0, prev_ho = 0, prev_wo = 0;
     bool have_prev = false, prev_valid = false;
-    uint32_t hph = 0;                                   // phase bits of the two head barriers
+    uint32_t hph = 0;                                   // phase of this group's head barrier
+    const uint32_t head_bar = smem_u32(res_bar + 4 * grp);            // no residual with a head: this group's first res_bar is free
+    const uint32_t head_d2 = tmem_base + 2 * ACC_COLS + grp * HEAD_MAX;   // this group's logits accumulator (16 TMEM columns)
     if constexpr (BLOCK_N == 64) {
         if (head) {
             // classifier weights -> BF16 [16 classes][64 ch] K-major SWIZZLE_128B tile behind the staging buffers (rows >= head_n: 0)
@@ -137,12 +146,16 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
             __nv_bfloat162 h4[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) h4[e] = __floats2bfloat162_rn(p.head.w[k][cidx * 8 + 2 * e], p.head.w[k][cidx * 8 + 2 * e + 1]);
-            sts128(smem_u32(epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES) + k * 128 + ((cidx ^ (k & 7)) << 4), *reinterpret_cast<const uint4 *>(h4));
-            fence_proxy_async();
-            named_bar_sync(1 + grp, 128);
+            if (grp == 0) {
+                sts128(smem_u32(epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES) + k * 128 + ((cidx ^ (k & 7)) << 4), *reinterpret_cast<const uint4 *>(h4));
+                fence_proxy_async();
+            }
+            named_bar_sync(3, ALT ? 256 : 128);
         }
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        if (ALT && (it & 1) != grp) continue;
         const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
         const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
         const int ho = th * p.TH + row / p.TW, wo = tw * p.TW + row % p.TW;
@@ -163,22 +176,33 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
         if constexpr (BLOCK_N == 64) {
             if (head) {
                 // ---------------- conv + activation + 1x1 classifier on the tensor core ----------------
-                // phase A(i): activation tile -> BF16 -> swizzled staging buffer (i & 1), which IS a K-major SWIZZLE_128B
-                // [128 pixels][64 ch] UMMA operand; one elected thread issues logits[128][16] = tile x head^T into spare TMEM
-                // columns.  phase B(i-1): the logits of the previous tile (its MMA had a whole tile period to retire) are read
-                // back and written NCHW FP32.  The 64-channel activation never leaves the SM.
+                // The activation tile -> BF16 -> this group's swizzled staging buffer, which IS a K-major SWIZZLE_128B
+                // [128 pixels][64 ch] UMMA operand; one elected thread issues logits[128][16] = tile x head^T into this group's
+                // spare TMEM columns.  The logits of the group's PREVIOUS tile (its MMA had two tile periods to retire) are read
+                // back first -- that wait also proves the staging buffer and the logits columns are free again.
+                if (have_prev) {
+                    head_emit(p, head_d2 + ((uint32_t)(q * 32) << 16), head_bar, hph, prev_img, prev_ho, prev_wo, prev_valid);
+                    hph ^= 1;
+                }
                 { HN_PROF_T0(); mbar_wait(smem_u32(tfull_bar + acc), acc_phase); HN_PROF_ADD(ew_tfull); }
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
-                const uint32_t poff = hpar * (4 * EPI_STAGE_BYTES);
 #pragma unroll
                 for (int si = 0; si < 2; ++si) {
                     uint32_t raw[32];
                     tmem_ld_32x32(taddr + si * 32, raw);
-                    tmem_ld_wait();
                     float v[32];
+                    if constexpr (NACC == 2) {
+                        uint32_t raw2[32];
+                        tmem_ld_32x32(taddr + SUB_ACC + si * 32, raw2);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) + __uint_as_float(raw2[j]);
+                    } else {
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+                    }
                     if (p.shift) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -200,32 +224,25 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
 #pragma unroll
                     for (int j = 0; j < 16; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) sts128(off[si * 4 + j] + poff, *reinterpret_cast<const uint4 *>(&h[4 * j]));
+                    for (int j = 0; j < 4; ++j) sts128(off[si * 4 + j], *reinterpret_cast<const uint4 *>(&h[4 * j]));
                 }
                 tcgen05_fence_before();
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
-                named_bar_sync(1 + grp, 128);           // all four staging quarters written; phase B(i-2) reads of D2[hpar] done
-                if (ew == 0 && lane == 0) {
+                if (ALT) acc_phase ^= 1;
+                else { acc ^= 1; if (acc == 0) acc_phase ^= 1; }
+                named_bar_sync(1 + grp, 128);           // all four staging quarters written, previous logits read
+                if (q == 0 && lane == 0) {
                     tcgen05_fence_after();
-                    const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(epi_stage) + poff);
+                    const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(epi_stage + (ew & 4) * EPI_STAGE_BYTES));
                     const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES));
-                    const uint32_t d2 = tmem_base + 2 * ACC_COLS + hpar * HEAD_MAX;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(d2, adesc + 2 * k, bdesc + 2 * k, make_idesc_bf16(128, HEAD_MAX), k != 0);
-                    umma_commit(smem_u32(res_bar + 4 + hpar));
-                }
-                if (have_prev) {
-                    head_emit(p, tmem_base + ((uint32_t)(q * 32) << 16) + 2 * ACC_COLS + (hpar ^ 1) * HEAD_MAX,
-                              smem_u32(res_bar + 4 + (hpar ^ 1)), (hph >> (hpar ^ 1)) & 1u, prev_img, prev_ho, prev_wo, prev_valid);
-                    hph ^= 1u << (hpar ^ 1);
+                    for (int k = 0; k < 4; ++k) umma_bf16(head_d2, adesc + 2 * k, bdesc + 2 * k, make_idesc_bf16(128, HEAD_MAX), k != 0);
+                    umma_commit(head_bar);
                 }
                 have_prev = true;
                 prev_img = img; prev_ho = ho; prev_wo = wo; prev_valid = valid;
-                hpar ^= 1;
                 continue;
             }
         }
@@ -254,7 +271,15 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
                 uint32_t raw[SUB];
                 if constexpr (SUB == 32) tmem_ld_32x32(taddr + si * SUB, raw);
                 else if constexpr (SUB == 16) tmem_ld_32x16(taddr + si * SUB, raw);
-                tmem_ld_wait();
+                if constexpr (NACC == 2 && SUB == 32) {
+                    uint32_t raw2[SUB];
+                    tmem_ld_32x32(taddr + SUB_ACC + si * SUB, raw2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < SUB; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
+                } else {
+                    tmem_ld_wait();
+                }
                 const int cbase = ctile + ck + si * SUB;
                 if (chunk_on) {
                     float v[SUB];
@@ -400,13 +425,11 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (ALT) acc_phase ^= 1;
+        else { acc ^= 1; if (acc == 0) acc_phase ^= 1; }
     }
     if constexpr (BLOCK_N == 64) {
-        if (head && have_prev)
-            head_emit(p, tmem_base + ((uint32_t)(q * 32) << 16) + 2 * ACC_COLS + (hpar ^ 1) * HEAD_MAX, smem_u32(res_bar + 4 + (hpar ^ 1)),
-                      (hph >> (hpar ^ 1)) & 1u, prev_img, prev_ho, prev_wo, prev_valid);
+        if (head && have_prev) head_emit(p, head_d2 + ((uint32_t)(q * 32) << 16), head_bar, hph, prev_img, prev_ho, prev_wo, prev_valid);
     }
     if (tma_out && lane == 0) bulk_wait_read0();    // staging tile must outlive the last bulk store
 #ifdef HN_PROFILE_ROLES

@@ -47,6 +47,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "r"(parity)
         : "memory");
 }
+// One lane of a converged warp.  The producer / MMA roles run their loops on the WHOLE warp (all values warp-uniform, so
+// ptxas keeps addresses, descriptors and barriers in uniform registers) and only the TMA / tcgen05 instruction itself is
+// predicated on the elected lane.  Running the loop on `lane == 0` alone makes every operand "divergent": each UTCHMMA /
+// UTMALDG then sits in an R2UR + ELECT waterfall loop, ~100 cycles per issued MMA (measured: N = 64 layers were issue-bound).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
