@@ -60,6 +60,7 @@ SIGNATURES = {
     "hn_bn_finalize": (C.c_int, [_P, _P, _I64, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _I32, _P]),
     "hn_act_bwd": (C.c_int, [_T, _T, _I32, _F, _T, _P]),
     "hn_bn_bwd": (C.c_int, [_T, _T, _T, _P, _P, _P, _I32, _F, _P, _P, _T, _T, _I32, _I32, _P, _P, _P, _I32, _P]),
+    "hn_stem_pad_slack_bytes": (_I64, []),
     "hn_conv3x3_head_fwd": (C.c_int, [_T, _P, _CV, _E, _P, _P, _I32, _P, _P]),
     "hn_bn_batch_stats_scratch_bytes": (_I64, [_I32]),
     "hn_bn_batch_stats": (C.c_int, [_T, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -113,7 +114,7 @@ def load():
 timeline = None
 _NO_TIMING = {"hn_last_error", "hn_version", "hn_device_check", "hn_prof_read", "hn_conv_cout_pad", "hn_conv_kpad", "hn_optim_chunk",
               "hn_conv2d_workspace_bytes", "hn_conv2d_wgrad_workspace_bytes", "hn_pyramid_pool_workspace_bytes",
-              "hn_bilinear_bwd_workspace_bytes", "hn_loss_scratch_bytes", "hn_bn_batch_stats_scratch_bytes"}
+              "hn_bilinear_bwd_workspace_bytes", "hn_loss_scratch_bytes", "hn_bn_batch_stats_scratch_bytes", "hn_stem_pad_slack_bytes"}
 
 
 def _describe(name, args):

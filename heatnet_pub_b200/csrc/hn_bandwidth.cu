@@ -377,6 +377,7 @@ constexpr int kMaxPoolCols = 12;  // sum of sizes, (1,2,3,6) -> 12
 struct PoolSizes {
     int n, s[4];
     int ncols, w0[kMaxPoolCols], w1[kMaxPoolCols];  // column-bin bounds of every size, concatenated
+    int nseg, segb[2 * kMaxPoolCols + 2];           // sorted union of all bounds: column segments, each inside or outside every bin
 };
 
 template <typename T>
@@ -393,14 +394,32 @@ __global__ void __launch_bounds__(256) pyramid_rows_kernel(const T *__restrict__
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[b][j] = 0.f;
     const T *row = x + nh * W * ldx + cv * 8;
-    for (int w = 0; w < W; ++w) {
-        float v[8];
-        Vec8<T>::load(row + (int64_t)w * ldx, v);
+    // walk the row segment by segment (warp-uniform bounds): 8 adds per load inside a segment, 4 loads in flight; a finished
+    // segment is added to every bin that contains it (bins of one size overlap when W % s != 0)
+    for (int sg = 0; sg < ps.nseg; ++sg) {
+        const int s0 = ps.segb[sg], s1 = ps.segb[sg + 1];
+        float seg[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) seg[j] = 0.f;
+        int w = s0;
+        for (; w + 4 <= s1; w += 4) {
+            float v[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) Vec8<T>::load(row + (int64_t)(w + u) * ldx, v[u]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) seg[j] += (v[0][j] + v[1][j]) + (v[2][j] + v[3][j]);
+        }
+        for (; w < s1; ++w) {
+            float v[8];
+            Vec8<T>::load(row + (int64_t)w * ldx, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) seg[j] += v[j];
+        }
 #pragma unroll
         for (int b = 0; b < kMaxPoolCols; ++b) {
-            if (b < ncols && w >= ps.w0[b] && w < ps.w1[b]) {
+            if (b < ncols && s0 >= ps.w0[b] && s1 <= ps.w1[b]) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[b][j] += v[j];
+                for (int j = 0; j < 8; ++j) acc[b][j] += seg[j];
             }
         }
     }
@@ -1022,6 +1041,16 @@ extern "C" int hn_pyramid_pool_fwd(const hn_tensor *x, const int32_t *sizes, int
             ps.w1[ps.ncols] = ((j + 1) * x->w + sizes[i] - 1) / sizes[i];
             ++ps.ncols;
         }
+    {   // segment bounds = sorted union of all bin bounds
+        int nb = 0, b[2 * kMaxPoolCols + 2];
+        for (int i = 0; i < ps.ncols; ++i) { b[nb++] = ps.w0[i]; b[nb++] = ps.w1[i]; }
+        for (int i = 1; i < nb; ++i)
+            for (int j = i; j > 0 && b[j - 1] > b[j]; --j) { int t = b[j]; b[j] = b[j - 1]; b[j - 1] = t; }
+        int m = 0;
+        for (int i = 0; i < nb; ++i)
+            if (m == 0 || ps.segb[m - 1] != b[i]) ps.segb[m++] = b[i];
+        ps.nseg = m - 1;
+    }
     if (workspace_bytes < hn_pyramid_pool_workspace_bytes(x, sizes, nsizes)) {
         set_error("hn_pyramid_pool_fwd: workspace too small");
         return HN_ERR_WORKSPACE;
@@ -1128,6 +1157,7 @@ __global__ void pack_stem_weight_kernel(const float *__restrict__ w, const float
     dst[i] = __float2bfloat16_rn(v);
 }
 int conv_stem_tc(const hn_tensor *xpad, const void *w, int cout, const hn_epilogue *ep, const hn_tensor *y, cudaStream_t st);
+int conv_stem_dense(const hn_tensor *xpad, const void *w, int cout, const hn_epilogue *ep, const hn_tensor *y, cudaStream_t st);
 }  // namespace hn
 
 extern "C" int hn_stem_pad(const hn_tensor *x, const hn_tensor *xpad, void *stream)
@@ -1157,5 +1187,9 @@ extern "C" int hn_stem7x7s2_fwd(const hn_tensor *xpad, const void *w_packed, int
 {
     HN_CHECK_ARG(xpad && w_packed && ep && y && xpad->ptr && y->ptr, "hn_stem7x7s2_fwd: null pointer");
     HN_CHECK_ARG(y->n == xpad->n && y->c == cout, "hn_stem7x7s2_fwd: output view mismatch");
-    return hn::conv_stem_tc(xpad, w_packed, cout, ep, y, (cudaStream_t)stream);
+    // default: the dense-row kernel (hn_conv_stem.cu; needs hn_stem_pad_slack_bytes() readable bytes behind the image);
+    // HN_STEM_WINDOW_TMA=1 selects the overlapping-window tensor-map variant (hn_conv_tc.cu)
+    static const bool window_tma = getenv("HN_STEM_WINDOW_TMA") != nullptr;
+    if (window_tma || xpad->w % 2 != 0) return hn::conv_stem_tc(xpad, w_packed, cout, ep, y, (cudaStream_t)stream);
+    return hn::conv_stem_dense(xpad, w_packed, cout, ep, y, (cudaStream_t)stream);
 }

@@ -384,7 +384,9 @@ def stem_conv(x: "Act", conv: torch.nn.Conv2d, wp: torch.Tensor, shift, act=ACT_
               out: Optional["Act"] = None, out_dtype=None) -> "Act":
     lib = _lib.load()
     ho, wo = conv_out_hw(x.h, x.w, conv)
-    xpad = new_act(x.n, 2 * ho + 6, 2 * wo + 6, 4, torch.bfloat16, x.buf.device)
+    hpad, wpad = 2 * ho + 6, 2 * wo + 6
+    flat = torch.empty((x.n * hpad * wpad * 4 + lib.hn_stem_pad_slack_bytes() // 2,), dtype=torch.bfloat16, device=x.buf.device)
+    xpad = Act(flat[:x.n * hpad * wpad * 4].view(x.n, hpad, wpad, 4))         # + readable slack behind the last row (hn_stem_pad_slack_bytes)
     if out is None:
         out = new_act(x.n, ho, wo, conv.out_channels, out_dtype or x.dtype, x.buf.device)
     ep = _epilogue(None, shift, None, act, slope, slope_ptr)

@@ -122,6 +122,10 @@ int hn_conv3x3_head_fwd(const hn_tensor *x, const void *w_packed, const hn_conv 
  * output pixel are contiguous and consecutive windows overlap, which a strided tensor map hands to TMA directly.
  * hn_pack_stem_weight: OIHW -> [64][7][8][4] (optionally scaled per output channel). */
 int hn_stem_pad(const hn_tensor *x, const hn_tensor *xpad, void *stream);
+/* hn_stem7x7s2_fwd feeds tcgen05 straight from dense rows of the padded image (the overlapping windows are expressed by the
+ * operand descriptor's strides, hn_conv_stem.cu) and reads whole 2112-byte row segments: the allocation behind xpad must
+ * extend at least this many bytes past the last row (contents irrelevant). */
+int64_t hn_stem_pad_slack_bytes(void);
 int hn_pack_stem_weight(const float *w_oihw, const float *row_scale, void *dst, int32_t cout, int32_t cin, void *stream);
 int hn_stem7x7s2_fwd(const hn_tensor *xpad, const void *w_packed, int32_t cout, const hn_epilogue *ep, const hn_tensor *y, void *stream);
 
