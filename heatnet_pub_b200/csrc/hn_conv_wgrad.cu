@@ -49,6 +49,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
     uint64_t *full_bar = bars, *empty_bar = bars + STAGES, *tfull_bar = bars + 2 * STAGES, *tempty_bar = bars + 2 * STAGES + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 2);
+    float *tr_buf = reinterpret_cast<float *>(tmem_slot + 4);          // 4 epilogue warps x [32][36] floats (16-byte aligned)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = p.n_img * p.tiles_h * p.tiles_w;
@@ -151,17 +152,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
         }
     } else if (warp >= 4) {
         const int q = warp - 4;
-        const int row = q * 32 + lane;
         uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
             int mt, nt, tap, kb0, kb1;
             decode(item, mt, nt, tap, kb0, kb1);
-            const int co = mt * WG_M + row;
             mbar_wait(smem_u32(tfull_bar), acc_phase);
             tcgen05_fence_after();
             acc_phase ^= 1;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-            float *drow = p.dw + (int64_t)co * p.kpad + (int64_t)tap * p.ncols + nt * BN;
+            // Thread = one Cout row of the accumulator.  Adding it straight to the packed gradient would touch 32 rows (32
+            // sectors) per warp instruction; instead every 32x32 block goes through a padded shared-memory tile so that one
+            // red.global.add.v4.f32 per lane covers 4 rows x 128 contiguous bytes (8x fewer L2 sectors, 4x fewer instructions).
+            const uint32_t tbuf = smem_u32(tr_buf + q * (32 * 36));
+            const int64_t colbase = (int64_t)tap * p.ncols + nt * BN;
             constexpr int CH = BN < 32 ? BN : 32;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += CH) {
@@ -169,11 +172,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
                 if constexpr (CH == 32) tmem_ld_32x32(taddr + c0, raw);
                 else tmem_ld_32x16(taddr + c0, raw);
                 tmem_ld_wait();
-                if (co < p.Cout && kb1 > kb0) {
+                if (kb1 <= kb0) continue;                                    // warp-uniform
 #pragma unroll
-                    for (int j = 0; j < CH; ++j)
-                        if (nt * BN + c0 + j < p.ncols) atomicAdd(drow + c0 + j, __uint_as_float(raw[j]));
+                for (int j = 0; j < CH / 4; ++j)
+                    sts128(tbuf + lane * 144 + j * 16, make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = 4 * i + (lane >> 3), c4 = (lane & 7) * 4;
+                    if (c4 < CH) {
+                        const uint4 v = lds128(tbuf + r * 144 + c4 * 4);
+                        const int cor = mt * WG_M + q * 32 + r;
+                        if (cor < p.Cout && nt * BN + c0 + c4 < p.ncols) {
+                            float *dst = p.dw + (int64_t)cor * p.kpad + colbase + c0 + c4;
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(v.x)),
+                                         "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                                         : "memory");
+                        }
+                    }
                 }
+                __syncwarp();
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -191,7 +209,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
 template <int BN, int STAGES>
 static int launch_wgrad(const CUtensorMap &tdy, const CUtensorMap &tx, const WgParams &p, cudaStream_t st)
 {
-    constexpr size_t smem = (size_t)STAGES * (2 + BN / 64) * WG_BLOCK_BYTES + (2 * STAGES + 2) * 8 + 16 + 1024;
+    constexpr size_t smem = (size_t)STAGES * (2 + BN / 64) * WG_BLOCK_BYTES + (2 * STAGES + 2) * 8 + 16 + 4 * 32 * 36 * 4 + 1024;
+    static_assert(smem <= 227 * 1024, "wgrad shared memory");
     static bool configured = false;
     if (!configured) {
         HN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

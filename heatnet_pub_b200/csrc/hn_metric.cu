@@ -33,8 +33,9 @@ __device__ __forceinline__ void count_pixel(uint32_t *table, int lane, long long
         return;
     }
     int bin = (int)t * K + (int)p;
-    uint32_t *w = table + (bin >> 1) * 32 + lane;
-    *w += (bin & 1) ? 0x10000u : 1u;
+    // lane-private word: never contended, but the shared-memory atomic (result unused) is fire-and-forget, whereas a
+    // load-add-store chain on possibly-aliasing addresses serialises the pixels of a thread on the LDS latency
+    atomicAdd(table + (bin >> 1) * 32 + lane, (bin & 1) ? 0x10000u : 1u);
 }
 
 __device__ __forceinline__ void flush_table(uint32_t *table, int lane, int nwords, int nbins,

@@ -850,6 +850,8 @@ def conv2d_wgrad(x: Act, dy: Act, conv: torch.nn.Conv2d) -> torch.Tensor:
     ws_ptr = workspace(ws_bytes, x.buf.device).data_ptr() if ws_bytes else None
     _lib.check(lib.hn_conv2d_wgrad(C.byref(xh), C.byref(dh), C.byref(cv), packed.data_ptr(), 1, ws_ptr, ws_bytes, _stream()))
     _count(2 + (1 if ws_bytes else 0))
+    if k == 1 and kpad == cin and cout_pad == cout:       # 1x1, no padding: the packed [Cout][Cin] matrix IS the OIHW gradient
+        return packed.view(cout, cin, 1, 1)
     grad = torch.empty((cout, cin, k, k), dtype=torch.float32, device=x.buf.device)
     _lib.check(lib.hn_unpack_wgrad(packed.data_ptr(), grad.data_ptr(), cout, cin, k, k, kpad, 0, _stream()))
     _count()
