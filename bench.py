@@ -27,6 +27,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: NCCL's own banner / debug output ("NCCL version ...") goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "rgb_thermal_seg_images_per_sec"
 UNIT = "images/s"
