@@ -74,18 +74,21 @@ __global__ void __launch_bounds__(256) act_bwd_scalar_kernel(const TG *__restric
 //   apply : draw = gamma*invstd*(dz - s1/m - xhat*s2/m)   and   dres (+)= dz
 // blockDim = (CVB, PL) as in channel_stats_kernel.
 // ------------------------------------------------------------------------------------------------
-template <typename TG, typename TO, typename TR>
+// ZOUT = false: `out` is not read; the pre-activation z = fmaf(raw, fscale, fshift) is recomputed with the forward pass's own
+// scale/shift vectors (bit-identical to what the forward activated; only valid for layers without a residual input) -- one
+// tensor less to stream in both passes.
+template <typename TG, typename TO, typename TR, bool ZOUT>
 __global__ void bn_bwd_reduce_kernel(const TG *__restrict__ dout, int ldg, const TO *__restrict__ out, int ldo, const TR *__restrict__ raw,
                                      int ldr, const float *__restrict__ mean, const float *__restrict__ invstd, int act, float slope,
                                      const float *slope_ptr, int64_t npix, int C, int64_t pix_per_cta, double *s1, double *s2,
-                                     double *sprelu)
+                                     double *sprelu, const float *__restrict__ fscale, const float *__restrict__ fshift)
 {
     extern __shared__ float red[];  // [2][PL][CVB*8]
     const int cv = blockIdx.y * blockDim.x + threadIdx.x;
     const int ncv = C / 8;
     const int PL = blockDim.y, CVB = blockDim.x;
     if (slope_ptr) slope = __ldg(slope_ptr);
-    float a[8], b[8], mu[8], is[8], sp = 0.f;
+    float a[8], b[8], mu[8], is[8], fs[8], fh[8], sp = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) a[i] = b[i] = 0.f;
     const int64_t p_begin = (int64_t)blockIdx.x * pix_per_cta;
@@ -93,14 +96,19 @@ __global__ void bn_bwd_reduce_kernel(const TG *__restrict__ dout, int ldg, const
     if (cv < ncv) {
         Vec8<float>::load(mean + cv * 8, mu);
         Vec8<float>::load(invstd + cv * 8, is);
+        if (!ZOUT) {
+            Vec8<float>::load(fscale + cv * 8, fs);
+            Vec8<float>::load(fshift + cv * 8, fh);
+        }
         for (int64_t p = p_begin + threadIdx.y; p < p_end; p += PL) {
             float g[8], o[8], r[8];
             Vec8<TG>::load(dout + p * ldg + cv * 8, g);
-            Vec8<TO>::load(out + p * ldo + cv * 8, o);
+            if (ZOUT) Vec8<TO>::load(out + p * ldo + cv * 8, o);
             Vec8<TR>::load(raw + p * ldr + cv * 8, r);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                if (sprelu && o[i] < 0.f) sp += g[i] * (o[i] / slope);      // z = out / slope on the negative side
+                if (!ZOUT) o[i] = fmaf(r[i], fs[i], fh[i]);                   // z itself: act'(z) == act'(act(z)) for (leaky) ReLU
+                if (sprelu && o[i] < 0.f) sp += g[i] * (ZOUT ? o[i] / slope : o[i]);      // z = out / slope on the negative side
                 const float dz = g[i] * act_grad(o[i], act, slope);
                 a[i] += dz;
                 b[i] = fmaf(dz, (r[i] - mu[i]) * is[i], b[i]);
@@ -137,7 +145,7 @@ __global__ void bn_bwd_reduce_kernel(const TG *__restrict__ dout, int ldg, const
 // blockDim = (CVB, PL) like the reduce pass: a thread keeps ONE 8-channel group for all its pixels, so the per-channel
 // coefficients (FP64 sums -> three FP32 vectors) are formed once per thread and the pixel loop only moves data:
 //   draw = ka*dz + kb*(raw - mean) + kc,   ka = gamma*invstd, kb = -ka*invstd*s2/m, kc = -ka*s1/m
-template <typename TG, typename TO, typename TR>
+template <typename TG, typename TO, typename TR, bool ZOUT>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TG *__restrict__ dout, int ldg, const TO *__restrict__ out, int ldo,
                                                            const TR *__restrict__ raw, int ldr, const float *__restrict__ mean,
                                                            const float *__restrict__ invstd, const float *__restrict__ gamma,
@@ -145,7 +153,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TG *__restrict_
                                                            int act, float slope, const float *slope_ptr, TG *__restrict__ draw, int ldd,
                                                            TG *__restrict__ dres, int ldres, int dres_accumulate, int64_t npix, int C,
                                                            int64_t pix_per_cta, float *__restrict__ dbeta, float *__restrict__ dgamma,
-                                                           float *__restrict__ dslope, const double *__restrict__ sprelu, int param_accumulate)
+                                                           float *__restrict__ dslope, const double *__restrict__ sprelu, int param_accumulate,
+                                                           const float *__restrict__ fscale, const float *__restrict__ fshift)
 {
     const int cv = blockIdx.y * blockDim.x + threadIdx.x;
     if (cv >= C / 8) return;
@@ -160,7 +169,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TG *__restrict_
         }
         if (dslope && sprelu && cv == 0) dslope[0] = (param_accumulate ? dslope[0] : 0.f) + (float)sprelu[0];
     }
-    float mu[8], ka[8], kb[8], kc[8];
+    float mu[8], ka[8], kb[8], kc[8], fs[8], fh[8];
+    if (!ZOUT) {
+        Vec8<float>::load(fscale + c, fs);
+        Vec8<float>::load(fshift + c, fh);
+    }
     {
         float is[8], ga[8];
         Vec8<float>::load(mean + c, mu);
@@ -180,7 +193,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TG *__restrict_
         float dx[8], dz[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            dz[j] = g[j] * act_grad(o[j], act, slope);
+            dz[j] = g[j] * act_grad(ZOUT ? o[j] : fmaf(r[j], fs[j], fh[j]), act, slope);
             dx[j] = fmaf(ka[j], dz[j], fmaf(kb[j], r[j] - mu[j], kc[j]));
         }
         Vec8<TG>::store(draw + p * ldd + c, dx);
@@ -199,8 +212,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TG *__restrict_
         float g0[8], o0[8], r0[8], g1[8], o1[8], r1[8];
         Vec8<TG>::load(dout + p * ldg + c, g0);
         Vec8<TG>::load(dout + (p + PL) * ldg + c, g1);
-        Vec8<TO>::load(out + p * ldo + c, o0);
-        Vec8<TO>::load(out + (p + PL) * ldo + c, o1);
+        if (ZOUT) {
+            Vec8<TO>::load(out + p * ldo + c, o0);
+            Vec8<TO>::load(out + (p + PL) * ldo + c, o1);
+        }
         Vec8<TR>::load(raw + p * ldr + c, r0);
         Vec8<TR>::load(raw + (p + PL) * ldr + c, r1);
         one(p, g0, o0, r0);
@@ -209,7 +224,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TG *__restrict_
     if (p < p_end) {
         float g0[8], o0[8], r0[8];
         Vec8<TG>::load(dout + p * ldg + c, g0);
-        Vec8<TO>::load(out + p * ldo + c, o0);
+        if (ZOUT) Vec8<TO>::load(out + p * ldo + c, o0);
         Vec8<TR>::load(raw + p * ldr + c, r0);
         one(p, g0, o0, r0);
     }
@@ -802,9 +817,11 @@ extern "C" int hn_act_bwd(const hn_tensor *dout, const hn_tensor *out, int32_t a
 extern "C" int hn_bn_bwd(const hn_tensor *dout, const hn_tensor *out, const hn_tensor *raw, const float *mean, const float *invstd,
                          const float *gamma, int32_t act, float slope, const float *slope_ptr, double *sums /* [2*C + 1] scratch+result */,
                          const hn_tensor *draw, const hn_tensor *dres, int32_t dres_accumulate, int32_t want_prelu_grad, float *dbeta, float *dgamma,
-                         float *dslope, int32_t param_accumulate, void *stream)
+                         float *dslope, int32_t param_accumulate, const float *fwd_scale, const float *fwd_shift, void *stream)
 {
     HN_CHECK_ARG(dout && out && raw && mean && invstd && sums && draw, "hn_bn_bwd: null pointer");
+    HN_CHECK_ARG((fwd_scale != nullptr) == (fwd_shift != nullptr), "hn_bn_bwd: give both forward vectors or neither");
+    const bool zout = fwd_scale == nullptr;      // read the saved output; else recompute z = raw*scale + shift
     HN_CHECK_ARG(same_shape(dout, out) && same_shape(dout, raw) && same_shape(dout, draw), "hn_bn_bwd: shape mismatch");
     HN_CHECK_ARG(raw->dtype == HN_F32 || (raw->dtype == HN_BF16 && dout->dtype == HN_BF16), "hn_bn_bwd: the pre-normalisation tensor is FP32 (or BF16 on the BF16 path)");
     HN_CHECK_ARG(dout->dtype == draw->dtype && (!dres || dres->dtype == dout->dtype), "hn_bn_bwd: gradient dtypes must match");
@@ -832,10 +849,15 @@ extern "C" int hn_bn_bwd(const hn_tensor *dout, const hn_tensor *out, const hn_t
     chunks2 = cdiv(npix, pix_per_cta2);
     dim3 grid2((unsigned)chunks2, (unsigned)cvblocks);
     const double inv_count = 1.0 / (double)npix;
+#define HN_BN_BWD_Z(TG, TO, TR, Z)                                                                                                       \
+    do {                                                                                                                                  \
+        bn_bwd_reduce_kernel<TG, TO, TR, Z><<<grid, block, smem, st>>>((const TG *)dout->ptr, dout->ld, (const TO *)out->ptr, out->ld, (const TR *)raw->ptr, raw->ld, mean, invstd, act, slope, slope_ptr, npix, C, pix_per_cta, s1, s2, sp, fwd_scale, fwd_shift); \
+        bn_bwd_apply_kernel<TG, TO, TR, Z><<<grid2, block, 0, st>>>((const TG *)dout->ptr, dout->ld, (const TO *)out->ptr, out->ld, (const TR *)raw->ptr, raw->ld, mean, invstd, gamma, s1, s2, inv_count, act, slope, slope_ptr, (TG *)draw->ptr, draw->ld, dres ? (TG *)dres->ptr : nullptr, dres ? dres->ld : 0, dres_accumulate, npix, C, pix_per_cta2, dbeta, dgamma, want_prelu_grad ? dslope : nullptr, sp, param_accumulate, fwd_scale, fwd_shift); \
+    } while (0)
 #define HN_BN_BWD(TG, TO, TR)                                                                                                             \
     do {                                                                                                                                  \
-        bn_bwd_reduce_kernel<TG, TO, TR><<<grid, block, smem, st>>>((const TG *)dout->ptr, dout->ld, (const TO *)out->ptr, out->ld, (const TR *)raw->ptr, raw->ld, mean, invstd, act, slope, slope_ptr, npix, C, pix_per_cta, s1, s2, sp); \
-        bn_bwd_apply_kernel<TG, TO, TR><<<grid2, block, 0, st>>>((const TG *)dout->ptr, dout->ld, (const TO *)out->ptr, out->ld, (const TR *)raw->ptr, raw->ld, mean, invstd, gamma, s1, s2, inv_count, act, slope, slope_ptr, (TG *)draw->ptr, draw->ld, dres ? (TG *)dres->ptr : nullptr, dres ? dres->ld : 0, dres_accumulate, npix, C, pix_per_cta2, dbeta, dgamma, want_prelu_grad ? dslope : nullptr, sp, param_accumulate); \
+        if (zout) HN_BN_BWD_Z(TG, TO, TR, true);                                                                                          \
+        else HN_BN_BWD_Z(TG, TO, TR, false);                                                                                              \
     } while (0)
     if (dout->dtype == HN_BF16 && out->dtype == HN_BF16 && raw->dtype == HN_BF16) HN_BN_BWD(bf16, bf16, bf16);
     else if (dout->dtype == HN_BF16 && out->dtype == HN_BF16) HN_BN_BWD(bf16, bf16, float);
@@ -845,6 +867,7 @@ extern "C" int hn_bn_bwd(const hn_tensor *dout, const hn_tensor *out, const hn_t
         return HN_ERR_ARG;
     }
 #undef HN_BN_BWD
+#undef HN_BN_BWD_Z
     HN_LAUNCH_CHECK();
     return HN_OK;
 }

@@ -624,8 +624,10 @@ def conv_bn_act(x: Act, conv, bn, act=ACT_NONE, slope=0.0, slope_ptr=None, resid
                 if tape.needs(residual):
                     dres, dres_acc = grads.target(residual)
                 prelu = _wants(slope_ptr)
+                # no residual: the pre-activation is recomputed from raw with the forward's own scale/shift (y is not streamed)
+                fz = (bscale, bshift) if residual is None else (None, None)
                 draw, pg = bn_bwd(dout, y, raw, mean, invstd, bn.weight, act, slope, slope_ptr, dres, dres_acc, prelu,
-                                  _wants(bn.bias), _wants(bn.weight))
+                                  _wants(bn.bias), _wants(bn.weight), fz[0], fz[1])
                 if dres is not None:
                     grads.mark(residual)
                 if pg[0] is not None:
@@ -881,7 +883,7 @@ def vec_to_grad(src_f64: torch.Tensor, n: int) -> torch.Tensor:
 
 
 def bn_bwd(dout: Act, out: Act, raw: Act, mean, invstd, gamma, act, slope=0.0, slope_ptr=None, dres: Optional[Act] = None,
-           dres_accumulate=False, want_prelu_grad=False, want_dbeta=True, want_dgamma=True):
+           dres_accumulate=False, want_prelu_grad=False, want_dbeta=True, want_dgamma=True, fwd_scale=None, fwd_shift=None):
     """-> (draw Act, (dbeta, dgamma, dslope)): FP32 parameter gradients written by the apply kernel itself (None when not
     asked for)."""
     cch = dout.c
@@ -896,7 +898,7 @@ def bn_bwd(dout: Act, out: Act, raw: Act, mean, invstd, gamma, act, slope=0.0, s
     _lib.check(_lib.load().hn_bn_bwd(C.byref(dout.hn()), C.byref(out.hn()), C.byref(raw.hn()), p(mean), p(invstd), p(gamma), act,
                                     float(slope), p(slope_ptr), sums.data_ptr(), C.byref(draw.hn()),
                                     C.byref(dres.hn()) if dres is not None else None, int(dres_accumulate),
-                                    int(want_prelu_grad), p(dbeta), p(dgamma), p(dslope), 0, _stream()))
+                                    int(want_prelu_grad), p(dbeta), p(dgamma), p(dslope), 0, p(fwd_scale), p(fwd_shift), _stream()))
     _count(3)
     return draw, (dbeta, dgamma, dslope)
 

@@ -170,11 +170,14 @@ int hn_act_bwd(const hn_tensor *dout, const hn_tensor *out, int32_t act, float s
  *   dz = dout*act'(out);  sums[0..C) = sum dz (= dbeta), sums[C..2C) = sum dz*xhat (= dgamma), sums[2C] = dPReLU slope
  *   draw = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat));  dres (+)= dz.   raw: pre-normalisation tensor (FP32, or BF16
  *   on the BF16 path).  dbeta / dgamma [C] and dslope [1] (each optional) receive the FP32 parameter gradients directly,
- *   added to their current contents when param_accumulate is set (a second backward pass into an existing .grad). */
+ *   added to their current contents when param_accumulate is set (a second backward pass into an existing .grad).
+ *   fwd_scale / fwd_shift (both or neither): the scale/shift vectors the forward normalise pass used.  When given -- only valid
+ *   for a layer WITHOUT a residual input -- `out` is not read: the pre-activation z = fma(raw, scale, shift) is recomputed
+ *   bit-identically, which removes one tensor from both passes. */
 int hn_bn_bwd(const hn_tensor *dout, const hn_tensor *out, const hn_tensor *raw, const float *mean, const float *invstd,
               const float *gamma, int32_t act, float slope, const float *slope_ptr, double *sums, const hn_tensor *draw,
               const hn_tensor *dres, int32_t dres_accumulate, int32_t want_prelu_grad, float *dbeta, float *dgamma, float *dslope,
-              int32_t param_accumulate, void *stream);
+              int32_t param_accumulate, const float *fwd_scale, const float *fwd_shift, void *stream);
 /* y = x (accumulate == 0) or y += x; dtypes may differ */
 int hn_accumulate(const hn_tensor *x, const hn_tensor *y, int32_t accumulate, void *stream);
 /* MaxPool2d(3,2,1) forward that also records the winning tap (uint8 [N][Ho][Wo][C]) and its backward */

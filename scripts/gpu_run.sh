@@ -1,4 +1,2 @@
-set -x
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -c 600 gpurun_out/bench_n2.json; tail -3 gpurun_out/bench_n2.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --workload train_seg --height 320 --width 640 --batch 16 --steps 5 --warmup 3 > gpurun_out/train_seg_n2.json 2> gpurun_out/train_seg_n2.err; tail -c 500 gpurun_out/train_seg_n2.json; tail -3 gpurun_out/train_seg_n2.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/ref_n2.json 2> gpurun_out/ref_n2.err; tail -c 400 gpurun_out/ref_n2.json
+timeout 900 python -m pytest tests/test_gpu_backward.py tests/test_gpu_training.py -m gpu -q 2>&1 | grep -E "^E  |passed|failed|^FAILED" | cut -c1-250 | head -30
+python bench.py --workload train_seg --height 320 --width 640 --batch 16 --steps 5 --warmup 3 > gpurun_out/train_seg11.json 2> gpurun_out/train_seg11.err; tail -c 400 gpurun_out/train_seg11.json

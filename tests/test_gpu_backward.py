@@ -152,6 +152,17 @@ def test_bn_train_backward(E, dtype, tol, act):
     assert rel(pg[0].cpu(), beta.grad) < tol and rel(pg[1].cpu(), gamma.grad) < tol
     if res is not None:
         assert rel(back(dres), res.grad) < tol
+    if res is None:
+        # without a residual the saved output need not be read: z is recomputed from raw with the forward's scale / shift
+        fscale = (gamma.detach() * invstd).cuda()
+        fshift = (beta.detach() - mean * gamma.detach() * invstd).cuda()
+        draw2, pg2 = E.bn_bwd(to_act(E, dout, dtype), to_act(E, out.detach(), dtype), to_act(E, raw.detach(), torch.float32), mean.cuda(),
+                              invstd.cuda(), gamma.detach().cuda(), code, slope_ptr=slope.detach().cuda() if act == "prelu" else None,
+                              want_prelu_grad=(act == "prelu"), fwd_scale=fscale, fwd_shift=fshift)
+        assert rel(back(draw2), raw.grad) < tol
+        assert rel(pg2[0].cpu(), beta.grad) < tol and rel(pg2[1].cpu(), gamma.grad) < tol
+        if act == "prelu":
+            assert abs(pg2[2].item() - slope.grad.item()) < tol * max(1.0, abs(slope.grad.item())) * 5
     if act == "prelu":
         assert abs(pg[2].item() - slope.grad.item()) < tol * max(1.0, abs(slope.grad.item())) * 5
 
