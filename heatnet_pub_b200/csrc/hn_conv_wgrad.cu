@@ -27,9 +27,12 @@ struct WgParams {
     int tiles_w, tiles_h, n_img;    // pixel patches: n_img * tiles_h * tiles_w k-blocks in total
     int TH, TW;                     // TH*TW = 64
     int taps, S, pad, dil;          // taps = R*S (1 in flat mode)
-    int m_tiles, n_tiles;           // Cout / 128 tiles, Ncols / BN tiles
-    int splits;                     // pixel splits per (m, n, tap)
-    int Cout, ncols;                // valid rows / valid columns per tap (Cin, or Kpad in flat mode)
+    int m_tiles;                    // Cout / 128 tiles
+    int cblocks;                    // 64-column blocks per tap (Cin / 64, or Kpad / 64 in flat mode)
+    int blocks_total;               // taps * cblocks: the packed gradient row is blocks_total * 64 columns, block = tap * cblocks + cb
+    int nb_item, n_col_items;       // an item covers nb_item (<= BN / 64) consecutive blocks -- possibly of DIFFERENT taps
+    int splits;                     // pixel splits per (m, column item)
+    int Cout;                       // valid rows
     int kpad;                       // row stride of the packed gradient
     float *dw;                      // [Cout_pad][kpad] FP32, accumulated into
 };
@@ -41,7 +44,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
     constexpr int A_BYTES = 2 * WG_BLOCK_BYTES;              // 128 couts = 2 blocks
     constexpr int B_BYTES = (BN / 64) * WG_BLOCK_BYTES;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr uint32_t IDESC = make_idesc_bf16_mn(WG_M, BN);
     constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -53,7 +55,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = p.n_img * p.tiles_h * p.tiles_w;
-    const int num_items = p.m_tiles * p.n_tiles * p.taps * p.splits;
+    const int num_items = p.m_tiles * p.n_col_items * p.splits;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_dy);
@@ -77,13 +79,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // work item -> (split, tap, nt, mt), split fastest so concurrently running CTAs stream disjoint pixel ranges
-    auto decode = [&](int item, int &mt, int &nt, int &tap, int &kb0, int &kb1) {
+    // work item -> (split, column item, mt), split fastest so concurrently running CTAs stream disjoint pixel ranges.
+    // Column blocks are 64 gradient columns = (tap, 64 input channels).  Because the N index of the MMA only has to be a stack of
+    // 64-wide MN-major blocks LBO bytes apart, ONE MMA can span blocks of different taps: for Cin = 64 a 3x3 filter is 9 blocks
+    // and an item takes 3 of them (N = 192) instead of running 9 separate N = 64 passes at 39 % of the tensor pipe, and the
+    // dY tile is fetched once per 3 taps.
+    auto decode = [&](int item, int &mt, int &blk0, int &nb, int &kb0, int &kb1) {
         const int sp = item % p.splits;
-        int rest = item / p.splits;
-        tap = rest % p.taps; rest /= p.taps;
-        nt = rest % p.n_tiles;
-        mt = rest / p.n_tiles;
+        const int rest = item / p.splits;
+        const int ci = rest % p.n_col_items;
+        mt = rest / p.n_col_items;
+        blk0 = ci * p.nb_item;
+        nb = p.blocks_total - blk0 < p.nb_item ? p.blocks_total - blk0 : p.nb_item;
         const int per = (num_kb + p.splits - 1) / p.splits;
         kb0 = sp * per;
         kb1 = kb0 + per < num_kb ? kb0 + per : num_kb;
@@ -94,24 +101,31 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-                int mt, nt, tap, kb0, kb1;
-                decode(item, mt, nt, tap, kb0, kb1);
-                const int r = tap / p.S, s = tap - r * p.S;
-                const int dx = s * p.dil - p.pad, dyy = r * p.dil - p.pad;
-                const int xcol0 = (p.taps > 1 ? 0 : 0) + nt * BN;      // column offset inside the tap (Cin offset / flat K offset)
+                int mt, blk0, nb, kb0, kb1;
+                decode(item, mt, blk0, nb, kb0, kb1);
+                int bcol[BN / 64], bdx[BN / 64], bdy[BN / 64];      // per block: channel offset and tap shift
+#pragma unroll
+                for (int b = 0; b < BN / 64; ++b) {
+                    const int blk = blk0 + (b < nb ? b : 0);
+                    const int tap = blk / p.cblocks, cb = blk - tap * p.cblocks;
+                    const int r = tap / p.S, sx = tap - r * p.S;
+                    bcol[b] = cb * 64;
+                    bdx[b] = sx * p.dil - p.pad;
+                    bdy[b] = r * p.dil - p.pad;
+                }
                 for (int kb = kb0; kb < kb1; ++kb) {
                     const int tw = kb % p.tiles_w, th = (kb / p.tiles_w) % p.tiles_h, img = kb / (p.tiles_w * p.tiles_h);
                     mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
                     const uint32_t fb = smem_u32(full_bar + stage);
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                     if (elect_one()) {
-                        mbar_expect_tx(fb, STAGE_BYTES);
+                        mbar_expect_tx(fb, (2 + nb) * WG_BLOCK_BYTES);
 #pragma unroll
                         for (int b = 0; b < 2; ++b)
                             tma_load_4d(sa + b * WG_BLOCK_BYTES, &tmap_dy, fb, mt * WG_M + b * 64, tw * p.TW, th * p.TH, img);
 #pragma unroll
                         for (int b = 0; b < BN / 64; ++b)
-                            tma_load_4d(sa + A_BYTES + b * WG_BLOCK_BYTES, &tmap_x, fb, xcol0 + b * 64, tw * p.TW + dx, th * p.TH + dyy, img);
+                            if (b < nb) tma_load_4d(sa + A_BYTES + b * WG_BLOCK_BYTES, &tmap_x, fb, bcol[b], tw * p.TW + bdx[b], th * p.TH + bdy[b], img);
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -123,8 +137,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
             int stage = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-                int mt, nt, tap, kb0, kb1;
-                decode(item, mt, nt, tap, kb0, kb1);
+                int mt, blk0, nb, kb0, kb1;
+                decode(item, mt, blk0, nb, kb0, kb1);
+                const uint32_t idesc = make_idesc_bf16_mn(WG_M, 64 * nb);
                 mbar_wait(smem_u32(tempty_bar), acc_phase ^ 1);
                 tcgen05_fence_after();
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -137,7 +152,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
 #pragma unroll
                         for (int k = 0; k < WG_KPIX / 16; ++k) {
                             // 16 pixel rows = 2048 B further along K: +128 in the (addr >> 4) field
-                            umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+                            umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                         }
                         umma_commit(smem_u32(empty_bar + stage));
                         if (kb == kb1 - 1) umma_commit(smem_u32(tfull_bar));
@@ -154,8 +169,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
         const int q = warp - 4;
         uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-            int mt, nt, tap, kb0, kb1;
-            decode(item, mt, nt, tap, kb0, kb1);
+            int mt, blk0, nb, kb0, kb1;
+            decode(item, mt, blk0, nb, kb0, kb1);
             mbar_wait(smem_u32(tfull_bar), acc_phase);
             tcgen05_fence_after();
             acc_phase ^= 1;
@@ -164,13 +179,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
             // sectors) per warp instruction; instead every 32x32 block goes through a padded shared-memory tile so that one
             // red.global.add.v4.f32 per lane covers 4 rows x 128 contiguous bytes (8x fewer L2 sectors, 4x fewer instructions).
             const uint32_t tbuf = smem_u32(tr_buf + q * (32 * 36));
-            const int64_t colbase = (int64_t)tap * p.ncols + nt * BN;
-            constexpr int CH = BN < 32 ? BN : 32;
+            const int64_t colbase = (int64_t)blk0 * 64;
+            constexpr int CH = 32;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += CH) {
+            for (int c0 = 0; c0 < 64 * nb; c0 += CH) {
                 uint32_t raw[CH];
-                if constexpr (CH == 32) tmem_ld_32x32(taddr + c0, raw);
-                else tmem_ld_32x16(taddr + c0, raw);
+                tmem_ld_32x32(taddr + c0, raw);
                 tmem_ld_wait();
                 if (kb1 <= kb0) continue;                                    // warp-uniform
 #pragma unroll
@@ -183,7 +197,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
                     if (c4 < CH) {
                         const uint4 v = lds128(tbuf + r * 144 + c4 * 4);
                         const int cor = mt * WG_M + q * 32 + r;
-                        if (cor < p.Cout && nt * BN + c0 + c4 < p.ncols) {
+                        if (cor < p.Cout) {
                             float *dst = p.dw + (int64_t)cor * p.kpad + colbase + c0 + c4;
                             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(v.x)),
                                          "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
@@ -216,7 +230,7 @@ static int launch_wgrad(const CUtensorMap &tdy, const CUtensorMap &tx, const WgP
         HN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    const int items = p.m_tiles * p.n_tiles * p.taps * p.splits;
+    const int items = p.m_tiles * p.n_col_items * p.splits;
     int grid = items < num_sms() ? items : num_sms();
     wgrad_tc_kernel<BN, STAGES><<<grid, WG_THREADS, smem, st>>>(tdy, tx, p);
     HN_LAUNCH_CHECK();
@@ -285,11 +299,14 @@ int conv2d_wgrad_tc(const hn_tensor *x, const hn_tensor *dy, const hn_conv *cv, 
         rc = make_tmap(&tx, ws, 4, xd, xs, box);
         if (rc) return rc;
     }
-    p.ncols = ncols;
-    const int bn = ncols % 256 == 0 ? 256 : (ncols % 128 == 0 ? 128 : 64);
-    p.n_tiles = (int)cdiv(ncols, bn);
+    HN_CHECK_ARG(ncols % 64 == 0, "conv_wgrad: column count must be a multiple of 64");
+    p.cblocks = ncols / 64;
+    p.blocks_total = p.taps * p.cblocks;
+    p.n_col_items = (int)cdiv(p.blocks_total, 4);
+    p.nb_item = (int)cdiv(p.blocks_total, p.n_col_items);            // 1..4 blocks (N = 64..256) per item, evenly spread
+    const int bn = p.nb_item >= 3 ? 256 : (p.nb_item == 2 ? 128 : 64);
     const int num_kb = p.n_img * p.tiles_h * p.tiles_w;
-    const int base_items = p.m_tiles * p.n_tiles * p.taps;
+    const int base_items = p.m_tiles * p.n_col_items;
     int splits = (int)cdiv(2 * (int64_t)num_sms(), base_items);
     if (splits > num_kb) splits = num_kb;
     if (splits < 1) splits = 1;
