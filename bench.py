@@ -471,6 +471,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true", help="training workloads: leave the optimizer step out of the timed step")
     ap.add_argument("--torch-losses", action="store_true", help="training workloads: torch criteria instead of the fused loss kernels")
+    ap.add_argument("--cuda-graph", default="auto", choices=["auto", "on", "off"],
+                    help="infer workload: replay the forward as a CUDA graph (PSPNet.set_cuda_graph).  auto = on for launch-bound "
+                         "shapes (at most 8 images of 320x640 per step), off for the headline full-frame batch, which is GPU-bound")
     ap.add_argument("--layer-table", default=None, help="write the per-conv-launch timing table (JSON) here")
     ap.add_argument("--workload", default="infer", choices=["infer", "train_seg", "train_critic", "iou_eval"],
                     help="infer = the headline (BASELINE configs[1]); train_* = one adversarial training step (configs[2]/[3]): "
@@ -508,6 +511,9 @@ def main():
                         pretrained=False, late_fusion=True)
     he_init_(net)
     net = net.to(dev).eval().set_precision(args.precision)
+    use_graph = args.cuda_graph == "on" or (args.cuda_graph == "auto" and B * H * W <= 8 * 320 * 640)
+    if use_graph:
+        net.set_cuda_graph(True)
     rgb_h, ir_h = synthetic_batch(B, H, W, seed=SEED + rank)
     rgb_h, ir_h = rgb_h.pin_memory(), ir_h.pin_memory()
     rgb, ir = rgb_h.to(dev), ir_h.to(dev)
@@ -664,6 +670,7 @@ def main():
                 "config": {"workload": f"PSPNet-ResNet50 RGB+thermal late-fusion forward (eval), batch {B} per GPU, {H}x{W} frames -> "
                                        f"{Hout}x{Wout} logits, random-init weights",
                            "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"image-sharded x{world}, no collective",
+                           "cuda_graph": bool(use_graph),
                            "l2": "inputs and activations (GBs per step) far exceed the 126 MB L2; no explicit flush"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "what": "every step: pinned host FP32 frames -> H2D -> PSPNet forward (public module API) -> device argmax -> D2H uint8 label maps; "

@@ -190,10 +190,70 @@ class PSPNet(_KernelModule):
         if autograd.needs_autograd(self, modal_1, modal_2):
             outs = autograd.apply(self._autograd_runner, [modal_1, modal_2], self)
             return outs[0], list(outs), None
+        if getattr(self, "_graph_enabled", False) and self._graph_ok(modal_1, modal_2):
+            return self._forward_graph(modal_1, modal_2)
+        return self._forward_eager(modal_1, modal_2)
+
+    def _forward_eager(self, modal_1, modal_2=None):
         m1, m2 = self.feats._inputs(modal_1, modal_2)
         logits, f = self._run_full(m1, m2)
         out = logits if torch.is_tensor(logits) else E.to_nchw_f32(logits)      # the reference's NCHW FP32 logits
         return out, [out, f[0].nchw(), f[1].nchw(), f[2].nchw(), f[3].nchw(), f[4].nchw()], None
+
+    # ---- CUDA-graph replay of the inference forward -------------------------------------------------------------------
+    # A forward is ~105 kernel launches issued from Python (~30 us each): below ~10 images of 320x640 per call the step is
+    # launch-bound (3.2 ms whatever the batch; the kernels of a batch-1 forward take ~0.5 ms).  set_cuda_graph(True) captures
+    # the launch sequence once per (input shapes, precision, parameter versions) and replays it; inputs are copied into static
+    # buffers, the logits are returned as a fresh tensor, the feature taps are views of the graph's static buffers (valid
+    # until the next call with the same shapes).  Eval mode, torch.no_grad() only; anything else takes the eager path.
+    def set_cuda_graph(self, enabled: bool = True):
+        self._graph_enabled = bool(enabled)
+        self._graphs = {}
+        return self
+
+    def _graph_ok(self, modal_1, modal_2):
+        if self.training or torch.is_grad_enabled() or E.conv_timer is not None or E.op_timer is not None:
+            return False
+        if any(m.training for m in self.modules() if isinstance(m, (nn.BatchNorm2d, nn.Dropout2d))):
+            return False
+        return modal_1.is_cuda and (modal_2 is None or modal_2.is_cuda)
+
+    def _graph_key(self, modal_1, modal_2):
+        ver = sum(p._version for p in self.parameters()) + sum(b._version for b in self.buffers())
+        return (tuple(modal_1.shape), modal_1.dtype, None if modal_2 is None else (tuple(modal_2.shape), modal_2.dtype),
+                modal_1.device, self.precision or E.DEFAULT_PRECISION, ver, next(self.parameters()).data_ptr())
+
+    def _forward_graph(self, modal_1, modal_2):
+        key = self._graph_key(modal_1, modal_2)
+        entry = self._graphs.get(key)
+        if entry is None:
+            self._graphs.clear()                      # one live graph per module: its pool holds a full set of activations
+            s1 = torch.empty_like(modal_1, memory_format=torch.contiguous_format)
+            s2 = None if modal_2 is None else torch.empty_like(modal_2, memory_format=torch.contiguous_format)
+            s1.copy_(modal_1)
+            if s2 is not None:
+                s2.copy_(modal_2)
+            side = torch.cuda.Stream(device=modal_1.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):             # warm-up: weight packs, folded BN vectors, workspaces, smem attributes
+                for _ in range(2):
+                    self._forward_eager(s1, s2)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(modal_1.device)
+            graph = torch.cuda.CUDAGraph()
+            l0 = E.launch_count
+            with torch.cuda.graph(graph):
+                out = self._forward_eager(s1, s2)
+            entry = (graph, s1, s2, out, E.launch_count - l0)
+            self._graphs[key] = entry
+        graph, s1, s2, out, launches = entry
+        s1.copy_(modal_1)
+        if s2 is not None:
+            s2.copy_(modal_2)
+        graph.replay()
+        E.launch_count += launches
+        logits = out[0].clone()
+        return logits, [logits] + list(out[1][1:]), None
 
     def _autograd_runner(self, tape, inputs):
         """Forward under a tape: -> (input acts, output acts, output tensors) for autograd._NetFunction."""

@@ -1,3 +1,6 @@
-timeout 900 python -m pytest tests/test_gpu_backward.py tests/test_gpu_training.py -m gpu -q 2>&1 | grep -E "^E  |passed|failed|^FAILED" | cut -c1-250 | head -30
-HN_TIMELINE=1 python bench.py --workload train_seg --height 320 --width 640 --batch 16 --steps 5 --warmup 3 --layer-table gpurun_out/train_seg_calls4.json > gpurun_out/train_seg12.json 2> gpurun_out/train_seg12.err
-python bench.py --workload train_seg --height 320 --width 640 --batch 16 --steps 5 --warmup 3 > gpurun_out/train_seg13.json 2> gpurun_out/train_seg13.err; tail -c 300 gpurun_out/train_seg13.json
+timeout 600 python -m pytest tests/test_gpu_network.py -m gpu -q 2>&1 | grep -E "^E  |passed|failed|^FAILED|Error" | cut -c1-300 | head -20
+rm -f gpurun_out/sweep2.jsonl
+for B in 1 2 4 8; do python bench.py --batch $B --height 320 --width 640 --steps 20 --no-cpu-baseline 2>/dev/null | grep '^{' >> gpurun_out/sweep2.jsonl; done
+for B in 1 2; do python bench.py --batch $B --height 650 --width 1920 --steps 20 --no-cpu-baseline --cuda-graph on 2>/dev/null | grep '^{' >> gpurun_out/sweep2.jsonl; done
+python bench.py --steps 10 --no-cpu-baseline --cuda-graph on 2>/dev/null | grep '^{' >> gpurun_out/sweep2.jsonl
+wc -l gpurun_out/sweep2.jsonl

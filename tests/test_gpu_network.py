@@ -197,3 +197,38 @@ def test_grad_mode_is_refused_until_backward_exists():
     except NotImplementedError:
         return
     assert out.requires_grad, "forward under grad mode returned a tensor without a graph"
+
+
+def test_cuda_graph_replay_matches_eager():
+    """PSPNet.set_cuda_graph: the captured launch sequence gives the eager results bit for bit, follows new inputs and
+    re-captures after a parameter update (stale weight packs must not be replayed)."""
+    import torch
+    from heatnet_pub_b200 import pspnet
+    from oracle import heatnet_oracle as O
+    sd = O.recipe_fill(O.pspnet_state_dict(True, 4), seed=3)
+    net = pspnet.PSPNet(sizes=(1, 2, 3, 6), psp_size=2048, deep_features_size=1024, backend='resnet50', in_channels=4,
+                        pretrained=False, late_fusion=True)
+    net.load_state_dict(sd)
+    net = net.cuda().eval().set_precision("bf16")
+    rgb, ir = O.synthetic_inputs(2, 64, 96)
+    rgb, ir = rgb.cuda(), ir.cuda()
+    with torch.no_grad():
+        ref, ref_taps, _ = net(rgb, ir)
+        ref, ref_x5 = ref.clone(), ref_taps[1].clone()
+        net.set_cuda_graph(True)
+        a, taps, _ = net(rgb, ir)                      # capture + first replay
+        assert torch.equal(a, ref) and torch.equal(taps[1], ref_x5)
+        b, _, _ = net(rgb * 0.5, ir)                   # new input through the same graph
+        assert not torch.equal(b, ref)
+        c, _, _ = net(rgb, ir)
+        assert torch.equal(c, ref)
+        net.final[0].bias.add_(1.0)                    # parameter update -> new key -> re-capture
+        d, _, _ = net(rgb, ir)
+        assert torch.allclose(d, ref + 1.0, atol=1e-5)
+        net.set_cuda_graph(False)
+        e, _, _ = net(rgb, ir)
+        assert torch.equal(e, d)
+    # training / grad mode never takes the graph path
+    net.set_cuda_graph(True)
+    net.train()
+    assert not net._graph_ok(rgb, ir)
