@@ -610,6 +610,58 @@ def main():
     h2d = rgb_h.numel() * 4 + ir_h.numel() * 4
     d2h = labels_h.numel()
 
+    # ---- the same serving loop fed with RAW camera frames: uint8 RGB (N,H,W,3) + uint16 IR (N,H,W) in pinned host memory,
+    # normalised on the device by heatnet_pub_b200.inputs (the loaders' arithmetic, cm/thermal_loader.py:649-659,715-728)
+    from heatnet_pub_b200 import inputs as hn_inputs
+    gq = torch.Generator().manual_seed(SEED + rank)
+    rgb8_h = torch.randint(0, 256, (B, H, W, 3), generator=gq, dtype=torch.uint8).pin_memory()
+    ir16_h = torch.randint(21000, 26000, (B, H, W), generator=gq, dtype=torch.int32).to(torch.int16).pin_memory()   # counts < 2^15: int16 == uint16 bits
+    raw_bufs = [{"rgb": torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev), "ir": torch.empty((B, H, W), dtype=torch.int16, device=dev),
+                 "labels": torch.empty((B, Hout, Wout), dtype=torch.uint8, device=dev),
+                 "in_ready": torch.cuda.Event(), "out_ready": torch.cuda.Event(), "consumed": torch.cuda.Event()} for _ in range(2)]
+
+    def raw_stage_in(b):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(b["consumed"])
+            b["rgb"].copy_(rgb8_h, non_blocking=True)
+            b["ir"].copy_(ir16_h, non_blocking=True)
+            b["in_ready"].record(copy_stream)
+
+    def raw_compute(b):
+        main_stream.wait_event(b["in_ready"])
+        with torch.no_grad():
+            logits, _, _ = net(hn_inputs.prepare_rgb(b["rgb"], precision=args.precision), hn_inputs.prepare_ir(b["ir"], precision=args.precision))
+        _lib.check(lib.hn_argmax_labels(logits.data_ptr(), B, Hout * Wout, logits.shape[1], b["labels"].data_ptr(), None,
+                                        C.c_void_p(main_stream.cuda_stream)))
+        b["consumed"].record(main_stream)
+        b["out_ready"].record(main_stream)
+
+    def raw_run(nsteps):
+        for b in raw_bufs:
+            b["consumed"].record(main_stream)
+        raw_stage_in(raw_bufs[0])
+        for i in range(nsteps):
+            cur = raw_bufs[i & 1]
+            if i + 1 < nsteps:
+                raw_stage_in(raw_bufs[(i + 1) & 1])
+            raw_compute(cur)
+            stage_out(cur)
+        main_stream.wait_stream(copy_stream)
+
+    raw_run(2)
+    barrier()
+    ev0.record()
+    raw_run(args.steps)
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_raw = {"value": world * B * args.steps / (t.item() / 1000.0), "unit": UNIT, "h2d_bytes_per_step": rgb8_h.numel() + 2 * ir16_h.numel(),
+               "d2h_bytes_per_step": d2h, "what": "same loop from raw frames: pinned uint8 RGB + uint16 IR -> H2D -> device normalisation "
+               "(heatnet_pub_b200.inputs, zero-copy into the stems) -> forward -> argmax -> D2H uint8 label maps"}
+    del raw_bufs
+
     # ---- roofline of the dominant kernel: events around every conv launch, separate instrumented pass
     roofline = None
     if rank == 0:
@@ -672,6 +724,7 @@ def main():
                            "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"image-sharded x{world}, no collective",
                            "cuda_graph": bool(use_graph),
                            "l2": "inputs and activations (GBs per step) far exceed the 126 MB L2; no explicit flush"},
+                "e2e_raw_frames": e2e_raw,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "what": "every step: pinned host FP32 frames -> H2D -> PSPNet forward (public module API) -> device argmax -> D2H uint8 label maps; "
                                 "copies run on a second stream and overlap the neighbouring steps' compute (double-buffered)"},

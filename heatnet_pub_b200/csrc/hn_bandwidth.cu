@@ -186,7 +186,20 @@ __global__ void channel_stats_kernel(const T *__restrict__ x, int64_t npix, int 
     const int64_t p_begin = (int64_t)blockIdx.x * pix_per_cta;
     const int64_t p_end = min(p_begin + pix_per_cta, npix);
     if (cv < ncv) {
-        for (int64_t p = p_begin + threadIdx.y; p < p_end; p += PL) {
+        int64_t p = p_begin + threadIdx.y;
+        for (; p + 3 * PL < p_end; p += 4 * PL) {          // four pixels (up to 128 B per thread) in flight
+            float v[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) Vec8<T>::load(x + (p + u * PL) * ld + cv * 8, v[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    s[i] += v[u][i];
+                    q[i] = fmaf(v[u][i], v[u][i], q[i]);
+                }
+        }
+        for (; p < p_end; p += PL) {
             float v[8];
             Vec8<T>::load(x + p * ld + cv * 8, v);
 #pragma unroll
@@ -228,6 +241,53 @@ __global__ void channel_stats_kernel(const T *__restrict__ x, int64_t npix, int 
             for (int c = tid; c < C; c += CVB * PL) bn_finalize_channel(c, __ldcg(sum + c), __ldcg(sqsum + c), fin);
             if (tid == 0 && fin.num_batches_tracked) *fin.num_batches_tracked += 1;
         }
+    }
+}
+
+// Thread-fixed-channel variant of the normalise pass (per-channel scale AND shift, not per image): blockDim = (CVB, PL) as in
+// channel_stats_kernel; a thread keeps one 8-channel group, so scale / shift live in registers and the pixel loop only
+// streams x (+ residual) in and y out, two pixels in flight.  Same fmaf(x, scale, shift) + residual + activation expression.
+template <typename TI, typename T>
+__global__ void __launch_bounds__(256) affine_act_fixed_kernel(const TI *__restrict__ x, int ldx, const float *__restrict__ scale,
+                                                               const float *__restrict__ shift, const T *__restrict__ res, int ldr, int act,
+                                                               float slope, const float *slope_ptr, T *__restrict__ y, int ldy, int64_t npix,
+                                                               int C, int64_t pix_per_cta)
+{
+    const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+    if (cv >= C / 8) return;
+    const int PL = blockDim.y, c = cv * 8;
+    if (slope_ptr) slope = __ldg(slope_ptr);
+    float sc[8], sh[8];
+    Vec8<float>::load(scale + c, sc);
+    Vec8<float>::load(shift + c, sh);
+    const int64_t p_begin = (int64_t)blockIdx.x * pix_per_cta;
+    const int64_t p_end = min(p_begin + pix_per_cta, npix);
+    auto one = [&](int64_t p, float (&v)[8], const float (&r)[8]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v[j] = fmaf(v[j], sc[j], sh[j]);
+            if (res) v[j] += r[j];
+            v[j] = apply_act(v[j], act, slope);
+        }
+        Vec8<T>::store(y + p * ldy + c, v);
+    };
+    int64_t p = p_begin + threadIdx.y;
+    for (; p + PL < p_end; p += 2 * PL) {
+        float v0[8], v1[8], r0[8], r1[8];
+        Vec8<TI>::load(x + p * ldx + c, v0);
+        Vec8<TI>::load(x + (p + PL) * ldx + c, v1);
+        if (res) {
+            Vec8<T>::load(res + p * ldr + c, r0);
+            Vec8<T>::load(res + (p + PL) * ldr + c, r1);
+        }
+        one(p, v0, r0);
+        one(p + PL, v1, r1);
+    }
+    if (p < p_end) {
+        float v0[8], r0[8];
+        Vec8<TI>::load(x + p * ldx + c, v0);
+        if (res) Vec8<T>::load(res + p * ldr + c, r0);
+        one(p, v0, r0);
     }
 }
 
@@ -973,9 +1033,31 @@ extern "C" int hn_affine_act(const hn_tensor *x, const hn_epilogue *ep, const hn
     const int64_t npix = (int64_t)x->n * x->h * x->w;
     const int64_t ppi = ep->per_image ? (int64_t)x->h * x->w : 0;
     if (npix == 0) return HN_OK;
-    int grid = wave_grid(cdiv(npix, 64) * 256, 256, 16);
     cudaStream_t st = (cudaStream_t)stream;
     using bf16 = __nv_bfloat16;
+    if (ep->scale && ep->shift && !ep->per_image && npix >= 4096) {      // the BatchNorm2d normalise pass: thread-fixed channels
+        const int ncv = x->c / 8;
+        const int CVB = ncv < 32 ? ncv : 32;
+        const int PL = 256 / CVB;
+        const int cvblocks = (int)cdiv(ncv, CVB);
+        int64_t chunks = cdiv((int64_t)num_sms() * 8, cvblocks);
+        int64_t pix_per_cta = cdiv(npix, chunks);
+        if (pix_per_cta < (int64_t)PL * 4) pix_per_cta = (int64_t)PL * 4;
+        chunks = cdiv(npix, pix_per_cta);
+        dim3 g((unsigned)chunks, (unsigned)cvblocks), b(CVB, PL);
+        if (y->dtype == HN_BF16 && x->dtype == HN_BF16)
+            affine_act_fixed_kernel<bf16, bf16><<<g, b, 0, st>>>((const bf16 *)x->ptr, x->ld, ep->scale, ep->shift, (const bf16 *)ep->residual,
+                                                                 ep->residual_ld, ep->act, ep->slope, ep->slope_ptr, (bf16 *)y->ptr, y->ld, npix, x->c, pix_per_cta);
+        else if (y->dtype == HN_BF16)
+            affine_act_fixed_kernel<float, bf16><<<g, b, 0, st>>>((const float *)x->ptr, x->ld, ep->scale, ep->shift, (const bf16 *)ep->residual,
+                                                                  ep->residual_ld, ep->act, ep->slope, ep->slope_ptr, (bf16 *)y->ptr, y->ld, npix, x->c, pix_per_cta);
+        else
+            affine_act_fixed_kernel<float, float><<<g, b, 0, st>>>((const float *)x->ptr, x->ld, ep->scale, ep->shift, (const float *)ep->residual,
+                                                                   ep->residual_ld, ep->act, ep->slope, ep->slope_ptr, (float *)y->ptr, y->ld, npix, x->c, pix_per_cta);
+        HN_LAUNCH_CHECK();
+        return HN_OK;
+    }
+    int grid = wave_grid(cdiv(npix, 64) * 256, 256, 16);
     if (y->dtype == HN_BF16 && x->dtype == HN_BF16)
         affine_act_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16 *)x->ptr, x->ld, ep->scale, ep->shift, (const bf16 *)ep->residual,
                                                           ep->residual_ld, ep->act, ep->slope, ep->slope_ptr, (bf16 *)y->ptr, y->ld, npix,

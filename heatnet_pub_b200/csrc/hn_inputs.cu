@@ -1,0 +1,113 @@
+// Device-side input pipeline of the HeatNet loaders (cm/thermal_loader.py:649-659, 715-728; cm/train_trgb_segnet_conf.py:82-86):
+// the per-pixel arithmetic the reference runs on the CPU in numpy / torchvision before the H2D copy, done after it instead --
+// the host ships uint8 RGB and uint16 IR frames (5 bytes per pixel instead of 16 for FP32 NCHW) and one bandwidth-bound kernel
+// per modality writes the normalised NHWC activation the stems consume.
+#include "hn_common.cuh"
+
+namespace hn {
+
+// Both normalisations are pure functions of a small integer (a byte; a clipped 16-bit count), so the host evaluates them ONCE with
+// the reference's own arithmetic -- torch FP32 for F.to_tensor / F.normalize, numpy FP64 for the IR range scaling -- into lookup
+// tables and the kernels only gather: results are bit-identical to the reference's CPU path by construction.
+// RGB: lut[c][v] = ((v / 255) - mean[c]) / std[c], cm/thermal_loader.py:715-722
+template <typename T>
+__global__ void __launch_bounds__(256) prepare_rgb_kernel(const uint8_t *__restrict__ src, int64_t npix, const float *__restrict__ lut,
+                                                          T *__restrict__ dst, int ld)
+{
+    __shared__ float s_lut[3 * 256];
+    for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) s_lut[i] = lut[i];
+    __syncthreads();
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+        const uint8_t *s = src + p * 3;
+        T *d = dst + p * ld;
+        d[0] = from_f32<T>(s_lut[s[0]]);
+        d[1] = from_f32<T>(s_lut[256 + s[1]]);
+        d[2] = from_f32<T>(s_lut[512 + s[2]]);
+    }
+}
+
+// IR: lut[k] = (((clip(x) - minval) / (maxval - minval)) - mean) / std for k = clip(x) - minval, cm/thermal_loader.py:649-659,724-725
+template <typename TS, typename T>
+__global__ void __launch_bounds__(256) prepare_ir_kernel(const TS *__restrict__ src, int64_t npix, int minval, int maxval,
+                                                         const float *__restrict__ lut, T *__restrict__ dst, int ld)
+{
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+        int v = (int)src[p];
+        v = v < minval ? minval : (v > maxval ? maxval : v);
+        dst[p * ld] = from_f32<T>(__ldg(lut + (v - minval)));
+    }
+}
+
+// rectDropTensor: tensor[i, :, r0:r0+dh, c0:c0+dw] = 0 with Python slice clamping (cm/train_trgb_segnet_conf.py:82-86)
+template <typename T>
+__global__ void __launch_bounds__(256) rect_drop_kernel(T *__restrict__ x, int ld, int C, int H, int W, const int *__restrict__ params)
+{
+    const int n = blockIdx.y;
+    int r0 = params[n * 4 + 0], c0 = params[n * 4 + 1], r1 = r0 + params[n * 4 + 2], c1 = c0 + params[n * 4 + 3];
+    // Python slicing: negative indices count from the end, then clamp to [0, size]
+    auto norm = [](int i, int size) { if (i < 0) i += size; return i < 0 ? 0 : (i > size ? size : i); };
+    r0 = norm(r0, H); r1 = norm(r1, H); c0 = norm(c0, W); c1 = norm(c1, W);
+    const int dh = r1 - r0, dw = c1 - c0;
+    if (dh <= 0 || dw <= 0) return;
+    const int64_t total = (int64_t)dh * dw * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int64_t q = i / C;
+        const int col = c0 + (int)(q % dw), row = r0 + (int)(q / dw);
+        x[(((int64_t)n * H + row) * W + col) * ld + c] = from_f32<T>(0.f);
+    }
+}
+
+}  // namespace hn
+
+using namespace hn;
+
+static int grid_for(int64_t n) { int64_t g = cdiv(n, 256); int64_t cap = (int64_t)num_sms() * 16; return (int)(g < cap ? (g > 0 ? g : 1) : cap); }
+
+extern "C" int hn_prepare_rgb_u8(const uint8_t *rgb_nhwc, const float *lut_3x256, const hn_tensor *dst, void *stream)
+{
+    HN_CHECK_ARG(rgb_nhwc && lut_3x256 && dst && dst->ptr, "hn_prepare_rgb_u8: null pointer");
+    HN_CHECK_ARG(dst->c == 3 && dst->ld >= 3, "hn_prepare_rgb_u8: destination must be a 3-channel NHWC view");
+    const int64_t npix = (int64_t)dst->n * dst->h * dst->w;
+    if (npix == 0) return HN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dst->dtype == HN_BF16)
+        prepare_rgb_kernel<__nv_bfloat16><<<grid_for(npix), 256, 0, st>>>(rgb_nhwc, npix, lut_3x256, (__nv_bfloat16 *)dst->ptr, dst->ld);
+    else
+        prepare_rgb_kernel<float><<<grid_for(npix), 256, 0, st>>>(rgb_nhwc, npix, lut_3x256, (float *)dst->ptr, dst->ld);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_prepare_ir(const void *ir_nhw, int32_t src_bits, int32_t minval, int32_t maxval, const float *lut, const hn_tensor *dst,
+                             void *stream)
+{
+    HN_CHECK_ARG(ir_nhw && lut && dst && dst->ptr, "hn_prepare_ir: null pointer");
+    HN_CHECK_ARG(src_bits == 16 || src_bits == 32, "hn_prepare_ir: source must be uint16 or int32 (src_bits = 16 / 32)");
+    HN_CHECK_ARG(dst->c == 1 && dst->ld >= 1 && maxval > minval, "hn_prepare_ir: 1-channel destination, maxval > minval");
+    const int64_t npix = (int64_t)dst->n * dst->h * dst->w;
+    if (npix == 0) return HN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = grid_for(npix);
+#define HN_IR(TS, T) prepare_ir_kernel<TS, T><<<g, 256, 0, st>>>((const TS *)ir_nhw, npix, minval, maxval, lut, (T *)dst->ptr, dst->ld)
+    if (src_bits == 16 && dst->dtype == HN_BF16) HN_IR(uint16_t, __nv_bfloat16);
+    else if (src_bits == 16) HN_IR(uint16_t, float);
+    else if (dst->dtype == HN_BF16) HN_IR(int32_t, __nv_bfloat16);
+    else HN_IR(int32_t, float);
+#undef HN_IR
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_rect_drop(const hn_tensor *x, const int32_t *params_dev, void *stream)
+{
+    HN_CHECK_ARG(x && x->ptr && params_dev, "hn_rect_drop: null pointer");
+    if ((int64_t)x->n * x->h * x->w == 0) return HN_OK;
+    HN_CHECK_ARG(x->n <= 65535, "hn_rect_drop: batch too large");
+    dim3 grid((unsigned)grid_for((int64_t)x->h * x->w * x->c), (unsigned)x->n);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x->dtype == HN_BF16) rect_drop_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16 *)x->ptr, x->ld, x->c, x->h, x->w, params_dev);
+    else rect_drop_kernel<float><<<grid, 256, 0, st>>>((float *)x->ptr, x->ld, x->c, x->h, x->w, params_dev);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}

@@ -163,6 +163,17 @@ int hn_bn_batch_stats(const hn_tensor *x, void *scratch, const float *gamma, con
                       float *running_mean, float *running_var, int64_t *num_batches_tracked, float *scale, float *shift,
                       float *save_mean, float *save_invstd, void *stream);
 
+/* ---- input pipeline (cm/thermal_loader.py:649-659,715-728; cm/train_trgb_segnet_conf.py:82-86): the loaders' per-pixel
+ * normalisation after the H2D copy instead of before it.  Both functions gather from host-built lookup tables (the reference's
+ * own arithmetic evaluated once per possible input value), so the outputs are bit-identical to the CPU path.
+ * rgb_nhwc: uint8 [N][H][W][3]; lut_3x256: device float [3][256] = ((v / 255) - mean[c]) / std[c]; dst: 3-channel NHWC view. */
+int hn_prepare_rgb_u8(const uint8_t *rgb_nhwc, const float *lut_3x256, const hn_tensor *dst, void *stream);
+/* ir_nhw: uint16 (src_bits 16) or int32 (src_bits 32) [N][H][W]; values are clipped to [minval, maxval];
+ * lut: device float [maxval - minval + 1] = (((k / (maxval - minval)) - mean) / std); dst: 1-channel NHWC view. */
+int hn_prepare_ir(const void *ir_nhw, int32_t src_bits, int32_t minval, int32_t maxval, const float *lut, const hn_tensor *dst, void *stream);
+/* rectDropTensor: x[n, :, r0:r0+dh, c0:c0+dw] = 0, params_dev int32 [N][4] = (r0, c0, dh, dw), Python slice clamping. */
+int hn_rect_drop(const hn_tensor *x, const int32_t *params_dev, void *stream);
+
 /* ---- backward (autograd of the ops above; the reference gets these from torch.autograd / cuDNN) ---- */
 /* dz = dout * act'(out), the derivative taken through the saved output (conv + bias + activation layers) */
 int hn_act_bwd(const hn_tensor *dout, const hn_tensor *out, int32_t act, float slope, const hn_tensor *dz, void *stream);

@@ -201,3 +201,23 @@ def test_conf_segnet_training_step_matches_reference_golden(golden_dir):
         assert names == live
         gn = np.array([sd[k].grad.double().norm().item() for k in live])
         np.testing.assert_allclose(gn, g[phase + "/grad_norm"], rtol=2e-3, atol=1e-7)
+
+
+def test_inputs_oracle_matches_torchvision():
+    """oracle/inputs_oracle.py restates F.to_tensor / F.normalize; check it against torchvision itself (cm/thermal_loader.py:715-728)."""
+    import numpy as np
+    import torch
+    tvf = pytest.importorskip("torchvision.transforms.functional")
+    from oracle import inputs_oracle as IO
+    rng = np.random.RandomState(0)
+    rgb = rng.randint(0, 256, (37, 53, 3)).astype(np.uint8)
+    want = tvf.normalize(tvf.to_tensor(rgb), mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5))
+    assert torch.equal(IO.load_rgb(rgb), want)
+    ir = rng.randint(20000, 27000, (37, 53)).astype(np.uint16)
+    x = ir.astype(np.int64)
+    x[x < 21800] = 21800
+    x[x > 25000] = 25000
+    x = (x - 21800) / (25000 - 21800)
+    want_ir = tvf.normalize(tvf.to_tensor(x), mean=[0.5], std=[0.5]).float()
+    assert torch.equal(IO.load_ir(ir), want_ir)
+    assert want_ir.min() == -1.0 and want_ir.max() == 1.0
