@@ -27,8 +27,18 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly ONE JSON line: NCCL's own banner / debug output ("NCCL version ...") goes to stderr
+# stdout carries exactly ONE JSON line.  Libraries print to fd 1 behind Python's back (NCCL's "NCCL version ..." banner is a raw
+# printf), so fd 1 is pointed at stderr for the whole run and the result line is written to a private duplicate of the real stdout.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+sys.stdout.flush()
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
 
 METRIC = "rgb_thermal_seg_images_per_sec"
 UNIT = "images/s"
@@ -221,7 +231,7 @@ def run_reference(args):
             "config": {"workload": f"PSPNet-ResNet50 RGB+thermal late-fusion forward, {h}x{w}, 1 frame per step on CPU"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------- training step
@@ -348,7 +358,7 @@ def run_train(args):
                              "unit": "TFLOP/s", "frac": tflops / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
                              "note": "whole step (all kernels, not only convs) against algorithmic conv FLOPs of SURVEY.md section 8d",
                              "peak_source": peak_src}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -452,7 +462,7 @@ def run_iou_eval(args):
                 "roofline": {"kernel": "confusion_labels_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                              "traffic": None, "kernel_ms": kms, "algorithmic_bytes_per_pixel": 16, "peak_source": peak_src},
                 "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -729,7 +739,7 @@ def main():
                         "what": "every step: pinned host FP32 frames -> H2D -> PSPNet forward (public module API) -> device argmax -> D2H uint8 label maps; "
                                 "copies run on a second stream and overlap the neighbouring steps' compute (double-buffered)"},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
