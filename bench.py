@@ -180,8 +180,9 @@ def load_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arms
-def cpu_forward_images_per_sec(h, w, images, threads=None):
-    """The oracle (= the reference's own torch CPU FP32 arithmetic) on `images` frames of h x w, one at a time."""
+def cpu_forward_images_per_sec(h, w, images, threads=None, keep=None):
+    """The oracle (= the reference's own torch CPU FP32 arithmetic) on `images` frames of h x w, one at a time.
+    `keep` (a dict) receives the weights, the input frame and the oracle's logits for the parity check of the same run."""
     import torch
     from oracle import heatnet_oracle as O
     if threads:
@@ -191,8 +192,10 @@ def cpu_forward_images_per_sec(h, w, images, threads=None):
     with torch.no_grad():
         t0 = time.perf_counter()
         for _ in range(images):
-            O.pspnet_forward(sd, rgb, ir, late_fusion=True, training=False)
+            out = O.pspnet_forward(sd, rgb, ir, late_fusion=True, training=False)
         dt = time.perf_counter() - t0
+    if keep is not None:
+        keep.update(sd=sd, rgb=rgb, ir=ir, logits=out[0])
     return images / dt, torch.get_num_threads()
 
 
@@ -717,11 +720,26 @@ def main():
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            v, cores = cpu_forward_images_per_sec(H, W, images=2, threads=os.cpu_count())
+            keep = {}
+            v, cores = cpu_forward_images_per_sec(H, W, images=2, threads=os.cpu_count(), keep=keep)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"2 frames of {H}x{W} through oracle.pspnet_forward (torch CPU FP32, the reference's arithmetic), one frame per call"}
+            # parity of THIS build on the frame the oracle just computed (BASELINE metric: "argmax agree"): same weights, same input
+            net2 = pspnet.PSPNet(sizes=(1, 2, 3, 6), psp_size=2048, deep_features_size=1024, backend='resnet50', in_channels=4,
+                                 pretrained=False, late_fusion=True)
+            net2.load_state_dict(keep["sd"])
+            net2 = net2.to(dev).eval().set_precision(args.precision)
+            with torch.no_grad():
+                got = net2(keep["rgb"].to(dev), keep["ir"].to(dev))[0].cpu()
+            ref = keep["logits"]
+            parity = {"vs": "oracle (torch CPU FP32) on the same weights and frame", "frames": f"1 x {H}x{W}",
+                      "logits_rel_err": float((got - ref).abs().max() / ref.abs().max()),
+                      "argmax_agreement": float((got.argmax(1) == ref.argmax(1)).float().mean()),
+                      "tolerance": 2e-2 if args.precision == "bf16" else 1e-4}
+            del net2, got, keep
         except Exception as e:                                   # the baseline is reported, never required
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
 
@@ -738,7 +756,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "what": "every step: pinned host FP32 frames -> H2D -> PSPNet forward (public module API) -> device argmax -> D2H uint8 label maps; "
                                 "copies run on a second stream and overlap the neighbouring steps' compute (double-buffered)"},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

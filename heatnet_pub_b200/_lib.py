@@ -58,6 +58,7 @@ SIGNATURES = {
     "hn_affine_act": (C.c_int, [_T, _E, _T, _P]),
     "hn_channel_stats": (C.c_int, [_T, _P, _P, _P]),
     "hn_bn_finalize": (C.c_int, [_P, _P, _I64, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _I32, _P]),
+    "hn_bn_finalize_tracked": (C.c_int, [_P, _P, _I64, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _I32, _P]),
     "hn_act_bwd": (C.c_int, [_T, _T, _I32, _F, _T, _P]),
     "hn_bn_bwd": (C.c_int, [_T, _T, _T, _P, _P, _P, _I32, _F, _P, _P, _T, _T, _I32, _I32, _P, _P, _P, _I32, _P, _P, _P]),
     "hn_stem_pad_slack_bytes": (_I64, []),

@@ -63,7 +63,14 @@ extern "C" int hn_conv2d_fwd(const hn_tensor *x, const void *w_packed, const hn_
     HN_CHECK_ARG(y->n == x->n && y->h == Ho && y->w == Wo && y->c == cv->cout, "hn_conv2d_fwd: output view must be N=%d %dx%d C=%d", x->n,
                  Ho, Wo, cv->cout);
     // y = act(acc * scale + shift + residual): either vector may be absent (scale: 1, shift: 0)
-    HN_CHECK_ARG(!ep->out_nchw && !ep->stat_sum && !ep->stat_sqsum, "hn_conv2d_fwd: out_nchw / fused statistics are not implemented yet");
+    HN_CHECK_ARG(!ep->out_nchw, "hn_conv2d_fwd: out_nchw is not implemented (see hn_conv3x3_head_fwd for NCHW logits)");
+    HN_CHECK_ARG((ep->stat_sum != nullptr) == (ep->stat_sqsum != nullptr), "hn_conv2d_fwd: give both statistics accumulators or neither");
+    if (ep->stat_sum) {
+        const int cp = hn_conv_cout_pad(cv->cout, x->dtype);
+        HN_CHECK_ARG(x->dtype == HN_BF16 && y->dtype == HN_F32 && cp >= 32 && (reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0 && (y->ld * 4) % 16 == 0 &&
+                         !ep->residual && ep->act == HN_ACT_NONE,
+                     "hn_conv2d_fwd: fused statistics need the BF16 engine, an aligned FP32 output view, Cout >= 17, no residual / activation");
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (x->dtype == HN_F32) {
         HN_CHECK_ARG(y->dtype == HN_F32, "hn_conv2d_fwd: FP32 path writes FP32");

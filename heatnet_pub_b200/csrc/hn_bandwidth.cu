@@ -322,9 +322,10 @@ __global__ void __launch_bounds__(256) channel_stats_scalar_kernel(const T *__re
 
 __global__ void bn_finalize_kernel(const double *sum, const double *sqsum, double count, const float *gamma, const float *beta,
                                    float eps, float momentum, float *running_mean, float *running_var, float *scale, float *shift,
-                                   float *save_mean, float *save_invstd, int C)
+                                   float *save_mean, float *save_invstd, int C, long long *num_batches_tracked = nullptr)
 {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
     if (c >= C) return;
     double mean = sum[c] / count;
     double var = sqsum[c] / count - mean * mean;
@@ -952,6 +953,18 @@ extern "C" int hn_channel_stats(const hn_tensor *x, double *sum, double *sqsum, 
     return HN_OK;
 }
 
+extern "C" int hn_bn_finalize_tracked(const double *sum, const double *sqsum, int64_t count, const float *gamma, const float *beta, float eps,
+                                      float momentum, float *running_mean, float *running_var, int64_t *num_batches_tracked, float *scale,
+                                      float *shift, float *save_mean, float *save_invstd, int32_t c, void *stream)
+{
+    HN_CHECK_ARG(sum && sqsum && scale && shift && c > 0 && count > 0, "hn_bn_finalize_tracked: bad arguments");
+    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sqsum, (double)count, gamma, beta, eps, momentum,
+                                                                         running_mean, running_var, scale, shift, save_mean,
+                                                                         save_invstd, c, reinterpret_cast<long long *>(num_batches_tracked));
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
 extern "C" int64_t hn_bn_batch_stats_scratch_bytes(int32_t c) { return (int64_t)sizeof(double) * (2 * (int64_t)c + 1); }
 
 extern "C" int hn_bn_batch_stats(const hn_tensor *x, void *scratch, const float *gamma, const float *beta, float eps, float momentum,
@@ -1268,6 +1281,9 @@ extern "C" int hn_pack_stem_weight(const float *w_oihw, const float *row_scale, 
 extern "C" int hn_stem7x7s2_fwd(const hn_tensor *xpad, const void *w_packed, int32_t cout, const hn_epilogue *ep, const hn_tensor *y, void *stream)
 {
     HN_CHECK_ARG(xpad && w_packed && ep && y && xpad->ptr && y->ptr, "hn_stem7x7s2_fwd: null pointer");
+    HN_CHECK_ARG(!ep->stat_sum || (ep->stat_sqsum && y->dtype == HN_F32 && !ep->residual && ep->act == HN_ACT_NONE &&
+                                   (reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0 && (y->ld * 4) % 16 == 0),
+                 "hn_stem7x7s2_fwd: fused statistics need an aligned FP32 output view, no activation");
     HN_CHECK_ARG(y->n == xpad->n && y->c == cout, "hn_stem7x7s2_fwd: output view mismatch");
     // default: the dense-row kernel (hn_conv_stem.cu; needs hn_stem_pad_slack_bytes() readable bytes behind the image);
     // HN_STEM_WINDOW_TMA=1 selects the overlapping-window tensor-map variant (hn_conv_tc.cu)

@@ -37,6 +37,9 @@ struct TcParams {
     // TMA epilogue: output (and residual) go through a swizzled shared-memory staging tile per epilogue warp
     int tma_out, tma_res;
     int ebw;                       // staging box = {128 B of channels, ebw pixels, 32/ebw rows, 1}: ebw = min(TW, 32)
+    // train-mode BatchNorm2d statistics fused into the FP32-output epilogue: per-channel sum / sum of squares of the STORED
+    // pre-normalisation values over the valid pixels, FP32 per 32-row block, FP64 atomics into [Cout] accumulators
+    double *stat_sum, *stat_sqsum;
     // fused 1x1 classifier head (halo kernel, BLOCK_N = 64 = Cout): logits written as NCHW FP32, the activation is not stored
     float *head_out;               // [n_img][head_n][Ho][Wo]
     int head_n;                    // <= HEAD_MAX; 0 = no head
@@ -153,6 +156,24 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
             named_bar_sync(3, ALT ? 256 : 128);
         }
     }
+    // fused BatchNorm2d statistics (p.stat_sum): per-warp FP32 partial sums of this warp's COLS columns, one per lane and 32-column chunk
+    constexpr int STAT_CHUNKS = COLS >= 32 ? COLS / 32 : 1;
+    float st_s[STAT_CHUNKS], st_q[STAT_CHUNKS];
+#pragma unroll
+    for (int i = 0; i < STAT_CHUNKS; ++i) st_s[i] = st_q[i] = 0.f;
+    int stat_ctile = -1;
+    auto stat_flush = [&]() {
+        if (stat_ctile < 0) return;
+#pragma unroll
+        for (int i = 0; i < STAT_CHUNKS; ++i) {
+            const int ch = stat_ctile + 32 * i + lane;
+            if (ch < p.Cout && (st_s[i] != 0.f || st_q[i] != 0.f)) {
+                atomicAdd(p.stat_sum + ch, (double)st_s[i]);
+                atomicAdd(p.stat_sqsum + ch, (double)st_q[i]);
+            }
+            st_s[i] = st_q[i] = 0.f;
+        }
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         if (ALT && (it & 1) != grp) continue;
@@ -162,6 +183,10 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
         const bool valid = ho < p.Ho && wo < p.Wo;
         const int64_t pix = ((int64_t)img * p.Ho + ho) * p.Wo + wo;
         const int ctile = nt * BLOCK_N + col0;         // first output channel of this warp's columns
+        if (p.stat_sum && ctile != stat_ctile) {
+            stat_flush();
+            stat_ctile = ctile;
+        }
         // coordinates of this warp's 32-pixel box (first pixel = row q*32 of the tile)
         const int bx = tw * p.TW + (q * 32) % p.TW, by = th * p.TH + (q * 32) / p.TW;
         const __nv_bfloat16 *rrow = (const __nv_bfloat16 *)p.res + pix * p.ldr + ctile;
@@ -372,6 +397,35 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
                                                          __float_as_uint(v[4 * j + 3]));
                                     sts128(off[((si * SUB) >> 2) + j], o);
                                 }
+                                if constexpr (SUB == 32) {
+                                    if (p.stat_sum) {
+                                        // the staging tile now holds this warp's 32 pixels x 32 channels in FP32 (16-byte chunks swizzled by
+                                        // row): lane c sums channel c over the VALID rows (ragged tiles hold bias-only garbage beyond the
+                                        // image) into per-warp register accumulators, flushed (FP64 atomics) when the channel tile changes
+                                        __syncwarp();
+                                        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+                                        float cs = 0.f, cq = 0.f;
+                                        if (vmask == 0xffffffffu) {
+#pragma unroll 8
+                                            for (int r = 0; r < 32; ++r) {
+                                                const float x = lds32(stage + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+                                                cs += x;
+                                                cq = fmaf(x, x, cq);
+                                            }
+                                        } else {
+                                            for (int r = 0; r < 32; ++r) {
+                                                if ((vmask >> r) & 1u) {
+                                                    const float x = lds32(stage + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+                                                    cs += x;
+                                                    cq = fmaf(x, x, cq);
+                                                }
+                                            }
+                                        }
+#pragma unroll
+                                        for (int i = 0; i < STAT_CHUNKS; ++i)
+                                            if (i == (ck >> 5)) { st_s[i] += cs; st_q[i] += cq; }
+                                    }
+                                }
                             } else {
 #pragma unroll
                                 for (int j = 0; j < SUB / 8; ++j) {
@@ -428,6 +482,7 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
         if (ALT) acc_phase ^= 1;
         else { acc ^= 1; if (acc == 0) acc_phase ^= 1; }
     }
+    if (p.stat_sum) stat_flush();
     if constexpr (BLOCK_N == 64) {
         if (head && have_prev) head_emit(p, head_d2 + ((uint32_t)(q * 32) << 16), head_bar, hph, prev_img, prev_ho, prev_wo, prev_valid);
     }

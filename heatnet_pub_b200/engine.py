@@ -381,7 +381,7 @@ def packed_stem_weight(conv: torch.nn.Conv2d, bn: Optional[torch.nn.BatchNorm2d]
 
 
 def stem_conv(x: "Act", conv: torch.nn.Conv2d, wp: torch.Tensor, shift, act=ACT_NONE, slope=0.0, slope_ptr=None,
-              out: Optional["Act"] = None, out_dtype=None) -> "Act":
+              out: Optional["Act"] = None, out_dtype=None, stats: Optional[torch.Tensor] = None) -> "Act":
     lib = _lib.load()
     ho, wo = conv_out_hw(x.h, x.w, conv)
     hpad, wpad = 2 * ho + 6, 2 * wo + 6
@@ -389,7 +389,7 @@ def stem_conv(x: "Act", conv: torch.nn.Conv2d, wp: torch.Tensor, shift, act=ACT_
     xpad = Act(flat[:x.n * hpad * wpad * 4].view(x.n, hpad, wpad, 4))         # + readable slack behind the last row (hn_stem_pad_slack_bytes)
     if out is None:
         out = new_act(x.n, ho, wo, conv.out_channels, out_dtype or x.dtype, x.buf.device)
-    ep = _epilogue(None, shift, None, act, slope, slope_ptr)
+    ep = _epilogue(None, shift, None, act, slope, slope_ptr, stats)
     timing = conv_timer is not None
     if timing:
         ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -461,8 +461,11 @@ def conv_out_hw(h, w, conv: torch.nn.Conv2d):
     return (h + 2 * p - d * (k - 1) - 1) // s + 1, (w + 2 * p - d * (k - 1) - 1) // s + 1
 
 
-def _epilogue(scale, shift, residual: Optional[Act], act, slope, slope_ptr) -> HnEpilogue:
+def _epilogue(scale, shift, residual: Optional[Act], act, slope, slope_ptr, stats: Optional[torch.Tensor] = None) -> HnEpilogue:
     ep = HnEpilogue()
+    if stats is not None:        # FP64 [2, C] (or longer, [0:C] / [C:2C] used): per-channel sum / sum of squares accumulators
+        c = stats.numel() // 2 if stats.dim() == 1 else stats.shape[1]
+        ep.stat_sum, ep.stat_sqsum = stats.data_ptr(), stats.data_ptr() + 8 * c
     ep.scale = scale.data_ptr() if scale is not None else None
     ep.shift = shift.data_ptr() if shift is not None else None
     if residual is not None:
@@ -474,7 +477,7 @@ def _epilogue(scale, shift, residual: Optional[Act], act, slope, slope_ptr) -> H
 
 def conv2d_raw(x: Act, wp: torch.Tensor, cout: int, k: int, stride: int, pad: int, dil: int, scale=None, shift=None,
                residual: Optional[Act] = None, act=ACT_NONE, slope=0.0, slope_ptr=None, out: Optional[Act] = None,
-               out_dtype=None, out_hw=None) -> Act:
+               out_dtype=None, out_hw=None, stats: Optional[torch.Tensor] = None) -> Act:
     """One convolution launch on a packed weight matrix (see hn_conv2d_fwd)."""
     lib = _lib.load()
     ho = (x.h + 2 * pad - dil * (k - 1) - 1) // stride + 1
@@ -494,7 +497,7 @@ def conv2d_raw(x: Act, wp: torch.Tensor, cout: int, k: int, stride: int, pad: in
     if ws_bytes:
         ws_ptr = workspace(ws_bytes, x.buf.device).data_ptr()
         _count()
-    ep = _epilogue(scale, shift, residual, act, slope, slope_ptr)
+    ep = _epilogue(scale, shift, residual, act, slope, slope_ptr, stats)
     timing = conv_timer is not None
     if timing:
         ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -509,7 +512,7 @@ def conv2d_raw(x: Act, wp: torch.Tensor, cout: int, k: int, stride: int, pad: in
 
 
 def conv2d(x: Act, conv: torch.nn.Conv2d, scale=None, shift=None, residual: Optional[Act] = None, act=ACT_NONE,
-           slope=0.0, slope_ptr=None, out: Optional[Act] = None, out_dtype=None) -> Act:
+           slope=0.0, slope_ptr=None, out: Optional[Act] = None, out_dtype=None, stats: Optional[torch.Tensor] = None) -> Act:
     """y = act(conv(x) * scale + shift + residual) in one launch (plus an im2col gather for strided /
     small-Cin shapes on the BF16 path)."""
     assert conv.groups == 1 and conv.kernel_size[0] == conv.kernel_size[1] and conv.stride[0] == conv.stride[1]
@@ -517,7 +520,7 @@ def conv2d(x: Act, conv: torch.nn.Conv2d, scale=None, shift=None, residual: Opti
     if x.c != conv.in_channels:
         raise RuntimeError(f"expected input with {conv.in_channels} channels, got {x.c}")
     return conv2d_raw(x, packed_weight(conv, x.dtype), conv.out_channels, conv.kernel_size[0], conv.stride[0], conv.padding[0],
-                      conv.dilation[0], scale, shift, residual, act, slope, slope_ptr, out, out_dtype)
+                      conv.dilation[0], scale, shift, residual, act, slope, slope_ptr, out, out_dtype, stats=stats)
 
 
 def affine_act(x: Act, scale, shift, residual: Optional[Act], act, slope=0.0, slope_ptr=None, out: Optional[Act] = None) -> Act:
@@ -552,6 +555,50 @@ def batchnorm_train_affine(x: Act, bn: torch.nn.BatchNorm2d):
                                      out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), _stream()))
     _count(2)
     if track:   # in-place kernel writes bypass torch's version counter; bump it so folded caches refresh
+        bn.running_mean._bump_version() if hasattr(bn.running_mean, "_bump_version") else bn.running_mean.add_(0)
+        bn.running_var._bump_version() if hasattr(bn.running_var, "_bump_version") else bn.running_var.add_(0)
+    return out[0], out[1], out[2], out[3]
+
+
+BN_FUSED_STATS = os.environ.get("HN_NO_FUSED_BN_STATS") is None
+_stats_chunk = {}          # device index -> [zeroed FP64 chunk, next free element]: one memset serves ~30 BN layers
+
+
+def _stats_alloc(c: int, device) -> torch.Tensor:
+    """Zeroed FP64 [2, c] accumulator carved from a pooled chunk (each slice is handed out once; the chunk dies with its views)."""
+    key = torch.device(device).index
+    need = 2 * c
+    ent = _stats_chunk.get(key)
+    if ent is None or ent[1] + need > ent[0].numel():
+        ent = [torch.zeros((max(32768, need),), dtype=torch.float64, device=device), 0]
+        _stats_chunk[key] = ent
+        _count()
+    view = ent[0][ent[1]:ent[1] + need].view(2, c)
+    ent[1] += need
+    return view
+
+
+
+def batchnorm_finalize(sums: torch.Tensor, count: int, bn: torch.nn.BatchNorm2d):
+    """(scale, shift, mean, invstd) from the FP64 per-channel sums a convolution's epilogue accumulated (stats=...), plus the
+    running-statistic update of nn.BatchNorm2d in train mode -- one tiny launch."""
+    lib = _lib.load()
+    cch = bn.num_features
+    out = torch.empty((4, cch), dtype=torch.float32, device=sums.device)
+    track = bn.track_running_stats and bn.running_mean is not None
+    p = lambda t: t.detach().data_ptr() if t is not None else None
+    momentum, nbt = 0.0, None
+    if track:
+        if bn.momentum is None:
+            bn.num_batches_tracked.add_(1)
+            momentum = 1.0 / float(bn.num_batches_tracked.item())
+        else:
+            momentum, nbt = bn.momentum, p(bn.num_batches_tracked)
+    _lib.check(lib.hn_bn_finalize_tracked(sums.data_ptr(), sums.data_ptr() + 8 * cch, count, p(bn.weight), p(bn.bias), float(bn.eps),
+                                          float(momentum), p(bn.running_mean) if track else None, p(bn.running_var) if track else None,
+                                          nbt, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), cch, _stream()))
+    _count()
+    if track:
         bn.running_mean._bump_version() if hasattr(bn.running_mean, "_bump_version") else bn.running_mean.add_(0)
         bn.running_var._bump_version() if hasattr(bn.running_var, "_bump_version") else bn.running_var.add_(0)
     return out[0], out[1], out[2], out[3]
@@ -601,12 +648,19 @@ def conv_bn_act(x: Act, conv, bn, act=ACT_NONE, slope=0.0, slope_ptr=None, resid
     # which is large for channels with little spatial variation.  Statistics and the normalise pass read the
     # FP32 values; only the normalised activation is rounded to the compute dtype.
     raw_fp32 = BN_TRAIN_RAW_FP32
+    # BF16 engine with FP32 pre-normalisation output: the batch statistics are accumulated by the conv epilogue itself (FP32 per
+    # 32-pixel block, FP64 atomics), so train-mode BN costs one tiny finalize launch instead of a pass over the tensor
+    fused = BN_FUSED_STATS and raw_fp32 and x.dtype == torch.bfloat16 and conv.out_channels >= 17
+    sums = _stats_alloc(conv.out_channels, x.buf.device) if fused else None
     if stem_ok(x, conv):
         wp, shift = packed_stem_weight(conv, None)
-        raw = stem_conv(x, conv, wp, shift, out_dtype=torch.float32 if raw_fp32 else None)
+        raw = stem_conv(x, conv, wp, shift, out_dtype=torch.float32 if raw_fp32 else None, stats=sums)
     else:
-        raw = conv2d(x, conv, scale, shift, None, ACT_NONE, out_dtype=torch.float32 if raw_fp32 else None)
-    bscale, bshift, mean, invstd = batchnorm_train_affine(raw, bn)
+        raw = conv2d(x, conv, scale, shift, None, ACT_NONE, out_dtype=torch.float32 if raw_fp32 else None, stats=sums)
+    if fused:
+        bscale, bshift, mean, invstd = batchnorm_finalize(sums, raw.n * raw.h * raw.w, bn)
+    else:
+        bscale, bshift, mean, invstd = batchnorm_train_affine(raw, bn)
     if out is None:
         in_place = raw.dtype == x.dtype and tape is None
         out = raw if in_place else new_act(raw.n, raw.h, raw.w, raw.c, x.dtype, x.buf.device)

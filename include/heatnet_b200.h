@@ -55,8 +55,9 @@ typedef struct hn_epilogue {
     float slope;            /* used when slope_ptr == NULL */
     const float *slope_ptr; /* device scalar (PReLU weight), optional */
     int32_t out_nchw;       /* 1: y is written as NCHW FP32 (the reference's logits layout) */
-    float *stat_sum;        /* optional [Cout] FP32: += sum over pixels of the PRE-activation value ... */
-    float *stat_sqsum;      /* ... and of its square (BatchNorm2d batch statistics in train mode) */
+    double *stat_sum;       /* optional [Cout] FP64, caller-zeroed: += sum over the output pixels of the stored value ... */
+    double *stat_sqsum;     /* ... and of its square: BatchNorm2d batch statistics in train mode, fused into the conv epilogue
+                             * (BF16 engine, FP32 16-byte-aligned output view, Cout tile >= 32; else the call fails) */
     int32_t per_image;      /* hn_affine_act only: scale (and shift, if given) are [N][C] -- Dropout2d channel masks */
 } hn_epilogue;
 
@@ -155,6 +156,10 @@ int hn_channel_stats(const hn_tensor *x, double *sum, double *sqsum, void *strea
 int hn_bn_finalize(const double *sum, const double *sqsum, int64_t count, const float *gamma, const float *beta,
                    float eps, float momentum, float *running_mean, float *running_var, float *scale, float *shift,
                    float *save_mean, float *save_invstd, int32_t c, void *stream);
+/* same, and `num_batches_tracked += 1` in the same launch (the tail of a conv with fused statistics) */
+int hn_bn_finalize_tracked(const double *sum, const double *sqsum, int64_t count, const float *gamma, const float *beta,
+                           float eps, float momentum, float *running_mean, float *running_var, int64_t *num_batches_tracked,
+                           float *scale, float *shift, float *save_mean, float *save_invstd, int32_t c, void *stream);
 /* train-mode BatchNorm2d statistics in ONE kernel (+ one memset): hn_channel_stats and hn_bn_finalize fused through a
  * last-CTA ticket, including `num_batches_tracked += 1` (cm/models/extractors.py:85-101: every nn.BatchNorm2d in train mode).
  * scratch: device memory of hn_bn_batch_stats_scratch_bytes(C) (FP64 sums + ticket), zeroed by the call. */
