@@ -286,7 +286,7 @@ def run_train(args):
     # cm/train_trgb_segnet_conf.py:270: ONE RMSprop over all parameters; the frozen half has no .grad and is skipped
     optimizer = None if args.no_optimizer else optim.RMSprop(model.parameters(), lr=1e-5)
 
-    def step():
+    def train_step(rgb_d, ir_d, rgb_n, ir_n, label):
         for p in model.parameters():
             p.grad = None
         o = model([rgb_d, ir_d], [rgb_n, ir_n])
@@ -301,10 +301,27 @@ def run_train(args):
             optimizer.step()
         return total
 
+    batch = (rgb_d, ir_d, rgb_n, ir_n, label)
+
+    def step():
+        return train_step(*batch)
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # --cuda-graph on / auto: the whole step -- forward, losses, backward, optimizer -- is captured once and replayed
+    # (heatnet_pub_b200.graphs.GraphedStep): the ~2300 launches of a step are Python-bound below ~10 pairs per GPU (62 ms whatever
+    # the batch) and the replay still saves ~6 % at 16 pairs.  Single-GPU runs only: with N > 1 the bucketed NCCL all-reduce
+    # (async work handles + wait) would be part of the capture, which hung when tried at N = 2 -- multi-GPU steps stay eager
+    use_graph = world == 1 and args.cuda_graph in ("on", "auto") and not args.torch_losses and not args.layer_table
+    if use_graph:
+        from heatnet_pub_b200 import graphs
+        gstep = graphs.GraphedStep(train_step, batch, module=model, warmup=max(args.warmup, 3))
+
+        def step():
+            return gstep(*batch)           # copies the batch into the graph's static inputs, replays, returns the static loss
 
     for _ in range(args.warmup):
         loss = step()
@@ -354,7 +371,7 @@ def run_train(args):
                 "config": {"workload": f"conv_segnet {args.workload} step (PSPNet-ResNet50 late fusion + 6 FCDiscriminator critics), "
                                        f"{B} day+night pairs per GPU at {H}x{W}, fwd + {'torch' if args.torch_losses else 'fused'} losses + bwd + gradient all-reduce"
                                        f"{' (optimizer excluded)' if args.no_optimizer else ' + fused RMSprop step'}; 2 images per pair",
-                           "per_gpu_pairs": B, "global_pairs": B * world, "parallelism": f"batch-sharded x{world}, NCCL all-reduce of "
+                           "per_gpu_pairs": B, "global_pairs": B * world, "cuda_graph": bool(use_graph), "parallelism": f"batch-sharded x{world}, NCCL all-reduce of "
                            f"{reducer.last_bytes / 1e6:.1f} MB in {reducer.last_buckets} buckets" if world > 1 else "single GPU"},
                 "loss": float(loss), "gpu_launches": launches, "clocks": clocks,
                 "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),

@@ -564,6 +564,13 @@ BN_FUSED_STATS = os.environ.get("HN_NO_FUSED_BN_STATS") is None
 _stats_chunk = {}          # device index -> [zeroed FP64 chunk, next free element]: one memset serves ~30 BN layers
 
 
+def reset_stats_pool():
+    """Forget the current accumulator chunk.  A chunk is zeroed once, when it is created, so a CUDA-graph capture must not carve
+    slices from a chunk created before it (the memset would not be part of the graph and replays would keep accumulating), nor
+    may eager code afterwards use a chunk that lives in a graph's private pool: graphs.GraphedStep calls this on both sides."""
+    _stats_chunk.clear()
+
+
 def _stats_alloc(c: int, device) -> torch.Tensor:
     """Zeroed FP64 [2, c] accumulator carved from a pooled chunk (each slice is handed out once; the chunk dies with its views)."""
     key = torch.device(device).index

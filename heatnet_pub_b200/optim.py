@@ -37,7 +37,7 @@ class _FusedOptimizer(torch.optim.Optimizer):
         key = tuple((p.data_ptr(), p.grad.data_ptr(), *(s.data_ptr() if s is not None else 0 for s in st)) for p, st in zip(live, states))
         hit = self._tables.get(gi)
         if hit is not None and hit[0] == key:
-            return hit[1:]
+            return hit[1:5]
         chunk = _lib.load().hn_optim_chunk()
         slots = np.zeros((len(live), 5), dtype=np.int64)
         blocks = []
@@ -47,10 +47,27 @@ class _FusedOptimizer(torch.optim.Optimizer):
             blocks.append(np.stack([np.full(nchunk, i, dtype=np.int32), np.arange(nchunk, dtype=np.int32)], axis=1))
         bmap = np.concatenate(blocks, axis=0) if blocks else np.zeros((0, 2), dtype=np.int32)
         dev = live[0].device
-        slots_d = torch.from_numpy(slots).to(dev)
-        bmap_d = torch.from_numpy(np.ascontiguousarray(bmap)).to(dev)
-        partial = torch.empty(bmap.shape[0] + 1, dtype=torch.float64, device=dev)
-        self._tables[gi] = (key, slots_d, bmap_d, partial, bmap.shape[0])
+        # The tables travel through PINNED staging buffers with asynchronous copies: no host sync per rebuild (gradient tensors
+        # are new allocations every step, so their addresses can change), and a rebuild inside a CUDA-graph capture
+        # (graphs.GraphedStep: the gradients then live in the graph's pool) is a capturable memcpy node.  Buffers are allocated
+        # on the first (eager) call for a given live set and reused.
+        shape_key = (len(live), bmap.shape[0])
+        buf = hit[5] if (hit is not None and len(hit) > 5 and hit[5][0] == shape_key) else None
+        if buf is None:
+            buf = (shape_key, torch.empty((len(live), 5), dtype=torch.int64).pin_memory(), torch.empty((max(bmap.shape[0], 1), 2), dtype=torch.int32).pin_memory(),
+                   torch.empty((len(live), 5), dtype=torch.int64, device=dev), torch.empty((max(bmap.shape[0], 1), 2), dtype=torch.int32, device=dev),
+                   torch.empty(bmap.shape[0] + 1, dtype=torch.float64, device=dev), torch.cuda.Event())
+        _, slots_h, bmap_h, slots_d, bmap_d, partial, done = buf
+        if not torch.cuda.is_current_stream_capturing():
+            done.synchronize()                      # the previous copy out of the staging buffers has finished
+        slots_h.numpy()[...] = slots
+        if bmap.shape[0]:
+            bmap_h.numpy()[:bmap.shape[0]] = bmap
+        slots_d.copy_(slots_h, non_blocking=True)
+        bmap_d.copy_(bmap_h, non_blocking=True)
+        if not torch.cuda.is_current_stream_capturing():
+            done.record()
+        self._tables[gi] = (key, slots_d, bmap_d, partial, bmap.shape[0], buf)
         return slots_d, bmap_d, partial, bmap.shape[0]
 
     def _live(self, group):
@@ -140,6 +157,9 @@ class Adam(_FusedOptimizer):
         return st['exp_avg'], st['exp_avg_sq']
 
     def _launch(self, lib, group, live, slots_d, bmap_d, nblocks, max_norm, sq_ptr):
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("heatnet_pub_b200.optim.Adam: the bias-correction step count is a launch argument; a captured step "
+                               "would replay it unchanged -- use RMSprop inside graphs.GraphedStep, or step Adam eagerly")
         steps = {int(self.state[p]['step'].item()) for p in live}
         # one launch per distinct step count (parameters that joined later, e.g. after a phase switch, have their own)
         if len(steps) == 1:

@@ -242,8 +242,10 @@ class PSPNet(_KernelModule):
             torch.cuda.synchronize(modal_1.device)
             graph = torch.cuda.CUDAGraph()
             l0 = E.launch_count
+            E.reset_stats_pool()
             with torch.cuda.graph(graph):
                 out = self._forward_eager(s1, s2)
+            E.reset_stats_pool()
             entry = (graph, s1, s2, out, E.launch_count - l0)
             self._graphs[key] = entry
         graph, s1, s2, out, launches = entry

@@ -181,3 +181,75 @@ def test_conf_segnet_step_matches_reference_golden_fp32(golden_dir):
         # conv biases in front of a BN have an exactly-zero true gradient (both sides hold rounding noise there):
         # absolute slack of 1e-5 of the largest gradient norm
         np.testing.assert_allclose(gn, g[phase + "/grad_norm"], rtol=3e-3, atol=1e-5 * g[phase + "/grad_norm"].max())
+
+
+def test_graphed_train_step_matches_eager():
+    """graphs.GraphedStep: the captured conv_segnet train_seg step (fwd + fused losses + bwd + fused RMSprop) replays to the
+    same parameters, BN running statistics and loss as the eager loop (FP32 reds in wgrad are unordered: tolerance, not bits),
+    and bumps the version counters so a later eval forward sees the updated weights."""
+    import contextlib
+    import io
+    from heatnet_pub_b200 import conf_segnet, graphs, losses, optim
+
+    def make():
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = conf_segnet.conv_segnet(pretrained=False, disc_arch='cyclegan', num_critics=6, no_conf=False, modalities='ir_rgb',
+                                        arch='pspnet', late_fusion=True)
+            m = m.cuda().train()
+            m.setPhase('train_seg')
+        for mod in m.modules():
+            if isinstance(mod, nn.Dropout2d):
+                mod.p = 0.0                       # identical arithmetic in both runs (the RNG stream positions differ)
+        return m
+
+    g = torch.Generator().manual_seed(3)
+    mk = lambda c: (torch.rand(1, c, 256, 256, generator=g) * 2 - 1).cuda()
+    batches = [(mk(3), mk(1), mk(3), mk(1), torch.randint(0, 13, (1, 256, 256), generator=g).cuda()) for _ in range(2)]
+    mse, ce = losses.MSELoss(), losses.CrossEntropyLoss()
+
+    def runner(model, opt):
+        def train_step(rgb_d, ir_d, rgb_n, ir_n, label):
+            for p in model.parameters():
+                p.grad = None
+            o = model([rgb_d, ir_d], [rgb_n, ir_n])
+            conf = sum(mse(c, 1.0) for c in o['critics_a']) + sum(mse(c, 1.0) for c in o['critics_b'])
+            total = ce(o['pred_label_a'], label) + 0.1 * conf
+            total.backward()
+            opt.step()
+            return total
+        return train_step
+
+    def eager_run():
+        m = make()
+        opt = optim.RMSprop(m.parameters(), lr=1e-5)
+        st = runner(m, opt)
+        for _ in range(3):
+            st(*batches[0])
+        ls = [float(st(*bt).detach()) for bt in (batches[1], batches[0])]
+        torch.cuda.synchronize()
+        return m, ls
+
+    a, la = eager_run()
+    a2, la2 = eager_run()          # the eager loop against itself: FP32 reds in wgrad are unordered and RMSprop's first steps are
+    #                                sign-like (zero-initialised BN biases move by +-10 lr whatever |g|), so runs decorrelate on tiny gradients
+    b = make()
+    opt_b = optim.RMSprop(b.parameters(), lr=1e-5)
+    gstep = graphs.GraphedStep(runner(b, opt_b), batches[0], module=b, warmup=3)
+    v0 = b.trgb_segnet.final[0].weight._version
+    lb = [float(gstep(*bt).detach()) for bt in (batches[1], batches[0])]
+    assert b.trgb_segnet.final[0].weight._version > v0
+    torch.cuda.synchronize()
+    for x, y, z in zip(la, lb, la2):
+        assert abs(x - y) < max(2e-3 * abs(x), 3 * abs(x - z)), (la, lb, la2)
+    sa, sa2, sb = a.state_dict(), a2.state_dict(), b.state_dict()
+    worst = (0.0, None)
+    for k in sa:
+        if sa[k].is_floating_point():
+            noise = rel_l2(sa2[k].cpu(), sa[k].cpu())
+            dev = rel_l2(sb[k].cpu(), sa[k].cpu())
+            assert dev < max(2e-3, 3 * noise), (k, dev, noise)
+            worst = max(worst, (dev, k, noise))
+        else:
+            assert torch.equal(sa[k], sb[k]), k            # num_batches_tracked
+    print("graph vs eager: worst deviation", worst)
