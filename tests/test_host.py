@@ -150,3 +150,22 @@ def test_iou_value_host_logic_matches_oracle():
     assert np.array_equal(m.conf_metric.conf, mo.conf_metric.conf) and m.conf_metric.conf[12].sum() == 0
     with pytest.raises(ValueError):
         iou_eval.IoU(14, False, 1.5)
+
+
+def test_input_pipeline_lookup_tables_are_the_loader_arithmetic():
+    """heatnet_pub_b200.inputs evaluates the loaders' normalisation once per possible input value (CPU, no GPU needed): the tables
+    must equal oracle/inputs_oracle.py (= torchvision's to_tensor / normalize, cm/thermal_loader.py:649-659,715-728) bit for bit."""
+    import numpy as np
+    import torch
+    from heatnet_pub_b200 import inputs as I
+    from oracle import inputs_oracle as IO
+    for mean, std in (((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)), ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))):
+        lut = I._rgb_lut(mean, std, "cpu")
+        img = np.repeat(np.arange(256, dtype=np.uint8)[:, None, None], 3, axis=2)          # (256, 1, 3): every byte value in every channel
+        want = IO.load_rgb(img, mean, std).reshape(3, 256)
+        assert torch.equal(lut, want)
+    for lo, hi in ((21800, 25000), (20800, 27000)):
+        lut = I._ir_lut(lo, hi, 0.5, 0.5, "cpu")
+        counts = np.arange(lo, hi + 1, dtype=np.uint16)[None, :]
+        assert torch.equal(lut, IO.load_ir(counts, lo, hi).reshape(-1))
+        assert lut[0] == -1.0 and lut[-1] == 1.0
