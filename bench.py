@@ -286,7 +286,7 @@ def run_train(args):
     # cm/train_trgb_segnet_conf.py:270: ONE RMSprop over all parameters; the frozen half has no .grad and is skipped
     optimizer = None if args.no_optimizer else optim.RMSprop(model.parameters(), lr=1e-5)
 
-    def train_step(rgb_d, ir_d, rgb_n, ir_n, label):
+    def fwd_bwd(rgb_d, ir_d, rgb_n, ir_n, label):
         for p in model.parameters():
             p.grad = None
         o = model([rgb_d, ir_d], [rgb_n, ir_n])
@@ -296,6 +296,10 @@ def run_train(args):
         else:
             total = sum(mse(c, tgt(c, 1)) for c in o['critics_a']) + sum(mse(c, tgt(c, 0)) for c in o['critics_b'])
         total.backward()
+        return total
+
+    def train_step(*b):
+        total = fwd_bwd(*b)
         reducer.reduce()
         if optimizer is not None:
             optimizer.step()
@@ -313,15 +317,29 @@ def run_train(args):
 
     # --cuda-graph on / auto: the whole step -- forward, losses, backward, optimizer -- is captured once and replayed
     # (heatnet_pub_b200.graphs.GraphedStep): the ~2300 launches of a step are Python-bound below ~10 pairs per GPU (62 ms whatever
-    # the batch) and the replay still saves ~6 % at 16 pairs.  Single-GPU runs only: with N > 1 the bucketed NCCL all-reduce
-    # (async work handles + wait) would be part of the capture, which hung when tried at N = 2 -- multi-GPU steps stay eager
-    use_graph = world == 1 and args.cuda_graph in ("on", "auto") and not args.torch_losses and not args.layer_table
+    # the batch) and the replay still saves ~6 % at 16 pairs.  With N > 1 only forward + losses + backward are captured: the
+    # bucketed NCCL all-reduce (async work handles + wait) hung inside a capture when tried at N = 2
+    use_graph = args.cuda_graph in ("on", "auto") and not args.torch_losses and not args.layer_table
     if use_graph:
         from heatnet_pub_b200 import graphs
-        gstep = graphs.GraphedStep(train_step, batch, module=model, warmup=max(args.warmup, 3))
+        if world == 1:
+            gstep = graphs.GraphedStep(train_step, batch, module=model, warmup=max(args.warmup, 3))
 
-        def step():
-            return gstep(*batch)           # copies the batch into the graph's static inputs, replays, returns the static loss
+            def step():
+                return gstep(*batch)           # copies the batch into the graph's static inputs, replays, returns the static loss
+        else:
+            # N > 1: forward + losses + backward are replayed; the bucketed NCCL all-reduce and the (single-launch) optimizer step
+            # run eagerly on the graph's static gradient tensors
+            for _ in range(max(args.warmup, 3)):
+                train_step(*batch)
+            gstep = graphs.GraphedStep(fwd_bwd, batch, module=model, warmup=1, collectives_inside=False)
+
+            def step():
+                total = gstep(*batch)
+                reducer.reduce()
+                if optimizer is not None:
+                    optimizer.step()
+                return total
 
     for _ in range(args.warmup):
         loss = step()

@@ -14,8 +14,9 @@ Rules (the same as for any captured training loop):
     `loss.backward()` and `heatnet_pub_b200.optim.RMSprop.step()` are all fine; Adam is not (its step count is a launch argument).
   * launch arguments are frozen at capture: learning rate, loss weights, the phase (`conv_segnet.setPhase`), Dropout2d
     probabilities.  Call `recapture()` after changing any of them (StepLR changes lr once per N epochs).
-  * single process / single GPU: parallel.GradientReducer's asynchronous NCCL work handles are not capturable as written (a
-    capture with the reducer inside hung at N = 2); multi-GPU steps run eagerly.
+  * multi-GPU: parallel.GradientReducer's asynchronous NCCL work handles are not capturable as written (a capture with the reducer
+    inside hung at N = 2).  Capture forward + losses + backward only (`collectives_inside=False`; ~2290 of the ~2300 launches) and
+    call `reducer.reduce(); optimizer.step()` eagerly after each replay: the gradients are static tensors of the graph's pool.
   * Python-side effects of the step happen once, at capture; the parameters and BN buffers the kernels update behind torch's back
     get their version counters bumped after every replay, so packed-weight / folded-BN caches of a later eager or eval forward
     stay coherent.
@@ -28,10 +29,12 @@ from . import engine as E
 
 
 class GraphedStep:
-    def __init__(self, step_fn: Callable, example_inputs: Sequence[torch.Tensor], module: Optional[torch.nn.Module] = None, warmup: int = 3):
+    def __init__(self, step_fn: Callable, example_inputs: Sequence[torch.Tensor], module: Optional[torch.nn.Module] = None, warmup: int = 3,
+                 collectives_inside: bool = True):
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            raise RuntimeError("graphs.GraphedStep: multi-process steps (NCCL all-reduce inside the step) are not capturable yet; run eagerly")
+        if collectives_inside and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            raise RuntimeError("graphs.GraphedStep: a step with the NCCL all-reduce inside is not capturable yet; capture forward + "
+                               "losses + backward only (collectives_inside=False) and run reducer.reduce() / optimizer.step() eagerly")
         self.step_fn, self.module, self.warmup = step_fn, module, warmup
         self.static_inputs = [t.clone() for t in example_inputs]
         self.graph = None
