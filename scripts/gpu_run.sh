@@ -1,1 +1,6 @@
-timeout 170 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29551 bench.py --gpus 2 --workload train_seg --height 320 --width 640 --batch 16 --steps 5 --warmup 3 > gpurun_out/train_seg_n2_graph.json 2> gpurun_out/train_seg_n2_graph.err; echo rc=$?; tail -c 250 gpurun_out/train_seg_n2_graph.json; tail -3 gpurun_out/train_seg_n2_graph.err | cut -c1-300
+set -x
+timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -3
+timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -3
+timeout 400 python bench.py > gpurun_out/bench_final3.json 2> gpurun_out/bench_final3.err; wc -l gpurun_out/bench_final3.json
+timeout 300 python bench.py --workload train_seg --height 320 --width 640 --batch 16 --steps 5 --warmup 3 > gpurun_out/train_seg_final2.json 2> /dev/null
+timeout 300 python bench.py --workload train_critic --height 320 --width 640 --batch 16 --steps 5 --warmup 3 > gpurun_out/train_critic_final2.json 2> /dev/null
