@@ -59,6 +59,14 @@ def _worker(rank, world, port, q):
                 want = sum(both) / world
                 assert torch.allclose(live[k], want, atol=1e-6), k
             results[phase] = sorted(live)
+        # a training step with the all-reduce inside must not be captured as a CUDA graph under torch.distributed
+        from heatnet_pub_b200 import graphs
+        try:
+            graphs.GraphedStep(lambda t: t, [torch.zeros(1)], module=model)
+            refused = False
+        except RuntimeError as e:
+            refused = "collectives_inside=False" in str(e)
+        assert refused, "GraphedStep must refuse a capture with collectives inside when world_size > 1"
         q.put((rank, results))
     finally:
         dist.destroy_process_group()
