@@ -218,16 +218,23 @@ class PSPNet(_KernelModule):
             return False
         return modal_1.is_cuda and (modal_2 is None or modal_2.is_cuda)
 
+    MAX_GRAPHS = 2            # live graphs per module (one per input shape): each pool holds a full set of activations
+
     def _graph_key(self, modal_1, modal_2):
-        ver = sum(p._version for p in self.parameters()) + sum(b._version for b in self.buffers())
+        """-> (shape key, state version): a graph is reused for the same shapes while no parameter / buffer has changed."""
+        ver = (sum(p._version for p in self.parameters()) + sum(b._version for b in self.buffers()), next(self.parameters()).data_ptr())
         return (tuple(modal_1.shape), modal_1.dtype, None if modal_2 is None else (tuple(modal_2.shape), modal_2.dtype),
-                modal_1.device, self.precision or E.DEFAULT_PRECISION, ver, next(self.parameters()).data_ptr())
+                modal_1.device, self.precision or E.DEFAULT_PRECISION), ver
 
     def _forward_graph(self, modal_1, modal_2):
-        key = self._graph_key(modal_1, modal_2)
+        key, ver = self._graph_key(modal_1, modal_2)
         entry = self._graphs.get(key)
+        if entry is not None and entry[5] != ver:     # weights or BN buffers changed: the captured weight packs are stale
+            del self._graphs[key]
+            entry = None
         if entry is None:
-            self._graphs.clear()                      # one live graph per module: its pool holds a full set of activations
+            while len(self._graphs) >= self.MAX_GRAPHS:
+                del self._graphs[next(iter(self._graphs))]      # oldest first (dicts keep insertion order)
             s1 = torch.empty_like(modal_1, memory_format=torch.contiguous_format)
             s2 = None if modal_2 is None else torch.empty_like(modal_2, memory_format=torch.contiguous_format)
             s1.copy_(modal_1)
@@ -246,9 +253,9 @@ class PSPNet(_KernelModule):
             with torch.cuda.graph(graph):
                 out = self._forward_eager(s1, s2)
             E.reset_stats_pool()
-            entry = (graph, s1, s2, out, E.launch_count - l0)
+            entry = (graph, s1, s2, out, E.launch_count - l0, ver)
             self._graphs[key] = entry
-        graph, s1, s2, out, launches = entry
+        graph, s1, s2, out, launches, _ = entry
         s1.copy_(modal_1)
         if s2 is not None:
             s2.copy_(modal_2)

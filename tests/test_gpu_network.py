@@ -222,7 +222,16 @@ def test_cuda_graph_replay_matches_eager():
         assert not torch.equal(b, ref)
         c, _, _ = net(rgb, ir)
         assert torch.equal(c, ref)
-        net.final[0].bias.add_(1.0)                    # parameter update -> new key -> re-capture
+        rgb2, ir2 = O.synthetic_inputs(1, 64, 128)     # a second input shape gets its own graph; both stay cached
+        rgb2, ir2 = rgb2.cuda(), ir2.cuda()
+        net.set_cuda_graph(False)
+        want2 = net(rgb2, ir2)[0].clone()
+        net.set_cuda_graph(True)
+        net(rgb, ir)
+        assert torch.equal(net(rgb2, ir2)[0], want2) and len(net._graphs) == 2
+        g_first = net._graphs[next(iter(net._graphs))][0]
+        assert torch.equal(net(rgb, ir)[0], ref) and net._graphs[next(iter(net._graphs))][0] is g_first      # no re-capture
+        net.final[0].bias.add_(1.0)                    # parameter update -> stale version -> re-capture
         d, _, _ = net(rgb, ir)
         assert torch.allclose(d, ref + 1.0, atol=1e-5)
         net.set_cuda_graph(False)
