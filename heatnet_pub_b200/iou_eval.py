@@ -15,16 +15,20 @@ import torch
 from . import _lib
 
 
+def _require(condition, message):
+    """The reference signals bad inputs with `assert cond, message` (iou_eval.py:58-79,146-151): same exception, same text."""
+    if not condition:
+        raise AssertionError(message)
+
+
 class Metric(object):
-    """Base class for all metrics (iou_eval.py:5-17)."""
-    def reset(self):
-        pass
+    """Interface of the reference's metrics (iou_eval.py:5-17): reset / add / value, all no-ops here."""
 
-    def add(self):
-        pass
+    def reset(self): pass
 
-    def value(self):
-        pass
+    def add(self): pass
+
+    def value(self): pass
 
 
 def _device():
@@ -46,14 +50,12 @@ class ConfusionMatrix(Metric):
     """iou_eval.py:19-101.  `conf[t, p]` counts pixels of target class t predicted as p."""
 
     def __init__(self, num_classes, normalized=False):
-        super().__init__()
-        self.conf = np.ndarray((num_classes, num_classes), dtype=np.int32)
-        self.normalized = normalized
-        self.num_classes = num_classes
-        self.reset()
+        Metric.__init__(self)
+        self.num_classes, self.normalized = num_classes, normalized
+        self.conf = np.zeros((num_classes, num_classes), dtype=np.int32)      # int32 like the reference's accumulator (iou_eval.py:32)
 
     def reset(self):
-        self.conf.fill(0)
+        self.conf[...] = 0
 
     def _histogram(self, pred_labels, scores, n_images, hw, target):
         k = self.num_classes
@@ -68,33 +70,26 @@ class ConfusionMatrix(Metric):
         _lib.check(rc)
         host = out.cpu().numpy()                                          # the only D2H: (K*K+1) * 8 bytes
         flag = int(host[k * k]) & 0xFFFFFFFF
-        assert not (flag & 1), 'predicted values are not between 0 and k-1'
-        assert not (flag & 2), 'target values are not between 0 and k-1'
+        _require(not flag & 1, 'predicted values are not between 0 and k-1')
+        _require(not flag & 2, 'target values are not between 0 and k-1')
         return host[:k * k].reshape(k, k)
 
     def add(self, predicted, target):
         """predicted: N labels or N x K scores; target: N labels or N x K one-hot (iou_eval.py:38-88)."""
         k = self.num_classes
-        assert predicted.shape[0] == target.shape[0], \
-            'number of targets and predicted outputs do not match'
-        predicted = _as_cuda(predicted)
-        target = _as_cuda(target)
+        _require(predicted.shape[0] == target.shape[0], 'number of targets and predicted outputs do not match')
+        predicted, target = _as_cuda(predicted), _as_cuda(target)
         scores = None
-        if predicted.dim() != 1:
-            assert predicted.shape[1] == k, \
-                'number of predictions does not match size of confusion matrix'
-            # (N, K) scores: one "image" per row with hw = 1 is the same NCHW layout the kernel expects
-            scores = predicted.float().contiguous()
-            predicted = None
-        else:
+        if predicted.dim() == 1:
             predicted = predicted.to(torch.int64)
+        else:
+            _require(predicted.shape[1] == k, 'number of predictions does not match size of confusion matrix')
+            # (N, K) scores: one "image" per row with hw = 1 is the same NCHW layout the kernel expects
+            scores, predicted = predicted.float().contiguous(), None
         if target.dim() != 1:
-            assert target.shape[1] == k, \
-                'Onehot target does not match size of confusion matrix'
-            assert bool((target >= 0).all()) and bool((target <= 1).all()), \
-                'in one-hot encoding, target values should be 0 or 1'
-            assert bool((target.sum(1) == 1).all()), \
-                'multi-label setting is not supported'
+            _require(target.shape[1] == k, 'Onehot target does not match size of confusion matrix')
+            _require(bool(((target >= 0) & (target <= 1)).all()), 'in one-hot encoding, target values should be 0 or 1')
+            _require(bool((target.sum(1) == 1).all()), 'multi-label setting is not supported')
             target = target.argmax(1)
         target = target.to(torch.int64).contiguous()
         n = target.shape[0]
@@ -111,48 +106,50 @@ class ConfusionMatrix(Metric):
         k = self.num_classes
         scores = _as_cuda(scores, torch.float32)
         target = _as_cuda(target, torch.int64)
-        assert scores.shape[1] == k, 'number of predictions does not match size of confusion matrix'
+        _require(scores.shape[1] == k, 'number of predictions does not match size of confusion matrix')
         n, _, h, w = scores.shape
         if n * h * w == 0:
             return
         self.conf += self._histogram(None, scores, n, h * w, target.view(-1)).astype(np.int32)
 
     def value(self):
-        if self.normalized:
-            conf = self.conf.astype(np.float32)
-            return conf / conf.sum(1).clip(min=1e-12)[:, None]
-        else:
+        """The accumulator itself (NOT a copy: IoU.value() edits it in place, as in the reference), or its row-normalised FP32
+        version (iou_eval.py:90-101)."""
+        if not self.normalized:
             return self.conf
+        as_float = self.conf.astype(np.float32)
+        row_sums = as_float.sum(1).clip(min=1e-12)
+        return as_float / row_sums[:, None]
 
 
 class IoU(Metric):
     """iou_eval.py:103-182."""
 
     def __init__(self, num_classes, normalized=False, ignore_index=None):
-        super().__init__()
+        Metric.__init__(self)
         self.conf_metric = ConfusionMatrix(num_classes, normalized)
+        self.ignore_index = self._as_index_tuple(ignore_index)
 
+    @staticmethod
+    def _as_index_tuple(ignore_index):
+        """None, one class id, or an iterable of class ids (iou_eval.py:122-133)."""
         if ignore_index is None:
-            self.ignore_index = None
-        elif isinstance(ignore_index, int):
-            self.ignore_index = (ignore_index,)
-        else:
-            try:
-                self.ignore_index = tuple(ignore_index)
-            except TypeError:
-                raise ValueError("'ignore_index' must be an int or iterable")
+            return None
+        if isinstance(ignore_index, int):
+            return (ignore_index,)
+        try:
+            return tuple(ignore_index)
+        except TypeError:
+            raise ValueError("'ignore_index' must be an int or iterable")
 
     def reset(self):
         self.conf_metric.reset()
 
     def add(self, predicted, target):
         """predicted: (N, K, H, W) scores or (N, H, W) labels; target likewise (iou_eval.py:135-159)."""
-        assert predicted.size(0) == target.size(0), \
-            'number of targets and predicted outputs do not match'
-        assert predicted.dim() == 3 or predicted.dim() == 4, \
-            "predictions must be of dimension (N, H, W) or (N, K, H, W)"
-        assert target.dim() == 3 or target.dim() == 4, \
-            "targets must be of dimension (N, H, W) or (N, K, H, W)"
+        _require(predicted.size(0) == target.size(0), 'number of targets and predicted outputs do not match')
+        _require(predicted.dim() in (3, 4), "predictions must be of dimension (N, H, W) or (N, K, H, W)")
+        _require(target.dim() in (3, 4), "targets must be of dimension (N, H, W) or (N, K, H, W)")
 
         if target.dim() == 4:
             _, target = _as_cuda(target).max(1)
@@ -168,16 +165,16 @@ class IoU(Metric):
     def value(self):
         """-> (per-class IoU float64 array, mean IoU ignoring NaN) (iou_eval.py:161-182), including the
         reference's in-place zeroing of the ignored rows/columns of the shared accumulator."""
-        conf_matrix = self.conf_metric.value()
+        cm = self.conf_metric.value()
         if self.ignore_index is not None:
-            for index in self.ignore_index:
-                conf_matrix[:, self.ignore_index] = 0
-                conf_matrix[self.ignore_index, :] = 0
-        true_positive = np.diag(conf_matrix)
-        false_positive = np.sum(conf_matrix, 0) - true_positive
-        false_negative = np.sum(conf_matrix, 1) - true_positive
-
+            ignored = list(self.ignore_index)
+            # the reference zeroes ALL ignored rows and columns on every pass of its loop, in the matrix value() returned -- for
+            # an un-normalised metric that is the shared accumulator, so the counts are gone for later add() calls as well
+            cm[:, ignored] = 0
+            cm[ignored, :] = 0
+        tp = np.diag(cm)
+        fp = cm.sum(axis=0) - tp
+        fn = cm.sum(axis=1) - tp
         with np.errstate(divide='ignore', invalid='ignore'):
-            iou = true_positive / (true_positive + false_positive + false_negative)
-
+            iou = tp / (tp + fp + fn)                 # 0 / 0 -> NaN for classes that never occur
         return iou, np.nanmean(iou)
