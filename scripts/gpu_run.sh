@@ -1,1 +1,9 @@
-timeout 280 ncu --set full --clock-control none --import-source on -k regex:'conv_stem_dense|bilinear_up2_walk|pyramid_rows|maxpool_kernel|bilinear_sum_seg|nchw_to_nhwc_smallc|stem_pad' -s 12 -c 12 -o gpurun_out/prof_r1_bandwidth -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_f5.log 2>&1; echo rc=$?; ls -la gpurun_out/prof_r1_bandwidth.ncu-rep
+# Standard verification on a B200 box:  gpurun --timeout 1200 -- 'bash scripts/gpu_run.sh'
+set -x
+timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -3
+timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -3
+mkdir -p gpurun_out
+timeout 400 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 400 gpurun_out/bench.json
+timeout 300 python bench.py --workload iou_eval > gpurun_out/iou_eval.json 2> /dev/null
+timeout 300 python bench.py --workload train_seg --height 320 --width 640 --batch 16 --steps 5 --warmup 3 > gpurun_out/train_seg.json 2> /dev/null
+timeout 300 python bench.py --workload train_critic --height 320 --width 640 --batch 16 --steps 5 --warmup 3 > gpurun_out/train_critic.json 2> /dev/null
