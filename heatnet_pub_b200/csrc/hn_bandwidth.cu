@@ -463,6 +463,13 @@ __global__ void __launch_bounds__(256) pyramid_rows_kernel(const T *__restrict__
 #pragma unroll
         for (int j = 0; j < 8; ++j) seg[j] = 0.f;
         int w = s0;
+        for (; w + 8 <= s1; w += 8) {                      // 8 loads in flight: the kernel is latency-bound (ncu: 17 % issue active)
+            float v[8][8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) Vec8<T>::load(row + (int64_t)(w + u) * ldx, v[u]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) seg[j] += ((v[0][j] + v[1][j]) + (v[2][j] + v[3][j])) + ((v[4][j] + v[5][j]) + (v[6][j] + v[7][j]));
+        }
         for (; w + 4 <= s1; w += 4) {
             float v[4][8];
 #pragma unroll
@@ -740,6 +747,9 @@ __global__ void __launch_bounds__(128) bilinear_sum_seg_kernel(const __grid_cons
     T *yrow = y + (int64_t)row * Wo * ldy + c;
     float a0[4][8], a1[4][8];
     int cur[4] = {-1, -1, -1, -1};
+    float sw[4];                                           // W_s / Wo once per thread, not once per output pixel (a division each)
+#pragma unroll
+    for (int s = 0; s < 4; ++s) sw[s] = s < src.n ? (float)src.w[s] / (float)Wo : 0.f;
     for (int wo = w_begin; wo < w_end; ++wo) {
         float acc[8];
 #pragma unroll
@@ -750,7 +760,7 @@ __global__ void __launch_bounds__(128) bilinear_sum_seg_kernel(const __grid_cons
             const int H = src.h[s], W = src.w[s], ld = src.ld[s];
             int x0, x1;
             float lx;
-            bilinear_src(wo, (float)W / (float)Wo, W, x0, x1, lx);
+            bilinear_src(wo, sw[s], W, x0, x1, lx);
             if (x0 != cur[s]) {                                   // warp-uniform
                 int y0, y1;
                 float ly;
