@@ -56,6 +56,7 @@ SIGNATURES = {
     "hn_bilinear_fwd": (C.c_int, [_T, _T, _P]),
     "hn_bilinear_sum_fwd": (C.c_int, [_T, _I32, _T, _P]),
     "hn_affine_act": (C.c_int, [_T, _E, _T, _P]),
+    "hn_dropout2d_scale": (C.c_int, [_P, _I64, _F, _P, _P]),
     "hn_channel_stats": (C.c_int, [_T, _P, _P, _P]),
     "hn_bn_finalize": (C.c_int, [_P, _P, _I64, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _I32, _P]),
     "hn_bn_finalize_tracked": (C.c_int, [_P, _P, _I64, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _I32, _P]),

@@ -25,6 +25,8 @@ class _NetFunction(torch.autograd.Function):
     def forward(ctx, runner: Callable, n_inputs: int, *args):
         inputs, params = args[:n_inputs], args[n_inputs:]
         tape = E.Tape()
+        if E.grad_arena is not None:
+            E.grad_arena.on_forward()
         prev = E.current_tape
         E.current_tape = tape
         try:
@@ -39,6 +41,8 @@ class _NetFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *douts):
         grads = E.Grads()
+        if E.grad_arena is not None:
+            E.grad_arena.on_backward()
         for act, d in zip(ctx.out_acts, douts):
             if d is None or act is None:
                 continue
@@ -61,6 +65,11 @@ class _NetFunction(torch.autograd.Function):
                 in_grads.append(g.nchw())                       # the input was one of our NHWC views: same layout back
             else:
                 in_grads.append(E.to_nchw_f32(g).to(meta[0]))
+        # gradients written into the arena of a parallel.GradientReducer are bound to .grad here (a view of the parameter's slot:
+        # no copy, static address) and torch.autograd gets None for them; the rest travels back through autograd as usual
+        for p, slot in grads.arena_params.items():
+            if p.grad is None or p.grad.data_ptr() != slot.data_ptr():
+                p.grad = slot
         p_grads = [grads.params.get(p) if p.requires_grad else None for p in ctx.params]
         ctx.tape = ctx.in_acts = ctx.out_acts = None
         return (None, None, *in_grads, *p_grads)

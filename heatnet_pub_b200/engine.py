@@ -138,7 +138,8 @@ class Grads:
 
     def __init__(self):
         self.bufs = {}          # activation buf data_ptr -> [grad tensor, [(c0, c1), ...]]
-        self.params = {}        # nn.Parameter -> gradient tensor
+        self.params = {}        # nn.Parameter -> gradient tensor (returned to torch.autograd)
+        self.arena_params = {}  # nn.Parameter -> its slot of the gradient arena (assigned to .grad directly)
 
     def _entry(self, act: "Act", dtype=None):
         key = act.buf.data_ptr()
@@ -199,11 +200,26 @@ class Grads:
             self._zero_uncovered(e, c0, c1)
         return Act(e[0], act.c, act.coff)
 
-    def add_param(self, param, grad):
-        if param in self.params:
-            self.params[param] = self.params[param] + grad
-        else:
-            self.params[param] = grad
+    def param_sink(self, param):
+        """-> (FP32 tensor of the parameter's shape the backward kernel writes into, accumulate flag).  With a gradient arena
+        active (parallel.GradientReducer) that is the parameter's slot of the flat arena -- `.grad` becomes a view of it, no
+        copy, static address; otherwise a tensor handed back to torch.autograd.  Call param_done() once the kernel is enqueued."""
+        arena = grad_arena
+        if arena is not None and arena.owns(param):
+            t, acc = arena.sink(param)
+            self.arena_params[param] = t
+            return t, acc
+        t = self.params.get(param)
+        if t is not None:
+            return t, True
+        t = torch.empty(param.shape, dtype=torch.float32, device=param.device)
+        self.params[param] = t
+        return t, False
+
+    def param_done(self, param):
+        arena = grad_arena
+        if arena is not None and param in self.arena_params:
+            arena.produced(param)
 
 
 class Tape:
@@ -229,6 +245,8 @@ class Tape:
 
 
 current_tape: Optional[Tape] = None
+# parallel.GradientReducer registers itself here: parameter gradients are then written straight into its flat arena
+grad_arena = None
 
 
 def _wants(p) -> bool:
@@ -237,6 +255,21 @@ def _wants(p) -> bool:
 
 # -------------------------------------------------------------------------------------------------- workspace
 _workspace = {}
+_capture_refs = None       # list while a CUDA graph is being captured: every workspace a captured kernel was pointed at
+
+
+def begin_capture_refs() -> list:
+    """Capture sites (PSPNet._forward_graph, graphs.GraphedStep) call this before capturing and keep the returned list with the
+    graph: the grow-only workspace below is dropped when a later call needs a larger one, but a graph that baked the old
+    address into its kernels must keep that block alive (and away from the allocator) for its own lifetime."""
+    global _capture_refs
+    _capture_refs = []
+    return _capture_refs
+
+
+def end_capture_refs():
+    global _capture_refs
+    _capture_refs = None
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:
@@ -248,6 +281,8 @@ def workspace(nbytes: int, device) -> torch.Tensor:
         _workspace[key] = None
         ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
         _workspace[key] = ws
+    if _capture_refs is not None and not any(r is ws for r in _capture_refs):
+        _capture_refs.append(ws)
     return ws
 
 
@@ -618,9 +653,13 @@ def _conv_param_backward(grads: Grads, tape: Tape, x: Act, conv, dz: Act):
         accumulate(dz, cast, False)
         dz = cast
     if _wants(conv.weight):
-        grads.add_param(conv.weight, conv2d_wgrad(x, dz, conv))
+        dst, acc = grads.param_sink(conv.weight)
+        conv2d_wgrad(x, dz, conv, out=dst, accumulate=acc)
+        grads.param_done(conv.weight)
     if _wants(conv.bias):
-        grads.add_param(conv.bias, vec_to_grad(channel_sums(dz)[0], conv.out_channels))
+        dst, acc = grads.param_sink(conv.bias)
+        vec_to_grad(channel_sums(dz)[0], conv.out_channels, out=dst, accumulate=acc)
+        grads.param_done(conv.bias)
     if tape.needs(x):
         gx, inited = grads.target(x)
         conv2d_dgrad(dz, conv, x.h, x.w, out=gx, accumulate=inited)
@@ -687,16 +726,14 @@ def conv_bn_act(x: Act, conv, bn, act=ACT_NONE, slope=0.0, slope_ptr=None, resid
                 prelu = _wants(slope_ptr)
                 # no residual: the pre-activation is recomputed from raw with the forward's own scale/shift (y is not streamed)
                 fz = (bscale, bshift) if residual is None else (None, None)
-                draw, pg = bn_bwd(dout, y, raw, mean, invstd, bn.weight, act, slope, slope_ptr, dres, dres_acc, prelu,
-                                  _wants(bn.bias), _wants(bn.weight), fz[0], fz[1])
+                sinks = [grads.param_sink(q) if w else (None, False) for q, w in ((bn.bias, _wants(bn.bias)), (bn.weight, _wants(bn.weight)),
+                                                                                (slope_ptr, prelu))]
+                draw = bn_bwd(dout, y, raw, mean, invstd, bn.weight, act, slope, slope_ptr, dres, dres_acc, sinks, fz[0], fz[1])
                 if dres is not None:
                     grads.mark(residual)
-                if pg[0] is not None:
-                    grads.add_param(bn.bias, pg[0])
-                if pg[1] is not None:
-                    grads.add_param(bn.weight, pg[1])
-                if pg[2] is not None:
-                    grads.add_param(slope_ptr, pg[2])
+                for q, (t, _) in zip((bn.bias, bn.weight, slope_ptr), sinks):
+                    if t is not None:
+                        grads.param_done(q)
                 _conv_param_backward(grads, tape, x, conv, draw)
 
             tape.record(backward)
@@ -819,13 +856,40 @@ def bilinear(x: Act, h: int, w: int, out: Optional[Act] = None, out_dtype=None) 
     return out
 
 
+_dropout_state = {}        # device index -> int64 [2] on the device: {seed, masks drawn so far}
+
+
+def dropout_seed(seed: Optional[int] = None, device=None):
+    """(Re)seed the Dropout2d generator of `device`: the same seed reproduces the same sequence of channel masks.  Without an
+    explicit seed the state is created from torch.initial_seed() (so torch.manual_seed() before the first training forward
+    is enough).  The state lives in device memory and the mask kernel advances it itself: replays of a captured CUDA graph
+    draw a fresh mask each time (hn_dropout2d_scale)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if seed is None:
+        seed = torch.initial_seed()
+    st = torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=dev)
+    _dropout_state[dev.index] = st
+    return st
+
+
 def dropout2d(x: Act, p: float, mask: Optional[torch.Tensor] = None) -> Act:
     """nn.Dropout2d in train mode: whole channels of each image zeroed with probability p, survivors scaled by
-    1/(1-p).  `mask` (N, C) of {0,1} keep flags may be injected for parity runs; otherwise it is drawn from
-    torch's CUDA generator (the reference's exact RNG stream cannot be reproduced by any other kernel)."""
-    if mask is None:
-        mask = torch.rand((x.n, x.c), device=x.buf.device) >= p
-    scale = (mask.to(device=x.buf.device, dtype=torch.float32) * (1.0 / (1.0 - p))).contiguous()
+    1/(1-p); p = 1 zeroes everything (torch does the same).  `mask` (N, C) of {0,1} keep flags may be injected for
+    parity runs (the reference's RNG stream cannot be reproduced by another kernel); otherwise the [N, C] scale vector
+    comes from the keyed Philox kernel (dropout_seed)."""
+    if not 0.0 <= p <= 1.0:
+        raise ValueError(f"dropout probability has to be between 0 and 1, but got {p}")
+    if mask is not None:
+        assert tuple(mask.shape) == (x.n, x.c), f"injected Dropout2d mask must be (N, C) = {(x.n, x.c)}, got {tuple(mask.shape)}"
+        keep = 1.0 / (1.0 - p) if p < 1.0 else 0.0
+        scale = (mask.to(device=x.buf.device, dtype=torch.float32) * keep).contiguous()
+    else:
+        st = _dropout_state.get(x.buf.device.index)
+        if st is None:
+            st = dropout_seed(None, x.buf.device)
+        scale = torch.empty((x.n, x.c), dtype=torch.float32, device=x.buf.device)
+        _lib.check(_lib.load().hn_dropout2d_scale(st.data_ptr(), x.n * x.c, float(p), scale.data_ptr(), _stream()))
+        _count()
     ep = _epilogue(scale, None, None, ACT_NONE, 0.0, None)
     ep.per_image = 1
     out = new_act(x.n, x.h, x.w, x.c, x.dtype, x.buf.device)
@@ -900,25 +964,29 @@ def conv2d_dgrad(dy: Act, conv: torch.nn.Conv2d, in_h: int, in_w: int, out: Opti
     return conv2d_raw(g, wp, conv.in_channels, k, 1, padp, dil, residual=res, out=out)
 
 
-def conv2d_wgrad(x: Act, dy: Act, conv: torch.nn.Conv2d) -> torch.Tensor:
-    """-> OIHW FP32 weight gradient (new tensor)."""
+def conv2d_wgrad(x: Act, dy: Act, conv: torch.nn.Conv2d, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """-> OIHW FP32 weight gradient, written to (accumulate: added to) `out` when given, else a new tensor."""
     lib = _lib.load()
     hdt = _HN_DTYPE[x.dtype]
     cout, cin, k = conv.out_channels, conv.in_channels, conv.kernel_size[0]
     cout_pad, kpad = lib.hn_conv_cout_pad(cout, hdt), lib.hn_conv_kpad(cin, k, k)
-    packed = torch.empty((cout_pad, kpad), dtype=torch.float32, device=x.buf.device)
+    if out is None:
+        out, accumulate = torch.empty((cout, cin, k, k), dtype=torch.float32, device=x.buf.device), False
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == cout * cin * k * k
     cv = HnConv(cout, k, k, conv.stride[0], conv.padding[0], conv.dilation[0])
     xh, dh = x.hn(), dy.hn()
     ws_bytes = lib.hn_conv2d_wgrad_workspace_bytes(C.byref(xh), C.byref(cv))
     ws_ptr = workspace(ws_bytes, x.buf.device).data_ptr() if ws_bytes else None
-    _lib.check(lib.hn_conv2d_wgrad(C.byref(xh), C.byref(dh), C.byref(cv), packed.data_ptr(), 1, ws_ptr, ws_bytes, _stream()))
+    # 1x1 without padding: the packed [Cout][Cin] matrix IS the OIHW gradient -- the kernel accumulates straight into `out`
+    direct = k == 1 and kpad == cin and cout_pad == cout
+    packed = out if direct else torch.empty((cout_pad, kpad), dtype=torch.float32, device=x.buf.device)
+    _lib.check(lib.hn_conv2d_wgrad(C.byref(xh), C.byref(dh), C.byref(cv), packed.data_ptr(), 0 if (direct and accumulate) else 1, ws_ptr,
+                                   ws_bytes, _stream()))
     _count(2 + (1 if ws_bytes else 0))
-    if k == 1 and kpad == cin and cout_pad == cout:       # 1x1, no padding: the packed [Cout][Cin] matrix IS the OIHW gradient
-        return packed.view(cout, cin, 1, 1)
-    grad = torch.empty((cout, cin, k, k), dtype=torch.float32, device=x.buf.device)
-    _lib.check(lib.hn_unpack_wgrad(packed.data_ptr(), grad.data_ptr(), cout, cin, k, k, kpad, 0, _stream()))
-    _count()
-    return grad
+    if not direct:
+        _lib.check(lib.hn_unpack_wgrad(packed.data_ptr(), out.data_ptr(), cout, cin, k, k, kpad, int(accumulate), _stream()))
+        _count()
+    return out
 
 
 def act_bwd(dout: Act, out: Act, act, slope=0.0) -> Act:
@@ -936,32 +1004,43 @@ def channel_sums(x: Act) -> torch.Tensor:
     return sums
 
 
-def vec_to_grad(src_f64: torch.Tensor, n: int) -> torch.Tensor:
-    g = torch.empty((n,), dtype=torch.float32, device=src_f64.device)
-    _lib.check(_lib.load().hn_vec_to_grad(src_f64.data_ptr(), g.data_ptr(), n, 0, _stream()))
+def vec_to_grad(src_f64: torch.Tensor, n: int, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    if out is None:
+        out, accumulate = torch.empty((n,), dtype=torch.float32, device=src_f64.device), False
+    _lib.check(_lib.load().hn_vec_to_grad(src_f64.data_ptr(), out.data_ptr(), n, int(accumulate), _stream()))
     _count()
-    return g
+    return out
 
 
 def bn_bwd(dout: Act, out: Act, raw: Act, mean, invstd, gamma, act, slope=0.0, slope_ptr=None, dres: Optional[Act] = None,
-           dres_accumulate=False, want_prelu_grad=False, want_dbeta=True, want_dgamma=True, fwd_scale=None, fwd_shift=None):
-    """-> (draw Act, (dbeta, dgamma, dslope)): FP32 parameter gradients written by the apply kernel itself (None when not
-    asked for)."""
+           dres_accumulate=False, sinks=((None, False),) * 3, fwd_scale=None, fwd_shift=None) -> Act:
+    """-> draw.  `sinks` = (tensor or None, accumulate) for dbeta, dgamma, dPReLU-slope: FP32 parameter gradients written by the
+    apply kernel itself.  The kernel has ONE accumulate flag: sinks that disagree with it are routed through a scratch vector."""
     cch = dout.c
     dev = dout.buf.device
     sums = torch.empty((2 * cch + 1,), dtype=torch.float64, device=dev)
     draw = new_act(dout.n, dout.h, dout.w, cch, dout.dtype, dev)
-    pg = torch.empty((2 * cch + 1,), dtype=torch.float32, device=dev)
-    dbeta = pg[:cch] if want_dbeta else None
-    dgamma = pg[cch:2 * cch] if want_dgamma else None
-    dslope = pg[2 * cch:] if want_prelu_grad else None
+    wanted = [(t, a) for t, a in sinks if t is not None]
+    acc = bool(wanted) and all(a for _, a in wanted)
+    ptrs, fixups = [], []
+    for t, a in sinks:
+        if t is None:
+            ptrs.append(None)
+        elif a == acc:
+            ptrs.append(t.data_ptr())
+        else:                                  # mixed flags (cannot happen for one BN layer's own parameters in practice)
+            tmp = torch.empty_like(t)
+            ptrs.append(tmp.data_ptr())
+            fixups.append((t, tmp, a))
     p = lambda t: t.detach().data_ptr() if t is not None else None
     _lib.check(_lib.load().hn_bn_bwd(C.byref(dout.hn()), C.byref(out.hn()), C.byref(raw.hn()), p(mean), p(invstd), p(gamma), act,
                                     float(slope), p(slope_ptr), sums.data_ptr(), C.byref(draw.hn()),
                                     C.byref(dres.hn()) if dres is not None else None, int(dres_accumulate),
-                                    int(want_prelu_grad), p(dbeta), p(dgamma), p(dslope), 0, p(fwd_scale), p(fwd_shift), _stream()))
+                                    int(ptrs[2] is not None), ptrs[0], ptrs[1], ptrs[2], int(acc), p(fwd_scale), p(fwd_shift), _stream()))
     _count(3)
-    return draw, (dbeta, dgamma, dslope)
+    for t, tmp, a in fixups:
+        t.add_(tmp) if a else t.copy_(tmp)
+    return draw
 
 
 def accumulate(x: Act, y: Act, add: bool):

@@ -14,9 +14,9 @@ Rules (the same as for any captured training loop):
     `loss.backward()` and `heatnet_pub_b200.optim.RMSprop.step()` are all fine; Adam is not (its step count is a launch argument).
   * launch arguments are frozen at capture: learning rate, loss weights, the phase (`conv_segnet.setPhase`), Dropout2d
     probabilities.  Call `recapture()` after changing any of them (StepLR changes lr once per N epochs).
-  * multi-GPU: parallel.GradientReducer's asynchronous NCCL work handles are not capturable as written (a capture with the reducer
-    inside hung at N = 2).  Capture forward + losses + backward only (`collectives_inside=False`; ~2290 of the ~2300 launches) and
-    call `reducer.reduce(); optimizer.step()` eagerly after each replay: the gradients are static tensors of the graph's pool.
+  * multi-GPU: parallel.GradientReducer enqueues its bucketed ncclAllReduce calls on a communication stream ordered by CUDA
+    events (no work handles, no host waits), so the exchange is captured with the rest of the step and replayed: run the step
+    eagerly at least twice first (the first step of a phase learns the bucket plan; GraphedStep's own warm-up does that).
   * Python-side effects of the step happen once, at capture; the parameters and BN buffers the kernels update behind torch's back
     get their version counters bumped after every replay, so packed-weight / folded-BN caches of a later eager or eval forward
     stay coherent.
@@ -29,13 +29,8 @@ from . import engine as E
 
 
 class GraphedStep:
-    def __init__(self, step_fn: Callable, example_inputs: Sequence[torch.Tensor], module: Optional[torch.nn.Module] = None, warmup: int = 3,
-                 collectives_inside: bool = True):
-        import torch.distributed as dist
-        if collectives_inside and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            raise RuntimeError("graphs.GraphedStep: a step with the NCCL all-reduce inside is not capturable yet; capture forward + "
-                               "losses + backward only (collectives_inside=False) and run reducer.reduce() / optimizer.step() eagerly")
-        self.step_fn, self.module, self.warmup = step_fn, module, warmup
+    def __init__(self, step_fn: Callable, example_inputs: Sequence[torch.Tensor], module: Optional[torch.nn.Module] = None, warmup: int = 3):
+        self.step_fn, self.module, self.warmup = step_fn, module, max(int(warmup), 2 if E.grad_arena is not None else 1)
         self.static_inputs = [t.clone() for t in example_inputs]
         self.graph = None
         self.recapture()
@@ -53,8 +48,13 @@ class GraphedStep:
         graph = torch.cuda.CUDAGraph()
         l0 = E.launch_count
         E.reset_stats_pool()                     # zero-once accumulator chunks must be created (and zeroed) inside the graph
-        with torch.cuda.graph(graph):
-            self.static_outputs = self.step_fn(*self.static_inputs)
+        # scratch workspaces whose addresses the captured kernels carry stay alive as long as this graph does
+        self._workspaces = E.begin_capture_refs()
+        try:
+            with torch.cuda.graph(graph):
+                self.static_outputs = self.step_fn(*self.static_inputs)
+        finally:
+            E.end_capture_refs()
         E.reset_stats_pool()                     # ... and must not leak into eager code afterwards
         self.launches = E.launch_count - l0
         self.graph = graph

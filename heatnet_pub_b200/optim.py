@@ -30,14 +30,27 @@ class _FusedOptimizer(torch.optim.Optimizer):
         self.max_norm = max_norm
         self.grad_scale = float(grad_scale)
         self._tables = {}
+        self._spares = {}
         self.last_sqnorm = None
 
     # ---- device tables: slots (param, grad, state1, state2, numel) and the block -> (slot, chunk) map
+    EAGER_TABLES = 2          # eager-built table sets kept per param group (gradient tensors outside an arena move every step)
+
     def _table(self, gi, live, states):
+        """Table set for this exact set of addresses.  A set is IMMUTABLE once built: its pinned staging buffers are written
+        once and never reused for other contents, because a CUDA graph that captured the H2D copy re-reads them on every replay
+        (and its kernels read the device tables).  Sets built during a capture are therefore kept for good (the graph needs
+        them as long as it lives); sets built eagerly are kept in a small LRU.  With a gradient arena
+        (parallel.GradientReducer) the addresses never change and one set serves eager steps and captures alike."""
         key = tuple((p.data_ptr(), p.grad.data_ptr(), *(s.data_ptr() if s is not None else 0 for s in st)) for p, st in zip(live, states))
-        hit = self._tables.get(gi)
-        if hit is not None and hit[0] == key:
-            return hit[1:5]
+        cache = self._tables.setdefault(gi, {})
+        hit = cache.get(key)
+        if hit is not None:
+            if torch.cuda.is_current_stream_capturing():
+                hit["captured"] = True                 # a graph now points at these tables: never evict
+            elif not hit["captured"]:
+                cache[key] = cache.pop(key)            # LRU order
+            return hit["slots_d"], hit["bmap_d"], hit["partial"], hit["nblocks"]
         chunk = _lib.load().hn_optim_chunk()
         slots = np.zeros((len(live), 5), dtype=np.int64)
         blocks = []
@@ -47,28 +60,33 @@ class _FusedOptimizer(torch.optim.Optimizer):
             blocks.append(np.stack([np.full(nchunk, i, dtype=np.int32), np.arange(nchunk, dtype=np.int32)], axis=1))
         bmap = np.concatenate(blocks, axis=0) if blocks else np.zeros((0, 2), dtype=np.int32)
         dev = live[0].device
-        # The tables travel through PINNED staging buffers with asynchronous copies: no host sync per rebuild (gradient tensors
-        # are new allocations every step, so their addresses can change), and a rebuild inside a CUDA-graph capture
-        # (graphs.GraphedStep: the gradients then live in the graph's pool) is a capturable memcpy node.  Buffers are allocated
-        # on the first (eager) call for a given live set and reused.
-        shape_key = (len(live), bmap.shape[0])
-        buf = hit[5] if (hit is not None and len(hit) > 5 and hit[5][0] == shape_key) else None
-        if buf is None:
-            buf = (shape_key, torch.empty((len(live), 5), dtype=torch.int64).pin_memory(), torch.empty((max(bmap.shape[0], 1), 2), dtype=torch.int32).pin_memory(),
-                   torch.empty((len(live), 5), dtype=torch.int64, device=dev), torch.empty((max(bmap.shape[0], 1), 2), dtype=torch.int32, device=dev),
-                   torch.empty(bmap.shape[0] + 1, dtype=torch.float64, device=dev), torch.cuda.Event())
-        _, slots_h, bmap_h, slots_d, bmap_d, partial, done = buf
-        if not torch.cuda.is_current_stream_capturing():
-            done.synchronize()                      # the previous copy out of the staging buffers has finished
+        capturing = torch.cuda.is_current_stream_capturing()
+        # the tables travel through PINNED staging buffers with asynchronous copies: no host sync per rebuild, and a rebuild
+        # inside a capture is a memcpy node
+        # (pinned memory cannot be allocated while a stream is capturing: every eager build leaves one spare pair of this
+        # shape behind for a capture to take over -- graphs.GraphedStep always runs the step eagerly first)
+        shape_key = (len(live), max(bmap.shape[0], 1))
+        spares = self._spares.setdefault((gi, shape_key), [])
+        if capturing and spares:
+            slots_h, bmap_h = spares.pop()
+        else:
+            slots_h = torch.empty((shape_key[0], 5), dtype=torch.int64).pin_memory()
+            bmap_h = torch.empty((shape_key[1], 2), dtype=torch.int32).pin_memory()
+        if not capturing and not spares:
+            spares.append((torch.empty((shape_key[0], 5), dtype=torch.int64).pin_memory(), torch.empty((shape_key[1], 2), dtype=torch.int32).pin_memory()))
         slots_h.numpy()[...] = slots
         if bmap.shape[0]:
-            bmap_h.numpy()[:bmap.shape[0]] = bmap
-        slots_d.copy_(slots_h, non_blocking=True)
-        bmap_d.copy_(bmap_h, non_blocking=True)
-        if not torch.cuda.is_current_stream_capturing():
-            done.record()
-        self._tables[gi] = (key, slots_d, bmap_d, partial, bmap.shape[0], buf)
-        return slots_d, bmap_d, partial, bmap.shape[0]
+            bmap_h.numpy()[...] = bmap
+        ent = {"slots_h": slots_h, "bmap_h": bmap_h, "captured": capturing, "nblocks": bmap.shape[0],
+               "slots_d": torch.empty(slots_h.shape, dtype=torch.int64, device=dev), "bmap_d": torch.empty(bmap_h.shape, dtype=torch.int32, device=dev),
+               "partial": torch.empty(bmap.shape[0] + 1, dtype=torch.float64, device=dev)}
+        ent["slots_d"].copy_(slots_h, non_blocking=True)
+        ent["bmap_d"].copy_(bmap_h, non_blocking=True)
+        cache[key] = ent
+        eager = [k for k, v in cache.items() if not v["captured"]]
+        for k in eager[:max(0, len(eager) - self.EAGER_TABLES)]:
+            del cache[k]
+        return ent["slots_d"], ent["bmap_d"], ent["partial"], ent["nblocks"]
 
     def _live(self, group):
         live = []

@@ -250,12 +250,16 @@ class PSPNet(_KernelModule):
             graph = torch.cuda.CUDAGraph()
             l0 = E.launch_count
             E.reset_stats_pool()
-            with torch.cuda.graph(graph):
-                out = self._forward_eager(s1, s2)
+            ws_refs = E.begin_capture_refs()          # the scratch buffers the captured kernels point at live as long as the graph
+            try:
+                with torch.cuda.graph(graph):
+                    out = self._forward_eager(s1, s2)
+            finally:
+                E.end_capture_refs()
             E.reset_stats_pool()
-            entry = (graph, s1, s2, out, E.launch_count - l0, ver)
+            entry = (graph, s1, s2, out, E.launch_count - l0, ver, ws_refs)
             self._graphs[key] = entry
-        graph, s1, s2, out, launches, _ = entry
+        graph, s1, s2, out, launches = entry[:5]
         s1.copy_(modal_1)
         if s2 is not None:
             s2.copy_(modal_2)

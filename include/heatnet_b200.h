@@ -149,6 +149,11 @@ int hn_bilinear_sum_fwd(const hn_tensor *xs, int32_t nsrc, const hn_tensor *y, v
  * per_image=1 and shift=NULL the nn.Dropout2d channel mask of cm/models/pspnet.py:64-73):
  * y = act(x*scale[c] + shift[c] + residual) */
 int hn_affine_act(const hn_tensor *x, const hn_epilogue *ep, const hn_tensor *y, void *stream);
+/* nn.Dropout2d channel masks (cm/models/pspnet.py:49,55,64-73) as the [N*C] scale vector hn_affine_act(per_image=1) applies:
+ * scale_out[i] = u_i >= p ? 1/(1-p) : 0 (all zeros for p == 1, like torch), u_i = 24-bit uniform from Philox4x32-10 keyed by
+ * state_dev[0] (seed) with counter (state_dev[1], i).  The kernel increments state_dev[1] itself, so every call -- including every
+ * replay of a captured CUDA graph -- draws a new mask, and a given seed reproduces the whole sequence. */
+int hn_dropout2d_scale(uint64_t *state_dev, int64_t n, float p, float *scale_out, void *stream);
 /* per-channel sum / sum of squares over all pixels (BatchNorm2d batch statistics), FP64 accumulators */
 int hn_channel_stats(const hn_tensor *x, double *sum, double *sqsum, void *stream);
 /* train-mode BatchNorm2d finalize (cm/models/extractors.py:72-77): from FP64 sums over `count` pixels

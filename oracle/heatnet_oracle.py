@@ -66,6 +66,8 @@ def dropout2d(x: Tensor, p: float, training: bool, mask: Optional[Tensor]) -> Te
         return x
     if mask is None:
         return F.dropout2d(x, p, True)
+    if p >= 1.0:                                   # torch: every channel dropped, zeros (not 0 * inf)
+        return torch.zeros_like(x)
     return x * (mask.to(x.dtype) / (1.0 - p))[:, :, None, None]
 
 

@@ -87,6 +87,10 @@ def test_conv_dgrad_wgrad_fp32(E, case):
     assert rel(back(dx), dx_ref) < FP32_TOL
     dw = E.conv2d_wgrad(to_act(E, x, torch.float32), dya, convg)
     assert rel(dw.cpu(), dw_ref) < FP32_TOL
+    # second contribution accumulated into existing storage (a gradient-arena slot; the 1x1 layers accumulate in the kernel)
+    prev = torch.randn(dw.shape, generator=torch.Generator().manual_seed(2)).cuda()
+    acc = E.conv2d_wgrad(to_act(E, x, torch.float32), dya, convg, out=prev.clone(), accumulate=True)
+    assert rel((acc - prev).cpu(), dw_ref) < 2 * FP32_TOL
 
 
 def _padded_act(E, t, dtype):
@@ -112,6 +116,9 @@ def test_conv_dgrad_wgrad_bf16_tensor_core(E, case):
     assert dw.dtype == torch.float32
     assert rel(dw.cpu(), dw_r) < 2e-3            # FP32 accumulation of BF16 products
     assert rel(dw.cpu(), dw_ref) < BF16_TOL
+    prev = torch.randn(dw.shape, generator=torch.Generator().manual_seed(2)).cuda()
+    acc = E.conv2d_wgrad(to_act(E, x, torch.bfloat16), dya, convg, out=prev.clone(), accumulate=True)
+    assert rel((acc - prev).cpu(), dw_r) < 4e-3
 
 
 def test_dgrad_accumulates_through_epilogue(E):
@@ -145,9 +152,22 @@ def test_bn_train_backward(E, dtype, tol, act):
     invstd = 1.0 / torch.sqrt(raw.detach().var((0, 2, 3), unbiased=False) + 1e-5)
     code = {"relu": E.ACT_RELU, "prelu": E.ACT_LEAKY, "none": E.ACT_NONE}[act]
     dres = E.new_act(N, H, W, Cc, dtype, "cuda") if res is not None else None
-    draw, pg = E.bn_bwd(to_act(E, dout, dtype), to_act(E, out.detach(), dtype), to_act(E, raw.detach(), torch.float32), mean.cuda(),
-                          invstd.cuda(), gamma.detach().cuda(), code, slope_ptr=slope.detach().cuda() if act == "prelu" else None,
-                          dres=dres, want_prelu_grad=(act == "prelu"))
+    def sinks(prefill=None):
+        """(tensor, accumulate) for dbeta, dgamma, dslope; with `prefill` the kernel adds to existing contents"""
+        ts = [torch.full((Cc,), prefill or 0.0, device="cuda"), torch.full((Cc,), prefill or 0.0, device="cuda"),
+              torch.full((1,), prefill or 0.0, device="cuda") if act == "prelu" else None]
+        return [(t, prefill is not None) for t in ts]
+
+    sk = sinks()
+    draw = E.bn_bwd(to_act(E, dout, dtype), to_act(E, out.detach(), dtype), to_act(E, raw.detach(), torch.float32), mean.cuda(),
+                    invstd.cuda(), gamma.detach().cuda(), code, slope_ptr=slope.detach().cuda() if act == "prelu" else None,
+                    dres=dres, sinks=sk)
+    pg = [t for t, _ in sk]
+    # second contribution into the same parameter-gradient storage (the net runs on the day and on the night batch)
+    sk_acc = sinks(prefill=2.0)
+    E.bn_bwd(to_act(E, dout, dtype), to_act(E, out.detach(), dtype), to_act(E, raw.detach(), torch.float32), mean.cuda(),
+             invstd.cuda(), gamma.detach().cuda(), code, slope_ptr=slope.detach().cuda() if act == "prelu" else None, sinks=sk_acc)
+    assert torch.allclose(sk_acc[0][0], pg[0] + 2.0, rtol=1e-5, atol=1e-5) and torch.allclose(sk_acc[1][0], pg[1] + 2.0, rtol=1e-5, atol=1e-5)
     assert rel(back(draw), raw.grad) < tol
     assert rel(pg[0].cpu(), beta.grad) < tol and rel(pg[1].cpu(), gamma.grad) < tol
     if res is not None:
@@ -156,9 +176,11 @@ def test_bn_train_backward(E, dtype, tol, act):
         # without a residual the saved output need not be read: z is recomputed from raw with the forward's scale / shift
         fscale = (gamma.detach() * invstd).cuda()
         fshift = (beta.detach() - mean * gamma.detach() * invstd).cuda()
-        draw2, pg2 = E.bn_bwd(to_act(E, dout, dtype), to_act(E, out.detach(), dtype), to_act(E, raw.detach(), torch.float32), mean.cuda(),
-                              invstd.cuda(), gamma.detach().cuda(), code, slope_ptr=slope.detach().cuda() if act == "prelu" else None,
-                              want_prelu_grad=(act == "prelu"), fwd_scale=fscale, fwd_shift=fshift)
+        sk2 = sinks()
+        draw2 = E.bn_bwd(to_act(E, dout, dtype), to_act(E, out.detach(), dtype), to_act(E, raw.detach(), torch.float32), mean.cuda(),
+                         invstd.cuda(), gamma.detach().cuda(), code, slope_ptr=slope.detach().cuda() if act == "prelu" else None,
+                         sinks=sk2, fwd_scale=fscale, fwd_shift=fshift)
+        pg2 = [t for t, _ in sk2]
         assert rel(back(draw2), raw.grad) < tol
         assert rel(pg2[0].cpu(), beta.grad) < tol and rel(pg2[1].cpu(), gamma.grad) < tol
         if act == "prelu":

@@ -241,3 +241,28 @@ def test_cuda_graph_replay_matches_eager():
     net.set_cuda_graph(True)
     net.train()
     assert not net._graph_ok(rgb, ir)
+
+
+def test_graph_replay_after_workspace_growth():
+    """A captured forward keeps the scratch workspace it was captured with alive: capture shape A (strided / small-Cin convs use
+    the im2col workspace), run a LARGER shape eagerly so the grow-only workspace is re-allocated, allocate over the freed
+    block, replay A -- results must still equal eager A."""
+    from heatnet_pub_b200 import engine as E
+    net = _late_net(seed=3).eval().set_precision("bf16")
+    rgb, ir = O.synthetic_inputs(1, 64, 96)
+    rgb, ir = rgb.cuda(), ir.cuda()
+    with torch.no_grad():
+        want = net(rgb, ir)[0].clone()
+        net.set_cuda_graph(True)
+        assert torch.equal(net(rgb, ir)[0], want)
+        ws_small = E._workspace[torch.cuda.current_device()]
+        net._graph_enabled = False                           # eager, but keep the captured graph (set_cuda_graph() would drop it)
+        big_rgb, big_ir = O.synthetic_inputs(2, 256, 384)
+        net(big_rgb.cuda(), big_ir.cuda())
+        ws_big = E._workspace[torch.cuda.current_device()]
+        if ws_big is ws_small:
+            pytest.skip("workspace did not grow for the larger shape")
+        junk = [torch.full((ws_small.numel() // 4,), float("nan"), device="cuda") for _ in range(4)]     # would land on a freed block
+        net._graph_enabled = True
+        assert torch.equal(net(rgb, ir)[0], want)
+        del junk

@@ -110,3 +110,51 @@ def test_argument_errors():
         optim.RMSprop(p, lr=-1.0)
     with pytest.raises(ValueError):
         optim.Adam(p, betas=(1.0, 0.9))
+
+
+def test_captured_step_survives_interleaved_eager_steps():
+    """A captured optimizer step keeps its own (immutable) slot tables: graph replay -> eager step on NEW gradient tensors ->
+    graph replay again must equal the all-eager sequence.  (Round-1 shared one pinned staging buffer between eager steps and
+    captures: the eager step overwrote the addresses the graph's H2D node re-reads.)"""
+    from heatnet_pub_b200 import optim
+    steps = 4
+
+    def make():
+        ps = [torch.nn.Parameter(p.cuda()) for p in _params(3)]
+        return ps, optim.RMSprop(ps, lr=1e-2)
+
+    # all-eager reference: gradients g0, g1, g2, g3
+    ps_ref, opt_ref = make()
+    for s in range(steps):
+        for p, g in zip(ps_ref, _grads(s, 5)):
+            p.grad = g.cuda()
+        opt_ref.step()
+    # graph for steps 0 and 2 (static gradient tensors), eager steps 1 and 3 on fresh gradient tensors
+    ps, opt = make()
+    static = [torch.zeros_like(p) for p in ps]
+    for p, g in zip(ps, static):
+        p.grad = g
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        opt.step()        # warm-up with all-zero gradients: RMSprop leaves parameters and square_avg untouched (0 / (0 + eps))
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        opt.step()
+    for s in range(steps):
+        gs = _grads(s, 5)
+        if s % 2 == 0:
+            for st, g in zip(static, gs):
+                st.copy_(g.cuda())
+            for p, st in zip(ps, static):
+                p.grad = st
+            graph.replay()
+        else:
+            for p, g in zip(ps, gs):
+                p.grad = g.cuda().clone()                  # new addresses: the eager path builds (and may evict) its own tables
+            opt.step()
+    torch.cuda.synchronize()
+    for a, b in zip(ps_ref, ps):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-7)

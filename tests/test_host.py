@@ -189,5 +189,120 @@ def test_bench_reference_arm_prints_one_contract_line():
                 "config", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["impl"] == "reference" and d["metric"] == "rgb_thermal_seg_images_per_sec" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    from oracle import reference_loader as RL
+    # the unmodified reference modules when baseline/_ref travelled with the snapshot, the oracle port otherwise
+    assert d["cpu_baseline"]["kind"] == ("reference" if RL.available() else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_reference_install_matches_the_oracle_bit_for_bit():
+    """baseline/_ref (file-level install of the reference's hot-path modules) imports cleanly next to this package, and the
+    reference's own PSPNet.eval() forward equals the oracle restatement bit for bit on the same weights and frame."""
+    from oracle import reference_loader as RL
+    if not RL.available():
+        pytest.skip("baseline/_ref not installed")
+    PSPNet = RL.load_cm_pspnet()
+    net = PSPNet(sizes=(1, 2, 3, 6), psp_size=2048, deep_features_size=1024, backend='resnet50', in_channels=4, pretrained=False, late_fusion=True)
+    sd = O.recipe_fill(O.pspnet_state_dict(True, 4), seed=0)
+    net.load_state_dict(sd)
+    net.eval()
+    rgb, ir = O.synthetic_inputs(1, 32, 64)
+    import warnings
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = net(rgb, ir)[0]
+        b = O.pspnet_forward(sd, rgb, ir, late_fusion=True, training=False)[0]
+    assert torch.equal(a, b)
+    assert "models" not in __import__("sys").modules or not getattr(__import__("sys").modules["models"], "__file__", "").startswith(RL.REF_DIR)
+
+
+# ---------------------------------------------------------------------------------------------------- checkpoint I/O (SURVEY 8f-3)
+def test_checkpoint_helpers_roundtrip(tmp_path, monkeypatch, capsys):
+    """utils.initModelRenamed / Partial / Full (cm/utils.py:59-90) on the on-disk formats the trainers write: a DataParallel
+    `'module.trgb_segnet.'`-prefixed {'state_dict': ...} checkpoint (cm/train_trgb_segnet_conf.py:643-655), the
+    `<name>_<epoch>` snapshot convention of build_network (models/build_net.py:23-26, both signatures), and an
+    optimizer + StepLR resume (cm/train_trgb_segnet_conf.py:276-283)."""
+    from heatnet_pub_b200 import build_net, pspnet, utils
+    monkeypatch.setattr(nn.Module, "cuda", lambda self, *a, **k: self)
+    sd = O.recipe_fill(O.pspnet_state_dict(True, 4), seed=4)
+
+    def fresh():
+        return pspnet.PSPNet(sizes=(1, 2, 3, 6), psp_size=2048, deep_features_size=1024, backend='resnet50', in_channels=4,
+                             pretrained=False, late_fusion=True)
+
+    def same(net):
+        got = net.state_dict()
+        return all(torch.equal(got[k], v) for k, v in sd.items())
+
+    # (1) DataParallel(conv_segnet) checkpoint -> seg net only (train_trgb_segnet_conf.py:231 night-supervision load)
+    ck = {"state_dict": {"module.trgb_segnet." + k: v for k, v in sd.items()}, "epoch": 7, "best_iou": 0.5}
+    ck["state_dict"]["module.critics.0.conv1.weight"] = torch.zeros(64, 13, 4, 4)          # foreign keys are ignored
+    path = str(tmp_path / "checkpoint.pth.tar")
+    torch.save(ck, path)
+    net = fresh()
+    utils.initModelRenamed(net, path, "module.trgb_segnet.", "")
+    assert same(net) and "Loaded dict with 488 entries..." in capsys.readouterr().out
+    # bare state_dict with the plain DataParallel prefix (conf_segnet.py:80)
+    torch.save({"module." + k: v for k, v in sd.items()}, path)
+    net = fresh()
+    utils.initModelRenamed(net, path, "module.", "")
+    assert same(net)
+    with pytest.raises(AssertionError):                       # nothing matches: the reference asserts len > 0
+        utils.initModelRenamed(fresh(), path, "module.", "other.")
+    # (2) partial: only matching keys are taken, the rest keeps its initialisation
+    part = {"state_dict": {k: v for k, v in sd.items() if k.startswith("feats.")} | {"not.a.key": torch.zeros(1)}}
+    torch.save(part, path)
+    net = fresh()
+    before = net.final[0].weight.clone()
+    utils.initModelPartial(net, path)
+    got = net.state_dict()
+    assert all(torch.equal(got[k], v) for k, v in part["state_dict"].items() if k in got) and torch.equal(net.final[0].weight, before)
+    assert "Updated : %d entries" % len([k for k in part["state_dict"] if k in got]) in capsys.readouterr().out
+    # (3) full
+    torch.save(sd, path)
+    net = fresh()
+    utils.initModelFull(net, path)
+    assert same(net)
+    # (4) build_network snapshot convention, HeatNet signature (returns net) and top-level signature (returns (net, epoch))
+    snap = str(tmp_path / "PSPNet_7")
+    torch.save(sd, snap)
+    net = build_net.build_network(snap, 'resnet50', in_channels=4, late_fusion=True)
+    assert isinstance(net, pspnet.PSPNet) and same(net)
+    sd_rgb = O.recipe_fill(O.pspnet_state_dict(False, 3, n_classes=18), seed=6)
+    snap2 = str(tmp_path / "x_12")
+    torch.save(sd_rgb, snap2)
+    monkeypatch.setitem(build_net.models, 'resnet50',
+                        lambda: pspnet.PSPNetRGB(sizes=(1, 2, 3, 6), psp_size=2048, deep_features_size=1024, backend='resnet50', pretrained=False))
+    net2, epoch = build_net.build_network(snap2, 'ResNet50')          # backend is lower-cased like the reference does
+    assert epoch == 12 and isinstance(net2, pspnet.PSPNetRGB)
+    assert all(torch.equal(net2.state_dict()[k], v) for k, v in sd_rgb.items())
+    with pytest.raises(ValueError):                            # 'a_b_3' does not split into exactly (name, epoch): same failure as the reference
+        build_net.build_network(str(tmp_path / "a_b_3"), 'resnet50')
+
+
+def test_optimizer_and_scheduler_resume_roundtrip(tmp_path):
+    """cm/train_trgb_segnet_conf.py:276-283,643-655: checkpoint = {'state_dict', 'optimizer', 'lr_scheduler', 'epoch',
+    'best_iou'}; the fused RMSprop's state_dict loads into torch.optim.RMSprop and back (same keys), StepLR halves its lr."""
+    from heatnet_pub_b200 import optim
+    ps = [nn.Parameter(torch.randn(4, 3)), nn.Parameter(torch.randn(5))]
+    opt = optim.RMSprop(ps, lr=1e-3)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=2, gamma=0.5)
+    for p in ps:                                              # fabricate the state a few steps would leave (no GPU in this test)
+        opt.state[p] = {"step": torch.tensor(3.0), "square_avg": torch.rand_like(p)}
+    for _ in range(2):
+        sched.step()
+    assert opt.param_groups[0]["lr"] == pytest.approx(5e-4)
+    path = str(tmp_path / "ck.pth.tar")
+    torch.save({"optimizer": opt.state_dict(), "lr_scheduler": sched.state_dict(), "epoch": 2, "best_iou": 0.1}, path)
+    ck = torch.load(path)
+    ps2 = [nn.Parameter(p.detach().clone()) for p in ps]
+    opt2 = optim.RMSprop(ps2, lr=1e-3)
+    sched2 = torch.optim.lr_scheduler.StepLR(opt2, step_size=2, gamma=0.5)
+    opt2.load_state_dict(ck["optimizer"])
+    sched2.load_state_dict(ck["lr_scheduler"])
+    assert opt2.param_groups[0]["lr"] == pytest.approx(5e-4) and sched2.last_epoch == 2
+    for a, b in zip(ps, ps2):
+        assert torch.equal(opt.state[a]["square_avg"], opt2.state[b]["square_avg"]) and float(opt2.state[b]["step"]) == 3.0
+    ref = torch.optim.RMSprop([nn.Parameter(p.detach().clone()) for p in ps], lr=1e-3)       # and into stock torch
+    ref.load_state_dict(ck["optimizer"])
+    assert ref.param_groups[0]["lr"] == pytest.approx(5e-4)

@@ -221,3 +221,18 @@ def test_inputs_oracle_matches_torchvision():
     want_ir = tvf.normalize(tvf.to_tensor(x), mean=[0.5], std=[0.5]).float()
     assert torch.equal(IO.load_ir(ir), want_ir)
     assert want_ir.min() == -1.0 and want_ir.max() == 1.0
+
+
+def test_philox_known_answers():
+    """oracle/random_oracle.py against the known-answer vectors of the Random123 distribution (philox4x32, 10 rounds)."""
+    from oracle import random_oracle as R
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        assert tuple(int(v) for v in R.philox4x32_10(np.array(ctr), key)) == want
+    s = R.dropout2d_scale(99, 3, 20000, 0.3)
+    assert set(np.unique(s).tolist()) == {0.0, float(np.float32(1.0) / (np.float32(1.0) - np.float32(0.3)))}
+    assert abs((s > 0).mean() - 0.7) < 0.01
+    assert not np.array_equal(s, R.dropout2d_scale(99, 4, 20000, 0.3))
+    assert np.count_nonzero(R.dropout2d_scale(99, 0, 100, 1.0)) == 0
