@@ -430,7 +430,7 @@ def measure_train(ctx, args, workload, B, H, W, steps, warmup):
         scale = (H * W) / (320.0 * 640.0)
         tflops = TRAIN_GFLOP_PER_PAIR_320x640[workload] * scale * B * steps / (ms / 1000.0) / 1e3
         res = {"images_per_s": 2 * B * world * steps / (ms / 1000.0), "ms_per_step": ms / steps, "steps": steps, "per_gpu_pairs": B,
-               "global_pairs": B * world, "height": H, "width": W, "cuda_graph": bool(use_graph), "loss": float(loss), "gpu_launches": launches,
+               "global_pairs": B * world, "height": H, "width": W, "cuda_graph": bool(use_graph), "loss": float(loss.detach()), "gpu_launches": launches,
                "tflops_per_gpu": tflops, "frac_of_sustained_peak": tflops / peak, "frac_of_burst_peak": tflops / peaks["bf16_tflops"],
                "peak_source": peak_src, "clocks": clocks,
                "what": f"conv_segnet {workload} step (PSPNet-ResNet50 late fusion + 6 FCDiscriminator critics), {B} day+night pairs per GPU at "

@@ -70,7 +70,7 @@ def test_dropout2d_op_semantics(p):
     from heatnet_pub_b200 import engine as E
     g = torch.Generator().manual_seed(1)
     x = torch.randn(3, 40, 5, 7, generator=g)
-    mask = (torch.rand(3, 40, generator=g) >= 0.4).float()
+    mask = (torch.rand(3, 40, generator=g) >= 0.4).float() if p > 0.0 else torch.ones(3, 40)     # p = 0: nn.Dropout2d is the identity
     for dtype in (torch.float32, torch.bfloat16):
         a = E.from_nchw(x.cuda(), dtype)
         y = E.dropout2d(a, p, mask).nchw().float().cpu()
