@@ -24,6 +24,12 @@ class HnEpilogue(C.Structure):
                 ("stat_sum", C.c_void_p), ("stat_sqsum", C.c_void_p), ("per_image", C.c_int32)]
 
 
+class HnPackJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("cout", C.c_int32), ("cin", C.c_int32), ("r", C.c_int32), ("s", C.c_int32),
+                ("rows_pad", C.c_int32), ("kpad", C.c_int32), ("kind", C.c_int32), ("dtype", C.c_int32), ("ty", C.c_int32), ("tx", C.c_int32),
+                ("phiy", C.c_int32), ("phix", C.c_int32)]
+
+
 class HnConv(C.Structure):
     _fields_ = [("cout", C.c_int32), ("r", C.c_int32), ("s", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
                 ("dil", C.c_int32)]
@@ -60,6 +66,7 @@ SIGNATURES = {
     "hn_channel_stats": (C.c_int, [_T, _P, _P, _P]),
     "hn_bn_finalize": (C.c_int, [_P, _P, _I64, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _I32, _P]),
     "hn_bn_finalize_tracked": (C.c_int, [_P, _P, _I64, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _I32, _P]),
+    "hn_bn_apply_train": (C.c_int, [_T, _P, _P, _I64, _P, _P, _F, _F, _P, _P, _P, _E, _T, _P, _P, _P, _P, _P]),
     "hn_act_bwd": (C.c_int, [_T, _T, _I32, _F, _T, _P]),
     "hn_bn_bwd": (C.c_int, [_T, _T, _T, _P, _P, _P, _I32, _F, _P, _P, _T, _T, _I32, _I32, _P, _P, _P, _I32, _P, _P, _P]),
     "hn_stem_pad_slack_bytes": (_I64, []),
@@ -77,6 +84,13 @@ SIGNATURES = {
     "hn_pyramid_pool_bwd": (C.c_int, [_P, C.POINTER(_I32), _I32, _T, _I32, _P]),
     "hn_dilate": (C.c_int, [_T, _I32, _T, _P]),
     "hn_pack_weight_dgrad": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "hn_dgrad_s2_phase_kpad": (_I32, [_I32, _I32, _I32, _I32, _I32]),
+    "hn_pack_weight_dgrad_phase": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "hn_conv2d_dgrad_s2_ok": (C.c_int, [_T, _CV, _T]),
+    "hn_conv2d_dgrad_s2": (C.c_int, [_T, _P, _CV, _T, _I32, _P]),
+    "hn_pack_chunk": (_I32, []),
+    "hn_pack_job_init": (C.c_int, [C.POINTER(HnPackJob), _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32]),
+    "hn_pack_weights_multi": (C.c_int, [_P, _P, _I32, _P]),
     "hn_conv2d_wgrad_workspace_bytes": (_I64, [_T, _CV]),
     "hn_conv2d_wgrad": (C.c_int, [_T, _T, _CV, _P, _I32, _P, _I64, _P]),
     "hn_unpack_wgrad": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
@@ -119,7 +133,7 @@ def load():
 timeline = None
 _NO_TIMING = {"hn_last_error", "hn_version", "hn_device_check", "hn_prof_read", "hn_conv_cout_pad", "hn_conv_kpad", "hn_optim_chunk",
               "hn_conv2d_workspace_bytes", "hn_conv2d_wgrad_workspace_bytes", "hn_pyramid_pool_workspace_bytes",
-              "hn_bilinear_bwd_workspace_bytes", "hn_loss_scratch_bytes", "hn_bn_batch_stats_scratch_bytes", "hn_stem_pad_slack_bytes"}
+              "hn_bilinear_bwd_workspace_bytes", "hn_dgrad_s2_phase_kpad", "hn_conv2d_dgrad_s2_ok", "hn_pack_chunk", "hn_pack_job_init", "hn_loss_scratch_bytes", "hn_bn_batch_stats_scratch_bytes", "hn_stem_pad_slack_bytes"}
 
 
 def _describe(name, args):

@@ -67,9 +67,11 @@ extern "C" int hn_conv2d_fwd(const hn_tensor *x, const void *w_packed, const hn_
     HN_CHECK_ARG((ep->stat_sum != nullptr) == (ep->stat_sqsum != nullptr), "hn_conv2d_fwd: give both statistics accumulators or neither");
     if (ep->stat_sum) {
         const int cp = hn_conv_cout_pad(cv->cout, x->dtype);
-        HN_CHECK_ARG(x->dtype == HN_BF16 && y->dtype == HN_F32 && cp >= 32 && (reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0 && (y->ld * 4) % 16 == 0 &&
-                         !ep->residual && ep->act == HN_ACT_NONE,
-                     "hn_conv2d_fwd: fused statistics need the BF16 engine, an aligned FP32 output view, Cout >= 17, no residual / activation");
+        const size_t esz = elsize(y->dtype);
+        HN_CHECK_ARG(x->dtype == HN_BF16 && cp >= 32 && (reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0 && (y->ld * esz) % 16 == 0 &&
+                         !ep->residual && ep->act == HN_ACT_NONE && (y->dtype == HN_F32 || !ep->scale),
+                     "hn_conv2d_fwd: fused statistics need the BF16 engine, a 16-byte aligned output view, Cout >= 17, no residual / activation "
+                     "(and no explicit scale with a BF16 output)");
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (x->dtype == HN_F32) {

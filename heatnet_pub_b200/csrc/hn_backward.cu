@@ -2,9 +2,12 @@
 // (saved window indices), bilinear and pyramid-pool adjoints (gather form: deterministic, no atomics),
 // zero-insertion for strided-conv dgrad, gradient unpack/accumulate into the OIHW FP32 masters.
 // Same conventions as hn_bandwidth.cu: 8 channels per thread, row-decomposed grids, no 64-bit div/mod per element.
+#include <string.h>
+
 #include "hn_common.cuh"
 
 namespace hn {
+using bf16_t = __nv_bfloat16;
 
 static inline dim3 row_grid_b(int64_t rows, int64_t items_per_row, int threads = 256)
 {
@@ -776,6 +779,103 @@ __global__ void __launch_bounds__(256) pack_weight_dgrad_kernel(const float *__r
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stride-2 dgrad by parity phases.  Forward: y[o] = sum_r x[2o - pad + r] w[r].  For input position i = 2m + rho only the taps
+// r = phi, phi + 2, ... (phi = (rho + pad) mod 2) can reach it, from o = m + delta - t with r = phi + 2t, delta = (rho + pad - phi)/2:
+//     dx[2m + rho] = sum_{u=0}^{T-1} dy[m - pad' + u] * w[phi + 2(T-1-u)],   T = ceil((k - phi)/2),  pad' = T - 1 - delta
+// i.e. a stride-1 correlation of dY with a T-tap sub-filter, per axis.  The four (rho_y, rho_x) phases together touch every
+// filter tap exactly once: k*k tap evaluations per output pixel QUAD instead of 4*k*k on the zero-inserted gradient.
+// ------------------------------------------------------------------------------------------------
+struct PhaseAxis { int T, padp, phi, count; };     // taps, padding, first filter tap, lattice extent
+static PhaseAxis phase_axis(int rho, int k, int pad, int in_size)
+{
+    PhaseAxis a;
+    a.phi = (rho + pad) & 1;
+    a.T = a.phi < k ? (k - a.phi + 1) / 2 : 0;
+    const int delta = (rho + pad - a.phi) / 2;
+    a.padp = a.T - 1 - delta;
+    a.count = in_size > rho ? (in_size - rho + 1) / 2 : 0;
+    return a;
+}
+
+// sub-filter pack of one phase: dst[c][k], k = (uy*Tx + ux)*Cout + o  <-  w[o][c][phi_y + 2(Ty-1-uy)][phi_x + 2(Tx-1-ux)]
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weight_dgrad_phase_kernel(const float *__restrict__ w, T *__restrict__ dst, int cout, int cin, int R,
+                                                                      int S, int Ty, int Tx, int phiy, int phix, int cin_pad, int kpad)
+{
+    const int64_t total = (int64_t)cin_pad * kpad;
+    const int K = Ty * Tx * cout;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int ci = (int)(i / kpad), k = (int)(i - (int64_t)ci * kpad);
+        float v = 0.f;
+        if (ci < cin && k < K) {
+            int tap = k / cout, o = k - tap * cout;
+            int uy = tap / Tx, ux = tap - uy * Tx;
+            int r = phiy + 2 * (Ty - 1 - uy), s2 = phix + 2 * (Tx - 1 - ux);
+            v = __ldg(w + (((int64_t)o * cin + ci) * R + r) * S + s2);
+        }
+        dst[i] = from_f32<T>(v);
+    }
+}
+
+// zeros on one parity lattice of an NHWC view (phases no filter tap reaches, e.g. three of the four of a 1x1 stride-2 conv)
+template <typename T>
+__global__ void __launch_bounds__(256) zero_lattice_kernel(T *__restrict__ y, int64_t pix_stride, int64_t row_stride, int64_t img_stride, int N,
+                                                           int Hl, int Wl, int C)
+{
+    const int64_t total = (int64_t)N * Hl * Wl * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        int64_t q = i / C;
+        int wl = (int)(q % Wl), hl = (int)((q / Wl) % Hl), n = (int)(q / ((int64_t)Wl * Hl));
+        y[n * img_stride + hl * row_stride + wl * pix_stride + c] = from_f32<T>(0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// All weight packs of a training step in ONE launch (hn_pack_weights_multi): after every optimizer step each live convolution
+// needs its forward pack, its dgrad pack and (stride 2) its phase packs rebuilt from the FP32 master -- ~170 tiny launches per
+// step otherwise.  A block handles PACK_CHUNK consecutive destination elements of one job (block_map: job, chunk).
+// ------------------------------------------------------------------------------------------------
+constexpr int PACK_CHUNK = 4096;
+
+__device__ __forceinline__ float pack_source(const hn_pack_job &j, int row, int k)
+{
+    // row = destination row, k = destination column; returns the master-weight element that belongs there (0 for padding)
+    if (j.kind == 0) {                                   // forward: [cout_pad][kpad], k = (r*S+s)*Cin + c
+        if (row >= j.cout || k >= j.r * j.s * j.cin) return 0.f;
+        const int tap = k / j.cin, c = k - tap * j.cin;
+        const int r = tap / j.s, s2 = tap - r * j.s;
+        return __ldg(j.src + (((int64_t)row * j.cin + c) * j.r + r) * j.s + s2);
+    }
+    if (j.kind == 1) {                                   // dgrad: [cin_pad][kpad'], k' = ((R-1-r)*S + (S-1-s))*Cout + o
+        if (row >= j.cin || k >= j.r * j.s * j.cout) return 0.f;
+        const int tap = k / j.cout, o = k - tap * j.cout;
+        const int rf = tap / j.s, sf = tap - rf * j.s;
+        return __ldg(j.src + (((int64_t)o * j.cin + row) * j.r + (j.r - 1 - rf)) * j.s + (j.s - 1 - sf));
+    }
+    // kind 2: stride-2 dgrad phase: [cin_pad][kpad''], k'' = (uy*Tx + ux)*Cout + o  (ty, tx, phiy, phix precomputed by the host)
+    if (row >= j.cin || k >= j.ty * j.tx * j.cout) return 0.f;
+    const int tap = k / j.cout, o = k - tap * j.cout;
+    const int uy = tap / j.tx, ux = tap - uy * j.tx;
+    return __ldg(j.src + (((int64_t)o * j.cin + row) * j.r + (j.phiy + 2 * (j.ty - 1 - uy))) * j.s + (j.phix + 2 * (j.tx - 1 - ux)));
+}
+
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const hn_pack_job *__restrict__ jobs, const int32_t *__restrict__ block_map)
+{
+    const hn_pack_job j = jobs[block_map[2 * blockIdx.x]];
+    const int64_t total = (int64_t)j.rows_pad * j.kpad;
+    const int64_t i0 = (int64_t)block_map[2 * blockIdx.x + 1] * PACK_CHUNK;
+    for (int e = threadIdx.x; e < PACK_CHUNK; e += 256) {
+        const int64_t i = i0 + e;
+        if (i >= total) break;
+        const int row = (int)(i / j.kpad), k = (int)(i - (int64_t)row * j.kpad);
+        const float v = pack_source(j, row, k);
+        if (j.dtype == HN_BF16) ((bf16_t *)j.dst)[i] = __float2bfloat16_rn(v);
+        else ((float *)j.dst)[i] = v;
+    }
+}
+
 // f64 -> f32 vector add into a parameter gradient: grad (+)= alpha * src
 __global__ void vec_f64_to_grad_kernel(const double *__restrict__ src, float *__restrict__ grad, int n, int accumulate)
 {
@@ -1057,6 +1157,103 @@ extern "C" int hn_pack_weight_dgrad(const float *w_oihw, void *dst, int32_t dtyp
     int grid = wave_grid_b(total, 256);
     if (dtype == HN_BF16) pack_weight_dgrad_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, (bf16 *)dst, cout, cin, r, s, cin_pad, kpad);
     else pack_weight_dgrad_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, (float *)dst, cout, cin, r, s, cin_pad, kpad);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int32_t hn_dgrad_s2_phase_kpad(int32_t cout, int32_t r, int32_t s, int32_t pad, int32_t phase)
+{
+    const PhaseAxis ay = phase_axis(phase >> 1, r, pad, 2), ax = phase_axis(phase & 1, s, pad, 2);
+    return ay.T * ax.T == 0 ? 0 : hn_conv_kpad(cout, ay.T, ax.T);
+}
+
+extern "C" int hn_pack_weight_dgrad_phase(const float *w_oihw, void *dst, int32_t dtype, int32_t cout, int32_t cin, int32_t r, int32_t s,
+                                          int32_t pad, int32_t phase, int32_t cin_pad, void *stream)
+{
+    HN_CHECK_ARG(w_oihw && dst && cin_pad >= cin && phase >= 0 && phase < 4, "hn_pack_weight_dgrad_phase: bad arguments");
+    const PhaseAxis ay = phase_axis(phase >> 1, r, pad, 2), ax = phase_axis(phase & 1, s, pad, 2);
+    HN_CHECK_ARG(ay.T > 0 && ax.T > 0, "hn_pack_weight_dgrad_phase: phase %d has no taps", phase);
+    const int kpad = hn_conv_kpad(cout, ay.T, ax.T);
+    int64_t total = (int64_t)cin_pad * kpad;
+    int grid = wave_grid_b(total, 256);
+    if (dtype == HN_BF16)
+        pack_weight_dgrad_phase_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, (bf16 *)dst, cout, cin, r, s, ay.T, ax.T, ay.phi, ax.phi, cin_pad, kpad);
+    else
+        pack_weight_dgrad_phase_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, (float *)dst, cout, cin, r, s, ay.T, ax.T, ay.phi, ax.phi, cin_pad, kpad);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_conv2d_dgrad_s2_ok(const hn_tensor *dy, const hn_conv *cv, const hn_tensor *dx)
+{
+    if (!dy || !cv || !dx) return 0;
+    return dy->dtype == HN_BF16 && dx->dtype == HN_BF16 && cv->stride == 2 && cv->dil == 1 && dy->c % 64 == 0 && dy->ld % 8 == 0 &&
+           (reinterpret_cast<uintptr_t>(dy->ptr) & 15) == 0 && dx->ld % 8 == 0 && (reinterpret_cast<uintptr_t>(dx->ptr) & 15) == 0 && cv->pad <= cv->r - 1 &&
+           cv->pad <= cv->s - 1;
+}
+
+extern "C" int hn_conv2d_dgrad_s2(const hn_tensor *dy, const void *const *w_phase, const hn_conv *cv, const hn_tensor *dx, int32_t accumulate,
+                                  void *stream)
+{
+    HN_CHECK_ARG(dy && w_phase && cv && dx && dy->ptr && dx->ptr, "hn_conv2d_dgrad_s2: null pointer");
+    HN_CHECK_ARG(hn_conv2d_dgrad_s2_ok(dy, cv, dx), "hn_conv2d_dgrad_s2: needs BF16, stride 2, dilation 1, dY channels %% 64 == 0, aligned views");
+    HN_CHECK_ARG(dy->n == dx->n && dy->c == cv->cout, "hn_conv2d_dgrad_s2: shape mismatch");
+    HN_CHECK_ARG(dy->h == (dx->h + 2 * cv->pad - cv->r) / 2 + 1 && dy->w == (dx->w + 2 * cv->pad - cv->s) / 2 + 1,
+                 "hn_conv2d_dgrad_s2: dY must be %dx%d for a %dx%d input", (dx->h + 2 * cv->pad - cv->r) / 2 + 1, (dx->w + 2 * cv->pad - cv->s) / 2 + 1,
+                 dx->h, dx->w);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int phase = 0; phase < 4; ++phase) {
+        const int ry = phase >> 1, rx = phase & 1;
+        const PhaseAxis ay = phase_axis(ry, cv->r, cv->pad, dx->h), ax = phase_axis(rx, cv->s, cv->pad, dx->w);
+        if (ay.count == 0 || ax.count == 0) continue;
+        bf16 *base = (bf16 *)dx->ptr + ((int64_t)ry * dx->w + rx) * dx->ld;
+        const int64_t pix = 2 * (int64_t)dx->ld, row = 2 * (int64_t)dx->w * dx->ld, img = (int64_t)dx->h * dx->w * dx->ld;
+        if (ay.T == 0 || ax.T == 0) {
+            if (!accumulate) {
+                const int64_t total = (int64_t)dx->n * ay.count * ax.count * dx->c;
+                zero_lattice_kernel<bf16><<<wave_grid_b(total, 256), 256, 0, st>>>(base, pix, row, img, dx->n, ay.count, ax.count, dx->c);
+                HN_LAUNCH_CHECK();
+            }
+            continue;
+        }
+        HN_CHECK_ARG(w_phase[phase] != nullptr, "hn_conv2d_dgrad_s2: missing sub-filter pack of phase %d", phase);
+        TcSubConv sc{ay.T, ax.T, ay.padp, ax.padp, ay.count, ax.count, base, pix, row, img, accumulate};
+        int rc = conv2d_fwd_tc_sub(dy, w_phase[phase], dx->c, &sc, st);
+        if (rc) return rc;
+    }
+    return HN_OK;
+}
+
+extern "C" int32_t hn_pack_chunk(void) { return PACK_CHUNK; }
+
+extern "C" int hn_pack_job_init(hn_pack_job *job, const float *w_oihw, void *dst, int32_t dtype, int32_t kind, int32_t cout, int32_t cin, int32_t r,
+                                int32_t s, int32_t pad, int32_t phase)
+{
+    HN_CHECK_ARG(job && w_oihw && dst && kind >= 0 && kind <= 2, "hn_pack_job_init: bad arguments");
+    memset(job, 0, sizeof(*job));
+    job->src = w_oihw; job->dst = dst; job->dtype = dtype; job->kind = kind;
+    job->cout = cout; job->cin = cin; job->r = r; job->s = s;
+    if (kind == 0) {
+        job->rows_pad = hn_conv_cout_pad(cout, dtype);
+        job->kpad = hn_conv_kpad(cin, r, s);
+    } else if (kind == 1) {
+        job->rows_pad = hn_conv_cout_pad(cin, dtype);
+        job->kpad = hn_conv_kpad(cout, r, s);
+    } else {
+        const PhaseAxis ay = phase_axis(phase >> 1, r, pad, 2), ax = phase_axis(phase & 1, s, pad, 2);
+        HN_CHECK_ARG(ay.T > 0 && ax.T > 0, "hn_pack_job_init: phase %d has no taps", phase);
+        job->ty = ay.T; job->tx = ax.T; job->phiy = ay.phi; job->phix = ax.phi;
+        job->rows_pad = hn_conv_cout_pad(cin, dtype);
+        job->kpad = hn_conv_kpad(cout, ay.T, ax.T);
+    }
+    return HN_OK;
+}
+
+extern "C" int hn_pack_weights_multi(const hn_pack_job *jobs_dev, const int32_t *block_map_dev, int32_t n_blocks, void *stream)
+{
+    HN_CHECK_ARG(jobs_dev && block_map_dev && n_blocks >= 0, "hn_pack_weights_multi: bad arguments");
+    if (n_blocks == 0) return HN_OK;
+    pack_weights_multi_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>(jobs_dev, block_map_dev);
     HN_LAUNCH_CHECK();
     return HN_OK;
 }

@@ -291,6 +291,84 @@ __global__ void __launch_bounds__(256) affine_act_fixed_kernel(const TI *__restr
     }
 }
 
+// Train-mode BatchNorm2d finalize + normalise in ONE launch: the per-channel scale / shift are formed in every thread's prologue
+// from the FP64 sums the conv epilogue accumulated (same arithmetic as bn_finalize_kernel), the threads of the first pixel chunk
+// also write the vectors the backward needs (scale, shift, mean, invstd) and update the running statistics.  Removes one tiny
+// launch per BN layer (158 per training step).
+struct BnTrainFin {
+    const double *sum, *sqsum;
+    double count;
+    const float *gamma, *beta;
+    float eps, momentum;
+    float *running_mean, *running_var;
+    long long *num_batches_tracked;
+    float *scale, *shift, *save_mean, *save_invstd;
+};
+
+template <typename TI, typename T>
+__global__ void __launch_bounds__(256) bn_apply_train_kernel(const TI *__restrict__ x, int ldx, const BnTrainFin fin, const T *__restrict__ res,
+                                                             int ldr, int act, float slope, const float *slope_ptr, T *__restrict__ y, int ldy,
+                                                             int64_t npix, int C, int64_t pix_per_cta)
+{
+    const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+    if (cv >= C / 8) return;
+    const int PL = blockDim.y, c = cv * 8;
+    if (slope_ptr) slope = __ldg(slope_ptr);
+    float sc[8], sh[8];
+    const bool writer = blockIdx.x == 0 && threadIdx.y == 0;
+    if (writer && cv == 0 && fin.num_batches_tracked) *fin.num_batches_tracked += 1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double mean = fin.sum[c + j] / fin.count;
+        double var = fin.sqsum[c + j] / fin.count - mean * mean;
+        if (var < 0) var = 0;
+        const double invstd = 1.0 / sqrt(var + (double)fin.eps);
+        const float g = fin.gamma ? fin.gamma[c + j] : 1.f, b = fin.beta ? fin.beta[c + j] : 0.f;
+        sc[j] = (float)(g * invstd);
+        sh[j] = (float)(b - mean * g * invstd);
+        if (writer) {
+            fin.scale[c + j] = sc[j];
+            fin.shift[c + j] = sh[j];
+            fin.save_mean[c + j] = (float)mean;
+            fin.save_invstd[c + j] = (float)invstd;
+            if (fin.running_mean) {
+                const double unbiased = fin.count > 1 ? var * fin.count / (fin.count - 1.0) : var;
+                fin.running_mean[c + j] = (float)((1.0 - fin.momentum) * fin.running_mean[c + j] + fin.momentum * mean);
+                fin.running_var[c + j] = (float)((1.0 - fin.momentum) * fin.running_var[c + j] + fin.momentum * unbiased);
+            }
+        }
+    }
+    const int64_t p_begin = (int64_t)blockIdx.x * pix_per_cta;
+    const int64_t p_end = min(p_begin + pix_per_cta, npix);
+    auto one = [&](int64_t p, float (&v)[8], const float (&r)[8]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v[j] = fmaf(v[j], sc[j], sh[j]);
+            if (res) v[j] += r[j];
+            v[j] = apply_act(v[j], act, slope);
+        }
+        Vec8<T>::store(y + p * ldy + c, v);
+    };
+    int64_t p = p_begin + threadIdx.y;
+    for (; p + PL < p_end; p += 2 * PL) {
+        float v0[8], v1[8], r0[8], r1[8];
+        Vec8<TI>::load(x + p * ldx + c, v0);
+        Vec8<TI>::load(x + (p + PL) * ldx + c, v1);
+        if (res) {
+            Vec8<T>::load(res + p * ldr + c, r0);
+            Vec8<T>::load(res + (p + PL) * ldr + c, r1);
+        }
+        one(p, v0, r0);
+        one(p + PL, v1, r1);
+    }
+    if (p < p_end) {
+        float v0[8], r0[8];
+        Vec8<TI>::load(x + p * ldx + c, v0);
+        if (res) Vec8<T>::load(res + p * ldr + c, r0);
+        one(p, v0, r0);
+    }
+}
+
 // narrow / unaligned views (C = 13 logits, C = 1 critic maps): grid = (pixel chunks, C), block-wide reduction per channel
 template <typename T>
 __global__ void __launch_bounds__(256) channel_stats_scalar_kernel(const T *__restrict__ x, int64_t npix, int ld, int64_t pix_per_cta,
@@ -1097,6 +1175,44 @@ extern "C" int hn_affine_act(const hn_tensor *x, const hn_epilogue *ep, const hn
     return HN_OK;
 }
 
+extern "C" int hn_bn_apply_train(const hn_tensor *x, const double *sum, const double *sqsum, int64_t count, const float *gamma,
+                                 const float *beta, float eps, float momentum, float *running_mean, float *running_var,
+                                 int64_t *num_batches_tracked, const hn_epilogue *ep, const hn_tensor *y, float *scale, float *shift,
+                                 float *save_mean, float *save_invstd, void *stream)
+{
+    HN_CHECK_ARG(x && y && ep && sum && sqsum && scale && shift && save_mean && save_invstd && x->ptr && y->ptr, "hn_bn_apply_train: null pointer");
+    HN_CHECK_ARG(x->dtype == y->dtype || (x->dtype == HN_F32 && y->dtype == HN_BF16), "hn_bn_apply_train: x/y dtypes must match, or FP32 -> BF16");
+    HN_CHECK_ARG(x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c, "hn_bn_apply_train: shape mismatch");
+    HN_CHECK_ARG(vec8_ok(x) && vec8_ok(y), "hn_bn_apply_train: views must be 8-channel aligned");
+    HN_CHECK_ARG(count > 0 && (running_mean != nullptr) == (running_var != nullptr), "hn_bn_apply_train: bad count / running statistics");
+    const int64_t npix = (int64_t)x->n * x->h * x->w;
+    if (npix == 0) return HN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    using bf16 = __nv_bfloat16;
+    BnTrainFin fin{sum, sqsum, (double)count, gamma, beta, eps, momentum, running_mean, running_var, (long long *)num_batches_tracked,
+                   scale, shift, save_mean, save_invstd};
+    const int ncv = x->c / 8;
+    const int CVB = ncv < 32 ? ncv : 32;
+    const int PL = 256 / CVB;
+    const int cvblocks = (int)cdiv(ncv, CVB);
+    int64_t chunks = cdiv((int64_t)num_sms() * 8, cvblocks);
+    int64_t pix_per_cta = cdiv(npix, chunks);
+    if (pix_per_cta < (int64_t)PL * 4) pix_per_cta = (int64_t)PL * 4;
+    chunks = cdiv(npix, pix_per_cta);
+    dim3 g((unsigned)chunks, (unsigned)cvblocks), b(CVB, PL);
+    if (y->dtype == HN_BF16 && x->dtype == HN_BF16)
+        bn_apply_train_kernel<bf16, bf16><<<g, b, 0, st>>>((const bf16 *)x->ptr, x->ld, fin, (const bf16 *)ep->residual, ep->residual_ld, ep->act,
+                                                           ep->slope, ep->slope_ptr, (bf16 *)y->ptr, y->ld, npix, x->c, pix_per_cta);
+    else if (y->dtype == HN_BF16)
+        bn_apply_train_kernel<float, bf16><<<g, b, 0, st>>>((const float *)x->ptr, x->ld, fin, (const bf16 *)ep->residual, ep->residual_ld, ep->act,
+                                                            ep->slope, ep->slope_ptr, (bf16 *)y->ptr, y->ld, npix, x->c, pix_per_cta);
+    else
+        bn_apply_train_kernel<float, float><<<g, b, 0, st>>>((const float *)x->ptr, x->ld, fin, (const float *)ep->residual, ep->residual_ld, ep->act,
+                                                             ep->slope, ep->slope_ptr, (float *)y->ptr, y->ld, npix, x->c, pix_per_cta);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
 extern "C" int hn_maxpool3x3s2_fwd(const hn_tensor *x, const hn_tensor *y, void *stream)
 {
     HN_CHECK_ARG(x && y && x->ptr && y->ptr, "hn_maxpool3x3s2_fwd: null pointer");
@@ -1291,9 +1407,9 @@ extern "C" int hn_pack_stem_weight(const float *w_oihw, const float *row_scale, 
 extern "C" int hn_stem7x7s2_fwd(const hn_tensor *xpad, const void *w_packed, int32_t cout, const hn_epilogue *ep, const hn_tensor *y, void *stream)
 {
     HN_CHECK_ARG(xpad && w_packed && ep && y && xpad->ptr && y->ptr, "hn_stem7x7s2_fwd: null pointer");
-    HN_CHECK_ARG(!ep->stat_sum || (ep->stat_sqsum && y->dtype == HN_F32 && !ep->residual && ep->act == HN_ACT_NONE &&
-                                   (reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0 && (y->ld * 4) % 16 == 0),
-                 "hn_stem7x7s2_fwd: fused statistics need an aligned FP32 output view, no activation");
+    HN_CHECK_ARG(!ep->stat_sum || (ep->stat_sqsum && !ep->residual && ep->act == HN_ACT_NONE && (y->dtype == HN_F32 || !ep->scale) &&
+                                   (reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0 && (y->ld * hn::elsize(y->dtype)) % 16 == 0),
+                 "hn_stem7x7s2_fwd: fused statistics need a 16-byte aligned output view, no activation (no explicit scale with a BF16 output)");
     HN_CHECK_ARG(y->n == xpad->n && y->c == cout, "hn_stem7x7s2_fwd: output view mismatch");
     // default: the dense-row kernel (hn_conv_stem.cu; needs hn_stem_pad_slack_bytes() readable bytes behind the image);
     // HN_STEM_WINDOW_TMA=1 selects the overlapping-window tensor-map variant (hn_conv_tc.cu)

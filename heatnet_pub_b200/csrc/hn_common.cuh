@@ -110,6 +110,14 @@ int conv2d_fwd_f32(const hn_tensor *x, const void *w, const hn_conv *cv, const h
 int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn_epilogue *ep, const hn_tensor *y,
                   void *ws, int64_t ws_bytes, cudaStream_t st);
 int64_t conv2d_tc_workspace(const hn_tensor *x, const hn_conv *cv);
+struct TcSubConv {              // one parity phase of a stride-2 dgrad (hn_conv2d_dgrad_s2): stride-1 correlation onto a sub-lattice
+    int R, S, pad_h, pad_w;     // taps and per-axis padding of the phase's sub-filter
+    int out_h, out_w;           // extent of the phase's output lattice
+    void *y;                    // BF16 element (n=0, m=0, n=0, c=0) of the lattice
+    int64_t pix_stride, row_stride, img_stride;   // lattice strides in elements
+    int accumulate;             // add to the lattice's current contents
+};
+int conv2d_fwd_tc_sub(const hn_tensor *x, const void *w, int cout, const TcSubConv *sc, cudaStream_t st);
 bool conv_halo_ok(const hn_tensor *x, const hn_conv *cv, const hn_tensor *y, bool upsample);
 struct HeadArgs {               // fused 1x1 classifier head of the halo kernel (hn_conv3x3_head_fwd)
     const float *w, *b;         // HOST pointers: [n][64] FP32, [n] FP32 or NULL (they become kernel parameters)

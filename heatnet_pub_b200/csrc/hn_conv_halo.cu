@@ -347,7 +347,7 @@ int conv2d_fwd_halo(const hn_tensor *x, const void *w, const hn_conv *cv, const 
     p.TH = HALO_TH; p.TW = HALO_TW;
     p.tiles_h = (int)cdiv(Ho, HALO_TH); p.tiles_w = (int)cdiv(Wo, HALO_TW); p.n_img = x->n;
     p.Ho = Ho; p.Wo = Wo;
-    p.R = 3; p.S = 3; p.pad = cv->pad; p.dil = d; p.cblocks = x->c / 64;
+    p.R = 3; p.S = 3; p.pad = p.pad_w = cv->pad; p.dil = d; p.cblocks = x->c / 64;
     p.Cout = cv->cout;
     const int num_m_tiles = p.n_img * p.tiles_h * p.tiles_w;
     int bn = 64;

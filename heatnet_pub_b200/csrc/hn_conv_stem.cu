@@ -176,7 +176,7 @@ int conv_stem_dense(const hn_tensor *xpad, const void *w, int cout, const hn_epi
     p.TH = 1; p.TW = 128;
     p.tiles_w = (int)cdiv(Wo, 128); p.tiles_h = Ho; p.n_img = y->n;
     p.Ho = Ho; p.Wo = Wo;
-    p.R = 7; p.S = 1; p.pad = 0; p.dil = 1; p.cblocks = 1;
+    p.R = 7; p.S = 1; p.pad = p.pad_w = 0; p.dil = 1; p.cblocks = 1;
     p.n_tiles = 1; p.Cout = cout;
     p.y = y->ptr; p.ldy = y->ld; p.y_f32 = (y->dtype == HN_F32);
     p.scale = ep->scale; p.shift = ep->shift; p.res = nullptr; p.ldr = 0;

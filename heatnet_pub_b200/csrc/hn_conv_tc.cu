@@ -98,7 +98,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 ++ntl;
                 const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
                 const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
-                const int w_base = tw * p.TW - p.pad, h_base = th * p.TH * p.hmul - p.pad;
+                const int w_base = tw * p.TW - p.pad_w, h_base = th * p.TH * p.hmul - p.pad;
                 int kb = 0;
                 for (int r = 0; r < p.R; ++r)
                     for (int s = 0; s < p.S; ++s)
@@ -408,7 +408,7 @@ int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn
         p.tiles_w = (int)cdiv(M, 128); p.tiles_h = 1; p.n_img = 1;
         p.TH = 1; p.TW = 128; p.Ho = 1; p.Wo = (int)M;
         HN_CHECK_ARG(M < (int64_t)1 << 31, "conv_tc: too many pixels");
-        p.R = 1; p.S = 1; p.pad = 0; p.dil = 1; p.cblocks = cblocks;
+        p.R = 1; p.S = 1; p.pad = p.pad_w = 0; p.dil = 1; p.cblocks = cblocks;
     } else {
         // spatial tile menu: minimise padded area, prefer squarer tiles (halo reuse in L2)
         const int menu[5][2] = {{8, 16}, {4, 32}, {16, 8}, {2, 64}, {1, 128}};
@@ -426,7 +426,7 @@ int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn
         if (rc) return rc;
         p.tiles_w = (int)cdiv(Wo, p.TW); p.tiles_h = (int)cdiv(Ho, p.TH); p.n_img = x->n;
         p.Ho = Ho; p.Wo = Wo;
-        p.R = cv->r; p.S = cv->s; p.pad = cv->pad; p.dil = cv->dil; p.cblocks = x->c / 64;
+        p.R = cv->r; p.S = cv->s; p.pad = p.pad_w = cv->pad; p.dil = cv->dil; p.cblocks = x->c / 64;
     }
     const int num_m_tiles = p.n_img * p.tiles_h * p.tiles_w;
     // Cout tile: the widest of 256/128/64 that divides cout_pad and still leaves >= 2 tiles per SM
@@ -493,6 +493,93 @@ int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn
 }
 
 
+// ------------------------------------------------------------------------------------------------ phases of a strided dgrad
+// One parity class (rho_y, rho_x) of the input gradient of a stride-2 convolution is a stride-1 correlation of dY with the
+// sub-filter of the taps that can reach that parity (hn_backward.cu: hn_conv2d_dgrad_s2).  It runs on the implicit-GEMM path
+// above with two generalisations: per-axis padding, and an output (and accumulate-residual) tensor map whose pixel / row strides
+// address the phase's sub-lattice of dX directly, so no zero-inserted gradient and no scatter pass exist.
+int conv2d_fwd_tc_sub(const hn_tensor *x, const void *w, int cout, const TcSubConv *sc, cudaStream_t st)
+{
+    const int Ho = sc->out_h, Wo = sc->out_w;
+    const int64_t M = (int64_t)x->n * Ho * Wo;
+    if (M == 0) return HN_OK;
+    HN_CHECK_ARG(x->dtype == HN_BF16 && x->c % 64 == 0 && x->ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x->ptr) & 15) == 0,
+                 "conv_tc_sub: input must be a 16-byte aligned BF16 view with C %% 64 == 0");
+    const uint64_t esz = 2;
+    HN_CHECK_ARG((reinterpret_cast<uintptr_t>(sc->y) & 15) == 0 && (sc->pix_stride * esz) % 16 == 0 && (sc->row_stride * esz) % 16 == 0 &&
+                     (sc->img_stride * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+                 "conv_tc_sub: output lattice must be 16-byte aligned");
+    const int kpad = hn_conv_kpad(x->c, sc->R, sc->S);
+    const int cout_pad = hn_conv_cout_pad(cout, HN_BF16);
+    TcParams p{};
+    p.hmul = 1;
+    const int menu[5][2] = {{8, 16}, {4, 32}, {16, 8}, {2, 64}, {1, 128}};
+    int best = 0;
+    int64_t best_area = -1;
+    for (int i = 0; i < 5; ++i) {
+        int64_t area = cdiv(Ho, menu[i][0]) * menu[i][0] * cdiv(Wo, menu[i][1]) * menu[i][1];
+        if (best_area < 0 || area < best_area) { best_area = area; best = i; }
+    }
+    p.TH = menu[best][0]; p.TW = menu[best][1];
+    CUtensorMap ta, tb, ty, tr;
+    memset(&tr, 0, sizeof(tr));
+    {
+        uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
+        uint64_t strides[4] = {2, (uint64_t)x->ld * 2, (uint64_t)x->ld * 2 * x->w, (uint64_t)x->ld * 2 * x->w * x->h};
+        uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+        int rc = make_tmap(&ta, x->ptr, 4, dims, strides, box);
+        if (rc) return rc;
+    }
+    p.tiles_w = (int)cdiv(Wo, p.TW); p.tiles_h = (int)cdiv(Ho, p.TH); p.n_img = x->n;
+    p.Ho = Ho; p.Wo = Wo;
+    p.R = sc->R; p.S = sc->S; p.pad = sc->pad_h; p.pad_w = sc->pad_w; p.dil = 1; p.cblocks = x->c / 64;
+    const int num_m_tiles = p.n_img * p.tiles_h * p.tiles_w;
+    int bn;
+    if (cout_pad < 64) bn = cout_pad;
+    else {
+        bn = 64;
+        for (int cand : {256, 128}) {
+            if (cout_pad % cand == 0 && (int64_t)num_m_tiles * (cout_pad / cand) >= 2 * (int64_t)num_sms()) { bn = cand; break; }
+        }
+    }
+    p.n_tiles = cout_pad / bn;
+    p.Cout = cout;
+    {
+        uint64_t dims[2] = {(uint64_t)kpad, (uint64_t)cout_pad};
+        uint64_t strides[2] = {2, (uint64_t)kpad * 2};
+        uint32_t box[2] = {64, (uint32_t)bn};
+        int rc = make_tmap(&tb, w, 2, dims, strides, box);
+        if (rc) return rc;
+    }
+    p.y = sc->y; p.ldy = 0; p.y_f32 = 0;
+    p.act = HN_ACT_NONE;
+    p.ebw = p.TW < 32 ? p.TW : 32;
+    {
+        uint64_t dims[4] = {(uint64_t)cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)p.n_img};
+        uint64_t strides[4] = {esz, (uint64_t)sc->pix_stride * esz, (uint64_t)sc->row_stride * esz, (uint64_t)sc->img_stride * esz};
+        uint32_t box[4] = {64, (uint32_t)p.ebw, (uint32_t)(32 / p.ebw), 1};
+        int rc = make_tmap(&ty, sc->y, 4, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+        if (rc) return rc;
+        p.tma_out = 1;
+        if (sc->accumulate) {          // dX += ...: the lattice itself is the epilogue's residual input
+            rc = make_tmap(&tr, sc->y, 4, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+            if (rc) return rc;
+            p.res = sc->y; p.ldr = 0; p.tma_res = 1;
+        }
+    }
+    const int num_tiles = num_m_tiles * p.n_tiles;
+    switch (bn) {
+        case 256: return launch_tc<256, 4>(ta, tb, ty, tr, p, num_tiles, st);
+        case 128: return launch_tc<128, 6>(ta, tb, ty, tr, p, num_tiles, st);
+        case 64: return launch_tc<64, 7>(ta, tb, ty, tr, p, num_tiles, st);
+        case 32: return launch_tc<32, 8>(ta, tb, ty, tr, p, num_tiles, st);
+        case 16: return launch_tc<16, 8>(ta, tb, ty, tr, p, num_tiles, st);
+    }
+    set_error("conv_tc_sub: unsupported Cout tile %d", bn);
+    return HN_ERR_ARG;
+}
+
+
 // ------------------------------------------------------------------------------------------------ 7x7 stride-2 stems
 // The stems (Cin = 3 / 1 / 4) without an im2col pass: the input is kept as a zero-bordered, 4-channel NHWC image
 // xpad[N][Hp][Wp][4] (border 3 = the conv padding).  The 8 pixels x 4 channels = 32 BF16 that one filter row touches for
@@ -515,7 +602,7 @@ int conv_stem_tc(const hn_tensor *xpad, const void *w, int cout, const hn_epilog
     p.TH = 1; p.TW = 128;
     p.tiles_w = (int)cdiv(Wo, 128); p.tiles_h = Ho; p.n_img = y->n;
     p.Ho = Ho; p.Wo = Wo;
-    p.R = 7; p.S = 1; p.pad = 0; p.dil = 1; p.cblocks = 1;
+    p.R = 7; p.S = 1; p.pad = p.pad_w = 0; p.dil = 1; p.cblocks = 1;
     p.n_tiles = 1; p.Cout = cout;
     CUtensorMap ta, tb, ty, tr;
     memset(&ty, 0, sizeof(ty));

@@ -21,7 +21,8 @@ struct TcParams {
     int TH, TW;                    // TH*TW = 128
     int Ho, Wo;                    // output spatial size (flat mode: Ho = 1, Wo = total pixels)
     int n_tiles;                   // Cout tiles
-    int R, S, pad, dil;
+    int R, S, pad, dil;            // pad = rows; pad_w = columns (equal except for the phases of a strided dgrad)
+    int pad_w;
     int hmul;                      // input row of tap r = (output row) * hmul - pad + r * dil (2 for the stem's window map, else 1)
     int cblocks;                   // Cin / 64 (flat-from-workspace: kpad / 64 with R=S=1)
     int Cout;
@@ -157,17 +158,22 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
         }
     }
     // fused BatchNorm2d statistics (p.stat_sum): per-warp FP32 partial sums of this warp's COLS columns, one per lane and 32-column chunk
-    constexpr int STAT_CHUNKS = COLS >= 32 ? COLS / 32 : 1;
+    // Two lane <-> channel mappings share the accumulators: FP32 output -- slot i, lane l = channel 32*i + l of the warp's columns;
+    // BF16 output (64 channels per 128-byte staging row, a lane reads one BF16 PAIR per row) -- slot 2*j + e, lane l = channel
+    // 64*j + 2*l + e.  BF16 statistics are taken from the ROUNDED values, i.e. they are exactly the statistics of the stored tensor.
+    constexpr int STAT_CHUNKS = COLS >= 64 ? COLS / 32 : 2;
     float st_s[STAT_CHUNKS], st_q[STAT_CHUNKS];
 #pragma unroll
     for (int i = 0; i < STAT_CHUNKS; ++i) st_s[i] = st_q[i] = 0.f;
     int stat_ctile = -1;
+    const bool stat_bf16 = p.stat_sum != nullptr && !p.y_f32;
     auto stat_flush = [&]() {
         if (stat_ctile < 0) return;
 #pragma unroll
         for (int i = 0; i < STAT_CHUNKS; ++i) {
-            const int ch = stat_ctile + 32 * i + lane;
-            if (ch < p.Cout && (st_s[i] != 0.f || st_q[i] != 0.f)) {
+            const int ch = stat_bf16 ? stat_ctile + 64 * (i >> 1) + 2 * lane + (i & 1) : stat_ctile + 32 * i + lane;
+            const bool mine = stat_bf16 ? (64 * (i >> 1) + 2 * lane + (i & 1) < COLS) : (32 * i + lane < COLS);
+            if (mine && ch < p.Cout && (st_s[i] != 0.f || st_q[i] != 0.f)) {
                 atomicAdd(p.stat_sum + ch, (double)st_s[i]);
                 atomicAdd(p.stat_sqsum + ch, (double)st_q[i]);
             }
@@ -465,6 +471,30 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
                             }
                         }
                     }
+                }
+            }
+            if constexpr (SUB == 32) {
+                if (stat_bf16 && fast && chunk_on) {
+                    // the staging tile holds this warp's 32 pixels x (up to) 64 channels as BF16 (16-byte chunks swizzled by row): lane l
+                    // sums the channel pair (2l, 2l+1) over the VALID rows
+                    __syncwarp();
+                    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+                    const int ncol = (tch < COLS - ck ? tch : COLS - ck);
+                    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+                    if (2 * lane < ncol) {
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r) {
+                            if (vmask == 0xffffffffu || ((vmask >> r) & 1u)) {
+                                const uint32_t w2 = lds32u(stage + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+                                const float x0 = __uint_as_float(w2 << 16), x1 = __uint_as_float(w2 & 0xffff0000u);
+                                s0 += x0; q0 = fmaf(x0, x0, q0);
+                                s1 += x1; q1 = fmaf(x1, x1, q1);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < STAT_CHUNKS / 2; ++i)
+                        if (i == (ck >> 6)) { st_s[2 * i] += s0; st_q[2 * i] += q0; st_s[2 * i + 1] += s1; st_q[2 * i + 1] += q1; }
                 }
             }
             if (tma_out) {

@@ -18,10 +18,11 @@ _TORCH_DTYPE = {HN_F32: torch.float32, HN_BF16: torch.bfloat16}
 _HN_DTYPE = {torch.float32: HN_F32, torch.bfloat16: HN_BF16}
 
 DEFAULT_PRECISION = os.environ.get("HEATNET_B200_PRECISION", "bf16")
-# Storage type of the pre-normalisation conv output in train-mode BatchNorm2d on the BF16 path.  FP32 (default) keeps
-# (x - mean) * invstd free of the BF16 rounding of x (amplified by |mean|/std); "0" stores BF16 like torch.autocast does
-# (10 bytes/element less HBM traffic over the forward + backward of every BN layer).
-BN_TRAIN_RAW_FP32 = os.environ.get("HEATNET_B200_BN_RAW_FP32", "1") != "0"
+# Storage type of the pre-normalisation conv output in train-mode BatchNorm2d on the BF16 path.  BF16 (default) is what
+# torch.autocast stores too: 10 bytes/element less HBM traffic over the forward + backward of every BN layer, and the batch
+# statistics are those of the stored (rounded) tensor, accumulated by the conv epilogue.  "1" keeps the tensor in FP32:
+# (x - mean) * invstd is then free of the BF16 rounding of x (amplified by |mean|/std), closer to the FP32 reference.
+BN_TRAIN_RAW_FP32 = os.environ.get("HEATNET_B200_BN_RAW_FP32", "0") != "0"
 # Fused 2x-upsample + 3x3 conv (hn_upconv3x3_fwd) is used for inputs with at least this many channels.  Measured on B200
 # (batch 16, 650x1920): with the exact-2x bilinear kernel at 3.1 TB/s the separate path wins everywhere -- up_1 (Cin 1024):
 # fused 5.08 ms vs 0.82 + 3.60 ms unfused -- because the halo producers are CUDA-core work competing with the epilogue for
@@ -339,25 +340,105 @@ def _versions(*tensors):
     return tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors)
 
 
+# ---- multi-tensor repack: every plain pack built below is registered; after an optimizer step the first cache miss rebuilds ALL
+# stale registered packs with one launch (hn_pack_weights_multi) instead of ~170 single-tensor launches per training step
+MULTI_PACK = os.environ.get("HN_NO_MULTI_PACK") is None
+_pack_registry = {}        # (id(conv), cache key) -> (weakref to conv, cache key, kind, phase)
+_pack_tables = {}          # tuple of registry keys -> (jobs_dev, bmap_dev, n_blocks, host staging kept alive)
+
+
+def _register_pack(conv, key, kind, phase=0):
+    import weakref
+    rk = (id(conv), key)
+    if rk not in _pack_registry:
+        _pack_registry[rk] = (weakref.ref(conv), key, kind, phase)
+
+
+def repack_stale(device) -> int:
+    """Rebuild every registered pack whose master weight has changed since it was packed, in place, in one launch.
+    -> number of packs rebuilt (0: nothing stale, or fewer than two -- the caller's single-tensor path handles it)."""
+    if not MULTI_PACK:
+        return 0
+    lib = _lib.load()
+    stale = []
+    for rk, (ref, key, kind, phase) in list(_pack_registry.items()):
+        conv = ref()
+        if conv is None:
+            del _pack_registry[rk]
+            continue
+        hit = conv.__dict__.get("_hn_wcache", {}).get(key)
+        if hit is None or conv.weight.device != device or key[-1] != device:
+            continue
+        ver = _versions(conv.weight)
+        if hit[0] != ver:
+            if hit[0][0][0] != ver[0][0] or not conv.weight.is_contiguous() or conv.weight.dtype != torch.float32:
+                continue                        # the master moved / is not a dense FP32 tensor: rebuilt by the single-tensor path
+            stale.append((rk, conv, key, kind, phase, hit, ver))
+    if len(stale) < 2:
+        return 0
+    tkey = tuple(rk for rk, *_ in stale)
+    tab = _pack_tables.get(tkey)
+    if tab is None:
+        import numpy as np
+        chunk = lib.hn_pack_chunk()
+        jobs = (_lib.HnPackJob * len(stale))()
+        blocks = []
+        for i, (rk, conv, key, kind, phase, hit, ver) in enumerate(stale):
+            dtype = key[1] if kind != 2 else key[1]
+            dst = hit[1] if kind != 2 else hit[1][phase]
+            cout, cin, r, s = conv.weight.shape
+            _lib.check(lib.hn_pack_job_init(C.byref(jobs[i]), conv.weight.data_ptr(), dst.data_ptr(), _HN_DTYPE[dtype], kind, cout, cin, r, s,
+                                            conv.padding[0], phase))
+            assert jobs[i].rows_pad * jobs[i].kpad == dst.numel(), "pack geometry mismatch"
+            n = (dst.numel() + chunk - 1) // chunk
+            blocks.append(np.stack([np.full(n, i, dtype=np.int32), np.arange(n, dtype=np.int32)], axis=1))
+        bmap = np.ascontiguousarray(np.concatenate(blocks, axis=0))
+        jobs_h = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8)
+        bmap_h = torch.from_numpy(bmap)
+        if not torch.cuda.is_current_stream_capturing():
+            jobs_h, bmap_h = jobs_h.pin_memory(), bmap_h.pin_memory()
+        jobs_d = torch.empty(jobs_h.shape, dtype=torch.uint8, device=device)
+        bmap_d = torch.empty(bmap_h.shape, dtype=torch.int32, device=device)
+        jobs_d.copy_(jobs_h, non_blocking=True)
+        bmap_d.copy_(bmap_h, non_blocking=True)
+        if len(_pack_tables) >= 8:
+            _pack_tables.pop(next(iter(_pack_tables)))
+        tab = (jobs_d, bmap_d, bmap.shape[0], (jobs_h, bmap_h))
+        _pack_tables[tkey] = tab
+    jobs_d, bmap_d, n_blocks, _ = tab
+    _lib.check(lib.hn_pack_weights_multi(jobs_d.data_ptr(), bmap_d.data_ptr(), n_blocks, _stream()))
+    _count()
+    done = set()
+    for rk, conv, key, kind, phase, hit, ver in stale:
+        if (id(conv), key) in done:
+            continue
+        done.add((id(conv), key))
+        conv.__dict__["_hn_wcache"][key] = (ver,) + tuple(hit[1:])
+    return len(stale)
+
+
 def packed_weight(conv: torch.nn.Conv2d, dtype: torch.dtype) -> torch.Tensor:
     """K-major pack [cout_pad][kpad] of the OIHW FP32 master weight, cached until the parameter changes."""
     lib = _lib.load()
     cache = conv.__dict__.setdefault("_hn_wcache", {})
-    key = (dtype, conv.weight.device)
+    key = ("fwd", dtype, conv.weight.device)
     ver = _versions(conv.weight)
     hit = cache.get(key)
     if hit is not None and hit[0] == ver:
         return hit[1]
+    if hit is not None and repack_stale(conv.weight.device) and cache[key][0] == ver:
+        return cache[key][1]
     w = conv.weight.detach()
     if w.dtype != torch.float32 or not w.is_contiguous():
         w = w.float().contiguous()
     cout, cin, r, s = w.shape
     hdt = _HN_DTYPE[dtype]
     cout_pad, kpad = lib.hn_conv_cout_pad(cout, hdt), lib.hn_conv_kpad(cin, r, s)
-    dst = torch.empty((cout_pad, kpad), dtype=dtype, device=w.device)
+    dst = hit[1] if hit is not None else torch.empty((cout_pad, kpad), dtype=dtype, device=w.device)
     _lib.check(lib.hn_pack_weight(w.data_ptr(), dst.data_ptr(), hdt, cout, cin, r, s, cout_pad, kpad, _stream()))
     _count()
     cache[key] = (ver, dst)
+    _register_pack(conv, key, 0)
     return dst
 
 
@@ -646,6 +727,24 @@ def batchnorm_finalize(sums: torch.Tensor, count: int, bn: torch.nn.BatchNorm2d)
     return out[0], out[1], out[2], out[3]
 
 
+def batchnorm_apply_train(raw: Act, sums: torch.Tensor, bn: torch.nn.BatchNorm2d, residual: Optional[Act], act, slope, slope_ptr, out: Act):
+    """out = act(BN_train(raw) + residual) from the FP64 sums of a conv with fused statistics, and the running-statistic update of
+    nn.BatchNorm2d -- one launch (hn_bn_apply_train).  -> (scale, shift, mean, invstd) for the backward."""
+    cch = bn.num_features
+    vec = torch.empty((4, cch), dtype=torch.float32, device=sums.device)
+    track = bn.track_running_stats and bn.running_mean is not None
+    p = lambda t: t.detach().data_ptr() if t is not None else None
+    ep = _epilogue(None, None, residual, act, slope, slope_ptr)
+    _lib.check(_lib.load().hn_bn_apply_train(C.byref(raw.hn()), sums.data_ptr(), sums.data_ptr() + 8 * cch, raw.n * raw.h * raw.w, p(bn.weight),
+                                             p(bn.bias), float(bn.eps), float(bn.momentum), p(bn.running_mean) if track else None,
+                                             p(bn.running_var) if track else None, p(bn.num_batches_tracked) if track else None, C.byref(ep),
+                                             C.byref(out.hn()), vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(), vec[3].data_ptr(), _stream()))
+    _count()
+    if track:
+        torch.autograd.graph.increment_version([bn.running_mean, bn.running_var])
+    return vec[0], vec[1], vec[2], vec[3]
+
+
 def _conv_param_backward(grads: Grads, tape: Tape, x: Act, conv, dz: Act):
     """Shared tail of every conv backward: weight / bias gradients and the input gradient."""
     if dz.dtype != x.dtype:                       # e.g. FP32 critic map gradient -> BF16 operands
@@ -696,21 +795,26 @@ def conv_bn_act(x: Act, conv, bn, act=ACT_NONE, slope=0.0, slope_ptr=None, resid
     raw_fp32 = BN_TRAIN_RAW_FP32
     # BF16 engine with FP32 pre-normalisation output: the batch statistics are accumulated by the conv epilogue itself (FP32 per
     # 32-pixel block, FP64 atomics), so train-mode BN costs one tiny finalize launch instead of a pass over the tensor
-    fused = BN_FUSED_STATS and raw_fp32 and x.dtype == torch.bfloat16 and conv.out_channels >= 17
+    fused = BN_FUSED_STATS and x.dtype == torch.bfloat16 and conv.out_channels >= 17
     sums = _stats_alloc(conv.out_channels, x.buf.device) if fused else None
     if stem_ok(x, conv):
         wp, shift = packed_stem_weight(conv, None)
         raw = stem_conv(x, conv, wp, shift, out_dtype=torch.float32 if raw_fp32 else None, stats=sums)
     else:
         raw = conv2d(x, conv, scale, shift, None, ACT_NONE, out_dtype=torch.float32 if raw_fp32 else None, stats=sums)
-    if fused:
-        bscale, bshift, mean, invstd = batchnorm_finalize(sums, raw.n * raw.h * raw.w, bn)
-    else:
-        bscale, bshift, mean, invstd = batchnorm_train_affine(raw, bn)
     if out is None:
         in_place = raw.dtype == x.dtype and tape is None
         out = raw if in_place else new_act(raw.n, raw.h, raw.w, raw.c, x.dtype, x.buf.device)
-    y = affine_act(raw, bscale, bshift, residual, act, slope, slope_ptr, out=out)
+    if fused and bn.momentum is not None and raw.c % 8 == 0 and raw.ld % 8 == 0 and out.ld % 8 == 0:
+        # statistics came out of the conv epilogue: finalize + normalise + residual + activation in ONE launch
+        bscale, bshift, mean, invstd = batchnorm_apply_train(raw, sums, bn, residual, act, slope, slope_ptr, out)
+        y = out
+    else:
+        if fused:
+            bscale, bshift, mean, invstd = batchnorm_finalize(sums, raw.n * raw.h * raw.w, bn)
+        else:
+            bscale, bshift, mean, invstd = batchnorm_train_affine(raw, bn)
+        y = affine_act(raw, bscale, bshift, residual, act, slope, slope_ptr, out=out)
     if tape is not None:
         live = tape.needs(x) or tape.needs(residual) or any(_wants(p) for p in (conv.weight, conv.bias, bn.weight, bn.bias, slope_ptr))
         if live:
@@ -931,24 +1035,86 @@ def packed_weight_dgrad(conv: torch.nn.Conv2d, dtype: torch.dtype) -> torch.Tens
     hit = cache.get(key)
     if hit is not None and hit[0] == ver:
         return hit[1]
+    if hit is not None and repack_stale(conv.weight.device) and cache[key][0] == ver:
+        return cache[key][1]
     w = conv.weight.detach()
     if w.dtype != torch.float32 or not w.is_contiguous():
         w = w.float().contiguous()
     cout, cin, r, s = w.shape
     hdt = _HN_DTYPE[dtype]
     cin_pad, kpad = lib.hn_conv_cout_pad(cin, hdt), lib.hn_conv_kpad(cout, r, s)
-    dst = torch.empty((cin_pad, kpad), dtype=dtype, device=w.device)
+    dst = hit[1] if hit is not None else torch.empty((cin_pad, kpad), dtype=dtype, device=w.device)
     _lib.check(lib.hn_pack_weight_dgrad(w.data_ptr(), dst.data_ptr(), hdt, cout, cin, r, s, cin_pad, kpad, _stream()))
     _count()
     cache[key] = (ver, dst)
+    _register_pack(conv, key, 1)
     return dst
+
+
+def packed_weight_dgrad_phases(conv: torch.nn.Conv2d, dtype: torch.dtype):
+    """The four parity-phase sub-filter packs of a stride-2 convolution's dgrad (hn_pack_weight_dgrad_phase), cached like the other
+    packs -> (list of 4 tensors or None for phases no tap reaches, ctypes array of their addresses)."""
+    lib = _lib.load()
+    cache = conv.__dict__.setdefault("_hn_wcache", {})
+    key = ("dgrad_s2", dtype, conv.weight.device)
+    ver = _versions(conv.weight)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1], hit[2]
+    if hit is not None and repack_stale(conv.weight.device) and cache[key][0] == ver:
+        return cache[key][1], cache[key][2]
+    w = conv.weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    cout, cin, r, s = w.shape
+    hdt = _HN_DTYPE[dtype]
+    cin_pad = lib.hn_conv_cout_pad(cin, hdt)
+    packs = []
+    for phase in range(4):
+        kpad = lib.hn_dgrad_s2_phase_kpad(cout, r, s, conv.padding[0], phase)
+        if kpad == 0:
+            packs.append(None)
+            continue
+        dst = hit[1][phase] if hit is not None else torch.empty((cin_pad, kpad), dtype=dtype, device=w.device)
+        _lib.check(lib.hn_pack_weight_dgrad_phase(w.data_ptr(), dst.data_ptr(), hdt, cout, cin, r, s, conv.padding[0], phase, cin_pad, _stream()))
+        _count()
+        packs.append(dst)
+    ptrs = (C.c_void_p * 4)(*[t.data_ptr() if t is not None else None for t in packs])
+    cache[key] = (ver, packs, ptrs)
+    for phase in range(4):
+        if packs[phase] is not None:
+            _pack_registry.setdefault((id(conv), key, phase), (__import__("weakref").ref(conv), key, 2, phase))
+    return packs, ptrs
+
+
+DGRAD_S2_PHASES = os.environ.get("HN_NO_DGRAD_PHASES") is None
 
 
 def conv2d_dgrad(dy: Act, conv: torch.nn.Conv2d, in_h: int, in_w: int, out: Optional[Act] = None,
                  accumulate: bool = False) -> Act:
-    """dX of a convolution = stride-1 convolution of dY (zero-inserted when the forward stride is > 1) with the
-    flipped, channel-transposed filter; `accumulate` adds into `out` through the epilogue's residual input."""
+    """dX of a convolution.  Stride 1: a stride-1 convolution of dY with the flipped, channel-transposed filter.  Stride 2 on the
+    BF16 engine: four parity phases, each a stride-1 correlation of dY with a sub-filter, written straight onto its sub-lattice of
+    dX (hn_conv2d_dgrad_s2) -- no zero-inserted gradient.  Otherwise (FP32 parity path, odd shapes): zero insertion (hn_dilate)
+    followed by the stride-1 form.  `accumulate` adds into `out` through the epilogue's residual input."""
     k, st, pad, dil = conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0]
+    lib = _lib.load()
+    if st == 2 and DGRAD_S2_PHASES and dy.dtype == torch.bfloat16:
+        if out is None:
+            out, accumulate = new_act(dy.n, in_h, in_w, conv.in_channels, dy.dtype, dy.buf.device, ld=(conv.in_channels + 7) // 8 * 8), False
+        cv = HnConv(conv.out_channels, k, k, st, pad, dil)
+        dyh, oh = dy.hn(), out.hn()
+        if (out.h, out.w) == (in_h, in_w) and lib.hn_conv2d_dgrad_s2_ok(C.byref(dyh), C.byref(cv), C.byref(oh)):
+            packs, ptrs = packed_weight_dgrad_phases(conv, dy.dtype)
+            timing = conv_timer is not None
+            if timing:
+                ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev_a.record()
+            _lib.check(lib.hn_conv2d_dgrad_s2(C.byref(dyh), ptrs, C.byref(cv), C.byref(oh), int(accumulate), _stream()))
+            if timing:
+                ev_b.record()
+                conv_timer.append((f"dgrad {conv.in_channels}<-{conv.out_channels} k{k} s2 @{in_h}x{in_w}", ev_a, ev_b))
+            _count(4)
+            return out
     padp = dil * (k - 1) - pad
     assert padp >= 0, "dgrad needs pad <= dil*(k-1)"
     g = dy
@@ -956,7 +1122,7 @@ def conv2d_dgrad(dy: Act, conv: torch.nn.Conv2d, in_h: int, in_w: int, out: Opti
     hu, wu = in_h - dil * (k - 1) + 2 * pad, in_w - dil * (k - 1) + 2 * pad
     if st > 1 or (hu, wu) != (dy.h, dy.w):
         up = new_act(dy.n, hu, wu, dy.c, dy.dtype, dy.buf.device, ld=(dy.c + 7) // 8 * 8)
-        _lib.check(_lib.load().hn_dilate(C.byref(dy.hn()), st, C.byref(up.hn()), _stream()))
+        _lib.check(lib.hn_dilate(C.byref(dy.hn()), st, C.byref(up.hn()), _stream()))
         _count()
         g = up
     wp = packed_weight_dgrad(conv, dy.dtype)

@@ -57,7 +57,8 @@ typedef struct hn_epilogue {
     int32_t out_nchw;       /* 1: y is written as NCHW FP32 (the reference's logits layout) */
     double *stat_sum;       /* optional [Cout] FP64, caller-zeroed: += sum over the output pixels of the stored value ... */
     double *stat_sqsum;     /* ... and of its square: BatchNorm2d batch statistics in train mode, fused into the conv epilogue
-                             * (BF16 engine, FP32 16-byte-aligned output view, Cout tile >= 32; else the call fails) */
+                             * (BF16 engine, 16-byte-aligned output view, Cout tile >= 32; FP32 or BF16 output -- BF16: statistics of
+                             * the ROUNDED values, i.e. of the stored tensor, and no explicit scale; else the call fails) */
     int32_t per_image;      /* hn_affine_act only: scale (and shift, if given) are [N][C] -- Dropout2d channel masks */
 } hn_epilogue;
 
@@ -165,6 +166,14 @@ int hn_bn_finalize(const double *sum, const double *sqsum, int64_t count, const 
 int hn_bn_finalize_tracked(const double *sum, const double *sqsum, int64_t count, const float *gamma, const float *beta,
                            float eps, float momentum, float *running_mean, float *running_var, int64_t *num_batches_tracked,
                            float *scale, float *shift, float *save_mean, float *save_invstd, int32_t c, void *stream);
+/* hn_bn_finalize_tracked and the normalise pass hn_affine_act in ONE launch (cm/models/extractors.py:85-101 in train mode):
+ * y = act(x * scale + shift + residual) with scale / shift formed from the FP64 sums in every thread's prologue; the vectors the
+ * backward needs (scale, shift, save_mean, save_invstd: [C] each) are written and the running statistics / counter updated by
+ * the threads of the first pixel chunk.  ep supplies residual / act / slope only.  Views must be 8-channel aligned. */
+int hn_bn_apply_train(const hn_tensor *x, const double *sum, const double *sqsum, int64_t count, const float *gamma, const float *beta,
+                      float eps, float momentum, float *running_mean, float *running_var, int64_t *num_batches_tracked,
+                      const hn_epilogue *ep, const hn_tensor *y, float *scale, float *shift, float *save_mean, float *save_invstd,
+                      void *stream);
 /* train-mode BatchNorm2d statistics in ONE kernel (+ one memset): hn_channel_stats and hn_bn_finalize fused through a
  * last-CTA ticket, including `num_batches_tracked += 1` (cm/models/extractors.py:85-101: every nn.BatchNorm2d in train mode).
  * scratch: device memory of hn_bn_batch_stats_scratch_bytes(C) (FP64 sums + ticket), zeroed by the call. */
@@ -215,6 +224,35 @@ int hn_pyramid_pool_bwd(const void *dpool, const int32_t *sizes, int32_t nsizes,
 int hn_dilate(const hn_tensor *x, int32_t stride, const hn_tensor *up, void *stream);
 int hn_pack_weight_dgrad(const float *w_oihw, void *dst, int32_t dtype, int32_t cout, int32_t cin, int32_t r, int32_t s,
                          int32_t cin_pad, int32_t kpad, void *stream);
+/* Stride-2 dgrad WITHOUT the zero-inserted gradient (BF16 engine): the input gradient splits into the four parity phases
+ * (rho_y, rho_x) = (phase >> 1, phase & 1) of dX; each is a stride-1 correlation of dY with the sub-filter of the taps that reach
+ * that parity, written straight onto its sub-lattice of dX through a strided tensor map (k*k tap evaluations per output pixel quad
+ * instead of 4*k*k).  hn_pack_weight_dgrad_phase builds a phase's [cin_pad][kpad] pack, kpad = hn_dgrad_s2_phase_kpad(...) (0: no
+ * tap reaches the phase -- it is zero-filled, or skipped when accumulating).  cv = the FORWARD geometry (stride 2, dilation 1);
+ * w_phase: 4 device pointers (NULL for empty phases).  hn_conv2d_dgrad_s2_ok: 1 when the views qualify, else use hn_dilate. */
+int32_t hn_dgrad_s2_phase_kpad(int32_t cout, int32_t r, int32_t s, int32_t pad, int32_t phase);
+int hn_pack_weight_dgrad_phase(const float *w_oihw, void *dst, int32_t dtype, int32_t cout, int32_t cin, int32_t r, int32_t s, int32_t pad,
+                               int32_t phase, int32_t cin_pad, void *stream);
+int hn_conv2d_dgrad_s2_ok(const hn_tensor *dy, const hn_conv *cv, const hn_tensor *dx);
+int hn_conv2d_dgrad_s2(const hn_tensor *dy, const void *const *w_phase, const hn_conv *cv, const hn_tensor *dx, int32_t accumulate,
+                       void *stream);
+/* Every weight pack a training step needs, rebuilt from the FP32 masters in ONE launch (the optimizer invalidates ~170 packs per
+ * step: forward, dgrad and stride-2 phase packs of every live convolution).  The caller fills one hn_pack_job per pack with
+ * hn_pack_job_init (kind 0 = hn_pack_weight, 1 = hn_pack_weight_dgrad, 2 = hn_pack_weight_dgrad_phase layout), copies the array
+ * to the device and passes a block map of (job index, chunk index) int32 pairs, chunk c covering destination elements
+ * [c * hn_pack_chunk(), (c+1) * hn_pack_chunk()).  Results are bit-identical to the single-tensor pack functions. */
+typedef struct hn_pack_job {
+    const float *src; /* OIHW FP32 master (device) */
+    void *dst;        /* packed destination (device) */
+    int32_t cout, cin, r, s;
+    int32_t rows_pad, kpad;
+    int32_t kind, dtype;
+    int32_t ty, tx, phiy, phix; /* kind 2: taps and first filter tap per axis of the phase */
+} hn_pack_job;
+int32_t hn_pack_chunk(void);
+int hn_pack_job_init(hn_pack_job *job, const float *w_oihw, void *dst, int32_t dtype, int32_t kind, int32_t cout, int32_t cin, int32_t r,
+                     int32_t s, int32_t pad, int32_t phase);
+int hn_pack_weights_multi(const hn_pack_job *jobs_dev, const int32_t *block_map_dev, int32_t n_blocks, void *stream);
 /* conv wgrad into the packed FP32 layout [cout_pad][kpad] (BF16: tcgen05 with MN-major operands, split over pixels;
  * FP32: CUDA cores), then packed -> OIHW parameter gradient */
 int64_t hn_conv2d_wgrad_workspace_bytes(const hn_tensor *x, const hn_conv *cv);

@@ -121,6 +121,42 @@ def test_conv_dgrad_wgrad_bf16_tensor_core(E, case):
     assert rel((acc - prev).cpu(), dw_r) < 4e-3
 
 
+S2_CASES = [
+    # cin, cout, k, stride, pad, dil, h, w        stride-2 layers of the step: critics (4x4 p1), layer2.0 conv2 (3x3 p1) / downsample (1x1)
+    (64, 64, 4, 2, 1, 1, 32, 48),
+    (128, 256, 4, 2, 1, 1, 17, 31),      # odd input size: the four phase lattices differ in extent
+    (2048, 64, 4, 2, 1, 1, 8, 12),
+    (13, 64, 4, 2, 1, 1, 32, 48),        # 13-channel dX (critic on the logits): 16-wide Cout tile, channel stride 16
+    (128, 128, 3, 2, 1, 1, 20, 25),
+    (256, 512, 1, 2, 0, 1, 21, 24),      # three empty phases: zero-filled, or untouched when accumulating
+    (64, 64, 7, 2, 3, 1, 20, 24),        # up to 4 taps per axis and phase
+]
+
+
+@pytest.mark.parametrize("case", S2_CASES)
+def test_dgrad_stride2_parity_phases(E, case, monkeypatch):
+    """hn_conv2d_dgrad_s2 (four parity phases onto strided sub-lattices of dX) against autograd, against the zero-insertion
+    form it replaces, and in accumulate mode."""
+    conv, x, dy = _case(case)
+    dx_ref, _ = _ref_grads(conv, x, dy)
+    dx_r, _ = _ref_grads(conv, x, dy, round_bf16=True)
+    convg = copy.deepcopy(conv).cuda()
+    dya = _padded_act(E, dy, torch.bfloat16)
+    assert E.DGRAD_S2_PHASES
+    l0 = E.launch_count
+    dx = E.conv2d_dgrad(dya, convg, x.shape[2], x.shape[3])
+    assert E.launch_count - l0 <= 8, "phase path expected (no dilate / im2col launches)"
+    assert rel(back(dx), dx_r) < 1.2e-2 and rel(back(dx), dx_ref) < BF16_TOL
+    monkeypatch.setattr(E, "DGRAD_S2_PHASES", False)
+    dx_old = E.conv2d_dgrad(dya, convg, x.shape[2], x.shape[3])
+    monkeypatch.setattr(E, "DGRAD_S2_PHASES", True)
+    assert rel(back(dx), back(dx_old)) < 1.2e-2        # same products, different summation order / one BF16 rounding
+    prev = torch.randn(x.shape, generator=torch.Generator().manual_seed(9))
+    out = _padded_act(E, prev, torch.bfloat16)
+    E.conv2d_dgrad(dya, convg, x.shape[2], x.shape[3], out=out, accumulate=True)
+    assert rel(back(out), dx_r + prev.bfloat16().float()) < 1.5e-2
+
+
 def test_dgrad_accumulates_through_epilogue(E):
     conv, x, dy = _case((128, 128, 3, 1, 1, 1, 10, 12))
     dx_ref, _ = _ref_grads(conv, x, dy)

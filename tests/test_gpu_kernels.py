@@ -266,6 +266,53 @@ def test_conv_fused_epilogue_bn_residual_relu(E, dtype, tol):
     assert rel(back(y2), ref2) < tol
 
 
+STAT_CASES = [
+    # cin, cout, k, stride, pad, dil, h, w, bias     -- one case per Cout-tile width / kernel family of the BF16 engine
+    (64, 32, 1, 1, 0, 1, 9, 14, True),         # BLOCK_N = 32 (half of a staging row)
+    (64, 64, 1, 1, 0, 1, 20, 24, False),       # BLOCK_N = 64, alternating epilogue groups
+    (64, 256, 1, 1, 0, 1, 20, 24, False),      # wide tile, two 64-channel chunks per warp
+    (128, 512, 1, 1, 0, 1, 33, 40, False),     # several Cout tiles per pixel tile, ragged last pixel tile
+    (256, 256, 3, 1, 2, 2, 10, 13, False),     # implicit 3x3 with ragged spatial tiles (rows beyond the image must not count)
+    (64, 64, 3, 1, 1, 1, 24, 40, True),        # halo-patch kernel (3x3, narrow output)
+    (128, 128, 3, 2, 1, 1, 21, 24, False),     # strided: im2col + flat path
+    (3, 64, 7, 2, 3, 1, 33, 40, False),        # dense-row stem
+    (256, 100, 1, 1, 0, 1, 12, 16, True),      # Cout not a multiple of the tile: padded channels stay out of the sums
+]
+
+
+@pytest.mark.parametrize("case", STAT_CASES)
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_conv_fused_batch_statistics(E, case, out_dtype):
+    """hn_epilogue.stat_sum / stat_sqsum: the per-channel sum and sum of squares the conv epilogue accumulates equal those of
+    the tensor it stored (FP32 output: of the FP32 values; BF16 output: of the ROUNDED values), over exactly the valid pixels."""
+    cin, cout, k, stride, pad, dil, h, w, bias = case
+    g = torch.Generator().manual_seed(11)
+    conv = nn.Conv2d(cin, cout, k, stride, pad, dil, bias=bias)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * (2.0 / (cin * k * k)) ** 0.5)
+        if bias:
+            conv.bias.copy_(torch.randn(cout, generator=g))
+    conv = conv.cuda()
+    x = torch.randn(3, cin, h, w, generator=g) + 0.5
+    xa = to_act(E, x, torch.bfloat16)
+    sums = torch.zeros((2, cout), dtype=torch.float64, device="cuda")
+    scale, shift = E.folded_affine(conv, None)
+    if E.stem_ok(xa, conv):
+        wp, shift = E.packed_stem_weight(conv, None)
+        y = E.stem_conv(xa, conv, wp, shift, out_dtype=out_dtype, stats=sums)
+    else:
+        ho, wo = E.conv_out_hw(h, w, conv)
+        out = E.new_act(3, ho, wo, cout, out_dtype, "cuda", ld=(cout + 7) // 8 * 8)        # 16-byte aligned pixel stride
+        y = E.conv2d(xa, conv, scale, shift, None, E.ACT_NONE, out=out, stats=sums)
+    stored = y.nchw().double()                              # exactly what the kernel wrote
+    want = torch.stack([stored.sum((0, 2, 3)), (stored * stored).sum((0, 2, 3))])
+    err = ((sums - want).abs() / want.abs().clamp_min(1e-3 * want.abs().max())).max().item()
+    assert err < 2e-5, err                                   # FP32 partial sums per 32-pixel block, FP64 across blocks
+    with torch.no_grad():
+        ref = F.conv2d(x.cuda().bfloat16().float(), conv.weight.bfloat16().float(), conv.bias, stride, pad, dil)
+    assert rel(y.nchw().float(), ref) < 1e-2
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
 def test_conv_into_channel_slice_is_the_concat(E, dtype, tol):
     """Two producers writing channel halves of one buffer == torch.cat(dim=1) (cm/models/extractors.py:192)."""

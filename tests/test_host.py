@@ -42,7 +42,7 @@ def test_struct_layout_matches_header(tmp_path):
     import ctypes as C
     import subprocess
     from heatnet_pub_b200 import _lib
-    structs = {"hn_tensor": _lib.HnTensor, "hn_epilogue": _lib.HnEpilogue, "hn_conv": _lib.HnConv}
+    structs = {"hn_tensor": _lib.HnTensor, "hn_epilogue": _lib.HnEpilogue, "hn_conv": _lib.HnConv, "hn_pack_job": _lib.HnPackJob}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "heatnet_b200.h"', 'int main(void){']
     for cname, st in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
