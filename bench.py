@@ -392,7 +392,13 @@ def measure_train(ctx, args, workload, B, H, W, steps, warmup):
         loss = step()
     sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
     l0 = E.launch_count
+    prof_range = bool(os.environ.get("HN_PROFILE_RANGE"))      # `ncu --profile-from-start off`: only the timed steps are profiled
+    if prof_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     ms, loss = ctx.timed(step, steps)
+    if prof_range:
+        torch.cuda.profiler.stop()
     launches = E.launch_count - l0
     clocks = sampler.stop() if sampler else None
     buckets, nbytes, copied = reducer.last_buckets, reducer.last_bytes, reducer.copied

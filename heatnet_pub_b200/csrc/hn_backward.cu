@@ -80,59 +80,88 @@ __global__ void __launch_bounds__(256) act_bwd_scalar_kernel(const TG *__restric
 // ZOUT = false: `out` is not read; the pre-activation z = fmaf(raw, fscale, fshift) is recomputed with the forward pass's own
 // scale/shift vectors (bit-identical to what the forward activated; only valid for layers without a residual input) -- one
 // tensor less to stream in both passes.
+// blockDim = (CVB, PL): a thread owns ONE 4-channel group and streams its pixels four at a time (every load of a batch is
+// issued before the first use, batches are held packed); 64 registers -> 4 CTAs per SM.
 template <typename TG, typename TO, typename TR, bool ZOUT>
-__global__ void bn_bwd_reduce_kernel(const TG *__restrict__ dout, int ldg, const TO *__restrict__ out, int ldo, const TR *__restrict__ raw,
-                                     int ldr, const float *__restrict__ mean, const float *__restrict__ invstd, int act, float slope,
-                                     const float *slope_ptr, int64_t npix, int C, int64_t pix_per_cta, double *s1, double *s2,
-                                     double *sprelu, const float *__restrict__ fscale, const float *__restrict__ fshift)
+__global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const TG *__restrict__ dout, int ldg, const TO *__restrict__ out, int ldo,
+                                                               const TR *__restrict__ raw, int ldr, const float *__restrict__ mean,
+                                                               const float *__restrict__ invstd, int act, float slope, const float *slope_ptr,
+                                                               int64_t npix, int C, int64_t pix_per_cta, double *s1, double *s2, double *sprelu,
+                                                               const float *__restrict__ fscale, const float *__restrict__ fshift)
 {
-    extern __shared__ float red[];  // [2][PL][CVB*8]
+    extern __shared__ float red[];  // [2][PL][CVB*4]
     const int cv = blockIdx.y * blockDim.x + threadIdx.x;
-    const int ncv = C / 8;
+    const int ncv = C / 4;
     const int PL = blockDim.y, CVB = blockDim.x;
     if (slope_ptr) slope = __ldg(slope_ptr);
-    float a[8], b[8], mu[8], is[8], fs[8], fh[8], sp = 0.f;
+    float a[4], b[4], mu[4], is[4], fs[4], fh[4], sp = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = b[i] = 0.f;
+    for (int i = 0; i < 4; ++i) a[i] = b[i] = 0.f;
     const int64_t p_begin = (int64_t)blockIdx.x * pix_per_cta;
     const int64_t p_end = min(p_begin + pix_per_cta, npix);
     if (cv < ncv) {
-        Vec8<float>::load(mean + cv * 8, mu);
-        Vec8<float>::load(invstd + cv * 8, is);
+        const int c = cv * 4;
+        Vec4<float>::load(mean + c, mu);
+        Vec4<float>::load(invstd + c, is);
         if (!ZOUT) {
-            Vec8<float>::load(fscale + cv * 8, fs);
-            Vec8<float>::load(fshift + cv * 8, fh);
+            Vec4<float>::load(fscale + c, fs);
+            Vec4<float>::load(fshift + c, fh);
         }
-        for (int64_t p = p_begin + threadIdx.y; p < p_end; p += PL) {
-            float g[8], o[8], r[8];
-            Vec8<TG>::load(dout + p * ldg + cv * 8, g);
-            if (ZOUT) Vec8<TO>::load(out + p * ldo + cv * 8, o);
-            Vec8<TR>::load(raw + p * ldr + cv * 8, r);
+        auto one = [&](const float (&g)[4], float (&o)[4], const float (&r)[4]) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 4; ++i) {
                 if (!ZOUT) o[i] = fmaf(r[i], fs[i], fh[i]);                   // z itself: act'(z) == act'(act(z)) for (leaky) ReLU
                 if (sprelu && o[i] < 0.f) sp += g[i] * (ZOUT ? o[i] / slope : o[i]);      // z = out / slope on the negative side
                 const float dz = g[i] * act_grad(o[i], act, slope);
                 a[i] += dz;
                 b[i] = fmaf(dz, (r[i] - mu[i]) * is[i], b[i]);
             }
+        };
+        int64_t p = p_begin + threadIdx.y;
+        for (; p + 3 * PL < p_end; p += 4 * PL) {
+            typename Vec4<TG>::raw_t gv[4];
+            typename Vec4<TO>::raw_t ov[4];
+            typename Vec4<TR>::raw_t rv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) gv[u] = Vec4<TG>::ldraw(dout + (p + u * PL) * ldg + c);
+            if (ZOUT) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) ov[u] = Vec4<TO>::ldraw(out + (p + u * PL) * ldo + c);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rv[u] = Vec4<TR>::ldraw(raw + (p + u * PL) * ldr + c);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float g[4], o[4], r[4];
+                Vec4<TG>::unpack(gv[u], g);
+                if (ZOUT) Vec4<TO>::unpack(ov[u], o);
+                Vec4<TR>::unpack(rv[u], r);
+                one(g, o, r);
+            }
+        }
+        for (; p < p_end; p += PL) {
+            float g[4], o[4], r[4];
+            Vec4<TG>::load(dout + p * ldg + c, g);
+            if (ZOUT) Vec4<TO>::load(out + p * ldo + c, o);
+            Vec4<TR>::load(raw + p * ldr + c, r);
+            one(g, o, r);
         }
     }
-    float *ra = red, *rb = red + PL * CVB * 8;
+    float *ra = red, *rb = red + PL * CVB * 4;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        ra[(threadIdx.y * CVB + threadIdx.x) * 8 + i] = a[i];
-        rb[(threadIdx.y * CVB + threadIdx.x) * 8 + i] = b[i];
+    for (int i = 0; i < 4; ++i) {
+        ra[(threadIdx.y * CVB + threadIdx.x) * 4 + i] = a[i];
+        rb[(threadIdx.y * CVB + threadIdx.x) * 4 + i] = b[i];
     }
     __syncthreads();
     const int tid = threadIdx.y * CVB + threadIdx.x;
-    for (int col = tid; col < CVB * 8; col += CVB * PL) {
+    for (int col = tid; col < CVB * 4; col += CVB * PL) {
         double x = 0.0, y = 0.0;
         for (int l = 0; l < PL; ++l) {
-            x += (double)ra[l * CVB * 8 + col];
-            y += (double)rb[l * CVB * 8 + col];
+            x += (double)ra[l * CVB * 4 + col];
+            y += (double)rb[l * CVB * 4 + col];
         }
-        int ch = blockIdx.y * CVB * 8 + col;
+        int ch = blockIdx.y * CVB * 4 + col;
         if (ch < C) {
             atomicAdd(s1 + ch, x);
             atomicAdd(s2 + ch, y);
@@ -145,91 +174,129 @@ __global__ void bn_bwd_reduce_kernel(const TG *__restrict__ dout, int ldg, const
     }
 }
 
-// blockDim = (CVB, PL) like the reduce pass: a thread keeps ONE 8-channel group for all its pixels, so the per-channel
-// coefficients (FP64 sums -> three FP32 vectors) are formed once per thread and the pixel loop only moves data:
-//   draw = ka*dz + kb*(raw - mean) + kc,   ka = gamma*invstd, kb = -ka*invstd*s2/m, kc = -ka*s1/m
-template <typename TG, typename TO, typename TR, bool ZOUT>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TG *__restrict__ dout, int ldg, const TO *__restrict__ out, int ldo,
-                                                           const TR *__restrict__ raw, int ldr, const float *__restrict__ mean,
-                                                           const float *__restrict__ invstd, const float *__restrict__ gamma,
-                                                           const double *__restrict__ s1, const double *__restrict__ s2, double inv_count,
-                                                           int act, float slope, const float *slope_ptr, TG *__restrict__ draw, int ldd,
-                                                           TG *__restrict__ dres, int ldres, int dres_accumulate, int64_t npix, int C,
-                                                           int64_t pix_per_cta, float *__restrict__ dbeta, float *__restrict__ dgamma,
-                                                           float *__restrict__ dslope, const double *__restrict__ sprelu, int param_accumulate,
-                                                           const float *__restrict__ fscale, const float *__restrict__ fshift)
+// Same thread layout.  The per-channel coefficients (FP64 sums -> FP32) are formed once per CTA in shared memory and RE-READ from
+// there for every batch of four pixels (volatile loads: 5 LDS.128 per 8-12 global loads), so they occupy registers only while a
+// batch is being computed -- with them resident the kernel needed 124 registers (2 CTAs per SM) or spilled its addresses:
+//   draw = ka*dz + kb*raw + kd,   ka = gamma*invstd, kb = -ka*invstd*s2/m, kd = -ka*s1/m - kb*mean;   z = raw*fs + fh
+// DRES: 0 = no residual-branch gradient, 1 = dres = dz, 2 = dres += dz.
+__device__ __forceinline__ void lds_f4_volatile(const float *p, float (&v)[4])
 {
-    const int cv = blockIdx.y * blockDim.x + threadIdx.x;
-    if (cv >= C / 8) return;
-    const int PL = blockDim.y;
-    const int c = cv * 8;
-    if (slope_ptr) slope = __ldg(slope_ptr);
-    if (blockIdx.x == 0 && threadIdx.y == 0) {      // parameter gradients straight from the FP64 sums (no extra launches)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (dbeta) dbeta[c + j] = (param_accumulate ? dbeta[c + j] : 0.f) + (float)s1[c + j];
-            if (dgamma) dgamma[c + j] = (param_accumulate ? dgamma[c + j] : 0.f) + (float)s2[c + j];
-        }
-        if (dslope && sprelu && cv == 0) dslope[0] = (param_accumulate ? dslope[0] : 0.f) + (float)sprelu[0];
-    }
-    float mu[8], ka[8], kb[8], kc[8], fs[8], fh[8];
-    if (!ZOUT) {
-        Vec8<float>::load(fscale + c, fs);
-        Vec8<float>::load(fshift + c, fh);
-    }
-    {
-        float is[8], ga[8];
-        Vec8<float>::load(mean + c, mu);
-        Vec8<float>::load(invstd + c, is);
-        if (gamma) Vec8<float>::load(gamma + c, ga);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float m1 = (float)(s1[c + j] * inv_count), m2 = (float)(s2[c + j] * inv_count);
-            ka[j] = (gamma ? ga[j] : 1.f) * is[j];
-            kb[j] = -ka[j] * is[j] * m2;
-            kc[j] = -ka[j] * m1;
-        }
-    }
-    const int64_t p_begin = (int64_t)blockIdx.x * pix_per_cta;
-    const int64_t p_end = min(p_begin + pix_per_cta, npix);
-    auto one = [&](int64_t p, const float (&g)[8], const float (&o)[8], const float (&r)[8]) {
-        float dx[8], dz[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            dz[j] = g[j] * act_grad(ZOUT ? o[j] : fmaf(r[j], fs[j], fh[j]), act, slope);
-            dx[j] = fmaf(ka[j], dz[j], fmaf(kb[j], r[j] - mu[j], kc[j]));
-        }
-        Vec8<TG>::store(draw + p * ldd + c, dx);
-        if (dres) {
-            if (dres_accumulate) {
-                float e[8];
-                Vec8<TG>::load(dres + p * ldres + c, e);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) dz[j] += e[j];
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+
+template <typename TG, typename TO, typename TR, bool ZOUT, int DRES>
+__global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const TG *__restrict__ dout, int ldg, const TO *__restrict__ out, int ldo,
+                                                              const TR *__restrict__ raw, int ldr, const float *__restrict__ mean,
+                                                              const float *__restrict__ invstd, const float *__restrict__ gamma,
+                                                              const double *__restrict__ s1, const double *__restrict__ s2, double inv_count,
+                                                              int act, float slope, const float *slope_ptr, TG *__restrict__ draw, int ldd,
+                                                              TG *__restrict__ dres, int ldres, int npix, int C, int pix_per_cta,
+                                                              float *__restrict__ dbeta, float *__restrict__ dgamma, float *__restrict__ dslope,
+                                                              const double *__restrict__ sprelu, int param_accumulate,
+                                                              const float *__restrict__ fscale, const float *__restrict__ fshift)
+{
+    __shared__ __align__(16) float s_k[5][128];
+    const int PL = blockDim.y, CVB = blockDim.x;
+    const int tid = threadIdx.y * CVB + threadIdx.x;
+    if (tid < CVB * 4) {
+        const int ch = blockIdx.y * CVB * 4 + tid;
+        if (ch < C) {
+            const double d1 = s1[ch], d2 = s2[ch];
+            if (blockIdx.x == 0) {              // parameter gradients straight from the FP64 sums (no extra launches)
+                if (dbeta) dbeta[ch] = (param_accumulate ? dbeta[ch] : 0.f) + (float)d1;
+                if (dgamma) dgamma[ch] = (param_accumulate ? dgamma[ch] : 0.f) + (float)d2;
+                if (dslope && sprelu && ch == 0) dslope[0] = (param_accumulate ? dslope[0] : 0.f) + (float)sprelu[0];
             }
-            Vec8<TG>::store(dres + p * ldres + c, dz);
+            const float m1 = (float)(d1 * inv_count), m2 = (float)(d2 * inv_count);
+            const float is = invstd[ch], mu = mean[ch];
+            const float ka = (gamma ? gamma[ch] : 1.f) * is;
+            const float kb = -ka * is * m2;
+            s_k[0][tid] = ka;
+            s_k[1][tid] = kb;
+            s_k[2][tid] = -ka * m1 - kb * mu;
+            s_k[3][tid] = ZOUT ? 0.f : fscale[ch];
+            s_k[4][tid] = ZOUT ? 0.f : fshift[ch];
+        }
+    }
+    __syncthreads();
+    const int cv = blockIdx.y * CVB + threadIdx.x;
+    if (cv >= C / 4) return;
+    const int c = cv * 4;
+    if (slope_ptr) slope = __ldg(slope_ptr);
+    dout += c; out += c; raw += c; draw += c;
+    if (DRES) dres += c;
+    const float *kp = &s_k[0][threadIdx.x * 4];
+    const int p_begin = blockIdx.x * pix_per_cta;
+    const int p_end = min(p_begin + pix_per_cta, npix);
+    auto one = [&](int p, const float (&g)[4], const float (&o)[4], const float (&r)[4], const float (&e)[4], const float (&ka)[4],
+                   const float (&kb)[4], const float (&kd)[4], const float (&fs)[4], const float (&fh)[4]) {
+        float dx[4], dz[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            dz[j] = g[j] * act_grad(ZOUT ? o[j] : fmaf(r[j], fs[j], fh[j]), act, slope);
+            dx[j] = fmaf(ka[j], dz[j], fmaf(kb[j], r[j], kd[j]));
+        }
+        Vec4<TG>::store(draw + (int64_t)p * ldd, dx);
+        if (DRES) {
+            if (DRES == 2) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dz[j] += e[j];
+            }
+            Vec4<TG>::store(dres + (int64_t)p * ldres, dz);
         }
     };
-    int64_t p = p_begin + threadIdx.y;
-    for (; p + PL < p_end; p += 2 * PL) {       // two pixels in flight per thread
-        float g0[8], o0[8], r0[8], g1[8], o1[8], r1[8];
-        Vec8<TG>::load(dout + p * ldg + c, g0);
-        Vec8<TG>::load(dout + (p + PL) * ldg + c, g1);
+    int p = p_begin + threadIdx.y;
+    for (; p + 3 * PL < p_end; p += 4 * PL) {
+        typename Vec4<TG>::raw_t gv[4], ev[4];
+        typename Vec4<TO>::raw_t ov[4];
+        typename Vec4<TR>::raw_t rv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) gv[u] = Vec4<TG>::ldraw(dout + (int64_t)(p + u * PL) * ldg);
         if (ZOUT) {
-            Vec8<TO>::load(out + p * ldo + c, o0);
-            Vec8<TO>::load(out + (p + PL) * ldo + c, o1);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ov[u] = Vec4<TO>::ldraw(out + (int64_t)(p + u * PL) * ldo);
         }
-        Vec8<TR>::load(raw + p * ldr + c, r0);
-        Vec8<TR>::load(raw + (p + PL) * ldr + c, r1);
-        one(p, g0, o0, r0);
-        one(p + PL, g1, o1, r1);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) rv[u] = Vec4<TR>::ldraw(raw + (int64_t)(p + u * PL) * ldr);
+        if (DRES == 2) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ev[u] = Vec4<TG>::ldraw(dres + (int64_t)(p + u * PL) * ldres);
+        }
+        float ka[4], kb[4], kd[4], fs[4], fh[4];
+        lds_f4_volatile(kp, ka);
+        lds_f4_volatile(kp + 128, kb);
+        lds_f4_volatile(kp + 256, kd);
+        if (!ZOUT) {
+            lds_f4_volatile(kp + 384, fs);
+            lds_f4_volatile(kp + 512, fh);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float g[4], o[4], r[4], e[4];
+            Vec4<TG>::unpack(gv[u], g);
+            if (ZOUT) Vec4<TO>::unpack(ov[u], o);
+            Vec4<TR>::unpack(rv[u], r);
+            if (DRES == 2) Vec4<TG>::unpack(ev[u], e);
+            one(p + u * PL, g, o, r, e, ka, kb, kd, fs, fh);
+        }
     }
     if (p < p_end) {
-        float g0[8], o0[8], r0[8];
-        Vec8<TG>::load(dout + p * ldg + c, g0);
-        if (ZOUT) Vec8<TO>::load(out + p * ldo + c, o0);
-        Vec8<TR>::load(raw + p * ldr + c, r0);
-        one(p, g0, o0, r0);
+        float ka[4], kb[4], kd[4], fs[4], fh[4];
+        lds_f4_volatile(kp, ka);
+        lds_f4_volatile(kp + 128, kb);
+        lds_f4_volatile(kp + 256, kd);
+        if (!ZOUT) {
+            lds_f4_volatile(kp + 384, fs);
+            lds_f4_volatile(kp + 512, fh);
+        }
+        for (; p < p_end; p += PL) {
+            float g[4], o[4], r[4], e[4];
+            Vec4<TG>::load(dout + (int64_t)p * ldg, g);
+            if (ZOUT) Vec4<TO>::load(out + (int64_t)p * ldo, o);
+            Vec4<TR>::load(raw + (int64_t)p * ldr, r);
+            if (DRES == 2) Vec4<TG>::load(dres + (int64_t)p * ldres, e);
+            one(p, g, o, r, e, ka, kb, kd, fs, fh);
+        }
     }
 }
 
@@ -705,6 +772,90 @@ __global__ void __launch_bounds__(256) pyramid_bwd_kernel(const T *__restrict__ 
     }
 }
 
+// Row form of the same adjoint: a CTA owns one image row (n, h) and a block of 8-channel groups.  Which bins contain h is
+// row-constant; which bins contain each column w (<= 2 per size: adaptive bins overlap by at most one pixel) and their 1/width
+// are tabulated once per CTA in shared memory, so the inner loop is loads and FMAs only (the element-wise kernel above spent
+// ~100 integer instructions on divisions per 16 bytes written: 690 us for a 210 MB gradient).
+template <typename T>
+__global__ void __launch_bounds__(256) pyramid_bwd_rows_kernel(const T *__restrict__ dpool, T *__restrict__ dx, int ldx, int accumulate, int N,
+                                                               int H, int W, int C, PoolSizesB ps)
+{
+    extern __shared__ float tabf[];                       // [4][W][2] 1/width (0 = no such bin), then int [4][W] first bin
+    int *tabi = reinterpret_cast<int *>(tabf + 4 * W * 2);
+    for (int i = threadIdx.x; i < ps.n * W; i += blockDim.x) {
+        const int a = i / W, w = i - a * W, s = ps.s[a];
+        const int c0 = (w * s) / W;
+        int first = -1, k = 0;
+        float inv[2] = {0.f, 0.f};
+        for (int bj = max(c0 - 1, 0); bj <= min(c0 + 1, s - 1) && k < 2; ++bj) {
+            const int w0 = (bj * W) / s, w1 = ((bj + 1) * W + s - 1) / s;
+            if (w < w0 || w >= w1) continue;
+            if (first < 0) first = bj;
+            inv[k++] = 1.f / (float)(w1 - w0);
+        }
+        tabi[a * W + w] = first;
+        tabf[(a * W + w) * 2] = inv[0];
+        tabf[(a * W + w) * 2 + 1] = inv[1];
+    }
+    __syncthreads();
+    const int row = blockIdx.x;       // n*H + h
+    const int n = row / H, h = row - n * H;
+    const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+    if (cv >= C / 8) return;
+    const int c = cv * 8;
+    // row part: per size up to two bins containing h, with 1/height
+    int rb[4][2];
+    float rinv[4][2];
+    int64_t sbase[4];
+    int64_t base = 0;
+    for (int a = 0; a < 4; ++a) {
+        rb[a][0] = rb[a][1] = -1;
+        rinv[a][0] = rinv[a][1] = 0.f;
+        sbase[a] = base;
+        if (a >= ps.n) continue;
+        const int s = ps.s[a];
+        const int b0 = (h * s) / H;
+        int k = 0;
+        for (int bi = max(b0 - 1, 0); bi <= min(b0 + 1, s - 1) && k < 2; ++bi) {
+            const int h0 = (bi * H) / s, h1 = ((bi + 1) * H + s - 1) / s;
+            if (h < h0 || h >= h1) continue;
+            rb[a][k] = bi;
+            rinv[a][k] = 1.f / (float)(h1 - h0);
+            ++k;
+        }
+        base += (int64_t)s * s * N;
+    }
+    T *drow = dx + (int64_t)row * W * ldx + c;
+#pragma unroll 2
+    for (int w = 0; w < W; ++w) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        if (accumulate) Vec8<T>::load(drow + (int64_t)w * ldx, acc);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            if (a >= ps.n) break;
+            const int s = ps.s[a];
+            const int bj0 = tabi[a * W + w];
+#pragma unroll
+            for (int kh = 0; kh < 2; ++kh) {
+                if (rb[a][kh] < 0) continue;
+#pragma unroll
+                for (int kw = 0; kw < 2; ++kw) {
+                    const float iw = tabf[(a * W + w) * 2 + kw];
+                    if (iw == 0.f) continue;
+                    float g[8];
+                    Vec8<T>::load(dpool + (sbase[a] + ((int64_t)n * s + rb[a][kh]) * s + bj0 + kw) * C + c, g);
+                    const float inv = rinv[a][kh] * iw;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(g[j], inv, acc[j]);
+                }
+            }
+        }
+        Vec8<T>::store(drow + (int64_t)w * ldx, acc);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // zero insertion: up[n, h*stride, w*stride, c] = x[n,h,w,c], zeros elsewhere (strided-conv dgrad as a stride-1 conv)
 // ------------------------------------------------------------------------------------------------
@@ -928,31 +1079,36 @@ extern "C" int hn_bn_bwd(const hn_tensor *dout, const hn_tensor *out, const hn_t
     HN_CHECK_ARG(vec8_ok(dout) && vec8_ok(out) && vec8_ok(raw) && vec8_ok(draw) && (!dres || vec8_ok(dres)), "hn_bn_bwd: views must be 8-channel aligned");
     const int C = dout->c;
     const int64_t npix = (int64_t)dout->n * dout->h * dout->w;
+    HN_CHECK_ARG(npix < ((int64_t)1 << 31), "hn_bn_bwd: too many pixels");
     cudaStream_t st = (cudaStream_t)stream;
     HN_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C + 1), st));
     if (npix == 0) return HN_OK;
-    const int ncv = C / 8;
+    const int ncv = C / 4;
     const int CVB = ncv < 32 ? ncv : 32;
     const int PL = 256 / CVB;
     const int cvblocks = (int)cdiv(ncv, CVB);
-    int64_t chunks = cdiv((int64_t)num_sms() * 4, cvblocks);
+    int64_t chunks = cdiv((int64_t)num_sms() * 4, cvblocks);         // reduce pass: one wave of 4 CTAs per SM
     int64_t pix_per_cta = cdiv(npix, chunks);
-    if (pix_per_cta < (int64_t)PL * 8) pix_per_cta = (int64_t)PL * 8;
+    if (pix_per_cta < (int64_t)PL * 16) pix_per_cta = (int64_t)PL * 16;
     chunks = cdiv(npix, pix_per_cta);
     dim3 grid((unsigned)chunks, (unsigned)cvblocks), block(CVB, PL);
-    size_t smem = (size_t)2 * PL * CVB * 8 * sizeof(float);
+    size_t smem = (size_t)2 * PL * CVB * 4 * sizeof(float);
     double *s1 = sums, *s2 = sums + C, *sp = want_prelu_grad ? sums + 2 * C : nullptr;
-    // apply pass: no reduction, so finer pixel chunks (about 8 CTAs per SM)
+    // apply pass: no reduction, so finer pixel chunks (two waves)
     int64_t chunks2 = cdiv((int64_t)num_sms() * 8, cvblocks);
     int64_t pix_per_cta2 = cdiv(npix, chunks2);
-    if (pix_per_cta2 < (int64_t)PL * 4) pix_per_cta2 = (int64_t)PL * 4;
+    if (pix_per_cta2 < (int64_t)PL * 8) pix_per_cta2 = (int64_t)PL * 8;
     chunks2 = cdiv(npix, pix_per_cta2);
     dim3 grid2((unsigned)chunks2, (unsigned)cvblocks);
     const double inv_count = 1.0 / (double)npix;
+#define HN_BN_BWD_ZD(TG, TO, TR, Z, D)                                                                                                    \
+        bn_bwd_apply_kernel<TG, TO, TR, Z, D><<<grid2, block, 0, st>>>((const TG *)dout->ptr, dout->ld, (const TO *)out->ptr, out->ld, (const TR *)raw->ptr, raw->ld, mean, invstd, gamma, s1, s2, inv_count, act, slope, slope_ptr, (TG *)draw->ptr, draw->ld, dres ? (TG *)dres->ptr : nullptr, dres ? dres->ld : 0, (int)npix, C, (int)pix_per_cta2, dbeta, dgamma, want_prelu_grad ? dslope : nullptr, sp, param_accumulate, fwd_scale, fwd_shift)
 #define HN_BN_BWD_Z(TG, TO, TR, Z)                                                                                                       \
     do {                                                                                                                                  \
         bn_bwd_reduce_kernel<TG, TO, TR, Z><<<grid, block, smem, st>>>((const TG *)dout->ptr, dout->ld, (const TO *)out->ptr, out->ld, (const TR *)raw->ptr, raw->ld, mean, invstd, act, slope, slope_ptr, npix, C, pix_per_cta, s1, s2, sp, fwd_scale, fwd_shift); \
-        bn_bwd_apply_kernel<TG, TO, TR, Z><<<grid2, block, 0, st>>>((const TG *)dout->ptr, dout->ld, (const TO *)out->ptr, out->ld, (const TR *)raw->ptr, raw->ld, mean, invstd, gamma, s1, s2, inv_count, act, slope, slope_ptr, (TG *)draw->ptr, draw->ld, dres ? (TG *)dres->ptr : nullptr, dres ? dres->ld : 0, dres_accumulate, npix, C, pix_per_cta2, dbeta, dgamma, want_prelu_grad ? dslope : nullptr, sp, param_accumulate, fwd_scale, fwd_shift); \
+        if (!dres) HN_BN_BWD_ZD(TG, TO, TR, Z, 0);                                                                                        \
+        else if (!dres_accumulate) HN_BN_BWD_ZD(TG, TO, TR, Z, 1);                                                                        \
+        else HN_BN_BWD_ZD(TG, TO, TR, Z, 2);                                                                                              \
     } while (0)
 #define HN_BN_BWD(TG, TO, TR)                                                                                                             \
     do {                                                                                                                                  \
@@ -966,6 +1122,7 @@ extern "C" int hn_bn_bwd(const hn_tensor *dout, const hn_tensor *out, const hn_t
         set_error("hn_bn_bwd: unsupported dtype combination");
         return HN_ERR_ARG;
     }
+#undef HN_BN_BWD_ZD
 #undef HN_BN_BWD
 #undef HN_BN_BWD_Z
     HN_LAUNCH_CHECK();
@@ -1110,8 +1267,20 @@ extern "C" int hn_pyramid_pool_bwd(const void *dpool, const int32_t *sizes, int3
     PoolSizesB ps{};
     ps.n = nsizes;
     for (int i = 0; i < nsizes; ++i) ps.s[i] = sizes[i];
-    dim3 grid = row_grid_b((int64_t)dx->n * dx->h, (int64_t)dx->w * (dx->c / 8));
     cudaStream_t st = (cudaStream_t)stream;
+    const size_t tab_bytes = (size_t)4 * dx->w * 2 * sizeof(float) + (size_t)4 * dx->w * sizeof(int);
+    if (tab_bytes <= 40 * 1024 && (int64_t)dx->n * dx->h <= 0x7fffffff) {
+        const int ncv = dx->c / 8;
+        const int threads = ncv >= 256 ? 256 : (ncv >= 128 ? 128 : (ncv >= 64 ? 64 : 32));
+        dim3 g((unsigned)(dx->n * dx->h), (unsigned)cdiv(ncv, threads));
+        if (dx->dtype == HN_BF16)
+            pyramid_bwd_rows_kernel<bf16><<<g, threads, tab_bytes, st>>>((const bf16 *)dpool, (bf16 *)dx->ptr, dx->ld, accumulate, dx->n, dx->h, dx->w, dx->c, ps);
+        else
+            pyramid_bwd_rows_kernel<float><<<g, threads, tab_bytes, st>>>((const float *)dpool, (float *)dx->ptr, dx->ld, accumulate, dx->n, dx->h, dx->w, dx->c, ps);
+        HN_LAUNCH_CHECK();
+        return HN_OK;
+    }
+    dim3 grid = row_grid_b((int64_t)dx->n * dx->h, (int64_t)dx->w * (dx->c / 8));
     if (dx->dtype == HN_BF16) pyramid_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16 *)dpool, (bf16 *)dx->ptr, dx->ld, accumulate, dx->n, dx->h, dx->w, dx->c, ps);
     else pyramid_bwd_kernel<float><<<grid, 256, 0, st>>>((const float *)dpool, (float *)dx->ptr, dx->ld, accumulate, dx->n, dx->h, dx->w, dx->c, ps);
     HN_LAUNCH_CHECK();

@@ -305,66 +305,86 @@ struct BnTrainFin {
     float *scale, *shift, *save_mean, *save_invstd;
 };
 
+// blockDim = (CVB, PL): a thread keeps ONE 4-channel group (scale / shift in 8 registers) and streams its pixels four at a
+// time (all loads of a batch issued before the first use); 64 registers -> 4 CTAs per SM, i.e. >= 64 KB of loads in flight per SM.
 template <typename TI, typename T>
-__global__ void __launch_bounds__(256) bn_apply_train_kernel(const TI *__restrict__ x, int ldx, const BnTrainFin fin, const T *__restrict__ res,
-                                                             int ldr, int act, float slope, const float *slope_ptr, T *__restrict__ y, int ldy,
-                                                             int64_t npix, int C, int64_t pix_per_cta)
+__global__ void __launch_bounds__(256, 4) bn_apply_train_kernel(const TI *__restrict__ x, int ldx, const BnTrainFin fin, const T *__restrict__ res,
+                                                                int ldr, int act, float slope, const float *slope_ptr, T *__restrict__ y, int ldy,
+                                                                int64_t npix, int C, int64_t pix_per_cta)
 {
-    const int cv = blockIdx.y * blockDim.x + threadIdx.x;
-    if (cv >= C / 8) return;
-    const int PL = blockDim.y, c = cv * 8;
-    if (slope_ptr) slope = __ldg(slope_ptr);
-    float sc[8], sh[8];
-    const bool writer = blockIdx.x == 0 && threadIdx.y == 0;
-    if (writer && cv == 0 && fin.num_batches_tracked) *fin.num_batches_tracked += 1;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const double mean = fin.sum[c + j] / fin.count;
-        double var = fin.sqsum[c + j] / fin.count - mean * mean;
-        if (var < 0) var = 0;
-        const double invstd = 1.0 / sqrt(var + (double)fin.eps);
-        const float g = fin.gamma ? fin.gamma[c + j] : 1.f, b = fin.beta ? fin.beta[c + j] : 0.f;
-        sc[j] = (float)(g * invstd);
-        sh[j] = (float)(b - mean * g * invstd);
-        if (writer) {
-            fin.scale[c + j] = sc[j];
-            fin.shift[c + j] = sh[j];
-            fin.save_mean[c + j] = (float)mean;
-            fin.save_invstd[c + j] = (float)invstd;
-            if (fin.running_mean) {
-                const double unbiased = fin.count > 1 ? var * fin.count / (fin.count - 1.0) : var;
-                fin.running_mean[c + j] = (float)((1.0 - fin.momentum) * fin.running_mean[c + j] + fin.momentum * mean);
-                fin.running_var[c + j] = (float)((1.0 - fin.momentum) * fin.running_var[c + j] + fin.momentum * unbiased);
+    // per-channel scale / shift of this CTA's channel block: one thread per channel (FP64), shared with the other pixel lanes
+    __shared__ float s_sc[128], s_sh[128];
+    const int PL = blockDim.y, CVB = blockDim.x;
+    const int tid = threadIdx.y * CVB + threadIdx.x;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && fin.num_batches_tracked) *fin.num_batches_tracked += 1;
+    if (tid < CVB * 4) {
+        const int ch = blockIdx.y * CVB * 4 + tid;
+        if (ch < C) {
+            const double mean = fin.sum[ch] / fin.count;
+            double var = fin.sqsum[ch] / fin.count - mean * mean;
+            if (var < 0) var = 0;
+            const double invstd = 1.0 / sqrt(var + (double)fin.eps);
+            const float g = fin.gamma ? fin.gamma[ch] : 1.f, b = fin.beta ? fin.beta[ch] : 0.f;
+            const float scv = (float)(g * invstd), shv = (float)(b - mean * g * invstd);
+            s_sc[tid] = scv;
+            s_sh[tid] = shv;
+            if (blockIdx.x == 0) {
+                fin.scale[ch] = scv;
+                fin.shift[ch] = shv;
+                fin.save_mean[ch] = (float)mean;
+                fin.save_invstd[ch] = (float)invstd;
+                if (fin.running_mean) {
+                    const double unbiased = fin.count > 1 ? var * fin.count / (fin.count - 1.0) : var;
+                    fin.running_mean[ch] = (float)((1.0 - fin.momentum) * fin.running_mean[ch] + fin.momentum * mean);
+                    fin.running_var[ch] = (float)((1.0 - fin.momentum) * fin.running_var[ch] + fin.momentum * unbiased);
+                }
             }
         }
     }
+    __syncthreads();
+    const int cv = blockIdx.y * CVB + threadIdx.x;
+    if (cv >= C / 4) return;
+    const int c = cv * 4;
+    if (slope_ptr) slope = __ldg(slope_ptr);
+    float sc[4], sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        sc[j] = s_sc[threadIdx.x * 4 + j];
+        sh[j] = s_sh[threadIdx.x * 4 + j];
+    }
     const int64_t p_begin = (int64_t)blockIdx.x * pix_per_cta;
     const int64_t p_end = min(p_begin + pix_per_cta, npix);
-    auto one = [&](int64_t p, float (&v)[8], const float (&r)[8]) {
+    auto one = [&](int64_t p, float (&v)[4], const float (&r)[4]) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
             v[j] = fmaf(v[j], sc[j], sh[j]);
             if (res) v[j] += r[j];
             v[j] = apply_act(v[j], act, slope);
         }
-        Vec8<T>::store(y + p * ldy + c, v);
+        Vec4<T>::store(y + p * ldy + c, v);
     };
     int64_t p = p_begin + threadIdx.y;
-    for (; p + PL < p_end; p += 2 * PL) {
-        float v0[8], v1[8], r0[8], r1[8];
-        Vec8<TI>::load(x + p * ldx + c, v0);
-        Vec8<TI>::load(x + (p + PL) * ldx + c, v1);
+    for (; p + 3 * PL < p_end; p += 4 * PL) {
+        typename Vec4<TI>::raw_t xv[4];
+        typename Vec4<T>::raw_t rv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xv[u] = Vec4<TI>::ldraw(x + (p + u * PL) * ldx + c);
         if (res) {
-            Vec8<T>::load(res + p * ldr + c, r0);
-            Vec8<T>::load(res + (p + PL) * ldr + c, r1);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rv[u] = Vec4<T>::ldraw(res + (p + u * PL) * ldr + c);
         }
-        one(p, v0, r0);
-        one(p + PL, v1, r1);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float v[4], r[4];
+            Vec4<TI>::unpack(xv[u], v);
+            if (res) Vec4<T>::unpack(rv[u], r);
+            one(p + u * PL, v, r);
+        }
     }
-    if (p < p_end) {
-        float v0[8], r0[8];
-        Vec8<TI>::load(x + p * ldx + c, v0);
-        if (res) Vec8<T>::load(res + p * ldr + c, r0);
+    for (; p < p_end; p += PL) {
+        float v0[4], r0[4];
+        Vec4<TI>::load(x + p * ldx + c, v0);
+        if (res) Vec4<T>::load(res + p * ldr + c, r0);
         one(p, v0, r0);
     }
 }
@@ -1191,13 +1211,13 @@ extern "C" int hn_bn_apply_train(const hn_tensor *x, const double *sum, const do
     using bf16 = __nv_bfloat16;
     BnTrainFin fin{sum, sqsum, (double)count, gamma, beta, eps, momentum, running_mean, running_var, (long long *)num_batches_tracked,
                    scale, shift, save_mean, save_invstd};
-    const int ncv = x->c / 8;
+    const int ncv = x->c / 4;
     const int CVB = ncv < 32 ? ncv : 32;
     const int PL = 256 / CVB;
     const int cvblocks = (int)cdiv(ncv, CVB);
-    int64_t chunks = cdiv((int64_t)num_sms() * 8, cvblocks);
+    int64_t chunks = cdiv((int64_t)num_sms() * 8, cvblocks);       // two waves of 4 CTAs per SM
     int64_t pix_per_cta = cdiv(npix, chunks);
-    if (pix_per_cta < (int64_t)PL * 4) pix_per_cta = (int64_t)PL * 4;
+    if (pix_per_cta < (int64_t)PL * 8) pix_per_cta = (int64_t)PL * 8;
     chunks = cdiv(npix, pix_per_cta);
     dim3 g((unsigned)chunks, (unsigned)cvblocks), b(CVB, PL);
     if (y->dtype == HN_BF16 && x->dtype == HN_BF16)

@@ -97,6 +97,35 @@ template <> struct Vec8<float> {
     }
 };
 
+// 4 channels (8 B of BF16 / 16 B of FP32) <-> 4 floats: the streaming BatchNorm kernels keep per-channel coefficients in registers,
+// and 4 channels per thread (instead of 8) halves that footprint, which buys the occupancy a bandwidth-bound kernel needs
+template <typename T> struct Vec4;
+template <> struct Vec4<__nv_bfloat16> {
+    typedef uint2 raw_t;          // packed form: batches of loads are held packed and widened one pixel at a time
+    static __device__ __forceinline__ raw_t ldraw(const __nv_bfloat16 *p) { return *reinterpret_cast<const uint2 *>(p); }
+    static __device__ __forceinline__ void unpack(const raw_t &raw, float (&v)[4])
+    {
+        v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
+        v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
+    }
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[4]) { unpack(ldraw(p), v); }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float (&v)[4])
+    {
+        uint2 raw;
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+        raw.x = *reinterpret_cast<uint32_t *>(&a);
+        raw.y = *reinterpret_cast<uint32_t *>(&b);
+        *reinterpret_cast<uint2 *>(p) = raw;
+    }
+};
+template <> struct Vec4<float> {
+    typedef float4 raw_t;
+    static __device__ __forceinline__ raw_t ldraw(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+    static __device__ __forceinline__ void unpack(const raw_t &a, float (&v)[4]) { v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
+    static __device__ __forceinline__ void load(const float *p, float (&v)[4]) { unpack(ldraw(p), v); }
+    static __device__ __forceinline__ void store(float *p, const float (&v)[4]) { *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+
 // true when an NHWC view can be accessed in 8-channel vectors
 inline bool vec8_ok(const hn_tensor *t)
 {
@@ -110,6 +139,7 @@ int conv2d_fwd_f32(const hn_tensor *x, const void *w, const hn_conv *cv, const h
 int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn_epilogue *ep, const hn_tensor *y,
                   void *ws, int64_t ws_bytes, cudaStream_t st);
 int64_t conv2d_tc_workspace(const hn_tensor *x, const hn_conv *cv);
+bool conv_implicit_ok(const hn_tensor *x, const hn_conv *cv);     // BF16 implicit GEMM without an im2col workspace (stride 1 or 2)
 struct TcSubConv {              // one parity phase of a stride-2 dgrad (hn_conv2d_dgrad_s2): stride-1 correlation onto a sub-lattice
     int R, S, pad_h, pad_w;     // taps and per-axis padding of the phase's sub-filter
     int out_h, out_w;           // extent of the phase's output lattice

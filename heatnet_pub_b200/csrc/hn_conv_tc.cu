@@ -98,7 +98,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 ++ntl;
                 const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
                 const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
-                const int w_base = tw * p.TW - p.pad_w, h_base = th * p.TH * p.hmul - p.pad;
+                const int w_base = tw * p.TW * p.wmul - p.pad_w, h_base = th * p.TH * p.hmul - p.pad;
                 int kb = 0;
                 for (int r = 0; r < p.R; ++r)
                     for (int s = 0; s < p.S; ++s)
@@ -308,7 +308,7 @@ static PFN_encodeTiled get_encode()
 
 // BF16 tensor map over up to 4 dims (innermost first), 128B swizzle, zero OOB fill
 int make_tmap(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box,
-              CUtensorMapDataType dtype, CUtensorMapSwizzle swizzle)
+              CUtensorMapDataType dtype, CUtensorMapSwizzle swizzle, const uint32_t *elem_strides)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) {
@@ -321,7 +321,7 @@ int make_tmap(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, 
     for (int i = 0; i < rank; ++i) {
         gd[i] = dims[i];
         bx[i] = box[i];
-        es[i] = 1;
+        es[i] = elem_strides ? elem_strides[i] : 1;
         if (i > 0) gs[i - 1] = strides_bytes[i];
     }
     CUresult r = enc(m, dtype, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, es,
@@ -336,10 +336,15 @@ int make_tmap(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, 
     return HN_OK;
 }
 
+// Implicit GEMM straight from the NHWC input: stride 1, and stride 2 through a tensor map whose box traverses the pixel axes with
+// element stride 2 (the TMA unit then delivers every other pixel of every other row: no im2col workspace for the critics' 4x4 s2
+// convolutions, layer2.0's 3x3 s2 / 1x1 s2).  HN_NO_STRIDED_TMA=1 falls back to the im2col gather.
 static bool implicit_ok(const hn_tensor *x, const hn_conv *cv)
 {
-    return cv->stride == 1 && x->c % 64 == 0 && x->ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x->ptr) & 15) == 0;
+    static const bool no_strided = getenv("HN_NO_STRIDED_TMA") != nullptr;
+    return (cv->stride == 1 || (cv->stride == 2 && !no_strided)) && x->c % 64 == 0 && x->ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x->ptr) & 15) == 0;
 }
+bool conv_implicit_ok(const hn_tensor *x, const hn_conv *cv) { return implicit_ok(x, cv); }
 
 int64_t conv2d_tc_workspace(const hn_tensor *x, const hn_conv *cv)
 {
@@ -379,10 +384,10 @@ int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn
     HN_CHECK_ARG((reinterpret_cast<uintptr_t>(w) & 15) == 0, "conv_tc: packed weights must be 16-byte aligned");
 
     TcParams p{};
-    p.hmul = 1;
+    p.hmul = p.wmul = 1;
     CUtensorMap ta, tb;
     const bool implicit = implicit_ok(x, cv);
-    const bool flat = !implicit || (cv->r == 1 && cv->s == 1 && cv->pad == 0);
+    const bool flat = !implicit || (cv->r == 1 && cv->s == 1 && cv->pad == 0 && cv->stride == 1);
     if (flat) {
         // A is a dense-or-strided [M][K] matrix: the NHWC view itself (1x1 s1) or the im2col workspace
         const void *abase = x->ptr;
@@ -421,11 +426,14 @@ int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn
         p.TH = menu[best][0]; p.TW = menu[best][1];
         uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
         uint64_t strides[4] = {2, (uint64_t)x->ld * 2, (uint64_t)x->ld * 2 * x->w, (uint64_t)x->ld * 2 * x->w * x->h};
-        uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
-        int rc = make_tmap(&ta, x->ptr, 4, dims, strides, box);
+        const uint32_t st_ = (uint32_t)cv->stride;
+        uint32_t box[4] = {64, (uint32_t)p.TW * st_, (uint32_t)p.TH * st_, 1};      // traversed extent: TW x TH pixels at stride st_
+        uint32_t es[4] = {1, st_, st_, 1};
+        int rc = make_tmap(&ta, x->ptr, 4, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B, es);
         if (rc) return rc;
         p.tiles_w = (int)cdiv(Wo, p.TW); p.tiles_h = (int)cdiv(Ho, p.TH); p.n_img = x->n;
         p.Ho = Ho; p.Wo = Wo;
+        p.hmul = p.wmul = cv->stride;
         p.R = cv->r; p.S = cv->s; p.pad = p.pad_w = cv->pad; p.dil = cv->dil; p.cblocks = x->c / 64;
     }
     const int num_m_tiles = p.n_img * p.tiles_h * p.tiles_w;
@@ -512,7 +520,7 @@ int conv2d_fwd_tc_sub(const hn_tensor *x, const void *w, int cout, const TcSubCo
     const int kpad = hn_conv_kpad(x->c, sc->R, sc->S);
     const int cout_pad = hn_conv_cout_pad(cout, HN_BF16);
     TcParams p{};
-    p.hmul = 1;
+    p.hmul = p.wmul = 1;
     const int menu[5][2] = {{8, 16}, {4, 32}, {16, 8}, {2, 64}, {1, 128}};
     int best = 0;
     int64_t best_area = -1;
@@ -598,7 +606,7 @@ int conv_stem_tc(const hn_tensor *xpad, const void *w, int cout, const hn_epilog
     HN_CHECK_ARG(cout_pad == 64, "conv_stem: Cout must be 64 (got %d)", cout);
     constexpr int BK = 32, KTOT = 7 * BK;
     TcParams p{};
-    p.hmul = 2;
+    p.hmul = 2; p.wmul = 1;
     p.TH = 1; p.TW = 128;
     p.tiles_w = (int)cdiv(Wo, 128); p.tiles_h = Ho; p.n_img = y->n;
     p.Ho = Ho; p.Wo = Wo;

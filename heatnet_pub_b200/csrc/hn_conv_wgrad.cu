@@ -27,6 +27,7 @@ struct WgParams {
     int tiles_w, tiles_h, n_img;    // pixel patches: n_img * tiles_h * tiles_w k-blocks in total
     int TH, TW;                     // TH*TW = 64
     int taps, S, pad, dil;          // taps = R*S (1 in flat mode)
+    int stride;                     // conv stride (1 or 2): X patch of tap (r,s) starts at (dY patch origin) * stride + tap * dil - pad
     int m_tiles;                    // Cout / 128 tiles
     int cblocks;                    // 64-column blocks per tap (Cin / 64, or Kpad / 64 in flat mode)
     int blocks_total;               // taps * cblocks: the packed gradient row is blocks_total * 64 columns, block = tap * cblocks + cb
@@ -44,13 +45,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
     constexpr int A_BYTES = 2 * WG_BLOCK_BYTES;              // 128 couts = 2 blocks
     constexpr int B_BYTES = (BN / 64) * WG_BLOCK_BYTES;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr int ACC_COLS = BN < 32 ? 32 : BN;
+    constexpr int TMEM_COLS = 2 * ACC_COLS;          // two accumulators: the epilogue (red.global.add) of item i overlaps the main loop of item i+1
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
-    uint64_t *full_bar = bars, *empty_bar = bars + STAGES, *tfull_bar = bars + 2 * STAGES, *tempty_bar = bars + 2 * STAGES + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 2);
+    uint64_t *full_bar = bars, *empty_bar = bars + STAGES, *tfull_bar = bars + 2 * STAGES, *tempty_bar = bars + 2 * STAGES + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
     float *tr_buf = reinterpret_cast<float *>(tmem_slot + 4);          // 4 epilogue warps x [32][36] floats (16-byte aligned)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -66,8 +68,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
             mbar_init(smem_u32(full_bar + i), 1);
             mbar_init(smem_u32(empty_bar + i), 1);
         }
-        mbar_init(smem_u32(tfull_bar), 1);
-        mbar_init(smem_u32(tempty_bar), 4);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(tfull_bar + i), 1);
+            mbar_init(smem_u32(tempty_bar + i), 4);
+        }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -125,7 +129,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
                             tma_load_4d(sa + b * WG_BLOCK_BYTES, &tmap_dy, fb, mt * WG_M + b * 64, tw * p.TW, th * p.TH, img);
 #pragma unroll
                         for (int b = 0; b < BN / 64; ++b)
-                            if (b < nb) tma_load_4d(sa + A_BYTES + b * WG_BLOCK_BYTES, &tmap_x, fb, bcol[b], tw * p.TW + bdx[b], th * p.TH + bdy[b], img);
+                            if (b < nb) tma_load_4d(sa + A_BYTES + b * WG_BLOCK_BYTES, &tmap_x, fb, bcol[b], tw * p.TW * p.stride + bdx[b], th * p.TH * p.stride + bdy[b], img);
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -136,12 +140,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
         {
             int stage = 0;
             uint32_t phase = 0, acc_phase = 0;
+            int acc = 0;
             for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
                 int mt, blk0, nb, kb0, kb1;
                 decode(item, mt, blk0, nb, kb0, kb1);
                 const uint32_t idesc = make_idesc_bf16_mn(WG_M, 64 * nb);
-                mbar_wait(smem_u32(tempty_bar), acc_phase ^ 1);
+                mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
                 tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(smem_u32(full_bar + stage), phase);
                     tcgen05_fence_after();
@@ -152,29 +158,30 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
 #pragma unroll
                         for (int k = 0; k < WG_KPIX / 16; ++k) {
                             // 16 pixel rows = 2048 B further along K: +128 in the (addr >> 4) field
-                            umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                            umma_bf16(d_tmem, adesc + 128 * k, bdesc + 128 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                         }
                         umma_commit(smem_u32(empty_bar + stage));
-                        if (kb == kb1 - 1) umma_commit(smem_u32(tfull_bar));
+                        if (kb == kb1 - 1) umma_commit(smem_u32(tfull_bar + acc));
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (kb1 <= kb0 && elect_one()) umma_commit(smem_u32(tfull_bar));     // empty split: nothing was issued
+                if (kb1 <= kb0 && elect_one()) umma_commit(smem_u32(tfull_bar + acc));     // empty split: nothing was issued
                 __syncwarp();
-                acc_phase ^= 1;
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
             }
         }
     } else if (warp >= 4) {
         const int q = warp - 4;
         uint32_t acc_phase = 0;
+        int acc = 0;
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
             int mt, blk0, nb, kb0, kb1;
             decode(item, mt, blk0, nb, kb0, kb1);
-            mbar_wait(smem_u32(tfull_bar), acc_phase);
+            mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
             tcgen05_fence_after();
-            acc_phase ^= 1;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
             // Thread = one Cout row of the accumulator.  Adding it straight to the packed gradient would touch 32 rows (32
             // sectors) per warp instruction; instead every 32x32 block goes through a padded shared-memory tile so that one
             // red.global.add.v4.f32 per lane covers 4 rows x 128 contiguous bytes (8x fewer L2 sectors, 4x fewer instructions).
@@ -209,7 +216,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(tempty_bar));
+            if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
         }
     }
     tcgen05_fence_before();
@@ -223,7 +232,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
 template <int BN, int STAGES>
 static int launch_wgrad(const CUtensorMap &tdy, const CUtensorMap &tx, const WgParams &p, cudaStream_t st)
 {
-    constexpr size_t smem = (size_t)STAGES * (2 + BN / 64) * WG_BLOCK_BYTES + (2 * STAGES + 2) * 8 + 16 + 4 * 32 * 36 * 4 + 1024;
+    constexpr size_t smem = (size_t)STAGES * (2 + BN / 64) * WG_BLOCK_BYTES + (2 * STAGES + 4) * 8 + 16 + 4 * 32 * 36 * 4 + 1024;
     static_assert(smem <= 227 * 1024, "wgrad shared memory");
     static bool configured = false;
     if (!configured) {
@@ -247,8 +256,9 @@ int conv2d_wgrad_tc(const hn_tensor *x, const hn_tensor *dy, const hn_conv *cv, 
     const int64_t M = (int64_t)dy->n * dy->h * dy->w;
     if (M == 0) return HN_OK;
     HN_CHECK_ARG((reinterpret_cast<uintptr_t>(dy->ptr) & 15) == 0 && dy->ld % 8 == 0, "conv_wgrad: dY view must be 16-byte aligned");
-    const bool implicit = cv->stride == 1 && x->c % 64 == 0 && x->ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x->ptr) & 15) == 0;
+    const bool implicit = conv_implicit_ok(x, cv);      // stride 2: the X map traverses the pixel axes with element stride 2
     WgParams p{};
+    p.stride = 1;
     CUtensorMap tdy, tx;
     p.Cout = cv->cout;
     p.kpad = kpad;
@@ -265,7 +275,7 @@ int conv2d_wgrad_tc(const hn_tensor *x, const hn_tensor *dy, const hn_conv *cv, 
         }
         p.TH = menu[best][0]; p.TW = menu[best][1];
         p.tiles_h = (int)cdiv(dy->h, p.TH); p.tiles_w = (int)cdiv(dy->w, p.TW); p.n_img = dy->n;
-        p.taps = cv->r * cv->s; p.S = cv->s; p.pad = cv->pad; p.dil = cv->dil;
+        p.taps = cv->r * cv->s; p.S = cv->s; p.pad = cv->pad; p.dil = cv->dil; p.stride = cv->stride;
         ncols = x->c;
         uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
         uint64_t dd[4] = {(uint64_t)dy->c, (uint64_t)dy->w, (uint64_t)dy->h, (uint64_t)dy->n};
@@ -274,7 +284,10 @@ int conv2d_wgrad_tc(const hn_tensor *x, const hn_tensor *dy, const hn_conv *cv, 
         if (rc) return rc;
         uint64_t xd[4] = {(uint64_t)x->c, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
         uint64_t xs[4] = {2, (uint64_t)x->ld * 2, (uint64_t)x->ld * 2 * x->w, (uint64_t)x->ld * 2 * x->w * x->h};
-        rc = make_tmap(&tx, x->ptr, 4, xd, xs, box);
+        const uint32_t st_ = (uint32_t)cv->stride;
+        uint32_t xbox[4] = {64, (uint32_t)p.TW * st_, (uint32_t)p.TH * st_, 1};
+        uint32_t es[4] = {1, st_, st_, 1};
+        rc = make_tmap(&tx, x->ptr, 4, xd, xs, xbox, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B, es);
         if (rc) return rc;
     } else {
         const int64_t need = M * kpad * 2;
@@ -429,8 +442,7 @@ static int conv_out_dim_w(int in, int k, int stride, int pad, int dil) { return 
 extern "C" int64_t hn_conv2d_wgrad_workspace_bytes(const hn_tensor *x, const hn_conv *cv)
 {
     if (!x || !cv || x->dtype != HN_BF16) return 0;
-    const bool implicit = cv->stride == 1 && x->c % 64 == 0 && x->ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x->ptr) & 15) == 0;
-    if (implicit) return 0;
+    if (conv_implicit_ok(x, cv)) return 0;
     const int Ho = conv_out_dim_w(x->h, cv->r, cv->stride, cv->pad, cv->dil), Wo = conv_out_dim_w(x->w, cv->s, cv->stride, cv->pad, cv->dil);
     return (int64_t)x->n * Ho * Wo * hn_conv_kpad(x->c, cv->r, cv->s) * 2;
 }

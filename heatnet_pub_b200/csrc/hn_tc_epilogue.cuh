@@ -23,7 +23,8 @@ struct TcParams {
     int n_tiles;                   // Cout tiles
     int R, S, pad, dil;            // pad = rows; pad_w = columns (equal except for the phases of a strided dgrad)
     int pad_w;
-    int hmul;                      // input row of tap r = (output row) * hmul - pad + r * dil (2 for the stem's window map, else 1)
+    int hmul, wmul;                // input row / column of tap (r, s) = (output row / column) * hmul / wmul - pad + tap * dil: the conv stride
+                                   // (hmul = 2, wmul = 1 for the stem's window map, whose column stride is folded into the map)
     int cblocks;                   // Cin / 64 (flat-from-workspace: kpad / 64 with R=S=1)
     int Cout;
     // epilogue

@@ -220,7 +220,10 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, 
 __host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int m, int n) { return make_idesc_bf16(m, n) | (1u << 15) | (1u << 16); }
 
 // host: driver entry point for tensor-map encoding, BF16/FP32 maps of rank <= 4 with 128B swizzle and zero OOB fill
+// elem_strides (optional, per dimension): traversal stride of the box -- with stride e a box extent of b covers ceil(b / e) elements,
+// which is how a stride-2 convolution samples its input without an im2col pass (scripts/probe_tma_stride.cu)
 int make_tmap(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box,
-              CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B);
+              CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B,
+              const uint32_t *elem_strides = nullptr);
 
 }  // namespace hn

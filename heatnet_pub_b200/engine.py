@@ -171,6 +171,26 @@ class Grads:
             inited = True
         return Act(e[0], act.c, act.coff), inited
 
+    def segments(self, act: "Act", align: int = 64):
+        """Split act's channel range at the boundaries of what already holds gradient -> [(sub-view of the gradient, inited)] when
+        every piece is `align`-channel aligned, else None.  A producer that can write channel sub-ranges separately (conv dgrad:
+        rows of its weight pack) then overwrites the fresh pieces and accumulates into the others, instead of zero-filling the
+        fresh part and accumulating over everything (the x5 slice of the 10240-channel PSP input already holds the critics'
+        gradient when the bottleneck's dgrad arrives: that fill + read was 1.7 GB of traffic per step)."""
+        e = self._entry(act)
+        c0, c1 = act.coff, act.coff + act.c
+        cuts = {c0, c1}
+        for a, b in e[1]:
+            if a < c1 and c0 < b:
+                cuts.update((max(a, c0), min(b, c1)))
+        cuts = sorted(cuts)
+        if len(cuts) <= 2 or any((c - c0) % align for c in cuts):
+            return None
+        out = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            out.append((Act(e[0], b - a, a), self._covered(e[1], a, b)))
+        return out
+
     def _zero_uncovered(self, e, c0, c1):
         c = c0
         for a, b in sorted(e[1]):
@@ -760,8 +780,13 @@ def _conv_param_backward(grads: Grads, tape: Tape, x: Act, conv, dz: Act):
         vec_to_grad(channel_sums(dz)[0], conv.out_channels, out=dst, accumulate=acc)
         grads.param_done(conv.bias)
     if tape.needs(x):
-        gx, inited = grads.target(x)
-        conv2d_dgrad(dz, conv, x.h, x.w, out=gx, accumulate=inited)
+        segs = grads.segments(x) if (conv.stride[0] == 1 and x.dtype == torch.bfloat16) else None
+        if segs is not None:
+            for sub, inited in segs:          # partially initialised target: per channel range, fresh pieces are written, the rest accumulated
+                conv2d_dgrad(dz, conv, x.h, x.w, out=sub, accumulate=inited, cin_range=(sub.coff - x.coff, sub.coff - x.coff + sub.c))
+        else:
+            gx, inited = grads.target(x)
+            conv2d_dgrad(dz, conv, x.h, x.w, out=gx, accumulate=inited)
         grads.mark(x)
 
 
@@ -1091,7 +1116,7 @@ DGRAD_S2_PHASES = os.environ.get("HN_NO_DGRAD_PHASES") is None
 
 
 def conv2d_dgrad(dy: Act, conv: torch.nn.Conv2d, in_h: int, in_w: int, out: Optional[Act] = None,
-                 accumulate: bool = False) -> Act:
+                 accumulate: bool = False, cin_range=None) -> Act:
     """dX of a convolution.  Stride 1: a stride-1 convolution of dY with the flipped, channel-transposed filter.  Stride 2 on the
     BF16 engine: four parity phases, each a stride-1 correlation of dY with a sub-filter, written straight onto its sub-lattice of
     dX (hn_conv2d_dgrad_s2) -- no zero-inserted gradient.  Otherwise (FP32 parity path, odd shapes): zero insertion (hn_dilate)
@@ -1127,7 +1152,12 @@ def conv2d_dgrad(dy: Act, conv: torch.nn.Conv2d, in_h: int, in_w: int, out: Opti
         g = up
     wp = packed_weight_dgrad(conv, dy.dtype)
     res = out if accumulate else None
-    return conv2d_raw(g, wp, conv.in_channels, k, 1, padp, dil, residual=res, out=out)
+    cin = conv.in_channels
+    if cin_range is not None:       # only input channels [a, b): a row range of the pack (rows = input channels), stride-1 form only
+        a, b = cin_range
+        assert st == 1 and a % 64 == 0 and (b - a) % 64 == 0 and out is not None and out.c == b - a
+        wp, cin = wp[a:b], b - a
+    return conv2d_raw(g, wp, cin, k, 1, padp, dil, residual=res, out=out)
 
 
 def conv2d_wgrad(x: Act, dy: Act, conv: torch.nn.Conv2d, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:

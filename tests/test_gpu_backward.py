@@ -51,6 +51,8 @@ GRAD_CASES = [
     (128, 64, 4, 2, 1, 1, 16, 24),       # critic conv1 on x1
     (512, 1, 4, 2, 1, 1, 4, 6),          # critic classifier
     (3, 64, 7, 2, 3, 1, 33, 40),         # RGB stem (wgrad only matters; dgrad checked too)
+    (256, 512, 4, 2, 1, 1, 40, 80),      # stride-2 wgrad through the element-strided X map, several pixel blocks
+    (64, 128, 4, 2, 1, 1, 33, 47),       # odd input, ragged blocks
 ]
 
 

@@ -66,6 +66,8 @@ CONV_CASES = [
     (13, 64, 4, 2, 1, 1, 32, 48, True),       # critic conv1 on logits
     (128, 64, 4, 2, 1, 1, 16, 24, True),      # critic conv1 on x1
     (512, 1, 4, 2, 1, 1, 4, 6, True),         # critic classifier
+    (256, 512, 4, 2, 1, 1, 40, 80, True),     # critic conv4 class at a realistic size: strided tensor map, several pixel tiles
+    (64, 128, 4, 2, 1, 1, 33, 47, True),      # odd input, ragged output tiles
 ]
 
 

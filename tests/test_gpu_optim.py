@@ -129,32 +129,29 @@ def test_captured_step_survives_interleaved_eager_steps():
         for p, g in zip(ps_ref, _grads(s, 5)):
             p.grad = g.cuda()
         opt_ref.step()
-    # graph for steps 0 and 2 (static gradient tensors), eager steps 1 and 3 on fresh gradient tensors
-    ps, opt = make()
-    static = [torch.zeros_like(p) for p in ps]
-    for p, g in zip(ps, static):
-        p.grad = g
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        opt.step()        # warm-up with all-zero gradients: RMSprop leaves parameters and square_avg untouched (0 / (0 + eps))
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        opt.step()
-    for s in range(steps):
-        gs = _grads(s, 5)
-        if s % 2 == 0:
-            for st, g in zip(static, gs):
-                st.copy_(g.cuda())
-            for p, st in zip(ps, static):
-                p.grad = st
-            graph.replay()
-        else:
+    # graph for steps 0 and 2, eager steps 1 and 3 on fresh gradient tensors.  Two captured variants: gradients at static
+    # addresses (table set built by the warm-up, reused by the capture) and gradients allocated inside the capture (graph pool:
+    # the table set is built DURING the capture from a spare pinned pair).
+    from heatnet_pub_b200 import graphs
+    for in_pool in (False, True):
+        ps, opt = make()
+
+        def fn(*gs):
             for p, g in zip(ps, gs):
-                p.grad = g.cuda().clone()                  # new addresses: the eager path builds (and may evict) its own tables
+                p.grad = g * 1.0 if in_pool else g
             opt.step()
-    torch.cuda.synchronize()
-    for a, b in zip(ps_ref, ps):
-        assert torch.allclose(a, b, rtol=1e-6, atol=1e-7)
+            return ps[0]
+
+        zeros = [torch.zeros_like(p) for p in ps]       # warm-up with all-zero gradients: RMSprop leaves parameters and square_avg
+        gstep = graphs.GraphedStep(fn, zeros, warmup=2)  # untouched (0 / (0 + eps)), so the captured sequence starts from scratch
+        for s in range(steps):
+            gs = [g.cuda() for g in _grads(s, 5)]
+            if s % 2 == 0:
+                gstep(*gs)
+            else:
+                for p, g in zip(ps, gs):
+                    p.grad = g.clone()                     # new addresses: the eager path builds (and may evict) its own tables
+                opt.step()
+        torch.cuda.synchronize()
+        for a, b in zip(ps_ref, ps):
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-7), in_pool
