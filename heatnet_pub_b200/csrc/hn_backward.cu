@@ -2,6 +2,7 @@
 // (saved window indices), bilinear and pyramid-pool adjoints (gather form: deterministic, no atomics),
 // zero-insertion for strided-conv dgrad, gradient unpack/accumulate into the OIHW FP32 masters.
 // Same conventions as hn_bandwidth.cu: 8 channels per thread, row-decomposed grids, no 64-bit div/mod per element.
+#include <stdlib.h>
 #include <string.h>
 
 #include "hn_common.cuh"
@@ -599,6 +600,73 @@ __global__ void __launch_bounds__(256) bilinear_up2_bwd_kernel(const TG *__restr
     }
 }
 
+// Walk form of the exact-2x adjoint for the large decoder maps: a thread owns one dx row segment (UP2_SEG input columns) of one
+// 8-channel group and walks it left to right.  Per input column it loads the two NEW dy columns of the four dy rows above it
+// (8 independent 16-byte loads), folds the rows with the row weights into two column sums, and combines them with the two
+// column sums kept from the previous step: the 4-tap column window slides through registers.  Every dy element is loaded by
+// exactly two threads (vertically adjacent rows share two dy rows; the second read hits L1/L2) instead of 2.25 times in 6x6 blocks
+// with ~100 live registers; measured on the three PSPUpsample adjoints of a training step: 252 us -> see profiles/.
+constexpr int UP2_SEG = 16;
+template <typename TG, typename TX>
+__global__ void __launch_bounds__(128) bilinear_up2_bwd_walk_kernel(const TG *__restrict__ dy, int ldy, TX *__restrict__ dx, int ldx, int accumulate,
+                                                                    int N, int H, int W, int C)
+{
+    const int ncv = C / 8;
+    const int Ho = 2 * H, Wo = 2 * W;
+    const int nseg = (W + UP2_SEG - 1) / UP2_SEG;
+    const int row = blockIdx.x;                 // n*H + yi
+    const int n = row / H, yi = row - n * H;
+    const int item = blockIdx.y * blockDim.x + threadIdx.x;
+    if (item >= nseg * ncv) return;
+    const int seg = item / ncv, c = (item - seg * ncv) * 8;
+    float wy[4];
+    up2_adjoint_weights(yi, H, wy);
+    const TG *gbase = dy + ((int64_t)n * Ho * Wo) * ldy + c;
+    // column sum over the (up to) four dy rows 2yi-1 .. 2yi+2 at dy column xo (zero outside the map)
+    auto colsum = [&](int xo, float (&t)[8]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = 0.f;
+        if (xo < 0 || xo >= Wo) return;
+        float g[4][8];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int yo = 2 * yi - 1 + r;
+            if (yo >= 0 && yo < Ho) Vec8<TG>::load(gbase + ((int64_t)yo * Wo + xo) * ldy, g[r]);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g[r][j] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = fmaf(wy[r], g[r][j], t[j]);
+    };
+    const int x0 = seg * UP2_SEG, x1 = min(x0 + UP2_SEG, W);
+    float t0[8], t1[8], t2[8], t3[8];
+    colsum(2 * x0 - 1, t0);
+    colsum(2 * x0, t1);
+    TX *drow = dx + ((int64_t)row * W) * ldx + c;
+    for (int xi = x0; xi < x1; ++xi) {
+        colsum(2 * xi + 1, t2);
+        colsum(2 * xi + 2, t3);
+        float wx[4], v[8];
+        up2_adjoint_weights(xi, W, wx);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(wx[0], t0[j], fmaf(wx[1], t1[j], fmaf(wx[2], t2[j], wx[3] * t3[j])));
+        TX *d = drow + (int64_t)xi * ldx;
+        if (accumulate) {
+            float e[8];
+            Vec8<TX>::load(d, e);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += e[j];
+        }
+        Vec8<TX>::store(d, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { t0[j] = t2[j]; t1[j] = t3[j]; }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // large magnification (PSP priors s x s -> h x w, critic maps x32): the gather form leaves only N*H*W*C/8 threads with a long
 // serial loop each.  Separable two-pass adjoint instead, every element of dy read once by a fully parallel pass:
@@ -606,10 +674,11 @@ __global__ void __launch_bounds__(256) bilinear_up2_bwd_kernel(const TG *__restr
 //   pass B  dx[n, yi, xi, c] (+)= sum_yo wy(yo, yi) tmp[n, yo, xi, c]
 // ------------------------------------------------------------------------------------------------
 constexpr int kSepMaxW = 8;
-template <typename TG>
+template <typename TG, int MAXW>
 __global__ void __launch_bounds__(256) bilinear_bwd_rows_vec_kernel(const TG *__restrict__ dy, int ldy, float *__restrict__ tmp, int64_t nrows,
                                                                     int W, int Wo, int C, float sw)
 {
+    constexpr int kSepMaxW = MAXW;          // accumulator columns held in registers: W <= MAXW (2 / 4 / 8: fewer registers, more loads in flight)
     // one thread: one (n, yo) row x one 8-channel group, all W <= kSepMaxW input columns in registers
     const int ncv = C / 8;
     const int64_t total = nrows * ncv;
@@ -622,12 +691,10 @@ __global__ void __launch_bounds__(256) bilinear_bwd_rows_vec_kernel(const TG *__
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[x][j] = 0.f;
         const TG *g0 = dy + row * Wo * ldy + c;
-        for (int xo = 0; xo < Wo; ++xo) {
+        auto fold = [&](int xo, const float (&g)[8]) {
             int x0, x1;
             float lx;
             bilinear_src_b(xo, sw, W, x0, x1, lx);
-            float g[8];
-            Vec8<TG>::load(g0 + (int64_t)xo * ldy, g);
 #pragma unroll
             for (int x = 0; x < kSepMaxW; ++x) {
                 const float w = (x == x0 ? 1.f - lx : 0.f) + (x == x1 ? lx : 0.f);
@@ -636,6 +703,19 @@ __global__ void __launch_bounds__(256) bilinear_bwd_rows_vec_kernel(const TG *__
                     for (int j = 0; j < 8; ++j) acc[x][j] = fmaf(w, g[j], acc[x][j]);
                 }
             }
+        };
+        int xo = 0;
+        for (; xo + 3 < Wo; xo += 4) {              // four output columns (64 B) in flight per thread
+            float g[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) Vec8<TG>::load(g0 + (int64_t)(xo + u) * ldy, g[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) fold(xo + u, g[u]);
+        }
+        for (; xo < Wo; ++xo) {
+            float g[8];
+            Vec8<TG>::load(g0 + (int64_t)xo * ldy, g);
+            fold(xo, g);
         }
 #pragma unroll
         for (int x = 0; x < kSepMaxW; ++x)
@@ -1209,6 +1289,19 @@ extern "C" int hn_bilinear_bwd(const hn_tensor *dy, const hn_tensor *dx, int32_t
     const bool vec = vec8_ok(dy) && vec8_ok(dx);
     int mode = bilinear_bwd_mode(dy, dx);
     if (mode == 2 && (!workspace || workspace_bytes < hn_bilinear_bwd_workspace_bytes(dy, dx))) mode = 0;   // no scratch: gather form
+    static const bool no_walk = getenv("HN_NO_UP2_BWD_WALK") != nullptr;
+    if (mode == 1 && !no_walk && (int64_t)dx->n * dx->h <= 0x7fffffff && (int64_t)dx->n * dx->h * dx->w * dx->c >= (1 << 18)) {
+        const int nseg = (int)cdiv(dx->w, UP2_SEG);
+        dim3 grid((unsigned)(dx->n * dx->h), (unsigned)cdiv((int64_t)nseg * (dx->c / 8), 128));
+#define HN_UP2_WALK(TG, TX) bilinear_up2_bwd_walk_kernel<TG, TX><<<grid, 128, 0, st>>>((const TG *)dy->ptr, dy->ld, (TX *)dx->ptr, dx->ld, accumulate, dx->n, dx->h, dx->w, dx->c)
+        if (dy->dtype == HN_BF16 && dx->dtype == HN_BF16) HN_UP2_WALK(bf16, bf16);
+        else if (dy->dtype == HN_F32 && dx->dtype == HN_F32) HN_UP2_WALK(float, float);
+        else if (dy->dtype == HN_F32 && dx->dtype == HN_BF16) HN_UP2_WALK(float, bf16);
+        else HN_UP2_WALK(bf16, float);
+#undef HN_UP2_WALK
+        HN_LAUNCH_CHECK();
+        return HN_OK;
+    }
     if (mode == 1) {
         dim3 grid = row_grid_b((int64_t)dx->n * ((dx->h + 1) / 2), (int64_t)((dx->w + 1) / 2) * (dx->c / 8));
 #define HN_UP2_BWD(TG, TX) bilinear_up2_bwd_kernel<TG, TX><<<grid, 256, 0, st>>>((const TG *)dy->ptr, dy->ld, (TX *)dx->ptr, dx->ld, accumulate, dx->n, dx->h, dx->w, dx->c)
@@ -1225,8 +1318,17 @@ extern "C" int hn_bilinear_bwd(const hn_tensor *dy, const hn_tensor *dx, int32_t
         const int64_t nrows = (int64_t)dy->n * dy->h;
         if (vec) {
             const int g1 = wave_grid_b(nrows * (dx->c / 8), 256, 8);
-            if (dy->dtype == HN_BF16) bilinear_bwd_rows_vec_kernel<bf16><<<g1, 256, 0, st>>>((const bf16 *)dy->ptr, dy->ld, tmp, nrows, dx->w, dy->w, dx->c, sw);
-            else bilinear_bwd_rows_vec_kernel<float><<<g1, 256, 0, st>>>((const float *)dy->ptr, dy->ld, tmp, nrows, dx->w, dy->w, dx->c, sw);
+#define HN_ROWS_VEC(TG, MW) bilinear_bwd_rows_vec_kernel<TG, MW><<<g1, 256, 0, st>>>((const TG *)dy->ptr, dy->ld, tmp, nrows, dx->w, dy->w, dx->c, sw)
+            if (dy->dtype == HN_BF16) {
+                if (dx->w <= 2) HN_ROWS_VEC(bf16, 2);
+                else if (dx->w <= 4) HN_ROWS_VEC(bf16, 4);
+                else HN_ROWS_VEC(bf16, 8);
+            } else {
+                if (dx->w <= 2) HN_ROWS_VEC(float, 2);
+                else if (dx->w <= 4) HN_ROWS_VEC(float, 4);
+                else HN_ROWS_VEC(float, 8);
+            }
+#undef HN_ROWS_VEC
         } else {
             const int g1 = wave_grid_b(nrows * dx->w * dx->c, 256, 8);
             if (dy->dtype == HN_BF16) bilinear_bwd_rows_scalar_kernel<bf16><<<g1, 256, 0, st>>>((const bf16 *)dy->ptr, dy->ld, tmp, nrows, dx->w, dy->w, dx->c, sw);

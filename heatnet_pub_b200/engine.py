@@ -326,7 +326,9 @@ def from_nchw(t: torch.Tensor, dtype: torch.dtype, out: Optional[Act] = None) ->
         src = src.float().contiguous()
     n, c, h, w = src.shape
     if out is None:
-        out = new_act(n, h, w, c, dtype, src.device)
+        # wide odd channel counts (the 13-channel logits a critic consumes) get a 16-byte aligned pixel stride so that the vector /
+        # TMA paths apply to the view and to its gradient; 1-4 channel images stay dense (the stems read them as they are)
+        out = new_act(n, h, w, c, dtype, src.device, ld=(c + 7) // 8 * 8 if c > 4 else None)
     assert (out.n, out.h, out.w, out.c) == (n, h, w, c) and out.dtype == dtype
     with _timed("nchw_to_nhwc"):
         _lib.check(_lib.load().hn_nchw_to_nhwc(src.data_ptr(), C.byref(out.hn()), _stream()))

@@ -258,7 +258,8 @@ def test_maxpool_backward(E, dtype, hw):
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
 @pytest.mark.parametrize("sizes", [((6, 6), (40, 80)), ((1, 1), (8, 12)), ((8, 12), (16, 24)), ((41, 60), (82, 120)), ((3, 3), (11, 30)), ((2, 3), (64, 96)),
                                    ((1, 1), (2, 2)), ((5, 7), (10, 14)), ((1, 9), (2, 18)), ((7, 1), (14, 2)),      # exact 2x, odd sizes (2x2 micro-tiles)
-                                   ((2, 2), (40, 80)), ((6, 8), (41, 83)), ((3, 12), (30, 120))])                    # separable two-pass / gather fallback (W > 8)
+                                   ((2, 2), (40, 80)), ((6, 8), (41, 83)), ((3, 12), (30, 120)),                     # separable two-pass / gather fallback (W > 8)
+                                   ((33, 70), (66, 140)), ((48, 49), (96, 98))])                                    # exact 2x, large: walk kernel, ragged last segment
 def test_bilinear_backward(E, dtype, tol, sizes):
     """All three adjoint algorithms (exact-2x micro-tiles, separable two-pass, generic gather) against autograd of
     F.interpolate (= the reference's F.upsample / nn.Upsample), plus the accumulate flag."""
