@@ -73,6 +73,7 @@ SIGNATURES = {
     "hn_prepare_rgb_u8": (C.c_int, [_P, _P, _T, _P]),
     "hn_prepare_ir": (C.c_int, [_P, _I32, _I32, _I32, _P, _T, _P]),
     "hn_rect_drop": (C.c_int, [_T, _P, _P]),
+    "hn_label_scale": (C.c_int, [_T, _P, _P, _I32, _F, _P, _P]),
     "hn_conv3x3_head_fwd": (C.c_int, [_T, _P, _CV, _E, _P, _P, _I32, _P, _P]),
     "hn_bn_batch_stats_scratch_bytes": (_I64, [_I32]),
     "hn_bn_batch_stats": (C.c_int, [_T, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -58,6 +58,30 @@ __global__ void __launch_bounds__(256) rect_drop_kernel(T *__restrict__ x, int l
     }
 }
 
+// IR intensity augmentation of the trainer (cm/train_trgb_segnet_conf.py:101-110,394-410): `ir_day = scale * ir_day` and
+// smartAugment -- for every class l present in the label map the IR pixels of that class are multiplied by their own factor.
+// Every pixel has exactly one label, so the per-class torch.where passes of the reference collapse into ONE gather-multiply:
+// x[n, :, p] *= factor[label[n, p]] (factor == NULL: plain scale by `scale`).  FP32 multiply by an FP32-rounded factor, i.e. what
+// torch does with a Python float scalar: bit-identical.
+template <typename T>
+__global__ void __launch_bounds__(256) label_scale_kernel(T *__restrict__ x, int ld, int C, int64_t npix, const int64_t *__restrict__ labels,
+                                                          const float *__restrict__ factors, int k, float scale, int *__restrict__ flags)
+{
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+        float f = scale;
+        if (factors) {
+            const int64_t l = labels[p];
+            if (l < 0 || l >= k) {
+                if (flags) atomicOr(flags, 1);
+                continue;
+            }
+            f = __ldg(factors + l);
+        }
+        T *d = x + p * ld;
+        for (int c = 0; c < C; ++c) d[c] = from_f32<T>(to_f32<T>(d[c]) * f);
+    }
+}
+
 }  // namespace hn
 
 using namespace hn;
@@ -108,6 +132,22 @@ extern "C" int hn_rect_drop(const hn_tensor *x, const int32_t *params_dev, void 
     cudaStream_t st = (cudaStream_t)stream;
     if (x->dtype == HN_BF16) rect_drop_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16 *)x->ptr, x->ld, x->c, x->h, x->w, params_dev);
     else rect_drop_kernel<float><<<grid, 256, 0, st>>>((float *)x->ptr, x->ld, x->c, x->h, x->w, params_dev);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
+extern "C" int hn_label_scale(const hn_tensor *x, const int64_t *labels_dev, const float *factors_dev, int32_t k, float scale, int32_t *flags_dev,
+                              void *stream)
+{
+    HN_CHECK_ARG(x && x->ptr, "hn_label_scale: null pointer");
+    HN_CHECK_ARG((labels_dev != nullptr) == (factors_dev != nullptr) && (!factors_dev || k >= 1), "hn_label_scale: give labels and factors together");
+    const int64_t npix = (int64_t)x->n * x->h * x->w;
+    if (npix == 0) return HN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x->dtype == HN_BF16)
+        label_scale_kernel<__nv_bfloat16><<<grid_for(npix), 256, 0, st>>>((__nv_bfloat16 *)x->ptr, x->ld, x->c, npix, labels_dev, factors_dev, k, scale, flags_dev);
+    else
+        label_scale_kernel<float><<<grid_for(npix), 256, 0, st>>>((float *)x->ptr, x->ld, x->c, npix, labels_dev, factors_dev, k, scale, flags_dev);
     HN_LAUNCH_CHECK();
     return HN_OK;
 }

@@ -94,3 +94,52 @@ def rectDropTensor(tensor: torch.Tensor, params: torch.Tensor) -> torch.Tensor:
     _lib.check(_lib.load().hn_rect_drop(C.byref(act.hn()), p.data_ptr(), E._stream()))
     E._count()
     return tensor
+
+
+def _as_act(t: torch.Tensor):
+    """NHWC view behind one of our channels-last tensors, or -- for a plain contiguous (N, 1, H, W) tensor, whose NCHW and NHWC
+    layouts coincide -- a zero-copy reinterpretation."""
+    act = E.act_from_view(t)
+    if act is None and t.dim() == 4 and t.shape[1] == 1 and t.is_contiguous() and t.is_cuda and t.dtype in (torch.float32, torch.bfloat16):
+        act = E.Act(t.view(t.shape[0], t.shape[2], t.shape[3], 1))
+    return act
+
+
+def ir_scale_aug(ir: torch.Tensor, scale: float) -> torch.Tensor:
+    """cm/train_trgb_segnet_conf.py:404-406 `ir_day = scale * ir_day`, in place, one launch."""
+    _lib.require_device()
+    act = _as_act(ir)
+    if act is None:
+        return ir.mul_(scale)
+    _lib.check(_lib.load().hn_label_scale(C.byref(act.hn()), None, None, 0, float(scale), None, E._stream()))
+    E._count()
+    return ir
+
+
+def smartAugment(ir_day: torch.Tensor, label_day: torch.Tensor, rng=None) -> torch.Tensor:
+    """cm/train_trgb_segnet_conf.py:101-110: every class present in `label_day` gets its own factor ~ U(0.1, 1.0) and the IR pixels
+    of that class are multiplied by it.  The factors are drawn exactly like the reference draws them -- `random.uniform(0.1, 1.0)`
+    once per entry of `torch.unique(label_day)`, in ascending label order -- so the same `random.seed()` gives the same augmentation;
+    the per-class torch.where passes are one gather-multiply launch (in place)."""
+    import random as _random
+    _lib.require_device()
+    rng = rng or _random
+    labels = label_day.to(torch.int64).contiguous()
+    present = torch.unique(labels).tolist()                      # ascending, like the reference's loop order
+    k = (max(present) + 1) if present else 1
+    if present and min(present) < 0:
+        raise IndexError("smartAugment: negative label")
+    factors = [1.0] * k
+    for l in present:
+        factors[int(l)] = rng.uniform(0.1, 1.0)
+    act = _as_act(ir_day)
+    if act is None:                                               # foreign layout: the reference's own loop
+        for l in present:
+            for b in range(ir_day.shape[0]):
+                ir_day[b] = torch.where(label_day[b] == l, ir_day[b] * factors[int(l)], ir_day[b])
+        return ir_day
+    assert labels.shape == (act.n, act.h, act.w), "label map must be (N, H, W) matching the IR tensor"
+    fdev = torch.tensor(factors, dtype=torch.float32, device=ir_day.device)
+    _lib.check(_lib.load().hn_label_scale(C.byref(act.hn()), labels.data_ptr(), fdev.data_ptr(), k, 1.0, None, E._stream()))
+    E._count()
+    return ir_day

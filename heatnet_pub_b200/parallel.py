@@ -50,7 +50,7 @@ def shard_batch(t: torch.Tensor, rank: int, world: int) -> torch.Tensor:
 
 # ---------------------------------------------------------------------------------------------------- NCCL, stream-ordered
 class _NcclUniqueId(C.Structure):
-    _fields_ = [("internal", C.c_char * 128)]
+    _fields_ = [("internal", C.c_ubyte * 128)]      # c_ubyte, not c_char: a c_char array field reads back truncated at the first NUL
 
 
 _NCCL_FLOAT32, _NCCL_SUM, _NCCL_AVG = 7, 0, 4
@@ -67,10 +67,12 @@ class NcclComm:
         uid = _NcclUniqueId()
         if self.rank == 0:
             self._check(self.lib.ncclGetUniqueId(C.byref(uid)))
-        t = torch.frombuffer(bytearray(bytes(uid.internal) if self.rank == 0 else bytes(128)), dtype=torch.uint8).clone().to(device)
+        raw = C.string_at(C.addressof(uid), 128) if self.rank == 0 else bytes(128)
+        t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone().to(device)
         dist.broadcast(t, 0)
-        raw = bytes(t.cpu().numpy().tobytes())
-        C.memmove(C.byref(uid), raw, 128)
+        raw = t.cpu().numpy().tobytes()
+        assert len(raw) == 128
+        C.memmove(C.addressof(uid), raw, 128)
         self.comm = C.c_void_p()
         with torch.cuda.device(device):
             self._check(self.lib.ncclCommInitRank(C.byref(self.comm), self.world, uid, self.rank))

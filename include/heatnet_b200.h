@@ -193,6 +193,12 @@ int hn_prepare_ir(const void *ir_nhw, int32_t src_bits, int32_t minval, int32_t 
 /* rectDropTensor: x[n, :, r0:r0+dh, c0:c0+dw] = 0, params_dev int32 [N][4] = (r0, c0, dh, dw), Python slice clamping. */
 int hn_rect_drop(const hn_tensor *x, const int32_t *params_dev, void *stream);
 
+/* IR intensity augmentation (cm/train_trgb_segnet_conf.py:101-110 smartAugment, :394-410 ir_scale_aug), in place:
+ * factors_dev == NULL: x *= scale.  Otherwise x[n, :, p] *= factors_dev[labels_dev[n, p]] (labels int64 [N][H][W], factors float [k]);
+ * labels outside [0, k) leave the pixel unchanged and set bit 0 of *flags_dev (optional). */
+int hn_label_scale(const hn_tensor *x, const int64_t *labels_dev, const float *factors_dev, int32_t k, float scale, int32_t *flags_dev,
+                   void *stream);
+
 /* ---- backward (autograd of the ops above; the reference gets these from torch.autograd / cuDNN) ---- */
 /* dz = dout * act'(out), the derivative taken through the saved output (conv + bias + activation layers) */
 int hn_act_bwd(const hn_tensor *dout, const hn_tensor *out, int32_t act, float slope, const hn_tensor *dz, void *stream);

@@ -2,6 +2,7 @@
     cm/thermal_loader.py:649-659   IR clip to [21800, 25000] and (x - min) / (max - min)   (numpy, float64)
     cm/thermal_loader.py:715-728   F.to_tensor + F.normalize(mean .5, std .5) for RGB (FP32) and IR (FP64 -> .float())
     cm/train_trgb_segnet_conf.py:82-86   rectDropTensor
+    cm/train_trgb_segnet_conf.py:101-110,404-406   smartAugment / ir_scale_aug
 torchvision's to_tensor / normalize are restated in plain torch (uint8 HWC -> CHW float / 255; (t - mean) / std) and checked
 against torchvision itself in tests/test_oracle.py when it is importable.  Parity pinned by that check and by construction
 (the product path evaluates the same expressions once per input value); the reference ships no fixtures for its loaders."""
@@ -47,3 +48,18 @@ def rect_drop_tensor(tensor: torch.Tensor, params: torch.Tensor) -> torch.Tensor
     for i in range(tensor.size(0)):
         tensor[i, :, params[i, 0]:(params[i, 0] + params[i, 2]), params[i, 1]:(params[i, 1] + params[i, 3])] = 0
     return tensor
+
+
+def smart_augment(ir_day: torch.Tensor, label_day: torch.Tensor, rng) -> torch.Tensor:
+    """train_trgb_segnet_conf.py:101-110, with the module-level `random` replaced by the generator passed in."""
+    label_indices = torch.unique(label_day)
+    for l in label_indices:
+        factor = rng.uniform(0.1, 1.0)
+        for b in range(ir_day.shape[0]):
+            ir_day[b] = torch.where(label_day[b] == l, ir_day[b] * factor, ir_day[b])
+    return ir_day
+
+
+def ir_scale_aug(ir_day: torch.Tensor, scale: float) -> torch.Tensor:
+    """train_trgb_segnet_conf.py:404-406."""
+    return scale * ir_day

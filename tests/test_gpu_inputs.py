@@ -78,3 +78,40 @@ def test_pipeline_feeds_the_network_zero_copy():
         l0 = E.launch_count
         got, _, _ = net(a, b)
         assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("source", ["plain_nchw", "pipeline_view"])
+def test_smart_augment_and_ir_scale_bit_exact(source):
+    """smartAugment / ir_scale_aug (cm/train_trgb_segnet_conf.py:101-110,404-406) as one gather-multiply launch: bit-identical to
+    the reference's per-class torch.where loop given the same `random` stream, incl. classes absent from the label map (their
+    factors are never drawn) and the order the factors are consumed in."""
+    import random
+    from heatnet_pub_b200 import inputs as I
+    from oracle import inputs_oracle as IO
+    n, h, w = 3, 37, 53
+    g = torch.Generator().manual_seed(4)
+    label = torch.randint(0, 13, (n, h, w), generator=g)
+    label[label == 5] = 7                                  # class 5 absent; 12 present only in image 0
+    label[label == 12] = 0
+    label[0, :3, :3] = 12
+    if source == "plain_nchw":
+        ir = (torch.rand(n, 1, h, w, generator=g) * 2 - 1)
+        dev = ir.cuda()
+    else:
+        counts = torch.randint(21000, 26000, (n, h, w), generator=g, dtype=torch.int32)
+        dev = I.prepare_ir(counts.cuda(), precision="fp32")
+        ir = dev.cpu().contiguous()
+    want = IO.smart_augment(ir.clone(), label, random.Random(99))
+    got = I.smartAugment(dev, label.cuda(), rng=random.Random(99))
+    assert got is dev
+    assert torch.equal(got.cpu().contiguous(), want)
+    # ir_scale_aug: one in-place launch, same FP32 product as `scale * ir_day`
+    scale = random.Random(5).uniform(0.1, 1)
+    assert torch.equal(I.ir_scale_aug(dev, scale).cpu().contiguous(), IO.ir_scale_aug(want, scale))
+    # BF16 pipeline views round once per multiply
+    if source == "pipeline_view":
+        devb = I.prepare_ir(counts.cuda(), precision="bf16")
+        base = devb.float().cpu().contiguous()
+        gotb = I.smartAugment(devb, label.cuda(), rng=random.Random(99)).float().cpu().contiguous()
+        wantb = IO.smart_augment(base.clone(), label, random.Random(99)).bfloat16().float()
+        assert torch.equal(gotb, wantb)

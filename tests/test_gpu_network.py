@@ -266,3 +266,37 @@ def test_graph_replay_after_workspace_growth():
         net._graph_enabled = True
         assert torch.equal(net(rgb, ir)[0], want)
         del junk
+
+
+def test_validate_step_matches_reference_validation_loop():
+    """utils.validate_step == one iteration of cm/validation_bdd_mf.py:281-335: modalities duplicated along the batch, model left in
+    TRAIN mode (batch-statistic BN, active Dropout2d -- masks injected on both sides), first image's argmax, counted into the
+    14 x 14 device confusion matrix; utils.ious_from_confusion == utils.calculate_ious of the reference (cm/utils.py:134-163)
+    evaluated by the oracle's boolean-mask restatement on the same predictions, bit for bit."""
+    from heatnet_pub_b200 import utils
+    from oracle.iou_oracle import calculate_ious_oracle
+    sd = O.recipe_fill(O.pspnet_state_dict(True, 4), seed=0)
+    net = _late_net().train().set_precision("fp32")
+    g = torch.Generator().manual_seed(3)
+    conf = None
+    preds, labels = [], []
+    for it in range(2):
+        rgb, ir = O.synthetic_inputs(1, 64, 96, seed=100 + it)
+        label = torch.randint(0, 14, (1, 64, 96), generator=g)
+        m1 = [(torch.rand(1, c, generator=g) >= p).float() for c, p in ((1024, 0.3), (256, 0.15), (64, 0.15), (64, 0.15))]
+        masks = [torch.cat([m, m]) for m in m1]                       # the duplicated image gets the same mask: any pair works for image 0
+        net._injected_dropout_masks = [m.clone() for m in masks]
+        seg, pred, conf = utils.validate_step(net, [rgb.cuda(), ir.cuda()], label.cuda(), conf)
+        assert seg.shape == (1, 13, 64, 96) and pred.shape == (1, 64, 96) and pred.dtype == torch.int64
+        with torch.no_grad():
+            ref, _, _ = O.pspnet_forward(sd, torch.cat([rgb, rgb]), torch.cat([ir, ir]), late_fusion=True, training=True, dropout_masks=masks)
+        assert rel(seg.cpu(), ref[0:1]) < 1e-4
+        assert (pred.cpu() == ref[0:1].argmax(1)).float().mean().item() >= 0.999
+        assert torch.equal(pred.cpu(), seg.cpu().argmax(1))           # first-max argmax, like torch.argmax
+        preds.append(pred.cpu())
+        labels.append(label)
+    got = utils.ious_from_confusion(conf.conf)
+    want = calculate_ious_oracle(torch.cat(preds).numpy(), torch.cat(labels).numpy())
+    assert got.shape == (12,) and np.array_equal(got, np.asarray(want), equal_nan=True)
+    # the BN running statistics moved (the reference's validation updates them too: it never calls .eval())
+    assert int(net.feats.bn1.num_batches_tracked) == 2
