@@ -21,7 +21,7 @@ class HnTensor(C.Structure):
 class HnEpilogue(C.Structure):
     _fields_ = [("scale", C.c_void_p), ("shift", C.c_void_p), ("residual", C.c_void_p), ("residual_ld", C.c_int32),
                 ("act", C.c_int32), ("slope", C.c_float), ("slope_ptr", C.c_void_p), ("out_nchw", C.c_int32),
-                ("stat_sum", C.c_void_p), ("stat_sqsum", C.c_void_p), ("per_image", C.c_int32)]
+                ("stat_sum", C.c_void_p), ("stat_sqsum", C.c_void_p), ("per_image", C.c_int32), ("stat_groups", C.c_int32)]
 
 
 class HnPackJob(C.Structure):
@@ -68,7 +68,7 @@ SIGNATURES = {
     "hn_bn_finalize_tracked": (C.c_int, [_P, _P, _I64, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _I32, _P]),
     "hn_bn_apply_train": (C.c_int, [_T, _P, _P, _I64, _P, _P, _F, _F, _P, _P, _P, _E, _T, _P, _P, _P, _P, _P]),
     "hn_act_bwd": (C.c_int, [_T, _T, _I32, _F, _T, _P]),
-    "hn_bn_bwd": (C.c_int, [_T, _T, _T, _P, _P, _P, _I32, _F, _P, _P, _T, _T, _I32, _I32, _P, _P, _P, _I32, _P, _P, _P]),
+    "hn_bn_bwd": (C.c_int, [_T, _T, _T, _P, _P, _P, _I32, _F, _P, _P, _T, _T, _I32, _I32, _P, _P, _P, _I32, _P, _P, _I32, _P]),
     "hn_stem_pad_slack_bytes": (_I64, []),
     "hn_prepare_rgb_u8": (C.c_int, [_P, _P, _T, _P]),
     "hn_prepare_ir": (C.c_int, [_P, _I32, _I32, _I32, _P, _T, _P]),

@@ -94,19 +94,23 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const TG *__restr
     const int cv = blockIdx.y * blockDim.x + threadIdx.x;
     const int ncv = C / 4;
     const int PL = blockDim.y, CVB = blockDim.x;
+    const int grp = blockIdx.z;       // statistics group: pixels [grp*npix, (grp+1)*npix), per-group vectors [grp][C], sums [grp][2C+1]
+    s1 += (int64_t)grp * (2 * C + 1);
+    s2 += (int64_t)grp * (2 * C + 1);
+    if (sprelu) sprelu += (int64_t)grp * (2 * C + 1);
     if (slope_ptr) slope = __ldg(slope_ptr);
     float a[4], b[4], mu[4], is[4], fs[4], fh[4], sp = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) a[i] = b[i] = 0.f;
-    const int64_t p_begin = (int64_t)blockIdx.x * pix_per_cta;
-    const int64_t p_end = min(p_begin + pix_per_cta, npix);
+    const int64_t p_begin = (int64_t)grp * npix + (int64_t)blockIdx.x * pix_per_cta;
+    const int64_t p_end = min(p_begin + pix_per_cta, (int64_t)(grp + 1) * npix);
     if (cv < ncv) {
         const int c = cv * 4;
-        Vec4<float>::load(mean + c, mu);
-        Vec4<float>::load(invstd + c, is);
+        Vec4<float>::load(mean + grp * C + c, mu);
+        Vec4<float>::load(invstd + grp * C + c, is);
         if (!ZOUT) {
-            Vec4<float>::load(fscale + c, fs);
-            Vec4<float>::load(fshift + c, fh);
+            Vec4<float>::load(fscale + grp * C + c, fs);
+            Vec4<float>::load(fshift + grp * C + c, fh);
         }
         auto one = [&](const float (&g)[4], float (&o)[4], const float (&r)[4]) {
 #pragma unroll
@@ -199,24 +203,32 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const TG *__restri
     __shared__ __align__(16) float s_k[5][128];
     const int PL = blockDim.y, CVB = blockDim.x;
     const int tid = threadIdx.y * CVB + threadIdx.x;
+    const int grp = blockIdx.z, groups = gridDim.z;     // statistics group (see the reduce kernel)
+    const int gstride = 2 * C + 1;
     if (tid < CVB * 4) {
         const int ch = blockIdx.y * CVB * 4 + tid;
         if (ch < C) {
-            const double d1 = s1[ch], d2 = s2[ch];
-            if (blockIdx.x == 0) {              // parameter gradients straight from the FP64 sums (no extra launches)
-                if (dbeta) dbeta[ch] = (param_accumulate ? dbeta[ch] : 0.f) + (float)d1;
-                if (dgamma) dgamma[ch] = (param_accumulate ? dgamma[ch] : 0.f) + (float)d2;
-                if (dslope && sprelu && ch == 0) dslope[0] = (param_accumulate ? dslope[0] : 0.f) + (float)sprelu[0];
+            const double d1 = s1[grp * gstride + ch], d2 = s2[grp * gstride + ch];
+            if (blockIdx.x == 0 && grp == 0) {  // parameter gradients straight from the FP64 sums (no extra launches), summed over the groups
+                double t1 = 0.0, t2 = 0.0, tp = 0.0;
+                for (int q = 0; q < groups; ++q) {
+                    t1 += s1[q * gstride + ch];
+                    t2 += s2[q * gstride + ch];
+                    if (sprelu) tp += sprelu[q * gstride];
+                }
+                if (dbeta) dbeta[ch] = (param_accumulate ? dbeta[ch] : 0.f) + (float)t1;
+                if (dgamma) dgamma[ch] = (param_accumulate ? dgamma[ch] : 0.f) + (float)t2;
+                if (dslope && sprelu && ch == 0) dslope[0] = (param_accumulate ? dslope[0] : 0.f) + (float)tp;
             }
             const float m1 = (float)(d1 * inv_count), m2 = (float)(d2 * inv_count);
-            const float is = invstd[ch], mu = mean[ch];
+            const float is = invstd[grp * C + ch], mu = mean[grp * C + ch];
             const float ka = (gamma ? gamma[ch] : 1.f) * is;
             const float kb = -ka * is * m2;
             s_k[0][tid] = ka;
             s_k[1][tid] = kb;
             s_k[2][tid] = -ka * m1 - kb * mu;
-            s_k[3][tid] = ZOUT ? 0.f : fscale[ch];
-            s_k[4][tid] = ZOUT ? 0.f : fshift[ch];
+            s_k[3][tid] = ZOUT ? 0.f : fscale[grp * C + ch];
+            s_k[4][tid] = ZOUT ? 0.f : fshift[grp * C + ch];
         }
     }
     __syncthreads();
@@ -227,8 +239,8 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const TG *__restri
     dout += c; out += c; raw += c; draw += c;
     if (DRES) dres += c;
     const float *kp = &s_k[0][threadIdx.x * 4];
-    const int p_begin = blockIdx.x * pix_per_cta;
-    const int p_end = min(p_begin + pix_per_cta, npix);
+    const int p_begin = grp * npix + blockIdx.x * pix_per_cta;
+    const int p_end = min(p_begin + pix_per_cta, (grp + 1) * npix);
     auto one = [&](int p, const float (&g)[4], const float (&o)[4], const float (&r)[4], const float (&e)[4], const float (&ka)[4],
                    const float (&kb)[4], const float (&kd)[4], const float (&fs)[4], const float (&fh)[4]) {
         float dx[4], dz[4];
@@ -1148,8 +1160,9 @@ extern "C" int hn_act_bwd(const hn_tensor *dout, const hn_tensor *out, int32_t a
 extern "C" int hn_bn_bwd(const hn_tensor *dout, const hn_tensor *out, const hn_tensor *raw, const float *mean, const float *invstd,
                          const float *gamma, int32_t act, float slope, const float *slope_ptr, double *sums /* [2*C + 1] scratch+result */,
                          const hn_tensor *draw, const hn_tensor *dres, int32_t dres_accumulate, int32_t want_prelu_grad, float *dbeta, float *dgamma,
-                         float *dslope, int32_t param_accumulate, const float *fwd_scale, const float *fwd_shift, void *stream)
+                         float *dslope, int32_t param_accumulate, const float *fwd_scale, const float *fwd_shift, int32_t groups, void *stream)
 {
+    if (groups < 1) groups = 1;
     HN_CHECK_ARG(dout && out && raw && mean && invstd && sums && draw, "hn_bn_bwd: null pointer");
     HN_CHECK_ARG((fwd_scale != nullptr) == (fwd_shift != nullptr), "hn_bn_bwd: give both forward vectors or neither");
     const bool zout = fwd_scale == nullptr;      // read the saved output; else recompute z = raw*scale + shift
@@ -1158,10 +1171,11 @@ extern "C" int hn_bn_bwd(const hn_tensor *dout, const hn_tensor *out, const hn_t
     HN_CHECK_ARG(dout->dtype == draw->dtype && (!dres || dres->dtype == dout->dtype), "hn_bn_bwd: gradient dtypes must match");
     HN_CHECK_ARG(vec8_ok(dout) && vec8_ok(out) && vec8_ok(raw) && vec8_ok(draw) && (!dres || vec8_ok(dres)), "hn_bn_bwd: views must be 8-channel aligned");
     const int C = dout->c;
-    const int64_t npix = (int64_t)dout->n * dout->h * dout->w;
-    HN_CHECK_ARG(npix < ((int64_t)1 << 31), "hn_bn_bwd: too many pixels");
+    HN_CHECK_ARG(dout->n % groups == 0, "hn_bn_bwd: %d images do not split into %d statistics groups", dout->n, groups);
+    HN_CHECK_ARG((int64_t)dout->n * dout->h * dout->w < ((int64_t)1 << 31), "hn_bn_bwd: too many pixels");
+    const int64_t npix = (int64_t)(dout->n / groups) * dout->h * dout->w;      // per statistics group
     cudaStream_t st = (cudaStream_t)stream;
-    HN_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C + 1), st));
+    HN_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C + 1) * groups, st));
     if (npix == 0) return HN_OK;
     const int ncv = C / 4;
     const int CVB = ncv < 32 ? ncv : 32;
@@ -1171,7 +1185,7 @@ extern "C" int hn_bn_bwd(const hn_tensor *dout, const hn_tensor *out, const hn_t
     int64_t pix_per_cta = cdiv(npix, chunks);
     if (pix_per_cta < (int64_t)PL * 16) pix_per_cta = (int64_t)PL * 16;
     chunks = cdiv(npix, pix_per_cta);
-    dim3 grid((unsigned)chunks, (unsigned)cvblocks), block(CVB, PL);
+    dim3 grid((unsigned)chunks, (unsigned)cvblocks, (unsigned)groups), block(CVB, PL);
     size_t smem = (size_t)2 * PL * CVB * 4 * sizeof(float);
     double *s1 = sums, *s2 = sums + C, *sp = want_prelu_grad ? sums + 2 * C : nullptr;
     // apply pass: no reduction, so finer pixel chunks (two waves)
@@ -1179,7 +1193,7 @@ extern "C" int hn_bn_bwd(const hn_tensor *dout, const hn_tensor *out, const hn_t
     int64_t pix_per_cta2 = cdiv(npix, chunks2);
     if (pix_per_cta2 < (int64_t)PL * 8) pix_per_cta2 = (int64_t)PL * 8;
     chunks2 = cdiv(npix, pix_per_cta2);
-    dim3 grid2((unsigned)chunks2, (unsigned)cvblocks);
+    dim3 grid2((unsigned)chunks2, (unsigned)cvblocks, (unsigned)groups);
     const double inv_count = 1.0 / (double)npix;
 #define HN_BN_BWD_ZD(TG, TO, TR, Z, D)                                                                                                    \
         bn_bwd_apply_kernel<TG, TO, TR, Z, D><<<grid2, block, 0, st>>>((const TG *)dout->ptr, dout->ld, (const TO *)out->ptr, out->ld, (const TR *)raw->ptr, raw->ld, mean, invstd, gamma, s1, s2, inv_count, act, slope, slope_ptr, (TG *)draw->ptr, draw->ld, dres ? (TG *)dres->ptr : nullptr, dres ? dres->ld : 0, (int)npix, C, (int)pix_per_cta2, dbeta, dgamma, want_prelu_grad ? dslope : nullptr, sp, param_accumulate, fwd_scale, fwd_shift)

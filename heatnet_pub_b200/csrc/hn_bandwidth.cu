@@ -296,7 +296,9 @@ __global__ void __launch_bounds__(256) affine_act_fixed_kernel(const TI *__restr
 // also write the vectors the backward needs (scale, shift, mean, invstd) and update the running statistics.  Removes one tiny
 // launch per BN layer (158 per training step).
 struct BnTrainFin {
-    const double *sum, *sqsum;
+    const double *sum, *sqsum;      // [groups][C] each
+    int groups;                     // image groups with separate statistics (blockIdx.z = group); scale .. save_invstd are [groups][C]
+    int64_t group_pix;              // pixels per group
     double count;
     const float *gamma, *beta;
     float eps, momentum;
@@ -316,12 +318,13 @@ __global__ void __launch_bounds__(256, 4) bn_apply_train_kernel(const TI *__rest
     __shared__ float s_sc[128], s_sh[128];
     const int PL = blockDim.y, CVB = blockDim.x;
     const int tid = threadIdx.y * CVB + threadIdx.x;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && fin.num_batches_tracked) *fin.num_batches_tracked += 1;
+    const int grp = blockIdx.z;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && grp == 0 && tid == 0 && fin.num_batches_tracked) *fin.num_batches_tracked += fin.groups;
     if (tid < CVB * 4) {
         const int ch = blockIdx.y * CVB * 4 + tid;
         if (ch < C) {
-            const double mean = fin.sum[ch] / fin.count;
-            double var = fin.sqsum[ch] / fin.count - mean * mean;
+            const double mean = fin.sum[grp * C + ch] / fin.count;
+            double var = fin.sqsum[grp * C + ch] / fin.count - mean * mean;
             if (var < 0) var = 0;
             const double invstd = 1.0 / sqrt(var + (double)fin.eps);
             const float g = fin.gamma ? fin.gamma[ch] : 1.f, b = fin.beta ? fin.beta[ch] : 0.f;
@@ -329,14 +332,24 @@ __global__ void __launch_bounds__(256, 4) bn_apply_train_kernel(const TI *__rest
             s_sc[tid] = scv;
             s_sh[tid] = shv;
             if (blockIdx.x == 0) {
-                fin.scale[ch] = scv;
-                fin.shift[ch] = shv;
-                fin.save_mean[ch] = (float)mean;
-                fin.save_invstd[ch] = (float)invstd;
-                if (fin.running_mean) {
-                    const double unbiased = fin.count > 1 ? var * fin.count / (fin.count - 1.0) : var;
-                    fin.running_mean[ch] = (float)((1.0 - fin.momentum) * fin.running_mean[ch] + fin.momentum * mean);
-                    fin.running_var[ch] = (float)((1.0 - fin.momentum) * fin.running_var[ch] + fin.momentum * unbiased);
+                fin.scale[grp * C + ch] = scv;
+                fin.shift[grp * C + ch] = shv;
+                fin.save_mean[grp * C + ch] = (float)mean;
+                fin.save_invstd[grp * C + ch] = (float)invstd;
+                if (fin.running_mean && grp == 0) {
+                    // the groups are consecutive forward calls of the reference (day batch, then night batch): one momentum
+                    // update per group, in order, by the same thread
+                    float rm = fin.running_mean[ch], rv = fin.running_var[ch];
+                    for (int q = 0; q < fin.groups; ++q) {
+                        const double mq = fin.sum[q * C + ch] / fin.count;
+                        double vq = fin.sqsum[q * C + ch] / fin.count - mq * mq;
+                        if (vq < 0) vq = 0;
+                        const double unbiased = fin.count > 1 ? vq * fin.count / (fin.count - 1.0) : vq;
+                        rm = (float)((1.0 - fin.momentum) * rm + fin.momentum * mq);
+                        rv = (float)((1.0 - fin.momentum) * rv + fin.momentum * unbiased);
+                    }
+                    fin.running_mean[ch] = rm;
+                    fin.running_var[ch] = rv;
                 }
             }
         }
@@ -352,8 +365,9 @@ __global__ void __launch_bounds__(256, 4) bn_apply_train_kernel(const TI *__rest
         sc[j] = s_sc[threadIdx.x * 4 + j];
         sh[j] = s_sh[threadIdx.x * 4 + j];
     }
-    const int64_t p_begin = (int64_t)blockIdx.x * pix_per_cta;
-    const int64_t p_end = min(p_begin + pix_per_cta, npix);
+    const int64_t g_begin = (int64_t)grp * fin.group_pix;                   // this group's pixel range (npix = pixels per group)
+    const int64_t p_begin = g_begin + (int64_t)blockIdx.x * pix_per_cta;
+    const int64_t p_end = min(p_begin + pix_per_cta, g_begin + npix);
     auto one = [&](int64_t p, float (&v)[4], const float (&r)[4]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -1200,16 +1214,19 @@ extern "C" int hn_bn_apply_train(const hn_tensor *x, const double *sum, const do
                                  int64_t *num_batches_tracked, const hn_epilogue *ep, const hn_tensor *y, float *scale, float *shift,
                                  float *save_mean, float *save_invstd, void *stream)
 {
+    const int groups = ep && ep->stat_groups > 1 ? ep->stat_groups : 1;
     HN_CHECK_ARG(x && y && ep && sum && sqsum && scale && shift && save_mean && save_invstd && x->ptr && y->ptr, "hn_bn_apply_train: null pointer");
     HN_CHECK_ARG(x->dtype == y->dtype || (x->dtype == HN_F32 && y->dtype == HN_BF16), "hn_bn_apply_train: x/y dtypes must match, or FP32 -> BF16");
     HN_CHECK_ARG(x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c, "hn_bn_apply_train: shape mismatch");
     HN_CHECK_ARG(vec8_ok(x) && vec8_ok(y), "hn_bn_apply_train: views must be 8-channel aligned");
     HN_CHECK_ARG(count > 0 && (running_mean != nullptr) == (running_var != nullptr), "hn_bn_apply_train: bad count / running statistics");
-    const int64_t npix = (int64_t)x->n * x->h * x->w;
+    HN_CHECK_ARG(x->n % groups == 0, "hn_bn_apply_train: %d images do not split into %d statistics groups", x->n, groups);
+    const int64_t npix = (int64_t)(x->n / groups) * x->h * x->w;          // per group; `count` is the per-group pixel count too
     if (npix == 0) return HN_OK;
+    HN_CHECK_ARG(count == npix, "hn_bn_apply_train: count must be the number of pixels per statistics group");
     cudaStream_t st = (cudaStream_t)stream;
     using bf16 = __nv_bfloat16;
-    BnTrainFin fin{sum, sqsum, (double)count, gamma, beta, eps, momentum, running_mean, running_var, (long long *)num_batches_tracked,
+    BnTrainFin fin{sum, sqsum, groups, npix, (double)count, gamma, beta, eps, momentum, running_mean, running_var, (long long *)num_batches_tracked,
                    scale, shift, save_mean, save_invstd};
     const int ncv = x->c / 4;
     const int CVB = ncv < 32 ? ncv : 32;
@@ -1219,7 +1236,7 @@ extern "C" int hn_bn_apply_train(const hn_tensor *x, const double *sum, const do
     int64_t pix_per_cta = cdiv(npix, chunks);
     if (pix_per_cta < (int64_t)PL * 8) pix_per_cta = (int64_t)PL * 8;
     chunks = cdiv(npix, pix_per_cta);
-    dim3 g((unsigned)chunks, (unsigned)cvblocks), b(CVB, PL);
+    dim3 g((unsigned)chunks, (unsigned)cvblocks, (unsigned)groups), b(CVB, PL);
     if (y->dtype == HN_BF16 && x->dtype == HN_BF16)
         bn_apply_train_kernel<bf16, bf16><<<g, b, 0, st>>>((const bf16 *)x->ptr, x->ld, fin, (const bf16 *)ep->residual, ep->residual_ld, ep->act,
                                                            ep->slope, ep->slope_ptr, (bf16 *)y->ptr, y->ld, npix, x->c, pix_per_cta);

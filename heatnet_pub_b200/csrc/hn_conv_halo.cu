@@ -390,6 +390,7 @@ int conv2d_fwd_halo(const hn_tensor *x, const void *w, const hn_conv *cv, const 
     p.scale = ep->scale; p.shift = ep->shift; p.res = ep->residual; p.ldr = ep->residual_ld;
     p.act = ep->act; p.slope = ep->slope; p.slope_ptr = ep->slope_ptr;
     p.stat_sum = ep->stat_sum; p.stat_sqsum = ep->stat_sqsum;
+    if (int rcg = set_stat_groups(p, ep, y)) return rcg;
     p.ebw = HALO_TW;
     if (head) {
         HN_CHECK_ARG(cv->cout == 64 && !ep->scale && !ep->residual, "conv3x3_head: needs Cout == 64, no explicit scale, no residual");

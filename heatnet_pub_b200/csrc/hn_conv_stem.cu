@@ -182,6 +182,7 @@ int conv_stem_dense(const hn_tensor *xpad, const void *w, int cout, const hn_epi
     p.scale = ep->scale; p.shift = ep->shift; p.res = nullptr; p.ldr = 0;
     p.act = ep->act; p.slope = ep->slope; p.slope_ptr = ep->slope_ptr;
     p.stat_sum = ep->stat_sum; p.stat_sqsum = ep->stat_sqsum;
+    if (int rcg = set_stat_groups(p, ep, y)) return rcg;
     p.ebw = 32;
     CUtensorMap ty, tr;
     memset(&ty, 0, sizeof(ty));

@@ -465,6 +465,7 @@ int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn
     p.scale = ep->scale; p.shift = ep->shift; p.res = ep->residual; p.ldr = ep->residual_ld;
     p.act = ep->act; p.slope = ep->slope; p.slope_ptr = ep->slope_ptr;
     p.stat_sum = ep->stat_sum; p.stat_sqsum = ep->stat_sqsum;
+    if (int rcg = set_stat_groups(p, ep, y)) return rcg;
     const int num_tiles = num_m_tiles * p.n_tiles;
     // epilogue tensor maps: the output view (and the residual view) as {C, W, H, N} with a {128 B, ebw, 32/ebw, 1} box
     CUtensorMap ty, tr;
@@ -634,6 +635,7 @@ int conv_stem_tc(const hn_tensor *xpad, const void *w, int cout, const hn_epilog
     p.scale = ep->scale; p.shift = ep->shift; p.res = ep->residual; p.ldr = ep->residual_ld;
     p.act = ep->act; p.slope = ep->slope; p.slope_ptr = ep->slope_ptr;
     p.stat_sum = ep->stat_sum; p.stat_sqsum = ep->stat_sqsum;
+    if (int rcg = set_stat_groups(p, ep, y)) return rcg;
     p.ebw = 32;
     {
         const uint64_t esz = p.y_f32 ? 4 : 2;

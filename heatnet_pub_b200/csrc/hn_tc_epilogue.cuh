@@ -42,11 +42,37 @@ struct TcParams {
     // train-mode BatchNorm2d statistics fused into the FP32-output epilogue: per-channel sum / sum of squares of the STORED
     // pre-normalisation values over the valid pixels, FP32 per 32-row block, FP64 atomics into [Cout] accumulators
     double *stat_sum, *stat_sqsum;
+    // image groups with SEPARATE statistics (the day and the night batch of a training step run through the convolutions as
+    // one batch, BatchNorm2d keeps normalising each domain by itself): accumulators are [groups][Cout]; a 32-pixel block belongs
+    // to group (image / stat_group_img) -- flat mode: (first pixel / stat_group_pix), stat_group_pix % 32 == 0.  0 = one group.
+    int stat_group_img, stat_group_pix;
     // fused 1x1 classifier head (halo kernel, BLOCK_N = 64 = Cout): logits written as NCHW FP32, the activation is not stored
     float *head_out;               // [n_img][head_n][Ho][Wo]
     int head_n;                    // <= HEAD_MAX; 0 = no head
     HeadConst head;                // classifier weights (rows >= head_n are zero)
 };
+
+// host: statistics groups of a launch whose tiling is already in p (n_img / Ho / Wo; flat mode has n_img == 1)
+inline int set_stat_groups(TcParams &p, const hn_epilogue *ep, const hn_tensor *y)
+{
+    p.stat_group_img = p.stat_group_pix = 0;
+    if (!ep->stat_sum || ep->stat_groups <= 1) return HN_OK;
+    const int g = ep->stat_groups;
+    if (y->n % g != 0) {
+        set_error("conv: %d images do not split into %d statistics groups", y->n, g);
+        return HN_ERR_ARG;
+    }
+    if (p.n_img == y->n) p.stat_group_img = y->n / g;
+    else {
+        const int64_t gp = (int64_t)(y->n / g) * y->h * y->w;
+        if (gp % 32 != 0 || gp >= ((int64_t)1 << 31)) {
+            set_error("conv: flattened statistics groups need (N / G) * H * W to be a multiple of 32 (got %lld)", (long long)gp);
+            return HN_ERR_ARG;
+        }
+        p.stat_group_pix = (int)gp;
+    }
+    return HN_OK;
+}
 
 constexpr int EPI_STAGE_BYTES = 32 * 128;   // 32 pixels x 128 B per epilogue warp
 constexpr int NUM_EPI_WARPS = 8;
@@ -166,7 +192,7 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
     float st_s[STAT_CHUNKS], st_q[STAT_CHUNKS];
 #pragma unroll
     for (int i = 0; i < STAT_CHUNKS; ++i) st_s[i] = st_q[i] = 0.f;
-    int stat_ctile = -1;
+    int stat_ctile = -1, stat_grp = 0;
     const bool stat_bf16 = p.stat_sum != nullptr && !p.y_f32;
     auto stat_flush = [&]() {
         if (stat_ctile < 0) return;
@@ -175,8 +201,8 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
             const int ch = stat_bf16 ? stat_ctile + 64 * (i >> 1) + 2 * lane + (i & 1) : stat_ctile + 32 * i + lane;
             const bool mine = stat_bf16 ? (64 * (i >> 1) + 2 * lane + (i & 1) < COLS) : (32 * i + lane < COLS);
             if (mine && ch < p.Cout && (st_s[i] != 0.f || st_q[i] != 0.f)) {
-                atomicAdd(p.stat_sum + ch, (double)st_s[i]);
-                atomicAdd(p.stat_sqsum + ch, (double)st_q[i]);
+                atomicAdd(p.stat_sum + stat_grp * p.Cout + ch, (double)st_s[i]);
+                atomicAdd(p.stat_sqsum + stat_grp * p.Cout + ch, (double)st_q[i]);
             }
             st_s[i] = st_q[i] = 0.f;
         }
@@ -190,9 +216,15 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
         const bool valid = ho < p.Ho && wo < p.Wo;
         const int64_t pix = ((int64_t)img * p.Ho + ho) * p.Wo + wo;
         const int ctile = nt * BLOCK_N + col0;         // first output channel of this warp's columns
-        if (p.stat_sum && ctile != stat_ctile) {
-            stat_flush();
-            stat_ctile = ctile;
+        if (p.stat_sum) {
+            int grp = 0;                             // warp-uniform: the statistics group of this warp's 32-pixel block
+            if (p.stat_group_img) grp = img / p.stat_group_img;
+            else if (p.stat_group_pix) grp = (tw * p.TW + q * 32) / p.stat_group_pix;
+            if (ctile != stat_ctile || grp != stat_grp) {
+                stat_flush();
+                stat_ctile = ctile;
+                stat_grp = grp;
+            }
         }
         // coordinates of this warp's 32-pixel box (first pixel = row q*32 of the tile)
         const int bx = tw * p.TW + (q * 32) % p.TW, by = th * p.TH + (q * 32) / p.TW;

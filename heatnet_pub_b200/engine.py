@@ -266,6 +266,9 @@ class Tape:
 
 
 current_tape: Optional[Tape] = None
+# > 1 while PSPNet.forward_pair runs: the batch holds that many equal groups of consecutive images (day batch, night batch) that
+# share every convolution launch but are normalised by BatchNorm2d separately, exactly as consecutive forward calls would
+bn_groups = 1
 # parallel.GradientReducer registers itself here: parameter gradients are then written straight into its flat arena
 grad_arena = None
 
@@ -519,7 +522,7 @@ def packed_stem_weight(conv: torch.nn.Conv2d, bn: Optional[torch.nn.BatchNorm2d]
 
 
 def stem_conv(x: "Act", conv: torch.nn.Conv2d, wp: torch.Tensor, shift, act=ACT_NONE, slope=0.0, slope_ptr=None,
-              out: Optional["Act"] = None, out_dtype=None, stats: Optional[torch.Tensor] = None) -> "Act":
+              out: Optional["Act"] = None, out_dtype=None, stats: Optional[torch.Tensor] = None, stat_groups: int = 1) -> "Act":
     lib = _lib.load()
     ho, wo = conv_out_hw(x.h, x.w, conv)
     hpad, wpad = 2 * ho + 6, 2 * wo + 6
@@ -527,7 +530,7 @@ def stem_conv(x: "Act", conv: torch.nn.Conv2d, wp: torch.Tensor, shift, act=ACT_
     xpad = Act(flat[:x.n * hpad * wpad * 4].view(x.n, hpad, wpad, 4))         # + readable slack behind the last row (hn_stem_pad_slack_bytes)
     if out is None:
         out = new_act(x.n, ho, wo, conv.out_channels, out_dtype or x.dtype, x.buf.device)
-    ep = _epilogue(None, shift, None, act, slope, slope_ptr, stats)
+    ep = _epilogue(None, shift, None, act, slope, slope_ptr, stats, stat_groups)
     timing = conv_timer is not None
     if timing:
         ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -599,9 +602,10 @@ def conv_out_hw(h, w, conv: torch.nn.Conv2d):
     return (h + 2 * p - d * (k - 1) - 1) // s + 1, (w + 2 * p - d * (k - 1) - 1) // s + 1
 
 
-def _epilogue(scale, shift, residual: Optional[Act], act, slope, slope_ptr, stats: Optional[torch.Tensor] = None) -> HnEpilogue:
+def _epilogue(scale, shift, residual: Optional[Act], act, slope, slope_ptr, stats: Optional[torch.Tensor] = None, stat_groups: int = 1) -> HnEpilogue:
     ep = HnEpilogue()
-    if stats is not None:        # FP64 [2, C] (or longer, [0:C] / [C:2C] used): per-channel sum / sum of squares accumulators
+    ep.stat_groups = stat_groups
+    if stats is not None:        # FP64 [2, G*C]: per-(group, channel) sum / sum of squares accumulators
         c = stats.numel() // 2 if stats.dim() == 1 else stats.shape[1]
         ep.stat_sum, ep.stat_sqsum = stats.data_ptr(), stats.data_ptr() + 8 * c
     ep.scale = scale.data_ptr() if scale is not None else None
@@ -615,7 +619,7 @@ def _epilogue(scale, shift, residual: Optional[Act], act, slope, slope_ptr, stat
 
 def conv2d_raw(x: Act, wp: torch.Tensor, cout: int, k: int, stride: int, pad: int, dil: int, scale=None, shift=None,
                residual: Optional[Act] = None, act=ACT_NONE, slope=0.0, slope_ptr=None, out: Optional[Act] = None,
-               out_dtype=None, out_hw=None, stats: Optional[torch.Tensor] = None) -> Act:
+               out_dtype=None, out_hw=None, stats: Optional[torch.Tensor] = None, stat_groups: int = 1) -> Act:
     """One convolution launch on a packed weight matrix (see hn_conv2d_fwd)."""
     lib = _lib.load()
     ho = (x.h + 2 * pad - dil * (k - 1) - 1) // stride + 1
@@ -635,7 +639,7 @@ def conv2d_raw(x: Act, wp: torch.Tensor, cout: int, k: int, stride: int, pad: in
     if ws_bytes:
         ws_ptr = workspace(ws_bytes, x.buf.device).data_ptr()
         _count()
-    ep = _epilogue(scale, shift, residual, act, slope, slope_ptr, stats)
+    ep = _epilogue(scale, shift, residual, act, slope, slope_ptr, stats, stat_groups)
     timing = conv_timer is not None
     if timing:
         ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -650,7 +654,8 @@ def conv2d_raw(x: Act, wp: torch.Tensor, cout: int, k: int, stride: int, pad: in
 
 
 def conv2d(x: Act, conv: torch.nn.Conv2d, scale=None, shift=None, residual: Optional[Act] = None, act=ACT_NONE,
-           slope=0.0, slope_ptr=None, out: Optional[Act] = None, out_dtype=None, stats: Optional[torch.Tensor] = None) -> Act:
+           slope=0.0, slope_ptr=None, out: Optional[Act] = None, out_dtype=None, stats: Optional[torch.Tensor] = None,
+           stat_groups: int = 1) -> Act:
     """y = act(conv(x) * scale + shift + residual) in one launch (plus an im2col gather for strided /
     small-Cin shapes on the BF16 path)."""
     assert conv.groups == 1 and conv.kernel_size[0] == conv.kernel_size[1] and conv.stride[0] == conv.stride[1]
@@ -658,7 +663,7 @@ def conv2d(x: Act, conv: torch.nn.Conv2d, scale=None, shift=None, residual: Opti
     if x.c != conv.in_channels:
         raise RuntimeError(f"expected input with {conv.in_channels} channels, got {x.c}")
     return conv2d_raw(x, packed_weight(conv, x.dtype), conv.out_channels, conv.kernel_size[0], conv.stride[0], conv.padding[0],
-                      conv.dilation[0], scale, shift, residual, act, slope, slope_ptr, out, out_dtype, stats=stats)
+                      conv.dilation[0], scale, shift, residual, act, slope, slope_ptr, out, out_dtype, stats=stats, stat_groups=stat_groups)
 
 
 def affine_act(x: Act, scale, shift, residual: Optional[Act], act, slope=0.0, slope_ptr=None, out: Optional[Act] = None) -> Act:
@@ -749,15 +754,16 @@ def batchnorm_finalize(sums: torch.Tensor, count: int, bn: torch.nn.BatchNorm2d)
     return out[0], out[1], out[2], out[3]
 
 
-def batchnorm_apply_train(raw: Act, sums: torch.Tensor, bn: torch.nn.BatchNorm2d, residual: Optional[Act], act, slope, slope_ptr, out: Act):
+def batchnorm_apply_train(raw: Act, sums: torch.Tensor, bn: torch.nn.BatchNorm2d, residual: Optional[Act], act, slope, slope_ptr, out: Act,
+                          groups: int = 1):
     """out = act(BN_train(raw) + residual) from the FP64 sums of a conv with fused statistics, and the running-statistic update of
     nn.BatchNorm2d -- one launch (hn_bn_apply_train).  -> (scale, shift, mean, invstd) for the backward."""
     cch = bn.num_features
-    vec = torch.empty((4, cch), dtype=torch.float32, device=sums.device)
+    vec = torch.empty((4, groups * cch), dtype=torch.float32, device=sums.device)      # scale, shift, mean, invstd: [groups][C] each
     track = bn.track_running_stats and bn.running_mean is not None
     p = lambda t: t.detach().data_ptr() if t is not None else None
-    ep = _epilogue(None, None, residual, act, slope, slope_ptr)
-    _lib.check(_lib.load().hn_bn_apply_train(C.byref(raw.hn()), sums.data_ptr(), sums.data_ptr() + 8 * cch, raw.n * raw.h * raw.w, p(bn.weight),
+    ep = _epilogue(None, None, residual, act, slope, slope_ptr, stat_groups=groups)
+    _lib.check(_lib.load().hn_bn_apply_train(C.byref(raw.hn()), sums.data_ptr(), sums.data_ptr() + 8 * groups * cch, (raw.n // groups) * raw.h * raw.w, p(bn.weight),
                                              p(bn.bias), float(bn.eps), float(bn.momentum), p(bn.running_mean) if track else None,
                                              p(bn.running_var) if track else None, p(bn.num_batches_tracked) if track else None, C.byref(ep),
                                              C.byref(out.hn()), vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(), vec[3].data_ptr(), _stream()))
@@ -823,20 +829,26 @@ def conv_bn_act(x: Act, conv, bn, act=ACT_NONE, slope=0.0, slope_ptr=None, resid
     # BF16 engine with FP32 pre-normalisation output: the batch statistics are accumulated by the conv epilogue itself (FP32 per
     # 32-pixel block, FP64 atomics), so train-mode BN costs one tiny finalize launch instead of a pass over the tensor
     fused = BN_FUSED_STATS and x.dtype == torch.bfloat16 and conv.out_channels >= 17
-    sums = _stats_alloc(conv.out_channels, x.buf.device) if fused else None
+    # statistics groups (PSPNet.forward_pair): the batch is the day batch followed by the night batch, convolved as one, normalised
+    # per domain -- only on the fused-statistics path (BF16 engine)
+    G = bn_groups if (bn_groups > 1 and x.n % bn_groups == 0) else 1
+    if G > 1 and not (fused and bn.momentum is not None and conv.out_channels % 8 == 0):
+        raise NotImplementedError("paired (grouped-statistics) forward needs the BF16 engine's fused BatchNorm statistics")
+    sums = _stats_alloc(G * conv.out_channels, x.buf.device) if fused else None
     if stem_ok(x, conv):
         wp, shift = packed_stem_weight(conv, None)
-        raw = stem_conv(x, conv, wp, shift, out_dtype=torch.float32 if raw_fp32 else None, stats=sums)
+        raw = stem_conv(x, conv, wp, shift, out_dtype=torch.float32 if raw_fp32 else None, stats=sums, stat_groups=G)
     else:
-        raw = conv2d(x, conv, scale, shift, None, ACT_NONE, out_dtype=torch.float32 if raw_fp32 else None, stats=sums)
+        raw = conv2d(x, conv, scale, shift, None, ACT_NONE, out_dtype=torch.float32 if raw_fp32 else None, stats=sums, stat_groups=G)
     if out is None:
         in_place = raw.dtype == x.dtype and tape is None
         out = raw if in_place else new_act(raw.n, raw.h, raw.w, raw.c, x.dtype, x.buf.device)
     if fused and bn.momentum is not None and raw.c % 8 == 0 and raw.ld % 8 == 0 and out.ld % 8 == 0:
         # statistics came out of the conv epilogue: finalize + normalise + residual + activation in ONE launch
-        bscale, bshift, mean, invstd = batchnorm_apply_train(raw, sums, bn, residual, act, slope, slope_ptr, out)
+        bscale, bshift, mean, invstd = batchnorm_apply_train(raw, sums, bn, residual, act, slope, slope_ptr, out, groups=G)
         y = out
     else:
+        assert G == 1
         if fused:
             bscale, bshift, mean, invstd = batchnorm_finalize(sums, raw.n * raw.h * raw.w, bn)
         else:
@@ -859,7 +871,7 @@ def conv_bn_act(x: Act, conv, bn, act=ACT_NONE, slope=0.0, slope_ptr=None, resid
                 fz = (bscale, bshift) if residual is None else (None, None)
                 sinks = [grads.param_sink(q) if w else (None, False) for q, w in ((bn.bias, _wants(bn.bias)), (bn.weight, _wants(bn.weight)),
                                                                                 (slope_ptr, prelu))]
-                draw = bn_bwd(dout, y, raw, mean, invstd, bn.weight, act, slope, slope_ptr, dres, dres_acc, sinks, fz[0], fz[1])
+                draw = bn_bwd(dout, y, raw, mean, invstd, bn.weight, act, slope, slope_ptr, dres, dres_acc, sinks, fz[0], fz[1], groups=G)
                 if dres is not None:
                     grads.mark(residual)
                 for q, (t, _) in zip((bn.bias, bn.weight, slope_ptr), sinks):
@@ -1211,12 +1223,12 @@ def vec_to_grad(src_f64: torch.Tensor, n: int, out: Optional[torch.Tensor] = Non
 
 
 def bn_bwd(dout: Act, out: Act, raw: Act, mean, invstd, gamma, act, slope=0.0, slope_ptr=None, dres: Optional[Act] = None,
-           dres_accumulate=False, sinks=((None, False),) * 3, fwd_scale=None, fwd_shift=None) -> Act:
+           dres_accumulate=False, sinks=((None, False),) * 3, fwd_scale=None, fwd_shift=None, groups: int = 1) -> Act:
     """-> draw.  `sinks` = (tensor or None, accumulate) for dbeta, dgamma, dPReLU-slope: FP32 parameter gradients written by the
     apply kernel itself.  The kernel has ONE accumulate flag: sinks that disagree with it are routed through a scratch vector."""
     cch = dout.c
     dev = dout.buf.device
-    sums = torch.empty((2 * cch + 1,), dtype=torch.float64, device=dev)
+    sums = torch.empty(((2 * cch + 1) * groups,), dtype=torch.float64, device=dev)
     draw = new_act(dout.n, dout.h, dout.w, cch, dout.dtype, dev)
     wanted = [(t, a) for t, a in sinks if t is not None]
     acc = bool(wanted) and all(a for _, a in wanted)
@@ -1234,7 +1246,7 @@ def bn_bwd(dout: Act, out: Act, raw: Act, mean, invstd, gamma, act, slope=0.0, s
     _lib.check(_lib.load().hn_bn_bwd(C.byref(dout.hn()), C.byref(out.hn()), C.byref(raw.hn()), p(mean), p(invstd), p(gamma), act,
                                     float(slope), p(slope_ptr), sums.data_ptr(), C.byref(draw.hn()),
                                     C.byref(dres.hn()) if dres is not None else None, int(dres_accumulate),
-                                    int(ptrs[2] is not None), ptrs[0], ptrs[1], ptrs[2], int(acc), p(fwd_scale), p(fwd_shift), _stream()))
+                                    int(ptrs[2] is not None), ptrs[0], ptrs[1], ptrs[2], int(acc), p(fwd_scale), p(fwd_shift), int(groups), _stream()))
     _count(3)
     for t, tmp, a in fixups:
         t.add_(tmp) if a else t.copy_(tmp)

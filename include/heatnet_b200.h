@@ -60,6 +60,8 @@ typedef struct hn_epilogue {
                              * (BF16 engine, 16-byte-aligned output view, Cout tile >= 32; FP32 or BF16 output -- BF16: statistics of
                              * the ROUNDED values, i.e. of the stored tensor, and no explicit scale; else the call fails) */
     int32_t per_image;      /* hn_affine_act only: scale (and shift, if given) are [N][C] -- Dropout2d channel masks */
+    int32_t stat_groups;    /* 0 / 1: one set of statistics.  G > 1: the batch is G equal groups of consecutive images with separate
+                             * statistics (a day and a night batch convolved as one): stat_sum / stat_sqsum are [G][Cout] */
 } hn_epilogue;
 
 typedef struct hn_conv {
@@ -169,7 +171,9 @@ int hn_bn_finalize_tracked(const double *sum, const double *sqsum, int64_t count
 /* hn_bn_finalize_tracked and the normalise pass hn_affine_act in ONE launch (cm/models/extractors.py:85-101 in train mode):
  * y = act(x * scale + shift + residual) with scale / shift formed from the FP64 sums in every thread's prologue; the vectors the
  * backward needs (scale, shift, save_mean, save_invstd: [C] each) are written and the running statistics / counter updated by
- * the threads of the first pixel chunk.  ep supplies residual / act / slope only.  Views must be 8-channel aligned. */
+ * the threads of the first pixel chunk.  ep supplies residual / act / slope and stat_groups: with G > 1 groups of consecutive
+ * images, sum / sqsum and the four output vectors are [G][C], count = pixels per group, and the running statistics receive G
+ * momentum updates in group order (what G consecutive forward calls of the reference do).  Views must be 8-channel aligned. */
 int hn_bn_apply_train(const hn_tensor *x, const double *sum, const double *sqsum, int64_t count, const float *gamma, const float *beta,
                       float eps, float momentum, float *running_mean, float *running_var, int64_t *num_batches_tracked,
                       const hn_epilogue *ep, const hn_tensor *y, float *scale, float *shift, float *save_mean, float *save_invstd,
@@ -209,11 +213,13 @@ int hn_act_bwd(const hn_tensor *dout, const hn_tensor *out, int32_t act, float s
  *   added to their current contents when param_accumulate is set (a second backward pass into an existing .grad).
  *   fwd_scale / fwd_shift (both or neither): the scale/shift vectors the forward normalise pass used.  When given -- only valid
  *   for a layer WITHOUT a residual input -- `out` is not read: the pre-activation z = fma(raw, scale, shift) is recomputed
- *   bit-identically, which removes one tensor from both passes. */
+ *   bit-identically, which removes one tensor from both passes.
+ *   groups > 1: the batch is `groups` equal groups of consecutive images normalised with SEPARATE statistics (hn_epilogue.stat_groups):
+ *   mean / invstd / fwd_scale / fwd_shift are [groups][C], sums is [groups][2C+1]; parameter gradients are summed over the groups. */
 int hn_bn_bwd(const hn_tensor *dout, const hn_tensor *out, const hn_tensor *raw, const float *mean, const float *invstd,
               const float *gamma, int32_t act, float slope, const float *slope_ptr, double *sums, const hn_tensor *draw,
               const hn_tensor *dres, int32_t dres_accumulate, int32_t want_prelu_grad, float *dbeta, float *dgamma, float *dslope,
-              int32_t param_accumulate, const float *fwd_scale, const float *fwd_shift, void *stream);
+              int32_t param_accumulate, const float *fwd_scale, const float *fwd_shift, int32_t groups, void *stream);
 /* y = x (accumulate == 0) or y += x; dtypes may differ */
 int hn_accumulate(const hn_tensor *x, const hn_tensor *y, int32_t accumulate, void *stream);
 /* MaxPool2d(3,2,1) forward that also records the winning tap (uint8 [N][Ho][Wo][C]) and its backward */
