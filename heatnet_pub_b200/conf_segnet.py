@@ -10,9 +10,14 @@ Only the path the north star names is built: arch='pspnet' with disc_arch='cycle
 "custom" arch, the ResNet critics, the feedback_seg DownNets, the input adapter and the certainty branch are out of
 scope and raise NotImplementedError instead of silently building something else.
 """
+import os
+
 import torch.nn as nn
 
 from . import build_net, discriminator_model, utils
+
+# one batched seg-net / critic pass over [day; night] instead of two (PSPNet.forward_pair); HN_NO_PAIR_FORWARD=1 keeps the two calls
+PAIR_FORWARD = os.environ.get("HN_NO_PAIR_FORWARD") is None
 
 # channel counts of the six critic taps [logits, x5, x4, x3, x2, x1] (conf_segnet.py:44-50): with late fusion the three
 # shallow taps are RGB || IR concatenations
@@ -81,6 +86,8 @@ class conv_segnet(nn.Module):
 
     # ---- conf_segnet.py:106-140: the same seg net on the day and the night input, one critic per feature tap
     def forward(self, input_a, input_b):
+        if PAIR_FORWARD and self.trgb_segnet.pair_ok(input_a, input_b):
+            return self._forward_pair(input_a, input_b)
         logits_a, taps_a, cert_a = self.trgb_segnet(*input_a)
         logits_b, taps_b, cert_b = self.trgb_segnet(*input_b)
         output = {}
@@ -88,4 +95,17 @@ class conv_segnet(nn.Module):
             output['critics_a'] = [critic(taps_a[i]) for i, critic in enumerate(self.critics)]
             output['critics_b'] = [critic(taps_b[i]) for i, critic in enumerate(self.critics)]
         output.update(pred_label_a=logits_a, pred_label_b=logits_b, cert_a=cert_a, cert_b=cert_b, inter_f_b=taps_b)
+        return output
+
+    def _forward_pair(self, input_a, input_b):
+        """The same dict from ONE seg-net pass over [day batch; night batch] (PSPNet.forward_pair) and ONE pass of every critic over
+        the 2B feature taps: outputs are the two halves of the batched results."""
+        b = input_a[0].shape[0]
+        logits, taps = self.trgb_segnet.forward_pair(input_a, input_b)
+        output = {}
+        if not self.no_conf:
+            maps = [critic(taps[i]) for i, critic in enumerate(self.critics)]
+            output['critics_a'] = [m[:b] for m in maps]
+            output['critics_b'] = [m[b:] for m in maps]
+        output.update(pred_label_a=logits[:b], pred_label_b=logits[b:], cert_a=None, cert_b=None, inter_f_b=[t[b:] for t in taps])
         return output

@@ -194,6 +194,37 @@ class PSPNet(_KernelModule):
             return self._forward_graph(modal_1, modal_2)
         return self._forward_eager(modal_1, modal_2)
 
+    def forward_pair(self, input_a, input_b):
+        """`forward(*input_a)` and `forward(*input_b)` (the day and the night batch of an adversarial step,
+        cm/models/conf_segnet.py:114-115) as ONE batch: every convolution, pooling and upsampling launch covers both domains
+        (half as many launches, twice the tiles per launch, weights fetched once, one wgrad per layer instead of two accumulated
+        ones), while every train-mode BatchNorm2d still normalises each domain with its own batch statistics and applies its
+        two running-statistic updates in call order -- the results equal two consecutive calls up to floating-point
+        summation order.  -> (logits, [logits, x5, x4, x3, x2, x1]) for the concatenated batch: rows [:B] are input_a's."""
+        ins = [torch.cat([a, b], dim=0) for a, b in zip(input_a, input_b)]
+        prev = E.bn_groups
+        E.bn_groups = 2
+        try:
+            logits, taps, _ = self.forward(*ins)
+        finally:
+            E.bn_groups = prev
+        return logits, taps
+
+    def pair_ok(self, input_a, input_b) -> bool:
+        """Can forward_pair replace two forward calls here?  Same shapes on the GPU; with BatchNorm2d in train mode the grouped
+        statistics live on the BF16 engine and the flattened 1x1 convolutions need whole 32-pixel blocks per domain."""
+        if len(input_a) != len(input_b) or any(a.shape != b.shape or not (a.is_cuda and b.is_cuda) for a, b in zip(input_a, input_b)):
+            return False
+        if not any(m.training for m in self.modules() if isinstance(m, nn.BatchNorm2d)):
+            return True
+        if (self.precision or E.DEFAULT_PRECISION) != "bf16" or E.BN_TRAIN_RAW_FP32 or not E.BN_FUSED_STATS:
+            return False
+        n, _, h, w = input_a[0].shape
+        h2, w2 = E.conv_out_hw(h, w, self.feats.conv1)
+        h4, w4 = (h2 - 1) // 2 + 1, (w2 - 1) // 2 + 1
+        h8, w8 = self._h8w8(h, w)
+        return (n * h4 * w4) % 32 == 0 and (n * h8 * w8) % 32 == 0
+
     def _forward_eager(self, modal_1, modal_2=None):
         m1, m2 = self.feats._inputs(modal_1, modal_2)
         logits, f = self._run_full(m1, m2)

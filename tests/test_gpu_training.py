@@ -253,3 +253,58 @@ def test_graphed_train_step_matches_eager():
         else:
             assert torch.equal(sa[k], sb[k]), k            # num_batches_tracked
     print("graph vs eager: worst deviation", worst)
+
+
+@pytest.mark.parametrize("phase", ["train_seg", "train_critic"])
+def test_paired_forward_equals_two_consecutive_calls(phase, monkeypatch):
+    """conv_segnet's batched [day; night] pass (PSPNet.forward_pair: shared convolution launches, per-domain BatchNorm statistics via
+    statistics groups in the conv epilogue / apply / backward kernels) against the two consecutive seg-net calls of
+    cm/models/conf_segnet.py:114-115: every output, every parameter gradient and every BN running statistic.  Both runs are BF16;
+    they differ only by summation order (statistics atomics, wgrad over 2B instead of B + B), bounded at BF16 resolution."""
+    import contextlib
+    import io
+    from heatnet_pub_b200 import conf_segnet, losses
+    sd = O.recipe_fill(O.conf_segnet_state_dict(True, 6), seed=3)
+    B, H, W = 2, 256, 256
+    day = [t.cuda() for t in O.synthetic_inputs(B, H, W, seed=31)]
+    night = [t.cuda() for t in O.synthetic_inputs(B, H, W, seed=32)]
+    label = torch.randint(0, 13, (B, H, W), generator=torch.Generator().manual_seed(33)).cuda()
+    mse, ce = losses.MSELoss(), losses.CrossEntropyLoss()
+
+    def run(pair):
+        monkeypatch.setattr(conf_segnet, "PAIR_FORWARD", pair)
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = conf_segnet.conv_segnet(pretrained=False, disc_arch='cyclegan', num_critics=6, no_conf=False, modalities='ir_rgb',
+                                        arch='pspnet', late_fusion=True)
+            m.load_state_dict(sd)
+            m = m.cuda().train()
+            m.setPhase(phase)
+        m.trgb_segnet.drop_1.p = m.trgb_segnet.drop_2.p = 0.0
+        o = m(list(day), list(night))
+        if phase == "train_seg":
+            total = ce(o['pred_label_a'], label) + 0.1 * (sum(mse(c, 1.0) for c in o['critics_a']) + sum(mse(c, 1.0) for c in o['critics_b']))
+        else:
+            total = sum(mse(c, 1.0) for c in o['critics_a']) + sum(mse(c, 0.0) for c in o['critics_b'])
+        total.backward()
+        outs = {k: ([t.detach().float().clone() for t in v] if isinstance(v, list) else v.detach().float().clone())
+                for k, v in o.items() if v is not None}
+        return m, total.item(), outs, {k: p.grad.float().clone() for k, p in m.named_parameters() if p.grad is not None}
+
+    ms, ls, os_, gs = run(False)
+    mp, lp, op, gp = run(True)
+    assert abs(lp - ls) < 5e-3 * abs(ls), (lp, ls)
+    for k in os_:
+        a, b = os_[k], op[k]
+        for x, y in (zip(a, b) if isinstance(a, list) else [(a, b)]):
+            assert x.shape == y.shape, k
+            assert rel(y.cpu(), x.cpu()) < 3e-2, k
+    assert set(gs) == set(gp)
+    worst = max((rel_l2(gp[k].cpu(), gs[k].cpu()), k) for k in gs if gs[k].abs().max() > 0)
+    print(f"[{phase}] paired vs sequential: loss {lp:.6f} / {ls:.6f}; worst gradient rel-L2 deviation {worst}")
+    assert worst[0] < 6e-2, worst
+    ss, sp = ms.state_dict(), mp.state_dict()
+    for k in ss:
+        if k.endswith("num_batches_tracked"):
+            assert int(ss[k]) == int(sp[k]) == 2, k                    # two forward calls' worth of updates, in order
+        elif "running_" in k:
+            assert rel(sp[k].cpu(), ss[k].cpu()) < 2e-3, k
