@@ -601,7 +601,7 @@ def measure_torch_gpu_baseline(ctx, args, B, H, W, ours_value, train_legs):
         out["infer"] = {"value": None, "failed": repr(e)[:300]}
     # train_seg step of the oracle graph at the training leg's shape
     ts = (train_legs or {}).get("train_seg")
-    if ts:
+    if ts and "images_per_s" in ts:
         Bt, Ht, Wt = ts["per_gpu_pairs"], ts["height"], ts["width"]
         for pairs in (Bt, Bt // 2, Bt // 4):
             if pairs < 1:
@@ -975,15 +975,23 @@ def main():
         if wl in want:
             try:
                 legs[wl] = measure_train(ctx, args, wl, args.train_pairs, 320, 640, leg_steps, 3)
-            except Exception as e:                               # a leg never takes the headline down with it
-                legs[wl] = {"failed": repr(e)[:400]} if rank == 0 else None
-                if world > 1:
-                    raise
+            except Exception as e:                               # a leg never takes the headline down with it (the same code runs
+                legs[wl] = {"failed": repr(e)[:400]}             # on every rank, so a failure is symmetric and nobody is left waiting)
+                from heatnet_pub_b200 import engine as _E2
+                _E2.grad_arena = None
+                _E2.bn_groups = 1
+                torch.cuda.empty_cache()
     if "iou_eval" in want:
-        legs["iou_eval"] = measure_iou_eval(ctx, args, 500, leg_steps, 3)
+        try:
+            legs["iou_eval"] = measure_iou_eval(ctx, args, 500, leg_steps, 3)
+        except Exception as e:
+            legs["iou_eval"] = {"failed": repr(e)[:400]}
     torch_gpu = None
     if "torch" in want and rank == 0 and world == 1:
-        torch_gpu = measure_torch_gpu_baseline(ctx, args, B, H, W, value, legs)
+        try:
+            torch_gpu = measure_torch_gpu_baseline(ctx, args, B, H, W, value, legs)
+        except Exception as e:
+            torch_gpu = {"failed": repr(e)[:400]}
 
     if rank == 0:
         cfg = {"workload": f"PSPNet-ResNet50 RGB+thermal late-fusion forward (eval), batch {B} per GPU, {H}x{W} frames -> "
@@ -1006,7 +1014,7 @@ def main():
             # cm/train_trgb_segnet_conf.py:157-158,577-592: 500 critic iterations, then 50 seg iterations, repeated
             pairs = ts["global_pairs"]
             cfg["train_mix_500_critic_50_seg_images_per_s"] = 2 * pairs * 550 / ((500 * tc["ms_per_step"] + 50 * ts["ms_per_step"]) / 1e3)
-        if ie:
+        if ie and "maps_per_s" in ie:
             cfg.update(iou_eval_label_maps_per_s=ie["maps_per_s"], iou_eval_hbm_frac=ie["roofline"]["frac"])
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
