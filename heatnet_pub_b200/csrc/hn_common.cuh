@@ -149,6 +149,7 @@ struct TcSubConv {              // one parity phase of a stride-2 dgrad (hn_conv
 };
 int conv2d_fwd_tc_sub(const hn_tensor *x, const void *w, int cout, const TcSubConv *sc, cudaStream_t st);
 bool conv_halo_ok(const hn_tensor *x, const hn_conv *cv, const hn_tensor *y, bool upsample);
+bool conv_pair_ok(int bn, int num_m_tiles, int num_kb, bool halo);                     // run this Cout tile on CTA pairs (cta_group::2)? (hn_conv_tc.cu)
 struct HeadArgs {               // fused 1x1 classifier head of the halo kernel (hn_conv3x3_head_fwd)
     const float *w, *b;         // HOST pointers: [n][64] FP32, [n] FP32 or NULL (they become kernel parameters)
     float *out;                 // NCHW FP32 logits

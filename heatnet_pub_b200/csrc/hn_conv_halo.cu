@@ -26,14 +26,15 @@ namespace hn {
 
 constexpr int HALO_THREADS = 384;
 constexpr int HALO_TH = 16, HALO_TW = 8;
-constexpr int HALO_NA = 2;        // A patch slots
+constexpr int HALO_NA_MAX = 4;    // A patch slots (upper bound; HaloParams::na are used)
 constexpr int HALO_NB_MAX = 12;   // B ring stages (upper bound)
 
 struct HaloParams {
     TcParams t;
     int PW, PH;              // patch extent in pixels
     int a_slot_bytes;        // patch bytes rounded up to 1024
-    int nb;                  // B ring depth
+    int na;                  // A patch slots: 2, or up to 4 for CTA pairs (a tile lasts half as long, the patch load does not)
+    int nb;                  // B ring depth (stages of TPS filter taps each)
     int b_resident;          // ring holds every (k-block, tap) tile: load once per CTA
     // upsample variant: low-resolution input [N][Hl][Wl][C]
     const __nv_bfloat16 *xlow;
@@ -50,19 +51,32 @@ __device__ __forceinline__ void bilinear_src_h(int dst, int in_size, int &i0, in
     l1 = src - (float)i0;
 }
 
-template <int BLOCK_N, bool UPSAMPLE>
+// PAIR: clusters of two CTAs work on two horizontally adjacent tiles with ONE M = 256 instruction stream (hn_tc_ptx.cuh, "CTA
+// pairs"): each CTA stages its own halo patch and half of the weight rows, the leader issues and commits for both.  These layers
+// are bound by the per-instruction floor of the tensor pipe, which the pair form halves.
+template <int BLOCK_N, bool UPSAMPLE, bool PAIR = false>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_r, const HaloParams hp)
 {
-    constexpr int B_STAGE_BYTES = BLOCK_N * 128;
+    constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;      // weight rows staged by this CTA
+    // a B ring stage holds TPS filter taps (TPS boxes on one barrier); pairs take a whole filter row per stage: at 43 cycles
+    // per MMA the issuing warp cannot afford a barrier wait + commit every 4 instructions
+    constexpr int TPS = PAIR ? 3 : 1;
+    constexpr int B_TAP_BYTES = B_ROWS * 128;
+    constexpr int B_STAGE_BYTES = TPS * B_TAP_BYTES;
     // BLOCK_N = 64: the 36+ MMAs of a tile alternate between TWO accumulators (independent dependency chains on the tensor
     // pipe), summed by the epilogue; + 2 x 16 columns for the fused classifier head
-    constexpr int NACC = BLOCK_N == 64 ? 2 : 1;
+    // (pairs: one chain already retires an instruction every 43 cycles; the TMEM columns go into FOUR tile buffers instead, because
+    // a tile lasts half as long while the epilogue's latency and the cross-CTA hand-over do not shrink)
+    constexpr int NACC = (BLOCK_N == 64 && !PAIR) ? 2 : 1;
+    constexpr int NBUF = (BLOCK_N == 64 && PAIR) ? 4 : 2;
     constexpr int SUB_ACC = BLOCK_N < 32 ? 32 : BLOCK_N;
     constexpr int ACC_COLS = NACC * SUB_ACC;
     constexpr int TMEM_COLS = BLOCK_N == 64 ? 512 : 2 * ACC_COLS;
-    constexpr uint32_t IDESC = make_idesc_bf16(128, BLOCK_N);
+    static_assert(NBUF * ACC_COLS + 2 * HEAD_MAX <= TMEM_COLS || BLOCK_N != 64, "accumulators + classifier columns exceed the TMEM allocation");
+    constexpr uint32_t IDESC = make_idesc_bf16(PAIR ? 256 : 128, BLOCK_N);
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0;
     // A-producer warps of the UPSAMPLE variant: warps 2,3 always; warps 8-11 too when the epilogue only needs 4 warps
     constexpr int NPROD = 6;   // warps 2, 3, 8-11 (the UPSAMPLE variant's epilogue runs on warps 4-7 only)
     const TcParams &p = hp.t;
@@ -70,18 +84,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *a_ring = smem;
-    uint8_t *b_ring = a_ring + HALO_NA * hp.a_slot_bytes;
+    uint8_t *b_ring = a_ring + hp.na * hp.a_slot_bytes;
     uint8_t *epi_stage = b_ring + hp.nb * B_STAGE_BYTES;
     // [16][64] BF16 classifier tile (2 KB, 1024-aligned) sits right behind the staging buffers: hn_tc_epilogue.cuh relies on it
     uint64_t *bars = reinterpret_cast<uint64_t *>(epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES + 2048);
-    uint64_t *a_full = bars, *a_empty = bars + HALO_NA, *b_full = bars + 2 * HALO_NA, *b_empty = b_full + HALO_NB_MAX;
-    uint64_t *tfull_bar = b_empty + HALO_NB_MAX, *tempty_bar = tfull_bar + 2, *res_bar = tempty_bar + 2;
+    uint64_t *a_full = bars, *a_empty = bars + HALO_NA_MAX, *b_full = bars + 2 * HALO_NA_MAX, *b_empty = b_full + HALO_NB_MAX;
+    uint64_t *tfull_bar = b_empty + HALO_NB_MAX, *tempty_bar = tfull_bar + 4, *res_bar = tempty_bar + 4;   // up to 4 tile buffers
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_bar + NUM_EPI_WARPS);
     float *s_shift = reinterpret_cast<float *>(tmem_slot + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_m_tiles = p.n_img * p.tiles_h * p.tiles_w;
-    const int num_tiles = num_m_tiles * p.n_tiles;
+    const int num_tiles = PAIR ? pair_num_tiles(num_m_tiles, p.n_tiles) : num_m_tiles * p.n_tiles;
     const int num_kb = p.cblocks;
     const int d = p.dil;
 
@@ -92,27 +106,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (p.tma_res) prefetch_tmap(&tmap_r);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < HALO_NA; ++i) {
-            mbar_init(smem_u32(a_full + i), UPSAMPLE ? NPROD : 1);
+        for (int i = 0; i < HALO_NA_MAX; ++i) {
+            mbar_init(smem_u32(a_full + i), UPSAMPLE ? NPROD * (PAIR ? 2 : 1) : 1);   // computed patches: the producer warps of both CTAs arrive
             mbar_init(smem_u32(a_empty + i), 1);
         }
         for (int i = 0; i < HALO_NB_MAX; ++i) {
             mbar_init(smem_u32(b_full + i), 1);
             mbar_init(smem_u32(b_empty + i), 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NBUF; ++i) {
             mbar_init(smem_u32(tfull_bar + i), 1);
-            mbar_init(smem_u32(tempty_bar + i), (BLOCK_N >= 128 && !UPSAMPLE) ? 8 : 4);
+            mbar_init(smem_u32(tempty_bar + i), ((BLOCK_N >= 128 && !UPSAMPLE) ? 8 : 4) * (PAIR ? 2 : 1));
         }
-        for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(smem_u32(res_bar + i), 1);
+        // (with a classifier head, pairs use the second res_bar of each epilogue group as the two-CTA "tile staged" barrier)
+        for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(smem_u32(res_bar + i), (PAIR && p.head_n > 0 && (i & 3) == 1) ? 2 : 1);
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
-        tmem_relinquish();
+        if constexpr (PAIR) { tmem_alloc_pair(smem_u32(tmem_slot), TMEM_COLS); tmem_relinquish_pair(); }
+        else { tmem_alloc(smem_u32(tmem_slot), TMEM_COLS); tmem_relinquish(); }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();
+    else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -127,26 +143,44 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             uint32_t aphase = 0, bphase = 0;
             bool first = true;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+                int nt, mt;
+                decode_tile<PAIR>(p, tile, nt, mt);
                 const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     if (!UPSAMPLE) {
                         mbar_wait(smem_u32(a_empty + aslot), aphase ^ 1);
                         const uint32_t fb = smem_u32(a_full + aslot);
                         if (elect_one()) {
-                            mbar_expect_tx(fb, hp.PW * hp.PH * 128);
-                            tma_load_4d(smem_u32(a_ring + aslot * hp.a_slot_bytes), &tmap_a, fb, kb * 64, tw * HALO_TW - d, th * HALO_TH - d, img);
+                            if constexpr (PAIR) {          // the patches of both CTAs are counted on the leader's barrier
+                                if (rank == 0) mbar_expect_tx(fb, 2 * hp.PW * hp.PH * 128);
+                                tma_load_4d_pair(smem_u32(a_ring + aslot * hp.a_slot_bytes), &tmap_a, mapa_u32(fb, 0), kb * 64, tw * HALO_TW - d,
+                                                 th * HALO_TH - d, img);
+                            } else {
+                                mbar_expect_tx(fb, hp.PW * hp.PH * 128);
+                                tma_load_4d(smem_u32(a_ring + aslot * hp.a_slot_bytes), &tmap_a, fb, kb * 64, tw * HALO_TW - d, th * HALO_TH - d, img);
+                            }
                         }
                         __syncwarp();
-                        if (++aslot == HALO_NA) { aslot = 0; aphase ^= 1; }
+                        if (++aslot == hp.na) { aslot = 0; aphase ^= 1; }
                     }
                     if (hp.b_resident && !first) continue;
-                    for (int tap = 0; tap < 9; ++tap) {
+                    for (int tap = 0; tap < 9; tap += TPS) {
                         if (!hp.b_resident) mbar_wait(smem_u32(b_empty + bst), bphase ^ 1);
                         const uint32_t fb = smem_u32(b_full + bst);
                         if (elect_one()) {
-                            mbar_expect_tx(fb, B_STAGE_BYTES);
-                            tma_load_2d(smem_u32(b_ring + bst * B_STAGE_BYTES), &tmap_b, fb, (tap * num_kb + kb) * 64, nt * BLOCK_N);
+                            if constexpr (PAIR) {
+                                const uint32_t lfb = mapa_u32(fb, 0);
+                                if (rank == 0) mbar_expect_tx(fb, 2 * B_STAGE_BYTES);
+#pragma unroll
+                                for (int t = 0; t < TPS; ++t)
+                                    tma_load_2d_pair(smem_u32(b_ring + bst * B_STAGE_BYTES + t * B_TAP_BYTES), &tmap_b, lfb, ((tap + t) * num_kb + kb) * 64,
+                                                     nt * BLOCK_N + (int)rank * B_ROWS);
+                            } else {
+                                mbar_expect_tx(fb, B_STAGE_BYTES);
+#pragma unroll
+                                for (int t = 0; t < TPS; ++t)
+                                    tma_load_2d(smem_u32(b_ring + bst * B_STAGE_BYTES + t * B_TAP_BYTES), &tmap_b, fb, ((tap + t) * num_kb + kb) * 64, nt * BLOCK_N);
+                            }
                         }
                         __syncwarp();
                         if (++bst == hp.nb) { bst = 0; bphase ^= 1; }
@@ -155,55 +189,78 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 first = false;
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (whole warp, elected lane issues) =====================
+    } else if (warp == 1 && rank == 0) {
+        // ===================== MMA issuer (whole warp, elected lane issues; the leader CTA of a pair) =====================
         {
             int aslot = 0, bst = 0, acc = 0;
             uint32_t aphase = 0, bphase = 0, acc_phase = 0;
             bool first = true;
+            long long mw_afull = 0, mw_bfull = 0, mw_tempty = 0, ntl = 0;
+            (void)mw_afull; (void)mw_bfull; (void)mw_tempty; (void)ntl;
+#ifdef HN_PROFILE_ROLES
+            const long long mma_t0 = clock64();
+#endif
             const uint32_t sbo = (uint32_t)(hp.PW * 128) >> 4;
             // everything of the A descriptor but the start address: LBO = 1, SBO = patch row pitch, version 1, SWIZZLE_128B
             const uint64_t adesc_hi = ((uint64_t)1 << 16) | ((uint64_t)(sbo & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
+                {
+                    HN_PROF_T0();
+                    if constexpr (PAIR) mbar_wait_cluster(smem_u32(tempty_bar + acc), acc_phase ^ 1);
+                    else mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
+                    HN_PROF_ADD(mw_tempty);
+                }
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
                 if (hp.b_resident) bst = 0;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(smem_u32(a_full + aslot), aphase);
+                    {
+                        HN_PROF_T0();
+                        if constexpr (PAIR && UPSAMPLE) mbar_wait_cluster(smem_u32(a_full + aslot), aphase);
+                        else mbar_wait(smem_u32(a_full + aslot), aphase);
+                        HN_PROF_ADD(mw_afull);
+                    }
                     tcgen05_fence_after();
                     const uint32_t a_base = smem_u32(a_ring + aslot * hp.a_slot_bytes);
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const int r = tap / 3, s = tap - r * 3;
-                        if (!hp.b_resident || first) {
+                        if ((!hp.b_resident || first) && tap % TPS == 0) {
+                            HN_PROF_T0();
                             mbar_wait(smem_u32(b_full + bst), bphase);
+                            HN_PROF_ADD(mw_bfull);
                             tcgen05_fence_after();
                         }
                         // sub-window of the patch: starts (r*d) patch rows and (s*d) pixels in; 8-row groups are one patch row apart
                         const uint32_t a_addr = a_base + (uint32_t)((r * d) * hp.PW + s * d) * 128;
                         const uint64_t adesc = adesc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
-                        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(b_ring + bst * B_STAGE_BYTES));
+                        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(b_ring + bst * B_STAGE_BYTES + (tap % TPS) * B_TAP_BYTES));
                         if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                umma_bf16(d_tmem + (NACC == 2 ? (tap & 1) * SUB_ACC : 0), adesc + 2 * k, bdesc + 2 * k, IDESC,
-                                          NACC == 2 ? ((kb | (tap >> 1) | k) != 0) : ((kb | tap | k) != 0));
-                            if (!hp.b_resident) umma_commit(smem_u32(b_empty + bst));
+                                umma_bf16_t<PAIR>(d_tmem + (NACC == 2 ? (tap & 1) * SUB_ACC : 0), adesc + 2 * k, bdesc + 2 * k, IDESC,
+                                                  NACC == 2 ? ((kb | (tap >> 1) | k) != 0) : ((kb | tap | k) != 0));
+                            if (!hp.b_resident && tap % TPS == TPS - 1) umma_commit_t<PAIR>(smem_u32(b_empty + bst));
                             if (tap == 8) {
-                                umma_commit(smem_u32(a_empty + aslot));
-                                if (kb == num_kb - 1) umma_commit(smem_u32(tfull_bar + acc));
+                                umma_commit_t<PAIR>(smem_u32(a_empty + aslot));
+                                if (kb == num_kb - 1) umma_commit_t<PAIR>(smem_u32(tfull_bar + acc));
                             }
                         }
                         __syncwarp();
-                        if (++bst == hp.nb) { bst = 0; bphase ^= 1; }
+                        if (tap % TPS == TPS - 1 && ++bst == hp.nb) { bst = 0; bphase ^= 1; }
                     }
-                    if (++aslot == HALO_NA) { aslot = 0; aphase ^= 1; }
+                    if (++aslot == hp.na) { aslot = 0; aphase ^= 1; }
                 }
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                if (++acc == NBUF) { acc = 0; acc_phase ^= 1; }
                 first = false;
+                ++ntl;
             }
+#ifdef HN_PROFILE_ROLES
+            if (lane == 0) {
+                HN_PROF_FLUSH(2, mw_afull); HN_PROF_FLUSH(11, mw_bfull); HN_PROF_FLUSH(3, mw_tempty); HN_PROF_FLUSH(4, clock64() - mma_t0);
+                HN_PROF_FLUSH(9, ntl); HN_PROF_FLUSH(10, 1);
+            }
+#endif
         }
     } else if (is_prod) {
         // ===================== halo patch producers (UPSAMPLE): bilinear 2x of the low-res input on the fly =====================
@@ -212,11 +269,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint32_t aphase = 0;
         const int Hu = 2 * hp.Hl, Wu = 2 * hp.Wl;
         const int ntask = hp.PH * hp.PW * 8;
+        const uint32_t a_full0 = PAIR ? mapa_u32(smem_u32(a_full), 0) : smem_u32(a_full);   // the leader's "patch ready" barriers
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int mt = tile / p.n_tiles;
+            int nt, mt;
+            decode_tile<PAIR>(p, tile, nt, mt);
+            (void)nt;
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
             const int uy0 = th * HALO_TH - 1, ux0 = tw * HALO_TW - 1;
-            const __nv_bfloat16 *ximg = hp.xlow + (int64_t)img * hp.Hl * hp.Wl * hp.ldx;
+            const bool img_ok = !PAIR || img < p.n_img;          // the filler tile of an odd pair: an all-zero patch
+            const __nv_bfloat16 *ximg = hp.xlow + (int64_t)(img_ok ? img : 0) * hp.Hl * hp.Wl * hp.ldx;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(smem_u32(a_empty + aslot), aphase ^ 1);
                 const uint32_t a_base = smem_u32(a_ring + aslot * hp.a_slot_bytes);
@@ -239,7 +300,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         const int uy = uy0 + py, ux = ux0 + px;
                         const uint32_t rowaddr = a_base + pp * 128;
                         dst[u] = rowaddr + ((j ^ ((rowaddr >> 7) & 7)) << 4);
-                        if (uy >= 0 && uy < Hu && ux >= 0 && ux < Wu) {
+                        if (img_ok && uy >= 0 && uy < Hu && ux >= 0 && ux < Wu) {
                             inb[u] = true;
                             int y0, y1, x0, x1;
                             bilinear_src_h(uy, hp.Hl, y0, y1, ly[u]);
@@ -276,33 +337,70 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(a_full + aslot));
-                if (++aslot == HALO_NA) { aslot = 0; aphase ^= 1; }
+                if (lane == 0) {
+                    if constexpr (PAIR) mbar_arrive_cluster(a_full0 + aslot * 8);
+                    else mbar_arrive(smem_u32(a_full + aslot));
+                }
+                if (++aslot == hp.na) { aslot = 0; aphase ^= 1; }
             }
         }
     } else if (is_epi) {
-        conv_epilogue<BLOCK_N, UPSAMPLE, NACC>(p, &tmap_y, &tmap_r, tmem_base, tfull_bar, tempty_bar, res_bar, epi_stage, s_shift, num_tiles, warp, lane);
+        conv_epilogue<BLOCK_N, UPSAMPLE, NACC, PAIR, NBUF>(p, &tmap_y, &tmap_r, tmem_base, tfull_bar, tempty_bar, res_bar, epi_stage, s_shift, num_tiles, warp, lane);
     }
 
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();
+    else __syncthreads();
     if (warp == 2) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if constexpr (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
-template <int BN, bool UP>
+template <int BN, bool UP, bool PAIR = false>
 static int launch_halo(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &ty, const CUtensorMap &tr, const HaloParams &hp,
-                       size_t smem, int num_tiles, cudaStream_t st)
+                       size_t smem, int num_m_tiles, cudaStream_t st)
 {
-    static size_t configured = 0;
-    if (configured < smem) {
-        HN_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-        configured = 227 * 1024;
+    static bool configured = false;
+    static int pairs = 0;
+    if (!configured) {
+        HN_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, UP, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        if (PAIR) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2, 1, 1);
+            cfg.blockDim = dim3(HALO_THREADS, 1, 1);
+            cfg.dynamicSmemBytes = 227 * 1024;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            if (cudaOccupancyMaxActiveClusters(&pairs, conv_halo_kernel<BN, UP, PAIR>, &cfg) != cudaSuccess || pairs < 1) {
+                cudaGetLastError();
+                pairs = num_sms() / 2;
+            }
+        }
+        configured = true;
     }
-    int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    conv_halo_kernel<BN, UP><<<grid, HALO_THREADS, smem, st>>>(ta, tb, ty, tr, hp);
+    if constexpr (PAIR) {
+        const int want = ((num_m_tiles + 1) / 2) * hp.t.n_tiles;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * (unsigned)(want < pairs ? want : pairs), 1, 1);
+        cfg.blockDim = dim3(HALO_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        HN_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, UP, PAIR>, ta, tb, ty, tr, hp));
+    } else {
+        const int num_tiles = num_m_tiles * hp.t.n_tiles;
+        int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+        conv_halo_kernel<BN, UP, PAIR><<<grid, HALO_THREADS, smem, st>>>(ta, tb, ty, tr, hp);
+    }
     HN_LAUNCH_CHECK();
     return HN_OK;
 }
@@ -325,7 +423,10 @@ bool conv_halo_ok(const hn_tensor *x, const hn_conv *cv, const hn_tensor *y, boo
         int64_t a = cdiv(y->h, menu[i][0]) * menu[i][0] * cdiv(y->w, menu[i][1]) * menu[i][1];
         if (best < 0 || a < best) best = a;
     }
-    if (halo_area * 100 > best * 104) return false;                 // > 4 % more padded work than the generic kernel
+    // more padded work than the generic kernel is acceptable up to a point: 4 %, or 30 % for Cout <= 64, where the generic kernel is
+    // bound by its nine tap fetches per k-block (~570 TFLOP/s) and this one, on CTA pairs, is not (~1200)
+    const int waste_pct = hn_conv_cout_pad(cv->cout, HN_BF16) <= 64 ? 130 : 104;
+    if (halo_area * 100 > best * waste_pct) return false;
     // the gain is the 9x smaller A traffic: decisive for narrow outputs, irrelevant for wide compute-bound layers
     return hn_conv_cout_pad(cv->cout, HN_BF16) <= 128;
 }
@@ -355,16 +456,27 @@ int conv2d_fwd_halo(const hn_tensor *x, const void *w, const hn_conv *cv, const 
         if (cout_pad % cand == 0 && (int64_t)num_m_tiles * (cout_pad / cand) >= 2 * (int64_t)num_sms()) { bn = cand; break; }
     if (head) bn = 64;
     p.n_tiles = cout_pad / bn;
+    const bool pair = conv_pair_ok(bn, num_m_tiles, 9 * p.cblocks, true);
+    const int b_rows = pair ? bn / 2 : bn;          // weight rows each CTA stages per (k-block, tap)
     const int tail = 2048 /*classifier tile*/ + 2048 /*barriers + shift table*/;
     // shared-memory plan: A slots + B ring + epilogue staging + barriers
-    const int64_t fixed = (int64_t)HALO_NA * hp.a_slot_bytes + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + tail;
-    int nb = (int)((227 * 1024 - fixed) / (bn * 128));
+    const int tps = pair ? 3 : 1;                   // filter taps per B ring stage (the kernel's TPS)
+    const int stage_bytes = tps * b_rows * 128;
+    const int stages_per_kb = 9 / tps;
+    hp.na = pair ? HALO_NA_MAX : 2;
+    int64_t fixed = 0;
+    int nb = 0;
+    for (;; --hp.na) {          // pairs: as many patch slots as leave room for a useful weight ring
+        fixed = (int64_t)hp.na * hp.a_slot_bytes + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + tail;
+        nb = (int)((227 * 1024 - fixed) / stage_bytes);
+        if (nb >= (pair ? 4 : 2) || hp.na == 2) break;
+    }
     if (nb > HALO_NB_MAX) nb = HALO_NB_MAX;
     HN_CHECK_ARG(nb >= 2, "conv_halo: shared memory too small for this shape");
     hp.nb = nb;
-    hp.b_resident = (p.cblocks * 9 <= nb && p.n_tiles == 1) ? 1 : 0;   // one Cout tile: the same weights for every tile
-    if (hp.b_resident) hp.nb = p.cblocks * 9;
-    const size_t smem = (size_t)HALO_NA * hp.a_slot_bytes + (size_t)hp.nb * bn * 128 + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 + tail;
+    hp.b_resident = (p.cblocks * stages_per_kb <= nb && p.n_tiles == 1) ? 1 : 0;   // one Cout tile: the same weights for every tile
+    if (hp.b_resident) hp.nb = p.cblocks * stages_per_kb;
+    const size_t smem = (size_t)hp.na * hp.a_slot_bytes + (size_t)hp.nb * stage_bytes + NUM_EPI_WARPS * EPI_STAGE_BYTES + 1024 + tail;
 
     CUtensorMap ta, tb, ty, tr;
     memset(&ta, 0, sizeof(ta));
@@ -383,7 +495,7 @@ int conv2d_fwd_halo(const hn_tensor *x, const void *w, const hn_conv *cv, const 
     {
         uint64_t dims[2] = {(uint64_t)kpad, (uint64_t)cout_pad};
         uint64_t strides[2] = {2, (uint64_t)kpad * 2};
-        uint32_t box[2] = {64, (uint32_t)bn};
+        uint32_t box[2] = {64, (uint32_t)b_rows};
         int rc = make_tmap(&tb, w, 2, dims, strides, box);
         if (rc) return rc;
     }
@@ -417,18 +529,23 @@ int conv2d_fwd_halo(const hn_tensor *x, const void *w, const hn_conv *cv, const 
             }
         }
     }
-    const int num_tiles = num_m_tiles * p.n_tiles;
+    if (pair) {
+        if (upsample) return bn == 128 ? launch_halo<128, true, true>(ta, tb, ty, tr, hp, smem, num_m_tiles, st)
+                                       : launch_halo<64, true, true>(ta, tb, ty, tr, hp, smem, num_m_tiles, st);
+        return bn == 128 ? launch_halo<128, false, true>(ta, tb, ty, tr, hp, smem, num_m_tiles, st)
+                         : launch_halo<64, false, true>(ta, tb, ty, tr, hp, smem, num_m_tiles, st);
+    }
     if (upsample) {
         switch (bn) {
-            case 256: return launch_halo<256, true>(ta, tb, ty, tr, hp, smem, num_tiles, st);
-            case 128: return launch_halo<128, true>(ta, tb, ty, tr, hp, smem, num_tiles, st);
-            default: return launch_halo<64, true>(ta, tb, ty, tr, hp, smem, num_tiles, st);
+            case 256: return launch_halo<256, true>(ta, tb, ty, tr, hp, smem, num_m_tiles, st);
+            case 128: return launch_halo<128, true>(ta, tb, ty, tr, hp, smem, num_m_tiles, st);
+            default: return launch_halo<64, true>(ta, tb, ty, tr, hp, smem, num_m_tiles, st);
         }
     }
     switch (bn) {
-        case 256: return launch_halo<256, false>(ta, tb, ty, tr, hp, smem, num_tiles, st);
-        case 128: return launch_halo<128, false>(ta, tb, ty, tr, hp, smem, num_tiles, st);
-        default: return launch_halo<64, false>(ta, tb, ty, tr, hp, smem, num_tiles, st);
+        case 256: return launch_halo<256, false>(ta, tb, ty, tr, hp, smem, num_m_tiles, st);
+        case 128: return launch_halo<128, false>(ta, tb, ty, tr, hp, smem, num_m_tiles, st);
+        default: return launch_halo<64, false>(ta, tb, ty, tr, hp, smem, num_m_tiles, st);
     }
 }
 

@@ -30,18 +30,22 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 384;   // 4 control warps + 8 epilogue warps
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int BLOCK_N, int STAGES, int BK = BLOCK_K>
+// PAIR: launched as clusters of two CTAs (hn_tc_ptx.cuh, "CTA pairs"): each CTA stages its own M tile and half of the Cout tile's
+// weight rows, the leader's MMA warp issues one M = 256 instruction for both and commits to the barriers of both.
+template <int BLOCK_N, int STAGES, int BK = BLOCK_K, bool PAIR = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_r, const TcParams p)
 {
     constexpr int A_STAGE_BYTES = BLOCK_M * BK * 2;
-    constexpr int B_STAGE_BYTES = BLOCK_N * BK * 2;
+    constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;      // weight rows staged by this CTA
+    constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static_assert(A_STAGE_BYTES % 1024 == 0 && B_STAGE_BYTES % 1024 == 0, "stage tiles must keep 1024-byte alignment");
     constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;   // columns per accumulator buffer
     constexpr int TMEM_COLS = 2 * ACC_COLS;                   // power of two >= 32
-    constexpr uint32_t IDESC = make_idesc_bf16(BLOCK_M, BLOCK_N);
+    constexpr uint32_t IDESC = make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -54,7 +58,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_m_tiles = p.n_img * p.tiles_h * p.tiles_w;
-    const int num_tiles = num_m_tiles * p.n_tiles;
+    const int num_tiles = PAIR ? pair_num_tiles(num_m_tiles, p.n_tiles) : num_m_tiles * p.n_tiles;
     const int num_kb = p.R * p.S * p.cblocks;
 
     if (warp == 0 && lane == 0) {
@@ -70,17 +74,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(tfull_bar + i), 1);
-            mbar_init(smem_u32(tempty_bar + i), BLOCK_N >= 128 ? 8 : 4);   // one arrive per working epilogue warp
+            mbar_init(smem_u32(tempty_bar + i), (BLOCK_N >= 128 ? 8 : 4) * (PAIR ? 2 : 1));   // one arrive per working epilogue warp (of both CTAs)
         }
         for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(smem_u32(res_bar + i), 1);
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
-        tmem_relinquish();
+        if constexpr (PAIR) { tmem_alloc_pair(smem_u32(tmem_slot), TMEM_COLS); tmem_relinquish_pair(); }
+        else { tmem_alloc(smem_u32(tmem_slot), TMEM_COLS); tmem_relinquish(); }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();          // the peer's barriers are initialised before anything is signalled on them
+    else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -96,7 +101,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #endif
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 ++ntl;
-                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+                int nt, mt;
+                decode_tile<PAIR>(p, tile, nt, mt);
                 const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
                 const int w_base = tw * p.TW * p.wmul - p.pad_w, h_base = th * p.TH * p.hmul - p.pad;
                 int kb = 0;
@@ -107,9 +113,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             const uint32_t fb = smem_u32(full_bar + stage);
                             const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                             if (elect_one()) {
-                                mbar_expect_tx(fb, STAGE_BYTES);
-                                tma_load_4d(sa, &tmap_a, fb, cb * BK, w_base + s * p.dil, h_base + r * p.dil, img);
-                                tma_load_2d(sa + A_STAGE_BYTES, &tmap_b, fb, kb * BK, nt * BLOCK_N);
+                                if constexpr (PAIR) {
+                                    // both CTAs' bytes are counted on the LEADER's barrier (its MMA warp consumes the stage of both)
+                                    const uint32_t lfb = mapa_u32(fb, 0);
+                                    if (rank == 0) mbar_expect_tx(fb, 2 * STAGE_BYTES);
+                                    tma_load_4d_pair(sa, &tmap_a, lfb, cb * BK, w_base + s * p.dil, h_base + r * p.dil, img);
+                                    tma_load_2d_pair(sa + A_STAGE_BYTES, &tmap_b, lfb, kb * BK, nt * BLOCK_N + (int)rank * B_ROWS);
+                                } else {
+                                    mbar_expect_tx(fb, STAGE_BYTES);
+                                    tma_load_4d(sa, &tmap_a, fb, cb * BK, w_base + s * p.dil, h_base + r * p.dil, img);
+                                    tma_load_2d(sa + A_STAGE_BYTES, &tmap_b, fb, kb * BK, nt * BLOCK_N);
+                                }
                             }
                             __syncwarp();
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -120,8 +134,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (lane == 0) { HN_PROF_FLUSH(0, pw_empty); HN_PROF_FLUSH(1, pw_total); HN_PROF_FLUSH(9, ntl); HN_PROF_FLUSH(10, 1); }
 #endif
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (whole warp, elected lane issues) =====================
+    } else if (warp == 1 && rank == 0) {
+        // ===================== MMA issuer (whole warp, elected lane issues; the leader CTA of a pair) =====================
         {
             int stage = 0;
             uint32_t phase = 0;
@@ -133,7 +147,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const long long mma_t0 = clock64();
 #endif
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                { HN_PROF_T0(); mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1); HN_PROF_ADD(mw_tempty); }
+                {
+                    HN_PROF_T0();
+                    if constexpr (PAIR) mbar_wait_cluster(smem_u32(tempty_bar + acc), acc_phase ^ 1);
+                    else mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
+                    HN_PROF_ADD(mw_tempty);
+                }
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -146,10 +165,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
                             // advance 16 BF16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
-                            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+                            umma_bf16_t<PAIR>(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
                         }
-                        umma_commit(smem_u32(empty_bar + stage));   // frees the smem slot when these MMAs retire
-                        if (kb == num_kb - 1) umma_commit(smem_u32(tfull_bar + acc));   // accumulator ready for the epilogue
+                        umma_commit_t<PAIR>(smem_u32(empty_bar + stage));   // frees the smem slot (of both CTAs) when these MMAs retire
+                        if (kb == num_kb - 1) umma_commit_t<PAIR>(smem_u32(tfull_bar + acc));   // accumulator ready for the epilogue(s)
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -162,14 +181,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #endif
         }
     } else if (warp >= EPI_WARP0) {
-        conv_epilogue<BLOCK_N>(p, &tmap_y, &tmap_r, tmem_base, tfull_bar, tempty_bar, res_bar, epi_stage, s_shift, num_tiles, warp, lane);
+        conv_epilogue<BLOCK_N, false, 1, PAIR>(p, &tmap_y, &tmap_r, tmem_base, tfull_bar, tempty_bar, res_bar, epi_stage, s_shift, num_tiles, warp, lane);
     }
 
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();          // no CTA leaves while its peer can still signal its barriers / write its TMEM
+    else __syncthreads();
     if (warp == 2) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if constexpr (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -354,22 +375,97 @@ int64_t conv2d_tc_workspace(const hn_tensor *x, const hn_conv *cv)
     return (int64_t)x->n * Ho * Wo * hn_conv_kpad(x->c, cv->r, cv->s) * 2;
 }
 
-template <int BN, int STAGES, int BK = BLOCK_K>
-static int launch_tc(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &ty, const CUtensorMap &tr, const TcParams &p,
-                     int num_tiles, cudaStream_t st)
+// CTA pairs pay off whenever the tile is too narrow for one instruction to keep a tensor pipe busy (N <= 128) and there are at least
+// two M tiles.  HN_NO_PAIR=1 keeps every launch on single CTAs (A/B measurements, bisecting).
+// Not for short reductions (1x1 layers: a tile is a handful of instructions and the kernel is bound by HBM and by the tile hand-over
+// between the roles, which the pair's cross-CTA signalling lengthens: measured 15-50 % slower) -- num_kb >= 9 k-blocks per tile.
+bool conv_pair_ok(int bn, int num_m_tiles, int num_kb, bool halo)
 {
-    constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BK * 2 + BN * BK * 2) + NUM_EPI_WARPS * EPI_STAGE_BYTES +
+    static const bool disabled = getenv("HN_NO_PAIR") != nullptr;
+    static const bool tc_disabled = getenv("HN_NO_PAIR_TC") != nullptr;          // generic kernel only
+    static const int min_kb = getenv("HN_PAIR_MIN_KB") ? atoi(getenv("HN_PAIR_MIN_KB")) : 9;
+    if (disabled || (tc_disabled && !halo)) return false;
+    return bn >= 32 && bn <= 128 && num_m_tiles >= 2 && (halo || num_kb >= min_kb);
+}
+
+// clusters of two CTAs that can be resident at once (one CTA per SM: normally num_sms / 2)
+template <typename K>
+static int max_pairs(K kernel, size_t smem, int threads)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2, 1, 1);
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = num_sms() / 2;
+    }
+    return n;
+}
+
+template <int BN, int STAGES, int BK = BLOCK_K, bool PAIR = false>
+static int launch_tc(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &ty, const CUtensorMap &tr, const TcParams &p,
+                     int num_m_tiles, cudaStream_t st)
+{
+    constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BK * 2 + (PAIR ? BN / 2 : BN) * BK * 2) + NUM_EPI_WARPS * EPI_STAGE_BYTES +
                             (2 * STAGES + 4 + NUM_EPI_WARPS) * 8 + 16 + (BN < 128 ? 2 : 1) * BN * 4 + 1024;   // narrow tiles: one shift table per epilogue group
     static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
     static bool configured = false;
+    static int pairs = 0;
     if (!configured) {
-        HN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, BK, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (PAIR) pairs = max_pairs(conv_tc_kernel<BN, STAGES, BK, PAIR>, smem, NUM_THREADS);
         configured = true;
     }
-    int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    conv_tc_kernel<BN, STAGES, BK><<<grid, NUM_THREADS, smem, st>>>(ta, tb, ty, tr, p);
+    if constexpr (PAIR) {
+        const int want = ((num_m_tiles + 1) / 2) * p.n_tiles;          // (M-tile pair, Cout tile) work items
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * (unsigned)(want < pairs ? want : pairs), 1, 1);
+        cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        HN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, BK, PAIR>, ta, tb, ty, tr, p));
+    } else {
+        const int num_tiles = num_m_tiles * p.n_tiles;
+        int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+        conv_tc_kernel<BN, STAGES, BK, PAIR><<<grid, NUM_THREADS, smem, st>>>(ta, tb, ty, tr, p);
+    }
     HN_LAUNCH_CHECK();
     return HN_OK;
+}
+
+// the Cout-tile menu of the kernel; `pair` selects the two-CTA form (the weight map's box then holds bn / 2 rows)
+static int launch_tc_bn(int bn, bool pair, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &ty, const CUtensorMap &tr,
+                        const TcParams &p, int num_m_tiles, cudaStream_t st)
+{
+    if (pair) {
+        switch (bn) {
+            case 128: return launch_tc<128, 6, BLOCK_K, true>(ta, tb, ty, tr, p, num_m_tiles, st);
+            case 64: return launch_tc<64, 8, BLOCK_K, true>(ta, tb, ty, tr, p, num_m_tiles, st);
+            case 32: return launch_tc<32, 8, BLOCK_K, true>(ta, tb, ty, tr, p, num_m_tiles, st);
+        }
+    } else {
+        switch (bn) {
+            case 256: return launch_tc<256, 4>(ta, tb, ty, tr, p, num_m_tiles, st);
+            case 128: return launch_tc<128, 6>(ta, tb, ty, tr, p, num_m_tiles, st);
+            case 64: return launch_tc<64, 7>(ta, tb, ty, tr, p, num_m_tiles, st);
+            case 32: return launch_tc<32, 8>(ta, tb, ty, tr, p, num_m_tiles, st);
+            case 16: return launch_tc<16, 8>(ta, tb, ty, tr, p, num_m_tiles, st);
+        }
+    }
+    set_error("conv_tc: unsupported Cout tile %d", bn);
+    return HN_ERR_ARG;
 }
 
 int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn_epilogue *ep, const hn_tensor *y, void *ws,
@@ -454,10 +550,11 @@ int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn
     }
     p.n_tiles = cout_pad / bn;
     p.Cout = cv->cout;
+    const bool pair = conv_pair_ok(bn, num_m_tiles, p.R * p.S * p.cblocks, false);
     {
         uint64_t dims[2] = {(uint64_t)kpad, (uint64_t)cout_pad};
         uint64_t strides[2] = {2, (uint64_t)kpad * 2};
-        uint32_t box[2] = {64, (uint32_t)bn};
+        uint32_t box[2] = {64, (uint32_t)(pair ? bn / 2 : bn)};
         int rc = make_tmap(&tb, w, 2, dims, strides, box);
         if (rc) return rc;
     }
@@ -466,7 +563,6 @@ int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn
     p.act = ep->act; p.slope = ep->slope; p.slope_ptr = ep->slope_ptr;
     p.stat_sum = ep->stat_sum; p.stat_sqsum = ep->stat_sqsum;
     if (int rcg = set_stat_groups(p, ep, y)) return rcg;
-    const int num_tiles = num_m_tiles * p.n_tiles;
     // epilogue tensor maps: the output view (and the residual view) as {C, W, H, N} with a {128 B, ebw, 32/ebw, 1} box
     CUtensorMap ty, tr;
     memset(&ty, 0, sizeof(ty));
@@ -490,15 +586,7 @@ int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn
             }
         }
     }
-    switch (bn) {
-        case 256: return launch_tc<256, 4>(ta, tb, ty, tr, p, num_tiles, st);
-        case 128: return launch_tc<128, 6>(ta, tb, ty, tr, p, num_tiles, st);
-        case 64: return launch_tc<64, 7>(ta, tb, ty, tr, p, num_tiles, st);
-        case 32: return launch_tc<32, 8>(ta, tb, ty, tr, p, num_tiles, st);
-        case 16: return launch_tc<16, 8>(ta, tb, ty, tr, p, num_tiles, st);
-    }
-    set_error("conv_tc: unsupported Cout tile %d", bn);
-    return HN_ERR_ARG;
+    return launch_tc_bn(bn, pair, ta, tb, ty, tr, p, num_m_tiles, st);
 }
 
 
@@ -553,10 +641,11 @@ int conv2d_fwd_tc_sub(const hn_tensor *x, const void *w, int cout, const TcSubCo
     }
     p.n_tiles = cout_pad / bn;
     p.Cout = cout;
+    const bool pair = conv_pair_ok(bn, num_m_tiles, p.R * p.S * p.cblocks, false);
     {
         uint64_t dims[2] = {(uint64_t)kpad, (uint64_t)cout_pad};
         uint64_t strides[2] = {2, (uint64_t)kpad * 2};
-        uint32_t box[2] = {64, (uint32_t)bn};
+        uint32_t box[2] = {64, (uint32_t)(pair ? bn / 2 : bn)};
         int rc = make_tmap(&tb, w, 2, dims, strides, box);
         if (rc) return rc;
     }
@@ -576,16 +665,7 @@ int conv2d_fwd_tc_sub(const hn_tensor *x, const void *w, int cout, const TcSubCo
             p.res = sc->y; p.ldr = 0; p.tma_res = 1;
         }
     }
-    const int num_tiles = num_m_tiles * p.n_tiles;
-    switch (bn) {
-        case 256: return launch_tc<256, 4>(ta, tb, ty, tr, p, num_tiles, st);
-        case 128: return launch_tc<128, 6>(ta, tb, ty, tr, p, num_tiles, st);
-        case 64: return launch_tc<64, 7>(ta, tb, ty, tr, p, num_tiles, st);
-        case 32: return launch_tc<32, 8>(ta, tb, ty, tr, p, num_tiles, st);
-        case 16: return launch_tc<16, 8>(ta, tb, ty, tr, p, num_tiles, st);
-    }
-    set_error("conv_tc_sub: unsupported Cout tile %d", bn);
-    return HN_ERR_ARG;
+    return launch_tc_bn(bn, pair, ta, tb, ty, tr, p, num_m_tiles, st);
 }
 
 
@@ -650,8 +730,7 @@ int conv_stem_tc(const hn_tensor *xpad, const void *w, int cout, const hn_epilog
         }
     }
     HN_CHECK_ARG(!ep->residual, "conv_stem: no residual input");
-    const int num_tiles = p.n_img * p.tiles_h * p.tiles_w;
-    return launch_tc<64, 12, BK>(ta, tb, ty, tr, p, num_tiles, st);
+    return launch_tc<64, 12, BK>(ta, tb, ty, tr, p, p.n_img * p.tiles_h * p.tiles_w, st);
 }
 
 }  // namespace hn

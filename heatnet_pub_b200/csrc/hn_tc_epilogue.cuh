@@ -114,7 +114,26 @@ __device__ __forceinline__ void head_emit(const TcParams &p, uint32_t taddr, uin
 // ~224 KB of the SM carved out as shared memory there is next to no L1: per-element __ldg costs an L2 round trip),
 // residual add / ReLU run on packed pairs, swizzled staging offsets are precomputed.  Anything else (FP32 outputs,
 // unaligned views, explicit scale, LeakyReLU + residual) takes the general path below.
-template <int BLOCK_N, bool ONE_GROUP = false, int NACC = 1>
+// CTA pairs (PAIR): `tile` walks an extended index space -- tile >> 1 is the (M-tile pair, Cout tile) the pair works on, tile & 1
+// (= this CTA's cluster rank) the M tile of the pair; an odd M-tile count leaves the last pair's second CTA a tile beyond the last
+// image, whose loads are zero-filled and whose stores are clipped by the TMA unit.
+template <bool PAIR>
+__device__ __forceinline__ void decode_tile(const TcParams &p, int tile, int &nt, int &mt)
+{
+    if constexpr (PAIR) {
+        const int pt = tile >> 1;
+        nt = pt % p.n_tiles;
+        mt = (pt / p.n_tiles) * 2 + (tile & 1);
+    } else {
+        nt = tile % p.n_tiles;
+        mt = tile / p.n_tiles;
+    }
+}
+// size of that index space
+__host__ __device__ inline int pair_num_tiles(int num_m_tiles, int n_tiles) { return 2 * ((num_m_tiles + 1) / 2) * n_tiles; }
+
+// NBUF: accumulator buffers of ACC_COLS TMEM columns each; this CTA's it-th tile uses buffer it % NBUF.
+template <int BLOCK_N, bool ONE_GROUP = false, int NACC = 1, bool PAIR = false, int NBUF = 2>
 __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorMap *tmap_y_p, const CUtensorMap *tmap_r_p, uint32_t tmem_base,
                                               uint64_t *tfull_bar, uint64_t *tempty_bar, uint64_t *res_bar, uint8_t *epi_stage,
                                               float *s_shift, int num_tiles, int warp, int lane)
@@ -131,7 +150,8 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
     constexpr int SUB = COLS < 32 ? COLS : 32;             // columns per tcgen05.ld
     const int ew = warp - EPI_WARP0;
     const int q = ew & 3, grp = ew >> 2;
-    // narrow tiles (one column group): the two groups of 4 warps ALTERNATE tiles -- group g owns accumulator buffer g, i.e.
+    static_assert(NBUF % 2 == 0, "the alternating epilogue groups need an even number of accumulator buffers");
+    // narrow tiles (one column group): the two groups of 4 warps ALTERNATE tiles -- group g owns the accumulator buffers = g (mod 2), i.e.
     // every other tile of this CTA -- so two tiles are in the epilogue at once (measured: the N = 64 layers were epilogue-bound)
     constexpr bool ALT = GROUPS == 1 && !ONE_GROUP;
     if (!ALT && grp >= GROUPS) return;
@@ -146,8 +166,6 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
     for (int c = 0; c < 8; ++c) off[c] = srow + ((c ^ (lane & 7)) << 4);
     const uint32_t rbar = smem_u32(res_bar + ew);
     uint32_t rphase = 0;
-    int acc = ALT ? grp : 0;
-    uint32_t acc_phase = 0;
     float slope = p.slope;
     if (p.slope_ptr) slope = __ldg(p.slope_ptr);
     const int act = p.act;
@@ -160,8 +178,8 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
     float *tab = s_shift + (ALT ? grp * BLOCK_N : col0);   // this group's per-channel shift table (ALT: one full table per group)
     const uint32_t tab_addr = smem_u32(tab);
     int loaded_ctile = -1;
-    long long ew_tfull = 0, ew_bulk = 0, ew_res = 0;
-    (void)ew_tfull; (void)ew_bulk; (void)ew_res;
+    long long ew_tfull = 0, ew_bulk = 0, ew_res = 0, ew_ld = 0, ew_st = 0, ew_arr = 0;
+    (void)ew_tfull; (void)ew_bulk; (void)ew_res; (void)ew_ld; (void)ew_st; (void)ew_arr;
 #ifdef HN_PROFILE_ROLES
     const long long epi_t0 = clock64();
 #endif
@@ -169,16 +187,22 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
     bool have_prev = false, prev_valid = false;
     uint32_t hph = 0;                                   // phase of this group's head barrier
     const uint32_t head_bar = smem_u32(res_bar + 4 * grp);            // no residual with a head: this group's first res_bar is free
-    const uint32_t head_d2 = tmem_base + 2 * ACC_COLS + grp * HEAD_MAX;   // this group's logits accumulator (16 TMEM columns)
+    const uint32_t head_ready = smem_u32(res_bar + 4 * grp + 1);      // pairs: "both CTAs have staged their tile" (initialised with count 2)
+    uint32_t rdy_phase = 0;
+    (void)head_ready; (void)rdy_phase;
+    const uint32_t head_d2 = tmem_base + NBUF * ACC_COLS + grp * HEAD_MAX;   // this group's logits accumulator (16 TMEM columns)
     if constexpr (BLOCK_N == 64) {
         if (head) {
             // classifier weights -> BF16 [16 classes][64 ch] K-major SWIZZLE_128B tile behind the staging buffers (rows >= head_n: 0)
-            const int t = q * 32 + lane, k = t >> 3, cidx = t & 7;
+            // (a CTA of a pair holds classes [8 * rank, +8): its half of the N = 16 rows of the pair's B operand)
+            const int t = q * 32 + lane, kl = PAIR ? (t >> 3) & 7 : t >> 3, cidx = t & 7;
+            const int k = PAIR ? 8 * (int)cluster_ctarank() + kl : kl;
             __nv_bfloat162 h4[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) h4[e] = __floats2bfloat162_rn(p.head.w[k][cidx * 8 + 2 * e], p.head.w[k][cidx * 8 + 2 * e + 1]);
             if (grp == 0) {
-                sts128(smem_u32(epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES) + k * 128 + ((cidx ^ (k & 7)) << 4), *reinterpret_cast<const uint4 *>(h4));
+                if (!PAIR || t < 64)
+                    sts128(smem_u32(epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES) + kl * 128 + ((cidx ^ (kl & 7)) << 4), *reinterpret_cast<const uint4 *>(h4));
                 fence_proxy_async();
             }
             named_bar_sync(3, ALT ? 256 : 128);
@@ -207,19 +231,33 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
             st_s[i] = st_q[i] = 0.f;
         }
     };
+    // "this accumulator has been read": the MMA issuer lives in the leader CTA of a pair
+    const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0;
+    const uint32_t tempty_leader = PAIR ? mapa_u32(smem_u32(tempty_bar), 0) : 0;
+    (void)pair_rank; (void)tempty_leader;
+    auto tempty_arrive = [&](int a) {
+        if constexpr (PAIR) {
+            if (pair_rank == 0) mbar_arrive(smem_u32(tempty_bar + a));
+            else mbar_arrive_cluster(tempty_leader + a * 8);
+        } else mbar_arrive(smem_u32(tempty_bar + a));
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         if (ALT && (it & 1) != grp) continue;
-        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+        const int acc = it % NBUF;                              // (ALT: the groups own the even / the odd buffers)
+        const uint32_t acc_phase = (uint32_t)(it / NBUF) & 1u;
+        int nt, mt;
+        decode_tile<PAIR>(p, tile, nt, mt);
         const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
         const int ho = th * p.TH + row / p.TW, wo = tw * p.TW + row % p.TW;
-        const bool valid = ho < p.Ho && wo < p.Wo;
+        const bool valid = ho < p.Ho && wo < p.Wo && (!PAIR || img < p.n_img);
         const int64_t pix = ((int64_t)img * p.Ho + ho) * p.Wo + wo;
         const int ctile = nt * BLOCK_N + col0;         // first output channel of this warp's columns
         if (p.stat_sum) {
             int grp = 0;                             // warp-uniform: the statistics group of this warp's 32-pixel block
             if (p.stat_group_img) grp = img / p.stat_group_img;
             else if (p.stat_group_pix) grp = (tw * p.TW + q * 32) / p.stat_group_pix;
+            if (PAIR && img >= p.n_img) grp = stat_grp;          // the filler tile of an odd pair contributes nothing
             if (ctile != stat_ctile || grp != stat_grp) {
                 stat_flush();
                 stat_ctile = ctile;
@@ -293,17 +331,27 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
                 tcgen05_fence_before();
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
-                if (ALT) acc_phase ^= 1;
-                else { acc ^= 1; if (acc == 0) acc_phase ^= 1; }
+                if (lane == 0) tempty_arrive(acc);
                 named_bar_sync(1 + grp, 128);           // all four staging quarters written, previous logits read
                 if (q == 0 && lane == 0) {
-                    tcgen05_fence_after();
-                    const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(epi_stage + (ew & 4) * EPI_STAGE_BYTES));
-                    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES));
+                    bool issue = true;
+                    if constexpr (PAIR) {
+                        // the pair's classifier MMA reads the staging tiles of BOTH CTAs: this group of either CTA reports "staged" on the
+                        // leader's barrier, the leader's thread issues for both and commits to the head barrier of both
+                        mbar_arrive_cluster(mapa_u32(head_ready, 0));
+                        issue = cluster_ctarank() == 0;
+                        if (issue) mbar_wait_cluster(head_ready, rdy_phase);
+                        rdy_phase ^= 1;
+                    }
+                    if (issue) {
+                        tcgen05_fence_after();
+                        const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(epi_stage + (ew & 4) * EPI_STAGE_BYTES));
+                        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(head_d2, adesc + 2 * k, bdesc + 2 * k, make_idesc_bf16(128, HEAD_MAX), k != 0);
-                    umma_commit(head_bar);
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_t<PAIR>(head_d2, adesc + 2 * k, bdesc + 2 * k, make_idesc_bf16(PAIR ? 256 : 128, HEAD_MAX), k != 0);
+                        umma_commit_t<PAIR>(head_bar);
+                    }
                 }
                 have_prev = true;
                 prev_img = img; prev_ho = ho; prev_wo = wo; prev_valid = valid;
@@ -333,6 +381,7 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
             const int nsub = (tch < COLS - ck ? tch : COLS - ck) / SUB;
             for (int si = 0; si < nsub; ++si) {
                 uint32_t raw[SUB];
+                HN_PROF_T0();
                 if constexpr (SUB == 32) tmem_ld_32x32(taddr + si * SUB, raw);
                 else if constexpr (SUB == 16) tmem_ld_32x16(taddr + si * SUB, raw);
                 if constexpr (NACC == 2 && SUB == 32) {
@@ -344,6 +393,7 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
                 } else {
                     tmem_ld_wait();
                 }
+                HN_PROF_ADD(ew_ld);
                 const int cbase = ctile + ck + si * SUB;
                 if (chunk_on) {
                     float v[SUB];
@@ -531,19 +581,23 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
                 }
             }
             if (tma_out) {
+                HN_PROF_T0();
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0 && chunk_on) {
                     tma_store_4d(&tmap_y, stage, ctile + ck, bx, by, img);
                     bulk_commit();
                 }
+                HN_PROF_ADD(ew_st);
             }
         }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
-        if (ALT) acc_phase ^= 1;
-        else { acc ^= 1; if (acc == 0) acc_phase ^= 1; }
+        {
+            HN_PROF_T0();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) tempty_arrive(acc);
+            HN_PROF_ADD(ew_arr);
+        }
     }
     if (p.stat_sum) stat_flush();
     if constexpr (BLOCK_N == 64) {
@@ -553,6 +607,7 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
 #ifdef HN_PROFILE_ROLES
     if (ew == 0 && lane == 0) {
         HN_PROF_FLUSH(5, ew_tfull); HN_PROF_FLUSH(6, ew_bulk); HN_PROF_FLUSH(7, ew_res); HN_PROF_FLUSH(8, clock64() - epi_t0);
+        HN_PROF_FLUSH(12, ew_ld); HN_PROF_FLUSH(13, ew_st); HN_PROF_FLUSH(14, ew_arr);
     }
 #endif
 }

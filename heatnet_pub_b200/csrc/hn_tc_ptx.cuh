@@ -74,6 +74,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3)
 {
     asm volatile(
@@ -202,6 +209,100 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n)
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+
+// ------------------------------------------------------------------------------------------------ CTA pairs (cta_group::2)
+// Two CTAs of a cluster on the two SMs of a TPC run ONE tcgen05.mma of M = 256: each CTA stages its own 128 A rows and HALF of
+// the B rows (N / 2) at the same shared-memory offsets, the leader (cluster rank 0) issues, D rows 0-127 land in the leader's
+// TMEM and rows 128-255 in the peer's.  What it buys (profiles/r2_mma_rate_probe_2cta.txt): one instruction feeds both tensor
+// pipes, so the ~82-cycle per-instruction floor that caps single-CTA N <= 128 tiles is paid once per 256 rows -- N = 64 runs at
+// 43 cycles per MMA (74 % of the pipe instead of 39 %), N = 128 at 64 cycles (100 % instead of 78 %).
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// Signal a barrier of the peer (or of this CTA, by its shared::cluster address).  RELAXED on purpose: a release at cluster scope costs a
+// ~2000-cycle fence per arrive (measured: it made the pair kernels slower than single CTAs), and nothing these signals hand over
+// travels through generic-proxy memory ordering -- an accumulator buffer is released after tcgen05.wait::ld has put it into registers,
+// a computed operand tile after fence.proxy.async + a CTA barrier have made it visible to the tensor core of the SM that holds it.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a local barrier whose arrivals may come from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+// TMA loads of a CTA pair: the data lands in the EXECUTING CTA's shared memory, the transaction bytes are signalled on `bar`, a
+// shared::cluster address that may belong to the peer (the leader's "operands of both CTAs have landed" barrier)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// the barrier at the same offset in BOTH CTAs of the pair arrives once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+// role-agnostic forms used by the kernels that are templated on PAIR
+template <bool PAIR> __device__ __forceinline__ void umma_bf16_t(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate)
+{
+    if constexpr (PAIR) umma_bf16_pair(d, a, b, idesc, accumulate);
+    else umma_bf16(d, a, b, idesc, accumulate);
+}
+template <bool PAIR> __device__ __forceinline__ void umma_commit_t(uint32_t bar)
+{
+    if constexpr (PAIR) umma_commit_pair(bar);
+    else umma_commit(bar);
+}
 
 // MN-major (the GEMM's M or N index is contiguous in memory), 128B-swizzled shared-memory matrix descriptor:
 // the tile is a stack of [K rows][64 elements = 128 B] blocks; LBO = byte distance between consecutive 64-element
