@@ -456,7 +456,7 @@ int conv2d_fwd_halo(const hn_tensor *x, const void *w, const hn_conv *cv, const 
         if (cout_pad % cand == 0 && (int64_t)num_m_tiles * (cout_pad / cand) >= 2 * (int64_t)num_sms()) { bn = cand; break; }
     if (head) bn = 64;
     p.n_tiles = cout_pad / bn;
-    const bool pair = conv_pair_ok(bn, num_m_tiles, 9 * p.cblocks, true);
+    const bool pair = bn <= 128 && conv_pair_ok(bn, num_m_tiles, 9 * p.cblocks, true);          // (the 256-wide tile only exists for upconv3x3)
     const int b_rows = pair ? bn / 2 : bn;          // weight rows each CTA stages per (k-block, tap)
     const int tail = 2048 /*classifier tile*/ + 2048 /*barriers + shift table*/;
     // shared-memory plan: A slots + B ring + epilogue staging + barriers

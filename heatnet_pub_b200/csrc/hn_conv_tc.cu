@@ -375,8 +375,10 @@ int64_t conv2d_tc_workspace(const hn_tensor *x, const hn_conv *cv)
     return (int64_t)x->n * Ho * Wo * hn_conv_kpad(x->c, cv->r, cv->s) * 2;
 }
 
-// CTA pairs pay off whenever the tile is too narrow for one instruction to keep a tensor pipe busy (N <= 128) and there are at least
-// two M tiles.  HN_NO_PAIR=1 keeps every launch on single CTAs (A/B measurements, bisecting).
+// CTA pairs pay off twice: a tile too narrow for one instruction to keep a tensor pipe busy (N <= 128) issues at up to twice the rate,
+// and every tile width stages only half of the weight rows per SM (N = 256: a third less L2 -> shared-memory traffic per k-block, one
+// more pipeline stage; measured +9 % on the 3x3 / deep 1x1 layers).  Needs two M tiles.  HN_NO_PAIR=1 keeps every launch on single
+// CTAs (A/B measurements, bisecting), HN_PAIR_MAX_BN / HN_PAIR_MIN_KB move the thresholds.
 // Not for short reductions (1x1 layers: a tile is a handful of instructions and the kernel is bound by HBM and by the tile hand-over
 // between the roles, which the pair's cross-CTA signalling lengthens: measured 15-50 % slower) -- num_kb >= 9 k-blocks per tile.
 bool conv_pair_ok(int bn, int num_m_tiles, int num_kb, bool halo)
@@ -384,8 +386,9 @@ bool conv_pair_ok(int bn, int num_m_tiles, int num_kb, bool halo)
     static const bool disabled = getenv("HN_NO_PAIR") != nullptr;
     static const bool tc_disabled = getenv("HN_NO_PAIR_TC") != nullptr;          // generic kernel only
     static const int min_kb = getenv("HN_PAIR_MIN_KB") ? atoi(getenv("HN_PAIR_MIN_KB")) : 9;
+    static const int max_bn = getenv("HN_PAIR_MAX_BN") ? atoi(getenv("HN_PAIR_MAX_BN")) : 256;
     if (disabled || (tc_disabled && !halo)) return false;
-    return bn >= 32 && bn <= 128 && num_m_tiles >= 2 && (halo || num_kb >= min_kb);
+    return bn >= 32 && bn <= max_bn && num_m_tiles >= 2 && (halo || num_kb >= min_kb);
 }
 
 // clusters of two CTAs that can be resident at once (one CTA per SM: normally num_sms / 2)
@@ -451,6 +454,7 @@ static int launch_tc_bn(int bn, bool pair, const CUtensorMap &ta, const CUtensor
 {
     if (pair) {
         switch (bn) {
+            case 256: return launch_tc<256, 5, BLOCK_K, true>(ta, tb, ty, tr, p, num_m_tiles, st);
             case 128: return launch_tc<128, 6, BLOCK_K, true>(ta, tb, ty, tr, p, num_m_tiles, st);
             case 64: return launch_tc<64, 8, BLOCK_K, true>(ta, tb, ty, tr, p, num_m_tiles, st);
             case 32: return launch_tc<32, 8, BLOCK_K, true>(ta, tb, ty, tr, p, num_m_tiles, st);

@@ -27,6 +27,10 @@ LAYERS = [
     ("up_3 class 3x3 64->64 full res (4 images)", 64, 64, 3, 1, 1, 1, 4, 650, 1920, False),
     ("up_2 3x3 256->64 half res (8 images)", 256, 64, 3, 1, 1, 1, 8, 325, 960, False),
     ("layer3 class 3x3 d2 256->256", 256, 256, 3, 1, 2, 2, 16, 82, 240, False),
+    ("layer4 3x3 d4 512->512", 512, 512, 3, 1, 4, 4, 16, 82, 240, False),
+    ("layer3 conv3 1x1 256->1024 +res", 256, 1024, 1, 1, 0, 1, 16, 82, 240, True),
+    ("layer4 conv1 1x1 2048->512", 2048, 512, 1, 1, 0, 1, 16, 82, 240, False),
+    ("layer3 conv1 1x1 1024->256", 1024, 256, 1, 1, 0, 1, 16, 82, 240, False),
     ("odd tile count 3x3 d2 64->64", 64, 64, 3, 1, 2, 2, 3, 37, 41, True),
 ]
 

@@ -141,6 +141,57 @@ def test_conv3x3_halo_patch_path(E, case):
     assert rel(back(y16), ref_r) < 1e-2
 
 
+PAIR_CASES = [
+    # cin, cout, k, pad, dil, n, h, w          two-CTA (cta_group::2) launches: the M tiles are handed out in pairs
+    (64, 64, 3, 1, 1, 1, 48, 8),       # halo kernel, 3 tiles: the last pair has a filler tile beyond the image
+    (64, 64, 3, 1, 1, 3, 16, 8),       # halo kernel, one tile per image, odd image count: filler tile = image index n
+    (256, 64, 3, 1, 1, 2, 40, 24),     # halo kernel, streamed weights (4 k-blocks x 3 ring stages), 9 tiles per image
+    (128, 128, 3, 1, 1, 1, 48, 24),    # halo kernel, N = 128
+    (64, 64, 3, 4, 4, 1, 24, 16),      # generic kernel (dilation 4), N = 64, 3 tiles
+    (128, 128, 3, 4, 4, 3, 8, 16),     # generic kernel, N = 128, odd tile count
+    (256, 256, 3, 4, 4, 1, 24, 16),    # generic kernel, N = 256 (the pair halves the staged weight rows), 3 tiles
+    (1024, 256, 1, 0, 1, 1, 9, 43),    # flat 1x1 with a long reduction (16 k-blocks): pairs over a flattened, ragged pixel axis
+    (192, 100, 3, 4, 4, 1, 24, 16),    # Cout not a multiple of the tile: the pair's second weight half is partly padding
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv_cta_pairs_with_odd_tile_counts(E, case):
+    """Layers that run on CTA pairs (hn_tc_ptx.cuh "CTA pairs": N <= 128 tiles, or >= 9 k-blocks on the generic kernel) with tile counts
+    that leave the last pair a filler tile: output, residual add and the fused batch statistics must ignore it."""
+    cin, cout, k, pad, dil, n, h, w = case
+    g = torch.Generator().manual_seed(21)
+    conv = nn.Conv2d(cin, cout, k, 1, pad, dil, bias=True)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * (2.0 / (k * k * cin)) ** 0.5)
+        conv.bias.copy_(torch.randn(cout, generator=g) * 0.1)
+    x = torch.randn(n, cin, h, w, generator=g)
+    res = torch.randn(n, cout, h, w, generator=g)
+    pre = F.conv2d(x.bfloat16().float(), conv.weight.detach().bfloat16().float(), conv.bias, 1, pad, dil)
+    convg = conv.cuda()
+    scale, shift = E.folded_affine(convg, None)
+    xa = to_act(E, x, torch.bfloat16)
+    ld = (cout + 7) // 8 * 8
+    # BF16 output + residual + ReLU through the TMA epilogue
+    y = E.conv2d(xa, convg, scale, shift, residual=to_act(E, res, torch.bfloat16), act=E.ACT_RELU, out=E.new_act(n, h, w, cout, torch.bfloat16, "cuda", ld=ld))
+    assert rel(back(y), F.relu(pre + res.bfloat16().float())) < 1e-2
+    # FP32 output with fused statistics: exactly the sums of what was stored
+    sums = torch.zeros((2, cout), dtype=torch.float64, device="cuda")
+    y32 = E.conv2d(xa, convg, scale, shift, None, E.ACT_NONE, out=E.new_act(n, h, w, cout, torch.float32, "cuda", ld=ld), stats=sums)
+    assert rel(back(y32), pre) < 1e-3
+    stored = y32.nchw().double()
+    want = torch.stack([stored.sum((0, 2, 3)), (stored * stored).sum((0, 2, 3))])
+    assert ((sums - want).abs() / want.abs().clamp_min(1e-3 * want.abs().max())).max().item() < 2e-5
+    # an unaligned output view (pixel stride not a multiple of 16 bytes) takes the per-thread store path: the filler tile must not write
+    if cout % 8 == 0:
+        guard = E.new_act(n, h, w, cout + 3, torch.bfloat16, "cuda")
+        guard.buf.fill_(7.0)
+        yv = E.conv2d(xa, convg, scale, shift, out=guard.slice(1, cout))
+        assert rel(back(yv), pre) < 1e-2
+        full = guard.nchw().float()
+        assert torch.all(full[:, 0] == 7.0) and torch.all(full[:, cout + 1:] == 7.0)
+
+
 @pytest.mark.parametrize("case", [(64, 64, 9, 11), (64, 64, 16, 8), (256, 64, 10, 12), (1024, 256, 6, 9), (128, 64, 1, 1)])
 def test_upsample2x_conv3x3_fused(E, case):
     """PSPUpsample's bilinear 2x + 3x3 conv in one kernel (the upsampled tensor only ever exists as shared-memory halo
@@ -166,7 +217,7 @@ def test_upsample2x_conv3x3_fused(E, case):
     assert rel(back(y), back(y2)) < 1e-5
 
 
-@pytest.mark.parametrize("case", [(64, 13, 16, 8), (64, 13, 21, 30), (128, 16, 9, 11), (64, 1, 5, 3)])
+@pytest.mark.parametrize("case", [(64, 13, 16, 8), (64, 13, 21, 30), (128, 16, 9, 11), (64, 1, 5, 3), (64, 13, 80, 72)])
 def test_conv3x3_bn_prelu_classifier_fused(E, case):
     """up_3.conv -> BN(eval) -> PReLU -> final 1x1 (cm/models/pspnet.py:72-75) in one kernel: NCHW FP32 logits equal
     conv -> BN -> PReLU -> 1x1 conv of the oracle on the BF16-rounded operands (the classifier is a second tcgen05 MMA on
