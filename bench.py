@@ -728,11 +728,16 @@ def main():
     l0 = E.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    prof_range = bool(os.environ.get("HN_PROFILE_RANGE"))      # `ncu --profile-from-start off`: only the timed steps are profiled
+    if prof_range:
+        torch.cuda.profiler.start()
     ev0.record()
     for _ in range(args.steps):
         out = step()
     ev1.record()
     barrier()
+    if prof_range:
+        torch.cuda.profiler.stop()
     ms = ev0.elapsed_time(ev1)
     launches = E.launch_count - l0
     clocks = sampler.stop() if sampler else None
