@@ -245,25 +245,44 @@ __global__ void __launch_bounds__(256) im2col_bf16_kernel(const __nv_bfloat16 *_
 // that 64 consecutive output pixels of one output row need in shared memory (coalesced, zero padded), then assembles the
 // K-major rows from shared memory and writes them as 16-byte chunks.  grid = (ceil(Wo/64), N*Ho).
 constexpr int IM2COL_TW = 64;
+// `pitch` = elements per staged pixel: ldx when the input's pixel stride is C itself or a power of two (the run of pixels a patch row
+// needs is then copied without a division per element), else C (compacted, general strides).
 __global__ void __launch_bounds__(256) im2col_smallc_kernel(const __nv_bfloat16 *__restrict__ x, int ldx, int N, int H, int W, int C, int Ho,
-                                                            int Wo, int R, int S, int stride, int pad, int dil, int kpad,
+                                                            int Wo, int R, int S, int stride, int pad, int dil, int kpad, int pitch,
                                                             __nv_bfloat16 *__restrict__ a)
 {
-    extern __shared__ __nv_bfloat16 patch[];   // [R][ncols][C]
+    extern __shared__ __nv_bfloat16 patch[];   // [R][ncols][pitch]
     const int row = blockIdx.y;
     const int n = row / Ho, ho = row - n * Ho;
     const int wo0 = blockIdx.x * IM2COL_TW;
     const int ncols = (IM2COL_TW - 1) * stride + (S - 1) * dil + 1;
     const int wi0 = wo0 * stride - pad;
     const __nv_bfloat16 *xin = x + (int64_t)n * H * W * ldx;
-    const int per_row = ncols * C;
-    for (int i = threadIdx.x; i < R * per_row; i += blockDim.x) {
-        const int r = i / per_row, rem = i - r * per_row;
-        const int col = rem / C, c = rem - col * C;
-        const int hi = ho * stride - pad + r * dil, wi = wi0 + col;
-        __nv_bfloat16 v = __float2bfloat16_rn(0.f);
-        if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = xin[((int64_t)hi * W + wi) * ldx + c];
-        patch[i] = v;
+    const int per_row = ncols * pitch;
+    const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+    if (pitch == ldx) {
+        // the pixels a patch row needs are one contiguous run of the input row: only its valid range [e_lo, e_hi) (columns left /
+        // right of the image are zero padding) and, for padded pixels, the channel index (a mask: pitch is a power of two) matter
+        const int e_lo = (wi0 < 0 ? -wi0 : 0) * pitch;
+        const int e_hi = (W - wi0 < ncols ? (W - wi0 > 0 ? W - wi0 : 0) : ncols) * pitch;
+        const bool dense = pitch == C;
+        for (int r = 0; r < R; ++r) {
+            const int hi = ho * stride - pad + r * dil;
+            const bool row_ok = hi >= 0 && hi < H;
+            const __nv_bfloat16 *src = xin + ((int64_t)hi * W + wi0) * ldx;
+            __nv_bfloat16 *dst = patch + r * per_row;
+            for (int e = threadIdx.x; e < per_row; e += blockDim.x)
+                dst[e] = (row_ok && e >= e_lo && e < e_hi && (dense || (e & (pitch - 1)) < C)) ? src[e] : zero;
+        }
+    } else {
+        for (int i = threadIdx.x; i < R * per_row; i += blockDim.x) {
+            const int r = i / per_row, rem = i - r * per_row;
+            const int col = rem / C, c = rem - col * C;
+            const int hi = ho * stride - pad + r * dil, wi = wi0 + col;
+            __nv_bfloat16 v = zero;
+            if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = xin[((int64_t)hi * W + wi) * ldx + c];
+            patch[i] = v;
+        }
     }
     __syncthreads();
     const int k8n = kpad / 8;
@@ -276,12 +295,18 @@ __global__ void __launch_bounds__(256) im2col_smallc_kernel(const __nv_bfloat16 
         __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(&out);
         int tap = k0 / C, c = k0 - tap * C;
         int r = tap / S, s = tap - r * S;
+        int idx = r * per_row + (pl * stride + s * dil) * pitch + c;     // walks (c, s, r) with increments only
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            if (k0 + j < K) o[j] = patch[(r * ncols + pl * stride + s * dil) * C + c];
+            if (k0 + j < K) o[j] = patch[idx];
+            ++idx;
             if (++c == C) {
                 c = 0;
-                if (++s == S) { s = 0; ++r; }
+                idx += dil * pitch - C;
+                if (++s == S) {
+                    s = 0;
+                    idx += per_row - S * dil * pitch;
+                }
             }
         }
         *reinterpret_cast<uint4 *>(arow + (int64_t)pl * kpad + k0) = out;
@@ -293,11 +318,13 @@ int im2col_bf16(const hn_tensor *x, const hn_conv *cv, int Ho, int Wo, int kpad,
     HN_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 127) == 0, "im2col: workspace must be 128-byte aligned");
     if (x->c < 8 || x->c % 8 != 0) {
         const int ncols = (IM2COL_TW - 1) * cv->stride + (cv->s - 1) * cv->dil + 1;
-        const size_t smem = (size_t)cv->r * ncols * x->c * 2;
+        const bool pow2 = (x->ld & (x->ld - 1)) == 0 && x->ld <= 64;
+        const int pitch = (x->ld == x->c || pow2) ? x->ld : x->c;
+        const size_t smem = (size_t)cv->r * ncols * pitch * 2;
         if (smem <= 48 * 1024 && (int64_t)x->n * Ho <= 65535) {
             dim3 grid((unsigned)cdiv(Wo, IM2COL_TW), (unsigned)(x->n * Ho));
             im2col_smallc_kernel<<<grid, 256, smem, st>>>((const __nv_bfloat16 *)x->ptr, x->ld, x->n, x->h, x->w, x->c, Ho, Wo, cv->r, cv->s,
-                                                       cv->stride, cv->pad, cv->dil, kpad, (__nv_bfloat16 *)ws);
+                                                       cv->stride, cv->pad, cv->dil, kpad, pitch, (__nv_bfloat16 *)ws);
             HN_LAUNCH_CHECK();
             return HN_OK;
         }
@@ -472,12 +499,125 @@ static int launch_tc_bn(int bn, bool pair, const CUtensorMap &ta, const CUtensor
     return HN_ERR_ARG;
 }
 
+// ------------------------------------------------------------------------------------------------ 1x1 with a handful of input channels
+// y[p][co] = act(sum_c x[p][c] * w[co][c] * scale[co] + shift[co] + res[p][co]) for Cin <= 16 (the dgrad of the 13-class classifier:
+// 13 -> 64 channels at full resolution).  Padding K to a 64-wide k-block costs an im2col pass that writes and re-reads 5x the
+// output; at 13 MACs per output this is bandwidth-bound CUDA-core work instead: a thread owns 8 output channels of one pixel,
+// the (scaled, transposed) FP32 filter sits in shared memory.
+template <typename OutT>
+__global__ void __launch_bounds__(256) conv1x1_smallk_kernel(const __nv_bfloat16 *__restrict__ x, int ldx, int C, int64_t M,
+                                                             const __nv_bfloat16 *__restrict__ w, int kpad, int cout,
+                                                             const float *__restrict__ scale, const float *__restrict__ shift,
+                                                             const __nv_bfloat16 *__restrict__ res, int ldr, int act, float slope,
+                                                             const float *__restrict__ slope_ptr, OutT *__restrict__ y, int ldy)
+{
+    extern __shared__ float wsm[];                     // [C][cout8] filter, then [cout8] shift
+    const int cout8 = (cout + 7) & ~7, chunks = cout8 >> 3;
+    float *shs = wsm + C * cout8;
+    for (int i = threadIdx.x; i < C * cout8; i += blockDim.x) {
+        const int c = i / cout8, co = i - c * cout8;
+        wsm[i] = co < cout ? __bfloat162float(w[(int64_t)co * kpad + c]) * (scale ? __ldg(scale + co) : 1.f) : 0.f;
+    }
+    for (int i = threadIdx.x; i < cout8; i += blockDim.x) shs[i] = (shift && i < cout) ? __ldg(shift + i) : 0.f;
+    __syncthreads();
+    if (slope_ptr) slope = __ldg(slope_ptr);
+    const bool xvec = (ldx & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    const bool yvec = (ldy * sizeof(OutT)) % 16 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+    const bool rvec = res && (ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(res) & 15) == 0;
+    const int64_t items = M * chunks;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pix = idx / chunks;
+        const int co0 = (int)(idx - pix * chunks) * 8;
+        float xv[16];
+        const __nv_bfloat16 *xp = x + pix * ldx;
+        if (xvec) {           // 16-byte loads may run past C inside the pixel's own stride (ldx >= 8 * ceil(C / 8)); the tail is not used
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                if (v * 8 < C) {
+                    float f8[8];
+                    Vec8<__nv_bfloat16>::load(xp + v * 8, f8);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) xv[v * 8 + j] = f8[j];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) xv[c] = c < C ? __bfloat162float(xp[c]) : 0.f;
+        }
+        float acc[8];
+        {
+            const float4 s0 = *reinterpret_cast<const float4 *>(shs + co0), s1 = *reinterpret_cast<const float4 *>(shs + co0 + 4);
+            acc[0] = s0.x; acc[1] = s0.y; acc[2] = s0.z; acc[3] = s0.w; acc[4] = s1.x; acc[5] = s1.y; acc[6] = s1.z; acc[7] = s1.w;
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            if (c < C) {
+                const float4 w0 = *reinterpret_cast<const float4 *>(wsm + c * cout8 + co0), w1 = *reinterpret_cast<const float4 *>(wsm + c * cout8 + co0 + 4);
+                acc[0] = fmaf(xv[c], w0.x, acc[0]); acc[1] = fmaf(xv[c], w0.y, acc[1]); acc[2] = fmaf(xv[c], w0.z, acc[2]); acc[3] = fmaf(xv[c], w0.w, acc[3]);
+                acc[4] = fmaf(xv[c], w1.x, acc[4]); acc[5] = fmaf(xv[c], w1.y, acc[5]); acc[6] = fmaf(xv[c], w1.z, acc[6]); acc[7] = fmaf(xv[c], w1.w, acc[7]);
+            }
+        }
+        const bool full = co0 + 8 <= cout;
+        if (res) {
+            const __nv_bfloat16 *rp = res + pix * ldr + co0;
+            if (rvec && full) {
+                float r8[8];
+                Vec8<__nv_bfloat16>::load(rp, r8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += r8[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (co0 + j < cout) acc[j] += __bfloat162float(rp[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = apply_act(acc[j], act, slope);
+        OutT *yp = y + pix * ldy + co0;
+        if (yvec && full) Vec8<OutT>::store(yp, acc);
+        else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (co0 + j < cout) yp[j] = from_f32<OutT>(acc[j]);
+        }
+    }
+}
+
+static bool smallk_ok(const hn_tensor *x, const hn_conv *cv, const hn_epilogue *ep)
+{
+    static const bool disabled = getenv("HN_NO_SMALLK") != nullptr;
+    return !disabled && cv->r == 1 && cv->s == 1 && cv->stride == 1 && cv->pad == 0 && x->c <= 16 && cv->cout <= 1024 && !ep->stat_sum;
+}
+
+static int conv1x1_smallk(const hn_tensor *x, const void *w, const hn_conv *cv, const hn_epilogue *ep, const hn_tensor *y, cudaStream_t st)
+{
+    const int64_t M = (int64_t)x->n * x->h * x->w;
+    const int kpad = hn_conv_kpad(x->c, 1, 1);
+    const int cout8 = (cv->cout + 7) & ~7;
+    const size_t smem = (size_t)(x->c + 1) * cout8 * 4;
+    const int64_t items = M * (cout8 / 8);
+    int64_t blocks = cdiv(items, 256);
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    const __nv_bfloat16 *xp = (const __nv_bfloat16 *)x->ptr, *wp = (const __nv_bfloat16 *)w, *rp = (const __nv_bfloat16 *)ep->residual;
+    if (y->dtype == HN_F32)
+        conv1x1_smallk_kernel<float><<<(unsigned)blocks, 256, smem, st>>>(xp, x->ld, x->c, M, wp, kpad, cv->cout, ep->scale, ep->shift, rp, ep->residual_ld,
+                                                                          ep->act, ep->slope, ep->slope_ptr, (float *)y->ptr, y->ld);
+    else
+        conv1x1_smallk_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, smem, st>>>(xp, x->ld, x->c, M, wp, kpad, cv->cout, ep->scale, ep->shift, rp,
+                                                                                  ep->residual_ld, ep->act, ep->slope, ep->slope_ptr,
+                                                                                  (__nv_bfloat16 *)y->ptr, y->ld);
+    HN_LAUNCH_CHECK();
+    return HN_OK;
+}
+
 int conv2d_fwd_tc(const hn_tensor *x, const void *w, const hn_conv *cv, const hn_epilogue *ep, const hn_tensor *y, void *ws,
                   int64_t ws_bytes, cudaStream_t st)
 {
     const int Ho = y->h, Wo = y->w;
     const int64_t M = (int64_t)x->n * Ho * Wo;
     if (M == 0) return HN_OK;
+    if (smallk_ok(x, cv, ep)) return conv1x1_smallk(x, w, cv, ep, y, st);
     if (conv_halo_ok(x, cv, y, false)) return conv2d_fwd_halo(x, w, cv, ep, y, false, st);   // 3x3 with narrow outputs: one halo patch per k-block
     const int kpad = hn_conv_kpad(x->c, cv->r, cv->s);
     const int cout_pad = hn_conv_cout_pad(cv->cout, HN_BF16);

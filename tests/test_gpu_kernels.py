@@ -68,6 +68,9 @@ CONV_CASES = [
     (512, 1, 4, 2, 1, 1, 4, 6, True),         # critic classifier
     (256, 512, 4, 2, 1, 1, 40, 80, True),     # critic conv4 class at a realistic size: strided tensor map, several pixel tiles
     (64, 128, 4, 2, 1, 1, 33, 47, True),      # odd input, ragged output tiles
+    (13, 64, 1, 1, 0, 1, 16, 24, True),       # Cin <= 16 1x1 (the classifier's dgrad shape): CUDA-core small-K kernel, padded pixel stride
+    (3, 100, 1, 1, 0, 1, 9, 11, True),        # small-K kernel, dense 3-channel pixels, Cout not a multiple of 8
+    (16, 520, 1, 1, 0, 1, 5, 7, False),       # small-K kernel, Cin = 16, many output chunks
 ]
 
 
