@@ -1064,6 +1064,64 @@ def dropout2d(x: Act, p: float, mask: Optional[torch.Tensor] = None) -> Act:
 
 
 # -------------------------------------------------------------------------------------------------- backward ops
+def record_projected_bottleneck(tape: Tape, feats: Act, priors: Sequence[Act], y: Act, bott: torch.nn.Conv2d):
+    """Backward of the PSP bottleneck in its projected form (pspnet.PSPModule._run_projected_train):
+        y = relu(W_f feats + b + sum_s up(W_s prior_s)),   W = [W_0 | ... | W_{S-1} | W_f] the column blocks of bott.weight.
+    One closure for the whole block, because the five column blocks of dW share one gradient sink:
+        dz = dy * (y > 0);  db = sum dz;  dW_f = dz^T feats,  dfeats += W_f^T dz;
+        dproj_s = up^T(dz)  (the adjoint of the bilinear upsample, [N, s, s, Cout]);  dW_s = dproj_s^T prior_s,  dprior_s = W_s^T dproj_s."""
+    import types
+    f = feats.c
+    S = len(priors)
+    cout = bott.out_channels
+    live = tape.needs(feats) or any(tape.needs(q) for q in priors) or _wants(bott.weight) or _wants(bott.bias)
+    if not live:
+        return
+    tape.require(y)
+    block = types.SimpleNamespace(out_channels=cout, in_channels=f, kernel_size=(1, 1), stride=(1, 1), padding=(0, 0), dilation=(1, 1))
+
+    def backward(grads: Grads):
+        dout = grads.get(y)
+        if dout is None:
+            return
+        dz = act_bwd(dout, y, ACT_RELU)
+        if _wants(bott.bias):
+            dst, acc = grads.param_sink(bott.bias)
+            vec_to_grad(channel_sums(dz)[0], cout, out=dst, accumulate=acc)
+            grads.param_done(bott.bias)
+        wsink, wacc = (None, False)
+        if _wants(bott.weight):
+            wsink, wacc = grads.param_sink(bott.weight)
+            wsink = wsink.view(cout, (S + 1) * f)
+
+        def block_backward(x: Act, g: Act, i: int):
+            if wsink is not None:
+                dw = conv2d_wgrad(x, g, block)                           # [cout, f, 1, 1]
+                col = wsink[:, i * f:(i + 1) * f]
+                col.add_(dw.view(cout, f)) if wacc else col.copy_(dw.view(cout, f))
+                _count()
+            if tape.needs(x):
+                segs = grads.segments(x) if i == S else None
+                if segs is not None:
+                    for sub, inited in segs:
+                        a = sub.coff - x.coff
+                        conv2d_dgrad(g, bott, x.h, x.w, out=sub, accumulate=inited, cin_range=(i * f + a, i * f + a + sub.c))
+                else:
+                    gx, inited = grads.target(x)
+                    conv2d_dgrad(g, bott, x.h, x.w, out=gx, accumulate=inited, cin_range=(i * f, (i + 1) * f))
+                grads.mark(x)
+
+        for i, q in enumerate(priors):
+            dproj = new_act(q.n, q.h, q.w, cout, dz.dtype, dz.buf.device)
+            bilinear_bwd(dz, dproj, False)
+            block_backward(q, dproj, i)
+        block_backward(feats, dz, S)
+        if wsink is not None:
+            grads.param_done(bott.weight)
+
+    tape.record(backward)
+
+
 def packed_weight_dgrad(conv: torch.nn.Conv2d, dtype: torch.dtype) -> torch.Tensor:
     """Pack for dgrad-as-forward-conv: [cin_pad][kpad'], k' = ((R-1-r)*S + (S-1-s))*Cout + o (flipped taps, in/out
     channels swapped), cached like the forward pack."""

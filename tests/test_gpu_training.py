@@ -308,3 +308,71 @@ def test_paired_forward_equals_two_consecutive_calls(phase, monkeypatch):
             assert int(ss[k]) == int(sp[k]) == 2, k                    # two forward calls' worth of updates, in order
         elif "running_" in k:
             assert rel(sp[k].cpu(), ss[k].cpu()) < 2e-3, k
+
+
+def test_projected_psp_bottleneck_trains_like_the_concat_formulation(monkeypatch):
+    """BF16 training runs the PSP bottleneck as W_f x5 + b + sum_s up(W_s prior_s) with one hand-written backward
+    (engine.record_projected_bottleneck) instead of the 10240-channel concat of cm/models/pspnet.py:21-24.  The block alone, driven
+    through the tape with the SAME incoming gradient for both formulations (inside the full step the two forward results differ in
+    the last BF16 bit and the train-mode BatchNorm layers downstream turn that into O(10 %) gradient noise -- the whole-step accuracy
+    is bounded against the FP32 oracle in test_gpu_bf16_training.py): output, input gradient, and every parameter gradient --
+    bottleneck.weight's five column blocks come from five weight-gradient GEMMs into one sink -- against the literal formulation
+    AND against torch autograd of the reference module in FP64 on the BF16-rounded operands."""
+    from heatnet_pub_b200 import engine as E, pspnet
+    g = torch.Generator().manual_seed(5)
+    N, H, W, Cf, Co = 3, 20, 24, 256, 128
+    ref = nn.Module()
+    ref.stages = nn.ModuleList([nn.Sequential(nn.AdaptiveAvgPool2d((s, s)), nn.Conv2d(Cf, Cf, 1, bias=False)) for s in (1, 2, 3, 6)])
+    ref.bottleneck = nn.Conv2d(Cf * 5, Co, 1)
+    x = torch.randn(N, Cf, H, W, generator=g)
+    dout = torch.randn(N, Co, H, W, generator=g)
+
+    def run(projected):
+        monkeypatch.setattr(pspnet, "PSP_PROJECTED_TRAIN", projected)
+        m = pspnet.PSPModule(Cf, Co).cuda().train()
+        m.precision = "bf16"
+        m.load_state_dict(ref.state_dict())
+        tape = E.Tape()
+        E.current_tape = tape
+        try:
+            if projected:
+                feats = E.from_nchw(x.cuda(), torch.bfloat16)
+                tape.require(feats)
+                y = m._run(feats)
+            else:           # the literal formulation reads the features from their channel slice of the concat buffer
+                cat = m.alloc_cat(N, H, W, torch.bfloat16, "cuda")
+                feats = E.from_nchw(x.cuda(), torch.bfloat16, m.feats_slice(cat))
+                tape.require(feats)
+                y = m._run_cat(cat)
+        finally:
+            E.current_tape = None
+        grads = E.Grads()
+        gy, _ = grads.target(y)
+        E.from_nchw(dout.cuda(), torch.bfloat16, gy)
+        grads.mark(y)
+        tape.backward(grads)
+        pg = {k: grads.params[p].float().cpu().clone() for k, p in m.named_parameters()}
+        return y.nchw().float().cpu(), grads.get(feats).nchw().float().cpu(), pg
+
+    yc, dxc, gc = run(False)
+    yp, dxp, gp = run(True)
+    # FP64 autograd of the reference module on BF16-rounded operands
+    r64 = ref.double()
+    with torch.no_grad():
+        for p in r64.parameters():
+            p.copy_(p.float().bfloat16().double())
+    xr = x.bfloat16().double().requires_grad_(True)
+    priors = [F.interpolate(st(xr), size=(H, W), mode="bilinear", align_corners=False) for st in r64.stages]
+    yr = F.relu(r64.bottleneck(torch.cat(priors + [xr], 1)))
+    yr.backward(dout.bfloat16().double())
+    gr = {k: p.grad.float() for k, p in r64.named_parameters()}
+    assert rel(yp, yr.detach().float()) < 2e-2 and rel(yc, yr.detach().float()) < 2e-2
+    errs = {"dx": (rel_l2(dxp, xr.grad.float()), rel_l2(dxc, xr.grad.float()))}
+    for k in gr:
+        assert gp[k].shape == gr[k].shape, k
+        errs[k] = (rel_l2(gp[k], gr[k]), rel_l2(gc[k], gr[k]))
+    print("rel-L2 error vs FP64 autograd (projected, concat):", {k: (round(a, 4), round(b, 4)) for k, (a, b) in errs.items()})
+    for k, (a, b) in errs.items():
+        assert a < max(1.5e-2, 1.5 * b), (k, a, b)          # as accurate as the literal formulation on the same engine
+    blocks = gp["bottleneck.weight"].view(Co, 5, Cf)
+    assert all(blocks[:, i].abs().max() > 0 for i in range(5))
