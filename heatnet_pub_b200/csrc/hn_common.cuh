@@ -30,15 +30,24 @@ void set_error(const char *fmt, ...);
 
 #define HN_LAUNCH_CHECK() HN_CUDA(cudaGetLastError())
 
+// Per-device host state (cudaFuncSetAttribute is per device, and so are SM counts): one process may drive several GPUs
+// (torch.nn.DataParallel-style callers), so nothing device-dependent is cached in a plain static.
+constexpr int HN_MAX_DEVICES = 64;
+inline int current_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= HN_MAX_DEVICES) dev = 0;
+    return dev;
+}
+
 inline int num_sms()
 {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-            n = 148;
+    static int n[HN_MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (n[dev] == 0) {
+        if (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n[dev] = 148;
     }
-    return n;
+    return n[dev];
 }
 
 inline size_t elsize(int dtype) { return dtype == HN_BF16 ? 2 : 4; }

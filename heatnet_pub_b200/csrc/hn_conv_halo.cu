@@ -362,8 +362,10 @@ template <int BN, bool UP, bool PAIR = false>
 static int launch_halo(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &ty, const CUtensorMap &tr, const HaloParams &hp,
                        size_t smem, int num_m_tiles, cudaStream_t st)
 {
-    static bool configured = false;
-    static int pairs = 0;
+    static bool configured_dev[HN_MAX_DEVICES] = {};
+    static int pairs_dev[HN_MAX_DEVICES] = {};
+    bool &configured = configured_dev[current_device()];
+    int &pairs = pairs_dev[current_device()];
     if (!configured) {
         HN_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, UP, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
         if (PAIR) {

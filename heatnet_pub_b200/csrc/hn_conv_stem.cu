@@ -202,7 +202,8 @@ int conv_stem_dense(const hn_tensor *xpad, const void *w, int cout, const hn_epi
     constexpr size_t smem = ST_B_BYTES + ((ST_STAGES * ST_STAGE_BYTES + 1023) / 1024) * 1024 + NUM_EPI_WARPS * EPI_STAGE_BYTES +
                             (2 * ST_STAGES + 4 + NUM_EPI_WARPS) * 8 + 16 + 2 * 64 * 4 + 1024;
     static_assert(smem <= 227 * 1024, "stem kernel shared memory");
-    static bool configured = false;
+    static bool configured_dev[HN_MAX_DEVICES] = {};
+    bool &configured = configured_dev[current_device()];
     if (!configured) {
         HN_CUDA(cudaFuncSetAttribute(conv_stem_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;

@@ -446,8 +446,10 @@ static int launch_tc(const CUtensorMap &ta, const CUtensorMap &tb, const CUtenso
     constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BK * 2 + (PAIR ? BN / 2 : BN) * BK * 2) + NUM_EPI_WARPS * EPI_STAGE_BYTES +
                             (2 * STAGES + 4 + NUM_EPI_WARPS) * 8 + 16 + (BN < 128 ? 2 : 1) * BN * 4 + 1024;   // narrow tiles: one shift table per epilogue group
     static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
-    static bool configured = false;
-    static int pairs = 0;
+    static bool configured_dev[HN_MAX_DEVICES] = {};
+    static int pairs_dev[HN_MAX_DEVICES] = {};
+    bool &configured = configured_dev[current_device()];
+    int &pairs = pairs_dev[current_device()];
     if (!configured) {
         HN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, BK, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (PAIR) pairs = max_pairs(conv_tc_kernel<BN, STAGES, BK, PAIR>, smem, NUM_THREADS);

@@ -234,7 +234,8 @@ static int launch_wgrad(const CUtensorMap &tdy, const CUtensorMap &tx, const WgP
 {
     constexpr size_t smem = (size_t)STAGES * (2 + BN / 64) * WG_BLOCK_BYTES + (2 * STAGES + 4) * 8 + 16 + 4 * 32 * 36 * 4 + 1024;
     static_assert(smem <= 227 * 1024, "wgrad shared memory");
-    static bool configured = false;
+    static bool configured_dev[HN_MAX_DEVICES] = {};
+    bool &configured = configured_dev[current_device()];
     if (!configured) {
         HN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
