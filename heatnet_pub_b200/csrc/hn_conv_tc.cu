@@ -526,10 +526,16 @@ __global__ void __launch_bounds__(256) conv1x1_smallk_kernel(const __nv_bfloat16
     const bool xvec = (ldx & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     const bool yvec = (ldy * sizeof(OutT)) % 16 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
     const bool rvec = res && (ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(res) & 15) == 0;
-    const int64_t items = M * chunks;
+    // a WARP owns 32 consecutive pixels x one chunk of 8 output channels: every filter read is a shared-memory broadcast (with the
+    // chunk index varying inside the warp the 128-bit reads were 2-way bank-conflicted and the kernel LSU-bound: 1.37 ms instead
+    // of 0.3 for the classifier's dgrad)
+    const int64_t pix_groups = (M + 31) >> 5;
+    const int64_t items = pix_groups * chunks * 32;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t pix = idx / chunks;
-        const int co0 = (int)(idx - pix * chunks) * 8;
+        const int64_t wg = idx >> 5;
+        const int64_t pix = (wg / chunks) * 32 + (idx & 31);
+        const int co0 = (int)(wg % chunks) * 8;
+        if (pix >= M) continue;
         float xv[16];
         const __nv_bfloat16 *xp = x + pix * ldx;
         if (xvec) {           // 16-byte loads may run past C inside the pixel's own stride (ldx >= 8 * ceil(C / 8)); the tail is not used
@@ -597,7 +603,7 @@ static int conv1x1_smallk(const hn_tensor *x, const void *w, const hn_conv *cv, 
     const int kpad = hn_conv_kpad(x->c, 1, 1);
     const int cout8 = (cv->cout + 7) & ~7;
     const size_t smem = (size_t)(x->c + 1) * cout8 * 4;
-    const int64_t items = M * (cout8 / 8);
+    const int64_t items = cdiv(M, 32) * 32 * (cout8 / 8);
     int64_t blocks = cdiv(items, 256);
     const int64_t cap = (int64_t)num_sms() * 8;
     if (blocks > cap) blocks = cap;

@@ -704,6 +704,11 @@ def batchnorm_train_affine(x: Act, bn: torch.nn.BatchNorm2d):
 
 
 BN_FUSED_STATS = os.environ.get("HN_NO_FUSED_BN_STATS") is None
+# Per-layer placement of the train-mode BatchNorm statistics on the BF16 engine: convolutions with fewer k-blocks than this leave
+# them to a separate pass over the stored tensor (hn_channel_stats, one launch per statistics group) instead of the epilogue --
+# their tiles are a handful of MMAs, the epilogue is the bound, and the statistics code roughly doubles it (measured: train_seg 62.96 ms at 0 = always
+# the epilogue, 62.5 at 9, 62.2 at 17 = every 1x1 up to 1024 input channels and the 64-channel 3x3s; beyond that within run-to-run noise).
+STATS_EPILOGUE_MIN_KB = int(os.environ.get("HN_STATS_EPILOGUE_MIN_KB", "17"))
 _stats_chunk = {}          # device index -> [zeroed FP64 chunk, next free element]: one memset serves ~30 BN layers
 
 
@@ -839,7 +844,17 @@ def conv_bn_act(x: Act, conv, bn, act=ACT_NONE, slope=0.0, slope_ptr=None, resid
         wp, shift = packed_stem_weight(conv, None)
         raw = stem_conv(x, conv, wp, shift, out_dtype=torch.float32 if raw_fp32 else None, stats=sums, stat_groups=G)
     else:
-        raw = conv2d(x, conv, scale, shift, None, ACT_NONE, out_dtype=torch.float32 if raw_fp32 else None, stats=sums, stat_groups=G)
+        kblocks = conv.kernel_size[0] * conv.kernel_size[1] * ((conv.in_channels + 63) // 64)
+        in_epilogue = (not fused) or kblocks >= STATS_EPILOGUE_MIN_KB or conv.out_channels % 8 != 0
+        raw = conv2d(x, conv, scale, shift, None, ACT_NONE, out_dtype=torch.float32 if raw_fp32 else None, stats=sums if in_epilogue else None,
+                     stat_groups=G)
+        if fused and not in_epilogue:        # the same [2][G][C] FP64 sums, from a pass over the stored tensor, one group at a time
+            lib = _lib.load()
+            ng, cch = raw.n // G, conv.out_channels
+            for g in range(G):
+                sub = Act(raw.buf[g * ng:(g + 1) * ng], raw.c, raw.coff)
+                _lib.check(lib.hn_channel_stats(C.byref(sub.hn()), sums[0, g * cch:].data_ptr(), sums[1, g * cch:].data_ptr(), _stream()))
+                _count(3)
     if out is None:
         in_place = raw.dtype == x.dtype and tape is None
         out = raw if in_place else new_act(raw.n, raw.h, raw.w, raw.c, x.dtype, x.buf.device)
