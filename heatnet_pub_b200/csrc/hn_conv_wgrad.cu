@@ -11,6 +11,7 @@
 // Strided / small-Cin convolutions run the same kernel in flat mode on the im2col workspace (K columns = taps*Cin).
 //
 // FP32 path: CUDA-core implicit GEMM with the same decomposition (parity mode).
+#include <stdlib.h>
 #include <string.h>
 
 #include "hn_common.cuh"
@@ -38,12 +39,17 @@ struct WgParams {
     float *dw;                      // [Cout_pad][kpad] FP32, accumulated into
 };
 
-template <int BN, int STAGES>
+// PAIR: two CTAs of a cluster take two adjacent Cout tiles of the same (column item, pixel split) and run ONE M = 256 instruction
+// stream (hn_tc_ptx.cuh, "CTA pairs"): each stages its own dY tile and HALF of the X blocks (every item has an even block count),
+// so an SM moves 32 KB instead of 48 KB per k-block from L2 into shared memory and the ring is 6 deep instead of 4.
+template <int BN, int STAGES, bool PAIR = false>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x, const WgParams p)
 {
     constexpr int A_BYTES = 2 * WG_BLOCK_BYTES;              // 128 couts = 2 blocks
-    constexpr int B_BYTES = (BN / 64) * WG_BLOCK_BYTES;
+    constexpr int B_BLOCKS = PAIR ? BN / 128 : BN / 64;       // X blocks staged by this CTA
+    constexpr int B_BYTES = B_BLOCKS * WG_BLOCK_BYTES;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int ACC_COLS = BN < 32 ? 32 : BN;
     constexpr int TMEM_COLS = 2 * ACC_COLS;          // two accumulators: the epilogue (red.global.add) of item i overlaps the main loop of item i+1
@@ -57,7 +63,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = p.n_img * p.tiles_h * p.tiles_w;
-    const int num_items = p.m_tiles * p.n_col_items * p.splits;
+    const int m_units = PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles;          // Cout tiles, or pairs of them (an odd count leaves a filler
+                                                                         // tile beyond Cout: its dY loads are zero-filled, its rows masked)
+    const int num_items = m_units * p.n_col_items * p.splits;
+    const int item0 = PAIR ? blockIdx.x >> 1 : blockIdx.x, item_step = PAIR ? gridDim.x >> 1 : gridDim.x;   // both CTAs of a pair walk the same items
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_dy);
@@ -70,16 +79,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(tfull_bar + i), 1);
-            mbar_init(smem_u32(tempty_bar + i), 4);
+            mbar_init(smem_u32(tempty_bar + i), PAIR ? 8 : 4);
         }
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
-        tmem_relinquish();
+        if constexpr (PAIR) { tmem_alloc_pair(smem_u32(tmem_slot), TMEM_COLS); tmem_relinquish_pair(); }
+        else { tmem_alloc(smem_u32(tmem_slot), TMEM_COLS); tmem_relinquish(); }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();
+    else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -93,6 +103,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
         const int rest = item / p.splits;
         const int ci = rest % p.n_col_items;
         mt = rest / p.n_col_items;
+        if (PAIR) mt = 2 * mt + (int)rank;
         blk0 = ci * p.nb_item;
         nb = p.blocks_total - blk0 < p.nb_item ? p.blocks_total - blk0 : p.nb_item;
         const int per = (num_kb + p.splits - 1) / p.splits;
@@ -104,7 +115,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
         {   // whole warp runs the loop, the elected lane issues (see elect_one)
             int stage = 0;
             uint32_t phase = 0;
-            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            for (int item = item0; item < num_items; item += item_step) {
                 int mt, blk0, nb, kb0, kb1;
                 decode(item, mt, blk0, nb, kb0, kb1);
                 int bcol[BN / 64], bdx[BN / 64], bdy[BN / 64];      // per block: channel offset and tap shift
@@ -123,28 +134,45 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
                     const uint32_t fb = smem_u32(full_bar + stage);
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                     if (elect_one()) {
-                        mbar_expect_tx(fb, (2 + nb) * WG_BLOCK_BYTES);
+                        if constexpr (PAIR) {
+                            // this CTA's dY tile and its half of the X blocks [rank * nb/2, +nb/2), counted on the leader's barrier
+                            const uint32_t lfb = mapa_u32(fb, 0);
+                            const int hb = nb >> 1;
+                            if (rank == 0) mbar_expect_tx(fb, 2 * (2 + hb) * WG_BLOCK_BYTES);
 #pragma unroll
-                        for (int b = 0; b < 2; ++b)
-                            tma_load_4d(sa + b * WG_BLOCK_BYTES, &tmap_dy, fb, mt * WG_M + b * 64, tw * p.TW, th * p.TH, img);
+                            for (int b = 0; b < 2; ++b)
+                                tma_load_4d_pair(sa + b * WG_BLOCK_BYTES, &tmap_dy, lfb, mt * WG_M + b * 64, tw * p.TW, th * p.TH, img);
 #pragma unroll
-                        for (int b = 0; b < BN / 64; ++b)
-                            if (b < nb) tma_load_4d(sa + A_BYTES + b * WG_BLOCK_BYTES, &tmap_x, fb, bcol[b], tw * p.TW * p.stride + bdx[b], th * p.TH * p.stride + bdy[b], img);
+                            for (int b = 0; b < B_BLOCKS; ++b)
+                                if (b < hb) {
+                                    const int g = (int)rank * hb + b;
+                                    tma_load_4d_pair(sa + A_BYTES + b * WG_BLOCK_BYTES, &tmap_x, lfb, bcol[g], tw * p.TW * p.stride + bdx[g],
+                                                     th * p.TH * p.stride + bdy[g], img);
+                                }
+                        } else {
+                            mbar_expect_tx(fb, (2 + nb) * WG_BLOCK_BYTES);
+#pragma unroll
+                            for (int b = 0; b < 2; ++b)
+                                tma_load_4d(sa + b * WG_BLOCK_BYTES, &tmap_dy, fb, mt * WG_M + b * 64, tw * p.TW, th * p.TH, img);
+#pragma unroll
+                            for (int b = 0; b < BN / 64; ++b)
+                                if (b < nb) tma_load_4d(sa + A_BYTES + b * WG_BLOCK_BYTES, &tmap_x, fb, bcol[b], tw * p.TW * p.stride + bdx[b], th * p.TH * p.stride + bdy[b], img);
+                        }
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 && rank == 0) {
         {
             int stage = 0;
             uint32_t phase = 0, acc_phase = 0;
             int acc = 0;
-            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            for (int item = item0; item < num_items; item += item_step) {
                 int mt, blk0, nb, kb0, kb1;
                 decode(item, mt, blk0, nb, kb0, kb1);
-                const uint32_t idesc = make_idesc_bf16_mn(WG_M, 64 * nb);
+                const uint32_t idesc = make_idesc_bf16_mn(PAIR ? 2 * WG_M : WG_M, 64 * nb);
                 mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
@@ -158,15 +186,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
 #pragma unroll
                         for (int k = 0; k < WG_KPIX / 16; ++k) {
                             // 16 pixel rows = 2048 B further along K: +128 in the (addr >> 4) field
-                            umma_bf16(d_tmem, adesc + 128 * k, bdesc + 128 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                            umma_bf16_t<PAIR>(d_tmem, adesc + 128 * k, bdesc + 128 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                         }
-                        umma_commit(smem_u32(empty_bar + stage));
-                        if (kb == kb1 - 1) umma_commit(smem_u32(tfull_bar + acc));
+                        umma_commit_t<PAIR>(smem_u32(empty_bar + stage));
+                        if (kb == kb1 - 1) umma_commit_t<PAIR>(smem_u32(tfull_bar + acc));
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (kb1 <= kb0 && elect_one()) umma_commit(smem_u32(tfull_bar + acc));     // empty split: nothing was issued
+                if (kb1 <= kb0 && elect_one()) umma_commit_t<PAIR>(smem_u32(tfull_bar + acc));     // empty split: nothing was issued
                 __syncwarp();
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
@@ -176,7 +204,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
         const int q = warp - 4;
         uint32_t acc_phase = 0;
         int acc = 0;
-        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        for (int item = item0; item < num_items; item += item_step) {
             int mt, blk0, nb, kb0, kb1;
             decode(item, mt, blk0, nb, kb0, kb1);
             mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
@@ -216,33 +244,62 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+            if (lane == 0) {
+                if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(tempty_bar + acc), 0));
+                else mbar_arrive(smem_u32(tempty_bar + acc));
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();
+    else __syncthreads();
     if (warp == 2) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if constexpr (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR = false>
 static int launch_wgrad(const CUtensorMap &tdy, const CUtensorMap &tx, const WgParams &p, cudaStream_t st)
 {
-    constexpr size_t smem = (size_t)STAGES * (2 + BN / 64) * WG_BLOCK_BYTES + (2 * STAGES + 4) * 8 + 16 + 4 * 32 * 36 * 4 + 1024;
+    constexpr size_t smem = (size_t)STAGES * (2 + (PAIR ? BN / 128 : BN / 64)) * WG_BLOCK_BYTES + (2 * STAGES + 4) * 8 + 16 + 4 * 32 * 36 * 4 + 1024;
     static_assert(smem <= 227 * 1024, "wgrad shared memory");
     static bool configured_dev[HN_MAX_DEVICES] = {};
+    static int pairs_dev[HN_MAX_DEVICES] = {};
     bool &configured = configured_dev[current_device()];
+    int &pairs = pairs_dev[current_device()];
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(WG_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
     if (!configured) {
-        HN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HN_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN, STAGES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (PAIR) {
+            cfg.gridDim = dim3(2, 1, 1);
+            if (cudaOccupancyMaxActiveClusters(&pairs, wgrad_tc_kernel<BN, STAGES, PAIR>, &cfg) != cudaSuccess || pairs < 1) {
+                cudaGetLastError();
+                pairs = num_sms() / 2;
+            }
+        }
         configured = true;
     }
-    const int items = p.m_tiles * p.n_col_items * p.splits;
-    int grid = items < num_sms() ? items : num_sms();
-    wgrad_tc_kernel<BN, STAGES><<<grid, WG_THREADS, smem, st>>>(tdy, tx, p);
+    if constexpr (PAIR) {
+        const int items = ((p.m_tiles + 1) / 2) * p.n_col_items * p.splits;
+        cfg.gridDim = dim3(2 * (unsigned)(items < pairs ? items : pairs), 1, 1);
+        cfg.stream = st;
+        HN_CUDA(cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<BN, STAGES, PAIR>, tdy, tx, p));
+    } else {
+        const int items = p.m_tiles * p.n_col_items * p.splits;
+        int grid = items < num_sms() ? items : num_sms();
+        wgrad_tc_kernel<BN, STAGES, PAIR><<<grid, WG_THREADS, smem, st>>>(tdy, tx, p);
+    }
     HN_LAUNCH_CHECK();
     return HN_OK;
 }
@@ -320,14 +377,19 @@ int conv2d_wgrad_tc(const hn_tensor *x, const hn_tensor *dy, const hn_conv *cv, 
     p.nb_item = (int)cdiv(p.blocks_total, p.n_col_items);            // 1..4 blocks (N = 64..256) per item, evenly spread
     const int bn = p.nb_item >= 3 ? 256 : (p.nb_item == 2 ? 128 : 64);
     const int num_kb = p.n_img * p.tiles_h * p.tiles_w;
-    const int base_items = p.m_tiles * p.n_col_items;
-    int splits = (int)cdiv(2 * (int64_t)num_sms(), base_items);
+    // CTA pairs: wide items only (N = 256: four X blocks), every item with an even block count, at least two Cout tiles
+    static const bool no_pair = getenv("HN_NO_PAIR") != nullptr || getenv("HN_NO_PAIR_WGRAD") != nullptr;
+    const int last_nb = p.blocks_total - (p.n_col_items - 1) * p.nb_item;
+    const bool pair = !no_pair && bn == 256 && p.nb_item % 2 == 0 && last_nb % 2 == 0 && p.m_tiles >= 2;
+    const int base_items = (pair ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_col_items;
+    int splits = (int)cdiv((pair ? 1 : 2) * (int64_t)num_sms(), base_items);          // ~2 items per SM (a pair item occupies two)
     if (splits > num_kb) splits = num_kb;
     if (splits < 1) splits = 1;
     // make every split non-empty
     const int per = (int)cdiv(num_kb, splits);
     splits = (int)cdiv(num_kb, per);
     p.splits = splits;
+    if (pair) return launch_wgrad<256, 6, true>(tdy, tx, p, st);
     switch (bn) {
         case 256: return launch_wgrad<256, 4>(tdy, tx, p, st);
         case 128: return launch_wgrad<128, 6>(tdy, tx, p, st);

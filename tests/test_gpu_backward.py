@@ -53,6 +53,9 @@ GRAD_CASES = [
     (3, 64, 7, 2, 3, 1, 33, 40),         # RGB stem (wgrad only matters; dgrad checked too)
     (256, 512, 4, 2, 1, 1, 40, 80),      # stride-2 wgrad through the element-strided X map, several pixel blocks
     (64, 128, 4, 2, 1, 1, 33, 47),       # odd input, ragged blocks
+    (256, 384, 3, 1, 1, 1, 9, 11),       # wgrad on CTA pairs with an odd number of Cout tiles (filler tile beyond Cout)
+    (128, 256, 3, 1, 1, 1, 10, 12),      # wgrad on CTA pairs: 18 column blocks = four items of 4 and a last one of 2
+    (512, 320, 1, 1, 0, 1, 7, 9),        # wgrad on CTA pairs: Cout not a multiple of the 128-row tile
 ]
 
 
