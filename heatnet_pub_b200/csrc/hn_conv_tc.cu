@@ -32,7 +32,8 @@ constexpr int NUM_THREADS = 384;   // 4 control warps + 8 epilogue warps
 // ------------------------------------------------------------------------------------------------ kernel
 // PAIR: launched as clusters of two CTAs (hn_tc_ptx.cuh, "CTA pairs"): each CTA stages its own M tile and half of the Cout tile's
 // weight rows, the leader's MMA warp issues one M = 256 instruction for both and commits to the barriers of both.
-template <int BLOCK_N, int STAGES, int BK = BLOCK_K, bool PAIR = false>
+// RES2: a second set of epilogue staging tiles (hn_tc_epilogue.cuh), paid for with one operand stage in the single-CTA 256-wide form.
+template <int BLOCK_N, int STAGES, int BK = BLOCK_K, bool PAIR = false, bool RES2 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_r, const TcParams p)
@@ -49,11 +50,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *epi_stage = smem + STAGES * STAGE_BYTES;                       // NUM_EPI_WARPS x 4 KB, 1024-aligned
-    uint64_t *bars = reinterpret_cast<uint64_t *>(epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES);
+    constexpr int EPI_SETS = RES2 ? 2 : 1;                                  // staging tiles + residual barriers per epilogue warp
+    uint8_t *epi_stage = smem + STAGES * STAGE_BYTES;                       // EPI_SETS x NUM_EPI_WARPS x 4 KB, 1024-aligned
+    uint64_t *bars = reinterpret_cast<uint64_t *>(epi_stage + EPI_SETS * NUM_EPI_WARPS * EPI_STAGE_BYTES);
     uint64_t *full_bar = bars, *empty_bar = bars + STAGES, *tfull_bar = bars + 2 * STAGES, *tempty_bar = bars + 2 * STAGES + 2;
-    uint64_t *res_bar = bars + 2 * STAGES + 4;                              // one per epilogue warp
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4 + NUM_EPI_WARPS);
+    uint64_t *res_bar = bars + 2 * STAGES + 4;                              // EPI_SETS per epilogue warp
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4 + EPI_SETS * NUM_EPI_WARPS);
     float *s_shift = reinterpret_cast<float *>(tmem_slot + 4);                // epilogue shift table(s): BLOCK_N floats (x2 for BLOCK_N < 128)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,7 +78,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_init(smem_u32(tfull_bar + i), 1);
             mbar_init(smem_u32(tempty_bar + i), (BLOCK_N >= 128 ? 8 : 4) * (PAIR ? 2 : 1));   // one arrive per working epilogue warp (of both CTAs)
         }
-        for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(smem_u32(res_bar + i), 1);
+        for (int i = 0; i < EPI_SETS * NUM_EPI_WARPS; ++i) mbar_init(smem_u32(res_bar + i), 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -181,7 +183,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #endif
         }
     } else if (warp >= EPI_WARP0) {
-        conv_epilogue<BLOCK_N, false, 1, PAIR>(p, &tmap_y, &tmap_r, tmem_base, tfull_bar, tempty_bar, res_bar, epi_stage, s_shift, num_tiles, warp, lane);
+        conv_epilogue<BLOCK_N, false, 1, PAIR, 2, RES2>(p, &tmap_y, &tmap_r, tmem_base, tfull_bar, tempty_bar, res_bar, epi_stage, s_shift, num_tiles, warp, lane);
     }
 
     tcgen05_fence_before();
@@ -439,20 +441,21 @@ static int max_pairs(K kernel, size_t smem, int threads)
     return n;
 }
 
-template <int BN, int STAGES, int BK = BLOCK_K, bool PAIR = false>
+template <int BN, int STAGES, int BK = BLOCK_K, bool PAIR = false, bool RES2 = false>
 static int launch_tc(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &ty, const CUtensorMap &tr, const TcParams &p,
                      int num_m_tiles, cudaStream_t st)
 {
-    constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BK * 2 + (PAIR ? BN / 2 : BN) * BK * 2) + NUM_EPI_WARPS * EPI_STAGE_BYTES +
-                            (2 * STAGES + 4 + NUM_EPI_WARPS) * 8 + 16 + (BN < 128 ? 2 : 1) * BN * 4 + 1024;   // narrow tiles: one shift table per epilogue group
+    constexpr int EPI_SETS = RES2 ? 2 : 1;
+    constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BK * 2 + (PAIR ? BN / 2 : BN) * BK * 2) + EPI_SETS * NUM_EPI_WARPS * EPI_STAGE_BYTES +
+                            (2 * STAGES + 4 + EPI_SETS * NUM_EPI_WARPS) * 8 + 16 + (BN < 128 ? 2 : 1) * BN * 4 + 1024;   // narrow tiles: one shift table per epilogue group
     static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
     static bool configured_dev[HN_MAX_DEVICES] = {};
     static int pairs_dev[HN_MAX_DEVICES] = {};
     bool &configured = configured_dev[current_device()];
     int &pairs = pairs_dev[current_device()];
     if (!configured) {
-        HN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, BK, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (PAIR) pairs = max_pairs(conv_tc_kernel<BN, STAGES, BK, PAIR>, smem, NUM_THREADS);
+        HN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, BK, PAIR, RES2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (PAIR) pairs = max_pairs(conv_tc_kernel<BN, STAGES, BK, PAIR, RES2>, smem, NUM_THREADS);
         configured = true;
     }
     if constexpr (PAIR) {
@@ -467,11 +470,11 @@ static int launch_tc(const CUtensorMap &ta, const CUtensorMap &tb, const CUtenso
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        HN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, BK, PAIR>, ta, tb, ty, tr, p));
+        HN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, BK, PAIR, RES2>, ta, tb, ty, tr, p));
     } else {
         const int num_tiles = num_m_tiles * p.n_tiles;
         int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-        conv_tc_kernel<BN, STAGES, BK, PAIR><<<grid, NUM_THREADS, smem, st>>>(ta, tb, ty, tr, p);
+        conv_tc_kernel<BN, STAGES, BK, PAIR, RES2><<<grid, NUM_THREADS, smem, st>>>(ta, tb, ty, tr, p);
     }
     HN_LAUNCH_CHECK();
     return HN_OK;
@@ -490,7 +493,13 @@ static int launch_tc_bn(int bn, bool pair, const CUtensorMap &ta, const CUtensor
         }
     } else {
         switch (bn) {
-            case 256: return launch_tc<256, 4>(ta, tb, ty, tr, p, num_m_tiles, st);
+            case 256: {
+                // single-CTA 256-wide tiles are the short-reduction 1x1 layers (bound by HBM and the epilogue): one operand stage less,
+                // two staging tiles per epilogue warp (RES2).  HN_NO_RES2=1 keeps the 4-stage / one-tile form for A/B runs.
+                static const bool no_res2 = getenv("HN_NO_RES2") != nullptr;
+                if (no_res2) return launch_tc<256, 4>(ta, tb, ty, tr, p, num_m_tiles, st);
+                return launch_tc<256, 3, BLOCK_K, false, true>(ta, tb, ty, tr, p, num_m_tiles, st);
+            }
             case 128: return launch_tc<128, 6>(ta, tb, ty, tr, p, num_m_tiles, st);
             case 64: return launch_tc<64, 7>(ta, tb, ty, tr, p, num_m_tiles, st);
             case 32: return launch_tc<32, 8>(ta, tb, ty, tr, p, num_m_tiles, st);

@@ -133,7 +133,11 @@ __device__ __forceinline__ void decode_tile(const TcParams &p, int tile, int &nt
 __host__ __device__ inline int pair_num_tiles(int num_m_tiles, int n_tiles) { return 2 * ((num_m_tiles + 1) / 2) * n_tiles; }
 
 // NBUF: accumulator buffers of ACC_COLS TMEM columns each; this CTA's it-th tile uses buffer it % NBUF.
-template <int BLOCK_N, bool ONE_GROUP = false, int NACC = 1, bool PAIR = false, int NBUF = 2>
+// RES2: every epilogue warp owns TWO staging tiles (the second set starts NUM_EPI_WARPS * EPI_STAGE_BYTES behind the first) and two
+// residual barriers (res_bar[NUM_EPI_WARPS + ew]): chunks alternate between them, the residual of chunk i+1 is fetched while chunk i
+// is computed (with one tile it could only be requested after chunk i's store had drained the tile: ~2300 cycles of load latency per
+// 128 x 256 tile sat exposed in the residual 1x1 layers), and a store may still be reading one tile while the next chunk fills the other.
+template <int BLOCK_N, bool ONE_GROUP = false, int NACC = 1, bool PAIR = false, int NBUF = 2, bool RES2 = false>
 __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorMap *tmap_y_p, const CUtensorMap *tmap_r_p, uint32_t tmem_base,
                                               uint64_t *tfull_bar, uint64_t *tempty_bar, uint64_t *res_bar, uint8_t *epi_stage,
                                               float *s_shift, int num_tiles, int warp, int lane)
@@ -151,6 +155,7 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
     const int ew = warp - EPI_WARP0;
     const int q = ew & 3, grp = ew >> 2;
     static_assert(NBUF % 2 == 0, "the alternating epilogue groups need an even number of accumulator buffers");
+    static_assert(!RES2 || (BLOCK_N >= 128 && !ONE_GROUP), "double-buffered staging is only wired up for the wide-tile epilogue");
     // narrow tiles (one column group): the two groups of 4 warps ALTERNATE tiles -- group g owns the accumulator buffers = g (mod 2), i.e.
     // every other tile of this CTA -- so two tiles are in the epilogue at once (measured: the N = 64 layers were epilogue-bound)
     constexpr bool ALT = GROUPS == 1 && !ONE_GROUP;
@@ -166,6 +171,11 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
     for (int c = 0; c < 8; ++c) off[c] = srow + ((c ^ (lane & 7)) << 4);
     const uint32_t rbar = smem_u32(res_bar + ew);
     uint32_t rphase = 0;
+    constexpr uint32_t STAGE2_DELTA = NUM_EPI_WARPS * EPI_STAGE_BYTES;      // second staging tile of this warp (RES2)
+    const uint32_t rbar2 = smem_u32(res_bar + NUM_EPI_WARPS + ew);
+    uint32_t rphase2 = 0, cc = 0;                                           // cc: chunks this warp has processed (its parity picks the tile)
+    bool primed = false;                                                    // RES2: the current chunk's residual has been requested
+    (void)rbar2; (void)rphase2; (void)cc; (void)primed;
     float slope = p.slope;
     if (p.slope_ptr) slope = __ldg(p.slope_ptr);
     const int act = p.act;
@@ -360,7 +370,39 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
         }
         for (int ck = 0; ck < COLS; ck += tch) {
             const bool chunk_on = ctile + ck < p.Cout;          // warp-uniform
-            if (tma_out && lane == 0) {
+            const uint32_t sdelta = RES2 ? (cc & 1u) * STAGE2_DELTA : 0u;   // this chunk's staging tile
+            if constexpr (RES2) {
+                if (tma_out && lane == 0) {
+                    if (p.tma_res) {
+                        // all earlier stores have drained: both tiles are reusable; request this chunk's residual if nobody has yet
+                        // (the warp's first chunk), then the NEXT chunk's into the other tile
+                        { HN_PROF_T0(); bulk_wait_read0(); HN_PROF_ADD(ew_bulk); }
+                        if (!primed && chunk_on) {
+                            const uint32_t rb = (cc & 1u) ? rbar2 : rbar;
+                            mbar_expect_tx(rb, EPI_STAGE_BYTES);
+                            tma_load_4d(stage + sdelta, &tmap_r, rb, ctile + ck, bx, by, img);
+                        }
+                        int ntile = tile, nck = ck + tch;
+                        if (nck >= COLS) { nck = 0; ntile = tile + (int)gridDim.x; }
+                        if (ntile < num_tiles) {
+                            int nnt, nmt;
+                            decode_tile<PAIR>(p, ntile, nnt, nmt);
+                            const int ntw = nmt % p.tiles_w, nth = (nmt / p.tiles_w) % p.tiles_h, nimg = nmt / (p.tiles_w * p.tiles_h);
+                            const int nctile = nnt * BLOCK_N + col0 + nck;
+                            if (nctile < p.Cout) {
+                                const uint32_t rb = (cc & 1u) ? rbar : rbar2;           // the other tile's barrier
+                                mbar_expect_tx(rb, EPI_STAGE_BYTES);
+                                tma_load_4d(stage + (STAGE2_DELTA - sdelta), &tmap_r, rb, nctile, ntw * p.TW + (q * 32) % p.TW,
+                                            nth * p.TH + (q * 32) / p.TW, nimg);
+                            }
+                        }
+                    } else {
+                        // no residual: only the store that read THIS tile (two chunks ago) must have drained
+                        HN_PROF_T0(); bulk_wait_read1(); HN_PROF_ADD(ew_bulk);
+                    }
+                }
+                primed = true;
+            } else if (tma_out && lane == 0) {
                 { HN_PROF_T0(); bulk_wait_read0(); HN_PROF_ADD(ew_bulk); }   // previous store has drained the staging tile
                 if (p.tma_res && chunk_on) {
                     mbar_expect_tx(rbar, EPI_STAGE_BYTES);
@@ -375,8 +417,13 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
             }
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + col0 + ck;
             if (p.tma_res && chunk_on) {
-                { HN_PROF_T0(); mbar_wait(rbar, rphase); HN_PROF_ADD(ew_res); }
-                rphase ^= 1;
+                if (RES2 && (cc & 1u)) {
+                    { HN_PROF_T0(); mbar_wait(rbar2, rphase2); HN_PROF_ADD(ew_res); }
+                    rphase2 ^= 1;
+                } else {
+                    { HN_PROF_T0(); mbar_wait(rbar, rphase); HN_PROF_ADD(ew_res); }
+                    rphase ^= 1;
+                }
             }
             const int nsub = (tch < COLS - ck ? tch : COLS - ck) / SUB;
             for (int si = 0; si < nsub; ++si) {
@@ -421,7 +468,7 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
                             if (p.res) {
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    const uint4 rv = lds128(off[si * 4 + j]);
+                                    const uint4 rv = lds128((off[si * 4 + j] + sdelta));
                                     const __nv_bfloat162 *r2 = reinterpret_cast<const __nv_bfloat162 *>(&rv);
 #pragma unroll
                                     for (int i = 0; i < 4; ++i) h[4 * j + i] = __hadd2(h[4 * j + i], r2[i]);
@@ -433,7 +480,7 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
                                 for (int j = 0; j < 16; ++j) h[j] = __hmax2(h[j], z);
                             }
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) sts128(off[si * 4 + j], *reinterpret_cast<const uint4 *>(&h[4 * j]));
+                            for (int j = 0; j < 4; ++j) sts128((off[si * 4 + j] + sdelta), *reinterpret_cast<const uint4 *>(&h[4 * j]));
                         }
                     } else {
                         // ---------------- general path ----------------
@@ -451,7 +498,7 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
                             if (p.tma_res) {          // residual chunk sits in the staging tile (BF16, swizzled)
 #pragma unroll
                                 for (int j = 0; j < SUB / 8; ++j) {
-                                    const uint4 rv = lds128(off[((si * SUB) >> 3) + j]);
+                                    const uint4 rv = lds128((off[((si * SUB) >> 3) + j] + sdelta));
                                     const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&rv);
 #pragma unroll
                                     for (int i = 0; i < 4; ++i) {
@@ -484,7 +531,7 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
                                 for (int j = 0; j < SUB / 4; ++j) {
                                     uint4 o = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
                                                          __float_as_uint(v[4 * j + 3]));
-                                    sts128(off[((si * SUB) >> 2) + j], o);
+                                    sts128((off[((si * SUB) >> 2) + j] + sdelta), o);
                                 }
                                 if constexpr (SUB == 32) {
                                     if (p.stat_sum) {
@@ -497,14 +544,14 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
                                         if (vmask == 0xffffffffu) {
 #pragma unroll 8
                                             for (int r = 0; r < 32; ++r) {
-                                                const float x = lds32(stage + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+                                                const float x = lds32((stage + sdelta) + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
                                                 cs += x;
                                                 cq = fmaf(x, x, cq);
                                             }
                                         } else {
                                             for (int r = 0; r < 32; ++r) {
                                                 if ((vmask >> r) & 1u) {
-                                                    const float x = lds32(stage + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+                                                    const float x = lds32((stage + sdelta) + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
                                                     cs += x;
                                                     cq = fmaf(x, x, cq);
                                                 }
@@ -522,7 +569,7 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
                                     __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&o);
 #pragma unroll
                                     for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
-                                    sts128(off[((si * SUB) >> 3) + j], o);
+                                    sts128((off[((si * SUB) >> 3) + j] + sdelta), o);
                                 }
                             }
                         } else if (valid) {
@@ -568,7 +615,7 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
 #pragma unroll 8
                         for (int r = 0; r < 32; ++r) {
                             if (vmask == 0xffffffffu || ((vmask >> r) & 1u)) {
-                                const uint32_t w2 = lds32u(stage + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+                                const uint32_t w2 = lds32u((stage + sdelta) + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
                                 const float x0 = __uint_as_float(w2 << 16), x1 = __uint_as_float(w2 & 0xffff0000u);
                                 s0 += x0; q0 = fmaf(x0, x0, q0);
                                 s1 += x1; q1 = fmaf(x1, x1, q1);
@@ -585,11 +632,12 @@ __device__ __forceinline__ void conv_epilogue(const TcParams &p, const CUtensorM
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0 && chunk_on) {
-                    tma_store_4d(&tmap_y, stage, ctile + ck, bx, by, img);
+                    tma_store_4d(&tmap_y, (stage + sdelta), ctile + ck, bx, by, img);
                     bulk_commit();
                 }
                 HN_PROF_ADD(ew_st);
             }
+            ++cc;
         }
         {
             HN_PROF_T0();

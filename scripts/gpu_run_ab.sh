@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 VAR=${VAR:-HN_PAIR_MIN_KB}
 for v in ${VALS:-9 8 4}; do
-  export $VAR=$v
+  if [ "$v" = unset ]; then unset $VAR; else export $VAR=$v; fi          # (the library's switches test presence, not value)
   timeout 300 python bench.py --legs none --no-logits-e2e --no-cpu-baseline > gpurun_out/ab_infer_$v.json 2> gpurun_out/ab_infer_$v.err
   if [ -n "$TRAIN" ]; then timeout 300 python bench.py --workload train_seg --height 320 --width 640 --batch 16 --steps 10 --warmup 3 > gpurun_out/ab_train_$v.json 2> gpurun_out/ab_train_$v.err; fi
   python - <<PY

@@ -155,6 +155,9 @@ PAIR_CASES = [
     (256, 256, 3, 4, 4, 1, 24, 16),    # generic kernel, N = 256 (the pair halves the staged weight rows), 3 tiles
     (1024, 256, 1, 0, 1, 1, 9, 43),    # flat 1x1 with a long reduction (16 k-blocks): pairs over a flattened, ragged pixel axis
     (192, 100, 3, 4, 4, 1, 24, 16),    # Cout not a multiple of the tile: the pair's second weight half is partly padding
+    (64, 512, 1, 0, 1, 3, 80, 80),     # single CTAs, N = 256, 300 tiles on 148 CTAs: the residual prefetch crosses tile boundaries
+    (576, 256, 1, 0, 1, 3, 80, 80),    # pairs, N = 256, 75 tile pairs on 74 clusters: one cluster runs two tiles (prefetch across them)
+    (128, 320, 1, 0, 1, 2, 40, 41),    # N = 64 tail-free but Cout = 320 -> 256-wide tiles with a half-empty second Cout tile (chunks switched off)
 ]
 
 
