@@ -203,6 +203,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint32_t sbo = (uint32_t)(hp.PW * 128) >> 4;
             // everything of the A descriptor but the start address: LBO = 1, SBO = patch row pitch, version 1, SWIZZLE_128B
             const uint64_t adesc_hi = ((uint64_t)1 << 16) | ((uint64_t)(sbo & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+            // B: canonical K-major SWIZZLE_128B tile (make_kmajor_sw128_desc) without the start address
+            const uint64_t bdesc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+            // start-address fields (address >> 4; the whole dynamic shared memory lies below 256 KB, so sums never leave the 14-bit field)
+            const uint32_t a_lo0 = (smem_u32(a_ring) & 0x3FFFFu) >> 4, a_slot16 = (uint32_t)hp.a_slot_bytes >> 4;
+            const uint32_t b_lo0 = (smem_u32(b_ring) & 0x3FFFFu) >> 4;
+            uint32_t tap_off[9];
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) tap_off[tap] = (uint32_t)(((tap / 3) * d * hp.PW + (tap % 3) * d) * 128) >> 4;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 {
                     HN_PROF_T0();
@@ -221,33 +229,39 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         HN_PROF_ADD(mw_afull);
                     }
                     tcgen05_fence_after();
-                    const uint32_t a_base = smem_u32(a_ring + aslot * hp.a_slot_bytes);
+                    // Descriptors are assembled from low words prepared outside the loops (slot / stage base >> 4 plus per-tap offsets):
+                    // every instruction between two MMAs costs issue time once a tile instruction retires every ~43 cycles
+                    // (profiles/r2_mma_rate_probe_mn_major_and_issue_loop.txt), and ONE elected region covers all taps of a weight stage.
+                    const uint32_t a_lo = a_lo0 + (uint32_t)aslot * a_slot16;
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int r = tap / 3, s = tap - r * 3;
-                        if ((!hp.b_resident || first) && tap % TPS == 0) {
+                    for (int tg = 0; tg < 9 / TPS; ++tg) {
+                        if (!hp.b_resident || first) {
                             HN_PROF_T0();
                             mbar_wait(smem_u32(b_full + bst), bphase);
                             HN_PROF_ADD(mw_bfull);
                             tcgen05_fence_after();
                         }
-                        // sub-window of the patch: starts (r*d) patch rows and (s*d) pixels in; 8-row groups are one patch row apart
-                        const uint32_t a_addr = a_base + (uint32_t)((r * d) * hp.PW + s * d) * 128;
-                        const uint64_t adesc = adesc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
-                        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(b_ring + bst * B_STAGE_BYTES + (tap % TPS) * B_TAP_BYTES));
+                        const uint32_t b_lo = b_lo0 + (uint32_t)bst * (uint32_t)(B_STAGE_BYTES >> 4);
                         if (elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_bf16_t<PAIR>(d_tmem + (NACC == 2 ? (tap & 1) * SUB_ACC : 0), adesc + 2 * k, bdesc + 2 * k, IDESC,
-                                                  NACC == 2 ? ((kb | (tap >> 1) | k) != 0) : ((kb | tap | k) != 0));
-                            if (!hp.b_resident && tap % TPS == TPS - 1) umma_commit_t<PAIR>(smem_u32(b_empty + bst));
-                            if (tap == 8) {
+                            for (int t = 0; t < TPS; ++t) {
+                                const int tap = tg * TPS + t;
+                                // sub-window of the patch: starts (r*d) patch rows and (s*d) pixels in; 8-row groups are one patch row apart
+                                const uint64_t adesc = adesc_hi | (uint64_t)(a_lo + tap_off[tap]);
+                                const uint64_t bdesc = bdesc_hi | (uint64_t)(b_lo + (uint32_t)t * (uint32_t)(B_TAP_BYTES >> 4));
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_bf16_t<PAIR>(d_tmem + (NACC == 2 ? (tap & 1) * SUB_ACC : 0), adesc + 2 * k, bdesc + 2 * k, IDESC,
+                                                      NACC == 2 ? ((kb | (tap >> 1) | k) != 0) : ((kb | tap | k) != 0));
+                            }
+                            if (!hp.b_resident) umma_commit_t<PAIR>(smem_u32(b_empty + bst));
+                            if (tg == 9 / TPS - 1) {
                                 umma_commit_t<PAIR>(smem_u32(a_empty + aslot));
                                 if (kb == num_kb - 1) umma_commit_t<PAIR>(smem_u32(tfull_bar + acc));
                             }
                         }
                         __syncwarp();
-                        if (tap % TPS == TPS - 1 && ++bst == hp.nb) { bst = 0; bphase ^= 1; }
+                        if (++bst == hp.nb) { bst = 0; bphase ^= 1; }
                     }
                     if (++aslot == hp.na) { aslot = 0; aphase ^= 1; }
                 }

@@ -145,6 +145,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             uint32_t acc_phase = 0;
             long long mw_full = 0, mw_tempty = 0;
             (void)mw_full; (void)mw_tempty;
+            const uint64_t desc_hi = make_kmajor_desc(0, BK * 2);                     // everything but the start address
+            const uint32_t lo0 = (smem_u32(smem) & 0x3FFFFu) >> 4;                    // (all of the dynamic shared memory lies below 256 KB)
 #ifdef HN_PROFILE_ROLES
             const long long mma_t0 = clock64();
 #endif
@@ -160,9 +162,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 for (int kb = 0; kb < num_kb; ++kb) {
                     { HN_PROF_T0(); mbar_wait(smem_u32(full_bar + stage), phase); HN_PROF_ADD(mw_full); }
                     tcgen05_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint64_t adesc = make_kmajor_desc(sa, BK * 2);
-                    const uint64_t bdesc = make_kmajor_desc(sa + A_STAGE_BYTES, BK * 2);
+                    // start-address fields from a base prepared outside the loops: nothing but adds between two groups of MMAs
+                    const uint32_t a_lo = lo0 + (uint32_t)stage * (uint32_t)(STAGE_BYTES >> 4);
+                    const uint64_t adesc = desc_hi | (uint64_t)a_lo;
+                    const uint64_t bdesc = desc_hi | (uint64_t)(a_lo + (uint32_t)(A_STAGE_BYTES >> 4));
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
