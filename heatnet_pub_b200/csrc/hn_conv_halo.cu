@@ -26,8 +26,8 @@ namespace hn {
 
 constexpr int HALO_THREADS = 384;
 constexpr int HALO_TH = 16, HALO_TW = 8;
-constexpr int HALO_NA_MAX = 4;    // A patch slots (upper bound; HaloParams::na are used)
-constexpr int HALO_NB_MAX = 12;   // B ring stages (upper bound)
+constexpr int HALO_NA_MAX = 6;    // A patch slots (upper bound; HaloParams::na are used)
+constexpr int HALO_NB_MAX = 16;   // B ring stages (upper bound)
 
 struct HaloParams {
     TcParams t;
@@ -479,7 +479,9 @@ int conv2d_fwd_halo(const hn_tensor *x, const void *w, const hn_conv *cv, const 
     const int tps = pair ? 3 : 1;                   // filter taps per B ring stage (the kernel's TPS)
     const int stage_bytes = tps * b_rows * 128;
     const int stages_per_kb = 9 / tps;
-    hp.na = pair ? HALO_NA_MAX : 2;
+    static const int na_env = getenv("HN_HALO_NA") ? atoi(getenv("HN_HALO_NA")) : 0;          // tuning knob (2..4)
+    hp.na = pair ? 4 : 2;
+    if (na_env >= 2 && na_env <= HALO_NA_MAX) hp.na = na_env;
     int64_t fixed = 0;
     int nb = 0;
     for (;; --hp.na) {          // pairs: as many patch slots as leave room for a useful weight ring
