@@ -470,7 +470,9 @@ def run_train(args):
                 "loss": r["loss"], "gpu_launches": r["gpu_launches"], "clocks": r["clocks"],
                 "roofline": {"bound": "tensor", "achieved": r["tflops_per_gpu"], "peak": load_peaks()[0].get("bf16_tflops_sustained"),
                              "unit": "TFLOP/s", "frac": r["frac_of_sustained_peak"], "frac_of_burst_peak": r["frac_of_burst_peak"],
-                             "note": "whole step (all kernels, not only convs) against algorithmic conv FLOPs of SURVEY.md section 8d",
+                             "note": "whole step (all kernels, not only convs) against algorithmic conv FLOPs of SURVEY.md section 8d -- the graph as the "
+                                     "reference writes it; the BF16 step runs the PSP bottleneck in projected form (2048 instead of 10240 input "
+                                     "channels in forward, dgrad and wgrad), so executed FLOPs are ~16 % lower than algorithmic",
                              "peak_source": r["peak_source"]}}
         emit(line)
     ctx.close()
