@@ -36,7 +36,22 @@ def back(act):
 
 
 # ------------------------------------------------------------------------------------------------ layout
-@pytest.mark.parametrize("shape", [(2, 3, 17, 23), (1, 1, 8, 8), (2, 13, 9, 31), (1, 64, 5, 7), (2, 100, 33, 4)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("c,coff,cbuf", [(13, 0, 16), (13, 2, 20), (16, 4, 24), (9, 3, 13), (12, 4, 16)])
+def test_nchw_into_narrow_channel_slice_keeps_the_neighbours(E, dtype, c, coff, cbuf):
+    """9..16-channel NCHW tensors (the logits and their gradient) enter the NHWC engine through a one-thread-per-pixel kernel whose
+    vector stores must stay inside the C valid channels: the other channels of the buffer keep their contents."""
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, c, 11, 7, generator=g)
+    buf = E.new_act(2, 11, 7, cbuf, dtype, "cuda")
+    buf.buf.fill_(7.0)
+    E.from_nchw(x.cuda(), dtype, buf.slice(coff, c))
+    full = buf.nchw().float().cpu()
+    assert torch.equal(full[:, coff:coff + c], x.to(dtype).float())
+    assert torch.all(full[:, :coff] == 7.0) and torch.all(full[:, coff + c:] == 7.0)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 17, 23), (1, 1, 8, 8), (2, 13, 9, 31), (1, 64, 5, 7), (2, 100, 33, 4), (2, 16, 7, 9), (1, 9, 4, 5)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_layout_roundtrip(E, shape, dtype):
     g = torch.Generator().manual_seed(0)
